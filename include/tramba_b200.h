@@ -1,0 +1,155 @@
+/* tramba_b200.h -- C ABI of the B200-native (sm_100a) 2D selective-scan hot path of Tramba.
+ *
+ * This is the drop-in boundary: plain pointers, sizes and enums; no torch types.  Device
+ * pointers are raw CUDA device addresses owned by the caller (torch's caching allocator in
+ * the Python host); nothing is allocated or freed here; inputs are never mutated.  `stream`
+ * is a cudaStream_t passed as void* (NULL = legacy default stream).  Every entry point
+ * returns 0 on success, a negative TRAMBA_E_* code for a rejected argument, or a positive
+ * cudaError_t value for a CUDA failure; tramba_error_string() renders all three.
+ * There is no CPU fallback: the compute entry points need an sm_100 device.
+ *
+ * Each entry point cites the reference interface it replaces (paths relative to the
+ * reference repository root).
+ */
+#ifndef TRAMBA_B200_H
+#define TRAMBA_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TRAMBA_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define TRAMBA_API __attribute__((visibility("default")))
+#else
+#define TRAMBA_API
+#endif
+
+typedef enum { TRAMBA_F32 = 0, TRAMBA_BF16 = 1, TRAMBA_F16 = 2 } tramba_dtype_t;
+
+/* Scan-order families.  LINE is the Helix-SS2D order: 4 standard directions followed by the
+ * 4 Bresenham radial-line lists (K = 8); every other family has K = 4.  CUSTOM takes a
+ * caller-supplied table with arbitrary (possibly repeating) indices. */
+typedef enum {
+    TRAMBA_ORDER_STD = 0,      /* Models/SS2D/csms6s.py:13-55   CrossScan / CrossMerge            */
+    TRAMBA_ORDER_DILATION = 1, /* Models/SS2D/csms6s.py:64-103  + Models/SS2D/Dilation.py:3-96    */
+    TRAMBA_ORDER_WINDOW = 2,   /* Models/SS2D/csms6s.py:113-152 + Models/SS2D/Window.py:3-86      */
+    TRAMBA_ORDER_LINE = 3,     /* Models/SS2D/csms6s.py:161-216 + Models/SS2D/SpiralLine.py:3-133 */
+    TRAMBA_ORDER_CUSTOM = 4
+} tramba_order_t;
+
+enum {
+    TRAMBA_OK = 0,
+    TRAMBA_E_NULL = -1,      /* a required pointer is NULL                         */
+    TRAMBA_E_SHAPE = -2,     /* a size is non-positive or inconsistent             */
+    TRAMBA_E_DTYPE = -3,     /* unsupported dtype combination                      */
+    TRAMBA_E_ORDER = -4,     /* unknown order / parameter not valid for this H     */
+    TRAMBA_E_ALIGN = -5,     /* a pointer is not aligned to its element size       */
+    TRAMBA_E_NODEVICE = -6,  /* no CUDA device / not an sm_100 device              */
+    TRAMBA_E_LIMIT = -7      /* size exceeds what the kernels support (see docs)   */
+};
+
+TRAMBA_API int tramba_abi_version(void);
+TRAMBA_API const char* tramba_error_string(int code);
+/* Number of kernels this library has launched in this process (bench.py's gpu_launches). */
+TRAMBA_API uint64_t tramba_launch_count(void);
+
+/* ----------------------------------------------------------------------------------------
+ * Scan-order tables (host code, no GPU needed).
+ * Replaces generate_dilation_indices (Models/SS2D/Dilation.py:3-45), generate_window_indices
+ * (Models/SS2D/Window.py:3-35), generate_indices (Models/SS2D/SpiralLine.py:27-82) and the
+ * module-level dicts at Models/SS2D/csms6s.py:58-61,107-110,157-158.  The table is the flat
+ * pixel index idx[k*L + t] (row*W + col), K = tramba_order_num_directions(order), L = H*W;
+ * square maps only (H == W), like the reference.  `param` = dilation rate / window size
+ * (ignored for STD and LINE).  Bit-exact with the reference generators.
+ * -------------------------------------------------------------------------------------- */
+TRAMBA_API int tramba_order_num_directions(int order);
+TRAMBA_API int tramba_order_table(int order, int H, int W, int param, int32_t* idx_out /* K*L, host */);
+
+/* Order plan = what the device kernels consume: one int32 blob of
+ * tramba_order_plan_elems(K, L) = K*(3L+1) entries laid out as
+ *   [0, K*L)              forward table idx[k][t]                    (cross-scan gathers with it)
+ *   [K*L, 2*K*L)          inverse entries: tokens t sorted by (pixel, t) per direction
+ *   [2*K*L, +K*(L+1))     CSR offsets per direction: tokens of pixel p are
+ *                         entries[k][off[k][p] .. off[k][p+1])        (cross-merge gathers with it)
+ * The inverse replaces the reference's scatter_add_ (Dilation.py:88-95, Window.py:78-85,
+ * SpiralLine.py:125-132) by a deterministic gather that adds duplicate hits in token order,
+ * i.e. exactly the order of a sequential scatter_add_.  _from_table builds a plan for a
+ * caller-supplied forward table (TRAMBA_ORDER_CUSTOM). */
+TRAMBA_API size_t tramba_order_plan_elems(int K, int L);
+TRAMBA_API int tramba_order_plan(int order, int H, int W, int param, int32_t* plan_out /* host */);
+TRAMBA_API int tramba_order_plan_from_table(int K, int L, const int32_t* table, int32_t* plan_out /* host */);
+
+/* ----------------------------------------------------------------------------------------
+ * Cross-scan: xs[b,k,c,t] = x[b,c].flat[idx[k,t]].
+ * Replaces CrossScan*.forward and CrossMerge*.backward (Models/SS2D/csms6s.py:15-22,45-55,
+ * 66-72,94-103,115-121,143-152,163-172,204-216).  x: (B,C,H,W) contiguous; xs: (B,K,C,L).
+ * `plan_dev`: device copy of the order plan.  dtype: element type of x and xs.
+ * -------------------------------------------------------------------------------------- */
+TRAMBA_API int tramba_cross_scan(const void* x, void* xs, const int32_t* plan_dev, int order, int K,
+                      int B, int C, int H, int W, int dtype, void* stream);
+
+/* Cross-merge: y[b,d,p] = sum_k sum_{t: idx[k,t]==p} ys[b,k,d,t]  (the exact transpose).
+ * Replaces CrossMerge*.forward and CrossScan*.backward (Models/SS2D/csms6s.py:25-31,36-42,
+ * 75-80,85-91,124-129,134-140,175-185,190-201) incl. get_re_*_scan's scatter_add_.
+ * ys: (B,K,D,L) contiguous; y: (B,D,L), same dtype.  Accumulation is fp32, deterministic, and
+ * follows the reference's association order: STD (ys0+flip ys2) + T(ys1+flip ys3);
+ * DILATION/WINDOW/CUSTOM sequential over k then t from zero; LINE = (sequential k=4..7) +
+ * (STD fold of k=0..3) -- bit-exact with the reference evaluated on CPU.
+ * -------------------------------------------------------------------------------------- */
+TRAMBA_API int tramba_cross_merge(const void* ys, void* y, const int32_t* plan_dev, int order, int K,
+                       int B, int D, int H, int W, int dtype, void* stream);
+
+/* ----------------------------------------------------------------------------------------
+ * Selective scan (S6 recurrence).
+ * Replaces selective_scan_cuda_oflex.fwd / .bwd as called at Models/SS2D/csms6s.py:910 and
+ * :920-922 (operator SelectiveScanOflex, csms6s.py:904-923; arguments prepared at
+ * Models/vmamba.py:244-257).
+ *   u, delta            (batch, dim, L)        in_dtype, contiguous, L innermost
+ *   A                   (dim, N)               fp32
+ *   Bm, Cm              (batch, groups, N, L)  in_dtype
+ *   D, delta_bias       (dim)                  fp32, either may be NULL (treated as 0)
+ *   out                 (batch, dim, L)        out_dtype (F32 when oflex=True)
+ *   ckpt                tramba_sscan_ckpt_elems() floats, or NULL for inference; opaque chunk
+ *                       boundary states handed back to _bwd (the reference's `x` tensor)
+ * dim % groups == 0; row d uses group d / (dim/groups); 1 <= N <= 64.
+ * -------------------------------------------------------------------------------------- */
+TRAMBA_API size_t tramba_sscan_ckpt_elems(int batch, int dim, int L, int N, int in_dtype);
+
+TRAMBA_API int tramba_sscan_fwd(const void* u, const void* delta, const float* A, const void* Bm,
+                     const void* Cm, const float* D, const float* delta_bias, void* out,
+                     float* ckpt, int batch, int dim, int L, int N, int groups, int in_dtype,
+                     int out_dtype, int delta_softplus, void* stream);
+
+/* Backward.  dout: (batch, dim, L) dout_dtype.  Outputs: du, ddelta (in_dtype); dA (dim,N),
+ * dD (dim), ddelta_bias (dim) fp32 summed over batch and L; dB, dC (batch,groups,N,L) fp32
+ * summed over the channels of a group.  dD / ddelta_bias may be NULL when D / delta_bias are.
+ * All outputs are overwritten (zero-initialised internally where accumulated). */
+TRAMBA_API int tramba_sscan_bwd(const void* u, const void* delta, const float* A, const void* Bm,
+                     const void* Cm, const float* D, const float* delta_bias, const void* dout,
+                     const float* ckpt, void* du, void* ddelta, float* dA, float* dB, float* dC,
+                     float* dD, float* ddelta_bias, int batch, int dim, int L, int N,
+                     int groups, int in_dtype, int dout_dtype, int delta_softplus, void* stream);
+
+/* ----------------------------------------------------------------------------------------
+ * DCT2D high/low split.  Replaces DCT2D.forward (Models/DCT_2D.py:12-29) and the two basis
+ * layers (DCT_2D.py:32-77): Y = Wy . X . Wx^T per plane, high = Y[H/2:, W/2:],
+ * low = Y[:H/2, :W/2].  x: (planes, H, W) fp32; wy: (H,H), wx: (W,W) fp32 bases (the
+ * module's registered buffers dct_y.weight / dct_x.weight); high, low: (planes, H/2, W/2).
+ * H and W even.  _bwd is the adjoint: gx = Wy^T . dY . Wx with dY zero outside the quadrants.
+ * -------------------------------------------------------------------------------------- */
+TRAMBA_API void tramba_dct_basis(int n, float* w_out /* n*n, host */); /* DCT_2D.py:37-45 */
+
+TRAMBA_API int tramba_dct2d_fwd(const float* x, const float* wy, const float* wx, float* high, float* low,
+                     int planes, int H, int W, void* stream);
+TRAMBA_API int tramba_dct2d_bwd(const float* ghigh, const float* glow, const float* wy, const float* wx,
+                     float* gx, int planes, int H, int W, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TRAMBA_B200_H */

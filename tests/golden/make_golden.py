@@ -48,7 +48,7 @@ def orders():
         out[f"window_{H}_{ws[H]}"] = flat_rowmajor(generate_window_indices(H, H, ws[H]), H)
     out["dilation_4_3"] = flat_rowmajor(generate_dilation_indices(4, 4, 3), 4)  # Dilation.py:103
     out["window_8_4"] = flat_rowmajor(generate_window_indices(8, 8, 4), 8)      # Window.py:93
-    for H in (6, 12, 14, 24, 28, 48, 56, 96, 192):
+    for H in (6, 7, 12, 14, 24, 28, 48, 56, 96, 192):
         out[f"line_{H}"] = flat_line(generate_indices(H, H), H)
     # the tables the reference actually holds at import (csms6s.py:60,109,158)
     for H in (12, 24, 48, 96):

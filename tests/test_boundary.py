@@ -1,0 +1,155 @@
+"""CPU-side checks of the drop-in boundary: the C-ABI library loads, exports exactly what
+include/tramba_b200.h declares, its host-side scan-order generators are bit-exact with the
+reference's golden tables, and the product never routes through the oracle or a CPU path."""
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+
+import tramba_b200
+from tramba_b200 import _lib, ops
+
+WS = {12: 4, 24: 8, 48: 12, 96: 16, 192: 32}
+
+
+def _header_symbols():
+    src = open(os.path.join(ROOT, "include", "tramba_b200.h")).read()
+    return sorted(set(re.findall(r"TRAMBA_API[^;(]*?\b(tramba_\w+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    syms = _header_symbols()
+    assert len(syms) >= 16
+    out = subprocess.check_output(["nm", "-D", "--defined-only", _lib.LIB_PATH], text=True)
+    exported = sorted(l.split()[-1] for l in out.splitlines() if " T " in l)
+    assert exported == syms                      # nothing missing, nothing extra
+    assert sorted(_lib.SIGNATURES) == syms       # the ctypes binding covers the whole header
+    assert _lib.lib.tramba_abi_version() == 1
+
+
+def test_library_is_sm100a_native_code():
+    out = subprocess.run(["cuobjdump", "-lelf", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    archs = set(re.findall(r"\.(sm_\w+)\.cubin", out))
+    assert archs == {"sm_100a"}, archs
+
+
+def test_tma_bulk_copies_present_in_sass():
+    out = subprocess.run(["cuobjdump", "-sass", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    assert "UBLKCP" in out            # cp.async.bulk (TMA 1-D) in SASS
+    assert "SYNCS" in out             # mbarrier arrive/try_wait
+
+
+@pytest.mark.parametrize("H", [12, 24, 48, 96, 192])
+def test_cxx_tables_bit_exact_with_reference(golden_orders, H):
+    assert np.array_equal(ops.order_table_host(_lib.ORDER_DILATION, H, 4), golden_orders[f"dilation_{H}_4"])
+    assert np.array_equal(ops.order_table_host(_lib.ORDER_WINDOW, H, WS[H]), golden_orders[f"window_{H}_{WS[H]}"])
+    line = ops.order_table_host(_lib.ORDER_LINE, H)
+    assert np.array_equal(line[4:], golden_orders[f"line_{H}"])
+    assert np.array_equal(line[:4], ops.order_table_host(_lib.ORDER_STD, H))
+
+
+@pytest.mark.parametrize("H", [6, 7, 14, 28, 56])
+def test_cxx_line_tables_other_sizes(golden_orders, H):
+    assert np.array_equal(ops.order_table_host(_lib.ORDER_LINE, H)[4:], golden_orders[f"line_{H}"])
+
+
+def test_cxx_tables_reference_main_blocks(golden_orders):
+    assert np.array_equal(ops.order_table_host(_lib.ORDER_DILATION, 4, 3), golden_orders["dilation_4_3"])
+    assert np.array_equal(ops.order_table_host(_lib.ORDER_WINDOW, 8, 4), golden_orders["window_8_4"])
+
+
+def test_std_table_matches_oracle():
+    from oracle import scan_orders as so
+    for H in (3, 12, 17):
+        assert np.array_equal(ops.order_table_host(_lib.ORDER_STD, H), so.std_indices(H, H))
+
+
+@pytest.mark.parametrize("order,H,param", [(_lib.ORDER_LINE, 12, 0), (_lib.ORDER_LINE, 96, 0),
+                                           (_lib.ORDER_WINDOW, 24, 8), (_lib.ORDER_DILATION, 48, 4)])
+def test_plan_inverse_is_the_sorted_csr(order, H, param):
+    K, plan = ops.order_plan_host(order, H, param)
+    L = H * H
+    fwd = plan[:K * L].reshape(K, L)
+    ent = plan[K * L:2 * K * L].reshape(K, L)
+    off = plan[2 * K * L:].reshape(K, L + 1)
+    for k in range(K):
+        assert off[k, 0] == 0 and off[k, L] == L
+        order_ = np.argsort(fwd[k], kind="stable")       # tokens sorted by (pixel, t)
+        assert np.array_equal(ent[k], order_)
+        assert np.array_equal(np.diff(off[k]), np.bincount(fwd[k], minlength=L))
+
+
+def test_order_errors():
+    buf = np.zeros(16, np.int32)
+    assert _lib.lib.tramba_order_table(_lib.ORDER_WINDOW, 12, 12, 5, buf.ctypes.data) == -4   # 12 % 5
+    assert _lib.lib.tramba_order_table(_lib.ORDER_STD, 12, 13, 0, buf.ctypes.data) == -2      # not square
+    assert _lib.lib.tramba_order_table(99, 12, 12, 0, buf.ctypes.data) == -4
+    assert _lib.lib.tramba_order_table(_lib.ORDER_STD, 2, 2, 0, None) == -1
+    with pytest.raises(KeyError):
+        ops.window_size_for["13"]                        # reference: window_index[str(H)] KeyError
+
+
+def test_dct_basis_bit_exact(golden_dct):
+    for n in (12, 24, 48, 96):
+        w = np.empty((n, n), np.float32)
+        _lib.lib.tramba_dct_basis(n, w.ctypes.data)
+        assert np.array_equal(w, golden_dct[f"dct_{n}_wx"])
+
+
+def test_state_dict_surface():
+    m = tramba_b200.SS2D(d_model=32, d_state=1, channel_first=True, k_group=8,
+                         scan=tramba_b200.CrossScan_Line, merge=tramba_b200.CrossMerge_Line)
+    sd = m.state_dict()
+    assert sd["x_proj_weight"].shape == (8, 2 + 2, 64)
+    assert sd["dt_projs_weight"].shape == (8, 64, 2) and sd["dt_projs_bias"].shape == (8, 64)
+    assert sd["A_logs"].shape == (8 * 64, 1) and sd["Ds"].shape == (8 * 64,)
+    assert set(sd) == {"x_proj_weight", "dt_projs_weight", "dt_projs_bias", "A_logs", "Ds", "out_norm.weight",
+                       "out_norm.bias", "in_proj.weight", "conv2d.weight", "out_proj.weight"}
+    d = tramba_b200.DCT2D(24, 24)
+    assert set(d.state_dict()) == {"dct_x.weight", "dct_y.weight"}
+
+
+def test_no_cpu_path_and_loud_errors():
+    import torch
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        tramba_b200.cross_scan(torch.zeros(1, 1, 12, 12), _lib.ORDER_STD)
+    with pytest.raises(RuntimeError):
+        tramba_b200.selective_scan_cuda_oflex.fwd(torch.zeros(1, 4, 12), torch.zeros(1, 4, 12), torch.zeros(4, 1),
+                                                  torch.zeros(1, 1, 1, 12), torch.zeros(1, 1, 1, 12), None, None,
+                                                  True, 1, True)
+    if not torch.cuda.is_available():
+        # compute entry points refuse to run without an sm_100 device (host pointers, no launch)
+        a = np.zeros(64, np.float32)
+        rc = _lib.lib.tramba_dct2d_fwd(a.ctypes.data, a.ctypes.data, a.ctypes.data, a.ctypes.data,
+                                       a.ctypes.data, 1, 4, 4, None)
+        assert rc == -6 and b"sm_100" in _lib.lib.tramba_error_string(rc)
+
+
+def test_product_never_imports_oracle_or_reference():
+    pkg = os.path.join(ROOT, "tramba_b200")
+    for dp, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
+                src = open(os.path.join(dp, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle", src, re.M), f
+                assert "/root/reference" not in src, f
+
+
+def test_extension_module_alias():
+    import sys
+    mod = tramba_b200.install_extension()
+    import selective_scan_cuda_oflex as ext
+    assert ext is mod and callable(ext.fwd) and callable(ext.bwd)
+    del sys.modules["selective_scan_cuda_oflex"]
+
+
+def test_sscan_ckpt_elems_plan():
+    f = _lib.lib.tramba_sscan_ckpt_elems
+    assert f(4, 1024, 9216, 1, _lib.F32) == 4 * 1024 * 24          # TSEG 12: 24 chunks of 384 per row
+    assert f(4, 4096, 576, 1, _lib.F32) == 4 * 4096 * 2            # TSEG 9: 2 chunks of 288 per row
+    assert f(2, 8192, 144, 1, _lib.F32) == 2 * 8192 // 2           # two 144-token rows per 288 chunk
+    assert f(1, 8, 50, 3, _lib.F32) > 0                            # generic path

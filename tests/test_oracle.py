@@ -22,7 +22,7 @@ def test_reference_main_block_cases(golden_orders):
     assert np.array_equal(so.window_indices(8, 8, 4), golden_orders["window_8_4"])
 
 
-@pytest.mark.parametrize("H", [6, 12, 14, 24, 28, 48, 56, 96, 192])
+@pytest.mark.parametrize("H", [6, 7, 12, 14, 24, 28, 48, 56, 96, 192])
 def test_line_tables_bit_exact(golden_orders, H):
     got = np.stack(so.line_indices(H, H))
     assert np.array_equal(got, golden_orders[f"line_{H}"])

@@ -1,0 +1,262 @@
+// extern "C" entry points of libtramba_b200.so (see include/tramba_b200.h).
+// Argument validation, plan selection and kernel launch; no torch, no allocation.
+#include <atomic>
+#include <cstdio>
+#include <cstring>
+#include <vector>
+
+#include "common.cuh"
+#include "sscan.cuh"
+
+namespace tramba {
+
+static std::atomic<uint64_t> g_launches{0};
+void note_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+
+cudaError_t launch_cross_scan(const void* x, void* xs, const int32_t* plan, int K, int B, int C, int L,
+                              int dtype, cudaStream_t st);
+cudaError_t launch_cross_merge(const void* ys, void* y, const int32_t* plan, int order, int K, int B, int D,
+                               int L, int dtype, cudaStream_t st);
+cudaError_t launch_dct2d_fwd(const float* x, const float* wy, const float* wx, float* high, float* low,
+                             int planes, int H, int W, cudaStream_t st);
+cudaError_t launch_dct2d_bwd(const float* ghigh, const float* glow, const float* wy, const float* wx, float* gx,
+                             int planes, int H, int W, cudaStream_t st);
+
+static int elem_size(int dtype) {
+    switch (dtype) {
+        case TRAMBA_F32: return 4;
+        case TRAMBA_BF16:
+        case TRAMBA_F16: return 2;
+        default: return 0;
+    }
+}
+static bool aligned(const void* p, int a) { return (reinterpret_cast<uintptr_t>(p) % a) == 0; }
+
+// One-time device check: the kernels are compiled for sm_100a only.
+static int check_device() {
+    static thread_local int cached_dev = -1;
+    static thread_local int cached_rc = 0;
+    int dev = -1;
+    if (cudaGetDevice(&dev) != cudaSuccess) {
+        cudaGetLastError();
+        return TRAMBA_E_NODEVICE;
+    }
+    if (dev == cached_dev) return cached_rc;
+    int major = 0;
+    if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess) {
+        cudaGetLastError();
+        return TRAMBA_E_NODEVICE;
+    }
+    cached_dev = dev;
+    cached_rc = (major == 10) ? TRAMBA_OK : TRAMBA_E_NODEVICE;
+    return cached_rc;
+}
+
+static int cuda_rc(cudaError_t e) { return e == cudaSuccess ? TRAMBA_OK : static_cast<int>(e); }
+
+}  // namespace tramba
+
+using namespace tramba;
+
+extern "C" int tramba_abi_version(void) { return TRAMBA_ABI_VERSION; }
+
+extern "C" uint64_t tramba_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+extern "C" const char* tramba_error_string(int code) {
+    switch (code) {
+        case TRAMBA_OK: return "ok";
+        case TRAMBA_E_NULL: return "tramba: a required pointer is NULL";
+        case TRAMBA_E_SHAPE: return "tramba: a size is non-positive or inconsistent";
+        case TRAMBA_E_DTYPE: return "tramba: unsupported dtype combination";
+        case TRAMBA_E_ORDER: return "tramba: unknown scan order or invalid order parameter";
+        case TRAMBA_E_ALIGN: return "tramba: pointer not sufficiently aligned (16 bytes required)";
+        case TRAMBA_E_NODEVICE: return "tramba: no CUDA device with compute capability 10.x (sm_100a) is current";
+        case TRAMBA_E_LIMIT: return "tramba: size exceeds what the kernels support";
+        default: break;
+    }
+    if (code > 0) return cudaGetErrorString(static_cast<cudaError_t>(code));
+    return "tramba: unknown error";
+}
+
+// ------------------------------------------------------------------------------ order plans
+extern "C" size_t tramba_order_plan_elems(int K, int L) {
+    if (K <= 0 || L <= 0) return 0;
+    return static_cast<size_t>(K) * (3 * static_cast<size_t>(L) + 1);
+}
+
+extern "C" int tramba_order_plan_from_table(int K, int L, const int32_t* table, int32_t* plan) {
+    if (!table || !plan) return TRAMBA_E_NULL;
+    if (K <= 0 || L <= 0) return TRAMBA_E_SHAPE;
+    int32_t* fwd = plan;
+    int32_t* ent = plan + static_cast<size_t>(K) * L;
+    int32_t* off = plan + 2 * static_cast<size_t>(K) * L;
+    if (fwd != table) std::memmove(fwd, table, sizeof(int32_t) * static_cast<size_t>(K) * L);
+    std::vector<int32_t> cur(L + 1);
+    for (int k = 0; k < K; ++k) {
+        const int32_t* tk = fwd + static_cast<size_t>(k) * L;
+        int32_t* ok = off + static_cast<size_t>(k) * (L + 1);
+        int32_t* ek = ent + static_cast<size_t>(k) * L;
+        std::fill(ok, ok + L + 1, 0);
+        for (int t = 0; t < L; ++t) {
+            if (tk[t] < 0 || tk[t] >= L) return TRAMBA_E_ORDER;
+            ++ok[tk[t] + 1];
+        }
+        for (int p = 0; p < L; ++p) ok[p + 1] += ok[p];
+        std::copy(ok, ok + L + 1, cur.begin());
+        for (int t = 0; t < L; ++t) ek[cur[tk[t]]++] = t;  // stable: ascending t per pixel
+    }
+    return TRAMBA_OK;
+}
+
+extern "C" int tramba_order_plan(int order, int H, int W, int param, int32_t* plan) {
+    const int K = tramba_order_num_directions(order);
+    if (K < 0) return K;
+    int rc = tramba_order_table(order, H, W, param, plan);
+    if (rc != TRAMBA_OK) return rc;
+    return tramba_order_plan_from_table(K, H * W, plan, plan);
+}
+
+// ------------------------------------------------------------------------------ scan / merge
+static int check_scan_args(const void* a, const void* b, const int32_t* plan, int order, int K, int B, int C,
+                           int H, int W, int dtype) {
+    if (!a || !b || !plan) return TRAMBA_E_NULL;
+    if (B <= 0 || C <= 0 || H <= 0 || W <= 0 || K <= 0) return TRAMBA_E_SHAPE;
+    if (order < TRAMBA_ORDER_STD || order > TRAMBA_ORDER_CUSTOM) return TRAMBA_E_ORDER;
+    if (order != TRAMBA_ORDER_CUSTOM && K != tramba_order_num_directions(order)) return TRAMBA_E_ORDER;
+    if (dtype != TRAMBA_F32 && dtype != TRAMBA_BF16) return TRAMBA_E_DTYPE;
+    if (!aligned(a, elem_size(dtype)) || !aligned(b, elem_size(dtype)) || !aligned(plan, 4)) return TRAMBA_E_ALIGN;
+    if (static_cast<long long>(H) * W > (1ll << 24)) return TRAMBA_E_LIMIT;
+    if (static_cast<long long>(B) * C >= (1ll << 31)) return TRAMBA_E_LIMIT;
+    return check_device();
+}
+
+extern "C" int tramba_cross_scan(const void* x, void* xs, const int32_t* plan_dev, int order, int K, int B,
+                                 int C, int H, int W, int dtype, void* stream) {
+    int rc = check_scan_args(x, xs, plan_dev, order, K, B, C, H, W, dtype);
+    if (rc != TRAMBA_OK) return rc;
+    cudaError_t e = launch_cross_scan(x, xs, plan_dev, K, B, C, H * W, dtype, static_cast<cudaStream_t>(stream));
+    if (e == cudaErrorInvalidConfiguration) return TRAMBA_E_LIMIT;
+    return cuda_rc(e);
+}
+
+extern "C" int tramba_cross_merge(const void* ys, void* y, const int32_t* plan_dev, int order, int K, int B,
+                                  int D, int H, int W, int dtype, void* stream) {
+    int rc = check_scan_args(ys, y, plan_dev, order, K, B, D, H, W, dtype);
+    if (rc != TRAMBA_OK) return rc;
+    return cuda_rc(
+        launch_cross_merge(ys, y, plan_dev, order, K, B, D, H * W, dtype, static_cast<cudaStream_t>(stream)));
+}
+
+// ------------------------------------------------------------------------------ selective scan
+static int sscan_common(int batch, int dim, int L, int N, int groups, int in_dtype, int io_dtype) {
+    if (batch <= 0 || dim <= 0 || L <= 0 || N <= 0 || groups <= 0) return TRAMBA_E_SHAPE;
+    if (dim % groups != 0) return TRAMBA_E_SHAPE;
+    if (N > kMaxState) return TRAMBA_E_LIMIT;
+    if (static_cast<long long>(batch) * dim >= (1ll << 31)) return TRAMBA_E_LIMIT;
+    if (in_dtype != TRAMBA_F32 && in_dtype != TRAMBA_BF16) return TRAMBA_E_DTYPE;
+    if (io_dtype != TRAMBA_F32 && io_dtype != in_dtype) return TRAMBA_E_DTYPE;
+    return TRAMBA_OK;
+}
+
+static void fill_args(SScanArgs& a, const SScanPlan& p, int batch, int dim, int L, int N, int groups,
+                      int softplus) {
+    a.batch = batch, a.dim = dim, a.L = L, a.N = N, a.groups = groups, a.dpg = dim / groups;
+    a.rows = batch * dim;
+    a.R = p.R, a.cpu = p.cpu, a.units = p.units;
+    a.softplus = softplus ? 1 : 0;
+    a.uniform = p.uniform ? 1 : 0;
+    a.rw = 1;
+    a.divL.init(static_cast<uint32_t>(L));
+    a.divDim.init(static_cast<uint32_t>(dim));
+    a.divDpg.init(static_cast<uint32_t>(dim / groups));
+}
+
+extern "C" size_t tramba_sscan_ckpt_elems(int batch, int dim, int L, int N, int in_dtype) {
+    if (batch <= 0 || dim <= 0 || L <= 0 || N <= 0 || elem_size(in_dtype) == 0) return 0;
+    const SScanPlan p = make_sscan_plan(static_cast<long long>(batch) * dim, L, elem_size(in_dtype));
+    return static_cast<size_t>(p.units) * p.cpu * N;
+}
+
+extern "C" int tramba_sscan_fwd(const void* u, const void* delta, const float* A, const void* Bm,
+                                const void* Cm, const float* D, const float* delta_bias, void* out,
+                                float* ckpt, int batch, int dim, int L, int N, int groups, int in_dtype,
+                                int out_dtype, int delta_softplus, void* stream) {
+    if (!u || !delta || !A || !Bm || !Cm || !out) return TRAMBA_E_NULL;
+    int rc = sscan_common(batch, dim, L, N, groups, in_dtype, out_dtype);
+    if (rc != TRAMBA_OK) return rc;
+    const SScanPlan p = make_sscan_plan(static_cast<long long>(batch) * dim, L, elem_size(in_dtype));
+    const int need = p.tma ? 16 : elem_size(in_dtype);
+    if (!aligned(u, need) || !aligned(delta, need) || !aligned(Bm, need) || !aligned(Cm, need) ||
+        !aligned(out, p.tma ? 16 : elem_size(out_dtype)) || !aligned(A, 4) || !aligned(D, 4) ||
+        !aligned(delta_bias, 4) || !aligned(ckpt, 4))
+        return TRAMBA_E_ALIGN;
+    rc = check_device();
+    if (rc != TRAMBA_OK) return rc;
+    SScanArgs a;
+    std::memset(&a, 0, sizeof(a));
+    a.u = u, a.delta = delta, a.A = A, a.Bm = Bm, a.Cm = Cm, a.D = D, a.bias = delta_bias;
+    a.out = out, a.ckpt = ckpt;
+    fill_args(a, p, batch, dim, L, N, groups, delta_softplus);
+    return cuda_rc(launch_sscan_fwd(a, p, in_dtype, out_dtype, static_cast<cudaStream_t>(stream)));
+}
+
+extern "C" int tramba_sscan_bwd(const void* u, const void* delta, const float* A, const void* Bm,
+                                const void* Cm, const float* D, const float* delta_bias, const void* dout,
+                                const float* ckpt, void* du, void* ddelta, float* dA, float* dB, float* dC,
+                                float* dD, float* ddelta_bias, int batch, int dim, int L, int N, int groups,
+                                int in_dtype, int dout_dtype, int delta_softplus, void* stream) {
+    if (!u || !delta || !A || !Bm || !Cm || !dout || !ckpt || !du || !ddelta || !dA || !dB || !dC)
+        return TRAMBA_E_NULL;
+    if ((D && !dD) || (delta_bias && !ddelta_bias)) return TRAMBA_E_NULL;
+    int rc = sscan_common(batch, dim, L, N, groups, in_dtype, dout_dtype);
+    if (rc != TRAMBA_OK) return rc;
+    const SScanPlan p = make_sscan_plan(static_cast<long long>(batch) * dim, L, elem_size(in_dtype));
+    const int need = p.tma ? 16 : elem_size(in_dtype);
+    if (!aligned(u, need) || !aligned(delta, need) || !aligned(Bm, need) || !aligned(Cm, need) ||
+        !aligned(du, need) || !aligned(ddelta, need) || !aligned(dout, p.tma ? 16 : elem_size(dout_dtype)) ||
+        !aligned(dB, 16) || !aligned(dC, 16) || !aligned(dA, 4) || !aligned(ckpt, 4))
+        return TRAMBA_E_ALIGN;
+    rc = check_device();
+    if (rc != TRAMBA_OK) return rc;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const size_t nbc = static_cast<size_t>(batch) * groups * N * L * sizeof(float);
+    cudaError_t e = cudaMemsetAsync(dB, 0, nbc, st);
+    if (e == cudaSuccess) e = cudaMemsetAsync(dC, 0, nbc, st);
+    if (e == cudaSuccess) e = cudaMemsetAsync(dA, 0, static_cast<size_t>(dim) * N * sizeof(float), st);
+    if (e == cudaSuccess && dD) e = cudaMemsetAsync(dD, 0, static_cast<size_t>(dim) * sizeof(float), st);
+    if (e == cudaSuccess && ddelta_bias) e = cudaMemsetAsync(ddelta_bias, 0, static_cast<size_t>(dim) * sizeof(float), st);
+    if (e != cudaSuccess) return cuda_rc(e);
+    SScanArgs a;
+    std::memset(&a, 0, sizeof(a));
+    a.u = u, a.delta = delta, a.A = A, a.Bm = Bm, a.Cm = Cm, a.D = D, a.bias = delta_bias;
+    a.dout = dout, a.ckpt_in = ckpt, a.du = du, a.ddelta = ddelta;
+    a.dA = dA, a.dB = dB, a.dC = dC, a.dD = dD, a.dbias = ddelta_bias;
+    fill_args(a, p, batch, dim, L, N, groups, delta_softplus);
+    // dB/dC pre-reduction over 8 rows of a group: needs whole rows per warp (uniform plan),
+    // one state, and groups whose channel count is a multiple of 8.
+    if (p.uniform && N == 1 && (dim / groups) % 8 == 0) a.rw = 8;
+    return cuda_rc(launch_sscan_bwd(a, p, in_dtype, dout_dtype, st));
+}
+
+// ------------------------------------------------------------------------------ DCT2D
+extern "C" int tramba_dct2d_fwd(const float* x, const float* wy, const float* wx, float* high, float* low,
+                                int planes, int H, int W, void* stream) {
+    if (!x || !wy || !wx || !high || !low) return TRAMBA_E_NULL;
+    if (planes <= 0 || H <= 0 || W <= 0 || (H & 1) || (W & 1)) return TRAMBA_E_SHAPE;
+    int rc = check_device();
+    if (rc != TRAMBA_OK) return rc;
+    cudaError_t e = launch_dct2d_fwd(x, wy, wx, high, low, planes, H, W, static_cast<cudaStream_t>(stream));
+    if (e == cudaErrorInvalidConfiguration) return TRAMBA_E_LIMIT;
+    return cuda_rc(e);
+}
+
+extern "C" int tramba_dct2d_bwd(const float* ghigh, const float* glow, const float* wy, const float* wx,
+                                float* gx, int planes, int H, int W, void* stream) {
+    if (!ghigh || !glow || !wy || !wx || !gx) return TRAMBA_E_NULL;
+    if (planes <= 0 || H <= 0 || W <= 0 || (H & 1) || (W & 1)) return TRAMBA_E_SHAPE;
+    int rc = check_device();
+    if (rc != TRAMBA_OK) return rc;
+    cudaError_t e = launch_dct2d_bwd(ghigh, glow, wy, wx, gx, planes, H, W, static_cast<cudaStream_t>(stream));
+    if (e == cudaErrorInvalidConfiguration) return TRAMBA_E_LIMIT;
+    return cuda_rc(e);
+}

@@ -1,0 +1,180 @@
+// Shared device helpers for the sm_100a kernels: mbarrier / TMA bulk-copy PTX wrappers,
+// fast transcendental helpers and dtype conversion.
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/tramba_b200.h"
+
+namespace tramba {
+
+constexpr float kLog2e = 1.4426950408889634f;
+constexpr float kLn2 = 0.6931471805599453f;
+
+// ------------------------------------------------------------------ launch accounting
+void note_launch();  // capi.cu
+
+// ------------------------------------------------------------------ mbarrier + TMA bulk
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async_smem() {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    while (!mbar_try_wait(bar, parity)) {
+    }
+}
+// global -> shared bulk copy (TMA, 1-D).  dst/src 16-byte aligned, bytes % 16 == 0.
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+            smem_u32(dst_smem)),
+        "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+        : "memory");
+}
+// shared -> global bulk copy (TMA, 1-D), tracked by the issuing thread's bulk async-group.
+__device__ __forceinline__ void bulk_s2g(void* dst_gmem, const void* src_smem, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_gmem),
+                 "r"(smem_u32(src_smem)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() {
+    asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+template <int N>
+__device__ __forceinline__ void bulk_wait_all() {
+    asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory");
+}
+
+// ------------------------------------------------------------------ math
+__device__ __forceinline__ float ex2f(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float lg2f(float x) {
+    float y;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float rcpf(float x) {
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+// softplus with torch's threshold (x > 20 -> x).  e = exp(x) is returned for the backward's
+// sigmoid.  log1p(e) uses a 4-term series below 2^-6 so that small deltas keep fp32 accuracy
+// (1+e would round away the low bits of e).
+__device__ __forceinline__ float softplus20(float x, float& e_out) {
+    float e = ex2f(x * kLog2e);
+    e_out = e;
+    float big = lg2f(1.0f + e) * kLn2;
+    float small = e * (1.0f + e * (-0.5f + e * (0.33333334f - 0.25f * e)));
+    float sp = (e < 0.015625f) ? small : big;
+    return (x > 20.0f) ? x : sp;
+}
+
+// ------------------------------------------------------------------ dtype helpers
+template <typename T>
+struct DTypeOf;
+template <>
+struct DTypeOf<float> {
+    static constexpr int value = TRAMBA_F32;
+};
+template <>
+struct DTypeOf<__nv_bfloat16> {
+    static constexpr int value = TRAMBA_BF16;
+};
+template <>
+struct DTypeOf<__half> {
+    static constexpr int value = TRAMBA_F16;
+};
+
+__device__ __forceinline__ float to_f32(float v) { return v; }
+__device__ __forceinline__ float to_f32(__nv_bfloat16 v) { return __bfloat162float(v); }
+__device__ __forceinline__ float to_f32(__half v) { return __half2float(v); }
+template <typename T>
+__device__ __forceinline__ T from_f32(float v);
+template <>
+__device__ __forceinline__ float from_f32<float>(float v) {
+    return v;
+}
+template <>
+__device__ __forceinline__ __nv_bfloat16 from_f32<__nv_bfloat16>(float v) {
+    return __float2bfloat16_rn(v);
+}
+template <>
+__device__ __forceinline__ __half from_f32<__half>(float v) {
+    return __float2half_rn(v);
+}
+
+// Load / store CNT consecutive elements (CNT % 4 == 0) as fp32 with the widest aligned
+// vector access the element type allows (16 B for fp32, 8 B for 16-bit types).
+template <int CNT, typename T>
+__device__ __forceinline__ void load_vec(const T* __restrict__ p, float (&v)[CNT]) {
+    static_assert(CNT % 4 == 0, "CNT % 4");
+    if constexpr (sizeof(T) == 4) {
+#pragma unroll
+        for (int i = 0; i < CNT / 4; ++i) {
+            float4 q = reinterpret_cast<const float4*>(p)[i];
+            v[4 * i] = q.x, v[4 * i + 1] = q.y, v[4 * i + 2] = q.z, v[4 * i + 3] = q.w;
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < CNT / 4; ++i) {
+            uint2 q = reinterpret_cast<const uint2*>(p)[i];
+            const T* h = reinterpret_cast<const T*>(&q);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) v[4 * i + j] = to_f32(h[j]);
+        }
+    }
+}
+template <int CNT, typename T>
+__device__ __forceinline__ void store_vec(T* __restrict__ p, const float (&v)[CNT]) {
+    static_assert(CNT % 4 == 0, "CNT % 4");
+    if constexpr (sizeof(T) == 4) {
+#pragma unroll
+        for (int i = 0; i < CNT / 4; ++i)
+            reinterpret_cast<float4*>(p)[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+    } else {
+#pragma unroll
+        for (int i = 0; i < CNT / 4; ++i) {
+            uint2 q;
+            T* h = reinterpret_cast<T*>(&q);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) h[j] = from_f32<T>(v[4 * i + j]);
+            reinterpret_cast<uint2*>(p)[i] = q;
+        }
+    }
+}
+
+}  // namespace tramba

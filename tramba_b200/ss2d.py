@@ -1,0 +1,158 @@
+"""SS2D module -- same constructor, parameter names/shapes and forward contract as the
+reference (Models/vmamba.py:18-323), running its core on the sm_100a operators.
+
+State-dict keys: in_proj.weight, conv2d.weight, x_proj_weight (K, R+2N, D), dt_projs_weight
+(K, D, R), dt_projs_bias (K, D), A_logs (K*D, N), Ds (K*D), out_norm.{weight,bias},
+out_proj.weight -- reference checkpoints load unchanged.
+
+The in/out projections, depthwise conv, x_proj/dt_proj and the LayerNorm stay PyTorch ops, as
+in the reference (north_star); cross-scan, selective scan and cross-merge are ours.
+"""
+import math
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import ops
+
+
+class Linear2d(nn.Linear):
+    """1x1 convolution with nn.Linear parameters (Models/modules.py:10-19)."""
+
+    def forward(self, x):
+        return F.conv2d(x, self.weight[:, :, None, None], self.bias)
+
+    def _load_from_state_dict(self, state_dict, prefix, *args, **kwargs):
+        key = prefix + "weight"
+        if key in state_dict:
+            state_dict[key] = state_dict[key].view(self.weight.shape)
+        return super()._load_from_state_dict(state_dict, prefix, *args, **kwargs)
+
+
+class LayerNorm2d(nn.LayerNorm):
+    """LayerNorm over the channel dim of an NCHW tensor (Models/modules.py:22-27)."""
+
+    def forward(self, x):
+        x = x.permute(0, 2, 3, 1).contiguous()
+        x = F.layer_norm(x, self.normalized_shape, self.weight, self.bias, self.eps)
+        return x.permute(0, 3, 1, 2).contiguous()
+
+
+def _dt_init(dt_rank, d_inner, dt_scale=1.0, dt_init="random", dt_min=0.001, dt_max=0.1, dt_init_floor=1e-4):
+    """Models/mamba_init.py:7-31."""
+    proj = nn.Linear(dt_rank, d_inner, bias=True)
+    std = dt_rank ** -0.5 * dt_scale
+    if dt_init == "constant":
+        nn.init.constant_(proj.weight, std)
+    elif dt_init == "random":
+        nn.init.uniform_(proj.weight, -std, std)
+    else:
+        raise NotImplementedError
+    dt = torch.exp(torch.rand(d_inner) * (math.log(dt_max) - math.log(dt_min)) + math.log(dt_min)).clamp(
+        min=dt_init_floor)
+    with torch.no_grad():
+        proj.bias.copy_(dt + torch.log(-torch.expm1(-dt)))  # softplus^-1
+    return proj
+
+
+def _a_log_init(d_state, d_inner, copies):
+    """Models/mamba_init.py:34-48: S4D-real, A = 1..N per row, K copies merged."""
+    a = torch.arange(1, d_state + 1, dtype=torch.float32).repeat(copies * d_inner, 1).contiguous()
+    p = nn.Parameter(torch.log(a))
+    p._no_weight_decay = True
+    return p
+
+
+def _d_init(d_inner, copies):
+    """Models/mamba_init.py:51-60."""
+    p = nn.Parameter(torch.ones(copies * d_inner))
+    p._no_weight_decay = True
+    return p
+
+
+class SS2D(nn.Module):
+    def __init__(
+            self,
+            d_model=96, d_state=16, ssm_ratio=2.0, dt_rank="auto", act_layer=nn.SiLU,
+            d_conv=3, conv_bias=False,
+            dropout=0.0, bias=False,
+            dt_min=0.001, dt_max=0.1, dt_init="random", dt_scale=1.0, dt_init_floor=1e-4, initialize="v0",
+            forward_type="v2", channel_first=False,
+            disable_z=True,
+            scan=ops.CrossScan,
+            merge=ops.CrossMerge,
+            k_group=4,
+            **kwargs,
+    ):
+        super().__init__()
+        d_inner = int(ssm_ratio * d_model)
+        dt_rank = math.ceil(d_model / 16) if dt_rank == "auto" else dt_rank
+        self.channel_first = channel_first
+        self.with_dconv = d_conv > 1
+        self.disable_z = disable_z
+        self.k_group = k_group
+        self.scan, self.merge = scan, merge
+        Linear = Linear2d if channel_first else nn.Linear
+        LayerNorm = LayerNorm2d if channel_first else nn.LayerNorm
+
+        self.out_norm = LayerNorm(d_inner)
+        self.in_proj = Linear(d_model, d_inner if disable_z else d_inner * 2, bias=bias)
+        self.act = act_layer()
+        if self.with_dconv:
+            self.conv2d = nn.Conv2d(d_inner, d_inner, groups=d_inner, bias=conv_bias, kernel_size=d_conv,
+                                    padding=(d_conv - 1) // 2)
+        x_proj = [nn.Linear(d_inner, dt_rank + d_state * 2, bias=False) for _ in range(k_group)]
+        self.x_proj_weight = nn.Parameter(torch.stack([t.weight for t in x_proj], dim=0))  # (K, R+2N, D)
+        self.out_act = nn.GELU()
+        self.out_proj = Linear(d_inner, d_model, bias=bias)
+        self.dropout = nn.Dropout(dropout) if dropout > 0.0 else nn.Identity()
+        if initialize in ["v0"]:
+            dt_projs = [_dt_init(dt_rank, d_inner, dt_scale, dt_init, dt_min, dt_max, dt_init_floor)
+                        for _ in range(k_group)]
+            self.dt_projs_weight = nn.Parameter(torch.stack([t.weight for t in dt_projs], dim=0))  # (K, D, R)
+            self.dt_projs_bias = nn.Parameter(torch.stack([t.bias for t in dt_projs], dim=0))      # (K, D)
+            self.A_logs = _a_log_init(d_state, d_inner, copies=k_group)                            # (K*D, N)
+            self.Ds = _d_init(d_inner, copies=k_group)                                             # (K*D)
+
+    def forward_core(self, x):
+        """Models/vmamba.py:231-273 (force_fp32=False, no_einsum=True, ssoflex=True)."""
+        B, D, H, W = x.shape
+        D, N = self.A_logs.shape
+        K, D, R = self.dt_projs_weight.shape
+        L = H * W
+        xs = self.scan.apply(x)                                                        # (B, K, D, L)
+        x_dbl = F.conv1d(xs.view(B, -1, L), self.x_proj_weight.view(-1, D, 1), bias=None, groups=K)
+        dts, Bs, Cs = torch.split(x_dbl.view(B, K, -1, L), [R, N, N], dim=2)
+        dts = F.conv1d(dts.contiguous().view(B, -1, L), self.dt_projs_weight.view(K * D, -1, 1), groups=K)
+        xs = xs.view(B, -1, L)
+        dts = dts.contiguous().view(B, -1, L)
+        As = -torch.exp(self.A_logs.to(torch.float))
+        Bs = Bs.contiguous().view(B, K, N, L)
+        Cs = Cs.contiguous().view(B, K, N, L)
+        Ds = self.Ds.to(torch.float)
+        delta_bias = self.dt_projs_bias.view(-1).to(torch.float)
+        ys = ops.SelectiveScanOflex.apply(xs, dts, As, Bs, Cs, Ds, delta_bias, True, -1, -1, True)
+        y = self.merge.apply(ys.view(B, K, -1, H, W))                                   # (B, D, L)
+        y = y.view(B, -1, H, W)
+        if not self.channel_first:
+            y = y.view(B, -1, H * W).transpose(1, 2).contiguous().view(B, H, W, -1)
+        y = self.out_norm(y)
+        return y.to(x.dtype)
+
+    def forward(self, x, **kwargs):
+        """Models/vmamba.py:275-291."""
+        x = self.in_proj(x)
+        z = None
+        if not self.disable_z:
+            x, z = x.chunk(2, dim=(1 if self.channel_first else -1))
+            z = self.act(z)
+        if not self.channel_first:
+            x = x.permute(0, 3, 1, 2).contiguous()
+        if self.with_dconv:
+            x = self.conv2d(x)
+        x = self.act(x)
+        y = self.out_act(self.forward_core(x))
+        if not self.disable_z:
+            y = y * z
+        return self.dropout(self.out_proj(y))
