@@ -1,0 +1,46 @@
+"""GPU parity: DCT2D high/low split vs the reference module's golden outputs and the oracle."""
+import numpy as np
+import pytest
+import torch
+
+import tramba_b200
+from oracle import dct as odct
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("B,C,H", [(2, 3, 24), (1, 2, 48), (1, 1, 96), (2, 2, 12)])
+def test_dct_vs_reference_golden(golden_dct, B, C, H):
+    x = np.random.RandomState(2000 + H).standard_normal((B, C, H, H)).astype(np.float32)
+    m = tramba_b200.DCT2D(H, H).cuda()
+    assert np.array_equal(m.dct_x.weight.cpu().numpy(), golden_dct[f"dct_{H}_wx"])
+    high, low = m(torch.from_numpy(x).cuda())
+    # fp32 tolerance stated by north_star: rtol 1e-3; the fp32 SIMT path is far inside it
+    np.testing.assert_allclose(high.cpu().numpy(), golden_dct[f"dct_{B}_{C}_{H}_high"], rtol=1e-3, atol=2e-5)
+    np.testing.assert_allclose(low.cpu().numpy(), golden_dct[f"dct_{B}_{C}_{H}_low"], rtol=1e-3, atol=2e-5)
+
+
+@pytest.mark.parametrize("B,C,H", [(4, 128, 96), (4, 256, 48), (4, 512, 24)])
+def test_dct_model_shapes_vs_oracle_and_backward(B, C, H):
+    """The three call sites of Tramba-V at 384^2, batch 4."""
+    x = torch.randn(B, C, H, H, device="cuda", requires_grad=True)
+    m = tramba_b200.DCT2D(H, H).cuda()
+    high, low = m(x)
+    sl = slice(0, 2), slice(0, 8)
+    rh, rl = odct.dct2d_split(x.detach()[sl].cpu().numpy())
+    np.testing.assert_allclose(high[sl].detach().cpu().numpy(), rh, rtol=1e-3, atol=2e-5)
+    np.testing.assert_allclose(low[sl].detach().cpu().numpy(), rl, rtol=1e-3, atol=2e-5)
+    gh, gl = torch.randn_like(high), torch.randn_like(low)
+    (gx,) = torch.autograd.grad([high, low], x, [gh, gl])
+    ref = odct.dct2d_split_bwd(gh[sl].cpu().numpy(), gl[sl].cpu().numpy(), H, H)
+    np.testing.assert_allclose(gx[sl].cpu().numpy(), ref, rtol=1e-3, atol=2e-5)
+    # orthonormality property at full size: energy of the two kept quadrants <= energy of x
+    assert (high.double().pow(2).sum() + low.double().pow(2).sum()) <= x.double().pow(2).sum() * (1 + 1e-6)
+
+
+def test_dct_bf16_input_is_promoted_like_reference():
+    x = torch.randn(1, 4, 24, 24, device="cuda").bfloat16()
+    high, low = tramba_b200.DCT2D(24, 24).cuda()(x)
+    assert high.dtype == torch.float32
+    rh, rl = odct.dct2d_split(x.float().cpu().numpy())
+    np.testing.assert_allclose(low.cpu().numpy(), rl, rtol=1e-3, atol=2e-5)

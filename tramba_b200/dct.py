@@ -25,13 +25,15 @@ def _stream():
 
 class _DCT2DSplit(torch.autograd.Function):
     @staticmethod
-    @torch.amp.custom_fwd(device_type="cuda", cast_inputs=torch.float32)
+    @torch.amp.custom_fwd(device_type="cuda")
     def forward(ctx, x, wy, wx):
+        ctx.in_dtype = x.dtype
         if not x.is_cuda:
             raise RuntimeError("tramba_b200 has no CPU path: DCT2D needs a CUDA tensor")
         B, C, H, W = x.shape
-        x = x.contiguous()
-        wy, wx = wy.contiguous(), wx.contiguous()
+        # the reference multiplies x by fp32 basis buffers, so any input is promoted to fp32
+        x = x.contiguous().float()
+        wy, wx = wy.contiguous().float(), wx.contiguous().float()
         high = x.new_empty((B, C, H // 2, W // 2))
         low = x.new_empty((B, C, H // 2, W // 2))
         with torch.cuda.device(x.device):
@@ -52,7 +54,7 @@ class _DCT2DSplit(torch.autograd.Function):
         with torch.cuda.device(ghigh.device):
             _lib.check(_lib.lib.tramba_dct2d_bwd(ghigh.data_ptr(), glow.data_ptr(), wy.data_ptr(), wx.data_ptr(),
                                                  gx.data_ptr(), B * C, H, W, _stream()))
-        return gx, None, None
+        return gx.to(ctx.in_dtype), None, None
 
 
 def dct2d_split(x, wy, wx):

@@ -93,6 +93,9 @@ class SS2D(nn.Module):
         self.disable_z = disable_z
         self.k_group = k_group
         self.scan, self.merge = scan, merge
+        # bound like the reference's partial(forward_corev2, SelectiveScan=SelectiveScanOflex, ...)
+        # (Models/vmamba.py:65-66); tests swap in the CPU oracle operator here
+        self.selective_scan = ops.SelectiveScanOflex
         Linear = Linear2d if channel_first else nn.Linear
         LayerNorm = LayerNorm2d if channel_first else nn.LayerNorm
 
@@ -132,7 +135,7 @@ class SS2D(nn.Module):
         Cs = Cs.contiguous().view(B, K, N, L)
         Ds = self.Ds.to(torch.float)
         delta_bias = self.dt_projs_bias.view(-1).to(torch.float)
-        ys = ops.SelectiveScanOflex.apply(xs, dts, As, Bs, Cs, Ds, delta_bias, True, -1, -1, True)
+        ys = self.selective_scan.apply(xs, dts, As, Bs, Cs, Ds, delta_bias, True, -1, -1, True)
         y = self.merge.apply(ys.view(B, K, -1, H, W))                                   # (B, D, L)
         y = y.view(B, -1, H, W)
         if not self.channel_first:
