@@ -165,6 +165,7 @@ static void fill_args(SScanArgs& a, const SScanPlan& p, int batch, int dim, int 
     a.R = p.R, a.cpu = p.cpu, a.units = p.units;
     a.softplus = softplus ? 1 : 0;
     a.uniform = p.uniform ? 1 : 0;
+    a.rpc = p.rpc;
     a.rw = 1;
     a.divL.init(static_cast<uint32_t>(L));
     a.divDim.init(static_cast<uint32_t>(dim));
@@ -232,9 +233,23 @@ extern "C" int tramba_sscan_bwd(const void* u, const void* delta, const float* A
     a.dout = dout, a.ckpt_in = ckpt, a.du = du, a.ddelta = ddelta;
     a.dA = dA, a.dB = dB, a.dC = dC, a.dD = dD, a.dbias = ddelta_bias;
     fill_args(a, p, batch, dim, L, N, groups, delta_softplus);
-    // dB/dC pre-reduction over 8 rows of a group: needs whole rows per warp (uniform plan),
-    // one state, and groups whose channel count is a multiple of 8.
-    if (p.uniform && N == 1 && (dim / groups) % 8 == 0) a.rw = 8;
+    // dB/dC pre-reduction over RW units of one (batch, group): largest RW in {8,4,2,1} that
+    // still leaves at least ~12 warps of work per SM (one warp per super-unit).
+    if (p.regular) {
+        if (N == 1) {
+            int sms = 148, dev = 0;
+            cudaGetDevice(&dev);
+            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+            const int rows_per_group = dim / groups;
+            for (int rw = 8; rw >= 1; rw >>= 1) {
+                if (rows_per_group % (rw * p.rpc) != 0) continue;
+                a.rw = rw;
+                if (p.units / rw >= 12ll * sms) break;
+            }
+        }
+    } else if (p.uniform && N == 1 && (dim / groups) % 8 == 0) {
+        a.rw = 8;
+    }
     return cuda_rc(launch_sscan_bwd(a, p, in_dtype, dout_dtype, st));
 }
 

@@ -91,16 +91,22 @@ __device__ __forceinline__ float rcpf(float x) {
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
 }
-// softplus with torch's threshold (x > 20 -> x).  e = exp(x) is returned for the backward's
-// sigmoid.  log1p(e) uses a 4-term series below 2^-6 so that small deltas keep fp32 accuracy
-// (1+e would round away the low bits of e).
-__device__ __forceinline__ float softplus20(float x, float& e_out) {
-    float e = ex2f(x * kLog2e);
+// softplus with torch's threshold (x > 20 -> x), branch-free.  e = exp(x) and w = 1 + e are
+// returned for the backward's sigmoid.  log1p(e) = log(w) + (e - (w - 1)) / w to first order;
+// the correction term restores the bits of e that rounding 1 + e drops, so small deltas keep
+// fp32 relative accuracy (1/w ~ 1 wherever the term matters; it is switched off for e >= 1).
+__device__ __forceinline__ float softplus20(float x, float& e_out, float& w_out) {
+    const float e = ex2f(x * kLog2e);
+    const float w = 1.0f + e;
+    const float corr = (e < 1.0f) ? (e - (w - 1.0f)) : 0.0f;
+    const float sp = fmaf(lg2f(w), kLn2, corr);
     e_out = e;
-    float big = lg2f(1.0f + e) * kLn2;
-    float small = e * (1.0f + e * (-0.5f + e * (0.33333334f - 0.25f * e)));
-    float sp = (e < 0.015625f) ? small : big;
+    w_out = w;
     return (x > 20.0f) ? x : sp;
+}
+__device__ __forceinline__ float softplus20(float x, float& e_out) {
+    float w;
+    return softplus20(x, e_out, w);
 }
 
 // ------------------------------------------------------------------ dtype helpers

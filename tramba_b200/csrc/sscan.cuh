@@ -52,6 +52,8 @@ struct SScanPlan {
     int ch;       // 32 * tseg
     bool tma;     // TMA-staged (rows are 16-byte multiples) vs DIRECT scalar path
     bool uniform; // every chunk lies inside one row (L % ch == 0)
+    bool regular; // uniform, or a chunk holds exactly rpc whole rows (rpc a power of two <= 4)
+    int rpc;      // rows per chunk (1 when uniform)
     int R;        // rows per unit
     int cpu;      // chunks per unit
     long long units;
@@ -95,6 +97,15 @@ inline SScanPlan make_sscan_plan(long long rows, int L, int es_in) {
         p.cpu = static_cast<int>((r * L + p.ch - 1) / p.ch);
     }
     p.units = (rows + p.R - 1) / p.R;
+    p.rpc = 1;
+    p.regular = p.uniform;
+    if (!p.uniform && p.tma && p.ch % L == 0) {
+        const int rpc = p.ch / L;
+        if ((rpc == 2 || rpc == 4) && rows % rpc == 0 && p.R == rpc && p.cpu == 1) {
+            p.rpc = rpc;
+            p.regular = true;
+        }
+    }
     return p;
 }
 
@@ -126,7 +137,8 @@ struct SScanArgs {
     long long units;
     int softplus;
     int uniform;
-    int rw;  // backward: rows pre-reduced per warp for dB/dC (uniform plans only)
+    int rpc;  // regular plans: whole rows per chunk (1, 2 or 4)
+    int rw;   // backward: rows pre-reduced per warp for dB/dC (uniform plans only)
     FastDiv divL, divDim, divDpg;
 };
 
@@ -164,6 +176,37 @@ __device__ __forceinline__ void warp_scan_affine_rev(float& P, float& S, int lan
             P = P * Pp;
         }
     }
+}
+// Width-LPR variants (LPR lanes per row, several rows side by side in one warp).
+template <int LPR>
+__device__ __forceinline__ void group_scan_affine(float& P, float& S, int sl) {
+#pragma unroll
+    for (int off = 1; off < LPR; off <<= 1) {
+        float Pp = __shfl_up_sync(0xffffffffu, P, off, LPR);
+        float Sp = __shfl_up_sync(0xffffffffu, S, off, LPR);
+        if (sl >= off) {
+            S = fmaf(P, Sp, S);
+            P = P * Pp;
+        }
+    }
+}
+template <int LPR>
+__device__ __forceinline__ void group_scan_affine_rev(float& P, float& S, int sl) {
+#pragma unroll
+    for (int off = 1; off < LPR; off <<= 1) {
+        float Pp = __shfl_down_sync(0xffffffffu, P, off, LPR);
+        float Sp = __shfl_down_sync(0xffffffffu, S, off, LPR);
+        if (sl + off < LPR) {
+            S = fmaf(P, Sp, S);
+            P = P * Pp;
+        }
+    }
+}
+template <int LPR>
+__device__ __forceinline__ float group_sum(float v) {
+#pragma unroll
+    for (int off = LPR / 2; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off, LPR);
+    return v;
 }
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
