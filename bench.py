@@ -1,0 +1,345 @@
+#!/usr/bin/env python
+"""bench.py -- Tramba-V 384^2 images/s, forward+backward (BASELINE.json metric, config 3).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]            our arm (sm_100a kernels)
+    python bench.py --impl reference [--gpus N] [--steps K] ...     the reference's CPU path (oracle port)
+
+A step = one full training step of Tramba-V-TSOD (tramba_b200/model.py harness: the reference's
+module tree with identical state_dict) at 384x384, batch 4 per GPU, bf16 autocast: forward,
+deep-supervision loss (train.py:74-85), backward, DDP gradient all-reduce (N > 1), Adam step.
+Random-init weights, synthetic N(0,1) images and Bernoulli(0.5) masks.
+
+  value    : images/s, whole job, inputs already resident in HBM, CUDA events, max over ranks
+  e2e      : same step through the public API with HOST inputs: pinned host -> device copy of
+             images + masks and a device -> host read of the loss inside the timed region
+  roofline : the dominant kernel of OUR library in the step (selective-scan backward), timed per
+             launch with CUDA events on the launching stream inside the timed region; achieved =
+             sum(algorithmic bytes) / sum(launch time) against MEASURED_PEAKS.json hbm_gbs
+  cpu_baseline : the oracle port of the reference path (same harness, oracle operators, fp32, CPU)
+             on this box's host cores; N = 1 only; bounded sample = 1 image forward+backward
+Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "Tramba-V 384x384 images/sec fwd+bwd (training step)"
+UNIT = "images/s"
+IMG = 384
+NCU_TRAFFIC_PATH = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=4, help="images per GPU per step (config 3: 4)")
+    ap.add_argument("--dtype", default="bf16", choices=["bf16", "f32"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-budget-s", type=float, default=240.0, help="wall budget of the reference arm")
+    return ap.parse_args()
+
+
+# ----------------------------------------------------------------------------------------------
+# clocks: sample nvidia-smi DURING the timed region (B200_PROFILING.md recipe)
+# ----------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+
+    def __init__(self, index):
+        self.lines = []
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i",
+                 str(index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append((time.time(), line.strip()))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, smax, pw, reasons = [], [], [], set()
+        for ts, ln in self.lines:
+            if ts < t0 or ts > t1 + 0.2:
+                continue
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])), smax.append(float(f[1])), pw.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(self.NAMES, f[3:7]):
+                if v == "Active":
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ----------------------------------------------------------------------------------------------
+# reference arm / cpu_baseline: the reference's CPU path = harness + oracle operators (fp32, CPU)
+# ----------------------------------------------------------------------------------------------
+def cpu_path_step_fn(batch):
+    """Returns (step, cores, sample description).  The ONLY place bench.py touches oracle/."""
+    import torch
+    from oracle import build as obuild
+    from oracle.torch_ops import oracleize
+    from tramba_b200.model import build_model, tsod_loss
+
+    obuild.build()
+    torch.manual_seed(0)
+    cores = torch.get_num_threads()
+    model = oracleize(build_model(deep_supervision=True, img_size=IMG, dims=128), f32=True).train()
+    opt = torch.optim.Adam(model.parameters(), lr=1e-4)
+    x = torch.randn(batch, 3, IMG, IMG)
+    y = (torch.rand(batch, 1, IMG, IMG) > 0.5).float()
+
+    def step():
+        opt.zero_grad(set_to_none=True)
+        loss = tsod_loss(model(x), y)
+        loss.backward()
+        opt.step()
+        return loss.item()
+
+    sample = (f"{batch} image(s) of the same training step (fwd + loss + bwd + Adam) on CPU: harness with the "
+              f"oracle operators (C/OpenMP fp32 selective scan, numpy scan/merge/DCT), torch CPU for the rest")
+    return step, cores, sample
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    step, cores, sample = cpu_path_step_fn(1)
+    t_begin = time.time()
+    t = time.perf_counter()
+    step()                                   # warm-up (also builds the order tables)
+    t_first = time.perf_counter() - t
+    warm = 1
+    while warm < args.warmup and (time.time() - t_begin) + 2 * t_first < 0.25 * args.cpu_budget_s:
+        step()
+        warm += 1
+    left = args.cpu_budget_s - (time.time() - t_begin)
+    steps = max(1, min(args.steps, int(left / max(t_first, 1e-3))))
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = time.perf_counter() - t0
+    v = steps * 1 / dt
+    line = {
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+        "warmup": warm, "requested_steps": args.steps, "requested_warmup": args.warmup,
+        "ms_per_step": 1e3 * dt / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "Tramba-V-TSOD training step 384x384 (BASELINE config 3), CPU sample batch 1",
+                   "img_size": IMG, "global_batch": 1, "parallelism": "cpu", "l2": "n/a (CPU)"},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+        "note": "reference is pure Python + an un-vendored CUDA extension: no oracle/_ref; this is the oracle port. "
+                "steps/warmup are clipped to --cpu-budget-s of wall time (requested_* = what was asked)",
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# ----------------------------------------------------------------------------------------------
+# our arm
+# ----------------------------------------------------------------------------------------------
+def summarize_prof(prof):
+    """(kind -> {launches, us, bytes, gbs}) from the event list recorded by tramba_b200._lib.timed."""
+    agg = {}
+    for kind, nbytes, e0, e1 in prof:
+        a = agg.setdefault(kind, {"launches": 0, "ms": 0.0, "bytes": 0})
+        a["launches"] += 1
+        a["ms"] += e0.elapsed_time(e1)
+        a["bytes"] += nbytes
+    for a in agg.values():
+        a["gbs"] = a["bytes"] / (a["ms"] * 1e-3) / 1e9 if a["ms"] > 0 else None
+        a["us_per_launch"] = 1e3 * a["ms"] / a["launches"]
+    return agg
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    assert world == args.gpus or world == 1, f"--gpus {args.gpus} but WORLD_SIZE={world}"
+
+    import tramba_b200
+    from tramba_b200 import _lib
+    from tramba_b200.model import build_model, tsod_loss
+
+    torch.backends.cudnn.benchmark = True               # train.py:29
+    torch.manual_seed(1026 + rank)                      # train.py:284 random_seed(1026)
+    model = build_model(deep_supervision=True, img_size=IMG, dims=128).to(dev).train()
+    enc = [p for n, p in model.named_parameters() if n.startswith("vssm_encoder")]
+    dec = [p for n, p in model.named_parameters() if not n.startswith("vssm_encoder")]
+    opt = torch.optim.Adam([{"params": enc, "lr": 1e-5}, {"params": dec, "lr": 1e-4}], fused=True)  # train.py:266-280
+    net = model
+    if world > 1:
+        net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local], gradient_as_bucket_view=True,
+                                                        static_graph=True)
+    B = args.batch
+    amp = torch.bfloat16 if args.dtype == "bf16" else None
+    g = torch.Generator().manual_seed(rank)
+    h_img = torch.randn(B, 3, IMG, IMG, generator=g).pin_memory()
+    h_lab = (torch.rand(B, 1, IMG, IMG, generator=g) > 0.5).float().pin_memory()
+    d_img, d_lab = h_img.to(dev), h_lab.to(dev)
+
+    def step(img, lab):
+        opt.zero_grad(set_to_none=True)
+        with torch.autocast("cuda", dtype=amp, enabled=amp is not None):
+            outs = net(img)
+        loss = tsod_loss(outs, lab)
+        loss.backward()
+        opt.step()
+        return loss
+
+    def sync():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step(d_img, d_lab)
+    sync()
+
+    sampler = ClockSampler(local) if rank == 0 else None
+    t_wall0 = time.time()
+    # ---- timed region 1: device-resident inputs, per-launch events on our kernels
+    _lib.prof = []
+    n0 = _lib.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sync()
+    e0.record()
+    for _ in range(args.steps):
+        loss = step(d_img, d_lab)
+    e1.record()
+    sync()
+    ms_dev = e0.elapsed_time(e1)
+    launches = _lib.launch_count() - n0
+    prof, _lib.prof = _lib.prof, None
+    kern = summarize_prof(prof)
+    loss_val = loss.item()
+
+    # ---- timed region 2: end to end through the public API with host buffers
+    sync()
+    e0.record()
+    for _ in range(args.steps):
+        img = h_img.to(dev, non_blocking=True)
+        lab = h_lab.to(dev, non_blocking=True)
+        lv = step(img, lab).item()                      # device -> host read of the step's result
+    e1.record()
+    sync()
+    ms_e2e = e0.elapsed_time(e1)
+    t_wall1 = time.time()
+    clocks = sampler.stop(t_wall0, t_wall1) if sampler else None
+
+    t = torch.tensor([ms_dev, ms_e2e], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_dev, ms_e2e = t.tolist()
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except OSError:
+            pass
+        peak, peak_src = (peaks["hbm_gbs"], "measured (MEASURED_PEAKS.json hbm_gbs)") if "hbm_gbs" in peaks \
+            else (6650.0, "fallback (B200_PROFILING.md)")
+        dom = "sscan_bwd"
+        traffic = None
+        try:
+            traffic = json.load(open(NCU_TRAFFIC_PATH)).get(dom)
+        except (OSError, ValueError):
+            pass
+        k = kern[dom]
+        roofline = {"bound": "hbm", "kernel": dom, "achieved": k["gbs"], "peak": peak, "unit": "GB/s",
+                    "frac": k["gbs"] / peak, "traffic": traffic, "peak_source": peak_src,
+                    "launches": k["launches"], "us_per_launch": k["us_per_launch"],
+                    "algorithmic_bytes_per_launch": k["bytes"] / k["launches"],
+                    "share_of_step": k["ms"] / ms_dev}
+        line = {
+            "metric": METRIC, "value": world * B * args.steps / (ms_dev * 1e-3), "unit": UNIT, "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_dev / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": args.dtype,
+            "data": "synthetic",
+            "config": {"workload": "Tramba-V-TSOD training step 384x384, batch 4 per GPU (BASELINE config 3)",
+                       "img_size": IMG, "global_batch": world * B, "parallelism": f"dp{world}",
+                       "weights": "random-init, 111.44 M params", "optimizer": "Adam (fused), DDP all-reduce",
+                       "l2": "no explicit flush: a step streams several GB of activations (>> 126 MB L2)"},
+            "e2e": {"value": world * B * args.steps / (ms_e2e * 1e-3), "unit": UNIT,
+                    "h2d_bytes_per_step": h_img.numel() * 4 + h_lab.numel() * 4, "d2h_bytes_per_step": 4,
+                    "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": launches,
+            "clocks": clocks,
+            "roofline": roofline,
+            "kernels": {kk: {"launches": v["launches"], "us_per_launch": round(v["us_per_launch"], 2),
+                             "gbs": round(v["gbs"], 1), "frac": round(v["gbs"] / peak, 4),
+                             "share_of_step": round(v["ms"] / ms_dev, 4)} for kk, v in sorted(kern.items())},
+            "loss": loss_val,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            stepc, cores, sample = cpu_path_step_fn(1)
+            stepc()                                     # warm-up: order tables, allocator
+            t0 = time.perf_counter()
+            stepc()
+            dt = time.perf_counter() - t0
+            line["cpu_baseline"] = {"value": 1.0 / dt, "unit": UNIT, "cores": cores, "kind": "port",
+                                    "sample": sample + "; 1 warm-up + 1 timed step"}
+        else:
+            line["cpu_baseline"] = None
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -31,6 +31,11 @@ SIGNATURES = {
     "tramba_sscan_fwd": (_i, [_vp, _vp, _fp, _vp, _vp, _fp, _fp, _vp, _fp] + [_i] * 8 + [_vp]),
     "tramba_sscan_bwd": (_i, [_vp, _vp, _fp, _vp, _vp, _fp, _fp, _vp, _fp, _vp, _vp, _fp, _fp, _fp, _fp, _fp]
                          + [_i] * 8 + [_vp]),
+    "tramba_order_table16": (_i, [_i, _i, _i, _i, _vp]),
+    "tramba_ss2d_fused_supported": (_i, [_i] * 8),
+    "tramba_ss2d_fused_fwd": (_i, [_vp, _vp, _vp, _vp, _fp, _fp, _fp, _vp, _fp] + [_i] * 9 + [_vp]),
+    "tramba_ss2d_fused_bwd": (_i, [_vp, _vp, _vp, _vp, _fp, _fp, _fp, _vp, _fp, _vp, _vp, _fp, _fp, _fp, _fp, _fp]
+                              + [_i] * 9 + [_vp]),
     "tramba_dct_basis": (None, [_i, _fp]),
     "tramba_dct2d_fwd": (_i, [_fp, _fp, _fp, _fp, _fp, _i, _i, _i, _vp]),
     "tramba_dct2d_bwd": (_i, [_fp, _fp, _fp, _fp, _fp, _i, _i, _i, _vp]),
@@ -38,9 +43,13 @@ SIGNATURES = {
 
 
 def _load():
-    if not os.path.exists(LIB_PATH):
-        from . import build as _build  # raises if nvcc is unavailable: no silent fallback
-        _build.build()
+    import importlib.util
+    # build.py is loaded by path so that building never needs the (possibly stale) library itself
+    spec = importlib.util.spec_from_file_location("_tramba_b200_build", os.path.join(_HERE, "build.py"))
+    _build = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(_build)
+    if not os.path.exists(LIB_PATH) or (_build.sources_newer_than_lib() and os.path.exists(_build.NVCC)):
+        _build.build()  # raises if nvcc is unavailable or fails: no silent fallback
     lib = ctypes.CDLL(LIB_PATH)
     for name, (res, args) in SIGNATURES.items():
         fn = getattr(lib, name)  # AttributeError if the library lacks a declared symbol
@@ -59,3 +68,32 @@ def check(rc):
 
 def launch_count():
     return int(lib.tramba_launch_count())
+
+
+# ---------------------------------------------------------------------------------------
+# Per-launch device timing (bench.py's roofline leg).  When `prof` is a list, every C-ABI compute
+# call made through the Python host is bracketed by CUDA events recorded on the launching stream
+# and appended as (kind, algorithmic_bytes, start_event, end_event); bench.py reads the elapsed
+# times after its own synchronize.  Off (None) by default: zero overhead on the product path.
+# ---------------------------------------------------------------------------------------
+prof = None
+
+
+class timed:
+    __slots__ = ("kind", "nbytes", "ev")
+
+    def __init__(self, kind, nbytes):
+        self.kind, self.nbytes, self.ev = kind, nbytes, None
+
+    def __enter__(self):
+        if prof is not None:
+            import torch
+            self.ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+            self.ev[0].record()
+        return self
+
+    def __exit__(self, *exc):
+        if self.ev is not None:
+            self.ev[1].record()
+            prof.append((self.kind, self.nbytes, self.ev[0], self.ev[1]))
+        return False

@@ -15,8 +15,9 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "_obj")
 LIB = os.path.join(HERE, "libtramba_b200.so")
-SOURCES = ["capi.cu", "sscan_fwd.cu", "sscan_bwd.cu", "cross_scan.cu", "dct2d.cu", "orders.cpp"]
-HEADERS = ["common.cuh", "sscan.cuh", os.path.join("..", "..", "include", "tramba_b200.h")]
+SOURCES = ["capi.cu", "sscan_fwd.cu", "sscan_bwd.cu", "ss2d_fused_fwd.cu", "ss2d_fused_bwd.cu", "cross_scan.cu",
+           "dct2d.cu", "orders.cpp"]
+HEADERS = ["common.cuh", "sscan.cuh", "ss2d_fused.cuh", os.path.join("..", "..", "include", "tramba_b200.h")]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
          "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "--expt-relaxed-constexpr"]
@@ -27,6 +28,11 @@ def _stale(target, deps):
         return True
     t = os.path.getmtime(target)
     return any(os.path.getmtime(d) > t for d in deps)
+
+
+def sources_newer_than_lib():
+    deps = [os.path.join(CSRC, f) for f in SOURCES + HEADERS]
+    return _stale(LIB, deps)
 
 
 def build(force=False, verbose=False):

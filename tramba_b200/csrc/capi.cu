@@ -7,6 +7,7 @@
 
 #include "common.cuh"
 #include "sscan.cuh"
+#include "ss2d_fused.cuh"
 
 namespace tramba {
 
@@ -21,6 +22,9 @@ cudaError_t launch_dct2d_fwd(const float* x, const float* wy, const float* wx, f
                              int planes, int H, int W, cudaStream_t st);
 cudaError_t launch_dct2d_bwd(const float* ghigh, const float* glow, const float* wy, const float* wx, float* gx,
                              int planes, int H, int W, cudaStream_t st);
+
+size_t ss2d_fused_bwd_smem(int L, int es, int xb, bool dup);
+bool ss2d_fused_bwd_fits(int L, int es, uint32_t dup_mask, int K);
 
 static int elem_size(int dtype) {
     switch (dtype) {
@@ -272,6 +276,109 @@ extern "C" int tramba_dct2d_bwd(const float* ghigh, const float* glow, const flo
     int rc = check_device();
     if (rc != TRAMBA_OK) return rc;
     cudaError_t e = launch_dct2d_bwd(ghigh, glow, wy, wx, gx, planes, H, W, static_cast<cudaStream_t>(stream));
+    if (e == cudaErrorInvalidConfiguration) return TRAMBA_E_LIMIT;
+    return cuda_rc(e);
+}
+
+
+// ------------------------------------------------------------------------------ fused SS2D core
+extern "C" int tramba_order_table16(int order, int H, int W, int param, uint16_t* idx_out) {
+    if (!idx_out) return TRAMBA_E_NULL;
+    const int K = tramba_order_num_directions(order);
+    if (K < 0) return K;
+    if (static_cast<long long>(H) * W > 65536) return TRAMBA_E_LIMIT;
+    std::vector<int32_t> t(static_cast<size_t>(K) * H * W);
+    int rc = tramba_order_table(order, H, W, param, t.data());
+    if (rc != TRAMBA_OK) return rc;
+    for (size_t i = 0; i < t.size(); ++i) idx_out[i] = static_cast<uint16_t>(t[i]);
+    return TRAMBA_OK;
+}
+
+static uint32_t fused_dup_mask(int order) { return order == TRAMBA_ORDER_LINE ? 0xF0u : 0u; }
+
+static int fused_geometry(FusedArgs& a, int order, int K, int B, int D, int H, int W, int N) {
+    if (B <= 0 || D <= 0 || H <= 0 || W <= 0 || K <= 0) return TRAMBA_E_SHAPE;
+    if (order < TRAMBA_ORDER_STD || order > TRAMBA_ORDER_LINE) return TRAMBA_E_ORDER;
+    if (K != tramba_order_num_directions(order)) return TRAMBA_E_ORDER;
+    if (N != 1) return TRAMBA_E_LIMIT;
+    const long long L = static_cast<long long>(H) * W;
+    if (L > 65536 || L % kFusedS != 0) return TRAMBA_E_LIMIT;
+    const int TP = static_cast<int>(L / kFusedS);
+    if (TP > kFusedNT || (TP & (TP - 1)) != 0) return TRAMBA_E_LIMIT;  // L = 18 * 2^m, m <= 9
+    const int PP = kFusedNT / TP;
+    if (D % PP != 0) return TRAMBA_E_LIMIT;
+    if (static_cast<long long>(B) * D / PP >= (1ll << 30)) return TRAMBA_E_LIMIT;
+    a.B = B, a.K = K, a.D = D, a.L = static_cast<int>(L), a.TP = TP, a.PP = PP;
+    a.rounds = B * D / PP;
+    a.dup_mask = fused_dup_mask(order);
+    return TRAMBA_OK;
+}
+
+extern "C" int tramba_ss2d_fused_supported(int order, int K, int D, int H, int W, int N, int in_dtype,
+                                           int need_bwd) {
+    FusedArgs a;
+    std::memset(&a, 0, sizeof(a));
+    const int es = elem_size(in_dtype);
+    if (in_dtype != TRAMBA_F32 && in_dtype != TRAMBA_BF16) return 0;
+    if (fused_geometry(a, order, K, 1, D, H, W, N) != TRAMBA_OK) return 0;
+    if (ss2d_fused_fwd_smem(a.L, es, 1) > 227 * 1024) return 0;
+    if (need_bwd && !ss2d_fused_bwd_fits(a.L, es, a.dup_mask, K)) return 0;
+    return 1;
+}
+
+extern "C" int tramba_ss2d_fused_fwd(const void* x, const void* dts, const void* Bs, const void* Cs,
+                                     const float* A, const float* Dp, const float* delta_bias,
+                                     const uint16_t* idx16, float* y, int order, int K, int B, int D, int H,
+                                     int W, int N, int in_dtype, int delta_softplus, void* stream) {
+    if (!x || !dts || !Bs || !Cs || !A || !idx16 || !y) return TRAMBA_E_NULL;
+    if (in_dtype != TRAMBA_F32 && in_dtype != TRAMBA_BF16) return TRAMBA_E_DTYPE;
+    FusedArgs a;
+    std::memset(&a, 0, sizeof(a));
+    int rc = fused_geometry(a, order, K, B, D, H, W, N);
+    if (rc != TRAMBA_OK) return rc;
+    if (!aligned(x, 16) || !aligned(dts, 16) || !aligned(Bs, 16) || !aligned(Cs, 16) || !aligned(y, 16) ||
+        !aligned(idx16, 4) || !aligned(A, 4) || !aligned(Dp, 4) || !aligned(delta_bias, 4))
+        return TRAMBA_E_ALIGN;
+    rc = check_device();
+    if (rc != TRAMBA_OK) return rc;
+    const int es = elem_size(in_dtype);
+    a.xb = ss2d_fused_fwd_smem(a.L, es, 2) <= 227 * 1024 ? 2 : 1;
+    if (ss2d_fused_fwd_smem(a.L, es, a.xb) > 227 * 1024) return TRAMBA_E_LIMIT;
+    a.x = x, a.dts = dts, a.Bs = Bs, a.Cs = Cs, a.A = A, a.Dp = Dp, a.bias = delta_bias, a.idx = idx16, a.y = y;
+    a.softplus = delta_softplus ? 1 : 0;
+    return cuda_rc(launch_ss2d_fused_fwd(a, in_dtype, static_cast<cudaStream_t>(stream)));
+}
+
+extern "C" int tramba_ss2d_fused_bwd(const void* x, const void* dts, const void* Bs, const void* Cs,
+                                     const float* A, const float* Dp, const float* delta_bias,
+                                     const uint16_t* idx16, const float* dy, void* dxk, void* ddts, float* dBs,
+                                     float* dCs, float* dA_part, float* dD_part, float* dbias_part, int order,
+                                     int K, int B, int D, int H, int W, int N, int in_dtype, int delta_softplus,
+                                     void* stream) {
+    if (!x || !dts || !Bs || !Cs || !A || !idx16 || !dy || !dxk || !ddts || !dBs || !dCs || !dA_part)
+        return TRAMBA_E_NULL;
+    if ((Dp && !dD_part) || (delta_bias && !dbias_part)) return TRAMBA_E_NULL;
+    if (in_dtype != TRAMBA_F32 && in_dtype != TRAMBA_BF16) return TRAMBA_E_DTYPE;
+    FusedArgs a;
+    std::memset(&a, 0, sizeof(a));
+    int rc = fused_geometry(a, order, K, B, D, H, W, N);
+    if (rc != TRAMBA_OK) return rc;
+    if (!aligned(x, 16) || !aligned(dts, 16) || !aligned(Bs, 16) || !aligned(Cs, 16) || !aligned(dy, 16) ||
+        !aligned(dxk, 16) || !aligned(ddts, 16) || !aligned(dBs, 16) || !aligned(dCs, 16) || !aligned(idx16, 4))
+        return TRAMBA_E_ALIGN;
+    if (!ss2d_fused_bwd_fits(a.L, elem_size(in_dtype), a.dup_mask, K)) return TRAMBA_E_LIMIT;
+    rc = check_device();
+    if (rc != TRAMBA_OK) return rc;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const size_t nbc = static_cast<size_t>(B) * K * a.L * sizeof(float);
+    cudaError_t e = cudaMemsetAsync(dBs, 0, nbc, st);
+    if (e == cudaSuccess) e = cudaMemsetAsync(dCs, 0, nbc, st);
+    if (e != cudaSuccess) return cuda_rc(e);
+    a.x = x, a.dts = dts, a.Bs = Bs, a.Cs = Cs, a.A = A, a.Dp = Dp, a.bias = delta_bias, a.idx = idx16;
+    a.dy = dy, a.dx = dxk, a.ddts = ddts, a.dBs = dBs, a.dCs = dCs, a.dA = dA_part, a.dD = dD_part,
+    a.dbias = dbias_part;
+    a.softplus = delta_softplus ? 1 : 0;
+    e = launch_ss2d_fused_bwd(a, in_dtype, st);
     if (e == cudaErrorInvalidConfiguration) return TRAMBA_E_LIMIT;
     return cuda_rc(e);
 }

@@ -1,0 +1,233 @@
+// Fused SS2D core, forward (sm_100a).  See ss2d_fused.cuh for the data model.
+// Replaces CrossScan* -> SelectiveScanOflex -> CrossMerge* of Models/vmamba.py:231-259 for N = 1.
+#include "ss2d_fused.cuh"
+
+namespace tramba {
+
+namespace {
+
+constexpr int S = kFusedS;
+constexpr int NT = kFusedNT;
+constexpr int TOK = kFusedTok;
+constexpr int NW = NT / 32;
+
+__host__ __device__ inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// shared-memory layout (byte offsets), identical on host and device
+struct FwdLayout {
+    size_t x, d, b, c, y, tot, bar, total;
+    __host__ __device__ FwdLayout(int L, int es, int xb) {
+        size_t o = 0;
+        x = o, o += static_cast<size_t>(xb) * TOK * es;
+        d = o, o += static_cast<size_t>(xb) * TOK * es;
+        b = o, o += align_up(static_cast<size_t>(xb) * L * es, 16);
+        c = o, o += align_up(static_cast<size_t>(xb) * L * es, 16);
+        y = o, o += static_cast<size_t>(TOK) * 4;
+        tot = o, o += 2 * NW * sizeof(float2);
+        bar = o, o += 8 * sizeof(uint64_t);
+        total = o;
+    }
+};
+
+template <typename in_t>
+__global__ void __launch_bounds__(NT, 1) ss2d_fwd_kernel(const FusedArgs p) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int L = p.L, K = p.K, D = p.D, TP = p.TP, PP = p.PP, XB = p.xb;
+    const FwdLayout lay(L, sizeof(in_t), XB);
+    in_t* sx = reinterpret_cast<in_t*>(smem + lay.x);
+    in_t* sd = reinterpret_cast<in_t*>(smem + lay.d);
+    in_t* sB = reinterpret_cast<in_t*>(smem + lay.b);
+    in_t* sC = reinterpret_cast<in_t*>(smem + lay.c);
+    float* sy = reinterpret_cast<float*>(smem + lay.y);
+    float2* stot = reinterpret_cast<float2*>(smem + lay.tot);
+    uint64_t* barX = reinterpret_cast<uint64_t*>(smem + lay.bar);  // [2]
+    uint64_t* barD = barX + 2;                                     // [2]
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int q = tid / TP;       // plane slot of this thread
+    const int j = tid - q * TP;   // segment index inside the plane
+    const int width = TP < 32 ? TP : 32;
+    const int sl = lane & (width - 1);
+    const int wq = TP > 32 ? (j >> 5) : 0;          // warp index inside the plane group
+    const int gw0 = TP > 32 ? (q * (TP >> 5)) : 0;  // first warp of the plane group
+
+    const in_t* __restrict__ gx = static_cast<const in_t*>(p.x);
+    const in_t* __restrict__ gd = static_cast<const in_t*>(p.dts);
+    const in_t* __restrict__ gB = static_cast<const in_t*>(p.Bs);
+    const in_t* __restrict__ gC = static_cast<const in_t*>(p.Cs);
+
+    const int my_rounds = (p.rounds - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) /
+                          static_cast<int>(gridDim.x);
+    const int nstages = my_rounds * K;
+    if (nstages <= 0) return;
+
+    if (tid == 0) {
+        mbar_init(&barX[0], 1), mbar_init(&barX[1], 1), mbar_init(&barD[0], 1), mbar_init(&barD[1], 1);
+        fence_mbar_init();
+        fence_proxy_async_smem();
+    }
+    __syncthreads();
+
+    // producer side (thread 0 only)
+    auto issue_x = [&](int i) {
+        const long long plane0 = (static_cast<long long>(blockIdx.x) + static_cast<long long>(i) * gridDim.x) * PP;
+        const int buf = i % XB;
+        mbar_expect_tx(&barX[buf], TOK * sizeof(in_t));
+        bulk_g2s(sx + static_cast<size_t>(buf) * TOK, gx + plane0 * L, TOK * sizeof(in_t), &barX[buf]);
+    };
+    auto issue_dir = [&](int s) {
+        const int i = s / K, k = s - i * K;
+        const long long plane0 = (static_cast<long long>(blockIdx.x) + static_cast<long long>(i) * gridDim.x) * PP;
+        const long long b = plane0 / D, d0 = plane0 - b * D;
+        const int buf = s % XB;
+        const uint32_t lb = L * sizeof(in_t);
+        mbar_expect_tx(&barD[buf], TOK * sizeof(in_t) + 2 * lb);
+        bulk_g2s(sd + static_cast<size_t>(buf) * TOK, gd + ((b * K + k) * D + d0) * L, TOK * sizeof(in_t), &barD[buf]);
+        bulk_g2s(sB + static_cast<size_t>(buf) * L, gB + (b * K + k) * L, lb, &barD[buf]);
+        bulk_g2s(sC + static_cast<size_t>(buf) * L, gC + (b * K + k) * L, lb, &barD[buf]);
+    };
+    if (tid == 0) {
+        issue_x(0);
+        issue_dir(0);
+    }
+
+    int s = 0;
+    for (int i = 0; i < my_rounds; ++i) {
+        const long long plane0 = (static_cast<long long>(blockIdx.x) + static_cast<long long>(i) * gridDim.x) * PP;
+        const int b = static_cast<int>(plane0 / D);
+        const int d = static_cast<int>(plane0 - static_cast<long long>(b) * D) + q;
+        const in_t* xq = sx + static_cast<size_t>(i % XB) * TOK + static_cast<size_t>(q) * L;
+        float* yq = sy + static_cast<size_t>(q) * L;
+        if (XB == 2 && tid == 0 && i + 1 < my_rounds) issue_x(i + 1);
+        mbar_wait(&barX[i % XB], static_cast<uint32_t>((i / XB) & 1));
+
+        for (int k = 0; k < K; ++k, ++s) {
+            const int buf = s % XB;
+            if (XB == 2 && tid == 0 && s + 1 < nstages) issue_dir(s + 1);
+            const int row = k * D + d;
+            const float A2 = __ldg(p.A + row) * kLog2e;
+            const float Dd = p.Dp ? __ldg(p.Dp + row) : 0.f;
+            const float bias = p.bias ? __ldg(p.bias + row) : 0.f;
+            uint32_t pk[S / 2];
+            {
+                const uint32_t* tp = reinterpret_cast<const uint32_t*>(p.idx + static_cast<size_t>(k) * L + j * S);
+#pragma unroll
+                for (int m = 0; m < S / 2; ++m) pk[m] = __ldg(tp + m);
+            }
+            mbar_wait(&barD[buf], static_cast<uint32_t>((s / XB) & 1));
+            const in_t* dq = sd + static_cast<size_t>(buf) * TOK + static_cast<size_t>(q) * L;
+            const in_t* Bq = sB + static_cast<size_t>(buf) * L;
+            const in_t* Cq = sC + static_cast<size_t>(buf) * L;
+
+            // ---- pass 1: local fold from a zero carry-in
+            float y0[S], g[S];
+            float P = 1.f, Sacc = 0.f;
+#pragma unroll
+            for (int m = 0; m < S; ++m) {
+                const int px = (m & 1) ? (pk[m >> 1] >> 16) : (pk[m >> 1] & 0xffffu);
+                const float u = to_f32(xq[px]);
+                const float raw = to_f32(dq[px]) + bias;
+                float e;
+                const float dl = p.softplus ? softplus20(raw, e) : raw;
+                const float a = ex2f(dl * A2);
+                const float bb = dl * to_f32(Bq[px]) * u;
+                const float Cv = to_f32(Cq[px]);
+                Sacc = fmaf(a, Sacc, bb);
+                P *= a;
+                y0[m] = fmaf(Cv, Sacc, Dd * u);
+                g[m] = Cv * P;
+            }
+            // ---- carry-in of this thread: scan over the TP threads of the plane
+            fused_scan(P, Sacc, sl, width);
+            float Pe = __shfl_up_sync(0xffffffffu, P, 1, width);
+            float Se = __shfl_up_sync(0xffffffffu, Sacc, 1, width);
+            if (sl == 0) Pe = 1.f, Se = 0.f;
+            const int par = s & 1;
+            if (TP > 32 && lane == 31) stot[par * NW + warp] = make_float2(P, Sacc);
+            if (tid == 0) {
+                if (XB == 1 && s + 1 < nstages) {
+                    // single-buffered: the next stage's loads may start once everybody is past pass 1;
+                    // issued below, after the barrier
+                }
+                if (k == 0 && i > 0) bulk_wait_read<0>();  // previous round's y store has left sy
+            }
+            __syncthreads();
+            if (XB == 1 && tid == 0) {
+                if (s + 1 < nstages) issue_dir(s + 1);
+                if (k == K - 1 && i + 1 < my_rounds) issue_x(i + 1);
+            }
+            float hin = Se;
+            if (TP > 32) {
+                float hp = 0.f;
+                for (int w = 0; w < wq; ++w) {
+                    const float2 t = stot[par * NW + gw0 + w];
+                    hp = fmaf(t.x, hp, t.y);
+                }
+                hin = fmaf(Pe, hp, Se);
+            }
+            // ---- pass 2: add the carry-in term and merge into the image plane
+            const bool dup = (p.dup_mask >> k) & 1u;
+            if (k == 0) {
+#pragma unroll
+                for (int m = 0; m < S; ++m) {
+                    const int px = (m & 1) ? (pk[m >> 1] >> 16) : (pk[m >> 1] & 0xffffu);
+                    yq[px] = fmaf(g[m], hin, y0[m]);
+                }
+            } else if (!dup) {
+#pragma unroll
+                for (int m = 0; m < S; ++m) {
+                    const int px = (m & 1) ? (pk[m >> 1] >> 16) : (pk[m >> 1] & 0xffffu);
+                    yq[px] += fmaf(g[m], hin, y0[m]);
+                }
+            } else {
+#pragma unroll
+                for (int m = 0; m < S; ++m) {
+                    const int px = (m & 1) ? (pk[m >> 1] >> 16) : (pk[m >> 1] & 0xffffu);
+                    atomicAdd(yq + px, fmaf(g[m], hin, y0[m]));
+                }
+            }
+        }
+        // ---- merged planes of this round -> global (PP planes are contiguous in y)
+        fence_proxy_async_smem();
+        __syncthreads();
+        if (tid == 0) {
+            bulk_s2g(p.y + plane0 * L, sy, TOK * sizeof(float));
+            bulk_commit();
+        }
+    }
+    if (tid == 0) bulk_wait_all<0>();
+}
+
+}  // namespace
+
+size_t ss2d_fused_fwd_smem(int L, int es, int xb) { return FwdLayout(L, es, xb).total; }
+
+template <typename in_t>
+static cudaError_t launch_t(const FusedArgs& a, cudaStream_t st) {
+    auto kern = ss2d_fwd_kernel<in_t>;
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e != cudaSuccess) return e;
+        configured = true;
+    }
+    static int sms = 0;
+    if (!sms) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    }
+    const size_t smem = FwdLayout(a.L, sizeof(in_t), a.xb).total;
+    const int grid = a.rounds < sms ? a.rounds : sms;
+    kern<<<grid, NT, smem, st>>>(a);
+    note_launch();
+    return cudaGetLastError();
+}
+
+cudaError_t launch_ss2d_fused_fwd(const FusedArgs& a, int in_dtype, cudaStream_t st) {
+    if (in_dtype == TRAMBA_F32) return launch_t<float>(a, st);
+    if (in_dtype == TRAMBA_BF16) return launch_t<__nv_bfloat16>(a, st);
+    return cudaErrorInvalidValue;
+}
+
+}  // namespace tramba

@@ -36,7 +36,7 @@ class _DCT2DSplit(torch.autograd.Function):
         wy, wx = wy.contiguous().float(), wx.contiguous().float()
         high = x.new_empty((B, C, H // 2, W // 2))
         low = x.new_empty((B, C, H // 2, W // 2))
-        with torch.cuda.device(x.device):
+        with torch.cuda.device(x.device), _lib.timed("dct2d_fwd", x.numel() * 6):
             _lib.check(_lib.lib.tramba_dct2d_fwd(x.data_ptr(), wy.data_ptr(), wx.data_ptr(), high.data_ptr(),
                                                  low.data_ptr(), B * C, H, W, _stream()))
         ctx.save_for_backward(wy, wx)
@@ -51,7 +51,7 @@ class _DCT2DSplit(torch.autograd.Function):
         B, C = ghigh.shape[:2]
         ghigh, glow = ghigh.contiguous().float(), glow.contiguous().float()
         gx = ghigh.new_empty((B, C, H, W))
-        with torch.cuda.device(ghigh.device):
+        with torch.cuda.device(ghigh.device), _lib.timed("dct2d_bwd", gx.numel() * 6):
             _lib.check(_lib.lib.tramba_dct2d_bwd(ghigh.data_ptr(), glow.data_ptr(), wy.data_ptr(), wx.data_ptr(),
                                                  gx.data_ptr(), B * C, H, W, _stream()))
         return gx.to(ctx.in_dtype), None, None

@@ -1,0 +1,118 @@
+"""Fused SS2D core: CrossScan* -> SelectiveScanOflex -> CrossMerge* as ONE autograd operator
+over the image-ordered operands (Models/vmamba.py:231-259 without the permuted copies).
+
+    y = ss2d_core_fused(x, dts, Bs, Cs, A, Ds, delta_bias, order, param)
+
+    x   (B, D, H, W)      dts (B, K, D, L)      Bs, Cs (B, K, L)      A, Ds, delta_bias (K*D) fp32
+    y   (B, D, L) fp32 -- what CrossMerge*.apply(SelectiveScanOflex.apply(...)) returns
+
+The forward is one kernel (tramba_ss2d_fused_fwd), the backward one kernel per staging mode
+(tramba_ss2d_fused_bwd) plus the sum of the per-direction input gradients.  N = 1 only; shapes the
+fused kernels do not cover are reported by `supported()` and run through the un-fused operators.
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _lib
+
+_DTYPE = {torch.float32: _lib.F32, torch.bfloat16: _lib.BF16}
+_idx_cache = {}
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def order_table16_host(order, H, param=0):
+    K = _lib.lib.tramba_order_num_directions(order)
+    _lib.check(min(K, 0))
+    t = np.empty((K, H * H), dtype=np.uint16)
+    _lib.check(_lib.lib.tramba_order_table16(order, H, H, param, t.ctypes.data))
+    return t
+
+
+def _idx16(order, H, param, device):
+    key = (order, H, param, device)
+    hit = _idx_cache.get(key)
+    if hit is None:
+        t = order_table16_host(order, H, param)
+        hit = torch.from_numpy(t.view(np.int16)).to(device)
+        _idx_cache[key] = hit
+    return hit
+
+
+def supported(order, K, D, H, W, N, dtype, need_bwd=True):
+    code = _DTYPE.get(dtype)
+    if code is None or H != W:
+        return False
+    return bool(_lib.lib.tramba_ss2d_fused_supported(order, K, D, H, W, N, code, int(need_bwd)))
+
+
+def _ptr(t):
+    return None if t is None else t.data_ptr()
+
+
+def _c16(t):
+    t = t.contiguous()
+    return t if t.data_ptr() % 16 == 0 else t.clone()
+
+
+class SS2DCoreFused(torch.autograd.Function):
+    @staticmethod
+    @torch.amp.custom_fwd(device_type="cuda")
+    def forward(ctx, x, dts, Bs, Cs, A, Ds, delta_bias, order, param, delta_softplus=True):
+        B, D, H, W = x.shape
+        K = dts.shape[1]
+        L = H * W
+        dt = x.dtype
+        x, dts = _c16(x), _c16(dts.to(dt))
+        Bs, Cs = _c16(Bs.to(dt)), _c16(Cs.to(dt))
+        A = A.contiguous().float()
+        Ds = None if Ds is None else Ds.contiguous().float()
+        delta_bias = None if delta_bias is None else delta_bias.contiguous().float()
+        idx = _idx16(order, H, param, x.device)
+        y = torch.empty((B, D, L), device=x.device, dtype=torch.float32)
+        es = x.element_size()
+        nbytes = (B * D * L) * (es + 4) + dts.numel() * es + 2 * Bs.numel() * es   # fused core
+        with torch.cuda.device(x.device), _lib.timed("ss2d_fused_fwd", nbytes):
+            _lib.check(_lib.lib.tramba_ss2d_fused_fwd(
+                x.data_ptr(), dts.data_ptr(), Bs.data_ptr(), Cs.data_ptr(), A.data_ptr(), _ptr(Ds),
+                _ptr(delta_bias), idx.data_ptr(), y.data_ptr(), order, K, B, D, H, W, 1, _DTYPE[dt],
+                int(bool(delta_softplus)), _stream()))
+        ctx.save_for_backward(x, dts, Bs, Cs, A, Ds, delta_bias, idx)
+        ctx.meta = (order, K, B, D, H, W, bool(delta_softplus))
+        return y
+
+    @staticmethod
+    @torch.amp.custom_bwd(device_type="cuda")
+    def backward(ctx, dy):
+        x, dts, Bs, Cs, A, Ds, delta_bias, idx = ctx.saved_tensors
+        order, K, B, D, H, W, softplus = ctx.meta
+        L = H * W
+        dt = x.dtype
+        dy = _c16(dy.float())
+        dxk = torch.empty((B, K, D, L), device=x.device, dtype=dt)
+        ddts = torch.empty((B, K, D, L), device=x.device, dtype=dt)
+        dBs = torch.empty((B, K, L), device=x.device, dtype=torch.float32)
+        dCs = torch.empty((B, K, L), device=x.device, dtype=torch.float32)
+        dA = torch.empty((B, K * D), device=x.device, dtype=torch.float32)
+        dD = None if Ds is None else torch.empty_like(dA)
+        db = None if delta_bias is None else torch.empty_like(dA)
+        es = x.element_size()
+        # algorithmic bytes: per direction read x, delta, dy; write du, ddelta; B/C in, dB/dC out
+        nbytes = K * B * D * L * (4 * es + 4) + 2 * Bs.numel() * (es + 4)
+        with torch.cuda.device(x.device), _lib.timed("ss2d_fused_bwd", nbytes):
+            _lib.check(_lib.lib.tramba_ss2d_fused_bwd(
+                x.data_ptr(), dts.data_ptr(), Bs.data_ptr(), Cs.data_ptr(), A.data_ptr(), _ptr(Ds),
+                _ptr(delta_bias), idx.data_ptr(), dy.data_ptr(), dxk.data_ptr(), ddts.data_ptr(), dBs.data_ptr(),
+                dCs.data_ptr(), dA.data_ptr(), _ptr(dD), _ptr(db), order, K, B, D, H, W, 1, _DTYPE[dt],
+                int(softplus), _stream()))
+        dx = dxk.sum(dim=1, dtype=torch.float32).to(dt).view(B, D, H, W)
+        return (dx, ddts, dBs.to(dt), dCs.to(dt), dA.sum(0), None if dD is None else dD.sum(0),
+                None if db is None else db.sum(0), None, None, None)
+
+
+def ss2d_core_fused(x, dts, Bs, Cs, A, Ds, delta_bias, order, param=0, delta_softplus=True):
+    return SS2DCoreFused.apply(x, dts, Bs, Cs, A, Ds, delta_bias, order, param, delta_softplus)

@@ -89,7 +89,7 @@ def cross_scan(x, order, param=0):
     x = x.contiguous()
     K, plan = _order_plan(order, H, param, x.device)
     xs = x.new_empty((B, K, C, H * W))
-    with torch.cuda.device(x.device):
+    with torch.cuda.device(x.device), _lib.timed("cross_scan", (1 + K) * x.numel() * x.element_size()):
         _lib.check(_lib.lib.tramba_cross_scan(x.data_ptr(), xs.data_ptr(), plan.data_ptr(), order, K, B, C, H, W,
                                               _dtype_code(x), _stream()))
     return xs
@@ -105,7 +105,7 @@ def cross_merge(ys, order, H, W, param=0):
     if K2 != K:
         raise ValueError(f"tramba_b200: order expects K={K2} directions, got {K}")
     y = ys.new_empty((B, D, H * W))
-    with torch.cuda.device(ys.device):
+    with torch.cuda.device(ys.device), _lib.timed("cross_merge", (1 + K) * y.numel() * y.element_size()):
         _lib.check(_lib.lib.tramba_cross_merge(ys.data_ptr(), y.data_ptr(), plan.data_ptr(), order, K, B, D, H, W,
                                                _dtype_code(ys), _stream()))
     return y
@@ -142,6 +142,8 @@ def _make_pair(name, order, param_of):
 
     Scan.__name__ = Scan.__qualname__ = "CrossScan" + name
     Merge.__name__ = Merge.__qualname__ = "CrossMerge" + name
+    Scan.tramba_order = Merge.tramba_order = order            # lets SS2D route the pair to the fused core
+    Scan.tramba_param = Merge.tramba_param = staticmethod(param_of)
     return Scan, Merge
 
 

@@ -71,7 +71,9 @@ def fwd(u, delta, A, B, C, D, delta_bias, delta_softplus, nrows, oflex=True):
     out = torch.empty((batch, dim, L), device=u.device, dtype=torch.float32 if oflex else u.dtype)
     x = torch.empty(max(1, _lib.lib.tramba_sscan_ckpt_elems(batch, dim, L, N, in_dt)),
                     device=u.device, dtype=torch.float32)
-    with torch.cuda.device(u.device):
+    # algorithmic bytes: read u, delta, B, C; write out
+    nbytes = u.numel() * (2 * u.element_size() + out.element_size()) + 2 * B.numel() * B.element_size()
+    with torch.cuda.device(u.device), _lib.timed("sscan_fwd", nbytes):
         _lib.check(_lib.lib.tramba_sscan_fwd(
             u.data_ptr(), delta.data_ptr(), A.data_ptr(), B.data_ptr(), C.data_ptr(), _ptr(D), _ptr(delta_bias),
             out.data_ptr(), x.data_ptr(), batch, dim, L, N, G, in_dt, _code(out), int(bool(delta_softplus)),
@@ -92,7 +94,10 @@ def bwd(u, delta, A, B, C, D, delta_bias, dout, x, delta_softplus, nrows):
     dC = torch.empty(C.shape, device=u.device, dtype=torch.float32)
     dD = None if D is None else torch.empty_like(D)
     dbias = None if delta_bias is None else torch.empty_like(delta_bias)
-    with torch.cuda.device(u.device):
+    # algorithmic bytes: read u, delta, dout, B, C; write du, ddelta, dB, dC (fp32)
+    nbytes = (u.numel() * (4 * u.element_size() + dout.element_size())
+              + 2 * B.numel() * (B.element_size() + 4))
+    with torch.cuda.device(u.device), _lib.timed("sscan_bwd", nbytes):
         _lib.check(_lib.lib.tramba_sscan_bwd(
             u.data_ptr(), delta.data_ptr(), A.data_ptr(), B.data_ptr(), C.data_ptr(), _ptr(D), _ptr(delta_bias),
             dout.data_ptr(), x.data_ptr(), du.data_ptr(), ddelta.data_ptr(), dA.data_ptr(), dB.data_ptr(),

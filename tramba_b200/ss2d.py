@@ -14,7 +14,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from . import ops
+from . import fused, ops
 
 
 class Linear2d(nn.Linear):
@@ -96,6 +96,9 @@ class SS2D(nn.Module):
         # bound like the reference's partial(forward_corev2, SelectiveScan=SelectiveScanOflex, ...)
         # (Models/vmamba.py:65-66); tests swap in the CPU oracle operator here
         self.selective_scan = ops.SelectiveScanOflex
+        # fused=True: run scan -> selective scan -> merge as one kernel on image-ordered operands when the
+        # (scan, merge) pair is one of ours and the shape is covered; False: the reference's op-by-op path
+        self.fused = kwargs.get("fused", True)
         Linear = Linear2d if channel_first else nn.Linear
         LayerNorm = LayerNorm2d if channel_first else nn.LayerNorm
 
@@ -118,8 +121,43 @@ class SS2D(nn.Module):
             self.A_logs = _a_log_init(d_state, d_inner, copies=k_group)                            # (K*D, N)
             self.Ds = _d_init(d_inner, copies=k_group)                                             # (K*D)
 
+    def _fused_order(self, x):
+        """(order, param) when this call can take the fused kernel, else None."""
+        order = getattr(self.scan, "tramba_order", None)
+        if (not self.fused or order is None or getattr(self.merge, "tramba_order", None) != order
+                or self.selective_scan is not ops.SelectiveScanOflex or not x.is_cuda):
+            return None
+        B, D, H, W = x.shape
+        K, N = self.k_group, self.A_logs.shape[1]
+        if not fused.supported(order, K, D, H, W, N, x.dtype, need_bwd=torch.is_grad_enabled()):
+            return None
+        return order, self.scan.tramba_param(H)
+
+    def forward_core_fused(self, x, order, param):
+        """Same function as forward_core.  x_proj / dt_proj are per-token linear maps, so they commute
+        with the cross-scan gather: they are evaluated once on the image-ordered map (one dense 1x1
+        conv instead of K grouped ones on the K-times larger xs), and the fused kernel applies the
+        scan order to x, delta, B and C through its shared-memory addressing."""
+        B, D, H, W = x.shape
+        K, D, R = self.dt_projs_weight.shape
+        N = self.A_logs.shape[1]
+        L = H * W
+        xf = x.contiguous().view(B, D, L)
+        x_dbl = F.conv1d(xf, self.x_proj_weight.view(-1, D, 1), bias=None).view(B, K, R + 2 * N, L)
+        dts, Bs, Cs = torch.split(x_dbl, [R, N, N], dim=2)
+        dts = F.conv1d(dts.contiguous().view(B, -1, L), self.dt_projs_weight.view(K * D, -1, 1), groups=K)
+        As = -torch.exp(self.A_logs.to(torch.float)).view(-1)
+        y = fused.ss2d_core_fused(x, dts.view(B, K, D, L), Bs.reshape(B, K, L), Cs.reshape(B, K, L), As,
+                                  self.Ds.to(torch.float), self.dt_projs_bias.view(-1).to(torch.float), order, param)
+        y = self.out_norm(y.view(B, -1, H, W)) if self.channel_first else \
+            self.out_norm(y.transpose(1, 2).contiguous().view(B, H, W, -1))
+        return y.to(x.dtype)
+
     def forward_core(self, x):
         """Models/vmamba.py:231-273 (force_fp32=False, no_einsum=True, ssoflex=True)."""
+        route = self._fused_order(x)
+        if route is not None:
+            return self.forward_core_fused(x, *route)
         B, D, H, W = x.shape
         D, N = self.A_logs.shape
         K, D, R = self.dt_projs_weight.shape
