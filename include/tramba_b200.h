@@ -140,26 +140,28 @@ TRAMBA_API int tramba_sscan_bwd(const void* u, const void* delta, const float* A
  * adjoint (backward), for d_state N = 1 (every SS2D of Tramba-V).  Replaces the composition in
  * SS2Dv2.forward_corev2, Models/vmamba.py:231-259, i.e. CrossScan*.apply (:231) ->
  * SelectiveScanOflex.apply (:255-257) -> CrossMerge*.apply (:259), without materialising the
- * permuted copies xs / ys.  All operands are in IMAGE order (the per-token x_proj / dt_proj
- * commute with the gather and are evaluated once on the un-permuted map by the host):
- *   x      (B, D, L)        in_dtype      L = H*W, square maps
- *   dts    (B, K, D, L)     in_dtype      pre-softplus delta of direction k at each pixel
- *   Bs, Cs (B, K, L)        in_dtype
- *   A, Dp, delta_bias (K*D) fp32          Dp / delta_bias may be NULL
- *   idx16  (K, L)           uint16, device: pixel visited by token t of direction k
- *                           (tramba_order_table16; bit-exact with the reference generators)
- *   y      (B, D, L)        fp32          merged output (the oflex=True contract)
+ * permuted copies xs / ys of the feature map.
+ *   x      (B, D, L)        in_dtype   IMAGE order (L = H*W, square maps); gathered in shared memory
+ *   dts    (B, K, D, L)     in_dtype   scan order: the dt_proj output, vmamba.py:236
+ *   Bs, Cs (B, K, L)        in_dtype   scan order
+ *   A, Dp, delta_bias (K*D) fp32       Dp / delta_bias may be NULL
+ *   idx16  (K, L)           uint16, device: SKEWED pixel p + 2*(p >> 6) of token t of direction k
+ *                           (tramba_order_table16_skewed; tramba_order_table16 is the plain table,
+ *                           bit-exact with the reference generators)
+ *   y      (B, D, L)        fp32       IMAGE order, merged over the K directions (oflex=True contract)
  * Supported: order STD / DILATION / WINDOW / LINE, N == 1, L = 18 * 2^m <= 9216 (H = 12, 24, 48,
  * 96), D a multiple of 512*18/L, and shared-memory fit (tramba_ss2d_fused_supported says which;
  * everything else runs through the un-fused entry points above).  Helix-line directions add
  * duplicate hits of a pixel with shared-memory fp32 atomics, so their merged sums are
  * order-nondeterministic at rounding level, like the reference's CUDA scatter_add_.
- * Backward outputs: dxk (B, K, D, L) in_dtype = per-direction du scattered back to image order
- * (the caller sums over K); ddts (B, K, D, L) in_dtype; dBs, dCs (B, K, L) fp32 (zeroed here,
- * accumulated over channels with vector reds); dA_part, dD_part, dbias_part (B, K*D) fp32
- * partial sums over L (the caller sums over B; no atomics).
+ * Backward: dy (B, D, L) fp32 image order in; du (B, K, D, L) in_dtype, scan order = the gradient
+ * w.r.t. xs (the caller folds it back with tramba_cross_merge: dx = CrossScan.backward(du));
+ * ddts (B, K, D, L) in_dtype scan order; dBs, dCs (B, K, L) fp32 (zeroed here, accumulated over
+ * channels with vector reds); dA_part, dD_part, dbias_part (B, K*D) fp32 partial sums over L
+ * (the caller sums over B; no atomics).
  * -------------------------------------------------------------------------------------- */
 TRAMBA_API int tramba_order_table16(int order, int H, int W, int param, uint16_t* idx_out /* K*L, host */);
+TRAMBA_API int tramba_order_table16_skewed(int order, int H, int W, int param, uint16_t* idx_out /* K*L, host */);
 TRAMBA_API int tramba_ss2d_fused_supported(int order, int K, int D, int H, int W, int N, int in_dtype,
                                            int need_bwd);
 TRAMBA_API int tramba_ss2d_fused_fwd(const void* x, const void* dts, const void* Bs, const void* Cs,
@@ -168,7 +170,7 @@ TRAMBA_API int tramba_ss2d_fused_fwd(const void* x, const void* dts, const void*
                                      int W, int N, int in_dtype, int delta_softplus, void* stream);
 TRAMBA_API int tramba_ss2d_fused_bwd(const void* x, const void* dts, const void* Bs, const void* Cs,
                                      const float* A, const float* Dp, const float* delta_bias,
-                                     const uint16_t* idx16, const float* dy, void* dxk, void* ddts, float* dBs,
+                                     const uint16_t* idx16, const float* dy, void* du, void* ddts, float* dBs,
                                      float* dCs, float* dA_part, float* dD_part, float* dbias_part, int order,
                                      int K, int B, int D, int H, int W, int N, int in_dtype, int delta_softplus,
                                      void* stream);

@@ -1,6 +1,7 @@
-"""float64 CPU statement of the fused SS2D core on IMAGE-ordered operands (test infrastructure):
-gather x / delta / B / C into scan order with the oracle's order table, run the oracle selective
-scan, scatter-add every token back to its pixel (Models/vmamba.py:231-259 as one function)."""
+"""float64 CPU statement of the fused SS2D core (test infrastructure): gather the image-ordered x
+into scan order with the oracle's order table, run the oracle selective scan on it with the
+scan-ordered delta / B / C, scatter-add every token back to its pixel (Models/vmamba.py:231-259 as
+one function)."""
 import numpy as np
 import torch
 
@@ -29,7 +30,7 @@ class _Sel(torch.autograd.Function):
 
 
 def fused_core_oracle(fam, H, tensors, dy=None):
-    """tensors = [x (B,D,H,H), dts (B,K,D,L), Bs (B,K,L), Cs (B,K,L), A (K*D), Ds (K*D), bias (K*D)].
+    """tensors = [x (B,D,H,H) image order, dts (B,K,D,L), Bs (B,K,L), Cs (B,K,L) scan order, A, Ds, bias (K*D)].
     Returns (y (B,D,L) float64, [grads wrt the 7 tensors] or None)."""
     x, dts, Bs, Cs, A, Ds, bias = [t.detach().double().requires_grad_(True) for t in tensors]
     B, D = x.shape[:2]
@@ -37,11 +38,10 @@ def fused_core_oracle(fam, H, tensors, dy=None):
     L = H * H
     tab = torch.from_numpy(so.order_table(fam, H, param_of(fam, H)).astype(np.int64))  # (K, L)
     t4 = tab.view(1, K, 1, L).expand(B, K, D, L)
-    t3 = tab.view(1, K, L).expand(B, K, L)
     xs = x.view(B, 1, D, L).expand(B, K, D, L).gather(3, t4)
-    dsc = dts.gather(3, t4)
-    Bsc = Bs.gather(2, t3).view(B, K, 1, L)
-    Csc = Cs.gather(2, t3).view(B, K, 1, L)
+    dsc = dts
+    Bsc = Bs.view(B, K, 1, L)
+    Csc = Cs.view(B, K, 1, L)
     ys = _Sel.apply(xs.reshape(B, K * D, L), dsc.reshape(B, K * D, L), A.view(K * D, 1), Bsc, Csc, Ds, bias)
     # merge = transpose of the gather: every token is added to its pixel
     y = torch.zeros(B, D, L, dtype=torch.float64).scatter_add(

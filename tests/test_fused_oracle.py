@@ -20,16 +20,13 @@ def test_image_order_statement_equals_op_by_op_oracle(fam, K, H):
     A, Ds, bias = -(0.2 + torch.rand(K * D, generator=g)), torch.randn(K * D, generator=g), torch.randn(K * D, generator=g)
     dy = torch.randn(B, D, L, generator=g)
     y, grads = fused_core_oracle(fam, H, [x, dts, Bs, Cs, A, Ds, bias], dy)
-    # op-by-op: gather the image-ordered delta / B / C with the pinned table, then the pinned operators
+    # op-by-op: the pinned operators on the same scan-ordered delta / B / C
     tab = so.order_table(fam, H, param_of(fam, H))
     Scan, Merge = make_pair(fam)
     xr = x.clone().requires_grad_(True)
     xs = Scan.apply(xr)
-    t = torch.from_numpy(tab.astype(np.int64))
-    dsc = dts.gather(3, t.view(1, K, 1, L).expand(B, K, D, L))
-    Bsc = Bs.gather(2, t.view(1, K, L).expand(B, K, L)).view(B, K, 1, L)
-    Csc = Cs.gather(2, t.view(1, K, L).expand(B, K, L)).view(B, K, 1, L)
-    ys = OracleSelectiveScan.apply(xs.view(B, K * D, L), dsc.reshape(B, K * D, L), A.view(-1, 1), Bsc, Csc, Ds, bias,
+    Bsc, Csc = Bs.view(B, K, 1, L), Cs.view(B, K, 1, L)
+    ys = OracleSelectiveScan.apply(xs.view(B, K * D, L), dts.reshape(B, K * D, L), A.view(-1, 1), Bsc, Csc, Ds, bias,
                                    True, 1, 1, True)
     y2 = Merge.apply(ys.view(B, K, D, H, H))
     y2.backward(dy)

@@ -46,6 +46,7 @@ def main():
     ap.add_argument("--reps", type=int, default=20)
     ap.add_argument("--nstate", type=int, default=1)
     ap.add_argument("--only", default="")
+    ap.add_argument("--fused-only", action="store_true", help="time only the fused SS2D core kernels")
     a = ap.parse_args()
     dt = torch.float32 if a.dtype == "f32" else torch.bfloat16
     es = 4 if a.dtype == "f32" else 2
@@ -66,6 +67,38 @@ def main():
         Cm = torch.randn(B, K, N, L, device=dev, dtype=dt)
         Dp = torch.ones(K * D, device=dev)
         bias = torch.randn(K * D, device=dev) - 3
+        r = dict(site=name, B=B, K=K, D=D, H=H, dtype=a.dtype, N=N)
+        from tramba_b200 import fused
+        if N == 1 and fused.supported(order, K, D, H, H, 1, dt, need_bwd=False):
+            dts_img = delta.view(B, K, D, L)
+            Bi, Ci = Bm.view(B, K, L), Cm.view(B, K, L)
+            Af = A.view(-1)
+            idx = fused._idx16(order, H, param, dev)
+            y = torch.empty(B, D, L, device=dev)
+            code = _lib.F32 if a.dtype == "f32" else _lib.BF16
+            import ctypes
+            st = lambda: ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+            ffwd = lambda: _lib.check(_lib.lib.tramba_ss2d_fused_fwd(
+                x.data_ptr(), dts_img.data_ptr(), Bi.data_ptr(), Ci.data_ptr(), Af.data_ptr(), Dp.data_ptr(),
+                bias.data_ptr(), idx.data_ptr(), y.data_ptr(), order, K, B, D, H, H, 1, code, 1, st()))
+            t_ff = timeit(ffwd, a.reps, flush)
+            by_ff = B * D * L * (es + 4) + K * B * D * L * es + 2 * B * K * L * es
+            r.update(ffwd_us=t_ff * 1e6, ffwd_gbs=by_ff / t_ff / 1e9, ffwd_gtok=K * B * D * L / t_ff / 1e9)
+            if fused.supported(order, K, D, H, H, 1, dt, need_bwd=True):
+                dy = torch.randn(B, D, L, device=dev)
+                dxk, ddt = torch.empty_like(dts_img), torch.empty_like(dts_img)
+                dBs, dCs = torch.empty(B, K, L, device=dev), torch.empty(B, K, L, device=dev)
+                pA, pD, pb = (torch.empty(B, K * D, device=dev) for _ in range(3))
+                fbwd = lambda: _lib.check(_lib.lib.tramba_ss2d_fused_bwd(
+                    x.data_ptr(), dts_img.data_ptr(), Bi.data_ptr(), Ci.data_ptr(), Af.data_ptr(), Dp.data_ptr(),
+                    bias.data_ptr(), idx.data_ptr(), dy.data_ptr(), dxk.data_ptr(), ddt.data_ptr(), dBs.data_ptr(),
+                    dCs.data_ptr(), pA.data_ptr(), pD.data_ptr(), pb.data_ptr(), order, K, B, D, H, H, 1, code, 1, st()))
+                t_fb = timeit(fbwd, a.reps, flush)
+                by_fb = K * B * D * L * (4 * es + 4) + 2 * B * K * L * (es + 4)
+                r.update(fbwd_us=t_fb * 1e6, fbwd_gbs=by_fb / t_fb / 1e9, fbwd_gtok=K * B * D * L / t_fb / 1e9)
+        if a.fused_only:
+            print(json.dumps({k: (round(v, 1) if isinstance(v, float) else v) for k, v in r.items()}), flush=True)
+            continue
         xs = tramba_b200.cross_scan(x, order, param)
         u = xs.view(B, K * D, L)
         out, ck = ext.fwd(u, delta, A, Bm, Cm, Dp, bias, True, 1, True)
@@ -80,7 +113,7 @@ def main():
         by_fwd = K * E * (2 * es + 4) + 2 * B * K * N * L * es
         by_bwd = K * E * (2 * es + 4) + K * E * 2 * es + 2 * B * K * N * L * (es + 4)
         by_merge = (1 + K) * E * 4
-        r = dict(site=name, B=B, K=K, D=D, H=H, dtype=a.dtype, N=N,
+        r.update(
                  scan_gbs=by_scan / t_scan / 1e9, fwd_gbs=by_fwd / t_fwd / 1e9, bwd_gbs=by_bwd / t_bwd / 1e9,
                  merge_gbs=by_merge / t_merge / 1e9,
                  scan_us=t_scan * 1e6, fwd_us=t_fwd * 1e6, bwd_us=t_bwd * 1e6, merge_us=t_merge * 1e6)

@@ -32,6 +32,7 @@ SIGNATURES = {
     "tramba_sscan_bwd": (_i, [_vp, _vp, _fp, _vp, _vp, _fp, _fp, _vp, _fp, _vp, _vp, _fp, _fp, _fp, _fp, _fp]
                          + [_i] * 8 + [_vp]),
     "tramba_order_table16": (_i, [_i, _i, _i, _i, _vp]),
+    "tramba_order_table16_skewed": (_i, [_i, _i, _i, _i, _vp]),
     "tramba_ss2d_fused_supported": (_i, [_i] * 8),
     "tramba_ss2d_fused_fwd": (_i, [_vp, _vp, _vp, _vp, _fp, _fp, _fp, _vp, _fp] + [_i] * 9 + [_vp]),
     "tramba_ss2d_fused_bwd": (_i, [_vp, _vp, _vp, _vp, _fp, _fp, _fp, _vp, _fp, _vp, _vp, _fp, _fp, _fp, _fp, _fp]

@@ -23,7 +23,6 @@ cudaError_t launch_dct2d_fwd(const float* x, const float* wy, const float* wx, f
 cudaError_t launch_dct2d_bwd(const float* ghigh, const float* glow, const float* wy, const float* wx, float* gx,
                              int planes, int H, int W, cudaStream_t st);
 
-size_t ss2d_fused_bwd_smem(int L, int es, int xb, bool dup);
 bool ss2d_fused_bwd_fits(int L, int es, uint32_t dup_mask, int K);
 
 static int elem_size(int dtype) {
@@ -294,6 +293,17 @@ extern "C" int tramba_order_table16(int order, int H, int W, int param, uint16_t
     return TRAMBA_OK;
 }
 
+// The table the fused kernels consume: skewed shared-memory position p + 2*(p >> 6) of each token's pixel.
+extern "C" int tramba_order_table16_skewed(int order, int H, int W, int param, uint16_t* idx_out) {
+    int rc = tramba_order_table16(order, H, W, param, idx_out);
+    if (rc != TRAMBA_OK) return rc;
+    const int K = tramba_order_num_directions(order);
+    const size_t n = static_cast<size_t>(K) * H * W;
+    if (fused_skew(H * W - 1) > 65535) return TRAMBA_E_LIMIT;
+    for (size_t i = 0; i < n; ++i) idx_out[i] = static_cast<uint16_t>(fused_skew(idx_out[i]));
+    return TRAMBA_OK;
+}
+
 static uint32_t fused_dup_mask(int order) { return order == TRAMBA_ORDER_LINE ? 0xF0u : 0u; }
 
 static int fused_geometry(FusedArgs& a, int order, int K, int B, int D, int H, int W, int N) {
@@ -351,11 +361,11 @@ extern "C" int tramba_ss2d_fused_fwd(const void* x, const void* dts, const void*
 
 extern "C" int tramba_ss2d_fused_bwd(const void* x, const void* dts, const void* Bs, const void* Cs,
                                      const float* A, const float* Dp, const float* delta_bias,
-                                     const uint16_t* idx16, const float* dy, void* dxk, void* ddts, float* dBs,
+                                     const uint16_t* idx16, const float* dy, void* du, void* ddts, float* dBs,
                                      float* dCs, float* dA_part, float* dD_part, float* dbias_part, int order,
                                      int K, int B, int D, int H, int W, int N, int in_dtype, int delta_softplus,
                                      void* stream) {
-    if (!x || !dts || !Bs || !Cs || !A || !idx16 || !dy || !dxk || !ddts || !dBs || !dCs || !dA_part)
+    if (!x || !dts || !Bs || !Cs || !A || !idx16 || !dy || !du || !ddts || !dBs || !dCs || !dA_part)
         return TRAMBA_E_NULL;
     if ((Dp && !dD_part) || (delta_bias && !dbias_part)) return TRAMBA_E_NULL;
     if (in_dtype != TRAMBA_F32 && in_dtype != TRAMBA_BF16) return TRAMBA_E_DTYPE;
@@ -364,7 +374,7 @@ extern "C" int tramba_ss2d_fused_bwd(const void* x, const void* dts, const void*
     int rc = fused_geometry(a, order, K, B, D, H, W, N);
     if (rc != TRAMBA_OK) return rc;
     if (!aligned(x, 16) || !aligned(dts, 16) || !aligned(Bs, 16) || !aligned(Cs, 16) || !aligned(dy, 16) ||
-        !aligned(dxk, 16) || !aligned(ddts, 16) || !aligned(dBs, 16) || !aligned(dCs, 16) || !aligned(idx16, 4))
+        !aligned(du, 16) || !aligned(ddts, 16) || !aligned(dBs, 16) || !aligned(dCs, 16) || !aligned(idx16, 4))
         return TRAMBA_E_ALIGN;
     if (!ss2d_fused_bwd_fits(a.L, elem_size(in_dtype), a.dup_mask, K)) return TRAMBA_E_LIMIT;
     rc = check_device();
@@ -375,7 +385,7 @@ extern "C" int tramba_ss2d_fused_bwd(const void* x, const void* dts, const void*
     if (e == cudaSuccess) e = cudaMemsetAsync(dCs, 0, nbc, st);
     if (e != cudaSuccess) return cuda_rc(e);
     a.x = x, a.dts = dts, a.Bs = Bs, a.Cs = Cs, a.A = A, a.Dp = Dp, a.bias = delta_bias, a.idx = idx16;
-    a.dy = dy, a.dx = dxk, a.ddts = ddts, a.dBs = dBs, a.dCs = dCs, a.dA = dA_part, a.dD = dD_part,
+    a.dy = dy, a.du = du, a.ddts = ddts, a.dBs = dBs, a.dCs = dCs, a.dA = dA_part, a.dD = dD_part,
     a.dbias = dbias_part;
     a.softplus = delta_softplus ? 1 : 0;
     e = launch_ss2d_fused_bwd(a, in_dtype, st);

@@ -3,21 +3,28 @@
 //
 // Replaces the composition at Models/vmamba.py:231-259 (SS2Dv2.forward_corev2):
 //     xs = CrossScan(x); ...proj...; ys = SelectiveScanOflex(xs, dts, A, Bs, Cs, Ds, bias); y = CrossMerge(ys)
-// without ever materialising the permuted copies xs / ys in HBM.  The per-token projections
-// (x_proj, dt_proj) commute with the gather, so the host evaluates them once in IMAGE order and
-// the kernels read every operand in image order:
-//     x    (B, D, L)       dts (B, K, D, L)      Bs, Cs (B, K, L)   (d_state N = 1, the model's shape)
-// The scan order enters only through the uint16 pixel table idx[k][t] (bit-exact with the
-// reference generators): token t of direction k reads pixel idx[k][t] of the staged planes and
-// its output is accumulated into pixel idx[k][t] of the merged plane -- the permutation is pure
-// shared-memory addressing.
+// without ever materialising the permuted copies xs / ys of the feature map in HBM.
+//     x    (B, D, L)      IMAGE order  -- gathered by the kernel (u_t = x[pixel(k, t)])
+//     dts  (B, K, D, L)   scan order   -- the dt_proj output, as in the reference (vmamba.py:236)
+//     Bs, Cs (B, K, L)    scan order   -- (d_state N = 1, the model's shape)
+//     y    (B, D, L)      IMAGE order  -- every token's output is added to its pixel in shared memory
+// The scan order enters only through the uint16 table idx[k][t] = skew(pixel of token t in direction
+// k) (bit-exact with the reference generators before the skew): the permutation is pure
+// shared-memory addressing.  (The host evaluates the tiny x_proj once on the un-permuted map and
+// gathers its R+2 channels into scan order -- 1/25 of a cross-scan -- so delta/B/C arrive in scan
+// order exactly as the reference produces them.)
+//
+// Shared-memory planes that are accessed through the table (x, dy, the merged y) are stored
+// SKEWED: element p lives at skew(p) = p + 2*(p >> 6), i.e. one pad word per 32 words, so that the
+// lane stride of column-major / window / dilated walks (a multiple of 32 words un-skewed) spreads
+// over the banks.  They are staged with 4-byte cp.async copies (a bulk copy cannot skew);
+// everything read in token order (delta, B, C) and everything written in token order (du, ddelta)
+// moves with 1-D TMA bulk copies.
 //
 // Work decomposition.  A "round" is PP whole image planes (b, d0 .. d0+PP-1) = NT*S tokens per
 // direction; thread (q, j) owns the S consecutive tokens [j*S, (j+1)*S) of plane q's sequence.
 // The recurrence over a plane's L = TP*S tokens is a three-level scan: sequential fold in the
 // thread, shuffle scan over the warp, running combine over the TP/32 warps of the plane.
-// Planes, delta/B/C of the next direction and x of the next round arrive by 1-D TMA bulk copies
-// into double buffers while the current direction computes.
 #pragma once
 #include "common.cuh"
 
@@ -28,19 +35,19 @@ constexpr int kFusedNT = 512;   // threads per CTA (one CTA per SM, persistent o
 constexpr int kFusedTok = kFusedS * kFusedNT;  // tokens per round and direction (= PP * L)
 
 struct FusedArgs {
-    const void* x;        // (B, D, L)
-    const void* dts;      // (B, K, D, L) pre-softplus delta, image order
-    const void* Bs;       // (B, K, L)
-    const void* Cs;       // (B, K, L)
+    const void* x;        // (B, D, L) image order
+    const void* dts;      // (B, K, D, L) pre-softplus delta, scan order
+    const void* Bs;       // (B, K, L) scan order
+    const void* Cs;       // (B, K, L) scan order
     const float* A;       // (K*D)
     const float* Dp;      // (K*D) or null
     const float* bias;    // (K*D) or null
-    const uint16_t* idx;  // (K, L) pixel of token t in direction k
-    float* y;             // fwd out: (B, D, L) merged, fp32
+    const uint16_t* idx;  // (K, L) skewed pixel of token t in direction k
+    float* y;             // fwd out: (B, D, L) merged, fp32, image order
     // backward
-    const float* dy;      // (B, D, L) fp32
-    void* dx;             // (B, K, D, L) in_t: per-direction du scattered back to image order
-    void* ddts;           // (B, K, D, L) in_t
+    const float* dy;      // (B, D, L) fp32, image order
+    void* du;             // (B, K, D, L) in_t, scan order (the caller merges it back: dx = CrossMerge(du))
+    void* ddts;           // (B, K, D, L) in_t, scan order
     float* dBs;           // (B, K, L) fp32 (accumulated with red.global.add)
     float* dCs;           // (B, K, L) fp32
     float* dA;            // (B, K*D) partial sums over L (host sums over B)
@@ -57,6 +64,36 @@ struct FusedArgs {
 cudaError_t launch_ss2d_fused_fwd(const FusedArgs& a, int in_dtype, cudaStream_t st);
 cudaError_t launch_ss2d_fused_bwd(const FusedArgs& a, int in_dtype, cudaStream_t st);
 size_t ss2d_fused_fwd_smem(int L, int es, int xb);
+size_t ss2d_fused_bwd_smem(int L, int es, int xb);
+
+// skewed plane length in elements (element p lives at p + 2*(p >> 6); +2 keeps planes word-aligned)
+__host__ __device__ inline int fused_skew_len(int L) { return L + 2 * ((L + 63) >> 6) + 2; }
+__host__ __device__ inline int fused_skew(int p) { return p + ((p >> 6) << 1); }
+
+// ---- cp.async (4-byte) with mbarrier completion
+__device__ __forceinline__ void cp_async4(void* dst_smem, const void* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(dst_smem)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_arrive(uint64_t* bar) {
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// Stage `nplanes` contiguous global planes of `wpl` 32-bit words each into skewed shared planes
+// (`wsk` words apart): all NT threads take part; completion arrives on `bar` (count NT).
+// ES = element size: a 32-bit word holds 4/ES elements, and element p must land at p + 2*(p >> 6).
+template <int ES>
+__device__ __forceinline__ void stage_skewed(uint32_t* dst, const uint32_t* __restrict__ src, int nplanes, int wpl,
+                                             int wsk, uint64_t* bar, int tid, int nthreads) {
+    const int total = nplanes * wpl;
+    int q = tid / wpl, w = tid - q * wpl;  // incremental (q, w) walk: nthreads may exceed wpl
+    const int dq = nthreads / wpl, dw = nthreads - dq * wpl;
+    for (int e = tid; e < total; e += nthreads) {
+        cp_async4(dst + q * wsk + (ES == 2 ? w + (w >> 5) : w + ((w >> 6) << 1)), src + e);
+        q += dq, w += dw;
+        if (w >= wpl) w -= wpl, ++q;
+    }
+    cp_async_arrive(bar);
+}
 
 // Affine-map inclusive scan over `width` lanes (width = 32 or a power of two below).
 __device__ __forceinline__ void fused_scan(float& P, float& S, int sl, int width) {
@@ -84,6 +121,47 @@ __device__ __forceinline__ void fused_scan_rev(float& P, float& S, int sl, int w
             }
         }
     }
+}
+
+// S consecutive elements of a token-ordered shared array -> fp32 registers (S even).
+template <int CNT>
+__device__ __forceinline__ void load_tokens(const float* p, float (&v)[CNT]) {
+    const float2* q = reinterpret_cast<const float2*>(p);
+#pragma unroll
+    for (int i = 0; i < CNT / 2; ++i) {
+        const float2 t = q[i];
+        v[2 * i] = t.x, v[2 * i + 1] = t.y;
+    }
+}
+template <int CNT>
+__device__ __forceinline__ void load_tokens(const __nv_bfloat16* p, float (&v)[CNT]) {
+    const uint32_t* q = reinterpret_cast<const uint32_t*>(p);
+#pragma unroll
+    for (int i = 0; i < CNT / 2; ++i) {
+        const uint32_t t = q[i];
+        v[2 * i] = __uint_as_float(t << 16), v[2 * i + 1] = __uint_as_float(t & 0xffff0000u);
+    }
+}
+// elements 2*i and 2*i+1 of a token-ordered shared array
+__device__ __forceinline__ void load_pair(const float* p, int i, float& lo, float& hi) {
+    const float2 t = reinterpret_cast<const float2*>(p)[i];
+    lo = t.x, hi = t.y;
+}
+__device__ __forceinline__ void load_pair(const __nv_bfloat16* p, int i, float& lo, float& hi) {
+    const uint32_t t = reinterpret_cast<const uint32_t*>(p)[i];
+    lo = __uint_as_float(t << 16), hi = __uint_as_float(t & 0xffff0000u);
+}
+template <int CNT>
+__device__ __forceinline__ void store_tokens(float* p, const float (&v)[CNT]) {
+    float2* q = reinterpret_cast<float2*>(p);
+#pragma unroll
+    for (int i = 0; i < CNT / 2; ++i) q[i] = make_float2(v[2 * i], v[2 * i + 1]);
+}
+template <int CNT>
+__device__ __forceinline__ void store_tokens(__nv_bfloat16* p, const float (&v)[CNT]) {
+    __nv_bfloat162* q = reinterpret_cast<__nv_bfloat162*>(p);
+#pragma unroll
+    for (int i = 0; i < CNT / 2; ++i) q[i] = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
 }
 
 }  // namespace tramba

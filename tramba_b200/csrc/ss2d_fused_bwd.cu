@@ -1,22 +1,21 @@
 // Fused SS2D core, backward (sm_100a).  See ss2d_fused.cuh for the data model.
-// Replaces CrossMerge*.backward -> SelectiveScanOflex.backward -> CrossScan*.backward
-// (Models/SS2D/csms6s.py:25-31,45-55,914-923 and the _Dilation/_Window/_Line variants) for N = 1.
+// Replaces CrossMerge*.backward -> SelectiveScanOflex.backward of Models/SS2D/csms6s.py:45-55,914-923
+// (and the _Dilation/_Window/_Line variants) for N = 1: the gradient of the merged map is
+// gathered through the scan-order table in shared memory, so neither the K-fold copy of dy
+// (CrossMerge.backward = a cross-scan) nor xs is ever materialised.
 //
 // Work item = (b, k, block of RB = R*PP channels): the CTA walks the R rounds of the item, each
 // round = PP whole planes of direction k.  Nothing is stored by the forward: pass 1 re-runs the
 // forward fold AND the reverse fold of  E_t = a_t*(g_t + E_{t+1}),  g_t = C_t*dy_t,  dh_t = g_t + E_{t+1}
 // over the thread's S tokens (both are affine maps sharing the same product of a's), the two
 // carries come from a forward and a reverse scan over the plane's threads, pass 2 walks the
-// segment right-to-left for dh and left-to-right for h and emits
-//     du_t     = D*dy_t + dh_t*delta_t*B_t                      -> dx[b,k,d,pixel]   (summed over k by the host op)
-//     ddelta_t = dh_t*(A*a_t*h_{t-1} + B_t*u_t) * sigmoid(raw)  -> ddts[b,k,d,pixel]
-// through pixel-ordered shared staging planes that leave with one bulk store per round.
+// segment right-to-left for dh and left-to-right for h and emits, in scan order,
+//     du_t     = D*dy_t + dh_t*delta_t*B_t                      (the caller folds it back: dx = CrossMerge(du))
+//     ddelta_t = dh_t*(A*a_t*h_{t-1} + B_t*u_t) * sigmoid(raw)
+// through token-ordered shared staging that leaves with one bulk store per round.
 // dB_t = sum_d dh_t*delta_t*u_t and dC_t = sum_d dy_t*h_t are accumulated in registers over all
-// rounds of the item (same b, k), transposed to pixel order in shared memory and added to
-// global memory with coalesced vector reductions once per item.  dA, dD, ddelta_bias leave as
-// per-(b, row) partial sums (no atomics; the host sums over b).
-#include <type_traits>
-
+// rounds of the item (same b, k) and added to global memory once per item.  dA, dD, ddelta_bias
+// leave as per-(b, row) partial sums (no atomics; the host sums over b).
 #include "ss2d_fused.cuh"
 
 namespace tramba {
@@ -31,18 +30,19 @@ constexpr int NW = NT / 32;
 __host__ __device__ inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 struct BwdLayout {
-    size_t x, d, dy, b, c, o0, o1, tot, red, bar, total;
-    // stage_es: element size of the output staging planes (in_t for permutation directions, 4 for
-    // directions with duplicate pixels, whose hits are summed with fp32 shared atomics)
-    __host__ __device__ BwdLayout(int L, int es, int xb, int stage_es) {
+    size_t x, dy, d, b, c, o0, o1, tot, red, bar, total;
+    int lsk;
+    __host__ __device__ BwdLayout(int L, int es, int xb) {
+        lsk = fused_skew_len(L);
+        const int pp = TOK / L;
         size_t o = 0;
-        x = o, o += static_cast<size_t>(xb) * TOK * es;
+        x = o, o += align_up(static_cast<size_t>(xb) * pp * lsk * es, 16);
+        dy = o, o += align_up(static_cast<size_t>(xb) * pp * lsk * 4, 16);
         d = o, o += static_cast<size_t>(xb) * TOK * es;
-        dy = o, o += static_cast<size_t>(xb) * TOK * 4;
         b = o, o += align_up(static_cast<size_t>(L) * es, 16);
         c = o, o += align_up(static_cast<size_t>(L) * es, 16);
-        o0 = o, o += static_cast<size_t>(TOK) * stage_es;
-        o1 = o, o += static_cast<size_t>(TOK) * stage_es;
+        o0 = o, o += static_cast<size_t>(TOK) * es;
+        o1 = o, o += static_cast<size_t>(TOK) * es;
         tot = o, o += 2 * 2 * NW * sizeof(float2);
         red = o, o += 3 * NW * sizeof(float);
         bar = o, o += 8 * sizeof(uint64_t);
@@ -50,29 +50,25 @@ struct BwdLayout {
     }
 };
 
-__device__ __forceinline__ void red_add_v4(float* dst, float4 v) {
-    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
-                 : "memory");
-}
-
-template <typename in_t, bool DUP>
-__global__ void __launch_bounds__(NT, 1) ss2d_bwd_kernel(const FusedArgs p, const int kbase, const int nk,
-                                                         const int R) {
+template <typename in_t>
+__global__ void __launch_bounds__(NT, 1) ss2d_bwd_kernel(const FusedArgs p, const int R) {
     extern __shared__ __align__(128) unsigned char smem[];
-    using st_t = typename std::conditional<DUP, float, in_t>::type;
+    constexpr int ES = sizeof(in_t);
     const int L = p.L, K = p.K, D = p.D, TP = p.TP, PP = p.PP, XB = p.xb;
-    const BwdLayout lay(L, sizeof(in_t), XB, sizeof(st_t));
-    in_t* sx = reinterpret_cast<in_t*>(smem + lay.x);
-    in_t* sd = reinterpret_cast<in_t*>(smem + lay.d);
-    float* sdy = reinterpret_cast<float*>(smem + lay.dy);
-    in_t* sB = reinterpret_cast<in_t*>(smem + lay.b);
-    in_t* sC = reinterpret_cast<in_t*>(smem + lay.c);
-    st_t* so_dd = reinterpret_cast<st_t*>(smem + lay.o0);  // ddelta staging, pixel order
-    st_t* so_du = reinterpret_cast<st_t*>(smem + lay.o1);  // du staging, pixel order
+    const BwdLayout lay(L, ES, XB);
+    const int LSK = lay.lsk;
+    in_t* sx = reinterpret_cast<in_t*>(smem + lay.x);      // [XB][PP][LSK] skewed
+    float* sdy = reinterpret_cast<float*>(smem + lay.dy);  // [XB][PP][LSK] skewed
+    in_t* sd = reinterpret_cast<in_t*>(smem + lay.d);      // [XB][TOK] token order
+    in_t* sB = reinterpret_cast<in_t*>(smem + lay.b);      // [L]
+    in_t* sC = reinterpret_cast<in_t*>(smem + lay.c);      // [L]
+    in_t* so_dd = reinterpret_cast<in_t*>(smem + lay.o0);  // [TOK] ddelta staging, token order
+    in_t* so_du = reinterpret_cast<in_t*>(smem + lay.o1);  // [TOK] du staging, token order
     float2* stot = reinterpret_cast<float2*>(smem + lay.tot);  // [2 parity][2 fwd/rev][NW]
     float* sred = reinterpret_cast<float*>(smem + lay.red);    // [3][NW]
-    uint64_t* barL = reinterpret_cast<uint64_t*>(smem + lay.bar);  // [2] round loads
-    uint64_t* barBC = barL + 2;                                    // [1] item B/C
+    uint64_t* barX = reinterpret_cast<uint64_t*>(smem + lay.bar);  // [2] count NT: x + dy (cp.async)
+    uint64_t* barD = barX + 2;                                     // [2] count 1: delta (TMA)
+    uint64_t* barBC = barX + 4;                                    // [1] count 1: item B/C (TMA)
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int q = tid / TP;
@@ -87,19 +83,20 @@ __global__ void __launch_bounds__(NT, 1) ss2d_bwd_kernel(const FusedArgs p, cons
     const in_t* __restrict__ gd = static_cast<const in_t*>(p.dts);
     const in_t* __restrict__ gB = static_cast<const in_t*>(p.Bs);
     const in_t* __restrict__ gC = static_cast<const in_t*>(p.Cs);
-    in_t* __restrict__ gdx = static_cast<in_t*>(p.dx);
+    in_t* __restrict__ gdu = static_cast<in_t*>(p.du);
     in_t* __restrict__ gdd = static_cast<in_t*>(p.ddts);
 
-    const int RB = R * PP;            // channels per item
+    const int RB = R * PP;  // channels per item
     const int dblocks = D / RB;
-    const int items = p.B * nk * dblocks;
+    const int items = p.B * K * dblocks;
     const int my_items = (items - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) /
                          static_cast<int>(gridDim.x);
     const int nrounds = my_items * R;
     if (nrounds <= 0) return;
 
     if (tid == 0) {
-        mbar_init(&barL[0], 1), mbar_init(&barL[1], 1), mbar_init(&barBC[0], 1);
+        mbar_init(&barX[0], NT), mbar_init(&barX[1], NT), mbar_init(&barD[0], 1), mbar_init(&barD[1], 1);
+        mbar_init(&barBC[0], 1);
         fence_mbar_init();
         fence_proxy_async_smem();
     }
@@ -110,21 +107,37 @@ __global__ void __launch_bounds__(NT, 1) ss2d_bwd_kernel(const FusedArgs p, cons
         const int item = static_cast<int>(blockIdx.x) + it * static_cast<int>(gridDim.x);
         const int db = item % dblocks;
         const int bk = item / dblocks;
-        k = kbase + bk % nk;
-        b = bk / nk;
+        k = bk % K;
+        b = bk / K;
         d0 = db * RB;
     };
-    auto issue_round = [&](int s) {  // thread 0
+    const int wpl_x = L * ES / 4, wsk_x = LSK * ES / 4;
+    auto issue_round = [&](int s) {  // all threads (x, dy by cp.async); thread 0 adds the delta bulk copy
         int b, k, d0;
         item_coord(s / R, b, k, d0);
         d0 += (s % R) * PP;
         const int buf = s % XB;
         const long long pl = static_cast<long long>(b) * D + d0;
-        mbar_expect_tx(&barL[buf], TOK * (2 * sizeof(in_t) + 4));
-        bulk_g2s(sx + static_cast<size_t>(buf) * TOK, gx + pl * L, TOK * sizeof(in_t), &barL[buf]);
-        bulk_g2s(sd + static_cast<size_t>(buf) * TOK, gd + ((static_cast<long long>(b) * K + k) * D + d0) * L,
-                 TOK * sizeof(in_t), &barL[buf]);
-        bulk_g2s(sdy + static_cast<size_t>(buf) * TOK, p.dy + pl * L, TOK * 4, &barL[buf]);
+        uint32_t* dx_ = reinterpret_cast<uint32_t*>(sx + static_cast<size_t>(buf) * PP * LSK);
+        uint32_t* dy_ = reinterpret_cast<uint32_t*>(sdy + static_cast<size_t>(buf) * PP * LSK);
+        {
+            // x and dy share one barrier phase: issue both, arrive once
+            const uint32_t* srcx = reinterpret_cast<const uint32_t*>(gx + pl * L);
+            const int total = PP * wpl_x;
+            int qq = tid / wpl_x, w = tid - qq * wpl_x;
+            const int dq = NT / wpl_x, dw = NT - dq * wpl_x;
+            for (int e = tid; e < total; e += NT) {
+                cp_async4(dx_ + qq * wsk_x + (ES == 2 ? w + (w >> 5) : w + ((w >> 6) << 1)), srcx + e);
+                qq += dq, w += dw;
+                if (w >= wpl_x) w -= wpl_x, ++qq;
+            }
+        }
+        stage_skewed<4>(dy_, reinterpret_cast<const uint32_t*>(p.dy + pl * L), PP, L, LSK, &barX[buf], tid, NT);
+        if (tid == 0) {
+            mbar_expect_tx(&barD[buf], TOK * sizeof(in_t));
+            bulk_g2s(sd + static_cast<size_t>(buf) * TOK, gd + ((static_cast<long long>(b) * K + k) * D + d0) * L,
+                     TOK * sizeof(in_t), &barD[buf]);
+        }
     };
     auto issue_bc = [&](int it) {  // thread 0
         int b, k, d0;
@@ -134,10 +147,8 @@ __global__ void __launch_bounds__(NT, 1) ss2d_bwd_kernel(const FusedArgs p, cons
         bulk_g2s(sB, gB + (static_cast<long long>(b) * K + k) * L, lb, &barBC[0]);
         bulk_g2s(sC, gC + (static_cast<long long>(b) * K + k) * L, lb, &barBC[0]);
     };
-    if (tid == 0) {
-        issue_bc(0);
-        issue_round(0);
-    }
+    if (tid == 0) issue_bc(0);
+    issue_round(0);
 
     int s = 0;
     for (int it = 0; it < my_items; ++it) {
@@ -153,10 +164,12 @@ __global__ void __launch_bounds__(NT, 1) ss2d_bwd_kernel(const FusedArgs p, cons
 #pragma unroll
         for (int m = 0; m < S; ++m) accB[m] = 0.f, accC[m] = 0.f;
         mbar_wait(&barBC[0], static_cast<uint32_t>(it & 1));
+        const in_t* Bq = sB + j * S;
+        const in_t* Cq = sC + j * S;
 
         for (int r = 0; r < R; ++r, ++s) {
             const int buf = s % XB;
-            if (XB == 2 && tid == 0 && s + 1 < nrounds) issue_round(s + 1);
+            if (XB == 2 && s + 1 < nrounds) issue_round(s + 1);
             const int d0 = d00 + r * PP;
             const int d = d0 + q;
             const int row = k * D + d;
@@ -164,27 +177,37 @@ __global__ void __launch_bounds__(NT, 1) ss2d_bwd_kernel(const FusedArgs p, cons
             const float A2 = Ar * kLog2e;
             const float Dd = p.Dp ? __ldg(p.Dp + row) : 0.f;
             const float bias = p.bias ? __ldg(p.bias + row) : 0.f;
-            mbar_wait(&barL[buf], static_cast<uint32_t>((s / XB) & 1));
-            const in_t* xq = sx + static_cast<size_t>(buf) * TOK + static_cast<size_t>(q) * L;
-            const in_t* dq = sd + static_cast<size_t>(buf) * TOK + static_cast<size_t>(q) * L;
-            const float* yq = sdy + static_cast<size_t>(buf) * TOK + static_cast<size_t>(q) * L;
+            mbar_wait(&barX[buf], static_cast<uint32_t>((s / XB) & 1));
+            mbar_wait(&barD[buf], static_cast<uint32_t>((s / XB) & 1));
+            const in_t* xq = sx + (static_cast<size_t>(buf) * PP + q) * LSK;
+            const float* yq = sdy + (static_cast<size_t>(buf) * PP + q) * LSK;
 
             // ---- pass 1: forward fold (P, Sf) and reverse fold (P, Sr) of the segment
             float sp[S];
             float P = 1.f, Sf = 0.f, Sr = 0.f;
+            {
+                load_tokens<S>(sd + static_cast<size_t>(buf) * TOK + static_cast<size_t>(q) * L + j * S, sp);
 #pragma unroll
-            for (int m = 0; m < S; ++m) {
-                const int px = (m & 1) ? (pk[m >> 1] >> 16) : (pk[m >> 1] & 0xffffu);
-                const float u = to_f32(xq[px]);
-                const float raw = to_f32(dq[px]) + bias;
-                float e;
-                sp[m] = p.softplus ? softplus20(raw, e) : raw;
-                const float a = ex2f(sp[m] * A2);
-                const float bb = sp[m] * to_f32(sB[px]) * u;
-                const float g = to_f32(sC[px]) * yq[px];
-                Sf = fmaf(a, Sf, bb);
-                P *= a;
-                Sr = fmaf(P, g, Sr);
+                for (int mp = 0; mp < S / 2; ++mp) {
+                    float Bv[2], Cv[2];
+                    load_pair(Bq, mp, Bv[0], Bv[1]);
+                    load_pair(Cq, mp, Cv[0], Cv[1]);
+#pragma unroll
+                    for (int h2 = 0; h2 < 2; ++h2) {
+                        const int m = 2 * mp + h2;
+                        const int px = h2 ? (pk[mp] >> 16) : (pk[mp] & 0xffffu);
+                        const float u = to_f32(xq[px]);
+                        const float raw = sp[m] + bias;
+                        float e;
+                        sp[m] = p.softplus ? softplus20(raw, e) : raw;
+                        const float a = ex2f(sp[m] * A2);
+                        const float bb = sp[m] * Bv[h2] * u;
+                        const float g = Cv[h2] * yq[px];
+                        Sf = fmaf(a, Sf, bb);
+                        P *= a;
+                        Sr = fmaf(P, g, Sr);
+                    }
+                }
             }
             // ---- carries: forward scan (h entering from the left), reverse scan (E entering from the right)
             float Pf = P, Pr = P;
@@ -220,42 +243,39 @@ __global__ void __launch_bounds__(NT, 1) ss2d_bwd_kernel(const FusedArgs p, cons
                 }
                 Ein = fmaf(Pre, ep, Sre);
             }
-            if (DUP) {
-                // fp32 staging planes accumulate duplicate hits: clear them first
-                float* z0 = reinterpret_cast<float*>(so_dd);
-                float* z1 = reinterpret_cast<float*>(so_du);
-                for (int e = tid; e < TOK; e += NT) z0[e] = 0.f, z1[e] = 0.f;
-                __syncthreads();
-            }
             // ---- pass 2a: right-to-left, dh_t = g_t + E_{t+1}
             float dh[S];
             {
                 float E = Ein;
 #pragma unroll
-                for (int m = S - 1; m >= 0; --m) {
-                    const int px = (m & 1) ? (pk[m >> 1] >> 16) : (pk[m >> 1] & 0xffffu);
-                    const float g = to_f32(sC[px]) * yq[px];
-                    const float a = ex2f(sp[m] * A2);
-                    dh[m] = g + E;
-                    E = a * dh[m];
+                for (int mp = S / 2 - 1; mp >= 0; --mp) {
+                    float Cv[2];
+                    load_pair(Cq, mp, Cv[0], Cv[1]);
+#pragma unroll
+                    for (int h2 = 1; h2 >= 0; --h2) {
+                        const int m = 2 * mp + h2;
+                        const int px = h2 ? (pk[mp] >> 16) : (pk[mp] & 0xffffu);
+                        const float g = Cv[h2] * yq[px];
+                        const float a = ex2f(sp[m] * A2);
+                        dh[m] = g + E;
+                        E = a * dh[m];
+                    }
                 }
             }
             // ---- pass 2b: left-to-right, h_t; emit du, ddelta; accumulate dB, dC, dA, dD, dbias
             float h = hin, sA = 0.f, sD = 0.f, sb = 0.f;
-            st_t* oq_dd = so_dd + static_cast<size_t>(q) * L;
-            st_t* oq_du = so_du + static_cast<size_t>(q) * L;
 #pragma unroll
             for (int m = 0; m < S; ++m) {
                 const int px = (m & 1) ? (pk[m >> 1] >> 16) : (pk[m >> 1] & 0xffffu);
                 const float u = to_f32(xq[px]);
-                const float Bv = to_f32(sB[px]);
                 const float dyv = yq[px];
+                const float Bm = to_f32(Bq[m]);
                 const float a = ex2f(sp[m] * A2);
-                const float w = a * h;                       // a_t * h_{t-1}
-                const float bu = Bv * u;
-                h = fmaf(sp[m], bu, w);                      // h_t
+                const float w = a * h;  // a_t * h_{t-1}
+                const float bu = Bm * u;
+                h = fmaf(sp[m], bu, w);  // h_t
                 const float dhs = dh[m] * sp[m];
-                const float du = fmaf(Dd, dyv, dhs * Bv);
+                const float du = fmaf(Dd, dyv, dhs * Bm);
                 float dd = dh[m] * fmaf(Ar, w, bu);
                 if (p.softplus) {
                     // sigmoid(raw) = 1 - exp(-softplus(raw)) = -expm1(-sp); series below 1/8 keeps
@@ -269,56 +289,34 @@ __global__ void __launch_bounds__(NT, 1) ss2d_bwd_kernel(const FusedArgs p, cons
                 sA = fmaf(dhs, w, sA);
                 sD = fmaf(dyv, u, sD);
                 sb += dd;
-                if (DUP) {
-                    atomicAdd(reinterpret_cast<float*>(oq_dd) + px, dd);
-                    atomicAdd(reinterpret_cast<float*>(oq_du) + px, du);
-                } else {
-                    oq_dd[px] = from_f32<st_t>(dd);
-                    oq_du[px] = from_f32<st_t>(du);
-                }
+                sp[m] = dd;  // reuse: sp <- ddelta, dh <- du (token-ordered outputs)
+                dh[m] = du;
             }
+            store_tokens<S>(so_dd + static_cast<size_t>(q) * L + j * S, sp);
+            store_tokens<S>(so_du + static_cast<size_t>(q) * L + j * S, dh);
             // ---- per-row sums over L: warp reduce, then over the plane's warps
-            {
 #pragma unroll
-                for (int off = 16; off > 0; off >>= 1) {
-                    if (off < width) {
-                        sA += __shfl_xor_sync(0xffffffffu, sA, off, width);
-                        sD += __shfl_xor_sync(0xffffffffu, sD, off, width);
-                        sb += __shfl_xor_sync(0xffffffffu, sb, off, width);
-                    }
+            for (int off = 16; off > 0; off >>= 1) {
+                if (off < width) {
+                    sA += __shfl_xor_sync(0xffffffffu, sA, off, width);
+                    sD += __shfl_xor_sync(0xffffffffu, sD, off, width);
+                    sb += __shfl_xor_sync(0xffffffffu, sb, off, width);
                 }
-                if (TP > 32 && lane == 0) sred[warp] = sA, sred[NW + warp] = sD, sred[2 * NW + warp] = sb;
             }
-            if (DUP) {
-                // fp32 staging -> in_t in place (thread t owns elements [t*S, (t+1)*S) of both planes)
-                __syncthreads();
-                float v0[S], v1[S];
-                const float* f0 = reinterpret_cast<const float*>(so_dd) + tid * S;
-                const float* f1 = reinterpret_cast<const float*>(so_du) + tid * S;
-#pragma unroll
-                for (int m = 0; m < S; ++m) v0[m] = f0[m], v1[m] = f1[m];
-                __syncthreads();
-                in_t* o0 = reinterpret_cast<in_t*>(so_dd) + tid * S;
-                in_t* o1 = reinterpret_cast<in_t*>(so_du) + tid * S;
-#pragma unroll
-                for (int m = 0; m < S; ++m) o0[m] = from_f32<in_t>(v0[m]), o1[m] = from_f32<in_t>(v1[m]);
-            }
+            if (TP > 32 && lane == 0) sred[warp] = sA, sred[NW + warp] = sD, sred[2 * NW + warp] = sb;
             fence_proxy_async_smem();
             __syncthreads();
             if (tid == 0) {
                 const long long po = ((static_cast<long long>(b) * K + k) * D + d0) * L;
                 bulk_s2g(gdd + po, so_dd, TOK * sizeof(in_t));
-                bulk_s2g(gdx + po, so_du, TOK * sizeof(in_t));
+                bulk_s2g(gdu + po, so_du, TOK * sizeof(in_t));
                 bulk_commit();
-                if (XB == 1 && s + 1 < nrounds) issue_round(s + 1);
             }
-            if (TP > 32) {
-                if (j == 0) {
-                    float tA = 0.f, tD = 0.f, tb = 0.f;
-                    for (int w = 0; w < nwg; ++w)
-                        tA += sred[gw0 + w], tD += sred[NW + gw0 + w], tb += sred[2 * NW + gw0 + w];
-                    sA = tA, sD = tD, sb = tb;
-                }
+            if (XB == 1 && s + 1 < nrounds) issue_round(s + 1);
+            if (TP > 32 && j == 0) {
+                float tA = 0.f, tD = 0.f, tb = 0.f;
+                for (int w = 0; w < nwg; ++w) tA += sred[gw0 + w], tD += sred[NW + gw0 + w], tb += sred[2 * NW + gw0 + w];
+                sA = tA, sD = tD, sb = tb;
             }
             if (j == 0) {
                 const size_t o = static_cast<size_t>(b) * K * D + row;
@@ -327,32 +325,40 @@ __global__ void __launch_bounds__(NT, 1) ss2d_bwd_kernel(const FusedArgs p, cons
                 if (p.dbias) p.dbias[o] = sb;
             }
         }
-        // ---- item flush: dB / dC (token order, registers) -> pixel order (shared) -> global reds
+        // ---- item flush: dB / dC of the item's channels (token order, registers) -> global reds
         {
-            if (tid == 0) bulk_wait_read<0>();  // the staging planes are reused as fp32 scratch below
-            __syncthreads();
-            float* f = reinterpret_cast<float*>(smem + lay.o0);  // L floats <= the two staging planes
-            const bool plain = (PP == 1 && !DUP);                // one plane, permutation: every pixel once
+            float* gdB = p.dBs + (static_cast<size_t>(b) * K + k) * L + j * S;
+            float* gdC = p.dCs + (static_cast<size_t>(b) * K + k) * L + j * S;
+            if (PP == 1) {
 #pragma unroll
-            for (int which = 0; which < 2; ++which) {
-                if (!plain) {
-                    for (int e = tid; e < L; e += NT) f[e] = 0.f;
-                    __syncthreads();
+                for (int m = 0; m < S; m += 2) {
+                    asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(gdB + m), "f"(accB[m]), "f"(accB[m + 1])
+                                 : "memory");
+                    asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(gdC + m), "f"(accC[m]), "f"(accC[m + 1])
+                                 : "memory");
                 }
+            } else {
+                // PP planes hold partial sums for the same tokens: add them up in shared memory first
+                if (tid == 0) bulk_wait_read<0>();  // the staging planes are reused as fp32 scratch
+                __syncthreads();
+                float* f = reinterpret_cast<float*>(smem + lay.o0);  // [2][L] floats <= 2 * TOK * ES bytes (PP >= 4)
+                for (int e = tid; e < 2 * L; e += NT) f[e] = 0.f;
+                __syncthreads();
 #pragma unroll
                 for (int m = 0; m < S; ++m) {
-                    const int px = (m & 1) ? (pk[m >> 1] >> 16) : (pk[m >> 1] & 0xffffu);
-                    const float v = which ? accC[m] : accB[m];
-                    if (plain)
-                        f[px] = v;
-                    else
-                        atomicAdd(f + px, v);
+                    atomicAdd(f + j * S + m, accB[m]);
+                    atomicAdd(f + L + j * S + m, accC[m]);
                 }
                 __syncthreads();
-                float* gdst = (which ? p.dCs : p.dBs) + (static_cast<size_t>(b) * K + k) * L;
-                for (int e = tid * 4; e < L; e += NT * 4) red_add_v4(gdst + e, *reinterpret_cast<const float4*>(f + e));
-                __syncthreads();
+                float* gB2 = p.dBs + (static_cast<size_t>(b) * K + k) * L;
+                float* gC2 = p.dCs + (static_cast<size_t>(b) * K + k) * L;
+                for (int e = tid * 2; e < L; e += NT * 2) {
+                    asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(gB2 + e), "f"(f[e]), "f"(f[e + 1]) : "memory");
+                    asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(gC2 + e), "f"(f[L + e]), "f"(f[L + e + 1])
+                                 : "memory");
+                }
             }
+            __syncthreads();  // everybody is done with sB / sC (and the scratch) before the next item's loads
             if (tid == 0 && it + 1 < my_items) issue_bc(it + 1);
         }
     }
@@ -361,11 +367,19 @@ __global__ void __launch_bounds__(NT, 1) ss2d_bwd_kernel(const FusedArgs p, cons
 
 }  // namespace
 
-size_t ss2d_fused_bwd_smem(int L, int es, int xb, bool dup) { return BwdLayout(L, es, xb, dup ? 4 : es).total; }
+size_t ss2d_fused_bwd_smem(int L, int es, int xb) { return BwdLayout(L, es, xb).total; }
 
-template <typename in_t, bool DUP>
-static cudaError_t launch_one(const FusedArgs& a, int kbase, int nk, int R, int xb, cudaStream_t st) {
-    auto kern = ss2d_bwd_kernel<in_t, DUP>;
+// Channels per item: enough rounds that the per-item dB/dC flush is amortised (>= 8 channels).
+static int pick_rounds(const FusedArgs& a) {
+    int R = 1;
+    while (R * a.PP < 8 && a.D % (2 * R * a.PP) == 0) R *= 2;
+    return R;
+}
+
+template <typename in_t>
+static cudaError_t launch_t(const FusedArgs& a, cudaStream_t st) {
+    const size_t cap = 227 * 1024;
+    auto kern = ss2d_bwd_kernel<in_t>;
     static bool configured = false;
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
@@ -379,44 +393,15 @@ static cudaError_t launch_one(const FusedArgs& a, int kbase, int nk, int R, int 
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     }
     FusedArgs b = a;
-    b.xb = xb;
-    const size_t smem = BwdLayout(a.L, sizeof(in_t), xb, DUP ? 4 : sizeof(in_t)).total;
-    const int items = a.B * nk * (a.D / (R * a.PP));
+    b.xb = BwdLayout(a.L, sizeof(in_t), 2).total <= cap ? 2 : 1;
+    const size_t smem = BwdLayout(a.L, sizeof(in_t), b.xb).total;
+    if (smem > cap) return cudaErrorInvalidConfiguration;
+    const int R = pick_rounds(a);
+    const int items = a.B * a.K * (a.D / (R * a.PP));
     const int grid = items < sms ? items : sms;
-    kern<<<grid, NT, smem, st>>>(b, kbase, nk, R);
+    kern<<<grid, NT, smem, st>>>(b, R);
     note_launch();
     return cudaGetLastError();
-}
-
-// Channels per item: enough rounds that the per-item dB/dC flush is amortised (>= 8 channels),
-// while leaving at least ~3 items per SM where the shape allows.
-static int pick_rounds(const FusedArgs& a, int nk) {
-    int R = 1;
-    while (R * a.PP < 8 && a.D % (2 * R * a.PP) == 0) R *= 2;
-    return R;
-}
-
-template <typename in_t>
-static cudaError_t launch_t(const FusedArgs& a, cudaStream_t st) {
-    const size_t cap = 227 * 1024;
-    // permutation directions and duplicate-pixel directions run as two launches (different staging)
-    int kperm = 0;
-    while (kperm < a.K && !((a.dup_mask >> kperm) & 1u)) ++kperm;
-    for (int k = kperm; k < a.K; ++k)
-        if (!((a.dup_mask >> k) & 1u)) return cudaErrorInvalidValue;  // dup directions must be a suffix
-    cudaError_t e = cudaSuccess;
-    if (kperm > 0) {
-        const int xb = BwdLayout(a.L, sizeof(in_t), 2, sizeof(in_t)).total <= cap ? 2 : 1;
-        if (BwdLayout(a.L, sizeof(in_t), xb, sizeof(in_t)).total > cap) return cudaErrorInvalidConfiguration;
-        e = launch_one<in_t, false>(a, 0, kperm, pick_rounds(a, kperm), xb, st);
-        if (e != cudaSuccess) return e;
-    }
-    if (kperm < a.K) {
-        const int xb = BwdLayout(a.L, sizeof(in_t), 2, 4).total <= cap ? 2 : 1;
-        if (BwdLayout(a.L, sizeof(in_t), xb, 4).total > cap) return cudaErrorInvalidConfiguration;
-        e = launch_one<in_t, true>(a, kperm, a.K - kperm, pick_rounds(a, a.K - kperm), xb, st);
-    }
-    return e;
 }
 
 cudaError_t launch_ss2d_fused_bwd(const FusedArgs& a, int in_dtype, cudaStream_t st) {
@@ -426,12 +411,8 @@ cudaError_t launch_ss2d_fused_bwd(const FusedArgs& a, int in_dtype, cudaStream_t
 }
 
 bool ss2d_fused_bwd_fits(int L, int es, uint32_t dup_mask, int K) {
-    const size_t cap = 227 * 1024;
-    bool ok = true;
-    if ((dup_mask & 1u) == 0) ok = ok && BwdLayout(L, es, 1, es).total <= cap;
-    if (dup_mask) ok = ok && BwdLayout(L, es, 1, 4).total <= cap;
-    (void)K;
-    return ok;
+    (void)dup_mask, (void)K;
+    return BwdLayout(L, es, 1).total <= 227 * 1024;
 }
 
 }  // namespace tramba

@@ -16,13 +16,16 @@ __host__ __device__ inline size_t align_up(size_t v, size_t a) { return (v + a -
 // shared-memory layout (byte offsets), identical on host and device
 struct FwdLayout {
     size_t x, d, b, c, y, tot, bar, total;
+    int lsk;  // skewed plane length, elements
     __host__ __device__ FwdLayout(int L, int es, int xb) {
+        lsk = fused_skew_len(L);
+        const int pp = TOK / L;
         size_t o = 0;
-        x = o, o += static_cast<size_t>(xb) * TOK * es;
+        x = o, o += align_up(static_cast<size_t>(xb) * pp * lsk * es, 16);
         d = o, o += static_cast<size_t>(xb) * TOK * es;
         b = o, o += align_up(static_cast<size_t>(xb) * L * es, 16);
         c = o, o += align_up(static_cast<size_t>(xb) * L * es, 16);
-        y = o, o += static_cast<size_t>(TOK) * 4;
+        y = o, o += align_up(static_cast<size_t>(pp) * lsk * 4, 16);
         tot = o, o += 2 * NW * sizeof(float2);
         bar = o, o += 8 * sizeof(uint64_t);
         total = o;
@@ -32,16 +35,18 @@ struct FwdLayout {
 template <typename in_t>
 __global__ void __launch_bounds__(NT, 1) ss2d_fwd_kernel(const FusedArgs p) {
     extern __shared__ __align__(128) unsigned char smem[];
+    constexpr int ES = sizeof(in_t);
     const int L = p.L, K = p.K, D = p.D, TP = p.TP, PP = p.PP, XB = p.xb;
-    const FwdLayout lay(L, sizeof(in_t), XB);
-    in_t* sx = reinterpret_cast<in_t*>(smem + lay.x);
-    in_t* sd = reinterpret_cast<in_t*>(smem + lay.d);
-    in_t* sB = reinterpret_cast<in_t*>(smem + lay.b);
-    in_t* sC = reinterpret_cast<in_t*>(smem + lay.c);
-    float* sy = reinterpret_cast<float*>(smem + lay.y);
+    const FwdLayout lay(L, ES, XB);
+    const int LSK = lay.lsk;
+    in_t* sx = reinterpret_cast<in_t*>(smem + lay.x);    // [XB][PP][LSK] skewed
+    in_t* sd = reinterpret_cast<in_t*>(smem + lay.d);    // [XB][TOK] token order
+    in_t* sB = reinterpret_cast<in_t*>(smem + lay.b);    // [XB][L]
+    in_t* sC = reinterpret_cast<in_t*>(smem + lay.c);    // [XB][L]
+    float* sy = reinterpret_cast<float*>(smem + lay.y);  // [PP][LSK] skewed
     float2* stot = reinterpret_cast<float2*>(smem + lay.tot);
-    uint64_t* barX = reinterpret_cast<uint64_t*>(smem + lay.bar);  // [2]
-    uint64_t* barD = barX + 2;                                     // [2]
+    uint64_t* barX = reinterpret_cast<uint64_t*>(smem + lay.bar);  // [2] count NT (cp.async arrivals)
+    uint64_t* barD = barX + 2;                                     // [2] count 1 (TMA tx)
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int q = tid / TP;       // plane slot of this thread
@@ -62,20 +67,21 @@ __global__ void __launch_bounds__(NT, 1) ss2d_fwd_kernel(const FusedArgs p) {
     if (nstages <= 0) return;
 
     if (tid == 0) {
-        mbar_init(&barX[0], 1), mbar_init(&barX[1], 1), mbar_init(&barD[0], 1), mbar_init(&barD[1], 1);
+        mbar_init(&barX[0], NT), mbar_init(&barX[1], NT), mbar_init(&barD[0], 1), mbar_init(&barD[1], 1);
         fence_mbar_init();
         fence_proxy_async_smem();
     }
     __syncthreads();
 
-    // producer side (thread 0 only)
-    auto issue_x = [&](int i) {
+    const int wpl = L * ES / 4;    // 32-bit words per plane
+    const int wsk = LSK * ES / 4;  // ... per skewed plane
+    auto issue_x = [&](int i) {    // all threads
         const long long plane0 = (static_cast<long long>(blockIdx.x) + static_cast<long long>(i) * gridDim.x) * PP;
         const int buf = i % XB;
-        mbar_expect_tx(&barX[buf], TOK * sizeof(in_t));
-        bulk_g2s(sx + static_cast<size_t>(buf) * TOK, gx + plane0 * L, TOK * sizeof(in_t), &barX[buf]);
+        stage_skewed<ES>(reinterpret_cast<uint32_t*>(sx + static_cast<size_t>(buf) * PP * LSK),
+                         reinterpret_cast<const uint32_t*>(gx + plane0 * L), PP, wpl, wsk, &barX[buf], tid, NT);
     };
-    auto issue_dir = [&](int s) {
+    auto issue_dir = [&](int s) {  // thread 0
         const int i = s / K, k = s - i * K;
         const long long plane0 = (static_cast<long long>(blockIdx.x) + static_cast<long long>(i) * gridDim.x) * PP;
         const long long b = plane0 / D, d0 = plane0 - b * D;
@@ -86,19 +92,17 @@ __global__ void __launch_bounds__(NT, 1) ss2d_fwd_kernel(const FusedArgs p) {
         bulk_g2s(sB + static_cast<size_t>(buf) * L, gB + (b * K + k) * L, lb, &barD[buf]);
         bulk_g2s(sC + static_cast<size_t>(buf) * L, gC + (b * K + k) * L, lb, &barD[buf]);
     };
-    if (tid == 0) {
-        issue_x(0);
-        issue_dir(0);
-    }
+    issue_x(0);
+    if (tid == 0) issue_dir(0);
 
     int s = 0;
     for (int i = 0; i < my_rounds; ++i) {
         const long long plane0 = (static_cast<long long>(blockIdx.x) + static_cast<long long>(i) * gridDim.x) * PP;
         const int b = static_cast<int>(plane0 / D);
         const int d = static_cast<int>(plane0 - static_cast<long long>(b) * D) + q;
-        const in_t* xq = sx + static_cast<size_t>(i % XB) * TOK + static_cast<size_t>(q) * L;
-        float* yq = sy + static_cast<size_t>(q) * L;
-        if (XB == 2 && tid == 0 && i + 1 < my_rounds) issue_x(i + 1);
+        const in_t* xq = sx + (static_cast<size_t>(i % XB) * PP + q) * LSK;
+        float* yq = sy + static_cast<size_t>(q) * LSK;
+        if (XB == 2 && i + 1 < my_rounds) issue_x(i + 1);
         mbar_wait(&barX[i % XB], static_cast<uint32_t>((i / XB) & 1));
 
         for (int k = 0; k < K; ++k, ++s) {
@@ -115,27 +119,29 @@ __global__ void __launch_bounds__(NT, 1) ss2d_fwd_kernel(const FusedArgs p) {
                 for (int m = 0; m < S / 2; ++m) pk[m] = __ldg(tp + m);
             }
             mbar_wait(&barD[buf], static_cast<uint32_t>((s / XB) & 1));
-            const in_t* dq = sd + static_cast<size_t>(buf) * TOK + static_cast<size_t>(q) * L;
-            const in_t* Bq = sB + static_cast<size_t>(buf) * L;
-            const in_t* Cq = sC + static_cast<size_t>(buf) * L;
 
             // ---- pass 1: local fold from a zero carry-in
             float y0[S], g[S];
             float P = 1.f, Sacc = 0.f;
+            {
+                float dl[S], Bv[S], Cv[S];
+                load_tokens<S>(sd + static_cast<size_t>(buf) * TOK + static_cast<size_t>(q) * L + j * S, dl);
+                load_tokens<S>(sB + static_cast<size_t>(buf) * L + j * S, Bv);
+                load_tokens<S>(sC + static_cast<size_t>(buf) * L + j * S, Cv);
 #pragma unroll
-            for (int m = 0; m < S; ++m) {
-                const int px = (m & 1) ? (pk[m >> 1] >> 16) : (pk[m >> 1] & 0xffffu);
-                const float u = to_f32(xq[px]);
-                const float raw = to_f32(dq[px]) + bias;
-                float e;
-                const float dl = p.softplus ? softplus20(raw, e) : raw;
-                const float a = ex2f(dl * A2);
-                const float bb = dl * to_f32(Bq[px]) * u;
-                const float Cv = to_f32(Cq[px]);
-                Sacc = fmaf(a, Sacc, bb);
-                P *= a;
-                y0[m] = fmaf(Cv, Sacc, Dd * u);
-                g[m] = Cv * P;
+                for (int m = 0; m < S; ++m) {
+                    const int px = (m & 1) ? (pk[m >> 1] >> 16) : (pk[m >> 1] & 0xffffu);
+                    const float u = to_f32(xq[px]);
+                    const float raw = dl[m] + bias;
+                    float e;
+                    const float dsp = p.softplus ? softplus20(raw, e) : raw;
+                    const float a = ex2f(dsp * A2);
+                    const float bb = dsp * Bv[m] * u;
+                    Sacc = fmaf(a, Sacc, bb);
+                    P *= a;
+                    y0[m] = fmaf(Cv[m], Sacc, Dd * u);
+                    g[m] = Cv[m] * P;
+                }
             }
             // ---- carry-in of this thread: scan over the TP threads of the plane
             fused_scan(P, Sacc, sl, width);
@@ -144,16 +150,9 @@ __global__ void __launch_bounds__(NT, 1) ss2d_fwd_kernel(const FusedArgs p) {
             if (sl == 0) Pe = 1.f, Se = 0.f;
             const int par = s & 1;
             if (TP > 32 && lane == 31) stot[par * NW + warp] = make_float2(P, Sacc);
-            if (tid == 0) {
-                if (XB == 1 && s + 1 < nstages) {
-                    // single-buffered: the next stage's loads may start once everybody is past pass 1;
-                    // issued below, after the barrier
-                }
-                if (k == 0 && i > 0) bulk_wait_read<0>();  // previous round's y store has left sy
-            }
             __syncthreads();
-            if (XB == 1 && tid == 0) {
-                if (s + 1 < nstages) issue_dir(s + 1);
+            if (XB == 1) {  // single-buffered staging: everybody is past pass 1, the buffers are free
+                if (tid == 0 && s + 1 < nstages) issue_dir(s + 1);
                 if (k == K - 1 && i + 1 < my_rounds) issue_x(i + 1);
             }
             float hin = Se;
@@ -165,7 +164,7 @@ __global__ void __launch_bounds__(NT, 1) ss2d_fwd_kernel(const FusedArgs p) {
                 }
                 hin = fmaf(Pe, hp, Se);
             }
-            // ---- pass 2: add the carry-in term and merge into the image plane
+            // ---- pass 2: add the carry-in term and merge into the (skewed) image plane
             const bool dup = (p.dup_mask >> k) & 1u;
             if (k == 0) {
 #pragma unroll
@@ -187,15 +186,19 @@ __global__ void __launch_bounds__(NT, 1) ss2d_fwd_kernel(const FusedArgs p) {
                 }
             }
         }
-        // ---- merged planes of this round -> global (PP planes are contiguous in y)
-        fence_proxy_async_smem();
+        // ---- merged planes of this round -> global (PP planes are contiguous in y), un-skewing
         __syncthreads();
-        if (tid == 0) {
-            bulk_s2g(p.y + plane0 * L, sy, TOK * sizeof(float));
-            bulk_commit();
+        {
+            float* gy = p.y + plane0 * L;
+            for (int e = tid * 4; e < TOK; e += NT * 4) {
+                const int qq = e / L, pp = e - qq * L;  // 4 consecutive pixels never straddle a pad (4 | 64)
+                const float* src = sy + static_cast<size_t>(qq) * LSK + fused_skew(pp);
+                *reinterpret_cast<float4*>(gy + e) = make_float4(src[0], src[1], src[2], src[3]);
+            }
         }
+        // the next round's first scatter into sy happens after its mid-stage barrier, which every
+        // thread reaches only after finishing the copy-out above
     }
-    if (tid == 0) bulk_wait_all<0>();
 }
 
 }  // namespace

@@ -1,14 +1,15 @@
 """Fused SS2D core: CrossScan* -> SelectiveScanOflex -> CrossMerge* as ONE autograd operator
-over the image-ordered operands (Models/vmamba.py:231-259 without the permuted copies).
+(Models/vmamba.py:231-259 without the permuted copies xs / ys of the feature map).
 
     y = ss2d_core_fused(x, dts, Bs, Cs, A, Ds, delta_bias, order, param)
 
-    x   (B, D, H, W)      dts (B, K, D, L)      Bs, Cs (B, K, L)      A, Ds, delta_bias (K*D) fp32
-    y   (B, D, L) fp32 -- what CrossMerge*.apply(SelectiveScanOflex.apply(...)) returns
+    x   (B, D, H, W) image order      dts (B, K, D, L), Bs, Cs (B, K, L) scan order (as the reference's
+    projections produce them)         A, Ds, delta_bias (K*D) fp32
+    y   (B, D, L) fp32, image order -- what CrossMerge*.apply(SelectiveScanOflex.apply(...)) returns
 
-The forward is one kernel (tramba_ss2d_fused_fwd), the backward one kernel per staging mode
-(tramba_ss2d_fused_bwd) plus the sum of the per-direction input gradients.  N = 1 only; shapes the
-fused kernels do not cover are reported by `supported()` and run through the un-fused operators.
+Forward = one kernel (tramba_ss2d_fused_fwd); backward = one kernel (tramba_ss2d_fused_bwd) that
+emits du / ddelta in scan order, followed by the cross-merge of du (= CrossScan.backward).  N = 1
+only; shapes the fused kernels do not cover are reported by `supported()` and run un-fused.
 """
 import ctypes
 
@@ -34,11 +35,24 @@ def order_table16_host(order, H, param=0):
 
 
 def _idx16(order, H, param, device):
+    """Device table the kernels consume: the SKEWED shared-memory position of every token's pixel."""
     key = (order, H, param, device)
     hit = _idx_cache.get(key)
     if hit is None:
-        t = order_table16_host(order, H, param)
+        K = _lib.lib.tramba_order_num_directions(order)
+        t = np.empty((K, H * H), dtype=np.uint16)
+        _lib.check(_lib.lib.tramba_order_table16_skewed(order, H, H, param, t.ctypes.data))
         hit = torch.from_numpy(t.view(np.int16)).to(device)
+        _idx_cache[key] = hit
+    return hit
+
+
+def token_index(order, H, param, device):
+    """(K, L) int64 pixel index of every token (for gathering small per-token tensors into scan order)."""
+    key = ("i64", order, H, param, device)
+    hit = _idx_cache.get(key)
+    if hit is None:
+        hit = torch.from_numpy(order_table16_host(order, H, param).astype(np.int64)).to(device)
         _idx_cache[key] = hit
     return hit
 
@@ -82,18 +96,18 @@ class SS2DCoreFused(torch.autograd.Function):
                 _ptr(delta_bias), idx.data_ptr(), y.data_ptr(), order, K, B, D, H, W, 1, _DTYPE[dt],
                 int(bool(delta_softplus)), _stream()))
         ctx.save_for_backward(x, dts, Bs, Cs, A, Ds, delta_bias, idx)
-        ctx.meta = (order, K, B, D, H, W, bool(delta_softplus))
+        ctx.meta = (order, param, K, B, D, H, W, bool(delta_softplus))
         return y
 
     @staticmethod
     @torch.amp.custom_bwd(device_type="cuda")
     def backward(ctx, dy):
         x, dts, Bs, Cs, A, Ds, delta_bias, idx = ctx.saved_tensors
-        order, K, B, D, H, W, softplus = ctx.meta
+        order, param, K, B, D, H, W, softplus = ctx.meta
         L = H * W
         dt = x.dtype
         dy = _c16(dy.float())
-        dxk = torch.empty((B, K, D, L), device=x.device, dtype=dt)
+        du = torch.empty((B, K, D, L), device=x.device, dtype=dt)
         ddts = torch.empty((B, K, D, L), device=x.device, dtype=dt)
         dBs = torch.empty((B, K, L), device=x.device, dtype=torch.float32)
         dCs = torch.empty((B, K, L), device=x.device, dtype=torch.float32)
@@ -106,10 +120,11 @@ class SS2DCoreFused(torch.autograd.Function):
         with torch.cuda.device(x.device), _lib.timed("ss2d_fused_bwd", nbytes):
             _lib.check(_lib.lib.tramba_ss2d_fused_bwd(
                 x.data_ptr(), dts.data_ptr(), Bs.data_ptr(), Cs.data_ptr(), A.data_ptr(), _ptr(Ds),
-                _ptr(delta_bias), idx.data_ptr(), dy.data_ptr(), dxk.data_ptr(), ddts.data_ptr(), dBs.data_ptr(),
+                _ptr(delta_bias), idx.data_ptr(), dy.data_ptr(), du.data_ptr(), ddts.data_ptr(), dBs.data_ptr(),
                 dCs.data_ptr(), dA.data_ptr(), _ptr(dD), _ptr(db), order, K, B, D, H, W, 1, _DTYPE[dt],
                 int(softplus), _stream()))
-        dx = dxk.sum(dim=1, dtype=torch.float32).to(dt).view(B, D, H, W)
+        from .ops import cross_merge                      # CrossScan*.backward (csms6s.py:25-31 etc.)
+        dx = cross_merge(du, order, H, W, param).view(B, D, H, W)
         return (dx, ddts, dBs.to(dt), dCs.to(dt), dA.sum(0), None if dD is None else dD.sum(0),
                 None if db is None else db.sum(0), None, None, None)
 

@@ -134,16 +134,20 @@ class SS2D(nn.Module):
         return order, self.scan.tramba_param(H)
 
     def forward_core_fused(self, x, order, param):
-        """Same function as forward_core.  x_proj / dt_proj are per-token linear maps, so they commute
-        with the cross-scan gather: they are evaluated once on the image-ordered map (one dense 1x1
-        conv instead of K grouped ones on the K-times larger xs), and the fused kernel applies the
-        scan order to x, delta, B and C through its shared-memory addressing."""
+        """Same function as forward_core (Models/vmamba.py:231-273).  x_proj is a per-token linear map,
+        so it commutes with the cross-scan gather: it is evaluated ONCE on the image-ordered map (one
+        dense 1x1 conv instead of K grouped ones on the K-times larger xs) and its R+2N channels -- 1/25
+        of the feature map -- are gathered into scan order; dt_proj then yields delta in scan order
+        exactly as in the reference, and the fused kernel applies the scan order to x and to the merged
+        output through its shared-memory addressing (xs / ys never exist)."""
         B, D, H, W = x.shape
         K, D, R = self.dt_projs_weight.shape
         N = self.A_logs.shape[1]
         L = H * W
         xf = x.contiguous().view(B, D, L)
         x_dbl = F.conv1d(xf, self.x_proj_weight.view(-1, D, 1), bias=None).view(B, K, R + 2 * N, L)
+        tok = fused.token_index(order, H, param, x.device)                       # (K, L)
+        x_dbl = x_dbl.gather(3, tok.view(1, K, 1, L).expand(B, K, R + 2 * N, L))  # image -> scan order
         dts, Bs, Cs = torch.split(x_dbl, [R, N, N], dim=2)
         dts = F.conv1d(dts.contiguous().view(B, -1, L), self.dt_projs_weight.view(K * D, -1, 1), groups=K)
         As = -torch.exp(self.A_logs.to(torch.float)).view(-1)
