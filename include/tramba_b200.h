@@ -175,6 +175,13 @@ TRAMBA_API int tramba_ss2d_fused_bwd(const void* x, const void* dts, const void*
                                      int K, int B, int D, int H, int W, int N, int in_dtype, int delta_softplus,
                                      void* stream);
 
+/* Cross-merge through the skewed table (same shape limits as the fused core): y (B, D, L) =
+ * fold of ys (B, K, D, L), fp32 accumulation in direction order k = 0..K-1, shared-memory atomics for
+ * duplicate pixels (helix lines).  Same sums as tramba_cross_merge up to fp32 association order;
+ * used by the fused backward for dx = CrossScan*.backward(du) (csms6s.py:25-31,75-80,124-129,175-185). */
+TRAMBA_API int tramba_cross_merge_skewed(const void* ys, void* y, const uint16_t* idx16, int order, int K, int B,
+                                         int D, int H, int W, int dtype, void* stream);
+
 /* ----------------------------------------------------------------------------------------
  * DCT2D high/low split.  Replaces DCT2D.forward (Models/DCT_2D.py:12-29) and the two basis
  * layers (DCT_2D.py:32-77): Y = Wy . X . Wx^T per plane, high = Y[H/2:, W/2:],

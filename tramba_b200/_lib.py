@@ -37,6 +37,7 @@ SIGNATURES = {
     "tramba_ss2d_fused_fwd": (_i, [_vp, _vp, _vp, _vp, _fp, _fp, _fp, _vp, _fp] + [_i] * 9 + [_vp]),
     "tramba_ss2d_fused_bwd": (_i, [_vp, _vp, _vp, _vp, _fp, _fp, _fp, _vp, _fp, _vp, _vp, _fp, _fp, _fp, _fp, _fp]
                               + [_i] * 9 + [_vp]),
+    "tramba_cross_merge_skewed": (_i, [_vp, _vp, _vp] + [_i] * 7 + [_vp]),
     "tramba_dct_basis": (None, [_i, _fp]),
     "tramba_dct2d_fwd": (_i, [_fp, _fp, _fp, _fp, _fp, _i, _i, _i, _vp]),
     "tramba_dct2d_bwd": (_i, [_fp, _fp, _fp, _fp, _fp, _i, _i, _i, _vp]),

@@ -24,6 +24,8 @@ cudaError_t launch_dct2d_bwd(const float* ghigh, const float* glow, const float*
                              int planes, int H, int W, cudaStream_t st);
 
 bool ss2d_fused_bwd_fits(int L, int es, uint32_t dup_mask, int K);
+cudaError_t launch_merge_skewed(const void* ys, void* y, const uint16_t* idx, int K, int B, int D, int L,
+                                uint32_t dup_mask, int dtype, cudaStream_t st);
 
 static int elem_size(int dtype) {
     switch (dtype) {
@@ -391,4 +393,18 @@ extern "C" int tramba_ss2d_fused_bwd(const void* x, const void* dts, const void*
     e = launch_ss2d_fused_bwd(a, in_dtype, st);
     if (e == cudaErrorInvalidConfiguration) return TRAMBA_E_LIMIT;
     return cuda_rc(e);
+}
+
+extern "C" int tramba_cross_merge_skewed(const void* ys, void* y, const uint16_t* idx16, int order, int K, int B,
+                                         int D, int H, int W, int dtype, void* stream) {
+    if (!ys || !y || !idx16) return TRAMBA_E_NULL;
+    if (dtype != TRAMBA_F32 && dtype != TRAMBA_BF16) return TRAMBA_E_DTYPE;
+    FusedArgs a;
+    std::memset(&a, 0, sizeof(a));
+    int rc = fused_geometry(a, order, K, B, D, H, W, 1);
+    if (rc != TRAMBA_OK) return rc;
+    if (!aligned(ys, 16) || !aligned(y, 16) || !aligned(idx16, 4)) return TRAMBA_E_ALIGN;
+    rc = check_device();
+    if (rc != TRAMBA_OK) return rc;
+    return cuda_rc(launch_merge_skewed(ys, y, idx16, K, B, D, a.L, a.dup_mask, dtype, static_cast<cudaStream_t>(stream)));
 }

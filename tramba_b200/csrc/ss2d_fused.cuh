@@ -78,21 +78,44 @@ __device__ __forceinline__ void cp_async_arrive(uint64_t* bar) {
     asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
-// Stage `nplanes` contiguous global planes of `wpl` 32-bit words each into skewed shared planes
-// (`wsk` words apart): all NT threads take part; completion arrives on `bar` (count NT).
-// ES = element size: a 32-bit word holds 4/ES elements, and element p must land at p + 2*(p >> 6).
+__device__ __forceinline__ void cp_async8(void* dst_smem, const void* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(dst_smem)), "l"(src) : "memory");
+}
+
+// Stage ONE global plane into a skewed shared plane, by the TP threads that own the plane (thread j
+// of TP copies words j, j+TP, j+2*TP, ...; consecutive threads -> consecutive words, coalesced).
+// Element p must land at p + 2*(p >> 6):
+//   2-byte elements: 32-bit word w -> w + (w >> 5)           (4-byte copies)
+//   4-byte elements: 64-bit pair  v -> v + (v >> 5) (pairs)  (8-byte copies; pads are 2 words per 64)
+// `n` = elements per plane.  The caller arrives on the mbarrier afterwards (cp_async_arrive).
 template <int ES>
-__device__ __forceinline__ void stage_skewed(uint32_t* dst, const uint32_t* __restrict__ src, int nplanes, int wpl,
-                                             int wsk, uint64_t* bar, int tid, int nthreads) {
-    const int total = nplanes * wpl;
-    int q = tid / wpl, w = tid - q * wpl;  // incremental (q, w) walk: nthreads may exceed wpl
-    const int dq = nthreads / wpl, dw = nthreads - dq * wpl;
-    for (int e = tid; e < total; e += nthreads) {
-        cp_async4(dst + q * wsk + (ES == 2 ? w + (w >> 5) : w + ((w >> 6) << 1)), src + e);
-        q += dq, w += dw;
-        if (w >= wpl) w -= wpl, ++q;
+__device__ __forceinline__ void stage_plane_skewed(void* dst_plane, const void* __restrict__ src_plane, int n, int j,
+                                                   int TP) {
+    if constexpr (ES == 2) {
+        uint32_t* d = static_cast<uint32_t*>(dst_plane);
+        const uint32_t* s = static_cast<const uint32_t*>(src_plane);
+        const int nw = n >> 1;
+        if ((TP & 31) == 0) {  // (w >> 5) advances by TP/32 per step: constant strides
+            uint32_t* dp = d + j + (j >> 5);
+            const uint32_t* sp = s + j;
+            const int dstep = TP + (TP >> 5);
+            for (int w = j; w < nw; w += TP, dp += dstep, sp += TP) cp_async4(dp, sp);
+        } else {
+            for (int w = j; w < nw; w += TP) cp_async4(d + w + (w >> 5), s + w);
+        }
+    } else {
+        uint2* d = static_cast<uint2*>(dst_plane);
+        const uint2* s = static_cast<const uint2*>(src_plane);
+        const int nv = n >> 1;
+        if ((TP & 31) == 0) {
+            uint2* dp = d + j + (j >> 5);
+            const uint2* sp = s + j;
+            const int dstep = TP + (TP >> 5);
+            for (int v = j; v < nv; v += TP, dp += dstep, sp += TP) cp_async8(dp, sp);
+        } else {
+            for (int v = j; v < nv; v += TP) cp_async8(d + v + (v >> 5), s + v);
+        }
     }
-    cp_async_arrive(bar);
 }
 
 // Affine-map inclusive scan over `width` lanes (width = 32 or a power of two below).

@@ -50,7 +50,7 @@ struct BwdLayout {
     }
 };
 
-template <typename in_t>
+template <typename in_t, bool SOFTPLUS>
 __global__ void __launch_bounds__(NT, 1) ss2d_bwd_kernel(const FusedArgs p, const int R) {
     extern __shared__ __align__(128) unsigned char smem[];
     constexpr int ES = sizeof(in_t);
@@ -111,28 +111,15 @@ __global__ void __launch_bounds__(NT, 1) ss2d_bwd_kernel(const FusedArgs p, cons
         b = bk / K;
         d0 = db * RB;
     };
-    const int wpl_x = L * ES / 4, wsk_x = LSK * ES / 4;
-    auto issue_round = [&](int s) {  // all threads (x, dy by cp.async); thread 0 adds the delta bulk copy
+    auto issue_round = [&](int s) {  // all threads (x, dy of the thread's own plane by cp.async); thread 0 adds delta
         int b, k, d0;
         item_coord(s / R, b, k, d0);
         d0 += (s % R) * PP;
         const int buf = s % XB;
-        const long long pl = static_cast<long long>(b) * D + d0;
-        uint32_t* dx_ = reinterpret_cast<uint32_t*>(sx + static_cast<size_t>(buf) * PP * LSK);
-        uint32_t* dy_ = reinterpret_cast<uint32_t*>(sdy + static_cast<size_t>(buf) * PP * LSK);
-        {
-            // x and dy share one barrier phase: issue both, arrive once
-            const uint32_t* srcx = reinterpret_cast<const uint32_t*>(gx + pl * L);
-            const int total = PP * wpl_x;
-            int qq = tid / wpl_x, w = tid - qq * wpl_x;
-            const int dq = NT / wpl_x, dw = NT - dq * wpl_x;
-            for (int e = tid; e < total; e += NT) {
-                cp_async4(dx_ + qq * wsk_x + (ES == 2 ? w + (w >> 5) : w + ((w >> 6) << 1)), srcx + e);
-                qq += dq, w += dw;
-                if (w >= wpl_x) w -= wpl_x, ++qq;
-            }
-        }
-        stage_skewed<4>(dy_, reinterpret_cast<const uint32_t*>(p.dy + pl * L), PP, L, LSK, &barX[buf], tid, NT);
+        const long long pl = static_cast<long long>(b) * D + d0 + q;
+        stage_plane_skewed<ES>(sx + (static_cast<size_t>(buf) * PP + q) * LSK, gx + pl * L, L, j, TP);
+        stage_plane_skewed<4>(sdy + (static_cast<size_t>(buf) * PP + q) * LSK, p.dy + pl * L, L, j, TP);
+        cp_async_arrive(&barX[buf]);
         if (tid == 0) {
             mbar_expect_tx(&barD[buf], TOK * sizeof(in_t));
             bulk_g2s(sd + static_cast<size_t>(buf) * TOK, gd + ((static_cast<long long>(b) * K + k) * D + d0) * L,
@@ -199,7 +186,7 @@ __global__ void __launch_bounds__(NT, 1) ss2d_bwd_kernel(const FusedArgs p, cons
                         const float u = to_f32(xq[px]);
                         const float raw = sp[m] + bias;
                         float e;
-                        sp[m] = p.softplus ? softplus20(raw, e) : raw;
+                        sp[m] = SOFTPLUS ? softplus20(raw, e) : raw;
                         const float a = ex2f(sp[m] * A2);
                         const float bb = sp[m] * Bv[h2] * u;
                         const float g = Cv[h2] * yq[px];
@@ -277,7 +264,7 @@ __global__ void __launch_bounds__(NT, 1) ss2d_bwd_kernel(const FusedArgs p, cons
                 const float dhs = dh[m] * sp[m];
                 const float du = fmaf(Dd, dyv, dhs * Bm);
                 float dd = dh[m] * fmaf(Ar, w, bu);
-                if (p.softplus) {
+                if (SOFTPLUS) {
                     // sigmoid(raw) = 1 - exp(-softplus(raw)) = -expm1(-sp); series below 1/8 keeps
                     // fp32 relative accuracy where 1 - exp(.) would cancel
                     const float t = sp[m];
@@ -376,10 +363,10 @@ static int pick_rounds(const FusedArgs& a) {
     return R;
 }
 
-template <typename in_t>
+template <typename in_t, bool SOFTPLUS>
 static cudaError_t launch_t(const FusedArgs& a, cudaStream_t st) {
     const size_t cap = 227 * 1024;
-    auto kern = ss2d_bwd_kernel<in_t>;
+    auto kern = ss2d_bwd_kernel<in_t, SOFTPLUS>;
     static bool configured = false;
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
@@ -405,8 +392,9 @@ static cudaError_t launch_t(const FusedArgs& a, cudaStream_t st) {
 }
 
 cudaError_t launch_ss2d_fused_bwd(const FusedArgs& a, int in_dtype, cudaStream_t st) {
-    if (in_dtype == TRAMBA_F32) return launch_t<float>(a, st);
-    if (in_dtype == TRAMBA_BF16) return launch_t<__nv_bfloat16>(a, st);
+    if (in_dtype == TRAMBA_F32) return a.softplus ? launch_t<float, true>(a, st) : launch_t<float, false>(a, st);
+    if (in_dtype == TRAMBA_BF16)
+        return a.softplus ? launch_t<__nv_bfloat16, true>(a, st) : launch_t<__nv_bfloat16, false>(a, st);
     return cudaErrorInvalidValue;
 }
 

@@ -32,7 +32,7 @@ struct FwdLayout {
     }
 };
 
-template <typename in_t>
+template <typename in_t, bool SOFTPLUS>
 __global__ void __launch_bounds__(NT, 1) ss2d_fwd_kernel(const FusedArgs p) {
     extern __shared__ __align__(128) unsigned char smem[];
     constexpr int ES = sizeof(in_t);
@@ -73,13 +73,11 @@ __global__ void __launch_bounds__(NT, 1) ss2d_fwd_kernel(const FusedArgs p) {
     }
     __syncthreads();
 
-    const int wpl = L * ES / 4;    // 32-bit words per plane
-    const int wsk = LSK * ES / 4;  // ... per skewed plane
-    auto issue_x = [&](int i) {    // all threads
+    auto issue_x = [&](int i) {  // all threads: thread (q, j) stages its own plane
         const long long plane0 = (static_cast<long long>(blockIdx.x) + static_cast<long long>(i) * gridDim.x) * PP;
         const int buf = i % XB;
-        stage_skewed<ES>(reinterpret_cast<uint32_t*>(sx + static_cast<size_t>(buf) * PP * LSK),
-                         reinterpret_cast<const uint32_t*>(gx + plane0 * L), PP, wpl, wsk, &barX[buf], tid, NT);
+        stage_plane_skewed<ES>(sx + (static_cast<size_t>(buf) * PP + q) * LSK, gx + (plane0 + q) * L, L, j, TP);
+        cp_async_arrive(&barX[buf]);
     };
     auto issue_dir = [&](int s) {  // thread 0
         const int i = s / K, k = s - i * K;
@@ -134,7 +132,7 @@ __global__ void __launch_bounds__(NT, 1) ss2d_fwd_kernel(const FusedArgs p) {
                     const float u = to_f32(xq[px]);
                     const float raw = dl[m] + bias;
                     float e;
-                    const float dsp = p.softplus ? softplus20(raw, e) : raw;
+                    const float dsp = SOFTPLUS ? softplus20(raw, e) : raw;
                     const float a = ex2f(dsp * A2);
                     const float bb = dsp * Bv[m] * u;
                     Sacc = fmaf(a, Sacc, bb);
@@ -205,9 +203,9 @@ __global__ void __launch_bounds__(NT, 1) ss2d_fwd_kernel(const FusedArgs p) {
 
 size_t ss2d_fused_fwd_smem(int L, int es, int xb) { return FwdLayout(L, es, xb).total; }
 
-template <typename in_t>
+template <typename in_t, bool SOFTPLUS>
 static cudaError_t launch_t(const FusedArgs& a, cudaStream_t st) {
-    auto kern = ss2d_fwd_kernel<in_t>;
+    auto kern = ss2d_fwd_kernel<in_t, SOFTPLUS>;
     static bool configured = false;
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
@@ -228,8 +226,9 @@ static cudaError_t launch_t(const FusedArgs& a, cudaStream_t st) {
 }
 
 cudaError_t launch_ss2d_fused_fwd(const FusedArgs& a, int in_dtype, cudaStream_t st) {
-    if (in_dtype == TRAMBA_F32) return launch_t<float>(a, st);
-    if (in_dtype == TRAMBA_BF16) return launch_t<__nv_bfloat16>(a, st);
+    if (in_dtype == TRAMBA_F32) return a.softplus ? launch_t<float, true>(a, st) : launch_t<float, false>(a, st);
+    if (in_dtype == TRAMBA_BF16)
+        return a.softplus ? launch_t<__nv_bfloat16, true>(a, st) : launch_t<__nv_bfloat16, false>(a, st);
     return cudaErrorInvalidValue;
 }
 

@@ -123,8 +123,10 @@ class SS2DCoreFused(torch.autograd.Function):
                 _ptr(delta_bias), idx.data_ptr(), dy.data_ptr(), du.data_ptr(), ddts.data_ptr(), dBs.data_ptr(),
                 dCs.data_ptr(), dA.data_ptr(), _ptr(dD), _ptr(db), order, K, B, D, H, W, 1, _DTYPE[dt],
                 int(softplus), _stream()))
-        from .ops import cross_merge                      # CrossScan*.backward (csms6s.py:25-31 etc.)
-        dx = cross_merge(du, order, H, W, param).view(B, D, H, W)
+        dx = torch.empty((B, D, H, W), device=x.device, dtype=dt)   # CrossScan*.backward (csms6s.py:25-31 etc.)
+        with torch.cuda.device(x.device), _lib.timed("cross_merge_skewed", (1 + K) * B * D * L * es):
+            _lib.check(_lib.lib.tramba_cross_merge_skewed(du.data_ptr(), dx.data_ptr(), idx.data_ptr(), order, K, B,
+                                                          D, H, W, _DTYPE[dt], _stream()))
         return (dx, ddts, dBs.to(dt), dCs.to(dt), dA.sum(0), None if dD is None else dD.sum(0),
                 None if db is None else db.sum(0), None, None, None)
 
