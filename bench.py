@@ -6,7 +6,7 @@
 
 A step = one full training step of Tramba-V-TSOD (tramba_b200/model.py harness: the reference's
 module tree with identical state_dict) at 384x384, batch 4 per GPU, bf16 autocast: forward,
-deep-supervision loss (train.py:74-85), backward, DDP gradient all-reduce (N > 1), Adam step.
+deep-supervision loss (train.py:74-85), backward, NCCL gradient all-reduce (N > 1), Adam step.
 Random-init weights, synthetic N(0,1) images and Bernoulli(0.5) masks.
 
   value    : images/s, whole job, inputs already resident in HBM, CUDA events, max over ranks
@@ -220,10 +220,19 @@ def run_ours(args):
     opt = torch.optim.Adam([{"params": enc, "lr": 1e-5}, {"params": dec, "lr": 1e-4}], fused=True,
                            capturable=True)                                                      # train.py:266-280
     graph_error = None
-    net = model
+    # Data parallel over images (the path shards by image): replicas start identical
+    # (broadcast from rank 0) and every gradient lives in ONE flat fp32 buffer that is all-reduced
+    # (NCCL, AVG) once per step between backward and the Adam step -- 446 MB over NVLink/NVSwitch.
+    params = [p for p in model.parameters()]
+    flat = torch.zeros(sum(p.numel() for p in params), device=dev, dtype=torch.float32)
+    off = 0
+    for p in params:
+        p.grad = flat[off:off + p.numel()].view_as(p)
+        off += p.numel()
     if world > 1:
-        net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local], gradient_as_bucket_view=True,
-                                                        static_graph=True)
+        for p in params:
+            dist.broadcast(p.data, 0)
+    net = model
     B = args.batch
     amp = torch.bfloat16 if args.dtype == "bf16" else None
     g = torch.Generator().manual_seed(rank)
@@ -231,12 +240,21 @@ def run_ours(args):
     h_lab = (torch.rand(B, 1, IMG, IMG, generator=g) > 0.5).float().pin_memory()
     d_img, d_lab = h_img.to(dev), h_lab.to(dev)
 
-    def step(img, lab):
-        opt.zero_grad(set_to_none=True)
+    def fwd_bwd(img, lab):
+        flat.zero_()                                   # gradients accumulate in place into the flat views
         with torch.autocast("cuda", dtype=amp, enabled=amp is not None):
             outs = net(img)
         loss = tsod_loss(outs, lab)
         loss.backward()
+        return loss
+
+    def reduce_grads():
+        if world > 1:
+            dist.all_reduce(flat, op=dist.ReduceOp.AVG)
+
+    def step(img, lab):
+        loss = fwd_bwd(img, lab)
+        reduce_grads()
         opt.step()
         return loss
 
@@ -254,10 +272,13 @@ def run_ours(args):
     t_wall0 = time.time()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 
-    # ---- capture the whole training step (fwd + loss + bwd + Adam) in one CUDA graph: the step is
-    # static-shaped and launch-bound in eager mode (~10^4 launches); single-GPU only (DDP stays eager)
-    graph, s_img, s_lab, s_loss = None, d_img.clone(), d_lab.clone(), None
-    if world == 1 and not args.no_graph:
+    # ---- capture the training step in CUDA graphs: the step is static-shaped and launch-bound in eager
+    # mode (~10^4 launches).  g_fb = zero grads + forward + loss + backward; g_opt = fused Adam step; the
+    # gradient all-reduce (N > 1) runs between the two replays on the same stream.
+    torch.autograd.graph.set_warn_on_accumulate_grad_stream_mismatch(False)
+    g_fb = g_opt = None
+    s_img, s_lab, s_loss = d_img.clone(), d_lab.clone(), None
+    if not args.no_graph:
         try:
             side = torch.cuda.Stream()
             side.wait_stream(torch.cuda.current_stream())
@@ -265,29 +286,34 @@ def run_ours(args):
                 for _ in range(3):
                     step(s_img, s_lab)
             torch.cuda.current_stream().wait_stream(side)
-            opt.zero_grad(set_to_none=True)
-            graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph):
-                with torch.autocast("cuda", dtype=amp, enabled=amp is not None):
-                    outs = net(s_img)
-                s_loss = tsod_loss(outs, s_lab)
-                s_loss.backward()
+            sync()
+            g_fb = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g_fb):
+                s_loss = fwd_bwd(s_img, s_lab)
+            g_opt = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g_opt, pool=g_fb.pool()):
                 opt.step()
             for _ in range(2):
-                graph.replay()
-            torch.cuda.synchronize()
-        except Exception as exc:  # capture unsupported by some op: measure eagerly and say so
+                g_fb.replay(), reduce_grads(), g_opt.replay()
+            sync()
+        except Exception as exc:
             import traceback
             traceback.print_exc()
             raise SystemExit(f"bench.py: CUDA graph capture failed ({type(exc).__name__}: {str(exc)[:300]}); "
                              f"re-run with --no-graph")
+    graph = g_fb
+
+    def graph_step():
+        g_fb.replay()
+        reduce_grads()
+        g_opt.replay()
 
     # ---- region B (`value`): device-resident inputs
     sync()
     e0.record()
     for _ in range(args.steps):
         if graph is not None:
-            graph.replay()
+            graph_step()
         else:
             step(d_img, d_lab)
     e1.record()
@@ -301,7 +327,7 @@ def run_ours(args):
         if graph is not None:
             s_img.copy_(h_img, non_blocking=True)
             s_lab.copy_(h_lab, non_blocking=True)
-            graph.replay()
+            graph_step()
             lv = s_loss.item()                          # device -> host read of the step's result
         else:
             img = h_img.to(dev, non_blocking=True)
@@ -362,9 +388,9 @@ def run_ours(args):
             "data": "synthetic",
             "config": {"workload": "Tramba-V-TSOD training step 384x384, batch 4 per GPU (BASELINE config 3)",
                        "img_size": IMG, "global_batch": world * B, "parallelism": f"dp{world}",
-                       "weights": "random-init, 111.44 M params", "optimizer": "Adam (fused), DDP all-reduce",
+                       "weights": "random-init, 111.44 M params", "optimizer": "Adam (fused); flat-buffer NCCL all-reduce (AVG) of all gradients per step",
                        "ss2d_path": "op-by-op kernels" if args.unfused else "fused core kernels",
-                       "step_launch": "one CUDA graph per step" if graph is not None else "eager",
+                       "step_launch": "CUDA graphs (fwd+bwd graph, all-reduce, Adam graph)" if graph is not None else "eager",
                        "l2": "no explicit flush: a step streams several GB of activations (>> 126 MB L2)"},
             "e2e": {"value": world * B * args.steps / (ms_e2e * 1e-3), "unit": UNIT,
                     "h2d_bytes_per_step": h_img.numel() * 4 + h_lab.numel() * 4, "d2h_bytes_per_step": 4,
