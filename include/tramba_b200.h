@@ -196,6 +196,29 @@ TRAMBA_API int tramba_dct2d_fwd(const float* x, const float* wy, const float* wx
 TRAMBA_API int tramba_dct2d_bwd(const float* ghigh, const float* glow, const float* wy, const float* wx,
                      float* gx, int planes, int H, int W, void* stream);
 
+/* ----------------------------------------------------------------------------------------
+ * LayerNorm2d (+ GELU): layer norm over the CHANNEL axis of a channel-first (B, C, L) map.
+ * Replaces LayerNorm2d.forward (Models/modules.py:22-27: permute -> F.layer_norm -> permute)
+ * and, with act = TRAMBA_ACT_GELU, the out_norm -> out_act chain applied to the merged map
+ * after every cross-merge (Models/vmamba.py:271 and :287) -- the op next to the path (SURVEY
+ * 8(f) item 2).  One HBM read and one write of the map instead of 6-8 map-sized passes.
+ *   x (B, C, L) in_dtype; weight (C) fp32; bias (C) fp32 or NULL; y (B, C, L) out_dtype =
+ *   act(((x - mean_c) * rstd_c) * weight + bias), statistics over C per (b, l), biased variance,
+ *   fp32 internals; mean, rstd (B, L) fp32 saved for the backward (NULL = do not save).
+ * Backward: gy (B, C, L) g_dtype; gx (B, C, L) in_dtype; gw_part / gb_part
+ * (B * tramba_layernorm2d_tiles(B, C, L), C) fp32 per-tile partial sums of dweight / dbias (the
+ * caller adds the rows; no atomics, deterministic).  gb_part may be NULL.
+ * in/out/g dtypes: F32 or BF16.  x, y, gy, gx must be 8-byte aligned.
+ * -------------------------------------------------------------------------------------- */
+enum { TRAMBA_ACT_NONE = 0, TRAMBA_ACT_GELU = 1 };
+TRAMBA_API int tramba_layernorm2d_tiles(int B, int C, int L);
+TRAMBA_API int tramba_layernorm2d_fwd(const void* x, const float* weight, const float* bias, void* y, float* mean,
+                                      float* rstd, int B, int C, int L, float eps, int act, int in_dtype,
+                                      int out_dtype, void* stream);
+TRAMBA_API int tramba_layernorm2d_bwd(const void* gy, const void* x, const float* weight, const float* bias,
+                                      const float* mean, const float* rstd, void* gx, float* gw_part, float* gb_part,
+                                      int B, int C, int L, int act, int in_dtype, int g_dtype, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -27,6 +27,20 @@ bool ss2d_fused_bwd_fits(int L, int es, uint32_t dup_mask, int K);
 cudaError_t launch_merge_skewed(const void* ys, void* y, const uint16_t* idx, int K, int B, int D, int L,
                                 uint32_t dup_mask, int dtype, cudaStream_t st);
 
+bool dct2d_tc_supported(int H, int W);
+cudaError_t launch_dct2d_fwd_tc(const float* x, const float* wy, const float* wx, float* high, float* low, int planes,
+                                int H, int W, cudaStream_t st);
+cudaError_t launch_dct2d_bwd_tc(const float* ghigh, const float* glow, const float* wy, const float* wx, float* gx,
+                                int planes, int H, int W, cudaStream_t st);
+
+int layernorm2d_tiles(int B, int C, int L);
+cudaError_t launch_layernorm2d_fwd(const void* x, const float* w, const float* b, void* y, float* mean, float* rstd,
+                                   int B, int C, int L, float eps, int act, int in_dtype, int out_dtype,
+                                   cudaStream_t st);
+cudaError_t launch_layernorm2d_bwd(const void* gy, const void* x, const float* w, const float* b, const float* mean,
+                                   const float* rstd, void* gx, float* gw_part, float* gb_part, int B, int C, int L,
+                                   int act, int in_dtype, int g_dtype, cudaStream_t st);
+
 static int elem_size(int dtype) {
     switch (dtype) {
         case TRAMBA_F32: return 4;
@@ -265,7 +279,11 @@ extern "C" int tramba_dct2d_fwd(const float* x, const float* wy, const float* wx
     if (planes <= 0 || H <= 0 || W <= 0 || (H & 1) || (W & 1)) return TRAMBA_E_SHAPE;
     int rc = check_device();
     if (rc != TRAMBA_OK) return rc;
-    cudaError_t e = launch_dct2d_fwd(x, wy, wx, high, low, planes, H, W, static_cast<cudaStream_t>(stream));
+    if (!aligned(x, 16) || !aligned(high, 8) || !aligned(low, 8)) return TRAMBA_E_ALIGN;
+    // tensor-core path (TF32 x3) for every shape it covers; exact-fp32 SIMT kernel otherwise
+    cudaError_t e = dct2d_tc_supported(H, W)
+                        ? launch_dct2d_fwd_tc(x, wy, wx, high, low, planes, H, W, static_cast<cudaStream_t>(stream))
+                        : launch_dct2d_fwd(x, wy, wx, high, low, planes, H, W, static_cast<cudaStream_t>(stream));
     if (e == cudaErrorInvalidConfiguration) return TRAMBA_E_LIMIT;
     return cuda_rc(e);
 }
@@ -276,7 +294,10 @@ extern "C" int tramba_dct2d_bwd(const float* ghigh, const float* glow, const flo
     if (planes <= 0 || H <= 0 || W <= 0 || (H & 1) || (W & 1)) return TRAMBA_E_SHAPE;
     int rc = check_device();
     if (rc != TRAMBA_OK) return rc;
-    cudaError_t e = launch_dct2d_bwd(ghigh, glow, wy, wx, gx, planes, H, W, static_cast<cudaStream_t>(stream));
+    if (!aligned(ghigh, 16) || !aligned(glow, 16) || !aligned(gx, 8)) return TRAMBA_E_ALIGN;
+    cudaError_t e = dct2d_tc_supported(H, W)
+                        ? launch_dct2d_bwd_tc(ghigh, glow, wy, wx, gx, planes, H, W, static_cast<cudaStream_t>(stream))
+                        : launch_dct2d_bwd(ghigh, glow, wy, wx, gx, planes, H, W, static_cast<cudaStream_t>(stream));
     if (e == cudaErrorInvalidConfiguration) return TRAMBA_E_LIMIT;
     return cuda_rc(e);
 }
@@ -407,4 +428,44 @@ extern "C" int tramba_cross_merge_skewed(const void* ys, void* y, const uint16_t
     rc = check_device();
     if (rc != TRAMBA_OK) return rc;
     return cuda_rc(launch_merge_skewed(ys, y, idx16, K, B, D, a.L, a.dup_mask, dtype, static_cast<cudaStream_t>(stream)));
+}
+
+// ------------------------------------------------------------------------------ LayerNorm2d
+static bool ln_dtype_ok(int d) { return d == TRAMBA_F32 || d == TRAMBA_BF16; }
+
+extern "C" int tramba_layernorm2d_tiles(int B, int C, int L) {
+    if (B <= 0 || C <= 0 || L <= 0) return TRAMBA_E_SHAPE;
+    int rc = check_device();
+    if (rc != TRAMBA_OK) return rc;
+    return layernorm2d_tiles(B, C, L);
+}
+
+extern "C" int tramba_layernorm2d_fwd(const void* x, const float* weight, const float* bias, void* y, float* mean,
+                                      float* rstd, int B, int C, int L, float eps, int act, int in_dtype,
+                                      int out_dtype, void* stream) {
+    if (!x || !weight || !y) return TRAMBA_E_NULL;
+    if (B <= 0 || C <= 0 || L <= 0 || B > 65535) return TRAMBA_E_SHAPE;
+    if (!ln_dtype_ok(in_dtype) || !ln_dtype_ok(out_dtype)) return TRAMBA_E_DTYPE;
+    if (act != TRAMBA_ACT_NONE && act != TRAMBA_ACT_GELU) return TRAMBA_E_SHAPE;
+    if (!aligned(x, 8) || !aligned(y, 8) || (mean && !aligned(mean, 8)) || (rstd && !aligned(rstd, 8)))
+        return TRAMBA_E_ALIGN;
+    int rc = check_device();
+    if (rc != TRAMBA_OK) return rc;
+    return cuda_rc(launch_layernorm2d_fwd(x, weight, bias, y, mean, rstd, B, C, L, eps, act, in_dtype, out_dtype,
+                                          static_cast<cudaStream_t>(stream)));
+}
+
+extern "C" int tramba_layernorm2d_bwd(const void* gy, const void* x, const float* weight, const float* bias,
+                                      const float* mean, const float* rstd, void* gx, float* gw_part, float* gb_part,
+                                      int B, int C, int L, int act, int in_dtype, int g_dtype, void* stream) {
+    if (!gy || !x || !weight || !mean || !rstd || !gx || !gw_part) return TRAMBA_E_NULL;
+    if (B <= 0 || C <= 0 || L <= 0 || B > 65535) return TRAMBA_E_SHAPE;
+    if (!ln_dtype_ok(in_dtype) || !ln_dtype_ok(g_dtype)) return TRAMBA_E_DTYPE;
+    if (act != TRAMBA_ACT_NONE && act != TRAMBA_ACT_GELU) return TRAMBA_E_SHAPE;
+    if (!aligned(x, 8) || !aligned(gy, 8) || !aligned(gx, 8) || !aligned(mean, 8) || !aligned(rstd, 8))
+        return TRAMBA_E_ALIGN;
+    int rc = check_device();
+    if (rc != TRAMBA_OK) return rc;
+    return cuda_rc(launch_layernorm2d_bwd(gy, x, weight, bias, mean, rstd, gx, gw_part, gb_part, B, C, L, act,
+                                          in_dtype, g_dtype, static_cast<cudaStream_t>(stream)));
 }

@@ -1,0 +1,312 @@
+// LayerNorm2d (+ optional GELU epilogue) for sm_100a: layer norm over the CHANNEL axis of a
+// channel-first (B, C, L) map in one pass over HBM, forward and backward.
+//
+// Replaces LayerNorm2d.forward (Models/modules.py:22-27: permute(0,2,3,1) -> F.layer_norm ->
+// permute(0,3,1,2), i.e. two full transposed copies around the norm) and, with act = GELU, the
+// out_norm -> .to(dtype) -> out_act chain that follows every cross-merge (Models/vmamba.py:271,
+// 287).  SURVEY 8(f) item 2: the op on the merged y, 6-8 map-sized passes in the reference.
+//
+// Decomposition: CTA = one batch image x one tile of 32*PPL consecutive pixels x ALL channels.
+// lane <-> PPL adjacent pixels (the contiguous axis: every warp access is one coalesced
+// 64/128/256-byte row segment), warps stride over the channels.  Pass 1 accumulates the
+// per-pixel moments (shifted by the pixel's channel-0 value, so E[d^2] - E[d]^2 does not cancel),
+// a shared-memory reduce over the warps yields mean / rstd, pass 2 re-reads the tile (it is still
+// in L1/L2: one HBM read), normalises, applies the affine map and the activation and writes the
+// output in the requested dtype.  The backward has the same shape: pass 1 gathers the two per-pixel
+// sums of the LN adjoint and the per-channel sums for dweight / dbias (warp-reduced over the tile's
+// pixels, written as per-tile partials -- no atomics, the caller sums them), pass 2 emits dx.
+#include <math_constants.h>
+
+#include "common.cuh"
+
+namespace tramba {
+
+namespace {
+
+constexpr int kMaxWarps = 32;
+
+template <typename T, int PPL>
+__device__ __forceinline__ void ld_px(const T* __restrict__ p, float (&v)[PPL]) {
+    if constexpr (PPL == 1) {
+        v[0] = to_f32(*p);
+    } else if constexpr (sizeof(T) == 4) {
+        const float2 t = *reinterpret_cast<const float2*>(p);
+        v[0] = t.x, v[1] = t.y;
+    } else {
+        const uint32_t t = *reinterpret_cast<const uint32_t*>(p);
+        if constexpr (DTypeOf<T>::value == TRAMBA_BF16) {
+            v[0] = __uint_as_float(t << 16), v[1] = __uint_as_float(t & 0xffff0000u);
+        } else {
+            const __half2 h = *reinterpret_cast<const __half2*>(&t);
+            v[0] = __low2float(h), v[1] = __high2float(h);
+        }
+    }
+}
+template <typename T, int PPL>
+__device__ __forceinline__ void st_px(T* __restrict__ p, const float (&v)[PPL]) {
+    if constexpr (PPL == 1) {
+        *p = from_f32<T>(v[0]);
+    } else if constexpr (sizeof(T) == 4) {
+        *reinterpret_cast<float2*>(p) = make_float2(v[0], v[1]);
+    } else if constexpr (DTypeOf<T>::value == TRAMBA_BF16) {
+        *reinterpret_cast<__nv_bfloat162*>(p) = __floats2bfloat162_rn(v[0], v[1]);
+    } else {
+        *reinterpret_cast<__half2*>(p) = __floats2half2_rn(v[0], v[1]);
+    }
+}
+
+// exact GELU (nn.GELU default, approximate='none') and its derivative
+__device__ __forceinline__ float gelu_f(float z) { return 0.5f * z * (1.0f + erff(z * 0.70710678118654752f)); }
+__device__ __forceinline__ float gelu_df(float z) {
+    const float cdf = 0.5f * (1.0f + erff(z * 0.70710678118654752f));
+    const float pdf = 0.3989422804014327f * __expf(-0.5f * z * z);
+    return fmaf(z, pdf, cdf);
+}
+
+template <typename in_t, typename out_t, int PPL, int ACT>
+__global__ void ln2d_fwd_kernel(const in_t* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bs,
+                                out_t* __restrict__ y, float* __restrict__ mean, float* __restrict__ rstd, int C,
+                                int L, float eps) {
+    __shared__ float red[2][kMaxWarps][32 * PPL];
+    __shared__ float stat[2][32 * PPL];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    const int b = blockIdx.y;
+    const int l0 = (blockIdx.x * 32 + lane) * PPL;
+    const bool ok = l0 < L;  // L % PPL == 0: a lane's pixels are all in or all out
+    const in_t* xb = x + static_cast<size_t>(b) * C * L + l0;
+
+    float k0[PPL], s1[PPL], s2[PPL];
+#pragma unroll
+    for (int i = 0; i < PPL; ++i) k0[i] = s1[i] = s2[i] = 0.f;
+    if (ok) {
+        ld_px<in_t, PPL>(xb, k0);
+#pragma unroll 4
+        for (int c = warp; c < C; c += nw) {
+            float v[PPL];
+            ld_px<in_t, PPL>(xb + static_cast<size_t>(c) * L, v);
+#pragma unroll
+            for (int i = 0; i < PPL; ++i) {
+                const float d = v[i] - k0[i];
+                s1[i] += d;
+                s2[i] = fmaf(d, d, s2[i]);
+            }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < PPL; ++i) red[0][warp][lane * PPL + i] = s1[i], red[1][warp][lane * PPL + i] = s2[i];
+    __syncthreads();
+    if (threadIdx.x < 32 * PPL) {
+        float a = 0.f, q = 0.f;
+        for (int ww = 0; ww < nw; ++ww) a += red[0][ww][threadIdx.x], q += red[1][ww][threadIdx.x];
+        const float inv = 1.0f / static_cast<float>(C);
+        const float m = a * inv;                      // mean of the shifted values
+        const float var = fmaxf(fmaf(-m, m, q * inv), 0.f);
+        stat[0][threadIdx.x] = m;
+        stat[1][threadIdx.x] = rsqrtf(var + eps);
+    }
+    __syncthreads();
+    if (!ok) return;
+    float mu[PPL], rs[PPL];
+#pragma unroll
+    for (int i = 0; i < PPL; ++i) mu[i] = stat[0][lane * PPL + i] + k0[i], rs[i] = stat[1][lane * PPL + i];
+    if (warp == 0) {
+        if (mean) st_px<float, PPL>(mean + static_cast<size_t>(b) * L + l0, mu);
+        if (rstd) st_px<float, PPL>(rstd + static_cast<size_t>(b) * L + l0, rs);
+    }
+    out_t* yb = y + static_cast<size_t>(b) * C * L + l0;
+#pragma unroll 4
+    for (int c = warp; c < C; c += nw) {
+        float v[PPL];
+        ld_px<in_t, PPL>(xb + static_cast<size_t>(c) * L, v);
+        const float wc = __ldg(w + c), bc = bs ? __ldg(bs + c) : 0.f;
+#pragma unroll
+        for (int i = 0; i < PPL; ++i) {
+            const float z = fmaf((v[i] - mu[i]) * rs[i], wc, bc);
+            v[i] = ACT ? gelu_f(z) : z;
+        }
+        st_px<out_t, PPL>(yb + static_cast<size_t>(c) * L, v);
+    }
+}
+
+// dx = rstd * (g*w - mean_c(g*w) - xhat * mean_c(g*w*xhat)),  g = gy * act'(xhat*w + b)
+// dweight_part[tile][c] = sum_{pixels of the tile} g * xhat ; dbias_part[tile][c] = sum g
+template <typename in_t, typename g_t, int PPL, int ACT>
+__global__ void ln2d_bwd_kernel(const g_t* __restrict__ gy, const in_t* __restrict__ x, const float* __restrict__ w,
+                                const float* __restrict__ bs, const float* __restrict__ mean,
+                                const float* __restrict__ rstd, in_t* __restrict__ gx, float* __restrict__ gw_part,
+                                float* __restrict__ gb_part, int C, int L) {
+    __shared__ float red[2][kMaxWarps][32 * PPL];
+    __shared__ float stat[2][32 * PPL];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    const int b = blockIdx.y;
+    const int l0 = (blockIdx.x * 32 + lane) * PPL;
+    const bool ok = l0 < L;
+    const size_t base = static_cast<size_t>(b) * C * L + l0;
+    const in_t* xb = x + base;
+    const g_t* gb = gy + base;
+    float mu[PPL], rs[PPL], s1[PPL], s2[PPL];
+#pragma unroll
+    for (int i = 0; i < PPL; ++i) mu[i] = 0.f, rs[i] = 0.f, s1[i] = 0.f, s2[i] = 0.f;
+    if (ok) {
+        ld_px<float, PPL>(mean + static_cast<size_t>(b) * L + l0, mu);
+        ld_px<float, PPL>(rstd + static_cast<size_t>(b) * L + l0, rs);
+    }
+    float* pw = gw_part + (static_cast<size_t>(b) * gridDim.x + blockIdx.x) * C;
+    float* pb = gb_part ? gb_part + (static_cast<size_t>(b) * gridDim.x + blockIdx.x) * C : nullptr;
+#pragma unroll 2
+    for (int c = warp; c < C; c += nw) {
+        float v[PPL], g[PPL];
+#pragma unroll
+        for (int i = 0; i < PPL; ++i) v[i] = 0.f, g[i] = 0.f;
+        if (ok) {
+            ld_px<in_t, PPL>(xb + static_cast<size_t>(c) * L, v);
+            ld_px<g_t, PPL>(gb + static_cast<size_t>(c) * L, g);
+        }
+        const float wc = __ldg(w + c), bc = bs ? __ldg(bs + c) : 0.f;
+        float cw = 0.f, cb = 0.f;
+#pragma unroll
+        for (int i = 0; i < PPL; ++i) {
+            const float xh = (v[i] - mu[i]) * rs[i];
+            float gi = g[i];
+            if (ACT) gi *= gelu_df(fmaf(xh, wc, bc));
+            cw = fmaf(gi, xh, cw);
+            cb += gi;
+            const float gw = gi * wc;
+            s1[i] += gw;
+            s2[i] = fmaf(gw, xh, s2[i]);
+        }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            cw += __shfl_xor_sync(0xffffffffu, cw, off);
+            cb += __shfl_xor_sync(0xffffffffu, cb, off);
+        }
+        if (lane == 0) {
+            pw[c] = cw;
+            if (pb) pb[c] = cb;
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < PPL; ++i) red[0][warp][lane * PPL + i] = s1[i], red[1][warp][lane * PPL + i] = s2[i];
+    __syncthreads();
+    if (threadIdx.x < 32 * PPL) {
+        float a = 0.f, q = 0.f;
+        for (int ww = 0; ww < nw; ++ww) a += red[0][ww][threadIdx.x], q += red[1][ww][threadIdx.x];
+        const float inv = 1.0f / static_cast<float>(C);
+        stat[0][threadIdx.x] = a * inv;
+        stat[1][threadIdx.x] = q * inv;
+    }
+    __syncthreads();
+    if (!ok) return;
+    float m1[PPL], m2[PPL];
+#pragma unroll
+    for (int i = 0; i < PPL; ++i) m1[i] = stat[0][lane * PPL + i], m2[i] = stat[1][lane * PPL + i];
+    in_t* ob = gx + base;
+#pragma unroll 2
+    for (int c = warp; c < C; c += nw) {
+        float v[PPL], g[PPL];
+        ld_px<in_t, PPL>(xb + static_cast<size_t>(c) * L, v);
+        ld_px<g_t, PPL>(gb + static_cast<size_t>(c) * L, g);
+        const float wc = __ldg(w + c), bc = bs ? __ldg(bs + c) : 0.f;
+#pragma unroll
+        for (int i = 0; i < PPL; ++i) {
+            const float xh = (v[i] - mu[i]) * rs[i];
+            float gi = g[i];
+            if (ACT) gi *= gelu_df(fmaf(xh, wc, bc));
+            v[i] = rs[i] * (fmaf(gi, wc, -m1[i]) - xh * m2[i]);
+        }
+        st_px<in_t, PPL>(ob + static_cast<size_t>(c) * L, v);
+    }
+}
+
+struct LnPlan {
+    int ppl, threads, tiles;
+};
+LnPlan ln_plan(int B, int C, int L) {
+    static int sms = 0;
+    if (!sms) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    }
+    LnPlan p;
+    // two pixels per lane (wider rows) once that still leaves >= 2 CTAs per SM
+    p.ppl = (L % 2 == 0 && static_cast<long long>(B) * ((L + 63) / 64) >= 2LL * sms) ? 2 : 1;
+    p.tiles = (L + 32 * p.ppl - 1) / (32 * p.ppl);
+    const long long ctas = static_cast<long long>(B) * p.tiles;
+    // few CTAs and many channels: more warps per CTA
+    p.threads = C >= 1024 ? 1024 : C >= 512 ? 512 : 256;
+    if (ctas >= 8LL * sms && p.threads > 256) p.threads = 256;
+    return p;
+}
+
+template <typename in_t, typename out_t>
+cudaError_t fwd_t(const void* x, const float* w, const float* b, void* y, float* mean, float* rstd, int B, int C, int L,
+                  float eps, int act, cudaStream_t st) {
+    const LnPlan p = ln_plan(B, C, L);
+    const dim3 grid(p.tiles, B);
+    const in_t* xi = static_cast<const in_t*>(x);
+    out_t* yo = static_cast<out_t*>(y);
+#define LN_GO(PPL, ACT) ln2d_fwd_kernel<in_t, out_t, PPL, ACT><<<grid, p.threads, 0, st>>>(xi, w, b, yo, mean, rstd, C, L, eps)
+    if (p.ppl == 2) {
+        if (act) LN_GO(2, 1); else LN_GO(2, 0);
+    } else {
+        if (act) LN_GO(1, 1); else LN_GO(1, 0);
+    }
+#undef LN_GO
+    note_launch();
+    return cudaGetLastError();
+}
+
+template <typename in_t, typename g_t>
+cudaError_t bwd_t(const void* gy, const void* x, const float* w, const float* b, const float* mean, const float* rstd,
+                  void* gx, float* gw_part, float* gb_part, int B, int C, int L, int act, cudaStream_t st) {
+    const LnPlan p = ln_plan(B, C, L);
+    const dim3 grid(p.tiles, B);
+    const g_t* gi = static_cast<const g_t*>(gy);
+    const in_t* xi = static_cast<const in_t*>(x);
+    in_t* go = static_cast<in_t*>(gx);
+#define LN_GO(PPL, ACT) \
+    ln2d_bwd_kernel<in_t, g_t, PPL, ACT><<<grid, p.threads, 0, st>>>(gi, xi, w, b, mean, rstd, go, gw_part, gb_part, C, L)
+    if (p.ppl == 2) {
+        if (act) LN_GO(2, 1); else LN_GO(2, 0);
+    } else {
+        if (act) LN_GO(1, 1); else LN_GO(1, 0);
+    }
+#undef LN_GO
+    note_launch();
+    return cudaGetLastError();
+}
+
+}  // namespace
+
+int layernorm2d_tiles(int B, int C, int L) { return ln_plan(B, C, L).tiles; }
+
+cudaError_t launch_layernorm2d_fwd(const void* x, const float* w, const float* b, void* y, float* mean, float* rstd,
+                                   int B, int C, int L, float eps, int act, int in_dtype, int out_dtype,
+                                   cudaStream_t st) {
+    if (in_dtype == TRAMBA_F32 && out_dtype == TRAMBA_F32)
+        return fwd_t<float, float>(x, w, b, y, mean, rstd, B, C, L, eps, act, st);
+    if (in_dtype == TRAMBA_F32 && out_dtype == TRAMBA_BF16)
+        return fwd_t<float, __nv_bfloat16>(x, w, b, y, mean, rstd, B, C, L, eps, act, st);
+    if (in_dtype == TRAMBA_BF16 && out_dtype == TRAMBA_BF16)
+        return fwd_t<__nv_bfloat16, __nv_bfloat16>(x, w, b, y, mean, rstd, B, C, L, eps, act, st);
+    if (in_dtype == TRAMBA_BF16 && out_dtype == TRAMBA_F32)
+        return fwd_t<__nv_bfloat16, float>(x, w, b, y, mean, rstd, B, C, L, eps, act, st);
+    return cudaErrorInvalidValue;
+}
+
+cudaError_t launch_layernorm2d_bwd(const void* gy, const void* x, const float* w, const float* b, const float* mean,
+                                   const float* rstd, void* gx, float* gw_part, float* gb_part, int B, int C, int L,
+                                   int act, int in_dtype, int g_dtype, cudaStream_t st) {
+    if (in_dtype == TRAMBA_F32 && g_dtype == TRAMBA_F32)
+        return bwd_t<float, float>(gy, x, w, b, mean, rstd, gx, gw_part, gb_part, B, C, L, act, st);
+    if (in_dtype == TRAMBA_F32 && g_dtype == TRAMBA_BF16)
+        return bwd_t<float, __nv_bfloat16>(gy, x, w, b, mean, rstd, gx, gw_part, gb_part, B, C, L, act, st);
+    if (in_dtype == TRAMBA_BF16 && g_dtype == TRAMBA_BF16)
+        return bwd_t<__nv_bfloat16, __nv_bfloat16>(gy, x, w, b, mean, rstd, gx, gw_part, gb_part, B, C, L, act, st);
+    if (in_dtype == TRAMBA_BF16 && g_dtype == TRAMBA_F32)
+        return bwd_t<__nv_bfloat16, float>(gy, x, w, b, mean, rstd, gx, gw_part, gb_part, B, C, L, act, st);
+    return cudaErrorInvalidValue;
+}
+
+}  // namespace tramba

@@ -44,6 +44,12 @@ class DropPath(nn.Module):
         return x * mask
 
 
+def _gemm_dtype():
+    """dtype a LayerNorm2d may emit directly when its only consumer is an autocast GEMM (the reference's
+    F.layer_norm returns fp32 under autocast and the GEMM casts it; same values, one pass less)."""
+    return torch.get_autocast_dtype("cuda") if torch.is_autocast_enabled() else None
+
+
 def _pixel_unshuffle_cf(x, p):
     """'b (p1 p2 c) h w -> b c (h p1) (w p2)' (modules.py:213,247,692)."""
     B, C, H, W = x.shape
@@ -105,8 +111,8 @@ class VSSBlock(nn.Module):
         self.mlp = Mlp(dim, int(dim * 4.0))
 
     def forward(self, x):
-        x = x + self.drop_path(self.op(self.norm(x)))
-        return x + self.drop_path(self.mlp(self.norm2(x)))
+        x = x + self.drop_path(self.op(self.norm(x, to_dtype=_gemm_dtype())))
+        return x + self.drop_path(self.mlp(self.norm2(x, to_dtype=_gemm_dtype())))
 
 
 class MultiScaleDecoderBlock(nn.Module):
@@ -121,8 +127,8 @@ class MultiScaleDecoderBlock(nn.Module):
         self.mlp = DWMSMlp(dim, int(dim * 4.0))
 
     def forward(self, x):
-        x = x + self.drop_path(self.op(self.norm1(x)))
-        return x + self.drop_path(self.mlp(self.norm2(x)))
+        x = x + self.drop_path(self.op(self.norm1(x, to_dtype=_gemm_dtype())))
+        return x + self.drop_path(self.mlp(self.norm2(x, to_dtype=_gemm_dtype())))
 
 
 def _stage(block, dim, drop_paths):
@@ -218,7 +224,7 @@ class FreqBlockv6(nn.Module):
 
     def forward(self, x):
         x = x + self.attn(self.norm1(x))
-        return x + self.mlp(self.norm2(x))
+        return x + self.mlp(self.norm2(x, to_dtype=_gemm_dtype()))
 
 
 class VSSMDecoder(nn.Module):

@@ -9,18 +9,33 @@ The in/out projections, depthwise conv, x_proj/dt_proj and the LayerNorm stay Py
 in the reference (north_star); cross-scan, selective scan and cross-merge are ours.
 """
 import math
+import os
 
 import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from . import fused, ops
+from . import fused, norm, ops
+
+
+def _pointwise(x, weight, bias=None):
+    """1x1 convolution of an NCHW map as ONE batched GEMM on the (B, C, L) view: the same function as
+    F.conv2d(x, weight[:, :, None, None], bias) without cuDNN's NCHW<->NHWC round trips."""
+    B, C, H, W = x.shape
+    y = torch.bmm(weight.unsqueeze(0).expand(B, -1, -1), x.reshape(B, C, H * W))
+    if bias is not None:
+        y = y + bias.view(1, -1, 1)
+    return y.view(B, -1, H, W)
 
 
 class Linear2d(nn.Linear):
     """1x1 convolution with nn.Linear parameters (Models/modules.py:10-19)."""
 
+    as_gemm = os.environ.get("TRAMBA_LINEAR2D", "gemm") != "conv"
+
     def forward(self, x):
+        if self.as_gemm:
+            return _pointwise(x, self.weight, self.bias)
         return F.conv2d(x, self.weight[:, :, None, None], self.bias)
 
     def _load_from_state_dict(self, state_dict, prefix, *args, **kwargs):
@@ -31,12 +46,25 @@ class Linear2d(nn.Linear):
 
 
 class LayerNorm2d(nn.LayerNorm):
-    """LayerNorm over the channel dim of an NCHW tensor (Models/modules.py:22-27)."""
+    """LayerNorm over the channel dim of an NCHW tensor (Models/modules.py:22-27).
 
-    def forward(self, x):
+    On a CUDA device this is ONE kernel (tramba_b200.norm.layer_norm2d) instead of permute ->
+    F.layer_norm -> permute.  `act="gelu"` fuses the activation that follows SS2D.out_norm
+    (Models/vmamba.py:287).  Output dtype = what the reference's ops produce: fp32 under autocast
+    (F.layer_norm is an autocast-to-fp32 op) unless `to_dtype` asks for the consumer's dtype."""
+
+    fused = os.environ.get("TRAMBA_LAYERNORM2D", "fused") != "torch"
+
+    def forward(self, x, act="none", to_dtype=None):
+        if self.fused and norm.supported(x, to_dtype):
+            out = to_dtype or (torch.float32 if torch.is_autocast_enabled() else x.dtype)
+            return norm.layer_norm2d(x, self.weight, self.bias, self.eps, act, out)
         x = x.permute(0, 2, 3, 1).contiguous()
         x = F.layer_norm(x, self.normalized_shape, self.weight, self.bias, self.eps)
-        return x.permute(0, 3, 1, 2).contiguous()
+        x = x.permute(0, 3, 1, 2).contiguous()
+        if to_dtype is not None:
+            x = x.to(to_dtype)
+        return F.gelu(x) if act == "gelu" else x
 
 
 def _dt_init(dt_rank, d_inner, dt_scale=1.0, dt_init="random", dt_min=0.001, dt_max=0.1, dt_init_floor=1e-4):
@@ -133,6 +161,16 @@ class SS2D(nn.Module):
             return None
         return order, self.scan.tramba_param(H)
 
+    @property
+    def _act_in_norm(self):
+        """channel-first: out_norm, the cast and out_act (vmamba.py:271,287) are one LayerNorm2d(+GELU) kernel."""
+        return self.channel_first and isinstance(self.out_act, nn.GELU) and self.out_act.approximate == "none"
+
+    def _out_norm_act(self, y, dtype):
+        if self._act_in_norm:
+            return self.out_norm(y, act="gelu", to_dtype=dtype)
+        return self.out_norm(y).to(dtype)
+
     def forward_core_fused(self, x, order, param):
         """Same function as forward_core (Models/vmamba.py:231-273).  x_proj is a per-token linear map,
         so it commutes with the cross-scan gather: it is evaluated ONCE on the image-ordered map (one
@@ -145,17 +183,17 @@ class SS2D(nn.Module):
         N = self.A_logs.shape[1]
         L = H * W
         xf = x.contiguous().view(B, D, L)
-        x_dbl = F.conv1d(xf, self.x_proj_weight.view(-1, D, 1), bias=None).view(B, K, R + 2 * N, L)
+        x_dbl = torch.bmm(self.x_proj_weight.view(1, -1, D).expand(B, -1, -1), xf).view(B, K, R + 2 * N, L)
         tok = fused.token_index(order, H, param, x.device)                       # (K, L)
         x_dbl = x_dbl.gather(3, tok.view(1, K, 1, L).expand(B, K, R + 2 * N, L))  # image -> scan order
         dts, Bs, Cs = torch.split(x_dbl, [R, N, N], dim=2)
-        dts = F.conv1d(dts.contiguous().view(B, -1, L), self.dt_projs_weight.view(K * D, -1, 1), groups=K)
+        dts = torch.matmul(self.dt_projs_weight, dts)                            # (K, D, R) @ (B, K, R, L)
         As = -torch.exp(self.A_logs.to(torch.float)).view(-1)
         y = fused.ss2d_core_fused(x, dts.view(B, K, D, L), Bs.reshape(B, K, L), Cs.reshape(B, K, L), As,
                                   self.Ds.to(torch.float), self.dt_projs_bias.view(-1).to(torch.float), order, param)
-        y = self.out_norm(y.view(B, -1, H, W)) if self.channel_first else \
-            self.out_norm(y.transpose(1, 2).contiguous().view(B, H, W, -1))
-        return y.to(x.dtype)
+        if self.channel_first:
+            return self._out_norm_act(y.view(B, -1, H, W), x.dtype)
+        return self.out_norm(y.transpose(1, 2).contiguous().view(B, H, W, -1)).to(x.dtype)
 
     def forward_core(self, x):
         """Models/vmamba.py:231-273 (force_fp32=False, no_einsum=True, ssoflex=True)."""
@@ -180,8 +218,9 @@ class SS2D(nn.Module):
         ys = self.selective_scan.apply(xs, dts, As, Bs, Cs, Ds, delta_bias, True, -1, -1, True)
         y = self.merge.apply(ys.view(B, K, -1, H, W))                                   # (B, D, L)
         y = y.view(B, -1, H, W)
-        if not self.channel_first:
-            y = y.view(B, -1, H * W).transpose(1, 2).contiguous().view(B, H, W, -1)
+        if self.channel_first:
+            return self._out_norm_act(y, x.dtype)
+        y = y.view(B, -1, H * W).transpose(1, 2).contiguous().view(B, H, W, -1)
         y = self.out_norm(y)
         return y.to(x.dtype)
 
@@ -197,7 +236,9 @@ class SS2D(nn.Module):
         if self.with_dconv:
             x = self.conv2d(x)
         x = self.act(x)
-        y = self.out_act(self.forward_core(x))
+        y = self.forward_core(x)
+        if not self._act_in_norm:
+            y = self.out_act(y)
         if not self.disable_z:
             y = y * z
         return self.dropout(self.out_proj(y))
