@@ -210,7 +210,7 @@ TRAMBA_API int tramba_dct2d_bwd(const float* ghigh, const float* glow, const flo
  * caller adds the rows; no atomics, deterministic).  gb_part may be NULL.
  * in/out/g dtypes: F32 or BF16.  x, y, gy, gx must be 8-byte aligned.
  * -------------------------------------------------------------------------------------- */
-enum { TRAMBA_ACT_NONE = 0, TRAMBA_ACT_GELU = 1 };
+enum { TRAMBA_ACT_NONE = 0, TRAMBA_ACT_GELU = 1, TRAMBA_ACT_SILU = 2 };
 TRAMBA_API int tramba_layernorm2d_tiles(int B, int C, int L);
 TRAMBA_API int tramba_layernorm2d_fwd(const void* x, const float* weight, const float* bias, void* y, float* mean,
                                       float* rstd, int B, int C, int L, float eps, int act, int in_dtype,
@@ -218,6 +218,25 @@ TRAMBA_API int tramba_layernorm2d_fwd(const void* x, const float* weight, const 
 TRAMBA_API int tramba_layernorm2d_bwd(const void* gy, const void* x, const float* weight, const float* bias,
                                       const float* mean, const float* rstd, void* gx, float* gw_part, float* gb_part,
                                       int B, int C, int L, int act, int in_dtype, int g_dtype, void* stream);
+
+/* ----------------------------------------------------------------------------------------
+ * Depthwise k x k convolution (+ bias, + SiLU) on channel-first planes, stride 1, "same" zero
+ * padding.  Replaces `x = self.act(self.conv2d(x))` of SS2D.forward (Models/vmamba.py:281-285;
+ * nn.Conv2d(d_inner, d_inner, groups=d_inner, kernel_size=d_conv, padding=(d_conv-1)//2),
+ * vmamba.py:72-79; act = SiLU) -- the producer of the scan's input.
+ *   x, y (B, C, H, W) dtype (F32 / BF16); weight (C, 1, K, K) fp32; bias (C) fp32 or NULL;
+ *   K in {3, 5, 7}; act TRAMBA_ACT_NONE or TRAMBA_ACT_SILU; fp32 accumulation.
+ * Backward: g = dy * act'(conv(x, w) + b) (pre-activation recomputed); dx = conv(g, flip(w));
+ * dw_part (B*C, K*K + 1): per-plane partial sums of dweight (K*K taps) and dbias (last column); the
+ * caller adds over B.
+ * Planes up to ~100 x 100 (tramba_dwconv2d_supported); pointers 16-byte aligned.
+ * -------------------------------------------------------------------------------------- */
+TRAMBA_API int tramba_dwconv2d_supported(int B, int C, int H, int W, int K);
+TRAMBA_API int tramba_dwconv2d_fwd(const void* x, const float* weight, const float* bias, void* y, int B, int C,
+                                   int H, int W, int K, int act, int dtype, void* stream);
+TRAMBA_API int tramba_dwconv2d_bwd(const void* x, const float* weight, const float* bias, const void* dy, void* dx,
+                                   float* dw_part, int B, int C, int H, int W, int K, int act, int dtype,
+                                   void* stream);
 
 #ifdef __cplusplus
 }

@@ -1,12 +1,17 @@
 #!/bin/bash
-# ncu evidence for profiles/: (1) launch list of ONE eager step of the bench command (the step bench.py brackets
-# with cudaProfilerStart/Stop), (2) --set full of fused backward / forward launches of that step (traffic per launch).
+# ncu evidence for profiles/ (kept small: gpurun_out/ must stay under 64 MiB or nothing comes back):
+# (1) launch list of ONE eager step of the bench command (the step bench.py brackets with cudaProfilerStart/Stop),
+# (2) dram bytes of every launch of our kernels in that step, (3) --set full of one fused backward / forward launch.
 mkdir -p gpurun_out
-CMD="python bench.py --steps 2 --warmup 3 --no-cpu-baseline"
-timeout 1200 ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches.csv $CMD > gpurun_out/ncu_bench.log 2>&1
+CMD="python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-graph"
+timeout 900 ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches.csv $CMD > gpurun_out/ncu_bench.log 2>&1
 echo "ncu list rc=$?"; wc -l gpurun_out/launches.csv
-timeout 600 ncu --profile-from-start off --set full --clock-control none --import-source on -k regex:ss2d_bwd -c 33 -o gpurun_out/prof_step_fbwd -f $CMD > gpurun_out/ncu_fbwd_step.log 2>&1
+python tools/launch_summary.py gpurun_out/launches.csv 70 > gpurun_out/launches_summary.txt 2>&1; head -50 gpurun_out/launches_summary.txt
+timeout 600 ncu --profile-from-start off -k regex:tramba --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none --csv --log-file gpurun_out/tramba_dram.csv $CMD > gpurun_out/ncu_dram.log 2>&1
+echo "ncu dram rc=$?"; wc -l gpurun_out/tramba_dram.csv
+timeout 300 ncu --set full --clock-control none -k regex:ss2d_bwd -s 3 -c 1 -o gpurun_out/prof_fbwd -f python tools/kernel_bench.py --dtype bf16 --fused-only --only enc0 --reps 2 > gpurun_out/ncu_fbwd.log 2>&1
 echo "ncu fbwd rc=$?"
-timeout 600 ncu --profile-from-start off --set full --clock-control none --import-source on -k regex:ss2d_fwd -c 33 -o gpurun_out/prof_step_ffwd -f $CMD > gpurun_out/ncu_ffwd_step.log 2>&1
+timeout 300 ncu --set full --clock-control none -k regex:ss2d_fwd -s 3 -c 1 -o gpurun_out/prof_ffwd -f python tools/kernel_bench.py --dtype bf16 --fused-only --only enc0 --reps 2 > gpurun_out/ncu_ffwd.log 2>&1
 echo "ncu ffwd rc=$?"
-ls -la gpurun_out | head -40; du -sh gpurun_out
+find gpurun_out -size +20M -print -delete
+du -sh gpurun_out

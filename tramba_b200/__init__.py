@@ -10,6 +10,8 @@ import sys
 from . import _lib  # noqa: F401  (fails loudly if the CUDA library cannot be loaded)
 from . import selective_scan_cuda_oflex
 from .dct import DCT2D, dct2d_split
+from .dwconv import dwconv2d
+from .norm import layer_norm2d
 from .ops import (CrossMerge, CrossMerge_Dilation, CrossMerge_Line, CrossMerge_Window, CrossScan,
                   CrossScan_Dilation, CrossScan_Line, CrossScan_Window, SelectiveScanOflex, cross_merge,
                   cross_scan, selective_scan_fn)
@@ -27,5 +29,6 @@ __all__ = [
     "SS2D", "DCT2D", "Linear2d", "LayerNorm2d", "SelectiveScanOflex", "selective_scan_fn",
     "CrossScan", "CrossMerge", "CrossScan_Dilation", "CrossMerge_Dilation", "CrossScan_Window",
     "CrossMerge_Window", "CrossScan_Line", "CrossMerge_Line", "cross_scan", "cross_merge", "dct2d_split",
+    "layer_norm2d", "dwconv2d",
     "install_extension", "selective_scan_cuda_oflex",
 ]

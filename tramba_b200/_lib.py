@@ -11,7 +11,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libtramba_b200.so")
 
 F32, BF16, F16 = 0, 1, 2
-ACT_NONE, ACT_GELU = 0, 1
+ACT_NONE, ACT_GELU, ACT_SILU = 0, 1, 2
 ORDER_STD, ORDER_DILATION, ORDER_WINDOW, ORDER_LINE, ORDER_CUSTOM = 0, 1, 2, 3, 4
 
 _vp, _i, _i32p, _fp = ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p
@@ -42,6 +42,9 @@ SIGNATURES = {
     "tramba_layernorm2d_tiles": (_i, [_i, _i, _i]),
     "tramba_layernorm2d_fwd": (_i, [_vp, _fp, _fp, _vp, _fp, _fp, _i, _i, _i, ctypes.c_float, _i, _i, _i, _vp]),
     "tramba_layernorm2d_bwd": (_i, [_vp, _vp, _fp, _fp, _fp, _fp, _vp, _fp, _fp] + [_i] * 6 + [_vp]),
+    "tramba_dwconv2d_supported": (_i, [_i] * 5),
+    "tramba_dwconv2d_fwd": (_i, [_vp, _fp, _fp, _vp] + [_i] * 7 + [_vp]),
+    "tramba_dwconv2d_bwd": (_i, [_vp, _fp, _fp, _vp, _vp, _fp] + [_i] * 7 + [_vp]),
     "tramba_dct_basis": (None, [_i, _fp]),
     "tramba_dct2d_fwd": (_i, [_fp, _fp, _fp, _fp, _fp, _i, _i, _i, _vp]),
     "tramba_dct2d_bwd": (_i, [_fp, _fp, _fp, _fp, _fp, _i, _i, _i, _vp]),

@@ -41,6 +41,12 @@ cudaError_t launch_layernorm2d_bwd(const void* gy, const void* x, const float* w
                                    const float* rstd, void* gx, float* gw_part, float* gb_part, int B, int C, int L,
                                    int act, int in_dtype, int g_dtype, cudaStream_t st);
 
+bool dwconv2d_supported(int B, int C, int H, int W, int K);
+cudaError_t launch_dwconv2d_fwd(const void* x, const float* w, const float* b, void* y, int B, int C, int H, int W,
+                                int K, int act, int dtype, cudaStream_t st);
+cudaError_t launch_dwconv2d_bwd(const void* x, const float* w, const float* b, const void* dy, void* dx, float* dwp,
+                                int B, int C, int H, int W, int K, int act, int dtype, cudaStream_t st);
+
 static int elem_size(int dtype) {
     switch (dtype) {
         case TRAMBA_F32: return 4;
@@ -468,4 +474,39 @@ extern "C" int tramba_layernorm2d_bwd(const void* gy, const void* x, const float
     if (rc != TRAMBA_OK) return rc;
     return cuda_rc(launch_layernorm2d_bwd(gy, x, weight, bias, mean, rstd, gx, gw_part, gb_part, B, C, L, act,
                                           in_dtype, g_dtype, static_cast<cudaStream_t>(stream)));
+}
+
+// ------------------------------------------------------------------------------ depthwise conv
+extern "C" int tramba_dwconv2d_supported(int B, int C, int H, int W, int K) {
+    if (B <= 0 || C <= 0 || H <= 0 || W <= 0) return 0;
+    return dwconv2d_supported(B, C, H, W, K) ? 1 : 0;
+}
+
+extern "C" int tramba_dwconv2d_fwd(const void* x, const float* weight, const float* bias, void* y, int B, int C,
+                                   int H, int W, int K, int act, int dtype, void* stream) {
+    if (!x || !weight || !y) return TRAMBA_E_NULL;
+    if (B <= 0 || C <= 0 || H <= 0 || W <= 0) return TRAMBA_E_SHAPE;
+    if (!ln_dtype_ok(dtype)) return TRAMBA_E_DTYPE;
+    if (act != TRAMBA_ACT_NONE && act != TRAMBA_ACT_SILU) return TRAMBA_E_SHAPE;
+    if (!dwconv2d_supported(B, C, H, W, K)) return TRAMBA_E_LIMIT;
+    if (!aligned(x, 16) || !aligned(y, 16)) return TRAMBA_E_ALIGN;
+    int rc = check_device();
+    if (rc != TRAMBA_OK) return rc;
+    return cuda_rc(launch_dwconv2d_fwd(x, weight, bias, y, B, C, H, W, K, act != TRAMBA_ACT_NONE, dtype,
+                                       static_cast<cudaStream_t>(stream)));
+}
+
+extern "C" int tramba_dwconv2d_bwd(const void* x, const float* weight, const float* bias, const void* dy, void* dx,
+                                   float* dw_part, int B, int C, int H, int W, int K, int act, int dtype,
+                                   void* stream) {
+    if (!x || !weight || !dy || !dx || !dw_part) return TRAMBA_E_NULL;
+    if (B <= 0 || C <= 0 || H <= 0 || W <= 0) return TRAMBA_E_SHAPE;
+    if (!ln_dtype_ok(dtype)) return TRAMBA_E_DTYPE;
+    if (act != TRAMBA_ACT_NONE && act != TRAMBA_ACT_SILU) return TRAMBA_E_SHAPE;
+    if (!dwconv2d_supported(B, C, H, W, K)) return TRAMBA_E_LIMIT;
+    if (!aligned(x, 16) || !aligned(dy, 16) || !aligned(dx, 16)) return TRAMBA_E_ALIGN;
+    int rc = check_device();
+    if (rc != TRAMBA_OK) return rc;
+    return cuda_rc(launch_dwconv2d_bwd(x, weight, bias, dy, dx, dw_part, B, C, H, W, K, act != TRAMBA_ACT_NONE, dtype,
+                                       static_cast<cudaStream_t>(stream)));
 }

@@ -15,15 +15,18 @@
 // output in the requested dtype.  The backward has the same shape: pass 1 gathers the two per-pixel
 // sums of the LN adjoint and the per-channel sums for dweight / dbias (warp-reduced over the tile's
 // pixels, written as per-tile partials -- no atomics, the caller sums them), pass 2 emits dx.
+#include <cooperative_groups.h>
 #include <math_constants.h>
 
 #include "common.cuh"
+
+namespace cg = cooperative_groups;
 
 namespace tramba {
 
 namespace {
 
-constexpr int kMaxWarps = 32;
+constexpr int kMaxWarps = 16;
 
 template <typename T, int PPL>
 __device__ __forceinline__ void ld_px(const T* __restrict__ p, float (&v)[PPL]) {
@@ -64,7 +67,7 @@ __device__ __forceinline__ float gelu_df(float z) {
 }
 
 template <typename in_t, typename out_t, int PPL, int ACT>
-__global__ void ln2d_fwd_kernel(const in_t* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bs,
+__global__ void __launch_bounds__(512) ln2d_fwd_kernel(const in_t* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bs,
                                 out_t* __restrict__ y, float* __restrict__ mean, float* __restrict__ rstd, int C,
                                 int L, float eps) {
     __shared__ float red[2][kMaxWarps][32 * PPL];
@@ -131,7 +134,7 @@ __global__ void ln2d_fwd_kernel(const in_t* __restrict__ x, const float* __restr
 // dx = rstd * (g*w - mean_c(g*w) - xhat * mean_c(g*w*xhat)),  g = gy * act'(xhat*w + b)
 // dweight_part[tile][c] = sum_{pixels of the tile} g * xhat ; dbias_part[tile][c] = sum g
 template <typename in_t, typename g_t, int PPL, int ACT>
-__global__ void ln2d_bwd_kernel(const g_t* __restrict__ gy, const in_t* __restrict__ x, const float* __restrict__ w,
+__global__ void __launch_bounds__(512) ln2d_bwd_kernel(const g_t* __restrict__ gy, const in_t* __restrict__ x, const float* __restrict__ w,
                                 const float* __restrict__ bs, const float* __restrict__ mean,
                                 const float* __restrict__ rstd, in_t* __restrict__ gx, float* __restrict__ gw_part,
                                 float* __restrict__ gb_part, int C, int L) {
@@ -218,8 +221,201 @@ __global__ void ln2d_bwd_kernel(const g_t* __restrict__ gy, const in_t* __restri
     }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Register-resident variant (the one the model's shapes take).  A thread-block CLUSTER of CS CTAs
+// shares one pixel tile (64 pixels, two per lane) and splits the channels; every thread keeps its
+// <= ROWS channel rows of the tile in registers (ROWS independent loads in flight per thread), the
+// per-pixel sums are reduced over the warps in shared memory and over the cluster's CTAs through
+// distributed shared memory, and the output is produced from the registers: exactly one HBM read
+// and one write, and CS x more CTAs than pixel tiles alone would give (small maps with many
+// channels -- 24x24x1024 -- would otherwise leave most SMs idle).
+// ------------------------------------------------------------------------------------------------
+constexpr int kRows = 16;   // channel rows per thread held in registers
+
+// all-CTA reduction of part[2][64]: returns the cluster-wide sums in tot[2][64] (both shared)
+__device__ __forceinline__ void cluster_sum(cg::cluster_group& cluster, float (*part)[64], float (*tot)[64], int cs) {
+    cluster.sync();                                    // every CTA's partials are written
+    if (threadIdx.x < 128) {
+        const int a = threadIdx.x >> 6, i = threadIdx.x & 63;
+        float s = 0.f;
+        for (int r = 0; r < cs; ++r) s += cluster.map_shared_rank(&part[0][0], r)[a * 64 + i];
+        tot[a][i] = s;
+    }
+    cluster.sync();                                    // all remote reads done (and tot visible to the CTA)
+}
+
+template <typename in_t, typename out_t, int ACT>
+__global__ void __launch_bounds__(512) ln2d_fwd_reg_kernel(const in_t* __restrict__ x, const float* __restrict__ w,
+                                                           const float* __restrict__ bs, out_t* __restrict__ y,
+                                                           float* __restrict__ mean, float* __restrict__ rstd, int C,
+                                                           int L, float eps) {
+    __shared__ float red[2][kMaxWarps][64];
+    __shared__ float part[2][64];
+    __shared__ float tot[2][64];
+    cg::cluster_group cluster = cg::this_cluster();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    const int cs = gridDim.y, stride = cs * nw, c0 = blockIdx.y * nw + warp;
+    const int b = blockIdx.z;
+    const int l0 = (blockIdx.x * 32 + lane) * 2;
+    const bool ok = l0 < L;
+    const in_t* xb = x + static_cast<size_t>(b) * C * L + l0;
+    float v[kRows][2], k0[2] = {0.f, 0.f}, s1[2] = {0.f, 0.f}, s2[2] = {0.f, 0.f};
+    if (ok) ld_px<in_t, 2>(xb, k0);
+#pragma unroll
+    for (int i = 0; i < kRows; ++i) {
+        const int c = c0 + i * stride;
+        v[i][0] = k0[0], v[i][1] = k0[1];
+        if (ok && c < C) ld_px<in_t, 2>(xb + static_cast<size_t>(c) * L, v[i]);
+    }
+#pragma unroll
+    for (int i = 0; i < kRows; ++i) {
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const float d = v[i][j] - k0[j];            // rows past C hold k0: they add exactly zero
+            s1[j] += d;
+            s2[j] = fmaf(d, d, s2[j]);
+        }
+    }
+    red[0][warp][lane * 2] = s1[0], red[0][warp][lane * 2 + 1] = s1[1];
+    red[1][warp][lane * 2] = s2[0], red[1][warp][lane * 2 + 1] = s2[1];
+    __syncthreads();
+    if (threadIdx.x < 128) {
+        const int a = threadIdx.x >> 6, i = threadIdx.x & 63;
+        float s = 0.f;
+        for (int ww = 0; ww < nw; ++ww) s += red[a][ww][i];
+        part[a][i] = s;
+    }
+    cluster_sum(cluster, part, tot, cs);
+    if (!ok) return;
+    const float inv = 1.0f / static_cast<float>(C);
+    float mu[2], rs[2];
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+        const float m = tot[0][lane * 2 + j] * inv;
+        const float var = fmaxf(fmaf(-m, m, tot[1][lane * 2 + j] * inv), 0.f);
+        mu[j] = m + k0[j];
+        rs[j] = rsqrtf(var + eps);
+    }
+    if (blockIdx.y == 0 && warp == 0) {
+        if (mean) st_px<float, 2>(mean + static_cast<size_t>(b) * L + l0, mu);
+        if (rstd) st_px<float, 2>(rstd + static_cast<size_t>(b) * L + l0, rs);
+    }
+    out_t* yb = y + static_cast<size_t>(b) * C * L + l0;
+#pragma unroll
+    for (int i = 0; i < kRows; ++i) {
+        const int c = c0 + i * stride;
+        if (c < C) {
+            const float wc = __ldg(w + c), bc = bs ? __ldg(bs + c) : 0.f;
+            float o[2];
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                const float z = fmaf((v[i][j] - mu[j]) * rs[j], wc, bc);
+                o[j] = ACT ? gelu_f(z) : z;
+            }
+            st_px<out_t, 2>(yb + static_cast<size_t>(c) * L, o);
+        }
+    }
+}
+
+template <typename in_t, typename g_t, int ACT>
+__global__ void __launch_bounds__(512) ln2d_bwd_reg_kernel(const g_t* __restrict__ gy, const in_t* __restrict__ x,
+                                                           const float* __restrict__ w, const float* __restrict__ bs,
+                                                           const float* __restrict__ mean,
+                                                           const float* __restrict__ rstd, in_t* __restrict__ gx,
+                                                           float* __restrict__ gw_part, float* __restrict__ gb_part,
+                                                           int C, int L) {
+    __shared__ float red[2][kMaxWarps][64];
+    __shared__ float part[2][64];
+    __shared__ float tot[2][64];
+    cg::cluster_group cluster = cg::this_cluster();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    const int cs = gridDim.y, stride = cs * nw, c0 = blockIdx.y * nw + warp;
+    const int b = blockIdx.z;
+    const int l0 = (blockIdx.x * 32 + lane) * 2;
+    const bool ok = l0 < L;
+    const size_t base = static_cast<size_t>(b) * C * L + l0;
+    const in_t* xb = x + base;
+    const g_t* gb = gy + base;
+    float xh[kRows][2], g[kRows][2];
+    float mu[2] = {0.f, 0.f}, rs[2] = {0.f, 0.f}, s1[2] = {0.f, 0.f}, s2[2] = {0.f, 0.f};
+    if (ok) {
+        ld_px<float, 2>(mean + static_cast<size_t>(b) * L + l0, mu);
+        ld_px<float, 2>(rstd + static_cast<size_t>(b) * L + l0, rs);
+    }
+#pragma unroll
+    for (int i = 0; i < kRows; ++i) {
+        const int c = c0 + i * stride;
+        xh[i][0] = mu[0], xh[i][1] = mu[1];               // -> xhat = 0 for rows past C / lanes past L
+        g[i][0] = g[i][1] = 0.f;
+        if (ok && c < C) {
+            ld_px<in_t, 2>(xb + static_cast<size_t>(c) * L, xh[i]);
+            ld_px<g_t, 2>(gb + static_cast<size_t>(c) * L, g[i]);
+        }
+    }
+    float* pw = gw_part + (static_cast<size_t>(b) * gridDim.x + blockIdx.x) * C;
+    float* pb = gb_part ? gb_part + (static_cast<size_t>(b) * gridDim.x + blockIdx.x) * C : nullptr;
+#pragma unroll
+    for (int i = 0; i < kRows; ++i) {
+        const int c = c0 + i * stride;
+        const bool cv = c < C;                            // warp-uniform
+        const float wc = cv ? __ldg(w + c) : 0.f, bc = (cv && bs) ? __ldg(bs + c) : 0.f;
+        float cw = 0.f, cb = 0.f;
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const float h = (xh[i][j] - mu[j]) * rs[j];
+            float gi = g[i][j];
+            if (ACT) gi *= gelu_df(fmaf(h, wc, bc));
+            xh[i][j] = h, g[i][j] = gi;                   // keep xhat and the activated gradient
+            cw = fmaf(gi, h, cw);
+            cb += gi;
+            const float gw = gi * wc;
+            s1[j] += gw;
+            s2[j] = fmaf(gw, h, s2[j]);
+        }
+        if (cv) {
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) {
+                cw += __shfl_xor_sync(0xffffffffu, cw, off);
+                cb += __shfl_xor_sync(0xffffffffu, cb, off);
+            }
+            if (lane == 0) {
+                pw[c] = cw;
+                if (pb) pb[c] = cb;
+            }
+        }
+    }
+    red[0][warp][lane * 2] = s1[0], red[0][warp][lane * 2 + 1] = s1[1];
+    red[1][warp][lane * 2] = s2[0], red[1][warp][lane * 2 + 1] = s2[1];
+    __syncthreads();
+    if (threadIdx.x < 128) {
+        const int a = threadIdx.x >> 6, i = threadIdx.x & 63;
+        float s = 0.f;
+        for (int ww = 0; ww < nw; ++ww) s += red[a][ww][i];
+        part[a][i] = s;
+    }
+    cluster_sum(cluster, part, tot, cs);
+    if (!ok) return;
+    const float inv = 1.0f / static_cast<float>(C);
+    const float m1[2] = {tot[0][lane * 2] * inv, tot[0][lane * 2 + 1] * inv};
+    const float m2[2] = {tot[1][lane * 2] * inv, tot[1][lane * 2 + 1] * inv};
+    in_t* ob = gx + base;
+#pragma unroll
+    for (int i = 0; i < kRows; ++i) {
+        const int c = c0 + i * stride;
+        if (c < C) {
+            const float wc = __ldg(w + c);
+            float o[2];
+#pragma unroll
+            for (int j = 0; j < 2; ++j) o[j] = rs[j] * (fmaf(g[i][j], wc, -m1[j]) - xh[i][j] * m2[j]);
+            st_px<in_t, 2>(ob + static_cast<size_t>(c) * L, o);
+        }
+    }
+}
+
 struct LnPlan {
     int ppl, threads, tiles;
+    int cs;   // > 0: register-resident cluster kernels with cs CTAs per pixel tile; 0: streaming kernels
 };
 LnPlan ln_plan(int B, int C, int L) {
     static int sms = 0;
@@ -229,12 +425,29 @@ LnPlan ln_plan(int B, int C, int L) {
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     }
     LnPlan p;
+    p.cs = 0;
+    if (L % 2 == 0) {
+        // register-resident plan: 64-pixel tiles; the smallest cluster size that yields >= 2 CTAs per SM
+        // (at most 8, the portable limit) and at most kRows channel rows per thread
+        const int tiles = (L + 63) / 64;
+        int cs = 1;
+        while (cs < 8 && static_cast<long long>(B) * tiles * cs < 2LL * sms) cs *= 2;
+        while (cs > 1 && C < cs * 8) cs /= 2;
+        int nw = 8;
+        auto rows = [&](int c_s, int n_w) { return (C + c_s * n_w - 1) / (c_s * n_w); };
+        if (rows(cs, nw) > kRows) nw = 16;
+        while (rows(cs, nw) > kRows && cs < 8) cs *= 2;
+        if (rows(cs, nw) <= kRows) {
+            p.cs = cs, p.ppl = 2, p.tiles = tiles, p.threads = nw * 32;
+            return p;
+        }
+    }
     // two pixels per lane (wider rows) once that still leaves >= 2 CTAs per SM
     p.ppl = (L % 2 == 0 && static_cast<long long>(B) * ((L + 63) / 64) >= 2LL * sms) ? 2 : 1;
     p.tiles = (L + 32 * p.ppl - 1) / (32 * p.ppl);
     const long long ctas = static_cast<long long>(B) * p.tiles;
     // few CTAs and many channels: more warps per CTA
-    p.threads = C >= 1024 ? 1024 : C >= 512 ? 512 : 256;
+    p.threads = C >= 512 ? 512 : 256;
     if (ctas >= 8LL * sms && p.threads > 256) p.threads = 256;
     return p;
 }
@@ -243,9 +456,23 @@ template <typename in_t, typename out_t>
 cudaError_t fwd_t(const void* x, const float* w, const float* b, void* y, float* mean, float* rstd, int B, int C, int L,
                   float eps, int act, cudaStream_t st) {
     const LnPlan p = ln_plan(B, C, L);
-    const dim3 grid(p.tiles, B);
     const in_t* xi = static_cast<const in_t*>(x);
     out_t* yo = static_cast<out_t*>(y);
+    if (p.cs > 0) {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(p.tiles, p.cs, B);
+        cfg.blockDim = dim3(p.threads);
+        cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 1, attr[0].val.clusterDim.y = p.cs, attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr, cfg.numAttrs = 1;
+        cudaError_t e = act ? cudaLaunchKernelEx(&cfg, ln2d_fwd_reg_kernel<in_t, out_t, 1>, xi, w, b, yo, mean, rstd, C, L, eps)
+                            : cudaLaunchKernelEx(&cfg, ln2d_fwd_reg_kernel<in_t, out_t, 0>, xi, w, b, yo, mean, rstd, C, L, eps);
+        note_launch();
+        return e != cudaSuccess ? e : cudaGetLastError();
+    }
+    const dim3 grid(p.tiles, B);
 #define LN_GO(PPL, ACT) ln2d_fwd_kernel<in_t, out_t, PPL, ACT><<<grid, p.threads, 0, st>>>(xi, w, b, yo, mean, rstd, C, L, eps)
     if (p.ppl == 2) {
         if (act) LN_GO(2, 1); else LN_GO(2, 0);
@@ -261,10 +488,24 @@ template <typename in_t, typename g_t>
 cudaError_t bwd_t(const void* gy, const void* x, const float* w, const float* b, const float* mean, const float* rstd,
                   void* gx, float* gw_part, float* gb_part, int B, int C, int L, int act, cudaStream_t st) {
     const LnPlan p = ln_plan(B, C, L);
-    const dim3 grid(p.tiles, B);
     const g_t* gi = static_cast<const g_t*>(gy);
     const in_t* xi = static_cast<const in_t*>(x);
     in_t* go = static_cast<in_t*>(gx);
+    if (p.cs > 0) {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(p.tiles, p.cs, B);
+        cfg.blockDim = dim3(p.threads);
+        cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 1, attr[0].val.clusterDim.y = p.cs, attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr, cfg.numAttrs = 1;
+        cudaError_t e = act ? cudaLaunchKernelEx(&cfg, ln2d_bwd_reg_kernel<in_t, g_t, 1>, gi, xi, w, b, mean, rstd, go, gw_part, gb_part, C, L)
+                            : cudaLaunchKernelEx(&cfg, ln2d_bwd_reg_kernel<in_t, g_t, 0>, gi, xi, w, b, mean, rstd, go, gw_part, gb_part, C, L);
+        note_launch();
+        return e != cudaSuccess ? e : cudaGetLastError();
+    }
+    const dim3 grid(p.tiles, B);
 #define LN_GO(PPL, ACT) \
     ln2d_bwd_kernel<in_t, g_t, PPL, ACT><<<grid, p.threads, 0, st>>>(gi, xi, w, b, mean, rstd, go, gw_part, gb_part, C, L)
     if (p.ppl == 2) {

@@ -16,13 +16,14 @@ Reference map:
     FreqSS2Dv6 / FreqBlockv6 Models/freq_mamba.py:11-82    FreqExpand2D       Models/modules.py:687-696
     VSSMDecoder / BaseUMamba Trambav6.py:13-165            loss               train.py:74-85, utils/loss.py:6-11
 """
+import os
 from collections import OrderedDict
 
 import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from . import ops
+from . import dwconv, ops
 from .dct import DCT2D
 from .ss2d import SS2D, LayerNorm2d, Linear2d
 
@@ -86,10 +87,26 @@ class DWMSMlp(nn.Module):
         self.act = nn.GELU()
         self.dwc3, self.dwc5, self.dwc7 = _DWConv(hidden, 3), _DWConv(hidden, 5), _DWConv(hidden, 7)
         self.fc2 = Linear2d(hidden, dim)
+        ident = torch.zeros(1, 1, 7, 7)
+        ident[0, 0, 3, 3] = 1.0
+        self.register_buffer("_ident", ident, persistent=False)     # not in the state_dict (reference keys only)
+
+    fused = os.environ.get("TRAMBA_DWCONV", "fused") != "torch"
+
+    def _taps(self):
+        """x + dwc3(x) + dwc5(x) + dwc7(x) is ONE 7x7 depthwise conv: the zero-padded 3x3 and 5x5 taps and
+        the identity add into the 7x7 taps (same 'same' padding), the biases add."""
+        w7 = self.dwc7.dw_conv.weight
+        w = w7 + F.pad(self.dwc5.dw_conv.weight, (1, 1, 1, 1)) + F.pad(self.dwc3.dw_conv.weight, (2, 2, 2, 2))
+        return w + self._ident, self.dwc3.dw_conv.bias + self.dwc5.dw_conv.bias + self.dwc7.dw_conv.bias
 
     def forward(self, x):
         x = self.fc1(x)
-        x = x + self.dwc3(x) + self.dwc5(x) + self.dwc7(x)
+        if self.fused and dwconv.supported(x, self.dwc7.dw_conv.weight):
+            w, b = self._taps()
+            x = dwconv.dwconv2d(x, w, b, "none")
+        else:
+            x = x + self.dwc3(x) + self.dwc5(x) + self.dwc7(x)
         return self.fc2(self.act(x))
 
 

@@ -65,15 +65,16 @@ class LayerNorm2dFn(torch.autograd.Function):
         with torch.cuda.device(x.device):
             tiles = _lib.lib.tramba_layernorm2d_tiles(B, C, L)
             _lib.check(min(tiles, 0))
-            gw = torch.empty((B * tiles, C), device=x.device, dtype=torch.float32)
-            gb = torch.empty((B * tiles, C), device=x.device, dtype=torch.float32) if b is not None else None
+            part = torch.empty((2 if b is not None else 1, B * tiles, C), device=x.device, dtype=torch.float32)
+            gw, gb = part[0], (part[1] if b is not None else None)
             nbytes = x.numel() * (2 * x.element_size() + gy.element_size())
             with _lib.timed("layernorm2d_bwd", nbytes):
                 _lib.check(_lib.lib.tramba_layernorm2d_bwd(
                     gy.data_ptr(), x.data_ptr(), w.data_ptr(), None if b is None else b.data_ptr(), mean.data_ptr(),
                     rstd.data_ptr(), gx.data_ptr(), gw.data_ptr(), None if gb is None else gb.data_ptr(),
                     B, C, L, _ACT[act], _DTYPE[x.dtype], _DTYPE[gy.dtype], _stream()))
-        return gx, gw.sum(0).to(wdt), None if gb is None else gb.sum(0).to(bdt), None, None, None
+        part = part.sum(1)                                      # one reduction for dweight and dbias
+        return gx, part[0].to(wdt), None if b is None else part[1].to(bdt), None, None, None
 
 
 def layer_norm2d(x, weight, bias=None, eps=1e-5, act="none", out_dtype=None):
