@@ -101,7 +101,7 @@ __device__ __forceinline__ void store_row(T* __restrict__ dst, const float (&v)[
 }
 
 template <typename T, int K, int ACT>
-__global__ void __launch_bounds__(320) dwconv_fwd_kernel(const T* __restrict__ x, const float* __restrict__ wgt,
+__global__ void __launch_bounds__(320, 2) dwconv_fwd_kernel(const T* __restrict__ x, const float* __restrict__ wgt,
                                                          const float* __restrict__ bias, T* __restrict__ y,
                                                          const DwGeom g) {
     extern __shared__ __align__(16) float sm[];
@@ -155,7 +155,7 @@ __global__ void __launch_bounds__(320) dwconv_fwd_kernel(const T* __restrict__ x
 
 // Backward.  Shared: plane X (input, zero halo) and plane G (g = dy * act'(pre), zero halo).
 template <typename T, int K, int ACT>
-__global__ void __launch_bounds__(320) dwconv_bwd_kernel(const T* __restrict__ x, const float* __restrict__ wgt,
+__global__ void __launch_bounds__(320, 2) dwconv_bwd_kernel(const T* __restrict__ x, const float* __restrict__ wgt,
                                                          const float* __restrict__ bias, const T* __restrict__ dy,
                                                          T* __restrict__ dx, float* __restrict__ dw_part,
                                                          const DwGeom g) {
@@ -374,7 +374,9 @@ int sm_count() {
 template <typename T, int K>
 cudaError_t fwd_k(const void* x, const float* w, const float* b, void* y, const DwPlan& p, int act, cudaStream_t st) {
     const int groups = (p.g.planes + p.g.ppc - 1) / p.g.ppc;
-    const int per_sm = static_cast<int>(std::max<size_t>(1, std::min<size_t>(6, (200 * 1024) / (p.smem_fwd + 1024))));
+    // co-resident CTAs per SM: shared memory, then registers (<= 102 per thread under the launch bounds)
+    const int per_sm = static_cast<int>(std::max<size_t>(
+        1, std::min<size_t>({6, (200 * 1024) / (p.smem_fwd + 1024), static_cast<size_t>(65536 / (104 * p.threads))})));
     const int grid = std::min(groups, sm_count() * per_sm);
     auto go = [&](auto kern) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
@@ -391,7 +393,8 @@ template <typename T, int K>
 cudaError_t bwd_k(const void* x, const float* w, const float* b, const void* dy, void* dx, float* dwp,
                   const DwPlan& p, int act, cudaStream_t st) {
     const int groups = (p.g.planes + p.g.ppc - 1) / p.g.ppc;
-    const int per_sm = static_cast<int>(std::max<size_t>(1, std::min<size_t>(6, (200 * 1024) / (p.smem_bwd + 1024))));
+    const int per_sm = static_cast<int>(std::max<size_t>(
+        1, std::min<size_t>({6, (200 * 1024) / (p.smem_bwd + 1024), static_cast<size_t>(65536 / (104 * p.threads))})));
     const int grid = std::min(groups, sm_count() * per_sm);
     auto go = [&](auto kern) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);

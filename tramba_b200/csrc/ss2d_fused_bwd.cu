@@ -186,7 +186,7 @@ __global__ void __launch_bounds__(NT, 1) ss2d_bwd_kernel(const FusedArgs p, cons
                         const float u = to_f32(xq[px]);
                         const float raw = sp[m] + bias;
                         float e;
-                        sp[m] = SOFTPLUS ? softplus20(raw, e) : raw;
+                        sp[m] = !SOFTPLUS ? raw : (ES == 2 ? softplus20_fast(raw) : softplus20(raw, e));
                         const float a = ex2f(sp[m] * A2);
                         const float bb = sp[m] * Bv[h2] * u;
                         const float g = Cv[h2] * yq[px];
@@ -268,8 +268,12 @@ __global__ void __launch_bounds__(NT, 1) ss2d_bwd_kernel(const FusedArgs p, cons
                     // sigmoid(raw) = 1 - exp(-softplus(raw)) = -expm1(-sp); series below 1/8 keeps
                     // fp32 relative accuracy where 1 - exp(.) would cancel
                     const float t = sp[m];
-                    const float ser = t * (1.0f - t * (0.5f - t * (0.16666667f - t * 0.041666668f)));
-                    dd *= (t < 0.125f) ? ser : (1.0f - ex2f(-t * kLog2e));
+                    if (ES == 2) {  // 16-bit operands: the cancellation error of 1 - exp(-t) (<= 6e-8 absolute) is moot
+                        dd *= 1.0f - ex2f(-t * kLog2e);
+                    } else {
+                        const float ser = t * (1.0f - t * (0.5f - t * (0.16666667f - t * 0.041666668f)));
+                        dd *= (t < 0.125f) ? ser : (1.0f - ex2f(-t * kLog2e));
+                    }
                 }
                 accB[m] = fmaf(dhs, u, accB[m]);
                 accC[m] = fmaf(dyv, h, accC[m]);

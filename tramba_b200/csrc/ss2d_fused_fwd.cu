@@ -132,7 +132,7 @@ __global__ void __launch_bounds__(NT, 1) ss2d_fwd_kernel(const FusedArgs p) {
                     const float u = to_f32(xq[px]);
                     const float raw = dl[m] + bias;
                     float e;
-                    const float dsp = SOFTPLUS ? softplus20(raw, e) : raw;
+                    const float dsp = !SOFTPLUS ? raw : (ES == 2 ? softplus20_fast(raw) : softplus20(raw, e));
                     const float a = ex2f(dsp * A2);
                     const float bb = dsp * Bv[m] * u;
                     Sacc = fmaf(a, Sacc, bb);
