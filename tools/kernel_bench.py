@@ -29,6 +29,7 @@ def timeit(fn, reps, flush):
     ts = []
     for _ in range(reps):
         flush.zero_()
+        torch.cuda._sleep(200000)   # keep the GPU busy while the CPU enqueues: no launch gap inside the events
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
         fn()

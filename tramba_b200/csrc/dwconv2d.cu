@@ -31,25 +31,47 @@ struct DwGeom {
     int ppc;           // planes per CTA iteration
     int planes;        // B * C
     int C;
+    unsigned mg_per, mg_cw;   // ceil(2^32 / d) for d = H*(W/4) and d = W/4: e / d == umulhi(e, mg) for e*d < 2^32
 };
 
-template <typename T>
-__device__ __forceinline__ void stage_plane(float* __restrict__ dst, const T* __restrict__ src, const DwGeom& g,
-                                            int pad, int tid, int nthr) {
-    // interior: dst[(h + pad) * ld + kHaloL + w] = src[h * W + w]; halo stays zero (cleared once)
+__device__ __forceinline__ int fast_div(int e, unsigned mg, int d) {
+    return d == 1 ? e : static_cast<int>(__umulhi(static_cast<unsigned>(e), mg));
+}
+
+// Stage `np` consecutive global planes (contiguous in memory) into their shared planes: interior
+// element (h, w) of plane pl lands at dst[pl*psz + (h + pad)*ld + kHaloL + w]; the halo stays zero
+// (cleared once per CTA).  One flat, fully coalesced sweep over all planes, U 16/8-byte loads in flight per
+// thread before the first shared store (U = 1 for the register-bound 7x7 kernels).
+template <typename T, int U>
+__device__ __forceinline__ void stage_planes(float* __restrict__ dst, const T* __restrict__ src, int np, int psz,
+                                             const DwGeom& g, int pad, int tid, int nthr) {
     const int W = g.W, H = g.H;
     if ((W & 3) == 0) {
-        const int cw = W >> 2;
-        for (int e = tid; e < H * cw; e += nthr) {
-            const int h = e / cw, c = e - h * cw;
-            float v[4];
-            load_vec<4, T>(src + static_cast<size_t>(h) * W + c * 4, v);
-            *reinterpret_cast<float4*>(dst + (h + pad) * g.ld + kHaloL + c * 4) = make_float4(v[0], v[1], v[2], v[3]);
+        const int cw = W >> 2, per = H * cw, total = np * per;
+        for (int e0 = tid; e0 < total; e0 += U * nthr) {
+            float v[U][4];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int e = e0 + u * nthr;
+                if (e < total) load_vec<4, T>(src + static_cast<size_t>(e) * 4, v[u]);
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int e = e0 + u * nthr;
+                if (e < total) {
+                    const int pl = fast_div(e, g.mg_per, per), r = e - pl * per;
+                    const int h = fast_div(r, g.mg_cw, cw), c = r - h * cw;
+                    *reinterpret_cast<float4*>(dst + pl * psz + (h + pad) * g.ld + kHaloL + c * 4) =
+                        make_float4(v[u][0], v[u][1], v[u][2], v[u][3]);
+                }
+            }
         }
     } else {
-        for (int e = tid; e < H * W; e += nthr) {
-            const int h = e / W, w = e - h * W;
-            dst[(h + pad) * g.ld + kHaloL + w] = to_f32(src[e]);
+        const int per = H * W, total = np * per;
+        for (int e = tid; e < total; e += nthr) {
+            const int pl = e / per, r = e - pl * per;
+            const int h = r / W, w = r - h * W;
+            dst[pl * psz + (h + pad) * g.ld + kHaloL + w] = to_f32(src[e]);
         }
     }
 }
@@ -119,8 +141,7 @@ __global__ void __launch_bounds__(320, 2) dwconv_fwd_kernel(const T* __restrict_
         __syncthreads();                          // previous iteration's readers are done
         const int p0 = grp * g.ppc;
         const int np = min(g.ppc, g.planes - p0);
-        for (int pl = 0; pl < np; ++pl)
-            stage_plane<T>(sm + pl * psz, x + static_cast<size_t>(p0 + pl) * g.H * g.W, g, PAD, tid, nthr);
+        stage_planes<T, (K == 7 ? 1 : 4)>(sm, x + static_cast<size_t>(p0) * g.H * g.W, np, psz, g, PAD, tid, nthr);
         for (int e = tid; e < np * (K * K + 1); e += nthr) {
             const int pl = e / (K * K + 1), i = e - pl * (K * K + 1);
             const int c = (p0 + pl) % g.C;
@@ -153,7 +174,7 @@ __global__ void __launch_bounds__(320, 2) dwconv_fwd_kernel(const T* __restrict_
     }
 }
 
-// Backward.  Shared: plane X (input, zero halo) and plane G (g = dy * act'(pre), zero halo).
+// Backward.  Shared: plane X (input, zero halo) and plane G (dy, scaled in place to g = dy * act'(pre); zero halo).
 template <typename T, int K, int ACT>
 __global__ void __launch_bounds__(320, 2) dwconv_bwd_kernel(const T* __restrict__ x, const float* __restrict__ wgt,
                                                          const float* __restrict__ bias, const T* __restrict__ dy,
@@ -179,10 +200,8 @@ __global__ void __launch_bounds__(320, 2) dwconv_bwd_kernel(const T* __restrict_
         __syncthreads();
         const int p0 = grp * g.ppc;
         const int np = min(g.ppc, g.planes - p0);
-        for (int pl = 0; pl < np; ++pl) {
-            stage_plane<T>(sX + pl * psz, x + static_cast<size_t>(p0 + pl) * g.H * g.W, g, PAD, tid, nthr);
-            if (!ACT) stage_plane<T>(sG + pl * psz, dy + static_cast<size_t>(p0 + pl) * g.H * g.W, g, PAD, tid, nthr);
-        }
+        stage_planes<T, (K == 7 ? 1 : 4)>(sX, x + static_cast<size_t>(p0) * g.H * g.W, np, psz, g, PAD, tid, nthr);
+        stage_planes<T, (K == 7 ? 1 : 4)>(sG, dy + static_cast<size_t>(p0) * g.H * g.W, np, psz, g, PAD, tid, nthr);
         for (int e = tid; e < np * (KK + 1); e += nthr) {
             const int pl = e / (KK + 1), i = e - pl * (KK + 1);
             const int c = (p0 + pl) % g.C;
@@ -208,22 +227,14 @@ __global__ void __launch_bounds__(320, 2) dwconv_bwd_kernel(const T* __restrict_
 #pragma unroll
                     for (int j = 0; j < TW; ++j) acc[o][j] = bc;
                 conv_tile<K>(acc, sX + q * psz, g.ld, h0, w0, wt);
-                const T* dyp = dy + static_cast<size_t>(p0 + q) * g.H * g.W;
 #pragma unroll
                 for (int o = 0; o < RH; ++o) {
-                    if (h0 + o < g.H) {
-                        float d[TW];
-                        if ((g.W & 3) == 0) {
-                            load_vec<4, T>(dyp + static_cast<size_t>(h0 + o) * g.W + w0, d);
-                        } else {
-#pragma unroll
-                            for (int j = 0; j < TW; ++j)
-                                d[j] = (w0 + j < g.W) ? to_f32(dyp[static_cast<size_t>(h0 + o) * g.W + w0 + j]) : 0.f;
-                        }
-#pragma unroll
-                        for (int j = 0; j < TW; ++j) gt[o][j] = d[j] * silu_df(acc[o][j]);
-                        *reinterpret_cast<float4*>(sG + q * psz + (h0 + o + PAD) * g.ld + kHaloL + w0) =
-                            make_float4(gt[o][0], gt[o][1], gt[o][2], gt[o][3]);
+                    if (h0 + o < g.H) {   // dy was staged into plane G with x: scale it in place
+                        float4* gp = reinterpret_cast<float4*>(sG + q * psz + (h0 + o + PAD) * g.ld + kHaloL + w0);
+                        const float4 d = *gp;
+                        gt[o][0] = d.x * silu_df(acc[o][0]), gt[o][1] = d.y * silu_df(acc[o][1]);
+                        gt[o][2] = d.z * silu_df(acc[o][2]), gt[o][3] = d.w * silu_df(acc[o][3]);
+                        *gp = make_float4(gt[o][0], gt[o][1], gt[o][2], gt[o][3]);
                     }
                 }
             }
@@ -332,6 +343,11 @@ DwPlan dw_plan(int B, int C, int H, int W, int K) {
     g.H = H, g.W = W, g.C = C, g.planes = B * C;
     g.tw = (W + TW - 1) / TW;
     g.th = (H + RH - 1) / RH;
+    {
+        const unsigned long long cw = W / 4 > 0 ? W / 4 : 1, per = static_cast<unsigned long long>(H) * cw;
+        g.mg_cw = static_cast<unsigned>(((1ull << 32) + cw - 1) / cw);
+        g.mg_per = static_cast<unsigned>(((1ull << 32) + per - 1) / per);
+    }
     g.rows = g.th * RH + K - 1;
     g.ld = kHaloL + g.tw * TW + 4;
     int tpp = g.tw * g.th;

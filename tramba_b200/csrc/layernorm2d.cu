@@ -58,12 +58,30 @@ __device__ __forceinline__ void st_px(T* __restrict__ p, const float (&v)[PPL]) 
     }
 }
 
-// exact GELU (nn.GELU default, approximate='none') and its derivative
-__device__ __forceinline__ float gelu_f(float z) { return 0.5f * z * (1.0f + erff(z * 0.70710678118654752f)); }
+// exact-form GELU (nn.GELU default, approximate='none': z * Phi(z)) and its derivative.  Phi through
+// Abramowitz-Stegun 7.1.26, erf(x) = 1 - (a1 t + ... + a5 t^5) exp(-x^2), t = 1/(1 + p x) (|error| <= 1.5e-7,
+// far inside the fp32 tolerance): one ex2 + one rcp + 7 FMAs instead of libdevice's erff, and the
+// exponential exp(-z^2/2) it needs IS the Gaussian density of the derivative.
+__device__ __forceinline__ void gelu_parts(float z, float& cdf, float& ez) {
+    const float x = fabsf(z) * 0.70710678118654752f;
+    const float t = rcpf(fmaf(0.3275911f, x, 1.0f));
+    ez = ex2f(-0.5f * kLog2e * z * z);                       // exp(-z^2 / 2) = exp(-x^2)
+    float p = fmaf(1.061405429f, t, -1.453152027f);
+    p = fmaf(p, t, 1.421413741f);
+    p = fmaf(p, t, -0.284496736f);
+    p = fmaf(p, t, 0.254829592f);
+    const float q = 0.5f * p * t * ez;                       // (1 - erf(x)) / 2 = Phi(-|z|)
+    cdf = z >= 0.f ? 1.0f - q : q;
+}
+__device__ __forceinline__ float gelu_f(float z) {
+    float cdf, ez;
+    gelu_parts(z, cdf, ez);
+    return z * cdf;
+}
 __device__ __forceinline__ float gelu_df(float z) {
-    const float cdf = 0.5f * (1.0f + erff(z * 0.70710678118654752f));
-    const float pdf = 0.3989422804014327f * __expf(-0.5f * z * z);
-    return fmaf(z, pdf, cdf);
+    float cdf, ez;
+    gelu_parts(z, cdf, ez);
+    return fmaf(z * 0.3989422804014327f, ez, cdf);
 }
 
 template <typename in_t, typename out_t, int PPL, int ACT>
@@ -233,14 +251,25 @@ __global__ void __launch_bounds__(512) ln2d_bwd_kernel(const g_t* __restrict__ g
 // ------------------------------------------------------------------------------------------------
 constexpr int kRows = 16;   // channel rows per thread held in registers
 
-// all-CTA reduction of part[2][64]: returns the cluster-wide sums in tot[2][64] (both shared)
-__device__ __forceinline__ void cluster_sum(cg::cluster_group& cluster, float (*part)[64], float (*tot)[64], int cs) {
-    cluster.sync();                                    // every CTA's partials are written
-    if (threadIdx.x < 128) {
-        const int a = threadIdx.x >> 6, i = threadIdx.x & 63;
+constexpr int kMaxWP = 4;   // 64-pixel sub-tiles per CTA (warps side by side along the pixel axis)
+
+// Reduce red[2][nw][64] over the WC warps that share a pixel sub-tile (warp = wc*WP + wp), then over
+// the cluster's CTAs through distributed shared memory: tot[a*WP*64 + wp*64 + i].
+__device__ __forceinline__ void tile_sums(cg::cluster_group& cluster, float (*red)[kMaxWarps][64], float* part,
+                                          float* tot, int cs, int WP, int WC) {
+    __syncthreads();
+    const int n = 2 * WP * 64;
+    for (int idx = threadIdx.x; idx < n; idx += blockDim.x) {
+        const int a = idx / (WP * 64), r = idx - a * WP * 64, wp = r >> 6, i = r & 63;
         float s = 0.f;
-        for (int r = 0; r < cs; ++r) s += cluster.map_shared_rank(&part[0][0], r)[a * 64 + i];
-        tot[a][i] = s;
+        for (int wc = 0; wc < WC; ++wc) s += red[a][wc * WP + wp][i];
+        part[idx] = s;
+    }
+    cluster.sync();                                    // every CTA's partials are written
+    for (int idx = threadIdx.x; idx < n; idx += blockDim.x) {
+        float s = 0.f;
+        for (int r = 0; r < cs; ++r) s += cluster.map_shared_rank(part, r)[idx];
+        tot[idx] = s;
     }
     cluster.sync();                                    // all remote reads done (and tot visible to the CTA)
 }
@@ -249,15 +278,16 @@ template <typename in_t, typename out_t, int ACT>
 __global__ void __launch_bounds__(512) ln2d_fwd_reg_kernel(const in_t* __restrict__ x, const float* __restrict__ w,
                                                            const float* __restrict__ bs, out_t* __restrict__ y,
                                                            float* __restrict__ mean, float* __restrict__ rstd, int C,
-                                                           int L, float eps) {
+                                                           int L, float eps, int WP) {
     __shared__ float red[2][kMaxWarps][64];
-    __shared__ float part[2][64];
-    __shared__ float tot[2][64];
+    __shared__ float part[2 * kMaxWP * 64];
+    __shared__ float tot[2 * kMaxWP * 64];
     cg::cluster_group cluster = cg::this_cluster();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
-    const int cs = gridDim.y, stride = cs * nw, c0 = blockIdx.y * nw + warp;
+    const int WC = nw / WP, wp = warp % WP, wc = warp / WP;
+    const int cs = gridDim.y, stride = cs * WC, c0 = blockIdx.y * WC + wc;
     const int b = blockIdx.z;
-    const int l0 = (blockIdx.x * 32 + lane) * 2;
+    const int l0 = ((blockIdx.x * WP + wp) * 32 + lane) * 2;
     const bool ok = l0 < L;
     const in_t* xb = x + static_cast<size_t>(b) * C * L + l0;
     float v[kRows][2], k0[2] = {0.f, 0.f}, s1[2] = {0.f, 0.f}, s2[2] = {0.f, 0.f};
@@ -279,25 +309,18 @@ __global__ void __launch_bounds__(512) ln2d_fwd_reg_kernel(const in_t* __restric
     }
     red[0][warp][lane * 2] = s1[0], red[0][warp][lane * 2 + 1] = s1[1];
     red[1][warp][lane * 2] = s2[0], red[1][warp][lane * 2 + 1] = s2[1];
-    __syncthreads();
-    if (threadIdx.x < 128) {
-        const int a = threadIdx.x >> 6, i = threadIdx.x & 63;
-        float s = 0.f;
-        for (int ww = 0; ww < nw; ++ww) s += red[a][ww][i];
-        part[a][i] = s;
-    }
-    cluster_sum(cluster, part, tot, cs);
+    tile_sums(cluster, red, part, tot, cs, WP, WC);
     if (!ok) return;
     const float inv = 1.0f / static_cast<float>(C);
     float mu[2], rs[2];
 #pragma unroll
     for (int j = 0; j < 2; ++j) {
-        const float m = tot[0][lane * 2 + j] * inv;
-        const float var = fmaxf(fmaf(-m, m, tot[1][lane * 2 + j] * inv), 0.f);
+        const float m = tot[wp * 64 + lane * 2 + j] * inv;
+        const float var = fmaxf(fmaf(-m, m, tot[WP * 64 + wp * 64 + lane * 2 + j] * inv), 0.f);
         mu[j] = m + k0[j];
         rs[j] = rsqrtf(var + eps);
     }
-    if (blockIdx.y == 0 && warp == 0) {
+    if (blockIdx.y == 0 && wc == 0) {
         if (mean) st_px<float, 2>(mean + static_cast<size_t>(b) * L + l0, mu);
         if (rstd) st_px<float, 2>(rstd + static_cast<size_t>(b) * L + l0, rs);
     }
@@ -324,15 +347,16 @@ __global__ void __launch_bounds__(512) ln2d_bwd_reg_kernel(const g_t* __restrict
                                                            const float* __restrict__ mean,
                                                            const float* __restrict__ rstd, in_t* __restrict__ gx,
                                                            float* __restrict__ gw_part, float* __restrict__ gb_part,
-                                                           int C, int L) {
+                                                           int C, int L, int WP) {
     __shared__ float red[2][kMaxWarps][64];
-    __shared__ float part[2][64];
-    __shared__ float tot[2][64];
+    __shared__ float part[2 * kMaxWP * 64];
+    __shared__ float tot[2 * kMaxWP * 64];
     cg::cluster_group cluster = cg::this_cluster();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
-    const int cs = gridDim.y, stride = cs * nw, c0 = blockIdx.y * nw + warp;
+    const int WC = nw / WP, wp = warp % WP, wc = warp / WP;
+    const int cs = gridDim.y, stride = cs * WC, c0 = blockIdx.y * WC + wc;
     const int b = blockIdx.z;
-    const int l0 = (blockIdx.x * 32 + lane) * 2;
+    const int l0 = ((blockIdx.x * WP + wp) * 32 + lane) * 2;
     const bool ok = l0 < L;
     const size_t base = static_cast<size_t>(b) * C * L + l0;
     const in_t* xb = x + base;
@@ -353,8 +377,9 @@ __global__ void __launch_bounds__(512) ln2d_bwd_reg_kernel(const g_t* __restrict
             ld_px<g_t, 2>(gb + static_cast<size_t>(c) * L, g[i]);
         }
     }
-    float* pw = gw_part + (static_cast<size_t>(b) * gridDim.x + blockIdx.x) * C;
-    float* pb = gb_part ? gb_part + (static_cast<size_t>(b) * gridDim.x + blockIdx.x) * C : nullptr;
+    const size_t prow = static_cast<size_t>(b) * gridDim.x * WP + blockIdx.x * WP + wp;   // one row per 64-pixel tile
+    float* pw = gw_part + prow * C;
+    float* pb = gb_part ? gb_part + prow * C : nullptr;
 #pragma unroll
     for (int i = 0; i < kRows; ++i) {
         const int c = c0 + i * stride;
@@ -387,18 +412,13 @@ __global__ void __launch_bounds__(512) ln2d_bwd_reg_kernel(const g_t* __restrict
     }
     red[0][warp][lane * 2] = s1[0], red[0][warp][lane * 2 + 1] = s1[1];
     red[1][warp][lane * 2] = s2[0], red[1][warp][lane * 2 + 1] = s2[1];
-    __syncthreads();
-    if (threadIdx.x < 128) {
-        const int a = threadIdx.x >> 6, i = threadIdx.x & 63;
-        float s = 0.f;
-        for (int ww = 0; ww < nw; ++ww) s += red[a][ww][i];
-        part[a][i] = s;
-    }
-    cluster_sum(cluster, part, tot, cs);
+    tile_sums(cluster, red, part, tot, cs, WP, WC);
     if (!ok) return;
     const float inv = 1.0f / static_cast<float>(C);
-    const float m1[2] = {tot[0][lane * 2] * inv, tot[0][lane * 2 + 1] * inv};
-    const float m2[2] = {tot[1][lane * 2] * inv, tot[1][lane * 2 + 1] * inv};
+    const float* t1 = tot + wp * 64 + lane * 2;
+    const float* t2 = tot + WP * 64 + wp * 64 + lane * 2;
+    const float m1[2] = {t1[0] * inv, t1[1] * inv};
+    const float m2[2] = {t2[0] * inv, t2[1] * inv};
     in_t* ob = gx + base;
 #pragma unroll
     for (int i = 0; i < kRows; ++i) {
@@ -416,6 +436,7 @@ __global__ void __launch_bounds__(512) ln2d_bwd_reg_kernel(const g_t* __restrict
 struct LnPlan {
     int ppl, threads, tiles;
     int cs;   // > 0: register-resident cluster kernels with cs CTAs per pixel tile; 0: streaming kernels
+    int wp;   // 64-pixel sub-tiles per CTA (register-resident kernels)
 };
 LnPlan ln_plan(int B, int C, int L) {
     static int sms = 0;
@@ -425,20 +446,33 @@ LnPlan ln_plan(int B, int C, int L) {
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     }
     LnPlan p;
-    p.cs = 0;
+    p.cs = 0, p.wp = 1;
     if (L % 2 == 0) {
-        // register-resident plan: 64-pixel tiles; the smallest cluster size that yields >= 2 CTAs per SM
-        // (at most 8, the portable limit) and at most kRows channel rows per thread
-        const int tiles = (L + 63) / 64;
-        int cs = 1;
-        while (cs < 8 && static_cast<long long>(B) * tiles * cs < 2LL * sms) cs *= 2;
-        while (cs > 1 && C < cs * 8) cs /= 2;
-        int nw = 8;
-        auto rows = [&](int c_s, int n_w) { return (C + c_s * n_w - 1) / (c_s * n_w); };
-        if (rows(cs, nw) > kRows) nw = 16;
-        while (rows(cs, nw) > kRows && cs < 8) cs *= 2;
-        if (rows(cs, nw) <= kRows) {
-            p.cs = cs, p.ppl = 2, p.tiles = tiles, p.threads = nw * 32;
+        // register-resident plan: 8 warps per CTA arranged as WP 64-pixel sub-tiles (side by side: one
+        // channel row of the CTA is WP*64 contiguous pixels) x WC channel groups; a cluster of cs CTAs splits
+        // the channels further so that a thread holds at most kRows rows and the machine is full.  Measured:
+        // cluster syncs cost more than narrow rows, so the SMALLEST cluster wins (cs <= 8, the portable limit).
+        const int t64 = (L + 63) / 64;
+        auto pow2_ge = [](long long v) { int r = 1; while (r < v) r *= 2; return r; };
+        const long long want = 3LL * sms / 2;          // CTAs for a full machine
+        int best_cs = 1 << 30, best_wp = 0, best_nw = 8;
+        for (int wp = kMaxWP; wp >= 1; wp /= 2) {
+            int nw = 8, wc = nw / wp;
+            int cs_min = pow2_ge((C + kRows * wc - 1) / (kRows * wc));
+            if (cs_min > 8 && wp == 1) {   // very wide: 16 warps
+                nw = 16, wc = 16;
+                cs_min = pow2_ge((C + kRows * wc - 1) / (kRows * wc));
+            }
+            if (cs_min > 8) continue;
+            const long long base = static_cast<long long>(B) * ((t64 + wp - 1) / wp);
+            int cs = cs_min;
+            while (cs < 8 && base * cs < want) cs *= 2;
+            while (cs > cs_min && C < cs * wc) cs /= 2;
+            if (cs < best_cs) best_cs = cs, best_wp = wp, best_nw = nw;   // smallest cluster; ties keep the wider tile
+        }
+        if (best_wp) {
+            p.cs = best_cs, p.wp = best_wp, p.ppl = 2, p.threads = best_nw * 32;
+            p.tiles = ((t64 + best_wp - 1) / best_wp) * best_wp;   // rows of the dweight / dbias partials per image
             return p;
         }
     }
@@ -460,15 +494,15 @@ cudaError_t fwd_t(const void* x, const float* w, const float* b, void* y, float*
     out_t* yo = static_cast<out_t*>(y);
     if (p.cs > 0) {
         cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = dim3(p.tiles, p.cs, B);
+        cfg.gridDim = dim3(p.tiles / p.wp, p.cs, B);
         cfg.blockDim = dim3(p.threads);
         cfg.stream = st;
         cudaLaunchAttribute attr[1];
         attr[0].id = cudaLaunchAttributeClusterDimension;
         attr[0].val.clusterDim.x = 1, attr[0].val.clusterDim.y = p.cs, attr[0].val.clusterDim.z = 1;
         cfg.attrs = attr, cfg.numAttrs = 1;
-        cudaError_t e = act ? cudaLaunchKernelEx(&cfg, ln2d_fwd_reg_kernel<in_t, out_t, 1>, xi, w, b, yo, mean, rstd, C, L, eps)
-                            : cudaLaunchKernelEx(&cfg, ln2d_fwd_reg_kernel<in_t, out_t, 0>, xi, w, b, yo, mean, rstd, C, L, eps);
+        cudaError_t e = act ? cudaLaunchKernelEx(&cfg, ln2d_fwd_reg_kernel<in_t, out_t, 1>, xi, w, b, yo, mean, rstd, C, L, eps, p.wp)
+                            : cudaLaunchKernelEx(&cfg, ln2d_fwd_reg_kernel<in_t, out_t, 0>, xi, w, b, yo, mean, rstd, C, L, eps, p.wp);
         note_launch();
         return e != cudaSuccess ? e : cudaGetLastError();
     }
@@ -493,15 +527,15 @@ cudaError_t bwd_t(const void* gy, const void* x, const float* w, const float* b,
     in_t* go = static_cast<in_t*>(gx);
     if (p.cs > 0) {
         cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = dim3(p.tiles, p.cs, B);
+        cfg.gridDim = dim3(p.tiles / p.wp, p.cs, B);
         cfg.blockDim = dim3(p.threads);
         cfg.stream = st;
         cudaLaunchAttribute attr[1];
         attr[0].id = cudaLaunchAttributeClusterDimension;
         attr[0].val.clusterDim.x = 1, attr[0].val.clusterDim.y = p.cs, attr[0].val.clusterDim.z = 1;
         cfg.attrs = attr, cfg.numAttrs = 1;
-        cudaError_t e = act ? cudaLaunchKernelEx(&cfg, ln2d_bwd_reg_kernel<in_t, g_t, 1>, gi, xi, w, b, mean, rstd, go, gw_part, gb_part, C, L)
-                            : cudaLaunchKernelEx(&cfg, ln2d_bwd_reg_kernel<in_t, g_t, 0>, gi, xi, w, b, mean, rstd, go, gw_part, gb_part, C, L);
+        cudaError_t e = act ? cudaLaunchKernelEx(&cfg, ln2d_bwd_reg_kernel<in_t, g_t, 1>, gi, xi, w, b, mean, rstd, go, gw_part, gb_part, C, L, p.wp)
+                            : cudaLaunchKernelEx(&cfg, ln2d_bwd_reg_kernel<in_t, g_t, 0>, gi, xi, w, b, mean, rstd, go, gw_part, gb_part, C, L, p.wp);
         note_launch();
         return e != cudaSuccess ? e : cudaGetLastError();
     }
