@@ -197,6 +197,24 @@ TRAMBA_API int tramba_dct2d_bwd(const float* ghigh, const float* glow, const flo
                      float* gx, int planes, int H, int W, void* stream);
 
 /* ----------------------------------------------------------------------------------------
+ * Projected-channel gather (host side of the fused core).  x_proj is a per-token linear map, so the
+ * fused path evaluates it once on the image-ordered map; these two entry points carry its R + 2N
+ * output channels into scan order and split them -- what CrossScan* -> x_proj -> torch.split produce
+ * in the reference (Models/vmamba.py:231-235), at 1/25 of the traffic -- and back:
+ *   gather : src (B, K, R+2N, L) image order -> dts (B, K, R, L), Bs (B, K, N, L), Cs (B, K, N, L),
+ *            out[b,k,c,t] = src[b,k,c, idx[k][t]]
+ *   scatter: the adjoint, gsrc[b,k,c,p] = sum_{t: idx[k][t]==p} g[b,k,c,t], as a deterministic gather
+ *            through the plan's inverse (CSR) table (no atomics; duplicate helix hits in token order).
+ * plan_dev = device copy of tramba_order_plan(order, H, W, param).  dtype F32 / BF16; the scatter's
+ * gBs / gCs may be F32 while gdts / gsrc are BF16 (bc_dtype).
+ * -------------------------------------------------------------------------------------- */
+TRAMBA_API int tramba_proj_gather(const void* src, void* dts, void* Bs, void* Cs, const int32_t* plan_dev, int K,
+                                  int B, int R, int N, int L, int dtype, void* stream);
+TRAMBA_API int tramba_proj_scatter(const void* gdts, const void* gBs, const void* gCs, void* gsrc,
+                                   const int32_t* plan_dev, int K, int B, int R, int N, int L, int dtype, int bc_dtype,
+                                   void* stream);
+
+/* ----------------------------------------------------------------------------------------
  * LayerNorm2d (+ GELU): layer norm over the CHANNEL axis of a channel-first (B, C, L) map.
  * Replaces LayerNorm2d.forward (Models/modules.py:22-27: permute -> F.layer_norm -> permute)
  * and, with act = TRAMBA_ACT_GELU, the out_norm -> out_act chain applied to the merged map

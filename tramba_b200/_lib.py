@@ -42,6 +42,8 @@ SIGNATURES = {
     "tramba_layernorm2d_tiles": (_i, [_i, _i, _i]),
     "tramba_layernorm2d_fwd": (_i, [_vp, _fp, _fp, _vp, _fp, _fp, _i, _i, _i, ctypes.c_float, _i, _i, _i, _vp]),
     "tramba_layernorm2d_bwd": (_i, [_vp, _vp, _fp, _fp, _fp, _fp, _vp, _fp, _fp] + [_i] * 6 + [_vp]),
+    "tramba_proj_gather": (_i, [_vp, _vp, _vp, _vp, _i32p] + [_i] * 6 + [_vp]),
+    "tramba_proj_scatter": (_i, [_vp, _vp, _vp, _vp, _i32p] + [_i] * 7 + [_vp]),
     "tramba_dwconv2d_supported": (_i, [_i] * 5),
     "tramba_dwconv2d_fwd": (_i, [_vp, _fp, _fp, _vp] + [_i] * 7 + [_vp]),
     "tramba_dwconv2d_bwd": (_i, [_vp, _fp, _fp, _vp, _vp, _fp] + [_i] * 7 + [_vp]),

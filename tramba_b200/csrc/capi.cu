@@ -47,6 +47,11 @@ cudaError_t launch_dwconv2d_fwd(const void* x, const float* w, const float* b, v
 cudaError_t launch_dwconv2d_bwd(const void* x, const float* w, const float* b, const void* dy, void* dx, float* dwp,
                                 int B, int C, int H, int W, int K, int act, int dtype, cudaStream_t st);
 
+cudaError_t launch_proj_gather(const void* src, void* dts, void* Bs, void* Cs, const int32_t* plan, int K, int B, int R,
+                               int N, int L, int dtype, cudaStream_t st);
+cudaError_t launch_proj_scatter(const void* gdts, const void* gBs, const void* gCs, void* gsrc, const int32_t* plan,
+                                int K, int B, int R, int N, int L, int dtype, int bc_dtype, cudaStream_t st);
+
 static int elem_size(int dtype) {
     switch (dtype) {
         case TRAMBA_F32: return 4;
@@ -508,5 +513,31 @@ extern "C" int tramba_dwconv2d_bwd(const void* x, const float* weight, const flo
     int rc = check_device();
     if (rc != TRAMBA_OK) return rc;
     return cuda_rc(launch_dwconv2d_bwd(x, weight, bias, dy, dx, dw_part, B, C, H, W, K, act != TRAMBA_ACT_NONE, dtype,
+                                       static_cast<cudaStream_t>(stream)));
+}
+
+// ------------------------------------------------------------------------------ projected-channel gather
+extern "C" int tramba_proj_gather(const void* src, void* dts, void* Bs, void* Cs, const int32_t* plan_dev, int K,
+                                  int B, int R, int N, int L, int dtype, void* stream) {
+    if (!src || !dts || !Bs || !Cs || !plan_dev) return TRAMBA_E_NULL;
+    if (K <= 0 || B <= 0 || R <= 0 || N <= 0 || L <= 0) return TRAMBA_E_SHAPE;
+    if (!ln_dtype_ok(dtype)) return TRAMBA_E_DTYPE;
+    if (static_cast<size_t>(L) * 4 > 200 * 1024) return TRAMBA_E_LIMIT;
+    int rc = check_device();
+    if (rc != TRAMBA_OK) return rc;
+    return cuda_rc(launch_proj_gather(src, dts, Bs, Cs, plan_dev, K, B, R, N, L, dtype, static_cast<cudaStream_t>(stream)));
+}
+
+extern "C" int tramba_proj_scatter(const void* gdts, const void* gBs, const void* gCs, void* gsrc,
+                                   const int32_t* plan_dev, int K, int B, int R, int N, int L, int dtype, int bc_dtype,
+                                   void* stream) {
+    if (!gdts || !gBs || !gCs || !gsrc || !plan_dev) return TRAMBA_E_NULL;
+    if (K <= 0 || B <= 0 || R <= 0 || N <= 0 || L <= 0) return TRAMBA_E_SHAPE;
+    if (!ln_dtype_ok(dtype) || !ln_dtype_ok(bc_dtype) || (dtype == TRAMBA_F32 && bc_dtype != TRAMBA_F32))
+        return TRAMBA_E_DTYPE;
+    if (static_cast<size_t>(L) * 4 > 200 * 1024) return TRAMBA_E_LIMIT;
+    int rc = check_device();
+    if (rc != TRAMBA_OK) return rc;
+    return cuda_rc(launch_proj_scatter(gdts, gBs, gCs, gsrc, plan_dev, K, B, R, N, L, dtype, bc_dtype,
                                        static_cast<cudaStream_t>(stream)));
 }

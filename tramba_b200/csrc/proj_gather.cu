@@ -1,0 +1,125 @@
+// Per-direction gather of the projected per-token channels into scan order, and its adjoint.
+//
+// The fused SS2D core evaluates x_proj ONCE on the image-ordered map (it is a per-token linear map, so
+// it commutes with the cross-scan gather; Models/vmamba.py:233-236).  What the scan consumes is that
+// result in SCAN order, split into the dt-rank channels, B and C:
+//     src (B, K, R + 2N, L) image order  ->  dts_r (B, K, R, L), Bs (B, K, N, L), Cs (B, K, N, L)
+//     out[b, k, c, t] = src[b, k, c, idx[k][t]]
+// i.e. the reference's xs -> x_dbl -> torch.split (vmamba.py:231-235) restricted to the R + 2N projected
+// channels (1/25 of a cross-scan of the feature map).  One kernel replaces gather + split + three
+// .contiguous() copies; the adjoint (one kernel) replaces cat + zero-fill + scatter_add_: it is a
+// GATHER through the inverse (CSR) table of the order plan, so duplicate hits of the helix lines are
+// added deterministically in token order, without atomics.
+#include <type_traits>
+
+#include "common.cuh"
+
+namespace tramba {
+
+namespace {
+
+constexpr int kThreads = 256;
+
+// row = (b, k, c); the row is staged in shared memory once (coalesced), the permuted side is an LDS
+template <typename T>
+__global__ void __launch_bounds__(kThreads) proj_gather_kernel(const T* __restrict__ src, T* __restrict__ dts,
+                                                               T* __restrict__ Bs, T* __restrict__ Cs,
+                                                               const int32_t* __restrict__ table, int K, int R, int N,
+                                                               int L) {
+    extern __shared__ float srow[];
+    const int CX = R + 2 * N;
+    const int row = blockIdx.x;               // (b * K + k) * CX + c
+    const int c = row % CX, bk = row / CX, k = bk % K;
+    const T* s = src + static_cast<size_t>(row) * L;
+    for (int e = threadIdx.x; e < L; e += kThreads) srow[e] = to_f32(s[e]);
+    __syncthreads();
+    T* out = c < R ? dts + (static_cast<size_t>(bk) * R + c) * L
+                   : c < R + N ? Bs + (static_cast<size_t>(bk) * N + (c - R)) * L
+                               : Cs + (static_cast<size_t>(bk) * N + (c - R - N)) * L;
+    const int32_t* tk = table + static_cast<size_t>(k) * L;
+    for (int t = threadIdx.x; t < L; t += kThreads) out[t] = from_f32<T>(srow[__ldg(tk + t)]);
+}
+
+// adjoint: gsrc[b, k, c, p] = sum_{t : idx[k][t] == p} g[b, k, c, t], tokens of a pixel in ascending order
+template <typename T, typename G>
+__global__ void __launch_bounds__(kThreads) proj_scatter_kernel(const T* __restrict__ gdts, const G* __restrict__ gBs,
+                                                                const G* __restrict__ gCs, T* __restrict__ gsrc,
+                                                                const int32_t* __restrict__ ent,
+                                                                const int32_t* __restrict__ off, int K, int R, int N,
+                                                                int L) {
+    extern __shared__ float srow[];
+    const int CX = R + 2 * N;
+    const int row = blockIdx.x;
+    const int c = row % CX, bk = row / CX, k = bk % K;
+    if (c < R) {
+        const T* g = gdts + (static_cast<size_t>(bk) * R + c) * L;
+        for (int e = threadIdx.x; e < L; e += kThreads) srow[e] = to_f32(g[e]);
+    } else {
+        const G* g = c < R + N ? gBs + (static_cast<size_t>(bk) * N + (c - R)) * L
+                               : gCs + (static_cast<size_t>(bk) * N + (c - R - N)) * L;
+        for (int e = threadIdx.x; e < L; e += kThreads) srow[e] = to_f32(g[e]);
+    }
+    __syncthreads();
+    const int32_t* ek = ent + static_cast<size_t>(k) * L;
+    const int32_t* ok = off + static_cast<size_t>(k) * (L + 1);
+    T* out = gsrc + static_cast<size_t>(row) * L;
+    for (int p = threadIdx.x; p < L; p += kThreads) {
+        const int e0 = __ldg(ok + p), e1 = __ldg(ok + p + 1);
+        float acc = 0.f;
+        for (int e = e0; e < e1; ++e) acc += srow[__ldg(ek + e)];
+        out[p] = from_f32<T>(acc);
+    }
+}
+
+}  // namespace
+
+cudaError_t launch_proj_gather(const void* src, void* dts, void* Bs, void* Cs, const int32_t* plan, int K, int B, int R,
+                               int N, int L, int dtype, cudaStream_t st) {
+    const int rows = B * K * (R + 2 * N);
+    const size_t smem = static_cast<size_t>(L) * sizeof(float);
+    if (smem > 200 * 1024) return cudaErrorInvalidConfiguration;
+    auto go = [&](auto kern, auto* tp) {
+        using T = std::remove_pointer_t<decltype(tp)>;
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        if (e != cudaSuccess) return e;
+        kern<<<rows, kThreads, smem, st>>>(static_cast<const T*>(src), static_cast<T*>(dts), static_cast<T*>(Bs),
+                                           static_cast<T*>(Cs), plan, K, R, N, L);
+        return cudaGetLastError();
+    };
+    cudaError_t e = cudaErrorInvalidValue;
+    if (dtype == TRAMBA_F32) e = go(proj_gather_kernel<float>, static_cast<float*>(nullptr));
+    if (dtype == TRAMBA_BF16) e = go(proj_gather_kernel<__nv_bfloat16>, static_cast<__nv_bfloat16*>(nullptr));
+    note_launch();
+    return e;
+}
+
+// gdts has `dtype`; gBs / gCs have `bc_dtype` (the fused core returns them in fp32)
+cudaError_t launch_proj_scatter(const void* gdts, const void* gBs, const void* gCs, void* gsrc, const int32_t* plan,
+                                int K, int B, int R, int N, int L, int dtype, int bc_dtype, cudaStream_t st) {
+    const int rows = B * K * (R + 2 * N);
+    const size_t smem = static_cast<size_t>(L) * sizeof(float);
+    if (smem > 200 * 1024) return cudaErrorInvalidConfiguration;
+    const int32_t* ent = plan + static_cast<size_t>(K) * L;
+    const int32_t* off = plan + 2 * static_cast<size_t>(K) * L;
+    auto go = [&](auto kern, auto* tp, auto* gp) {
+        using T = std::remove_pointer_t<decltype(tp)>;
+        using G = std::remove_pointer_t<decltype(gp)>;
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        if (e != cudaSuccess) return e;
+        kern<<<rows, kThreads, smem, st>>>(static_cast<const T*>(gdts), static_cast<const G*>(gBs),
+                                           static_cast<const G*>(gCs), static_cast<T*>(gsrc), ent, off, K, R, N, L);
+        return cudaGetLastError();
+    };
+    using bf = __nv_bfloat16;
+    cudaError_t e = cudaErrorInvalidValue;
+    if (dtype == TRAMBA_F32 && bc_dtype == TRAMBA_F32)
+        e = go(proj_scatter_kernel<float, float>, static_cast<float*>(nullptr), static_cast<float*>(nullptr));
+    else if (dtype == TRAMBA_BF16 && bc_dtype == TRAMBA_F32)
+        e = go(proj_scatter_kernel<bf, float>, static_cast<bf*>(nullptr), static_cast<float*>(nullptr));
+    else if (dtype == TRAMBA_BF16 && bc_dtype == TRAMBA_BF16)
+        e = go(proj_scatter_kernel<bf, bf>, static_cast<bf*>(nullptr), static_cast<bf*>(nullptr));
+    note_launch();
+    return e;
+}
+
+}  // namespace tramba

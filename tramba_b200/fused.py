@@ -135,3 +135,44 @@ class SS2DCoreFused(torch.autograd.Function):
 
 def ss2d_core_fused(x, dts, Bs, Cs, A, Ds, delta_bias, order, param=0, delta_softplus=True):
     return SS2DCoreFused.apply(x, dts, Bs, Cs, A, Ds, delta_bias, order, param, delta_softplus)
+
+
+class ProjGather(torch.autograd.Function):
+    """src (B, K, R+2N, L) image order -> (dts (B, K, R, L), Bs (B, K, N, L), Cs (B, K, N, L)) scan order: the
+    projected channels of the reference's xs -> x_dbl -> split (Models/vmamba.py:231-235) without xs.
+    One kernel each way (tramba_proj_gather / tramba_proj_scatter)."""
+
+    @staticmethod
+    @torch.amp.custom_fwd(device_type="cuda")
+    def forward(ctx, src, order, param, H, R, N):
+        from .ops import _order_plan
+        B, K, CX, L = src.shape
+        src = _c16(src)
+        _, plan = _order_plan(order, H, param, src.device)
+        dts = torch.empty((B, K, R, L), device=src.device, dtype=src.dtype)
+        Bs = torch.empty((B, K, N, L), device=src.device, dtype=src.dtype)
+        Cs = torch.empty((B, K, N, L), device=src.device, dtype=src.dtype)
+        with torch.cuda.device(src.device), _lib.timed("proj_gather", 2 * src.numel() * src.element_size()):
+            _lib.check(_lib.lib.tramba_proj_gather(src.data_ptr(), dts.data_ptr(), Bs.data_ptr(), Cs.data_ptr(),
+                                                   plan.data_ptr(), K, B, R, N, L, _DTYPE[src.dtype], _stream()))
+        ctx.plan = plan
+        ctx.meta = (B, K, R, N, L, src.dtype)
+        return dts, Bs, Cs
+
+    @staticmethod
+    @torch.amp.custom_bwd(device_type="cuda")
+    def backward(ctx, gdts, gBs, gCs):
+        B, K, R, N, L, dt = ctx.meta
+        gdts = _c16(gdts.to(dt))
+        bc = torch.float32 if (gBs.dtype == torch.float32 and gCs.dtype == torch.float32) else dt
+        gBs, gCs = _c16(gBs.to(bc)), _c16(gCs.to(bc))
+        g = torch.empty((B, K, R + 2 * N, L), device=gdts.device, dtype=dt)
+        with torch.cuda.device(gdts.device), _lib.timed("proj_scatter", 2 * g.numel() * g.element_size()):
+            _lib.check(_lib.lib.tramba_proj_scatter(gdts.data_ptr(), gBs.data_ptr(), gCs.data_ptr(), g.data_ptr(),
+                                                    ctx.plan.data_ptr(), K, B, R, N, L, _DTYPE[dt], _DTYPE[bc],
+                                                    _stream()))
+        return g, None, None, None, None, None
+
+
+def proj_gather(src, order, param, H, R, N):
+    return ProjGather.apply(src, order, param, H, R, N)

@@ -18,6 +18,7 @@ import torch.nn.functional as F
 from . import dwconv, fused, norm, ops
 
 
+_PROJ_KERNEL = os.environ.get("TRAMBA_PROJ_GATHER", "kernel") != "torch"  # tramba_proj_gather vs torch.gather + split
 _PROJ_GEMM = os.environ.get("TRAMBA_PROJ", "gemm") == "gemm"   # x_proj / dt_proj as batched GEMMs vs 1x1 conv1d
 
 
@@ -191,9 +192,12 @@ class SS2D(nn.Module):
             x_dbl = torch.bmm(self.x_proj_weight.view(1, -1, D).expand(B, -1, -1), xf).view(B, K, R + 2 * N, L)
         else:
             x_dbl = F.conv1d(xf, self.x_proj_weight.view(-1, D, 1), bias=None).view(B, K, R + 2 * N, L)
-        tok = fused.token_index(order, H, param, x.device)                       # (K, L)
-        x_dbl = x_dbl.gather(3, tok.view(1, K, 1, L).expand(B, K, R + 2 * N, L))  # image -> scan order
-        dts, Bs, Cs = torch.split(x_dbl, [R, N, N], dim=2)
+        if _PROJ_KERNEL:    # one kernel: image -> scan order + split (contiguous dts_r, Bs, Cs)
+            dts, Bs, Cs = fused.proj_gather(x_dbl, order, param, H, R, N)
+        else:
+            tok = fused.token_index(order, H, param, x.device)                       # (K, L)
+            x_dbl = x_dbl.gather(3, tok.view(1, K, 1, L).expand(B, K, R + 2 * N, L))  # image -> scan order
+            dts, Bs, Cs = torch.split(x_dbl, [R, N, N], dim=2)
         if _PROJ_GEMM:
             dts = torch.matmul(self.dt_projs_weight, dts)                        # (K, D, R) @ (B, K, R, L)
         else:
