@@ -190,6 +190,9 @@ TRAMBA_API int tramba_cross_merge_skewed(const void* ys, void* y, const uint16_t
  * H and W even.  _bwd is the adjoint: gx = Wy^T . dY . Wx with dY zero outside the quadrants.
  * -------------------------------------------------------------------------------------- */
 TRAMBA_API void tramba_dct_basis(int n, float* w_out /* n*n, host */); /* DCT_2D.py:37-45 */
+/* 1 when a plane of this size fits the kernels (bases + plane resident in one SM's shared memory: up to
+ * ~128 x 128); larger planes (H = 192 of the 768^2 stress config) return TRAMBA_E_LIMIT from _fwd/_bwd. */
+TRAMBA_API int tramba_dct2d_supported(int H, int W);
 
 TRAMBA_API int tramba_dct2d_fwd(const float* x, const float* wy, const float* wx, float* high, float* low,
                      int planes, int H, int W, void* stream);

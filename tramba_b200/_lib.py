@@ -48,6 +48,7 @@ SIGNATURES = {
     "tramba_dwconv2d_fwd": (_i, [_vp, _fp, _fp, _vp] + [_i] * 7 + [_vp]),
     "tramba_dwconv2d_bwd": (_i, [_vp, _fp, _fp, _vp, _vp, _fp] + [_i] * 7 + [_vp]),
     "tramba_dct_basis": (None, [_i, _fp]),
+    "tramba_dct2d_supported": (_i, [_i, _i]),
     "tramba_dct2d_fwd": (_i, [_fp, _fp, _fp, _fp, _fp, _i, _i, _i, _vp]),
     "tramba_dct2d_bwd": (_i, [_fp, _fp, _fp, _fp, _fp, _i, _i, _i, _vp]),
 }

@@ -284,6 +284,14 @@ extern "C" int tramba_sscan_bwd(const void* u, const void* delta, const float* A
 }
 
 // ------------------------------------------------------------------------------ DCT2D
+extern "C" int tramba_dct2d_supported(int H, int W) {
+    if (H <= 0 || W <= 0 || (H & 1) || (W & 1)) return 0;
+    if (dct2d_tc_supported(H, W)) return 1;
+    // SIMT kernel: plane + intermediate + both bases in one CTA's shared memory (dct2d.cu)
+    const size_t smem = (2ull * H * W + static_cast<size_t>(W) * W + static_cast<size_t>(H) * H) * 4;
+    return smem <= 220 * 1024 ? 1 : 0;
+}
+
 extern "C" int tramba_dct2d_fwd(const float* x, const float* wy, const float* wx, float* high, float* low,
                                 int planes, int H, int W, void* stream) {
     if (!x || !wy || !wx || !high || !low) return TRAMBA_E_NULL;
