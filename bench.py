@@ -49,6 +49,8 @@ def parse():
     ap.add_argument("--no-graph", action="store_true", help="do not capture the step in a CUDA graph")
     ap.add_argument("--unfused", action="store_true", help="op-by-op SS2D path instead of the fused core")
     ap.add_argument("--cpu-budget-s", type=float, default=240.0, help="wall budget of the reference arm")
+    ap.add_argument("--kernel-table", default="", help="write a per-kernel device-time table of 3 graph-replayed "
+                    "steps (torch.profiler / CUPTI; not part of the timed regions) to this file")
     return ap.parse_args()
 
 
@@ -188,6 +190,40 @@ def summarize_prof(prof):
     return agg
 
 
+def write_kernel_table(path, graph_step, sync, steps=3):
+    """Device time per kernel name over `steps` graph-replayed training steps (CUPTI activity records: warm
+    caches, back-to-back launches -- the complement of ncu's serialised cold-cache launch list)."""
+    import collections
+    import re
+    from torch.profiler import ProfilerActivity, profile
+    sync()
+    with profile(activities=[ProfilerActivity.CUDA]) as prof:
+        for _ in range(steps):
+            graph_step()
+        sync()
+    agg = collections.defaultdict(lambda: [0, 0.0])
+    for ev in prof.events():
+        if getattr(ev, "device_type", None) is None or "cuda" not in str(ev.device_type).lower():
+            continue
+        name = ev.name.replace("(anonymous namespace)::", "").replace("<unnamed>::", "")
+        name = re.sub(r"\(.*", "", name)
+        name = re.sub(r"^void ", "", name)[:110]
+        dur = getattr(ev, "device_time", None)
+        if dur is None:
+            dur = getattr(ev, "cuda_time", 0.0)
+        agg[name][0] += 1
+        agg[name][1] += float(dur)
+    tot = sum(v[1] for v in agg.values())
+    with open(path, "w") as f:
+        f.write(f"{steps} graph-replayed steps: {tot / steps / 1e3:.3f} ms device time per step in "
+                f"{sum(v[0] for v in agg.values()) // steps} kernels/memcpys per step\n")
+        ours = sum(v[1] for k, v in agg.items() if "tramba" in k)
+        f.write(f"tramba:: kernels: {100 * ours / max(tot, 1e-9):.2f}% of device time\n")
+        for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1])[:80]:
+            f.write(f"{100 * v[1] / tot:6.2f}% {v[1] / steps / 1e3:9.3f} ms/step {v[0] // steps:6d} x "
+                    f"{v[1] / v[0]:9.1f} us  {k}\n")
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -317,6 +353,9 @@ def run_ours(args):
         g_fb.replay()
         reduce_grads()
         g_opt.replay()
+
+    if args.kernel_table and graph is not None and rank == 0:
+        write_kernel_table(args.kernel_table, graph_step, sync)
 
     # ---- region B (`value`): device-resident inputs
     sync()

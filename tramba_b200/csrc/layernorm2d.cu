@@ -274,6 +274,27 @@ __device__ __forceinline__ void tile_sums(cg::cluster_group& cluster, float (*re
     cluster.sync();                                    // all remote reads done (and tot visible to the CTA)
 }
 
+// Row bookkeeping shared by the two kernels.  Every thread walks kRows channel rows c = c0 + i*stride;
+// rows past the tensor (i >= nvalid, warp-uniform) and lanes past the image (!ok) are handled WITHOUT
+// branches: their loads are redirected to a valid address (the row / pixel is clamped) and their
+// contributions are zeroed by a select, so the unrolled row loops are straight-line code.  The affine
+// parameters of the warp's rows live one per lane (lanes 0..15: weight of row i, lanes 16..31: bias of row
+// i - 16) and are broadcast with a shuffle where needed: one global load per thread instead of three per row.
+struct LnRows {
+    int c0, stride, nvalid;
+    float wb;   // this lane's weight (lane < 16) or bias (lane >= 16) of row (lane & 15)
+};
+__device__ __forceinline__ LnRows ln_rows(const float* __restrict__ w, const float* __restrict__ bs, int C, int c0,
+                                          int stride, int lane) {
+    LnRows r;
+    r.c0 = c0, r.stride = stride;
+    r.nvalid = c0 < C ? min(kRows, (C - c0 + stride - 1) / stride) : 0;
+    const int i = lane & 15, c = c0 + i * stride;
+    r.wb = 0.f;
+    if (i < r.nvalid) r.wb = lane < 16 ? __ldg(w + c) : (bs ? __ldg(bs + c) : 0.f);
+    return r;
+}
+
 template <typename in_t, typename out_t, int ACT>
 __global__ void __launch_bounds__(512) ln2d_fwd_reg_kernel(const in_t* __restrict__ x, const float* __restrict__ w,
                                                            const float* __restrict__ bs, out_t* __restrict__ y,
@@ -285,24 +306,26 @@ __global__ void __launch_bounds__(512) ln2d_fwd_reg_kernel(const in_t* __restric
     cg::cluster_group cluster = cg::this_cluster();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
     const int WC = nw / WP, wp = warp % WP, wc = warp / WP;
-    const int cs = gridDim.y, stride = cs * WC, c0 = blockIdx.y * WC + wc;
+    const int cs = gridDim.y;
+    const LnRows R = ln_rows(w, bs, C, blockIdx.y * WC + wc, cs * WC, lane);
     const int b = blockIdx.z;
     const int l0 = ((blockIdx.x * WP + wp) * 32 + lane) * 2;
     const bool ok = l0 < L;
-    const in_t* xb = x + static_cast<size_t>(b) * C * L + l0;
-    float v[kRows][2], k0[2] = {0.f, 0.f}, s1[2] = {0.f, 0.f}, s2[2] = {0.f, 0.f};
-    if (ok) ld_px<in_t, 2>(xb, k0);
+    const size_t pix = static_cast<size_t>(b) * C * L + (ok ? l0 : 0);
+    const size_t rstep = static_cast<size_t>(R.stride) * L;
+    const int last = max(R.nvalid - 1, 0);
+    const in_t* xr = x + pix + static_cast<size_t>(min(R.c0, C - 1)) * L;
+    float v[kRows][2], k0[2];
+    ld_px<in_t, 2>(x + pix, k0);                                  // channel 0 of the pixel: the shift
+#pragma unroll
+    for (int i = 0; i < kRows; ++i) ld_px<in_t, 2>(xr + static_cast<size_t>(min(i, last)) * rstep, v[i]);
+    float s1[2] = {0.f, 0.f}, s2[2] = {0.f, 0.f};
 #pragma unroll
     for (int i = 0; i < kRows; ++i) {
-        const int c = c0 + i * stride;
-        v[i][0] = k0[0], v[i][1] = k0[1];
-        if (ok && c < C) ld_px<in_t, 2>(xb + static_cast<size_t>(c) * L, v[i]);
-    }
-#pragma unroll
-    for (int i = 0; i < kRows; ++i) {
+        const float m = (i < R.nvalid && ok) ? 1.f : 0.f;
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
-            const float d = v[i][j] - k0[j];            // rows past C hold k0: they add exactly zero
+            const float d = (v[i][j] - k0[j]) * m;
             s1[j] += d;
             s2[j] = fmaf(d, d, s2[j]);
         }
@@ -310,7 +333,6 @@ __global__ void __launch_bounds__(512) ln2d_fwd_reg_kernel(const in_t* __restric
     red[0][warp][lane * 2] = s1[0], red[0][warp][lane * 2 + 1] = s1[1];
     red[1][warp][lane * 2] = s2[0], red[1][warp][lane * 2 + 1] = s2[1];
     tile_sums(cluster, red, part, tot, cs, WP, WC);
-    if (!ok) return;
     const float inv = 1.0f / static_cast<float>(C);
     float mu[2], rs[2];
 #pragma unroll
@@ -320,25 +342,38 @@ __global__ void __launch_bounds__(512) ln2d_fwd_reg_kernel(const in_t* __restric
         mu[j] = m + k0[j];
         rs[j] = rsqrtf(var + eps);
     }
-    if (blockIdx.y == 0 && wc == 0) {
+    if (ok && blockIdx.y == 0 && wc == 0) {
         if (mean) st_px<float, 2>(mean + static_cast<size_t>(b) * L + l0, mu);
         if (rstd) st_px<float, 2>(rstd + static_cast<size_t>(b) * L + l0, rs);
     }
-    out_t* yb = y + static_cast<size_t>(b) * C * L + l0;
+    out_t* yr = y + pix + static_cast<size_t>(min(R.c0, C - 1)) * L;
 #pragma unroll
     for (int i = 0; i < kRows; ++i) {
-        const int c = c0 + i * stride;
-        if (c < C) {
-            const float wc = __ldg(w + c), bc = bs ? __ldg(bs + c) : 0.f;
-            float o[2];
+        const float wc_ = __shfl_sync(0xffffffffu, R.wb, i), bc_ = __shfl_sync(0xffffffffu, R.wb, 16 + i);
+        float o[2];
 #pragma unroll
-            for (int j = 0; j < 2; ++j) {
-                const float z = fmaf((v[i][j] - mu[j]) * rs[j], wc, bc);
-                o[j] = ACT ? gelu_f(z) : z;
-            }
-            st_px<out_t, 2>(yb + static_cast<size_t>(c) * L, o);
+        for (int j = 0; j < 2; ++j) {
+            const float z = fmaf((v[i][j] - mu[j]) * rs[j], wc_, bc_);
+            o[j] = ACT ? gelu_f(z) : z;
+        }
+        if (i < R.nvalid && ok) st_px<out_t, 2>(yr + static_cast<size_t>(i) * rstep, o);
+    }
+}
+
+// Sum each of 16 per-lane values over the 32 lanes with a transposed butterfly: 8 + 4 + 2 + 1 + 1 = 16
+// shuffles instead of 16 x 5.  On return lane l holds the warp-wide total of value (l & 15).
+__device__ __forceinline__ float warp_sum16(float (&v)[16], int lane) {
+#pragma unroll
+    for (int h = 8; h >= 1; h >>= 1) {
+        const bool up = lane & h;
+#pragma unroll
+        for (int j = 0; j < h; ++j) {
+            const float keep = up ? v[j + h] : v[j];
+            const float give = up ? v[j] : v[j + h];
+            v[j] = keep + __shfl_xor_sync(0xffffffffu, give, h);
         }
     }
+    return v[0] + __shfl_xor_sync(0xffffffffu, v[0], 16);
 }
 
 template <typename in_t, typename g_t, int ACT>
@@ -354,82 +389,73 @@ __global__ void __launch_bounds__(512) ln2d_bwd_reg_kernel(const g_t* __restrict
     cg::cluster_group cluster = cg::this_cluster();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
     const int WC = nw / WP, wp = warp % WP, wc = warp / WP;
-    const int cs = gridDim.y, stride = cs * WC, c0 = blockIdx.y * WC + wc;
+    const int cs = gridDim.y;
+    const LnRows R = ln_rows(w, bs, C, blockIdx.y * WC + wc, cs * WC, lane);
     const int b = blockIdx.z;
     const int l0 = ((blockIdx.x * WP + wp) * 32 + lane) * 2;
     const bool ok = l0 < L;
-    const size_t base = static_cast<size_t>(b) * C * L + l0;
-    const in_t* xb = x + base;
-    const g_t* gb = gy + base;
-    float xh[kRows][2], g[kRows][2];
-    float mu[2] = {0.f, 0.f}, rs[2] = {0.f, 0.f}, s1[2] = {0.f, 0.f}, s2[2] = {0.f, 0.f};
-    if (ok) {
-        ld_px<float, 2>(mean + static_cast<size_t>(b) * L + l0, mu);
-        ld_px<float, 2>(rstd + static_cast<size_t>(b) * L + l0, rs);
-    }
+    const size_t pix = static_cast<size_t>(b) * C * L + (ok ? l0 : 0);
+    const size_t rstep = static_cast<size_t>(R.stride) * L;
+    const size_t row0 = pix + static_cast<size_t>(min(R.c0, C - 1)) * L;
+    const int last = max(R.nvalid - 1, 0);
+    float xh[kRows][2], g[kRows][2], mu[2], rs[2];
+    ld_px<float, 2>(mean + static_cast<size_t>(b) * L + (ok ? l0 : 0), mu);
+    ld_px<float, 2>(rstd + static_cast<size_t>(b) * L + (ok ? l0 : 0), rs);
 #pragma unroll
     for (int i = 0; i < kRows; ++i) {
-        const int c = c0 + i * stride;
-        xh[i][0] = mu[0], xh[i][1] = mu[1];               // -> xhat = 0 for rows past C / lanes past L
-        g[i][0] = g[i][1] = 0.f;
-        if (ok && c < C) {
-            ld_px<in_t, 2>(xb + static_cast<size_t>(c) * L, xh[i]);
-            ld_px<g_t, 2>(gb + static_cast<size_t>(c) * L, g[i]);
-        }
+        const size_t o = row0 + static_cast<size_t>(min(i, last)) * rstep;
+        ld_px<in_t, 2>(x + o, xh[i]);
+        ld_px<g_t, 2>(gy + o, g[i]);
     }
+    float s1[2] = {0.f, 0.f}, s2[2] = {0.f, 0.f};
     const size_t prow = static_cast<size_t>(b) * gridDim.x * WP + blockIdx.x * WP + wp;   // one row per 64-pixel tile
-    float* pw = gw_part + prow * C;
-    float* pb = gb_part ? gb_part + prow * C : nullptr;
 #pragma unroll
-    for (int i = 0; i < kRows; ++i) {
-        const int c = c0 + i * stride;
-        const bool cv = c < C;                            // warp-uniform
-        const float wc = cv ? __ldg(w + c) : 0.f, bc = (cv && bs) ? __ldg(bs + c) : 0.f;
-        float cw = 0.f, cb = 0.f;
+    for (int half = 0; half < 2; ++half) {               // rows in two batches of 8: 16 channel sums per batch
+        float cwb[16];
 #pragma unroll
-        for (int j = 0; j < 2; ++j) {
-            const float h = (xh[i][j] - mu[j]) * rs[j];
-            float gi = g[i][j];
-            if (ACT) gi *= gelu_df(fmaf(h, wc, bc));
-            xh[i][j] = h, g[i][j] = gi;                   // keep xhat and the activated gradient
-            cw = fmaf(gi, h, cw);
-            cb += gi;
-            const float gw = gi * wc;
-            s1[j] += gw;
-            s2[j] = fmaf(gw, h, s2[j]);
+        for (int ii = 0; ii < 8; ++ii) {
+            const int i = half * 8 + ii;
+            const float m = (i < R.nvalid && ok) ? 1.f : 0.f;
+            const float wc_ = __shfl_sync(0xffffffffu, R.wb, i), bc_ = __shfl_sync(0xffffffffu, R.wb, 16 + i);
+            float cw = 0.f, cb = 0.f;
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                const float h = (xh[i][j] - mu[j]) * rs[j];
+                float gi = g[i][j] * m;
+                if (ACT) gi *= gelu_df(fmaf(h, wc_, bc_));
+                xh[i][j] = h, g[i][j] = gi;               // keep xhat and the activated gradient
+                cw = fmaf(gi, h, cw);
+                cb += gi;
+                const float gw = gi * wc_;
+                s1[j] += gw;
+                s2[j] = fmaf(gw, h, s2[j]);
+            }
+            cwb[ii] = cw, cwb[8 + ii] = cb;
         }
-        if (cv) {
-#pragma unroll
-            for (int off = 16; off > 0; off >>= 1) {
-                cw += __shfl_xor_sync(0xffffffffu, cw, off);
-                cb += __shfl_xor_sync(0xffffffffu, cb, off);
-            }
-            if (lane == 0) {
-                pw[c] = cw;
-                if (pb) pb[c] = cb;
-            }
+        // lane l ends up with: l & 15 < 8 -> dweight partial of row half*8 + (l & 7); else dbias partial
+        const float t = warp_sum16(cwb, lane);
+        const int i = half * 8 + (lane & 7);
+        if (lane < 16 && i < R.nvalid) {
+            const int c = R.c0 + i * R.stride;
+            if (lane < 8) gw_part[prow * C + c] = t;
+            else if (gb_part) gb_part[prow * C + c] = t;
         }
     }
     red[0][warp][lane * 2] = s1[0], red[0][warp][lane * 2 + 1] = s1[1];
     red[1][warp][lane * 2] = s2[0], red[1][warp][lane * 2 + 1] = s2[1];
     tile_sums(cluster, red, part, tot, cs, WP, WC);
-    if (!ok) return;
     const float inv = 1.0f / static_cast<float>(C);
     const float* t1 = tot + wp * 64 + lane * 2;
     const float* t2 = tot + WP * 64 + wp * 64 + lane * 2;
     const float m1[2] = {t1[0] * inv, t1[1] * inv};
     const float m2[2] = {t2[0] * inv, t2[1] * inv};
-    in_t* ob = gx + base;
 #pragma unroll
     for (int i = 0; i < kRows; ++i) {
-        const int c = c0 + i * stride;
-        if (c < C) {
-            const float wc = __ldg(w + c);
-            float o[2];
+        const float wc_ = __shfl_sync(0xffffffffu, R.wb, i);
+        float o[2];
 #pragma unroll
-            for (int j = 0; j < 2; ++j) o[j] = rs[j] * (fmaf(g[i][j], wc, -m1[j]) - xh[i][j] * m2[j]);
-            st_px<in_t, 2>(ob + static_cast<size_t>(c) * L, o);
-        }
+        for (int j = 0; j < 2; ++j) o[j] = rs[j] * (fmaf(g[i][j], wc_, -m1[j]) - xh[i][j] * m2[j]);
+        if (i < R.nvalid && ok) st_px<in_t, 2>(gx + row0 + static_cast<size_t>(i) * rstep, o);
     }
 }
 
