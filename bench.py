@@ -12,9 +12,11 @@ Random-init weights, synthetic N(0,1) images and Bernoulli(0.5) masks.
   value    : images/s, whole job, inputs already resident in HBM, CUDA events, max over ranks
   e2e      : same step through the public API with HOST inputs: pinned host -> device copy of
              images + masks and a device -> host read of the loss inside the timed region
-  roofline : the dominant kernel of OUR library in the step (selective-scan backward), timed per
-             launch with CUDA events on the launching stream inside the timed region; achieved =
-             sum(algorithmic bytes) / sum(launch time) against MEASURED_PEAKS.json hbm_gbs
+  roofline : the dominant kernel of the scan path in the step (fused selective-scan backward); per-launch
+             device time inside the graph-replayed step from CUPTI activity records (CUDA events around every
+             launch in an eager region when CUPTI is unavailable); achieved = sum(algorithmic bytes) /
+             sum(launch time) against MEASURED_PEAKS.json hbm_gbs; traffic = ncu DRAM bytes per launch
+             (profiles/roofline_traffic.json)
   cpu_baseline : the oracle port of the reference path (same harness, oracle operators, fp32, CPU)
              on this box's host cores; N = 1 only; bounded sample = 1 image forward+backward
 Prints ONE JSON line on rank 0.
@@ -190,9 +192,28 @@ def summarize_prof(prof):
     return agg
 
 
-def write_kernel_table(path, graph_step, sync, steps=3):
+# kernel-name fragment -> the `kind` tramba_b200._lib.timed records for it
+KIND_OF = {"ss2d_bwd_kernel": "ss2d_fused_bwd", "ss2d_fwd_kernel": "ss2d_fused_fwd", "merge_skewed_kernel": "cross_merge_skewed",
+           "ln2d_fwd": "layernorm2d_fwd", "ln2d_bwd": "layernorm2d_bwd", "dct2d_fwd": "dct2d_fwd", "dct2d_bwd": "dct2d_bwd",
+           "proj_gather": "proj_gather", "proj_scatter": "proj_scatter", "dwconv_fwd": "dwconv_fwd", "dwconv_bwd": "dwconv_bwd",
+           "sscan_fwd": "sscan_fwd", "sscan_bwd": "sscan_bwd", "cross_scan_kernel": "cross_scan", "cross_merge": "cross_merge"}
+
+
+def kind_of(name):
+    """bench `kind` (as recorded by tramba_b200._lib.timed) of a CUPTI kernel name, or None."""
+    import re
+    if "tramba" not in name:
+        return None
+    m = re.search(r"dwconv_(fwd|bwd)_kernel<[^,]+, (\d)", name)
+    if m:
+        return f"dwconv{m.group(2)}_{m.group(1)}"
+    return next((v for kk, v in KIND_OF.items() if kk in name), None)
+
+
+def kernel_times(graph_step, sync, steps=3, path=""):
     """Device time per kernel name over `steps` graph-replayed training steps (CUPTI activity records: warm
-    caches, back-to-back launches -- the complement of ncu's serialised cold-cache launch list)."""
+    caches, back-to-back launches -- the complement of ncu's serialised cold-cache launch list).  Returns
+    {kernel name: [launches per step, us per step]}; optionally writes the table to `path`."""
     import collections
     import re
     from torch.profiler import ProfilerActivity, profile
@@ -214,6 +235,9 @@ def write_kernel_table(path, graph_step, sync, steps=3):
         agg[name][0] += 1
         agg[name][1] += float(dur)
     tot = sum(v[1] for v in agg.values())
+    out = {k: [v[0] / steps, v[1] / steps] for k, v in agg.items()}
+    if not path:
+        return out
     with open(path, "w") as f:
         f.write(f"{steps} graph-replayed steps: {tot / steps / 1e3:.3f} ms device time per step in "
                 f"{sum(v[0] for v in agg.values()) // steps} kernels/memcpys per step\n")
@@ -222,6 +246,7 @@ def write_kernel_table(path, graph_step, sync, steps=3):
         for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1])[:80]:
             f.write(f"{100 * v[1] / tot:6.2f}% {v[1] / steps / 1e3:9.3f} ms/step {v[0] // steps:6d} x "
                     f"{v[1] / v[0]:9.1f} us  {k}\n")
+    return out
 
 
 def run_ours(args):
@@ -354,8 +379,14 @@ def run_ours(args):
         reduce_grads()
         g_opt.replay()
 
-    if args.kernel_table and graph is not None and rank == 0:
-        write_kernel_table(args.kernel_table, graph_step, sync)
+    # per-kernel device time INSIDE the graph-replayed step (CUPTI): what the roofline is computed from
+    ktimes = None
+    if graph is not None and rank == 0:
+        try:
+            ktimes = kernel_times(graph_step, sync, steps=3, path=args.kernel_table)
+        except Exception as exc:  # no CUPTI: the roofline falls back to the event-timed eager region
+            print(f"bench.py: torch.profiler unavailable ({type(exc).__name__}); roofline from CUDA events",
+                  file=sys.stderr)
 
     # ---- region B (`value`): device-resident inputs
     sync()
@@ -422,6 +453,27 @@ def run_ours(args):
             pass
         peak, peak_src = (peaks["hbm_gbs"], "measured (MEASURED_PEAKS.json hbm_gbs)") if "hbm_gbs" in peaks \
             else (6650.0, "fallback (B200_PROFILING.md)")
+        timed_in = "eager instrumented region (CUDA events around every launch of our kernels)"
+        step_ms_for_share = ms_eager / args.steps
+        if ktimes:
+            # replace the event-timed durations (which include the CPU launch gap of eager mode) by the CUPTI
+            # device times of the same launches inside the graph-replayed step; bytes/launch counts stay
+            cupti = {}
+            for name, (n, us) in ktimes.items():
+                kind = kind_of(name)
+                if kind is not None:
+                    c = cupti.setdefault(kind, [0.0, 0.0])
+                    c[0] += n
+                    c[1] += us
+            for kind, a in kern.items():
+                c = cupti.get(kind)
+                if c:
+                    a["ms"] = c[1] * 1e-3 * args.steps
+                    a["us_per_launch"] = c[1] / max(c[0], 1)
+                    a["gbs"] = a["bytes"] / (a["ms"] * 1e-3) / 1e9
+                    a["cupti"] = True
+            timed_in = "graph-replayed step, per-launch device time from CUPTI activity records (torch.profiler)"
+            step_ms_for_share = ms_dev / args.steps
         # the dominant kernel of the hot path proper (scan / selective scan / merge), by device time;
         # the ops either side of it (LayerNorm2d, depthwise conv, DCT) are listed under "kernels"
         path = [kk for kk in kern if kk.startswith(("ss2d_fused", "sscan", "cross_"))] or list(kern)
@@ -436,8 +488,9 @@ def run_ours(args):
                     "frac": k["gbs"] / peak, "traffic": traffic, "peak_source": peak_src,
                     "launches": k["launches"], "us_per_launch": k["us_per_launch"],
                     "algorithmic_bytes_per_launch": k["bytes"] / k["launches"],
-                    "share_of_step": k["ms"] / ms_eager,
-                    "timed_in": "eager instrumented region (CUDA events around every launch of our kernels)"}
+                    "share_of_step": (k["ms"] / args.steps) / step_ms_for_share,
+                    "timed_in": timed_in if k.get("cupti") or not ktimes else
+                    "eager instrumented region (CUDA events around every launch of our kernels)"}
         line = {
             "metric": METRIC, "value": world * B * args.steps / (ms_dev * 1e-3), "unit": UNIT, "n_gpus": world,
             "steps": args.steps, "warmup": W, "ms_per_step": ms_dev / args.steps,
@@ -457,7 +510,9 @@ def run_ours(args):
             "roofline": roofline,
             "kernels": {kk: {"launches": v["launches"], "us_per_launch": round(v["us_per_launch"], 2),
                              "gbs": round(v["gbs"], 1), "frac": round(v["gbs"] / peak, 4),
-                             "share_of_step": round(v["ms"] / ms_eager, 4)} for kk, v in sorted(kern.items())},
+                             "share_of_step": round((v["ms"] / args.steps) / step_ms_for_share, 4)}
+                        for kk, v in sorted(kern.items())},
+            "kernels_timed_in": timed_in,
             "eager_ms_per_step": ms_eager / args.steps,
             "cuda_graph": graph is not None, "cuda_graph_error": graph_error,
             "loss": loss_val,
