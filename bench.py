@@ -210,18 +210,20 @@ def kind_of(name):
     return next((v for kk, v in KIND_OF.items() if kk in name), None)
 
 
-def kernel_times(graph_step, sync, steps=3, path=""):
+def kernel_times(local_step, steps=3, path=""):
     """Device time per kernel name over `steps` graph-replayed training steps (CUPTI activity records: warm
     caches, back-to-back launches -- the complement of ncu's serialised cold-cache launch list).  Returns
-    {kernel name: [launches per step, us per step]}; optionally writes the table to `path`."""
+    {kernel name: [launches per step, us per step]}; optionally writes the table to `path`.
+    `local_step` must be free of collectives: this runs on rank 0 only."""
     import collections
     import re
+    import torch
     from torch.profiler import ProfilerActivity, profile
-    sync()
+    torch.cuda.synchronize()
     with profile(activities=[ProfilerActivity.CUDA]) as prof:
         for _ in range(steps):
-            graph_step()
-        sync()
+            local_step()
+        torch.cuda.synchronize()
     agg = collections.defaultdict(lambda: [0, 0.0])
     for ev in prof.events():
         if getattr(ev, "device_type", None) is None or "cuda" not in str(ev.device_type).lower():
@@ -379,11 +381,16 @@ def run_ours(args):
         reduce_grads()
         g_opt.replay()
 
-    # per-kernel device time INSIDE the graph-replayed step (CUPTI): what the roofline is computed from
+    # per-kernel device time INSIDE the graph-replayed step (CUPTI): what the roofline is computed from.
+    # Single-process runs only: the profiled replays happen on one rank, so they must not contain a collective
+    # (at N > 1 the step has the gradient all-reduce; the roofline then comes from the event-timed eager region).
     ktimes = None
-    if graph is not None and rank == 0:
+    if graph is not None and world == 1:
+        def local_step():
+            g_fb.replay()
+            g_opt.replay()
         try:
-            ktimes = kernel_times(graph_step, sync, steps=3, path=args.kernel_table)
+            ktimes = kernel_times(local_step, steps=3, path=args.kernel_table)
         except Exception as exc:  # no CUPTI: the roofline falls back to the event-timed eager region
             print(f"bench.py: torch.profiler unavailable ({type(exc).__name__}); roofline from CUDA events",
                   file=sys.stderr)
