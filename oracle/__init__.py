@@ -10,7 +10,15 @@ Pinning status:
                                            (tests/golden/orders.npz, scanmerge.npz)
   DCT2D                                  : PINNED to the reference module run on CPU
                                            (tests/golden/dct.npz) and scipy.fft.dctn
-  selective-scan recurrence              : PARITY UNPINNED -- not present in /root/reference
-                                           (external CUDA extension); restated from the
-                                           published selective_scan_ref algorithm.
+  selective-scan recurrence              : PARITY UNPINNED against the reference's own code -- the
+                                           recurrence is an external CUDA extension absent from
+                                           /root/reference; restated from the published
+                                           selective_scan_ref algorithm and PINNED to an independent
+                                           executed implementation of it (HF transformers
+                                           MambaMixer.slow_forward: tests/golden/sscan_hf.npz,
+                                           forward + all gradients, fp64)
+  LayerNorm2d (+GELU)                    : PINNED to the reference class run on CPU
+                                           (tests/golden/layernorm2d.npz)
+  depthwise conv (+SiLU)                 : PINNED to the reference's own torch ops (nn.Conv2d
+                                           groups=C + nn.SiLU) run on CPU (tests/golden/dwconv.npz)
 """

@@ -1,7 +1,9 @@
 """CPU ORACLE (test infrastructure, NOT product code) -- selective scan fwd/bwd.
 
 ctypes front-end over oracle/sscan_ref.c plus a tiny pure-numpy statement used to
-cross-check the C code.  PARITY UNPINNED (see sscan_ref.c header): follows the call sites
+cross-check the C code.  PARITY UNPINNED against the reference's own (absent) extension; pinned instead to an
+independent executed implementation of the same published algorithm (HF transformers MambaMixer.slow_forward,
+tests/test_oracle_sscan_pin.py) -- see the sscan_ref.c header.  Follows the call sites
 Models/SS2D/csms6s.py:904-923 and the argument preparation in Models/vmamba.py:244-257.
 """
 import ctypes

@@ -1,15 +1,18 @@
 /* CPU ORACLE (test infrastructure, NOT product code) -- selective-scan recurrence.
  *
- * PARITY UNPINNED: the recurrence is not in /root/reference.  The reference only calls an
- * un-vendored third-party CUDA extension (MzeroMiko/VMamba kernels/selective_scan, derived
- * from state-spaces/mamba; no version pin anywhere in the reference, README.md:38) at
+ * PARITY UNPINNED against the reference's OWN implementation: the recurrence is not in /root/reference.  The
+ * reference only calls an un-vendored third-party CUDA extension (MzeroMiko/VMamba kernels/selective_scan,
+ * derived from state-spaces/mamba; no version pin anywhere in the reference, README.md:38) at
  *   Models/SS2D/csms6s.py:910      selective_scan_cuda_oflex.fwd(u,delta,A,B,C,D,delta_bias,softplus,1,oflex)
  *   Models/SS2D/csms6s.py:920-922  selective_scan_cuda_oflex.bwd(u,delta,A,B,C,D,delta_bias,dout,x,softplus,1)
  * This file restates the published algorithm of that dependency (the canonical
  * `selective_scan_ref`): fp32/fp64 internals, softplus with threshold 20, grouped B/C with
- * channel->group = d / (dim/groups), out = y + u*D.  It is validated in tests against an
- * independent torch-autograd statement of the same formulas in fp64 (tests/test_oracle.py),
- * which is the strongest pin available offline.
+ * channel->group = d / (dim/groups), out = y + u*D.  What it IS pinned to (tests/test_oracle_sscan_pin.py,
+ * fixture tests/golden/sscan_hf.npz from tests/golden/make_golden_sscan_hf.py): an independent, executed public
+ * implementation of that algorithm -- Hugging Face transformers 5.5 `MambaMixer.slow_forward`, the pure-PyTorch
+ * statement of state-spaces/mamba's selective scan -- forward to 1e-10 and all seven gradients against its
+ * autograd in fp64; plus an independent torch-autograd statement of the same formulas (tests/test_oracle.py).
+ * That is the strongest anchor available offline; the reference's own extension remains absent.
  *
  * Layouts (all contiguous, L innermost), as the reference call site passes them
  * (Models/vmamba.py:244-257):
