@@ -286,13 +286,9 @@ def run_ours(args):
     # Data parallel over images (the path shards by image): replicas start identical
     # (broadcast from rank 0) and every gradient lives in ONE flat fp32 buffer that is all-reduced
     # (NCCL, AVG) once per step between backward and the Adam step -- 446 MB over NVLink/NVSwitch.
+    from tramba_b200.dp import FlatGradients
     params = [p for p in model.parameters()]
-    flat = torch.zeros(sum(p.numel() for p in params), device=dev, dtype=torch.float32)
-    views, off = [], 0
-    for p in params:
-        views.append(flat[off:off + p.numel()].view_as(p))
-        p.grad = views[-1]
-        off += p.numel()
+    fg = FlatGradients(params)
     if world > 1:
         for p in params:
             dist.broadcast(p.data, 0)
@@ -307,23 +303,16 @@ def run_ours(args):
     def fwd_bwd(img, lab):
         # autograd ASSIGNS fresh gradients (p.grad is None: no zero-fill + 679 accumulate kernels); they are
         # then packed into the flat buffer with one multi-tensor copy and the optimizer sees the flat views
-        for p in params:
-            p.grad = None
+        fg.begin()
         with torch.autocast("cuda", dtype=amp, enabled=amp is not None):
             outs = net(img)
         loss = tsod_loss(outs, lab)
         loss.backward()
-        got = [(v, p.grad) for v, p in zip(views, params) if p.grad is not None]
-        torch._foreach_copy_([v for v, _ in got], [g for _, g in got])
-        for v, p in zip(views, params):
-            if p.grad is None:
-                v.zero_()
-            p.grad = v
+        fg.pack()
         return loss
 
     def reduce_grads():
-        if world > 1:
-            dist.all_reduce(flat, op=dist.ReduceOp.AVG)
+        fg.all_reduce(world)
 
     def step(img, lab):
         loss = fwd_bwd(img, lab)

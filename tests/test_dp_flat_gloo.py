@@ -1,0 +1,87 @@
+"""The data-parallel host logic bench.py uses (tramba_b200.dp.FlatGradients): world_size-2 gloo run on CPU.
+After begin() -> backward -> pack() -> all_reduce(), every rank's flat buffer (and every p.grad view) holds the
+MEAN of the per-rank gradients, and an optimizer step from the flat views keeps the replicas identical."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _model():
+    torch.manual_seed(0)
+    return torch.nn.Sequential(torch.nn.Conv2d(3, 8, 3, padding=1), torch.nn.GELU(), torch.nn.Conv2d(8, 4, 1),
+                               torch.nn.Flatten(), torch.nn.Linear(4 * 8 * 8, 5), torch.nn.Linear(5, 1, bias=False))
+
+
+def _worker(rank, world, port, out_dir):
+    sys.path.insert(0, os.path.dirname(HERE))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.set_num_threads(1)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from tramba_b200.dp import FlatGradients
+
+    model = _model()
+    params = list(model.parameters())
+    opt = torch.optim.Adam(params, lr=1e-2)
+    fg = FlatGradients(params)
+    assert all(p.grad.data_ptr() == v.data_ptr() for p, v in zip(params, fg.views))
+    g = torch.Generator().manual_seed(100 + rank)
+    x = torch.randn(2, 3, 8, 8, generator=g)
+    worst = 0.0
+    for _ in range(2):                                        # two steps: the views must survive a step
+        fg.begin()
+        assert all(p.grad is None for p in params)
+        model(x).square().mean().backward()
+        local = [p.grad.clone() for p in params]
+        fg.pack()
+        assert all(p.grad.data_ptr() == v.data_ptr() for p, v in zip(params, fg.views))
+        assert all(torch.equal(p.grad, l) for p, l in zip(params, local))
+        fg.all_reduce(world)
+        for p, l in zip(params, local):
+            mean = l.clone()
+            dist.all_reduce(mean)
+            mean /= world
+            worst = max(worst, float((mean - p.grad).abs().max()))
+        opt.step()
+    w = torch.cat([p.detach().flatten() for p in params])
+    ws = [torch.empty_like(w) for _ in range(world)]
+    dist.all_gather(ws, w)
+    same = all(torch.equal(ws[0], t) for t in ws)
+    np.save(os.path.join(out_dir, f"r{rank}.npy"), np.array([worst, float(same)]))
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+def test_flat_gradients_world2_gloo(tmp_path):
+    world = 2
+    mp.spawn(_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    for r in range(world):
+        worst, same = np.load(tmp_path / f"r{r}.npy")
+        assert worst < 1e-6, worst
+        assert same == 1.0
+
+
+def test_flat_gradients_unused_parameter_is_zeroed():
+    sys.path.insert(0, os.path.dirname(HERE))
+    from tramba_b200.dp import FlatGradients
+    a, b = torch.nn.Parameter(torch.ones(3)), torch.nn.Parameter(torch.ones(2))
+    fg = FlatGradients([a, b])
+    fg.flat.fill_(7.0)
+    fg.begin()
+    (a * 2).sum().backward()                                  # b unused
+    fg.pack()
+    assert torch.equal(a.grad, torch.full((3,), 2.0)) and torch.equal(b.grad, torch.zeros(2))
+    assert torch.equal(fg.flat, torch.tensor([2.0, 2.0, 2.0, 0.0, 0.0]))
