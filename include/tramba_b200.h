@@ -32,14 +32,23 @@ extern "C" {
 typedef enum { TRAMBA_F32 = 0, TRAMBA_BF16 = 1, TRAMBA_F16 = 2 } tramba_dtype_t;
 
 /* Scan-order families.  LINE is the Helix-SS2D order: 4 standard directions followed by the
- * 4 Bresenham radial-line lists (K = 8); every other family has K = 4.  CUSTOM takes a
- * caller-supplied table with arbitrary (possibly repeating) indices. */
+ * 4 Bresenham radial-line lists (K = 8).  CUSTOM takes a caller-supplied table with arbitrary
+ * (possibly repeating) indices.  Values 5..11 are the reference's ablation orders (not on the
+ * Tramba-V path): they run through the table-driven scan / merge kernels,
+ * never through the fused core. */
 typedef enum {
     TRAMBA_ORDER_STD = 0,      /* Models/SS2D/csms6s.py:13-55   CrossScan / CrossMerge            */
     TRAMBA_ORDER_DILATION = 1, /* Models/SS2D/csms6s.py:64-103  + Models/SS2D/Dilation.py:3-96    */
     TRAMBA_ORDER_WINDOW = 2,   /* Models/SS2D/csms6s.py:113-152 + Models/SS2D/Window.py:3-86      */
     TRAMBA_ORDER_LINE = 3,     /* Models/SS2D/csms6s.py:161-216 + Models/SS2D/SpiralLine.py:3-133 */
-    TRAMBA_ORDER_CUSTOM = 4
+    TRAMBA_ORDER_CUSTOM = 4,
+    TRAMBA_ORDER_LINE4 = 5,    /* csms6s.py:219-265  CrossScan_Line_4direction: the 4 helix lists, K = 4  */
+    TRAMBA_ORDER_SPIRAL = 6,   /* csms6s.py:264-368 + Spiral.py:3-82: std + cw/ccw spirals + flips, K = 8 */
+    TRAMBA_ORDER_HILBERT = 7,  /* csms6s.py:371-473 + Hilbert.py:9-331 (sides 2^m and 3*2^m), K = 4        */
+    TRAMBA_ORDER_DIAGONAL = 8, /* csms6s.py:478-615: std + (anti-)diagonal wraps + flips, K = 8           */
+    TRAMBA_ORDER_DS = 9,       /* csms6s.py:619-674: helix lists + diagonal wraps + flips, K = 8          */
+    TRAMBA_ORDER_AB2 = 10,     /* csms6s.py:678-710  CrossScan_Ab_2direction, K = 4                       */
+    TRAMBA_ORDER_AB1 = 11      /* csms6s.py:713-737  CrossScan_Ab_1direction, K = 4                       */
 } tramba_order_t;
 
 enum {
@@ -65,7 +74,7 @@ TRAMBA_API uint64_t tramba_launch_count(void);
  * module-level dicts at Models/SS2D/csms6s.py:58-61,107-110,157-158.  The table is the flat
  * pixel index idx[k*L + t] (row*W + col), K = tramba_order_num_directions(order), L = H*W;
  * square maps only (H == W), like the reference.  `param` = dilation rate / window size
- * (ignored for STD and LINE).  Bit-exact with the reference generators.
+ * (ignored by every other family).  Bit-exact with the reference generators.
  * -------------------------------------------------------------------------------------- */
 TRAMBA_API int tramba_order_num_directions(int order);
 TRAMBA_API int tramba_order_table(int order, int H, int W, int param, int32_t* idx_out /* K*L, host */);

@@ -16,6 +16,14 @@ Reference lines followed:
   dilation  Models/SS2D/Dilation.py:3-45,66    (generate_dilation_indices, flat = c0*H+c1)
   window    Models/SS2D/Window.py:3-35,56      (generate_window_indices,   flat = c0*H+c1)
   line      Models/SS2D/SpiralLine.py:3-82,103 (bresenham, generate_indices, flat = x+y*H)
+Ablation families (pinned by tests/golden/ablation_orders.npz = the reference
+classes' own outputs, made by tests/golden/make_golden_ablation.py):
+  line4     Models/SS2D/csms6s.py:219-265      (the four line lists alone)
+  spiral    Models/SS2D/csms6s.py:264-339 + Spiral.py:3-82
+  hilbert   Models/SS2D/csms6s.py:374-405 + Hilbert.py:9-331 (sides 2^m and 3*2^m only)
+  diagonal  Models/SS2D/csms6s.py:478-549
+  ds        Models/SS2D/csms6s.py:619-631
+  ab2 / ab1 Models/SS2D/csms6s.py:678-685, 713-718
 """
 import numpy as np
 
@@ -26,6 +34,7 @@ REF_WINDOW_SIZE = {12: 4, 24: 8, 48: 12, 96: 16}
 # build-side extension for the 768^2 stress config: dilation 4, window 32
 EXT_DILATION_RATE = {192: 4}
 EXT_WINDOW_SIZE = {192: 32}
+ABLATION = ("line4", "spiral", "hilbert", "diagonal", "ds", "ab2", "ab1")
 
 
 def std_indices(H, W):
@@ -128,10 +137,119 @@ def line_indices(H, W):
     return out  # list: lengths equal H*W only for even H
 
 
+def spiral_indices(H, W):
+    """Spiral.py:3-60 + 62-71: clockwise from the top-left, counter-clockwise from the bottom-right; the
+    walks emit (row, col) and the gather index is `y*H + x` with (x, y) = (row, col): the TRANSPOSED pixel."""
+    def walk(ccw):
+        top, bottom, left, right = 0, H - 1, 0, W - 1
+        pts = []
+        while top <= bottom and left <= right:
+            if not ccw:
+                pts += [(top, i) for i in range(left, right + 1)]
+                top += 1
+                pts += [(i, right) for i in range(top, bottom + 1)]
+                right -= 1
+                if top <= bottom:
+                    pts += [(bottom, i) for i in range(right, left - 1, -1)]
+                    bottom -= 1
+                if left <= right:
+                    pts += [(i, left) for i in range(bottom, top - 1, -1)]
+                    left += 1
+            else:
+                pts += [(bottom, i) for i in range(right, left - 1, -1)]
+                bottom -= 1
+                pts += [(i, left) for i in range(bottom, top - 1, -1)]
+                left += 1
+                if top <= bottom:
+                    pts += [(top, i) for i in range(left, right + 1)]
+                    top += 1
+                if left <= right:
+                    pts += [(i, right) for i in range(top, bottom + 1)]
+                    right -= 1
+        a = np.asarray(pts, dtype=np.int64)
+        return a[:, 1] * H + a[:, 0]
+    return np.stack([walk(False), walk(True)])
+
+
+def diagonal_indices(H, W):
+    """csms6s.py:478-497: gather(3, (h + w) % W) / gather(3, (w - h) % W), transpose(-1, -2), flatten:
+    token t = w*H + h reads x[h, (h + w) % W] (diagonal) and x[h, (w - h) % W] (anti-diagonal)."""
+    t = np.arange(H * W, dtype=np.int64)
+    w, h = t // H, t % H
+    return np.stack([h * W + (h + w) % W, h * W + (w - h) % W])
+
+
+def hilbert_indices(H):
+    """Hilbert.py:9-331 restricted to what a square of side 2^m or 3*2^m reaches: even-even blocks are
+    quartered (:187-200), odd-odd 3x3 blocks split 2+1 (:242-257), blocks of <= 6 cells are rendered as
+    strips (:33-64).  Returns the (L,) walk `int(y-1)*H + int(x-1)` (:8); raises ValueError elsewhere."""
+    out = []
+
+    def strip(x0, y0, ax, ay, ox, oy, back):
+        n = abs(ax + ay)
+        ddx, ddy = ax / n, ay / n
+        for ii in (range(n - 1, -1, -1) if back else range(n)):
+            out.append(int(y0 + ii * ddy + (oy + ddy - 1) / 2 - 1) * H + int(x0 + ii * ddx + (ox + ddx - 1) / 2 - 1))
+
+    def go(x0, y0, xl, yl, xr, yr, d):
+        nl, nr = abs(xl + yl), abs(xr + yr)
+        if nl * nr <= 6:
+            if nl == 1:
+                return strip(x0, y0, xr, yr, xl, yl, False)
+            if nr == 1:
+                return strip(x0, y0, xl, yl, xr, yr, False)
+            if d == "l":
+                strip(x0, y0, xr, yr, xl / 2, yl / 2, False)
+                return strip(x0, y0, xr, yr, xl + xl / 2, yl + yl / 2, True)
+            if d == "r":
+                strip(x0, y0, xl, yl, xr / 2, yr / 2, False)
+                return strip(x0, y0, xl, yl, xr + xr / 2, yr + yr / 2, True)
+            raise ValueError("hilbert: leaf outside the restricted set")
+        if 2 * nl > 3 * nr or 2 * nr > 3 * nl or d == "m":
+            raise ValueError("hilbert: side not 2^m or 3*2^m")
+        xl2, yl2, xr2, yr2 = round(xl / 2), round(yl / 2), round(xr / 2), round(yr / 2)
+        if nl % 2 == 0 and nr % 2 == 0:
+            if abs(xl2 + yl2 + xr2 + yr2) % 2:
+                raise ValueError("hilbert: side not 2^m or 3*2^m")
+            mid = None
+        elif nl % 2 and nr % 2:
+            xl2 = xl - xl2 if xl2 % 2 else xl2
+            yl2 = yl - yl2 if yl2 % 2 else yl2
+            xr2 = xr - xr2 if xr2 % 2 else xr2
+            yr2 = yr - yr2 if yr2 % 2 else yr2
+            mid = "m"
+        else:
+            raise ValueError("hilbert: side not 2^m or 3*2^m")
+        if d == "l":
+            go(x0, y0, xl2, yl2, xr2, yr2, "r")
+            if mid:
+                go(x0 + xr2, y0 + yr2, xl2, yl2, xr - xr2, yr - yr2, "m")
+                go(x0 + xr + xl2, y0 + yr + yl2, xr2 - xr, yr2 - yr, xl - xl2, yl - yl2, "m")
+            else:
+                go(x0 + xr2, y0 + yr2, xl2, yl2, xr - xr2, yr - yr2, "l")
+                go(x0 + xr2 + xl2, y0 + yr2 + yl2, xl - xl2, yl - yl2, xr - xr2, yr - yr2, "l")
+            go(x0 + xr2 + xl, y0 + yr2 + yl, xl2 - xl, yl2 - yl, -xr2, -yr2, "r")
+        else:
+            go(x0, y0, xl2, yl2, xr2, yr2, "l")
+            if mid:
+                go(x0 + xl2, y0 + yl2, xl - xl2, yl - yl2, xr2, yr2, "m")
+                go(x0 + xl + xr2, y0 + yl + yr2, xr - xr2, yr - yr2, xl2 - xl, yl2 - yl, "m")
+            else:
+                go(x0 + xl2, y0 + yl2, xl - xl2, yl - yl2, xr2, yr2, "r")
+                go(x0 + xr2 + xl2, y0 + yr2 + yl2, xl - xl2, yl - yl2, xr - xr2, yr - yr2, "r")
+            go(x0 + xl2 + xr, y0 + yl2 + yr, -xl2, -yl2, xr2 - xr, yr2 - yr, "l")
+
+    go(1, 1, H, 0, 0, H, "l")
+    a = np.asarray(out, dtype=np.int64)
+    if len(a) != H * H or len(np.unique(a)) != H * H:
+        raise ValueError("hilbert: walk is not a permutation")
+    return a
+
+
 def order_table(family, H, param=0):
     """(K, L) int64 table for a named family as the reference's CrossScan* classes use it.
     family: 'std' | 'dilation' | 'window' | 'line' (line = std k0-3 + 4 line lists,
-    csms6s.py:167-171)."""
+    csms6s.py:167-171) | ablation: 'line4' | 'spiral' | 'hilbert' | 'diagonal' | 'ds' | 'ab2' | 'ab1'."""
     if family == "std":
         return std_indices(H, H)
     if family == "dilation":
@@ -142,6 +260,26 @@ def order_table(family, H, param=0):
         ln = line_indices(H, H)
         assert all(len(a) == H * H for a in ln), "line family needs even H"
         return np.concatenate([std_indices(H, H), np.stack(ln)])
+    if family in ("line4", "ds"):
+        ln = line_indices(H, H)
+        assert all(len(a) == H * H for a in ln), "line family needs even H"
+        if family == "line4":
+            return np.stack(ln)
+        dg = diagonal_indices(H, H)
+        return np.concatenate([np.stack(ln), dg, dg[:, ::-1]])          # csms6s.py:624-630
+    if family == "spiral":
+        sp = spiral_indices(H, H)
+        return np.concatenate([std_indices(H, H), sp, sp[:, ::-1]])      # csms6s.py:321-326
+    if family == "diagonal":
+        dg = diagonal_indices(H, H)
+        return np.concatenate([std_indices(H, H), dg, dg[:, ::-1]])      # csms6s.py:539-547
+    if family == "hilbert":
+        h0 = hilbert_indices(H)
+        h1 = (H - 1 - h0 // H) * H + h0 % H                               # flip(input, [2]) (csms6s.py:401)
+        return np.stack([h0, h1, h0[::-1], h1[::-1]])
+    if family in ("ab2", "ab1"):
+        t = np.arange(H * H, dtype=np.int64)
+        return np.stack([t, t, t[::-1], t[::-1]] if family == "ab2" else [t] * 4)
     raise ValueError(family)
 
 
@@ -182,4 +320,8 @@ def cross_merge(ys, table, family):
         return scatter(range(4))
     if family == "line":
         return scatter(range(4, 8)) + std_fold()
+    if family in ABLATION or family == "custom":
+        # the exact transpose, added sequentially over k then t.  The reference groups these sums
+        # differently per family (e.g. y_h + y_rc, csms6s.py:333-338): same value up to fp32 association
+        return scatter(range(K))
     raise ValueError(family)

@@ -14,7 +14,7 @@ WS = {12: 4, 24: 8, 48: 12, 96: 16, 192: 32}
 
 
 def _param(fam, H):
-    return {"std": 0, "dilation": 4, "window": WS.get(H, 0), "line": 0}[fam]
+    return {"dilation": 4, "window": WS.get(H, 0)}.get(fam, 0)
 
 
 def make_pair(fam):

@@ -27,3 +27,8 @@ def golden_scanmerge():
 @pytest.fixture(scope="session")
 def golden_dct():
     return np.load(os.path.join(GOLDEN, "dct.npz"))
+
+
+@pytest.fixture(scope="session")
+def golden_ablation():
+    return np.load(os.path.join(GOLDEN, "ablation_orders.npz"))

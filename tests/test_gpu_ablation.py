@@ -1,0 +1,118 @@
+"""GPU parity of the reference's ablation scan orders (csms6s.py:219-737) through the
+table-driven cross-scan / cross-merge kernels: against the reference classes' own outputs (small sizes) and the
+oracle (full sizes).  Gathers are bit-exact; merges are bit-exact against the oracle's sequential sums and within
+fp32 association (2e-6) of the reference's per-family grouping."""
+import numpy as np
+import pytest
+import torch
+
+import tramba_b200
+from tramba_b200 import _lib
+from oracle import scan_orders as so
+
+pytestmark = pytest.mark.gpu
+
+PAIRS = {
+    "line4": (tramba_b200.CrossScan_Line_4direction, tramba_b200.CrossMerge_Line_4direction, _lib.ORDER_LINE4),
+    "spiral": (tramba_b200.CrossScan_Spiral, tramba_b200.CrossMerge_Spiral, _lib.ORDER_SPIRAL),
+    "hilbert": (tramba_b200.CrossScan_Hilbert, tramba_b200.CrossMerge_Hilbert, _lib.ORDER_HILBERT),
+    "diagonal": (tramba_b200.CrossScan_Diagonal, tramba_b200.CrossMerge_Diagonal, _lib.ORDER_DIAGONAL),
+    "ds": (tramba_b200.CrossScan_DS, tramba_b200.CrossMerge_DS, _lib.ORDER_DS),
+    "ab2": (tramba_b200.CrossScan_Ab_2direction, tramba_b200.CrossMerge_Ab_2direction, _lib.ORDER_AB2),
+    "ab1": (tramba_b200.CrossScan_Ab_1direction, tramba_b200.CrossMerge_Ab_1direction, _lib.ORDER_AB1),
+}
+
+
+@pytest.mark.parametrize("fam", list(PAIRS))
+def test_against_reference_golden(golden_ablation, fam):
+    g, H = golden_ablation, 12
+    S, M, _ = PAIRS[fam]
+    K = g[f"table_{fam}_{H}"].shape[0]
+    rs = np.random.RandomState(3000 + K)
+    x = rs.standard_normal((2, 3, H, H)).astype(np.float32)
+    ys = rs.standard_normal((2, K, 3, H, H)).astype(np.float32)
+    xt = torch.from_numpy(x).cuda().requires_grad_(True)
+    xs = S.apply(xt)
+    assert np.array_equal(xs.detach().cpu().numpy(), g[f"{fam}_{H}_scan"])
+    (gx,) = torch.autograd.grad(xs, xt, torch.from_numpy(ys).cuda().view(2, K, 3, H * H))
+    np.testing.assert_allclose(gx.cpu().numpy().reshape(2, 3, H * H), g[f"{fam}_{H}_scan_bwd"], rtol=0, atol=2e-6)
+    yt = torch.from_numpy(ys).cuda().requires_grad_(True)
+    y = M.apply(yt)
+    np.testing.assert_allclose(y.detach().cpu().numpy(), g[f"{fam}_{H}_merge"], rtol=0, atol=2e-6)
+    (gys,) = torch.autograd.grad(y, yt, torch.from_numpy(x).cuda().view(2, 3, H * H))
+    assert np.array_equal(gys.cpu().numpy().reshape(2, K, 3, H * H), g[f"{fam}_{H}_merge_bwd"])
+
+
+@pytest.mark.parametrize("fam", list(PAIRS))
+@pytest.mark.parametrize("H,B,C", [(96, 2, 5), (48, 1, 7)])
+def test_full_size_vs_oracle(fam, H, B, C):
+    order = PAIRS[fam][2]
+    tab = so.order_table(fam, H)
+    K = tab.shape[0]
+    rs = np.random.RandomState(H + B)
+    x = rs.standard_normal((B, C, H, H)).astype(np.float32)
+    ys = rs.standard_normal((B, K, C, H * H)).astype(np.float32)
+    xs = tramba_b200.cross_scan(torch.from_numpy(x).cuda(), order)
+    assert np.array_equal(xs.cpu().numpy(), so.cross_scan(x, tab))
+    y = tramba_b200.cross_merge(torch.from_numpy(ys).cuda(), order, H, H)
+    assert np.array_equal(y.cpu().numpy(), so.cross_merge(ys, tab, fam))
+
+
+@pytest.mark.parametrize("fam", ["spiral", "hilbert", "ds"])
+def test_bf16(fam):
+    H, B, C = 24, 2, 8
+    order = PAIRS[fam][2]
+    tab = so.order_table(fam, H)
+    K = tab.shape[0]
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(B, C, H, H, generator=g).bfloat16()
+    ys = torch.randn(B, K, C, H * H, generator=g).bfloat16()
+    xs = tramba_b200.cross_scan(x.cuda(), order)
+    assert xs.dtype == torch.bfloat16
+    assert np.array_equal(xs.float().cpu().numpy(), so.cross_scan(x.float().numpy(), tab))
+    y = tramba_b200.cross_merge(ys.cuda(), order, H, H)
+    ref = torch.from_numpy(so.cross_merge(ys.float().numpy(), tab, fam)).bfloat16()   # fp32 sums, one rounding
+    assert torch.equal(y.cpu(), ref)
+
+
+def test_custom_pair_with_duplicates_and_reference_table(golden_ablation):
+    """make_custom_pair: a random table with repeated pixels, and the reference's own Hilbert table passed in as a
+    caller-supplied table (what a user holding the reference's generators would do)."""
+    H, L = 12, 144
+    rs = np.random.RandomState(11)
+    tabs = {"random": rs.randint(0, L, size=(3, L)).astype(np.int64),
+            "hilbert": golden_ablation["table_hilbert_12"].astype(np.int64)}
+    for name, tab in tabs.items():
+        K = tab.shape[0]
+        S, M = tramba_b200.make_custom_pair("_" + name, lambda h, t=tab: t)
+        x = rs.standard_normal((2, 5, H, H)).astype(np.float32)
+        ys = rs.standard_normal((2, K, 5, H, H)).astype(np.float32)
+        xt = torch.from_numpy(x).cuda().requires_grad_(True)
+        xs = S.apply(xt)
+        assert np.array_equal(xs.detach().cpu().numpy(), so.cross_scan(x, tab))
+        (gx,) = torch.autograd.grad(xs, xt, torch.from_numpy(ys).cuda().view(2, K, 5, L))
+        want = so.cross_merge(ys.reshape(2, K, 5, L), tab, "custom")
+        assert np.array_equal(gx.cpu().numpy().reshape(2, 5, L), want)
+        y = M.apply(torch.from_numpy(ys).cuda())
+        assert np.array_equal(y.cpu().numpy(), want)
+    S, M = tramba_b200.make_custom_pair("_hilbert", lambda h: tabs["hilbert"])
+    x = torch.randn(1, 2, H, H, device="cuda")
+    assert torch.equal(S.apply(x), tramba_b200.CrossScan_Hilbert.apply(x))
+
+
+def test_roundtrip_multiplicity_full_size():
+    """merge(scan(x)) == (number of tokens reading each pixel) * x at BASELINE size, exactly (small integers)."""
+    H = 96
+    x = torch.randint(-8, 8, (2, 64, H, H), device="cuda").float()
+    for fam, (_, _, order) in PAIRS.items():
+        tab = torch.from_numpy(so.order_table(fam, H)).cuda()
+        mult = torch.zeros(H * H, device="cuda").index_add_(0, tab.flatten(), torch.ones(tab.numel(), device="cuda"))
+        y = tramba_b200.cross_merge(tramba_b200.cross_scan(x, order), order, H, H)
+        assert torch.equal(y, x.flatten(2) * mult), fam
+
+
+def test_size_errors_like_reference():
+    with pytest.raises(KeyError):
+        tramba_b200.CrossScan_DS.apply(torch.zeros(1, 1, 20, 20, device="cuda"))
+    with pytest.raises(AssertionError):
+        tramba_b200.CrossScan_Spiral.apply(torch.zeros(1, 1, 20, 20, device="cuda"))

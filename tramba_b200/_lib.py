@@ -13,6 +13,8 @@ LIB_PATH = os.path.join(_HERE, "libtramba_b200.so")
 F32, BF16, F16 = 0, 1, 2
 ACT_NONE, ACT_GELU, ACT_SILU = 0, 1, 2
 ORDER_STD, ORDER_DILATION, ORDER_WINDOW, ORDER_LINE, ORDER_CUSTOM = 0, 1, 2, 3, 4
+# ablation orders of the reference (csms6s.py:219-737); table-driven kernels only, never the fused core
+ORDER_LINE4, ORDER_SPIRAL, ORDER_HILBERT, ORDER_DIAGONAL, ORDER_DS, ORDER_AB2, ORDER_AB1 = 5, 6, 7, 8, 9, 10, 11
 
 _vp, _i, _i32p, _fp = ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p
 

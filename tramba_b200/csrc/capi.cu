@@ -151,7 +151,7 @@ static int check_scan_args(const void* a, const void* b, const int32_t* plan, in
                            int H, int W, int dtype) {
     if (!a || !b || !plan) return TRAMBA_E_NULL;
     if (B <= 0 || C <= 0 || H <= 0 || W <= 0 || K <= 0) return TRAMBA_E_SHAPE;
-    if (order < TRAMBA_ORDER_STD || order > TRAMBA_ORDER_CUSTOM) return TRAMBA_E_ORDER;
+    if (order < TRAMBA_ORDER_STD || order > TRAMBA_ORDER_AB1) return TRAMBA_E_ORDER;
     if (order != TRAMBA_ORDER_CUSTOM && K != tramba_order_num_directions(order)) return TRAMBA_E_ORDER;
     if (dtype != TRAMBA_F32 && dtype != TRAMBA_BF16) return TRAMBA_E_DTYPE;
     if (!aligned(a, elem_size(dtype)) || !aligned(b, elem_size(dtype)) || !aligned(plan, 4)) return TRAMBA_E_ALIGN;

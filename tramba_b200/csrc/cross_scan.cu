@@ -214,7 +214,10 @@ cudaError_t merge_t(const T* ys, T* y, const int32_t* plan, int order, int K, in
     cfg.has_std = (order == TRAMBA_ORDER_STD || order == TRAMBA_ORDER_LINE);
     cfg.klo = (order == TRAMBA_ORDER_LINE) ? 4 : 0;
     cfg.khi = (order == TRAMBA_ORDER_STD) ? 0 : K;
-    cfg.perm = (order == TRAMBA_ORDER_DILATION || order == TRAMBA_ORDER_WINDOW);
+    // every direction a permutation (one token per pixel): the CSR offsets need not be read
+    cfg.perm = (order == TRAMBA_ORDER_DILATION || order == TRAMBA_ORDER_WINDOW || order == TRAMBA_ORDER_SPIRAL ||
+                order == TRAMBA_ORDER_HILBERT || order == TRAMBA_ORDER_DIAGONAL || order == TRAMBA_ORDER_AB2 ||
+                order == TRAMBA_ORDER_AB1);
     const int planes = B * D;
     const int Lp = skewed_len(L);
     const int nacc = (cfg.khi > cfg.klo ? 1 : 0) + (cfg.has_std ? 1 : 0);

@@ -3,6 +3,10 @@
 // Models/SS2D/SpiralLine.py:3-82 and the standard unfold of Models/SS2D/csms6s.py:13-31.
 // All tables are flat pixel indices row*W + col of a square map; closed forms where the order
 // is a permutation, an integer Bresenham walk for the helix lines.
+// The ablation families follow Models/SS2D/csms6s.py:219-737, Spiral.py:3-82
+// and Hilbert.py:9-331; each is the table T with  CrossScan_X(x)[b,k,c,t] = x[b,c].flat[T[k][t]].
+#include <algorithm>
+#include <cmath>
 #include <cstdlib>
 #include <vector>
 
@@ -124,14 +128,188 @@ int line_table(int H, int W, int32_t* out) {
     return (wE == L && wO == L) ? TRAMBA_OK : TRAMBA_E_ORDER;
 }
 
+// out[dst] = reverse of out[src] along t (torch.flip(..., dims=[-1])).
+void flip_row(int L, int32_t* out, int dst, int src) {
+    for (int t = 0; t < L; ++t) out[dst * L + t] = out[src * L + (L - 1 - t)];
+}
+
+// Spiral.py:3-60.  The walks emit (row, col); the forward gather uses `y*H + x` with (x, y) = (row, col)
+// (Spiral.py:68-71), i.e. the TRANSPOSED pixel col*H + row.  Slot `kc` clockwise from the top-left corner,
+// slot `kc + 1` counter-clockwise from the bottom-right corner.
+void spiral_tables(int H, int W, int32_t* out, int kc) {
+    const int L = H * W;
+    int32_t* cw = out + kc * L;
+    int32_t* ccw = out + (kc + 1) * L;
+    int w = 0;
+    auto put = [&](int32_t* dst, int r, int c) { dst[w++] = c * H + r; };
+    int top = 0, bottom = H - 1, left = 0, right = W - 1;
+    while (top <= bottom && left <= right) {
+        for (int i = left; i <= right; ++i) put(cw, top, i);
+        ++top;
+        for (int i = top; i <= bottom; ++i) put(cw, i, right);
+        --right;
+        if (top <= bottom) {
+            for (int i = right; i >= left; --i) put(cw, bottom, i);
+            --bottom;
+        }
+        if (left <= right) {
+            for (int i = bottom; i >= top; --i) put(cw, i, left);
+            ++left;
+        }
+    }
+    w = 0, top = 0, bottom = H - 1, left = 0, right = W - 1;
+    while (top <= bottom && left <= right) {
+        for (int i = right; i >= left; --i) put(ccw, bottom, i);
+        --bottom;
+        for (int i = bottom; i >= top; --i) put(ccw, i, left);
+        ++left;
+        if (top <= bottom) {
+            for (int i = left; i <= right; ++i) put(ccw, top, i);
+            ++top;
+        }
+        if (left <= right) {
+            for (int i = top; i <= bottom; ++i) put(ccw, i, right);
+            --right;
+        }
+    }
+}
+
+// csms6s.py:478-497: gather(3, (h +/- w) % W) then transpose + flatten, i.e. token t = w*H + h reads
+// x[h, (h + w) % W] (diagonal, slot kd) and x[h, (w - h) mod W] (anti-diagonal, slot kd + 1).
+void diagonal_tables(int H, int W, int32_t* out, int kd) {
+    const int L = H * W;
+    for (int t = 0; t < L; ++t) {
+        const int w = t / H, h = t % H;
+        out[kd * L + t] = h * W + (h + w) % W;
+        out[(kd + 1) * L + t] = h * W + ((w - h) % W + W) % W;
+    }
+}
+
+// Hilbert.py:9-331 ("spacefill" of an arbitrary rectangle), restricted to the cases a square of side
+// 2^m or 3*2^m reaches: halving even-even blocks (Hilbert.py:187-200), splitting odd-odd 3x3 blocks into
+// 2+1 strips (:242-257) and the <= 6-cell leaves (:33-64).  Coordinates are the reference's 1-based
+// doubles (block corners sit on half-integers after the /2 terms); anything outside the restricted set
+// marks the walk as failed and the caller reports TRAMBA_E_ORDER.
+struct HilbertWalk {
+    int H;
+    std::vector<int32_t>* out;
+    bool ok = true;
+    static int iabs(int v) { return v < 0 ? -v : v; }
+    static int half_even(int v) { return static_cast<int>(std::nearbyint(v / 2.0)); }  // Python round()
+    void emit(double x, double y) {                                                    // Hilbert.py:7-9
+        out->push_back(static_cast<int>(y - 1) * H + static_cast<int>(x - 1));
+    }
+    // leaf: walk n cells along (ax, ay) at the half-offset (ox, oy), forwards or backwards
+    void strip(double x0, double y0, int ax, int ay, double ox, double oy, bool backwards) {
+        const int n = iabs(ax + ay);
+        const double ddx = static_cast<double>(ax) / n, ddy = static_cast<double>(ay) / n;
+        for (int s = 0; s < n; ++s) {
+            const int ii = backwards ? n - 1 - s : s;
+            emit(x0 + ii * ddx + (ox + ddx - 1) / 2, y0 + ii * ddy + (oy + ddy - 1) / 2);
+        }
+    }
+    void go(int x0, int y0, int xl, int yl, int xr, int yr, char dir) {
+        if (!ok) return;
+        const int nl = iabs(xl + yl), nr = iabs(xr + yr);
+        if (nl * nr <= 6) {
+            if (nl == 1) return strip(x0, y0, xr, yr, xl, yl, false);                  // :34-39
+            if (nr == 1) return strip(x0, y0, xl, yl, xr, yr, false);                  // :41-46
+            if (dir == 'l') {                                                          // :48-55
+                strip(x0, y0, xr, yr, xl / 2.0, yl / 2.0, false);
+                return strip(x0, y0, xr, yr, xl + xl / 2.0, yl + yl / 2.0, true);
+            }
+            if (dir == 'r') {                                                          // :57-64
+                strip(x0, y0, xl, yl, xr / 2.0, yr / 2.0, false);
+                return strip(x0, y0, xl, yl, xr + xr / 2.0, yr + yr / 2.0, true);
+            }
+            ok = false;
+            return;
+        }
+        // squares only: neither side is "much longer" than the other (:102,142), and dir is l / r
+        if (2 * nl > 3 * nr || 2 * nr > 3 * nl || dir == 'm') {
+            ok = false;
+            return;
+        }
+        int xl2 = half_even(xl), yl2 = half_even(yl), xr2 = half_even(xr), yr2 = half_even(yr);
+        const bool le = nl % 2 == 0, re = nr % 2 == 0;
+        char mid;
+        if (le && re) {
+            if (iabs(xl2 + yl2 + xr2 + yr2) % 2 != 0) {                                // ee-oo / oo-ee: not reached
+                ok = false;
+                return;
+            }
+            mid = 0;
+        } else if (!le && !re) {                                                       // odd-odd -> eo-eo (:244-247)
+            if (xl2 % 2 != 0) xl2 = xl - xl2;
+            if (yl2 % 2 != 0) yl2 = yl - yl2;
+            if (xr2 % 2 != 0) xr2 = xr - xr2;
+            if (yr2 % 2 != 0) yr2 = yr - yr2;
+            mid = 'm';
+        } else {
+            ok = false;
+            return;
+        }
+        if (dir == 'l') {
+            go(x0, y0, xl2, yl2, xr2, yr2, 'r');
+            if (mid) {                                                                 // :250-251
+                go(x0 + xr2, y0 + yr2, xl2, yl2, xr - xr2, yr - yr2, 'm');
+                go(x0 + xr + xl2, y0 + yr + yl2, xr2 - xr, yr2 - yr, xl - xl2, yl - yl2, 'm');
+            } else {                                                                   // :193-194
+                go(x0 + xr2, y0 + yr2, xl2, yl2, xr - xr2, yr - yr2, 'l');
+                go(x0 + xr2 + xl2, y0 + yr2 + yl2, xl - xl2, yl - yl2, xr - xr2, yr - yr2, 'l');
+            }
+            go(x0 + xr2 + xl, y0 + yr2 + yl, xl2 - xl, yl2 - yl, -xr2, -yr2, 'r');
+        } else {
+            go(x0, y0, xl2, yl2, xr2, yr2, 'l');
+            if (mid) {                                                                 // :255-256
+                go(x0 + xl2, y0 + yl2, xl - xl2, yl - yl2, xr2, yr2, 'm');
+                go(x0 + xl + xr2, y0 + yl + yr2, xr - xr2, yr - yr2, xl2 - xl, yl2 - yl, 'm');
+            } else {                                                                   // :198-199
+                go(x0 + xl2, y0 + yl2, xl - xl2, yl - yl2, xr2, yr2, 'r');
+                go(x0 + xr2 + xl2, y0 + yr2 + yl2, xl - xl2, yl - yl2, xr - xr2, yr - yr2, 'r');
+            }
+            go(x0 + xl2 + xr, y0 + yl2 + yr, -xl2, -yl2, xr2 - xr, yr2 - yr, 'l');
+        }
+    }
+};
+
+// csms6s.py:374-405: k0 = x.flat[hilbert], k1 = flip(x, rows).flat[hilbert], k2/k3 = their reversals.
+// get_hilber_spacefill(1, 1, H, H) -> spacefill(ll=1, tt=1, ww=H, hh=H) -> go(1, 1, H, 0, 0, H, "l").
+int hilbert_table(int H, int W, int32_t* out) {
+    const int L = H * W;
+    std::vector<int32_t> walk;
+    walk.reserve(L);
+    HilbertWalk hw{H, &walk};
+    hw.go(1, 1, W, 0, 0, H, 'l');
+    if (!hw.ok || static_cast<int>(walk.size()) != L) return TRAMBA_E_ORDER;
+    std::vector<char> seen(L, 0);
+    for (int t = 0; t < L; ++t) {
+        const int p = walk[t];
+        if (p < 0 || p >= L || seen[p]) return TRAMBA_E_ORDER;
+        seen[p] = 1;
+        out[t] = p;
+        out[L + t] = (H - 1 - p / W) * W + p % W;   // torch.flip(input, [2]) (csms6s.py:401)
+    }
+    flip_row(L, out, 2, 0);
+    flip_row(L, out, 3, 1);
+    return TRAMBA_OK;
+}
+
 }  // namespace
 
 extern "C" int tramba_order_num_directions(int order) {
     switch (order) {
         case TRAMBA_ORDER_STD:
         case TRAMBA_ORDER_DILATION:
-        case TRAMBA_ORDER_WINDOW: return 4;
-        case TRAMBA_ORDER_LINE: return 8;
+        case TRAMBA_ORDER_WINDOW:
+        case TRAMBA_ORDER_LINE4:
+        case TRAMBA_ORDER_HILBERT:
+        case TRAMBA_ORDER_AB2:
+        case TRAMBA_ORDER_AB1: return 4;
+        case TRAMBA_ORDER_LINE:
+        case TRAMBA_ORDER_SPIRAL:
+        case TRAMBA_ORDER_DIAGONAL:
+        case TRAMBA_ORDER_DS: return 8;
         default: return TRAMBA_E_ORDER;
     }
 }
@@ -140,6 +318,7 @@ extern "C" int tramba_order_table(int order, int H, int W, int param, int32_t* i
     if (!idx_out) return TRAMBA_E_NULL;
     if (H <= 0 || W <= 0 || H != W) return TRAMBA_E_SHAPE;  // square maps only (reference: row*H+col)
     if (static_cast<long long>(H) * W > (1ll << 24)) return TRAMBA_E_LIMIT;
+    const int L = H * W;
     switch (order) {
         case TRAMBA_ORDER_STD: std_table(H, W, idx_out); return TRAMBA_OK;
         case TRAMBA_ORDER_DILATION:
@@ -154,12 +333,46 @@ extern "C" int tramba_order_table(int order, int H, int W, int param, int32_t* i
         case TRAMBA_ORDER_LINE:
             std_table(H, W, idx_out);
             return line_table(H, W, idx_out);
+        case TRAMBA_ORDER_LINE4: {  // csms6s.py:219-265: the four helix lists alone
+            std::vector<int32_t> t8(static_cast<size_t>(8) * L);
+            const int rc = line_table(H, W, t8.data());
+            if (rc != TRAMBA_OK) return rc;
+            std::copy(t8.begin() + static_cast<size_t>(4) * L, t8.end(), idx_out);
+            return TRAMBA_OK;
+        }
+        case TRAMBA_ORDER_SPIRAL:  // csms6s.py:316-339: std k0-3, cw, ccw, flip(cw), flip(ccw)
+            std_table(H, W, idx_out);
+            spiral_tables(H, W, idx_out, 4);
+            flip_row(L, idx_out, 6, 4);
+            flip_row(L, idx_out, 7, 5);
+            return TRAMBA_OK;
+        case TRAMBA_ORDER_HILBERT: return hilbert_table(H, W, idx_out);
+        case TRAMBA_ORDER_DIAGONAL:  // csms6s.py:531-549: std k0-3, diag, anti-diag, their flips
+            std_table(H, W, idx_out);
+            diagonal_tables(H, W, idx_out, 4);
+            flip_row(L, idx_out, 6, 4);
+            flip_row(L, idx_out, 7, 5);
+            return TRAMBA_OK;
+        case TRAMBA_ORDER_DS: {  // csms6s.py:619-631: helix lists in slots 0-3, diagonals in 4-7
+            const int rc = line_table(H, W, idx_out);  // fills slots 4-7
+            if (rc != TRAMBA_OK) return rc;
+            std::copy(idx_out + static_cast<size_t>(4) * L, idx_out + static_cast<size_t>(8) * L, idx_out);
+            diagonal_tables(H, W, idx_out, 4);
+            flip_row(L, idx_out, 6, 4);
+            flip_row(L, idx_out, 7, 5);
+            return TRAMBA_OK;
+        }
+        case TRAMBA_ORDER_AB2:  // csms6s.py:678-685: row-major twice, then both reversed
+        case TRAMBA_ORDER_AB1:  // csms6s.py:713-718: row-major four times
+            for (int k = 0; k < 4; ++k)
+                for (int t = 0; t < L; ++t)
+                    idx_out[k * L + t] = (order == TRAMBA_ORDER_AB2 && k >= 2) ? L - 1 - t : t;
+            return TRAMBA_OK;
         default: return TRAMBA_E_ORDER;
     }
 }
 
 // DCT_2D.py:37-45: W[v][j] = cos(pi*(0.5+j)*v/n)/sqrt(n) * (v ? sqrt(2) : 1), in double, stored fp32.
-#include <cmath>
 extern "C" void tramba_dct_basis(int n, float* w_out) {
     const double pi = 3.141592653589793;  // == math.pi
     for (int v = 0; v < n; ++v)

@@ -5,6 +5,10 @@
     CrossScan_Window / CrossMerge_Window         Models/SS2D/csms6s.py:113-152
     CrossScan_Line / CrossMerge_Line             Models/SS2D/csms6s.py:161-216   (Helix-SS2D, K = 8)
     SelectiveScanOflex                           Models/SS2D/csms6s.py:904-923
+Ablation orders (not on the Tramba-V path; table-driven kernels, never the fused core):
+    CrossScan_Line_4direction / _Spiral / _Hilbert / _Diagonal / _DS / _Ab_2direction / _Ab_1direction
+    and their CrossMerge_* twins                 Models/SS2D/csms6s.py:219-737
+    make_custom_pair(name, table)                any caller-supplied (K, L) gather table
 
 Each is a torch.autograd.Function used through `.apply`, exactly like the reference classes,
 so they can be passed as `scan=` / `merge=` to SS2D or assigned over the reference's own
@@ -111,6 +115,22 @@ def cross_merge(ys, order, H, W, param=0):
     return y
 
 
+def _custom_plan(table, device):
+    """Order plan (device) of a caller-supplied (K, L) gather table; cached on the table's bytes."""
+    table = np.ascontiguousarray(table, dtype=np.int32)
+    if table.ndim != 2:
+        raise ValueError("tramba_b200: a custom order table must be (K, L)")
+    key = ("custom", table.shape, hash(table.tobytes()), device)
+    hit = _plan_cache.get(key)
+    if hit is None:
+        K, L = table.shape
+        plan = np.empty(_lib.lib.tramba_order_plan_elems(K, L), dtype=np.int32)
+        _lib.check(_lib.lib.tramba_order_plan_from_table(K, L, table.ctypes.data, plan.ctypes.data))
+        hit = (K, torch.from_numpy(plan).to(device))
+        _plan_cache[key] = hit
+    return hit
+
+
 def _make_pair(name, order, param_of):
     """Build the CrossScan*/CrossMerge* pair for one order family."""
 
@@ -158,6 +178,90 @@ CrossScan_Dilation, CrossMerge_Dilation = _make_pair("_Dilation", _lib.ORDER_DIL
                                                      lambda H: dilation_rate_for[str(H)])
 CrossScan_Window, CrossMerge_Window = _make_pair("_Window", _lib.ORDER_WINDOW, lambda H: window_size_for[str(H)])
 CrossScan_Line, CrossMerge_Line = _make_pair("_Line", _lib.ORDER_LINE, _line_param)
+
+
+# --- the reference's ablation orders (csms6s.py:219-737).  They are not on the Tramba-V path: the pairs carry
+# no `tramba_order` routing attribute, so SS2D always runs them op-by-op on the table-driven kernels.
+def _ref_sizes_only(H):
+    assert H in sizes            # reference: `assert H == W and H in [12, 24, 48, 96]` (csms6s.py:272,392)
+    return 0
+
+
+def _ablation_pair(name, order, param_of):
+    S, M = _make_pair(name, order, param_of)
+    for cls in (S, M):
+        cls.tramba_ablation_order = order
+        del cls.tramba_order, cls.tramba_param
+    return S, M
+
+
+CrossScan_Line_4direction, CrossMerge_Line_4direction = _ablation_pair("_Line_4direction", _lib.ORDER_LINE4, _line_param)
+CrossScan_Spiral, CrossMerge_Spiral = _ablation_pair("_Spiral", _lib.ORDER_SPIRAL, _ref_sizes_only)
+CrossScan_Hilbert, CrossMerge_Hilbert = _ablation_pair("_Hilbert", _lib.ORDER_HILBERT, _ref_sizes_only)
+CrossScan_Diagonal, CrossMerge_Diagonal = _ablation_pair("_Diagonal", _lib.ORDER_DIAGONAL, lambda H: 0)
+CrossScan_DS, CrossMerge_DS = _ablation_pair("_DS", _lib.ORDER_DS, _line_param)
+CrossScan_Ab_2direction, CrossMerge_Ab_2direction = _ablation_pair("_Ab_2direction", _lib.ORDER_AB2, lambda H: 0)
+CrossScan_Ab_1direction, CrossMerge_Ab_1direction = _ablation_pair("_Ab_1direction", _lib.ORDER_AB1, lambda H: 0)
+
+
+def make_custom_pair(name, table_of):
+    """(CrossScan, CrossMerge) autograd pair for ANY gather table: `table_of(H)` returns the (K, L = H*H) flat
+    pixel index of every token (repeats allowed, like the helix lists).  scan: xs[b,k,c,t] = x[b,c].flat[T[k,t]];
+    merge: its exact transpose, summed sequentially over k then t (deterministic, no atomics)."""
+
+    def scan(x):
+        B, C, H, W = x.shape
+        _check_square(H, W)
+        _require_cuda(x)
+        x = x.contiguous()
+        K, plan = _custom_plan(table_of(H), x.device)
+        xs = x.new_empty((B, K, C, H * W))
+        with torch.cuda.device(x.device), _lib.timed("cross_scan", (1 + K) * x.numel() * x.element_size()):
+            _lib.check(_lib.lib.tramba_cross_scan(x.data_ptr(), xs.data_ptr(), plan.data_ptr(), _lib.ORDER_CUSTOM, K,
+                                                  B, C, H, W, _dtype_code(x), _stream()))
+        return xs
+
+    def merge(ys, H, W):
+        _check_square(H, W)
+        _require_cuda(ys)
+        B, K, D = ys.shape[:3]
+        ys = ys.contiguous()
+        K2, plan = _custom_plan(table_of(H), ys.device)
+        if K2 != K:
+            raise ValueError(f"tramba_b200: order expects K={K2} directions, got {K}")
+        y = ys.new_empty((B, D, H * W))
+        with torch.cuda.device(ys.device), _lib.timed("cross_merge", (1 + K) * y.numel() * y.element_size()):
+            _lib.check(_lib.lib.tramba_cross_merge(ys.data_ptr(), y.data_ptr(), plan.data_ptr(), _lib.ORDER_CUSTOM, K,
+                                                   B, D, H, W, _dtype_code(ys), _stream()))
+        return y
+
+    class Scan(torch.autograd.Function):
+        @staticmethod
+        def forward(ctx, x):
+            ctx.shape = x.shape
+            return scan(x)
+
+        @staticmethod
+        def backward(ctx, ys):
+            B, C, H, W = ctx.shape
+            return merge(ys, H, W).view(B, -1, H, W)
+
+    class Merge(torch.autograd.Function):
+        @staticmethod
+        def forward(ctx, ys):
+            B, K, D, H, W = ys.shape
+            ctx.shape = (H, W)
+            return merge(ys.view(B, K, D, -1), H, W)
+
+        @staticmethod
+        def backward(ctx, x):
+            H, W = ctx.shape
+            B, C, L = x.shape
+            return scan(x.view(B, C, H, W)).view(B, -1, C, H, W)
+
+    Scan.__name__ = Scan.__qualname__ = "CrossScan" + name
+    Merge.__name__ = Merge.__qualname__ = "CrossMerge" + name
+    return Scan, Merge
 
 
 class SelectiveScanOflex(torch.autograd.Function):
