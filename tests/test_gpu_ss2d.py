@@ -18,9 +18,6 @@ CASES = [
     ("window", tramba_b200.CrossScan_Window, tramba_b200.CrossMerge_Window, 4, 1, 24),
     ("dilation", tramba_b200.CrossScan_Dilation, tramba_b200.CrossMerge_Dilation, 4, 1, 12),
     ("std", tramba_b200.CrossScan, tramba_b200.CrossMerge, 4, 16, 12),      # config-2 state size
-    # ablation orders (csms6s.py:316-368, 439-473): op-by-op on the table-driven kernels
-    ("spiral", tramba_b200.CrossScan_Spiral, tramba_b200.CrossMerge_Spiral, 8, 1, 12),
-    ("hilbert", tramba_b200.CrossScan_Hilbert, tramba_b200.CrossMerge_Hilbert, 4, 1, 12),
 ]
 
 

@@ -1,7 +1,13 @@
 """GPU parity of the reference's ablation scan orders (csms6s.py:219-737) through the
 table-driven cross-scan / cross-merge kernels: against the reference classes' own outputs (small sizes) and the
 oracle (full sizes).  Gathers are bit-exact; merges are bit-exact against the oracle's sequential sums and within
-fp32 association (2e-6) of the reference's per-family grouping."""
+fp32 association (2e-6) of the reference's per-family grouping.
+
+Written after round 1's GPU budget was spent: the logic of every test here was exercised against a CPU emulation
+of tramba_cross_scan / tramba_cross_merge (oracle behind the same pointers), but none has run on a B200 yet.
+The file name sorts after every GPU-verified test file so that `pytest -x` reaches those first."""
+import copy
+
 import numpy as np
 import pytest
 import torch
@@ -9,6 +15,7 @@ import torch
 import tramba_b200
 from tramba_b200 import _lib
 from oracle import scan_orders as so
+from _oracle_ops import OracleSelectiveScan, make_pair
 
 pytestmark = pytest.mark.gpu
 
@@ -116,3 +123,35 @@ def test_size_errors_like_reference():
         tramba_b200.CrossScan_DS.apply(torch.zeros(1, 1, 20, 20, device="cuda"))
     with pytest.raises(AssertionError):
         tramba_b200.CrossScan_Spiral.apply(torch.zeros(1, 1, 20, 20, device="cuda"))
+
+
+@pytest.mark.parametrize("fam,K", [("spiral", 8), ("hilbert", 4)])
+def test_ss2d_module_with_ablation_order(fam, K):
+    """SS2D(scan=CrossScan_Spiral, ...) as BaseUMamba-style ablations build it: op-by-op on the table-driven
+    kernels (these pairs are never routed to the fused core), forward + backward vs the oracle composition."""
+    S, M, _ = PAIRS[fam]
+    H = 12
+    torch.manual_seed(0)
+    m = tramba_b200.SS2D(d_model=32, d_state=1, ssm_ratio=2.0, dt_rank="auto", d_conv=3, conv_bias=False,
+                         channel_first=True, disable_z=True, scan=S, merge=M, k_group=K)
+    assert m._fused_order(torch.zeros(2, 64, H, H)) is None
+    ref = copy.deepcopy(m)
+    ref.scan, ref.merge = make_pair(fam)
+    ref.selective_scan = OracleSelectiveScan
+    x = torch.randn(2, 32, H, H)
+    xr = x.clone().requires_grad_(True)
+    yr = ref(xr)
+    gy = torch.randn_like(yr)
+    yr.backward(gy)
+    m = m.cuda()
+    xg = x.cuda().requires_grad_(True)
+    yg = m(xg)
+    yg.backward(gy.cuda())
+    np.testing.assert_allclose(yg.detach().cpu().numpy(), yr.detach().numpy(), rtol=1e-3,
+                               atol=1e-3 * float(yr.detach().abs().max()))
+    np.testing.assert_allclose(xg.grad.cpu().numpy(), xr.grad.numpy(), rtol=1e-3,
+                               atol=1e-3 * float(xr.grad.abs().max()))
+    for (n, pg), (_, pr) in zip(m.named_parameters(), ref.named_parameters()):
+        assert pg.grad is not None, n
+        np.testing.assert_allclose(pg.grad.cpu().numpy(), pr.grad.numpy(), rtol=2e-3,
+                                   atol=2e-3 * float(pr.grad.abs().max()) + 1e-7, err_msg=n)

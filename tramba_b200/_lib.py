@@ -8,7 +8,13 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libtramba_b200.so")
+# TRAMBA_B200_LIB=next loads the CANDIDATE build (libtramba_b200_next.so: same sources compiled with
+# -DTRAMBA_NEXT plus csrc/next/, see build.py) so that the whole test suite and bench.py can be pointed at kernels
+# under evaluation without touching the product library.  Unset (the default) = the product library.
+VARIANT = os.environ.get("TRAMBA_B200_LIB", "")
+if VARIANT not in ("", "next"):
+    raise ImportError(f"tramba_b200: unknown TRAMBA_B200_LIB={VARIANT!r} (expected unset or 'next')")
+LIB_PATH = os.path.join(_HERE, "libtramba_b200_next.so" if VARIANT == "next" else "libtramba_b200.so")
 
 F32, BF16, F16 = 0, 1, 2
 ACT_NONE, ACT_GELU, ACT_SILU = 0, 1, 2
@@ -62,7 +68,10 @@ def _load():
     spec = importlib.util.spec_from_file_location("_tramba_b200_build", os.path.join(_HERE, "build.py"))
     _build = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(_build)
-    if not os.path.exists(LIB_PATH) or (_build.sources_newer_than_lib() and os.path.exists(_build.NVCC)):
+    if VARIANT == "next":
+        if not os.path.exists(LIB_PATH):
+            _build.build(next_variant=True)
+    elif not os.path.exists(LIB_PATH) or (_build.sources_newer_than_lib() and os.path.exists(_build.NVCC)):
         _build.build()  # raises if nvcc is unavailable or fails: no silent fallback
     lib = ctypes.CDLL(LIB_PATH)
     for name, (res, args) in SIGNATURES.items():

@@ -1,6 +1,9 @@
 """Build libtramba_b200.so (C-ABI, sm_100a only) in-tree with nvcc.
 
     python -m tramba_b200.build [--force] [--verbose]
+    python -m tramba_b200.build --next      # libtramba_b200_next.so: the same library compiled with -DTRAMBA_NEXT
+                                            # plus the candidate kernels under csrc/next/ (not the product; see
+                                            # tools/variant_bench.py and TRAMBA_B200_LIB=next in _lib.py)
 
 The library links the CUDA runtime statically and has no torch / Python dependency; the
 Python host loads it with ctypes (tramba_b200/_lib.py).  Built artefacts are git-ignored but
@@ -35,13 +38,23 @@ def sources_newer_than_lib():
     return _stale(LIB, deps)
 
 
-def build(force=False, verbose=False):
+NEXT_SOURCES = [os.path.join("next", "ss2d_fused_fwd_cg.cu"), os.path.join("next", "ss2d_fused_bwd_cg.cu")]
+LIB_NEXT = os.path.join(HERE, "libtramba_b200_next.so")
+
+
+def build(force=False, verbose=False, next_variant=False):
+    """next_variant: build libtramba_b200_next.so (candidate kernels, -DTRAMBA_NEXT) into its own object
+    directory; the product library and its objects are not touched."""
+    OBJ = os.path.join(HERE, "_obj_next" if next_variant else "_obj")
+    LIB = LIB_NEXT if next_variant else globals()["LIB"]
+    SOURCES = globals()["SOURCES"] + (NEXT_SOURCES if next_variant else [])
+    FLAGS = globals()["FLAGS"] + (["-DTRAMBA_NEXT"] if next_variant else [])
     os.makedirs(OBJ, exist_ok=True)
     hdrs = [os.path.join(CSRC, h) for h in HEADERS] + [os.path.abspath(__file__)]
     jobs = []
     for s in SOURCES:
         src = os.path.join(CSRC, s)
-        obj = os.path.join(OBJ, os.path.splitext(s)[0] + ".o")
+        obj = os.path.join(OBJ, os.path.splitext(os.path.basename(s))[0] + ".o")
         if force or _stale(obj, [src] + hdrs):
             if s.endswith(".cu"):
                 cmd = [NVCC] + FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj]
@@ -55,7 +68,7 @@ def build(force=False, verbose=False):
                     sys.stderr.write(" ".join(cmd) + "\n" + res.stdout + res.stderr)
                 if res.returncode != 0:
                     raise RuntimeError("nvcc failed: " + " ".join(cmd))
-    objs = [os.path.join(OBJ, os.path.splitext(s)[0] + ".o") for s in SOURCES]
+    objs = [os.path.join(OBJ, os.path.splitext(os.path.basename(s))[0] + ".o") for s in SOURCES]
     if force or jobs or _stale(LIB, objs):
         cmd = [NVCC, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", LIB] + objs + [
                "-Xcompiler", "-fPIC", "-cudart", "static",
@@ -65,4 +78,4 @@ def build(force=False, verbose=False):
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv))
+    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv, next_variant="--next" in sys.argv))

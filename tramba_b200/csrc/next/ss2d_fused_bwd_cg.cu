@@ -1,4 +1,17 @@
-// Fused SS2D core, backward (sm_100a).  See ss2d_fused.cuh for the data model.
+// Fused SS2D core, backward (sm_100a) -- COMPILE-TIME-GEOMETRY candidate ("next" build only, -DTRAMBA_NEXT).
+// Same algorithm, data layout, shared-memory layout and results as ss2d_fused_bwd.cu (see there and
+// ss2d_fused.cuh); what changes is how much of the index arithmetic the compiler can fold:
+//   * TPC (threads per plane = L / 18) and XB (staging depth) are template constants, so L, PP, LSK, every
+//     shared-memory offset, tid / TP, e / L ... are immediates or shifts;
+//   * the S/2 cp.async copies that stage a thread's share of the x and dy planes are fully unrolled with
+//     constant strides (ss2d_fused.cuh: stage_plane_skewed_c) instead of a pointer-chasing loop;
+//   * the (b, k, channel) coordinates of the next round are carried incrementally (one division per ITEM
+//     instead of three per ROUND per thread);
+//   * A / D / bias of the next round are loaded one round ahead (their L2 latency used to sit on the
+//     critical path right after the barrier).
+// NOT part of libtramba_b200.so: built into libtramba_b200_next.so by `python -m tramba_b200.build --next`
+// and compared against the product kernels on the GPU by tools/variant_bench.py (bit-identical du / ddelta /
+// dA / dD / dbias expected: the floating-point operations and their order are unchanged).
 // Replaces CrossMerge*.backward -> SelectiveScanOflex.backward of Models/SS2D/csms6s.py:45-55,914-923
 // (and the _Dilation/_Window/_Line variants) for N = 1: the gradient of the merged map is
 // gathered through the scan-order table in shared memory, so neither the K-fold copy of dy
@@ -16,7 +29,7 @@
 // dB_t = sum_d dh_t*delta_t*u_t and dC_t = sum_d dy_t*h_t are accumulated in registers over all
 // rounds of the item (same b, k) and added to global memory once per item.  dA, dD, ddelta_bias
 // leave as per-(b, row) partial sums (no atomics; the host sums over b).
-#include "ss2d_fused.cuh"
+#include "../ss2d_fused.cuh"
 
 namespace tramba {
 
@@ -50,11 +63,13 @@ struct BwdLayout {
     }
 };
 
-template <typename in_t, bool SOFTPLUS>
-__global__ void __launch_bounds__(NT, 1) ss2d_bwd_kernel(const FusedArgs p, const int R) {
+template <typename in_t, bool SOFTPLUS, int TPC, int XB>
+__global__ void __launch_bounds__(NT, 1) ss2d_bwd_cg_kernel(const FusedArgs p, const int R) {
     extern __shared__ __align__(128) unsigned char smem[];
     constexpr int ES = sizeof(in_t);
-    const int L = p.L, K = p.K, D = p.D, TP = p.TP, PP = p.PP, XB = p.xb;
+    constexpr int TP = TPC, L = S * TPC, PP = NT / TPC;
+    static_assert(TPC >= 1 && (TPC & (TPC - 1)) == 0 && TPC <= NT, "threads per plane: a power of two <= 512");
+    const int K = p.K, D = p.D;
     const BwdLayout lay(L, ES, XB);
     const int LSK = lay.lsk;
     in_t* sx = reinterpret_cast<in_t*>(smem + lay.x);      // [XB][PP][LSK] skewed
@@ -111,14 +126,12 @@ __global__ void __launch_bounds__(NT, 1) ss2d_bwd_kernel(const FusedArgs p, cons
         b = bk / K;
         d0 = db * RB;
     };
-    auto issue_round = [&](int s) {  // all threads (x, dy of the thread's own plane by cp.async); thread 0 adds delta
-        int b, k, d0;
-        item_coord(s / R, b, k, d0);
-        d0 += (s % R) * PP;
+    // round s of this CTA = planes d0 .. d0+PP-1 of (b, k); the caller tracks (b, k, d0) incrementally
+    auto issue_round = [&](int s, int b, int k, int d0) {  // all threads (x, dy by cp.async); thread 0 adds delta
         const int buf = s % XB;
         const long long pl = static_cast<long long>(b) * D + d0 + q;
-        stage_plane_skewed<ES>(sx + (static_cast<size_t>(buf) * PP + q) * LSK, gx + pl * L, L, j, TP);
-        stage_plane_skewed<4>(sdy + (static_cast<size_t>(buf) * PP + q) * LSK, p.dy + pl * L, L, j, TP);
+        stage_plane_skewed_c<ES, TPC>(sx + (static_cast<size_t>(buf) * PP + q) * LSK, gx + pl * L, j);
+        stage_plane_skewed_c<4, TPC>(sdy + (static_cast<size_t>(buf) * PP + q) * LSK, p.dy + pl * L, j);
         cp_async_arrive(&barX[buf]);
         if (tid == 0) {
             mbar_expect_tx(&barD[buf], TOK * sizeof(in_t));
@@ -134,13 +147,23 @@ __global__ void __launch_bounds__(NT, 1) ss2d_bwd_kernel(const FusedArgs p, cons
         bulk_g2s(sB, gB + (static_cast<long long>(b) * K + k) * L, lb, &barBC[0]);
         bulk_g2s(sC, gC + (static_cast<long long>(b) * K + k) * L, lb, &barBC[0]);
     };
+    // per-row scalars of one round (A, D, delta_bias of row k*D + d0 + q)
+    auto load_row = [&](int k, int d0, float& Ar, float& Dd, float& bias) {
+        const int row = k * D + d0 + q;
+        Ar = __ldg(p.A + row);
+        Dd = p.Dp ? __ldg(p.Dp + row) : 0.f;
+        bias = p.bias ? __ldg(p.bias + row) : 0.f;
+    };
+    int nb, nk, nd0;  // coordinates of the next round to be issued / processed
+    item_coord(0, nb, nk, nd0);
     if (tid == 0) issue_bc(0);
-    issue_round(0);
+    issue_round(0, nb, nk, nd0);
+    float nAr, nDd, nbias;  // ... and its per-row scalars, loaded one round ahead
+    load_row(nk, nd0, nAr, nDd, nbias);
 
     int s = 0;
     for (int it = 0; it < my_items; ++it) {
-        int b, k, d00;
-        item_coord(it, b, k, d00);
+        const int b = nb, k = nk, d00 = nd0;  // == item_coord(it): the first round of an item starts at its d00
         uint32_t pk[S / 2];
         {
             const uint32_t* tp = reinterpret_cast<const uint32_t*>(p.idx + static_cast<size_t>(k) * L + j * S);
@@ -156,14 +179,21 @@ __global__ void __launch_bounds__(NT, 1) ss2d_bwd_kernel(const FusedArgs p, cons
 
         for (int r = 0; r < R; ++r, ++s) {
             const int buf = s % XB;
-            if (XB == 2 && s + 1 < nrounds) issue_round(s + 1);
             const int d0 = d00 + r * PP;
             const int d = d0 + q;
             const int row = k * D + d;
-            const float Ar = __ldg(p.A + row);
+            const float Ar = nAr, Dd = nDd, bias = nbias;  // loaded during the previous round
             const float A2 = Ar * kLog2e;
-            const float Dd = p.Dp ? __ldg(p.Dp + row) : 0.f;
-            const float bias = p.bias ? __ldg(p.bias + row) : 0.f;
+            // coordinates of round s + 1: the next plane block of this item, or the first one of the next item
+            if (r + 1 < R) {
+                nd0 = d0 + PP;
+            } else if (it + 1 < my_items) {
+                item_coord(it + 1, nb, nk, nd0);
+            }
+            if (s + 1 < nrounds) {
+                if (XB == 2) issue_round(s + 1, nb, nk, nd0);
+                load_row(nk, nd0, nAr, nDd, nbias);
+            }
             mbar_wait(&barX[buf], static_cast<uint32_t>((s / XB) & 1));
             mbar_wait(&barD[buf], static_cast<uint32_t>((s / XB) & 1));
             const in_t* xq = sx + (static_cast<size_t>(buf) * PP + q) * LSK;
@@ -303,7 +333,7 @@ __global__ void __launch_bounds__(NT, 1) ss2d_bwd_kernel(const FusedArgs p, cons
                 bulk_s2g(gdu + po, so_du, TOK * sizeof(in_t));
                 bulk_commit();
             }
-            if (XB == 1 && s + 1 < nrounds) issue_round(s + 1);
+            if (XB == 1 && s + 1 < nrounds) issue_round(s + 1, nb, nk, nd0);
             if (TP > 32 && j == 0) {
                 float tA = 0.f, tD = 0.f, tb = 0.f;
                 for (int w = 0; w < nwg; ++w) tA += sred[gw0 + w], tD += sred[NW + gw0 + w], tb += sred[2 * NW + gw0 + w];
@@ -356,21 +386,17 @@ __global__ void __launch_bounds__(NT, 1) ss2d_bwd_kernel(const FusedArgs p, cons
     if (tid == 0) bulk_wait_all<0>();
 }
 
-}  // namespace
-
-size_t ss2d_fused_bwd_smem(int L, int es, int xb) { return BwdLayout(L, es, xb).total; }
-
-// Channels per item: enough rounds that the per-item dB/dC flush is amortised (>= 8 channels).
+// Channels per item: enough rounds that the per-item dB/dC flush is amortised (>= 8 channels); same rule as
+// ss2d_fused_bwd.cu so that both kernels split the work identically.
 static int pick_rounds(const FusedArgs& a) {
     int R = 1;
     while (R * a.PP < 8 && a.D % (2 * R * a.PP) == 0) R *= 2;
     return R;
 }
 
-template <typename in_t, bool SOFTPLUS>
-static cudaError_t launch_t(const FusedArgs& a, cudaStream_t st) {
-    const size_t cap = 227 * 1024;
-    auto kern = ss2d_bwd_kernel<in_t, SOFTPLUS>;
+template <typename in_t, bool SOFTPLUS, int TPC, int XB>
+static cudaError_t launch_cg(const FusedArgs& a, cudaStream_t st) {
+    auto kern = ss2d_bwd_cg_kernel<in_t, SOFTPLUS, TPC, XB>;
     static bool configured = false;
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
@@ -384,9 +410,8 @@ static cudaError_t launch_t(const FusedArgs& a, cudaStream_t st) {
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     }
     FusedArgs b = a;
-    b.xb = BwdLayout(a.L, sizeof(in_t), 2).total <= cap ? 2 : 1;
-    const size_t smem = BwdLayout(a.L, sizeof(in_t), b.xb).total;
-    if (smem > cap) return cudaErrorInvalidConfiguration;
+    b.xb = XB;
+    const size_t smem = BwdLayout(a.L, sizeof(in_t), XB).total;
     const int R = pick_rounds(a);
     const int items = a.B * a.K * (a.D / (R * a.PP));
     const int grid = items < sms ? items : sms;
@@ -395,24 +420,33 @@ static cudaError_t launch_t(const FusedArgs& a, cudaStream_t st) {
     return cudaGetLastError();
 }
 
-#ifdef TRAMBA_NEXT
-cudaError_t launch_ss2d_fused_bwd_cg(const FusedArgs& a, int in_dtype, cudaStream_t st);  // csrc/next/
-#endif
-
-cudaError_t launch_ss2d_fused_bwd(const FusedArgs& a, int in_dtype, cudaStream_t st) {
-#ifdef TRAMBA_NEXT  // candidate build (libtramba_b200_next.so): compile-time-geometry kernels where they apply
-    const cudaError_t e = launch_ss2d_fused_bwd_cg(a, in_dtype, st);
-    if (e != cudaErrorNotSupported) return e;
-#endif
-    if (in_dtype == TRAMBA_F32) return a.softplus ? launch_t<float, true>(a, st) : launch_t<float, false>(a, st);
-    if (in_dtype == TRAMBA_BF16)
-        return a.softplus ? launch_t<__nv_bfloat16, true>(a, st) : launch_t<__nv_bfloat16, false>(a, st);
-    return cudaErrorInvalidValue;
+template <typename in_t, int XB>
+static cudaError_t dispatch_tp(const FusedArgs& a, cudaStream_t st) {
+    switch (a.TP) {  // L = 18 * TP: 144, 576, 2304, 9216 -- every Tramba-V map at 384^2
+        case 8: return launch_cg<in_t, true, 8, XB>(a, st);
+        case 32: return launch_cg<in_t, true, 32, XB>(a, st);
+        case 128: return launch_cg<in_t, true, 128, XB>(a, st);
+        case 512: return launch_cg<in_t, true, 512, XB>(a, st);
+        default: return cudaErrorNotSupported;
+    }
 }
 
-bool ss2d_fused_bwd_fits(int L, int es, uint32_t dup_mask, int K) {
-    (void)dup_mask, (void)K;
-    return BwdLayout(L, es, 1).total <= 227 * 1024;
+}  // namespace
+
+// Returns cudaErrorNotSupported when the shape is not one of the specialised ones (the caller then launches
+// the generic kernel).  Staging depth as the generic launcher picks it: 2 if it fits 227 KB, else 1.
+cudaError_t launch_ss2d_fused_bwd_cg(const FusedArgs& a, int in_dtype, cudaStream_t st) {
+    if (!a.softplus || a.L != S * a.TP || a.PP * a.TP != NT) return cudaErrorNotSupported;
+    const size_t cap = 227 * 1024;
+    if (in_dtype == TRAMBA_BF16) {
+        if (BwdLayout(a.L, 2, 2).total > cap) return cudaErrorNotSupported;
+        return dispatch_tp<__nv_bfloat16, 2>(a, st);
+    }
+    if (in_dtype == TRAMBA_F32) {
+        if (BwdLayout(a.L, 4, 2).total <= cap || BwdLayout(a.L, 4, 1).total > cap) return cudaErrorNotSupported;
+        return dispatch_tp<float, 1>(a, st);
+    }
+    return cudaErrorNotSupported;
 }
 
 }  // namespace tramba

@@ -118,6 +118,46 @@ __device__ __forceinline__ void stage_plane_skewed(void* dst_plane, const void* 
     }
 }
 
+// Same staging with the geometry known at compile time (TPC = threads per plane, n = kFusedS * TPC elements):
+// the kFusedS / 2 copies of a thread are fully unrolled and, for TPC a multiple of 32, their source and
+// destination strides are constants (vector v = j + i*TPC lands at v + (v >> 5) = j + (j >> 5) + i*(TPC + TPC/32)).
+// Used by the compile-time-geometry kernels under csrc/next/.
+template <int ES, int TPC>
+__device__ __forceinline__ void stage_plane_skewed_c(void* dst_plane, const void* __restrict__ src_plane, int j) {
+    static_assert(ES == 2 || ES == 4, "bf16 / fp32 planes");
+    if constexpr (ES == 2) {
+        uint32_t* d = static_cast<uint32_t*>(dst_plane);
+        const uint32_t* s = static_cast<const uint32_t*>(src_plane);
+        if constexpr ((TPC & 31) == 0) {
+            uint32_t* dp = d + j + (j >> 5);
+            const uint32_t* sp = s + j;
+#pragma unroll
+            for (int i = 0; i < kFusedS / 2; ++i) cp_async4(dp + i * (TPC + (TPC >> 5)), sp + i * TPC);
+        } else {
+#pragma unroll
+            for (int i = 0; i < kFusedS / 2; ++i) {
+                const int w = j + i * TPC;
+                cp_async4(d + w + (w >> 5), s + w);
+            }
+        }
+    } else {
+        uint2* d = static_cast<uint2*>(dst_plane);
+        const uint2* s = static_cast<const uint2*>(src_plane);
+        if constexpr ((TPC & 31) == 0) {
+            uint2* dp = d + j + (j >> 5);
+            const uint2* sp = s + j;
+#pragma unroll
+            for (int i = 0; i < kFusedS / 2; ++i) cp_async8(dp + i * (TPC + (TPC >> 5)), sp + i * TPC);
+        } else {
+#pragma unroll
+            for (int i = 0; i < kFusedS / 2; ++i) {
+                const int v = j + i * TPC;
+                cp_async8(d + v + (v >> 5), s + v);
+            }
+        }
+    }
+}
+
 // Affine-map inclusive scan over `width` lanes (width = 32 or a power of two below).
 __device__ __forceinline__ void fused_scan(float& P, float& S, int sl, int width) {
 #pragma unroll
