@@ -31,3 +31,4 @@ for f in ("gpurun_out/bench.json", "gpurun_out/bench_next.json"):
 PY
 timeout 300 python tools/ss2d_bench.py > gpurun_out/ss2d_bench.jsonl 2>&1; echo "ss2d_bench rc=$?"
 timeout 300 python tools/kernel_bench.py --dtype bf16 --fused-only > gpurun_out/kernel_bench_fused_bf16.jsonl 2>&1
+timeout 600 python tools/op_profile.py > gpurun_out/op_profile.txt 2> gpurun_out/op_profile.err; echo "op_profile rc=$?"; head -30 gpurun_out/op_profile.txt
