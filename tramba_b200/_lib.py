@@ -68,11 +68,18 @@ def _load():
     spec = importlib.util.spec_from_file_location("_tramba_b200_build", os.path.join(_HERE, "build.py"))
     _build = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(_build)
-    if VARIANT == "next":
-        if not os.path.exists(LIB_PATH):
-            _build.build(next_variant=True)
-    elif not os.path.exists(LIB_PATH) or (_build.sources_newer_than_lib() and os.path.exists(_build.NVCC)):
-        _build.build()  # raises if nvcc is unavailable or fails: no silent fallback
+    # one builder at a time: under torchrun every rank imports the package at the same moment
+    import fcntl
+    with open(os.path.join(_HERE, ".build.lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if VARIANT == "next":
+                if not os.path.exists(LIB_PATH):
+                    _build.build(next_variant=True)
+            elif not os.path.exists(LIB_PATH) or (_build.sources_newer_than_lib() and os.path.exists(_build.NVCC)):
+                _build.build()  # raises if nvcc is unavailable or fails: no silent fallback
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
     lib = ctypes.CDLL(LIB_PATH)
     for name, (res, args) in SIGNATURES.items():
         fn = getattr(lib, name)  # AttributeError if the library lacks a declared symbol
