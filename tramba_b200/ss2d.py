@@ -103,6 +103,16 @@ def _d_init(d_inner, copies):
     return p
 
 
+def _adopt(cls):
+    """A scan / merge class that is not ours but carries the name of one of the reference's operators
+    (csms6s.py:13-737) -> our class of that name; anything else (ours, custom pairs, unknown names) unchanged."""
+    name = getattr(cls, "__name__", "")
+    if getattr(cls, "__module__", "").startswith("tramba_b200") or not name.startswith(("CrossScan", "CrossMerge")):
+        return cls
+    ours = getattr(ops, name, None)
+    return ours if isinstance(ours, type) and issubclass(ours, torch.autograd.Function) else cls
+
+
 class SS2D(nn.Module):
     def __init__(
             self,
@@ -124,7 +134,10 @@ class SS2D(nn.Module):
         self.with_dconv = d_conv > 1
         self.disable_z = disable_z
         self.k_group = k_group
-        self.scan, self.merge = scan, merge
+        # The reference's module tree passes ITS classes (`scan=CrossScan_Line`, Models/vmamba.py:666-667,
+        # freq_mamba.py:22-33).  Same-named classes are the same operators: adopt ours, so that a module-level
+        # swap reaches the kernels (and the fused core) without also patching the operator names.
+        self.scan, self.merge = _adopt(scan), _adopt(merge)
         # bound like the reference's partial(forward_corev2, SelectiveScan=SelectiveScanOflex, ...)
         # (Models/vmamba.py:65-66); tests swap in the CPU oracle operator here
         self.selective_scan = ops.SelectiveScanOflex
