@@ -64,22 +64,23 @@ def timeit(fn, reps, flush):
     return ts[len(ts) // 2] * 1e3   # us
 
 
-def main():
+def main(argv=None):
     ap = argparse.ArgumentParser()
     ap.add_argument("--batch", type=int, default=4)
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "f32"])
     ap.add_argument("--reps", type=int, default=20)
     ap.add_argument("--only", default="")
+    ap.add_argument("--device", default="cuda:0")
     ap.add_argument("--base", default=os.path.join(os.path.dirname(_lib.LIB_PATH), "libtramba_b200.so"))
     ap.add_argument("--cand", default=os.path.join(os.path.dirname(_lib.LIB_PATH), "libtramba_b200_next.so"))
-    a = ap.parse_args()
+    a = ap.parse_args(argv)
     libs = {"base": load(a.base), "cand": load(a.cand)}
     dt = torch.bfloat16 if a.dtype == "bf16" else torch.float32
     code = _lib.BF16 if a.dtype == "bf16" else _lib.F32
     es = 2 if a.dtype == "bf16" else 4
-    dev = torch.device("cuda:0")
+    dev = torch.device(a.device)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-    st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream if dev.type == "cuda" else 0)
     B = a.batch
     tot = {"base": [0.0, 0.0], "cand": [0.0, 0.0]}
     ok_all = True
