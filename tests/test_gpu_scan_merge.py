@@ -78,7 +78,7 @@ def test_bf16(fam):
 @pytest.mark.parametrize("H", [6, 7, 14])
 def test_line_small_and_odd_sizes(H):
     """L % 4 != 0 exercises the scalar paths; H = 7 is an odd-size table the reference also builds."""
-    tab = so.order_table("std", H) if False else np.concatenate([so.std_indices(H, H), np.stack(so.line_indices(H, H))])
+    tab = np.concatenate([so.std_indices(H, H), np.stack(so.line_indices(H, H))])   # order_table() insists on even H
     rs = np.random.RandomState(H)
     x = rs.standard_normal((2, 3, H, H)).astype(np.float32)
     ys = rs.standard_normal((2, 8, 3, H * H)).astype(np.float32)

@@ -209,12 +209,20 @@ def make_custom_pair(name, table_of):
     pixel index of every token (repeats allowed, like the helix lists).  scan: xs[b,k,c,t] = x[b,c].flat[T[k,t]];
     merge: its exact transpose, summed sequentially over k then t (deterministic, no atomics)."""
 
+    plans = {}                       # (H, device) -> (K, device plan): table_of() runs once per map size
+
+    def plan_for(H, device):
+        hit = plans.get((H, device))
+        if hit is None:
+            hit = plans[(H, device)] = _custom_plan(table_of(H), device)
+        return hit
+
     def scan(x):
         B, C, H, W = x.shape
         _check_square(H, W)
         _require_cuda(x)
         x = x.contiguous()
-        K, plan = _custom_plan(table_of(H), x.device)
+        K, plan = plan_for(H, x.device)
         xs = x.new_empty((B, K, C, H * W))
         with torch.cuda.device(x.device), _lib.timed("cross_scan", (1 + K) * x.numel() * x.element_size()):
             _lib.check(_lib.lib.tramba_cross_scan(x.data_ptr(), xs.data_ptr(), plan.data_ptr(), _lib.ORDER_CUSTOM, K,
@@ -226,7 +234,7 @@ def make_custom_pair(name, table_of):
         _require_cuda(ys)
         B, K, D = ys.shape[:3]
         ys = ys.contiguous()
-        K2, plan = _custom_plan(table_of(H), ys.device)
+        K2, plan = plan_for(H, ys.device)
         if K2 != K:
             raise ValueError(f"tramba_b200: order expects K={K2} directions, got {K}")
         y = ys.new_empty((B, D, H * W))
