@@ -96,3 +96,29 @@ def test_emulator_scope_is_restored():
         assert torch.zeros(1).is_cuda
     assert not torch.zeros(1).is_cuda
     assert not hasattr(_lib.lib, "calls")
+
+
+def test_ss2d_module_bf16_marshalling():
+    """bf16 activations with fp32 parameters (what autocast hands the operators on the GPU): dtype codes, the fp32
+    merged output of the fused core, fp32 dB / dC cast back, LayerNorm2d fp32 -> bf16.  CPU autocast stands in for
+    CUDA autocast; the result must stay within bf16 rounding of the fp32 run."""
+    torch.manual_seed(2)
+    m = tramba_b200.SS2D(d_model=32, d_state=1, channel_first=True, k_group=8, scan=tramba_b200.CrossScan_Line,
+                         merge=tramba_b200.CrossMerge_Line)
+    x = torch.randn(2, 32, 24, 24)
+    with installed() as lib:
+        x32 = x.clone().requires_grad_(True)
+        y32 = m(x32)
+        y32.sum().backward()
+        g32 = x32.grad.clone()
+        n32 = len(lib.calls)
+        x16 = x.clone().requires_grad_(True)
+        with torch.autocast("cpu", dtype=torch.bfloat16):
+            y16 = m(x16)
+        y16.float().sum().backward()
+    assert "tramba_ss2d_fused_fwd" in lib.calls[n32:] and "tramba_ss2d_fused_bwd" in lib.calls[n32:]
+    assert y16.dtype == torch.bfloat16 and x16.grad is not None and torch.isfinite(x16.grad).all()
+    rel = (y16.float() - y32).abs().max() / y32.abs().max()
+    assert rel < 5e-2, rel
+    relg = (x16.grad - g32).abs().max() / g32.abs().max()
+    assert relg < 1e-1, relg
