@@ -32,3 +32,12 @@ PY
 timeout 300 python tools/ss2d_bench.py > gpurun_out/ss2d_bench.jsonl 2>&1; echo "ss2d_bench rc=$?"
 timeout 300 python tools/kernel_bench.py --dtype bf16 --fused-only > gpurun_out/kernel_bench_fused_bf16.jsonl 2>&1
 timeout 600 python tools/op_profile.py > gpurun_out/op_profile.txt 2> gpurun_out/op_profile.err; echo "op_profile rc=$?"; head -30 gpurun_out/op_profile.txt
+# ncu of the candidate kernels on the enc0 site (only after the plain run above exited 0): same capture as the
+# product's r01_ncu_f{bwd,fwd}_enc0_* so that instruction counts / stall reasons can be compared line by line
+if grep -q '"all_parity_ok": true' gpurun_out/variant_bf16.jsonl; then
+  for k in bwd fwd; do
+    timeout 600 ncu --set full --import-source on --clock-control none -k regex:ss2d_${k}_cg_kernel -c 1 -f \
+      -o gpurun_out/prof_f${k}_cg python tools/variant_bench.py --only enc0 --reps 1 > gpurun_out/ncu_f${k}_cg.log 2>&1
+    echo "ncu ${k}_cg rc=$?"
+  done
+fi
