@@ -93,6 +93,25 @@ def test_order_errors():
         ops.window_size_for["13"]                        # reference: window_index[str(H)] KeyError
 
 
+def test_scan_merge_argument_checks_cover_the_ablation_orders():
+    """Order / K validation happens before the device check, so it is observable without a GPU."""
+    import torch
+    a = np.zeros(256, np.float32)
+    p = a.ctypes.data
+    plan = np.zeros(4096, np.int32).ctypes.data
+    scan, merge = _lib.lib.tramba_cross_scan, _lib.lib.tramba_cross_merge
+    assert scan(p, p, plan, _lib.ORDER_SPIRAL, 4, 1, 1, 4, 4, _lib.F32, None) == -4      # spiral has K = 8
+    assert merge(p, p, plan, _lib.ORDER_HILBERT, 8, 1, 1, 4, 4, _lib.F32, None) == -4    # hilbert has K = 4
+    assert scan(p, p, plan, _lib.ORDER_AB1 + 1, 4, 1, 1, 4, 4, _lib.F32, None) == -4     # past the last family
+    if not torch.cuda.is_available():
+        assert scan(p, p, plan, _lib.ORDER_SPIRAL, 8, 1, 1, 4, 4, _lib.F32, None) == -6  # valid arguments: no device
+        assert scan(p, p, plan, _lib.ORDER_CUSTOM, 3, 1, 1, 4, 4, _lib.F32, None) == -6  # any K with a caller table
+        assert merge(p, p, plan, _lib.ORDER_DS, 8, 1, 1, 4, 4, _lib.F32, None) == -6
+    # the fused core never accepts them (they run op-by-op)
+    assert _lib.lib.tramba_ss2d_fused_supported(_lib.ORDER_SPIRAL, 8, 64, 24, 24, 1, _lib.BF16, 1) == 0
+    assert _lib.lib.tramba_ss2d_fused_supported(_lib.ORDER_LINE, 8, 64, 24, 24, 1, _lib.BF16, 1) == 1
+
+
 def test_dct_basis_bit_exact(golden_dct):
     for n in (12, 24, 48, 96):
         w = np.empty((n, n), np.float32)
