@@ -172,3 +172,25 @@ def test_sscan_ckpt_elems_plan():
     assert f(4, 4096, 576, 1, _lib.F32) == 4 * 4096 * 2            # TSEG 9: 2 chunks of 288 per row
     assert f(2, 8192, 144, 1, _lib.F32) == 2 * 8192 // 2           # two 144-token rows per 288 chunk
     assert f(1, 8, 50, 3, _lib.F32) > 0                            # generic path
+
+
+def test_c_consumer_builds_and_runs(tmp_path):
+    """examples/abi_demo.c: the header is valid (pedantic) C99 and a plain C program links the library and uses the
+    host-side entry points -- no torch, no Python, no CUDA headers on the consumer side."""
+    import shutil
+    import torch
+    if shutil.which("gcc") is None:
+        pytest.skip("no gcc")
+    exe = str(tmp_path / "abi_demo")
+    libdir = os.path.dirname(_lib.LIB_PATH)
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Werror", "-pedantic", "-I" + os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "examples", "abi_demo.c"), "-L" + libdir, "-ltramba_b200",
+                           "-Wl,-rpath," + libdir, "-o", exe])
+    env = dict(os.environ)
+    if not torch.cuda.is_available():
+        env["TRAMBA_DEMO_NO_DEVICE"] = "1"
+    out = subprocess.run([exe], capture_output=True, text=True, env=env)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert "window K=4 first tokens 0 1 24 575" in out.stdout and "helix K=8 plan elems 13832" in out.stdout
+    if not torch.cuda.is_available():
+        assert "cross_scan without a device -> -6" in out.stdout
