@@ -194,3 +194,22 @@ def test_c_consumer_builds_and_runs(tmp_path):
     assert "window K=4 first tokens 0 1 24 575" in out.stdout and "helix K=8 plan elems 13832" in out.stdout
     if not torch.cuda.is_available():
         assert "cross_scan without a device -> -6" in out.stdout
+
+
+def test_checkpoint_surface_linear2d_and_ss2d_roundtrip():
+    """SURVEY 5 (checkpoint / resume): reference checkpoints must load into the drop-ins.  Linear2d accepts both the
+    nn.Linear-shaped (out, in) weight and a conv-shaped (out, in, 1, 1) one (Models/modules.py:15-19); an SS2D
+    state_dict round-trips with strict=True and identical values."""
+    import torch
+    lin = tramba_b200.Linear2d(6, 4, bias=True)
+    w = torch.randn(4, 6)
+    lin.load_state_dict({"weight": w.view(4, 6, 1, 1), "bias": torch.zeros(4)}, strict=True)
+    assert torch.equal(lin.weight, w) and lin.weight.shape == (4, 6)
+    lin.load_state_dict({"weight": 2 * w, "bias": torch.ones(4)}, strict=True)
+    assert torch.equal(lin.weight, 2 * w)
+    a = tramba_b200.SS2D(d_model=16, d_state=1, channel_first=True, k_group=4)
+    b = tramba_b200.SS2D(d_model=16, d_state=1, channel_first=True, k_group=4)
+    missing = b.load_state_dict(a.state_dict(), strict=True)
+    assert not missing.missing_keys and not missing.unexpected_keys
+    for (k, va), (_, vb) in zip(a.state_dict().items(), b.state_dict().items()):
+        assert torch.equal(va, vb), k

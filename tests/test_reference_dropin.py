@@ -121,3 +121,26 @@ def test_level3_modules_fused_core(ref):
         ss2d = [m for m in model.modules() if isinstance(m, tb.SS2D)]
         assert len(ss2d) == 33
         assert all(m.scan.__module__ == "tramba_b200.ops" and m.merge.__module__ == "tramba_b200.ops" for m in ss2d)
+
+
+def test_reference_checkpoint_loads_into_the_harness_and_the_dropin_modules(ref):
+    """A state_dict saved from the REAL reference model (train.py:251-263) loads with strict=True into (a) the
+    benchmark harness and (b) the reference model built on tb.SS2D / tb.DCT2D, value for value."""
+    from tramba_b200.model import build_model
+    dims = int(GOLD["dims"])
+    with contextlib.redirect_stdout(io.StringIO()):
+        src = ref["Trambav6"].bulid_model(deep_supervision=True, use_pretrain=False, img_size=384, dims=dims)
+    det_fill(src)
+    sd = src.state_dict()
+    harness = build_model(img_size=384, dims=dims)
+    res = harness.load_state_dict(sd, strict=True)
+    assert not res.missing_keys and not res.unexpected_keys
+    vm, fm = ref["vm"], ref["fm"]
+    with patched([(vm, "SS2D", tb.SS2D), (fm, "SS2D", tb.SS2D), (fm, "DCT2D", tb.DCT2D)]):
+        with contextlib.redirect_stdout(io.StringIO()):
+            dropin = ref["Trambav6"].bulid_model(deep_supervision=True, use_pretrain=False, img_size=384, dims=dims)
+    res = dropin.load_state_dict(sd, strict=True)
+    assert not res.missing_keys and not res.unexpected_keys
+    for k, v in sd.items():
+        assert torch.equal(harness.state_dict()[k].view_as(v), v), k
+        assert torch.equal(dropin.state_dict()[k].view_as(v), v), k
