@@ -107,6 +107,9 @@ def launch_count():
 # times after its own synchronize.  Off (None) by default: zero overhead on the product path.
 # ---------------------------------------------------------------------------------------
 prof = None
+# TRAMBA_NVTX=1: every C-ABI compute call is wrapped in an NVTX range named after its kind ("ss2d_fused_bwd", ...)
+# so that `ncu --nvtx --nvtx-include "ss2d_fused_bwd/"` (or nsys) can select call sites by stage.  Off by default.
+NVTX = os.environ.get("TRAMBA_NVTX", "") == "1"
 
 
 class timed:
@@ -116,6 +119,9 @@ class timed:
         self.kind, self.nbytes, self.ev = kind, nbytes, None
 
     def __enter__(self):
+        if NVTX:
+            import torch
+            torch.cuda.nvtx.range_push(self.kind)
         if prof is not None:
             import torch
             self.ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
@@ -126,4 +132,7 @@ class timed:
         if self.ev is not None:
             self.ev[1].record()
             prof.append((self.kind, self.nbytes, self.ev[0], self.ev[1]))
+        if NVTX:
+            import torch
+            torch.cuda.nvtx.range_pop()
         return False
