@@ -70,16 +70,26 @@ def _load():
     spec.loader.exec_module(_build)
     # one builder at a time: under torchrun every rank imports the package at the same moment
     import fcntl
-    with open(os.path.join(_HERE, ".build.lock"), "w") as lock:
-        fcntl.flock(lock, fcntl.LOCK_EX)
-        try:
-            if VARIANT == "next":
-                if not os.path.exists(LIB_PATH):
-                    _build.build(next_variant=True)
-            elif not os.path.exists(LIB_PATH) or (_build.sources_newer_than_lib() and os.path.exists(_build.NVCC)):
-                _build.build()  # raises if nvcc is unavailable or fails: no silent fallback
-        finally:
+
+    def ensure_built():
+        if VARIANT == "next":
+            if not os.path.exists(LIB_PATH):
+                _build.build(next_variant=True)
+        elif not os.path.exists(LIB_PATH) or (_build.sources_newer_than_lib() and os.path.exists(_build.NVCC)):
+            _build.build()  # raises if nvcc is unavailable or fails: no silent fallback
+
+    try:
+        lock = open(os.path.join(_HERE, ".build.lock"), "w")
+    except OSError:          # read-only tree: nothing to serialise, the library must already be there
+        lock = None
+    try:
+        if lock is not None:
+            fcntl.flock(lock, fcntl.LOCK_EX)
+        ensure_built()
+    finally:
+        if lock is not None:
             fcntl.flock(lock, fcntl.LOCK_UN)
+            lock.close()
     lib = ctypes.CDLL(LIB_PATH)
     for name, (res, args) in SIGNATURES.items():
         fn = getattr(lib, name)  # AttributeError if the library lacks a declared symbol
