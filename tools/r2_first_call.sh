@@ -44,10 +44,10 @@ fi
 # compute-sanitizer (race detection) on the small fused / scan / LayerNorm / dwconv cases: memcheck for
 # out-of-bounds, racecheck for shared-memory hazards between the pipeline stages of the fused kernels
 for tool in memcheck racecheck; do
-  timeout 900 compute-sanitizer --tool $tool --error-exitcode 9 python -m pytest tests/test_gpu_fused.py -q -m gpu -x \
+  timeout 300 compute-sanitizer --tool $tool --error-exitcode 9 python -m pytest tests/test_gpu_fused.py -q -m gpu -x \
     -k "12 or 24" > gpurun_out/sanitizer_${tool}_fused.log 2>&1
   echo "compute-sanitizer $tool fused rc=$? : $(grep -E 'ERROR SUMMARY|RACECHECK SUMMARY' gpurun_out/sanitizer_${tool}_fused.log | tail -1)"
 done
-timeout 900 compute-sanitizer --tool memcheck --error-exitcode 9 python __graft_entry__.py --smoke \
+timeout 300 compute-sanitizer --tool memcheck --error-exitcode 9 python __graft_entry__.py --smoke \
   > gpurun_out/sanitizer_memcheck_smoke.log 2>&1
 echo "compute-sanitizer memcheck smoke rc=$? : $(grep 'ERROR SUMMARY' gpurun_out/sanitizer_memcheck_smoke.log | tail -1)"
