@@ -1,0 +1,156 @@
+"""The fused SS2D kernels executed on the CPU (tools/cpu_sim: the CUDA sources compiled as host code, every CUDA
+thread a cooperative fiber, inline PTX replaced by functional equivalents) against the float64 oracle composition
+CrossScan -> selective scan -> CrossMerge (tests/_fused_oracle.py).
+
+Covers what can be known without a GPU: index arithmetic, work decomposition over CTAs / rounds / items, the
+three-level scan and its carries, barrier and mbarrier protocols (a mismatch is reported as a deadlock), and the
+numerics of the recurrence -- for the product kernels (GPU-verified in tests/test_gpu_fused.py; here they validate
+the simulator) and for the compile-time-geometry candidates under csrc/next/ (not yet run on a GPU; here they
+must reproduce the product kernels bit for bit).  Asynchrony, memory ordering and performance are out of its reach."""
+import ctypes
+import importlib.util
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import ROOT
+from tramba_b200 import _lib
+from _fused_oracle import fused_core_oracle, param_of
+
+ORDER = {"std": (_lib.ORDER_STD, 4), "dilation": (_lib.ORDER_DILATION, 4), "window": (_lib.ORDER_WINDOW, 4),
+         "line": (_lib.ORDER_LINE, 8)}
+PTRS = ["x", "dts", "Bs", "Cs", "A", "Dp", "bias", "idx", "y", "dy", "du", "ddts", "dBs", "dCs", "dA", "dD", "dbias"]
+
+
+class FusedArgs(ctypes.Structure):            # csrc/ss2d_fused.cuh: struct FusedArgs
+    _fields_ = [(n, ctypes.c_void_p) for n in PTRS] + [(n, ctypes.c_int) for n in ("B", "K", "D", "L", "TP", "PP",
+                                                                                  "rounds", "softplus")] + \
+               [("dup_mask", ctypes.c_uint32), ("xb", ctypes.c_int)]
+
+
+@pytest.fixture(scope="module")
+def sim():
+    spec = importlib.util.spec_from_file_location("build_sim", os.path.join(ROOT, "tools", "cpu_sim", "build_sim.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    lib = ctypes.CDLL(mod.build())
+    for name in ("sim_fwd", "sim_bwd", "sim_fwd_cg", "sim_bwd_cg"):
+        fn = getattr(lib, name)
+        fn.restype, fn.argtypes = ctypes.c_char_p, [ctypes.POINTER(FusedArgs), ctypes.c_int, ctypes.c_int]
+    return lib
+
+
+def _dev(t, bf16):
+    """torch tensor -> contiguous numpy buffer as the kernels see it (bf16 as raw uint16)."""
+    t = t.contiguous()
+    return t.bfloat16().view(torch.int16).numpy().copy() if bf16 else t.float().numpy().copy()
+
+
+def _host(a, bf16):
+    return torch.from_numpy(a.view(np.int16)).view(torch.bfloat16).float() if bf16 else torch.from_numpy(a)
+
+
+def _run(sim, fam, H, D, B, bf16, grid, seed=0):
+    order, K = ORDER[fam]
+    L = H * H
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(B, D, H, H, generator=g)
+    dts = torch.randn(B, K, D, L, generator=g)
+    Bs, Cs = torch.randn(B, K, L, generator=g), torch.randn(B, K, L, generator=g)
+    A = -(0.2 + torch.rand(K * D, generator=g))
+    Ds = 1 + 0.1 * torch.randn(K * D, generator=g)
+    bias = torch.randn(K * D, generator=g) - 2.0
+    dy = torch.randn(B, D, L, generator=g)
+    if bf16:      # round once so the oracle and the kernels start from identical values
+        x, dts, Bs, Cs = [t.bfloat16().float() for t in (x, dts, Bs, Cs)]
+    t16 = np.empty((K, L), dtype=np.uint16)
+    _lib.check(_lib.lib.tramba_order_table16_skewed(order, H, H, param_of(fam, H), t16.ctypes.data))
+    code = _lib.BF16 if bf16 else _lib.F32
+    ins = dict(x=_dev(x, bf16), dts=_dev(dts, bf16), Bs=_dev(Bs, bf16), Cs=_dev(Cs, bf16), A=_dev(A, False),
+               Dp=_dev(Ds, False), bias=_dev(bias, False), idx=t16, dy=_dev(dy, False))
+    TP = L // 18
+    res = {}
+    for tag in ("", "_cg"):
+        out = dict(y=np.full((B, D, L), np.nan, np.float32),
+                   du=np.zeros((B, K, D, L), np.uint16 if bf16 else np.float32),
+                   ddts=np.zeros((B, K, D, L), np.uint16 if bf16 else np.float32),
+                   dBs=np.zeros((B, K, L), np.float32), dCs=np.zeros((B, K, L), np.float32),
+                   dA=np.full((B, K * D), np.nan, np.float32), dD=np.full((B, K * D), np.nan, np.float32),
+                   dbias=np.full((B, K * D), np.nan, np.float32))
+        a = FusedArgs(B=B, K=K, D=D, L=L, TP=TP, PP=512 // TP, rounds=B * D // (512 // TP), softplus=1,
+                      dup_mask=0xF0 if fam == "line" else 0, xb=0,
+                      **{k: v.ctypes.data for k, v in {**ins, **out}.items()})
+        for fn in ("sim_fwd", "sim_bwd"):
+            err = getattr(sim, fn + tag)(ctypes.byref(a), code, grid)
+            assert err is None, (fn + tag, err.decode())
+        res[tag] = out
+    ref_y, ref_g = fused_core_oracle(fam, H, [x, dts, Bs, Cs, A, Ds, bias], dy)
+    return res, ref_y, ref_g, bf16
+
+
+def _close(a, b, rtol, what):
+    a, b = np.asarray(a, np.float64), b.detach().double().numpy()
+    tol = rtol * np.abs(b) + rtol * np.abs(b).max()
+    bad = np.abs(a - b) > tol
+    assert not bad.any(), f"{what}: {bad.sum()} of {bad.size} off, max err {np.abs(a - b).max():.3e}"
+
+
+CASES = [  # family, H, D, B, bf16, grid
+    ("std", 12, 64, 2, False, 3), ("std", 12, 128, 1, True, 2), ("line", 12, 64, 1, False, 3),
+    ("window", 24, 32, 2, False, 3), ("dilation", 24, 16, 1, True, 1), ("line", 24, 16, 1, True, 2),
+    ("std", 48, 8, 1, False, 2), ("window", 48, 4, 1, True, 1), ("std", 96, 2, 1, True, 2),
+    ("dilation", 96, 8, 1, True, 3),   # 96 x 96, one plane per round, R = 8 rounds per backward item, several items per CTA
+    ("line", 96, 2, 1, True, 2),       # helix duplicates (shared-memory atomics) with 512 threads per plane
+]
+
+
+@pytest.mark.parametrize("fam,H,D,B,bf16,grid", CASES)
+def test_fused_kernels_on_the_cpu_simulator(sim, fam, H, D, B, bf16, grid):
+    res, ref_y, ref_g, bf16 = _run(sim, fam, H, D, B, bf16, grid)
+    rtol = 1e-2 if bf16 else 1e-3
+    for tag, out in res.items():
+        K = out["du"].shape[1]
+        _close(out["y"], ref_y, rtol, f"y{tag}")
+        # du is the gradient w.r.t. xs (scan order); the oracle differentiates w.r.t. the image: fold du back
+        from oracle import scan_orders as so
+        tab = so.order_table(fam, H, param_of(fam, H))
+        dx = so.cross_merge(_host(out["du"], bf16).double().numpy(), tab, "custom").reshape(ref_g[0].shape)
+        _close(dx, ref_g[0], 2 * rtol, f"dx{tag}")
+        _close(_host(out["ddts"], bf16).numpy(), ref_g[1], rtol, f"ddelta{tag}")
+        _close(out["dBs"], ref_g[2], rtol, f"dB{tag}")
+        _close(out["dCs"], ref_g[3], rtol, f"dC{tag}")
+        _close(out["dA"].sum(0), ref_g[4], rtol, f"dA{tag}")
+        _close(out["dD"].sum(0), ref_g[5], rtol, f"dD{tag}")
+        _close(out["dbias"].sum(0), ref_g[6], rtol, f"dbias{tag}")
+    # the candidates perform the same floating-point operations in the same order as the product kernels
+    for k in ("y", "du", "ddts", "dA", "dD", "dbias"):
+        assert np.array_equal(res[""][k], res["_cg"][k]), k
+    for k in ("dBs", "dCs"):        # accumulated across CTAs: the simulator runs CTAs in order, so still identical
+        assert np.array_equal(res[""][k], res["_cg"][k]), k
+
+
+def test_simulator_runs_an_empty_launch(sim):
+    """Zero rounds: every thread returns before touching a barrier; the scheduler must terminate cleanly."""
+    a = FusedArgs(B=1, K=4, D=64, L=144, TP=8, PP=64, rounds=0, softplus=1, dup_mask=0, xb=0)
+    assert sim.sim_fwd(ctypes.byref(a), _lib.F32, 1) is None
+
+
+def test_simulator_selftest(sim):
+    """The runtime itself: shuffles / segmented scans give the right values, a thread that skips a barrier and an
+    mbarrier whose transaction never completes are both REPORTED (as a deadlock) instead of hanging or passing."""
+    cp, fp = ctypes.c_char_p, ctypes.c_void_p
+    sim.sim_selftest_shuffle.restype, sim.sim_selftest_shuffle.argtypes = cp, [fp, fp, ctypes.c_int]
+    sim.sim_selftest_mismatch.restype, sim.sim_selftest_mismatch.argtypes = cp, []
+    sim.sim_selftest_mbar.restype, sim.sim_selftest_mbar.argtypes = cp, [ctypes.c_int, fp]
+    x = np.arange(64, dtype=np.float32) + 1
+    out = np.zeros(2 * 64 + 1, np.float32)
+    assert sim.sim_selftest_shuffle(x.ctypes.data, out.ctypes.data, 3) is None
+    assert np.array_equal(out[:32], np.full(32, x[:32].sum())) and np.array_equal(out[32:64], np.full(32, x[32:].sum()))
+    want = np.concatenate([np.cumsum(x[i:i + 16]) for i in range(0, 64, 16)])
+    assert np.array_equal(out[64:128], want) and out[128] == x[32:].sum() + 2       # thread 63 holds warp 1's sum; the last CTA is blockIdx 2
+    assert b"deadlock" in sim.sim_selftest_mismatch()
+    o = np.zeros(32, np.float32)
+    assert sim.sim_selftest_mbar(1, o.ctypes.data) is None and np.array_equal(o[:4], [1, 2, 3, 4])
+    assert b"deadlock" in sim.sim_selftest_mbar(0, o.ctypes.data)

@@ -1,0 +1,191 @@
+#!/usr/bin/env python
+"""Builds tools/cpu_sim/_gen/libtramba_sim.so: the fused SS2D kernels (product: csrc/ss2d_fused_{fwd,bwd}.cu,
+candidates: csrc/next/*_cg.cu) compiled as HOST code against tools/cpu_sim/sim_common.h (see there).
+
+The kernel sources are copied, not edited in place; the only textual changes are (1) inline PTX -> the simulator's
+functions, (2) `extern __shared__ ... smem[]` -> the simulator's per-CTA buffer, (3) the CUDA launchers at the end
+of each file are cut off and replaced by a small `extern "C"` driver.  TEST INFRASTRUCTURE (g++ only, no GPU).
+
+    python tools/cpu_sim/build_sim.py        # -> path of the library
+"""
+import os
+import re
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+CSRC = os.path.join(ROOT, "tramba_b200", "csrc")
+GEN = os.path.join(HERE, "_gen")
+LIB = os.path.join(GEN, "libtramba_sim.so")
+
+
+def sub1(s, old, new):
+    assert s.count(old) == 1, (s.count(old), old[:80])
+    return s.replace(old, new)
+
+
+def gen_header():
+    s = open(os.path.join(CSRC, "ss2d_fused.cuh")).read()
+    s = sub1(s, '#include "common.cuh"', '#include "sim_common.h"')
+    s = sub1(s, 'asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(dst_smem)), "l"(src) : "memory");',
+             "std::memcpy(dst_smem, src, 4);")
+    s = sub1(s, 'asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(dst_smem)), "l"(src) : "memory");',
+             "std::memcpy(dst_smem, src, 8);")
+    s = sub1(s, 'asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");',
+             "sim::mbar_arrive(bar);")
+    assert "asm" not in s
+    open(os.path.join(GEN, "ss2d_fused.cuh"), "w").write(s)
+
+
+RED = re.compile(r'asm volatile\("red\.global\.add\.v2\.f32 \[%0\], \{%1, %2\};" ::"l"\((.*?)\), "f"\((.*?)\), '
+                 r'"f"\((.*?)\)\s*: "memory"\);', re.S)
+
+TAIL_FWD = r'''
+template <typename in_t>
+static const char* run(const FusedArgs& a, int grid) {
+    FusedArgs b = a;
+    b.xb = FwdLayout(a.L, sizeof(in_t), 2).total <= 227 * 1024 ? 2 : 1;
+    const size_t smem = FwdLayout(a.L, sizeof(in_t), b.xb).total;
+    if (smem > 227 * 1024) return "shared memory does not fit";
+    if (grid > a.rounds) grid = a.rounds;
+    return sim::launch(grid, NT, smem, [&] { ss2d_fwd_kernel<in_t, true>(b); });
+}
+}  // namespace
+extern "C" const char* sim_fwd(const FusedArgs* a, int in_dtype, int grid) {
+    return in_dtype == TRAMBA_F32 ? run<float>(*a, grid) : run<__nv_bfloat16>(*a, grid);
+}
+}  // namespace tramba
+'''
+
+TAIL_FWD_CG = r'''
+template <typename in_t, int TPC, int XB>
+static const char* run1(const FusedArgs& a, int grid) {
+    FusedArgs b = a;
+    b.xb = XB;
+    const size_t smem = FwdLayout(a.L, sizeof(in_t), XB).total;
+    if (grid > a.rounds) grid = a.rounds;
+    return sim::launch(grid, NT, smem, [&] { ss2d_fwd_cg_kernel<in_t, true, TPC, XB>(b); });
+}
+template <typename in_t, int XB>
+static const char* run_tp(const FusedArgs& a, int grid) {
+    switch (a.TP) {
+        case 8: return run1<in_t, 8, XB>(a, grid);
+        case 32: return run1<in_t, 32, XB>(a, grid);
+        case 128: return run1<in_t, 128, XB>(a, grid);
+        case 512: return run1<in_t, 512, XB>(a, grid);
+        default: return "threads per plane not specialised";
+    }
+}
+template <typename in_t>
+static const char* run(const FusedArgs& a, int grid) {
+    const int xb = FwdLayout(a.L, sizeof(in_t), 2).total <= 227 * 1024 ? 2 : 1;
+    if (FwdLayout(a.L, sizeof(in_t), xb).total > 227 * 1024) return "shared memory does not fit";
+    return xb == 2 ? run_tp<in_t, 2>(a, grid) : run_tp<in_t, 1>(a, grid);
+}
+}  // namespace
+extern "C" const char* sim_fwd_cg(const FusedArgs* a, int in_dtype, int grid) {
+    return in_dtype == TRAMBA_F32 ? run<float>(*a, grid) : run<__nv_bfloat16>(*a, grid);
+}
+}  // namespace tramba
+'''
+
+PICK = r'''
+static int pick_rounds(const FusedArgs& a) {   // as in ss2d_fused_bwd.cu
+    int R = 1;
+    while (R * a.PP < 8 && a.D % (2 * R * a.PP) == 0) R *= 2;
+    return R;
+}
+'''
+
+TAIL_BWD = PICK + r'''
+template <typename in_t>
+static const char* run(const FusedArgs& a, int grid) {
+    FusedArgs b = a;
+    b.xb = BwdLayout(a.L, sizeof(in_t), 2).total <= 227 * 1024 ? 2 : 1;
+    const size_t smem = BwdLayout(a.L, sizeof(in_t), b.xb).total;
+    if (smem > 227 * 1024) return "shared memory does not fit";
+    const int R = pick_rounds(a);
+    const int items = a.B * a.K * (a.D / (R * a.PP));
+    if (grid > items) grid = items;
+    return sim::launch(grid, NT, smem, [&] { ss2d_bwd_kernel<in_t, true>(b, R); });
+}
+}  // namespace
+extern "C" const char* sim_bwd(const FusedArgs* a, int in_dtype, int grid) {
+    return in_dtype == TRAMBA_F32 ? run<float>(*a, grid) : run<__nv_bfloat16>(*a, grid);
+}
+}  // namespace tramba
+'''
+
+TAIL_BWD_CG = PICK + r'''
+template <typename in_t, int TPC, int XB>
+static const char* run1(const FusedArgs& a, int grid) {
+    FusedArgs b = a;
+    b.xb = XB;
+    const size_t smem = BwdLayout(a.L, sizeof(in_t), XB).total;
+    if (smem > 227 * 1024) return "shared memory does not fit";
+    const int R = pick_rounds(a);
+    const int items = a.B * a.K * (a.D / (R * a.PP));
+    if (grid > items) grid = items;
+    return sim::launch(grid, NT, smem, [&] { ss2d_bwd_cg_kernel<in_t, true, TPC, XB>(b, R); });
+}
+template <typename in_t, int XB>
+static const char* run(const FusedArgs& a, int grid) {
+    switch (a.TP) {
+        case 8: return run1<in_t, 8, XB>(a, grid);
+        case 32: return run1<in_t, 32, XB>(a, grid);
+        case 128: return run1<in_t, 128, XB>(a, grid);
+        case 512: return run1<in_t, 512, XB>(a, grid);
+        default: return "threads per plane not specialised";
+    }
+}
+}  // namespace
+extern "C" const char* sim_bwd_cg(const FusedArgs* a, int in_dtype, int grid) {   // staging depth as launch_ss2d_fused_bwd_cg
+    return in_dtype == TRAMBA_F32 ? run<float, 1>(*a, grid) : run<__nv_bfloat16, 2>(*a, grid);
+}
+}  // namespace tramba
+'''
+
+KERNELS = [  # source, cut marker (everything from it on is replaced by the tail), tail, anonymous namespace still open?
+    ("ss2d_fused_fwd.cu", "}  // namespace\n\nsize_t ss2d_fused_fwd_smem", TAIL_FWD),
+    ("ss2d_fused_bwd.cu", "}  // namespace\n\nsize_t ss2d_fused_bwd_smem", TAIL_BWD),
+    (os.path.join("next", "ss2d_fused_fwd_cg.cu"),
+     "template <typename in_t, bool SOFTPLUS, int TPC, int XB>\nstatic cudaError_t launch_cg", TAIL_FWD_CG),
+    (os.path.join("next", "ss2d_fused_bwd_cg.cu"), "// Channels per item: enough rounds that the per-item", TAIL_BWD_CG),
+]
+
+
+def gen_kernel(rel, marker, tail):
+    s = open(os.path.join(CSRC, rel)).read()
+    i = s.index(marker)
+    s = s[:i] + tail
+    s = s.replace('#include "../ss2d_fused.cuh"', '#include "ss2d_fused.cuh"')
+    s = sub1(s, "extern __shared__ __align__(128) unsigned char smem[];", "unsigned char* smem = sim::smem();")
+    s = RED.sub(r"sim::red_add_v2(\1, \2, \3);", s)
+    assert "asm" not in s.replace("__nv_bfloat16", ""), rel
+    out = os.path.join(GEN, os.path.basename(rel).replace(".cu", "_sim.cpp"))
+    open(out, "w").write(s)
+    return out
+
+
+def build(force=False):
+    os.makedirs(GEN, exist_ok=True)
+    deps = [os.path.join(CSRC, k[0]) for k in KERNELS] + [os.path.join(CSRC, "ss2d_fused.cuh"),
+                                                          os.path.join(HERE, "sim_common.h"), os.path.join(HERE, "selftest.cpp"),
+                                                          os.path.abspath(__file__)]
+    if not force and os.path.exists(LIB) and all(os.path.getmtime(d) <= os.path.getmtime(LIB) for d in deps):
+        return LIB
+    gen_header()
+    srcs = [gen_kernel(*k) for k in KERNELS]
+    cmd = ["g++", "-std=c++17", "-O1", "-fPIC", "-shared", "-w", "-I" + HERE, "-I" + GEN,
+           "-I" + os.path.join(ROOT, "include"), "-I/usr/local/cuda/include"] + srcs + [
+               os.path.join(HERE, "selftest.cpp"), "-o", LIB]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        sys.stderr.write(res.stdout + res.stderr)
+        raise RuntimeError("cpu_sim build failed")
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv))

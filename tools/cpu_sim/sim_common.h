@@ -1,0 +1,263 @@
+// CPU functional simulator for the fused SS2D kernels -- TEST INFRASTRUCTURE, host only (g++, no nvcc, no GPU).
+//
+// tools/cpu_sim/build_sim.py copies the kernel sources (csrc/ss2d_fused_{fwd,bwd}.cu, csrc/next/*_cg.cu) next to
+// this header with the inline PTX swapped for the functions below and compiles them as ordinary C++: this file
+// stands in for csrc/common.cuh.  Execution model: one CTA at a time, every CUDA thread a cooperative fiber
+// (ucontext) that yields only inside __syncthreads(), warp shuffles and mbarrier waits, so runs are deterministic
+// and data-race free by construction.  Asynchronous copies (cp.async, TMA bulk copies) complete at issue.
+//
+// What it checks: the kernels' index arithmetic, work decomposition, scan / carry logic, barrier and mbarrier
+// protocols (a barrier mismatch shows up as a reported deadlock) and numerics against the oracle.
+// What it cannot check: anything that depends on copies being asynchronous (reading a buffer before its barrier,
+// overwriting a bulk-store source early), memory-model ordering, bank conflicts, performance.
+#pragma once
+#include <cuda_bf16.h>
+#include <driver_types.h>
+#include <stdint.h>
+#include <ucontext.h>
+
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <functional>
+#include <unordered_map>
+#include <vector>
+
+#include "tramba_b200.h"
+
+#define __launch_bounds__(...)
+
+namespace sim {
+
+struct Idx3 {
+    unsigned x, y, z;
+};
+struct Mbar {
+    uint32_t count = 0, pending = 0, phase = 0;
+    long long tx = 0;
+};
+struct Warp {
+    uint32_t slot[32];
+    int count = 0, gen = 0;
+};
+struct Cta {
+    int nthreads = 0, bx = 0, gdim = 0;
+    unsigned char* smem = nullptr;
+    ucontext_t sched;
+    std::vector<ucontext_t> ctx;
+    std::vector<char> done;
+    int cur = 0;
+    int bar_count = 0, bar_gen = 0;
+    std::vector<Warp> warps;
+    std::unordered_map<const void*, Mbar> mbars;
+    long long progress = 0;
+    const char* error = nullptr;
+};
+inline Cta* g = nullptr;
+inline std::function<void()>* g_body = nullptr;
+
+inline Idx3 tidx() { return Idx3{static_cast<unsigned>(g->cur), 0, 0}; }
+inline Idx3 bidx() { return Idx3{static_cast<unsigned>(g->bx), 0, 0}; }
+inline Idx3 gdim() { return Idx3{static_cast<unsigned>(g->gdim), 1, 1}; }
+inline Idx3 bdim() { return Idx3{static_cast<unsigned>(g->nthreads), 1, 1}; }
+inline unsigned char* smem() { return g->smem; }
+
+inline void yield() { swapcontext(&g->ctx[g->cur], &g->sched); }
+
+inline void syncthreads() {
+    const int gen = g->bar_gen;
+    if (++g->bar_count == g->nthreads) {
+        g->bar_count = 0, ++g->bar_gen, ++g->progress;
+    } else {
+        while (g->bar_gen == gen) yield();
+    }
+}
+inline void warp_barrier() {
+    Warp& w = g->warps[g->cur >> 5];
+    const int gen = w.gen;
+    if (++w.count == 32) {
+        w.count = 0, ++w.gen, ++g->progress;
+    } else {
+        while (w.gen == gen) yield();
+    }
+}
+// every lane of the warp publishes v, then reads lane `src` (src < 0: keeps its own value)
+inline uint32_t shfl(uint32_t v, int src) {
+    Warp& w = g->warps[g->cur >> 5];
+    w.slot[g->cur & 31] = v;
+    warp_barrier();
+    const uint32_t r = src >= 0 ? w.slot[src] : v;
+    warp_barrier();
+    return r;
+}
+inline uint32_t f2u(float f) {
+    uint32_t u;
+    std::memcpy(&u, &f, 4);
+    return u;
+}
+inline float u2f(uint32_t u) {
+    float f;
+    std::memcpy(&f, &u, 4);
+    return f;
+}
+
+// ---- mbarrier (phase completes when the pending arrivals and the pending transaction bytes are both zero)
+inline void mbar_check(Mbar& b) {
+    if (b.pending == 0 && b.tx == 0) b.phase ^= 1u, b.pending = b.count, ++g->progress;
+}
+inline void mbar_arrive(const void* bar) {
+    Mbar& b = g->mbars[bar];
+    if (b.pending == 0) g->error = "mbarrier: more arrivals than the barrier's count in one phase";
+    else --b.pending;
+    mbar_check(b);
+}
+inline void mbar_complete_tx(const void* bar, long long bytes) {
+    Mbar& b = g->mbars[bar];
+    b.tx -= bytes;
+    mbar_check(b);
+}
+inline void red_add_v2(float* p, float a, float b) { p[0] += a, p[1] += b; }
+
+// Runs `body` as grid x nthreads CUDA threads, CTA after CTA.  Returns nullptr or an error string.
+inline const char* launch(int grid, int nthreads, size_t smem_bytes, std::function<void()> body) {
+    static std::vector<char*> stacks;
+    const size_t kStack = 256 * 1024;
+    while (static_cast<int>(stacks.size()) < nthreads) stacks.push_back(static_cast<char*>(std::malloc(kStack)));
+    void* raw = nullptr;
+    if (posix_memalign(&raw, 1024, smem_bytes + 1024) != 0) return "out of memory";
+    const char* err = nullptr;
+    g_body = &body;
+    for (int bx = 0; bx < grid && !err; ++bx) {
+        Cta cta;
+        cta.nthreads = nthreads, cta.bx = bx, cta.gdim = grid;
+        cta.smem = static_cast<unsigned char*>(raw);
+        std::memset(cta.smem, 0xCD, smem_bytes);   // poison: uninitialised shared memory must not go unnoticed
+        cta.ctx.resize(nthreads), cta.done.assign(nthreads, 0), cta.warps.resize((nthreads + 31) / 32);
+        g = &cta;
+        for (int t = 0; t < nthreads; ++t) {
+            getcontext(&cta.ctx[t]);
+            cta.ctx[t].uc_stack.ss_sp = stacks[t];
+            cta.ctx[t].uc_stack.ss_size = kStack;
+            cta.ctx[t].uc_link = &cta.sched;
+            makecontext(&cta.ctx[t], reinterpret_cast<void (*)()>(+[]() {
+                            (*g_body)();
+                            g->done[g->cur] = 1;
+                            ++g->progress;
+                        }),
+                        0);
+        }
+        int alive = nthreads;
+        while (alive > 0 && !cta.error) {
+            const long long before = cta.progress;
+            alive = 0;
+            for (int t = 0; t < nthreads; ++t) {
+                if (cta.done[t]) continue;
+                cta.cur = t;
+                swapcontext(&cta.sched, &cta.ctx[t]);
+                if (!cta.done[t]) ++alive;
+            }
+            if (alive > 0 && cta.progress == before) cta.error = "deadlock: every live thread is blocked";
+        }
+        err = cta.error;
+        g = nullptr;
+    }
+    std::free(raw);
+    return err;
+}
+
+}  // namespace sim
+
+// ---------------------------------------------------------------------------------------------- CUDA surface
+#define threadIdx (sim::tidx())
+#define blockIdx (sim::bidx())
+#define gridDim (sim::gdim())
+#define blockDim (sim::bdim())
+inline void __syncthreads() { sim::syncthreads(); }
+inline float __shfl_up_sync(unsigned, float v, int delta, int width = 32) {
+    const int lane = sim::g->cur & 31, sl = lane % width;
+    return sim::u2f(sim::shfl(sim::f2u(v), sl >= delta ? lane - delta : -1));
+}
+inline float __shfl_down_sync(unsigned, float v, int delta, int width = 32) {
+    const int lane = sim::g->cur & 31, sl = lane % width;
+    return sim::u2f(sim::shfl(sim::f2u(v), sl + delta < width ? lane + delta : -1));
+}
+inline float __shfl_xor_sync(unsigned, float v, int mask, int width = 32) {
+    const int lane = sim::g->cur & 31, src = lane ^ mask;
+    return sim::u2f(sim::shfl(sim::f2u(v), (src / width) == (lane / width) ? src : -1));
+}
+template <typename T>
+inline T __ldg(const T* p) {
+    return *p;
+}
+inline float __uint_as_float(uint32_t u) { return sim::u2f(u); }
+inline uint32_t __float_as_uint(float f) { return sim::f2u(f); }
+inline float atomicAdd(float* p, float v) {
+    const float old = *p;
+    *p = old + v;
+    return old;
+}
+
+namespace tramba {
+
+constexpr float kLog2e = 1.4426950408889634f;
+constexpr float kLn2 = 0.6931471805599453f;
+
+inline void note_launch() {}
+
+// ---- mbarrier + TMA bulk: the same names as csrc/common.cuh
+inline void mbar_init(uint64_t* bar, uint32_t count) {
+    sim::Mbar& b = sim::g->mbars[bar];
+    b.count = b.pending = count, b.phase = 0, b.tx = 0;
+}
+inline void fence_mbar_init() {}
+inline void fence_proxy_async_smem() {}
+inline void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    sim::g->mbars[bar].tx += bytes;
+    sim::mbar_arrive(bar);
+}
+inline void mbar_arrive(uint64_t* bar) { sim::mbar_arrive(bar); }
+inline bool mbar_try_wait(uint64_t* bar, uint32_t parity) { return sim::g->mbars[bar].phase != parity; }
+inline void mbar_wait(uint64_t* bar, uint32_t parity) {
+    while (!mbar_try_wait(bar, parity)) sim::yield();
+}
+inline void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+    if ((reinterpret_cast<uintptr_t>(dst_smem) | reinterpret_cast<uintptr_t>(src_gmem) | bytes) & 15)
+        sim::g->error = "bulk_g2s: address or size not a multiple of 16 bytes";
+    std::memcpy(dst_smem, src_gmem, bytes);
+    sim::mbar_complete_tx(bar, bytes);
+}
+inline void bulk_s2g(void* dst_gmem, const void* src_smem, uint32_t bytes) {
+    if ((reinterpret_cast<uintptr_t>(dst_gmem) | reinterpret_cast<uintptr_t>(src_smem) | bytes) & 15)
+        sim::g->error = "bulk_s2g: address or size not a multiple of 16 bytes";
+    std::memcpy(dst_gmem, src_smem, bytes);
+}
+inline void bulk_commit() {}
+template <int N>
+inline void bulk_wait_read() {}
+template <int N>
+inline void bulk_wait_all() {}
+
+// ---- math (libm instead of the .approx MUFU ops: differences are far below the parity tolerance)
+inline float ex2f(float x) { return exp2f(x); }
+inline float lg2f(float x) { return log2f(x); }
+inline float softplus20(float x, float& e_out, float& w_out) {
+    const float e = ex2f(x * kLog2e);
+    const float w = 1.0f + e;
+    const float corr = (e < 1.0f) ? (e - (w - 1.0f)) : 0.0f;
+    const float sp = fmaf(lg2f(w), kLn2, corr);
+    e_out = e, w_out = w;
+    return (x > 20.0f) ? x : sp;
+}
+inline float softplus20(float x, float& e_out) {
+    float w;
+    return softplus20(x, e_out, w);
+}
+inline float softplus20_fast(float x) {
+    const float sp = lg2f(1.0f + ex2f(x * kLog2e)) * kLn2;
+    return (x > 20.0f) ? x : sp;
+}
+inline float to_f32(float v) { return v; }
+inline float to_f32(__nv_bfloat16 v) { return __bfloat162float(v); }
+
+}  // namespace tramba
