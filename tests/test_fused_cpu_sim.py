@@ -39,7 +39,9 @@ def sim():
     for name in ("sim_fwd", "sim_bwd", "sim_fwd_cg", "sim_bwd_cg"):
         fn = getattr(lib, name)
         fn.restype, fn.argtypes = ctypes.c_char_p, [ctypes.POINTER(FusedArgs), ctypes.c_int, ctypes.c_int]
-    return lib
+    lib.sim_set_lazy.restype, lib.sim_set_lazy.argtypes = None, [ctypes.c_int]
+    yield lib
+    lib.sim_set_lazy(0)
 
 
 def _dev(t, bf16):
@@ -106,8 +108,13 @@ CASES = [  # family, H, D, B, bf16, grid
 ]
 
 
+@pytest.mark.parametrize("lazy", [0, 1], ids=["eager-copies", "lazy-copies"])
 @pytest.mark.parametrize("fam,H,D,B,bf16,grid", CASES)
-def test_fused_kernels_on_the_cpu_simulator(sim, fam, H, D, B, bf16, grid):
+def test_fused_kernels_on_the_cpu_simulator(sim, fam, H, D, B, bf16, grid, lazy):
+    """lazy = 0: asynchronous copies land when issued (a buffer refilled too early corrupts its readers);
+    lazy = 1: they land when waited for and their destinations are poisoned meanwhile, bulk stores read their shared
+    source at the wait_group (a read before the barrier / a staging buffer overwritten too early corrupts data)."""
+    sim.sim_set_lazy(lazy)
     res, ref_y, ref_g, bf16 = _run(sim, fam, H, D, B, bf16, grid)
     rtol = 1e-2 if bf16 else 1e-3
     for tag, out in res.items():
@@ -144,6 +151,7 @@ def test_simulator_selftest(sim):
     sim.sim_selftest_shuffle.restype, sim.sim_selftest_shuffle.argtypes = cp, [fp, fp, ctypes.c_int]
     sim.sim_selftest_mismatch.restype, sim.sim_selftest_mismatch.argtypes = cp, []
     sim.sim_selftest_mbar.restype, sim.sim_selftest_mbar.argtypes = cp, [ctypes.c_int, fp]
+    sim.sim_set_lazy(0)
     x = np.arange(64, dtype=np.float32) + 1
     out = np.zeros(2 * 64 + 1, np.float32)
     assert sim.sim_selftest_shuffle(x.ctypes.data, out.ctypes.data, 3) is None

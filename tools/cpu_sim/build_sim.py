@@ -29,11 +29,11 @@ def gen_header():
     s = open(os.path.join(CSRC, "ss2d_fused.cuh")).read()
     s = sub1(s, '#include "common.cuh"', '#include "sim_common.h"')
     s = sub1(s, 'asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(dst_smem)), "l"(src) : "memory");',
-             "std::memcpy(dst_smem, src, 4);")
+             "sim::cp_async(dst_smem, src, 4);")
     s = sub1(s, 'asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(dst_smem)), "l"(src) : "memory");',
-             "std::memcpy(dst_smem, src, 8);")
+             "sim::cp_async(dst_smem, src, 8);")
     s = sub1(s, 'asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");',
-             "sim::mbar_arrive(bar);")
+             "sim::cp_async_arrive(bar);")
     assert "asm" not in s
     open(os.path.join(GEN, "ss2d_fused.cuh"), "w").write(s)
 

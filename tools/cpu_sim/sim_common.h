@@ -4,12 +4,17 @@
 // this header with the inline PTX swapped for the functions below and compiles them as ordinary C++: this file
 // stands in for csrc/common.cuh.  Execution model: one CTA at a time, every CUDA thread a cooperative fiber
 // (ucontext) that yields only inside __syncthreads(), warp shuffles and mbarrier waits, so runs are deterministic
-// and data-race free by construction.  Asynchronous copies (cp.async, TMA bulk copies) complete at issue.
+// and data-race free by construction.  Asynchronous copies (cp.async, TMA bulk copies) are modelled at the two
+// extremes of what the hardware may do: EAGER (default) -- the copy lands the moment it is issued, which exposes a
+// buffer that is refilled while slower threads still read it; LAZY (sim_set_lazy(1)) -- the destination is poisoned
+// at issue and the data lands only when somebody waits on the copy's mbarrier (global->shared), respectively the
+// shared source is read only at the issuing thread's cp.async.bulk.wait_group (shared->global), which exposes a
+// read before the wait and a staging buffer overwritten before its bulk store has drained.
 //
 // What it checks: the kernels' index arithmetic, work decomposition, scan / carry logic, barrier and mbarrier
 // protocols (a barrier mismatch shows up as a reported deadlock) and numerics against the oracle.
-// What it cannot check: anything that depends on copies being asynchronous (reading a buffer before its barrier,
-// overwriting a bulk-store source early), memory-model ordering, bank conflicts, performance.
+// What it cannot check: interleavings between the two extremes, memory-model ordering (fences, proxies), bank
+// conflicts, performance.
 #pragma once
 #include <cuda_bf16.h>
 #include <driver_types.h>
@@ -41,8 +46,17 @@ struct Warp {
     uint32_t slot[32];
     int count = 0, gen = 0;
 };
+struct Copy {
+    void* dst;
+    const void* src;
+    size_t bytes;
+};
 struct Cta {
     int nthreads = 0, bx = 0, gdim = 0;
+    std::unordered_map<const void*, std::vector<Copy>> bar_copies;     // lazy g2s copies, per mbarrier
+    std::unordered_map<const void*, std::vector<long long>> bar_tx;    // ... and their complete_tx bytes (-1: an arrive)
+    std::vector<std::vector<Copy>> thread_async;                       // cp.async issued, not yet bound to a barrier
+    std::vector<std::vector<Copy>> thread_stores;                      // lazy s2g bulk stores of each thread
     unsigned char* smem = nullptr;
     ucontext_t sched;
     std::vector<ucontext_t> ctx;
@@ -56,6 +70,7 @@ struct Cta {
 };
 inline Cta* g = nullptr;
 inline std::function<void()>* g_body = nullptr;
+inline bool lazy = false;
 
 inline Idx3 tidx() { return Idx3{static_cast<unsigned>(g->cur), 0, 0}; }
 inline Idx3 bidx() { return Idx3{static_cast<unsigned>(g->bx), 0, 0}; }
@@ -119,6 +134,62 @@ inline void mbar_complete_tx(const void* bar, long long bytes) {
 }
 inline void red_add_v2(float* p, float a, float b) { p[0] += a, p[1] += b; }
 
+// ---- asynchronous copies
+inline void cp_async(void* dst, const void* src, size_t n) {            // cp.async.ca.shared.global (4 / 8 bytes)
+    if (!lazy) {
+        std::memcpy(dst, src, n);
+        return;
+    }
+    std::memset(dst, 0xCD, n);
+    g->thread_async[g->cur].push_back(Copy{dst, src, n});
+}
+inline void cp_async_arrive(const void* bar) {                          // cp.async.mbarrier.arrive.noinc
+    if (!lazy) {
+        mbar_arrive(bar);
+        return;
+    }
+    auto& mine = g->thread_async[g->cur];
+    auto& q = g->bar_copies[bar];
+    q.insert(q.end(), mine.begin(), mine.end());
+    mine.clear();
+    g->bar_tx[bar].push_back(-1);
+}
+inline void g2s(void* dst, const void* src, size_t bytes, const void* bar) {
+    if (!lazy) {
+        std::memcpy(dst, src, bytes);
+        mbar_complete_tx(bar, static_cast<long long>(bytes));
+        return;
+    }
+    std::memset(dst, 0xCD, bytes);
+    g->bar_copies[bar].push_back(Copy{dst, src, bytes});
+    g->bar_tx[bar].push_back(static_cast<long long>(bytes));
+}
+inline void flush_barrier(const void* bar) {                            // somebody waits: everything in flight lands now
+    auto it = g->bar_copies.find(bar);
+    if (it != g->bar_copies.end()) {
+        for (const Copy& c : it->second) std::memcpy(c.dst, c.src, c.bytes);
+        it->second.clear();
+    }
+    auto jt = g->bar_tx.find(bar);
+    if (jt != g->bar_tx.end()) {
+        std::vector<long long> evs;
+        evs.swap(jt->second);
+        for (long long e : evs) {
+            if (e < 0) mbar_arrive(bar);
+            else mbar_complete_tx(bar, e);
+        }
+    }
+}
+inline void s2g(void* dst, const void* src, size_t bytes) {
+    if (!lazy) std::memcpy(dst, src, bytes);
+    else g->thread_stores[g->cur].push_back(Copy{dst, src, bytes});
+}
+inline void drain_stores() {                                            // cp.async.bulk.wait_group[.read] 0
+    auto& q = g->thread_stores[g->cur];
+    for (const Copy& c : q) std::memcpy(c.dst, c.src, c.bytes);
+    q.clear();
+}
+
 // Runs `body` as grid x nthreads CUDA threads, CTA after CTA.  Returns nullptr or an error string.
 inline const char* launch(int grid, int nthreads, size_t smem_bytes, std::function<void()> body) {
     static std::vector<char*> stacks;
@@ -134,6 +205,7 @@ inline const char* launch(int grid, int nthreads, size_t smem_bytes, std::functi
         cta.smem = static_cast<unsigned char*>(raw);
         std::memset(cta.smem, 0xCD, smem_bytes);   // poison: uninitialised shared memory must not go unnoticed
         cta.ctx.resize(nthreads), cta.done.assign(nthreads, 0), cta.warps.resize((nthreads + 31) / 32);
+        cta.thread_async.resize(nthreads), cta.thread_stores.resize(nthreads);
         g = &cta;
         for (int t = 0; t < nthreads; ++t) {
             getcontext(&cta.ctx[t]);
@@ -142,6 +214,7 @@ inline const char* launch(int grid, int nthreads, size_t smem_bytes, std::functi
             cta.ctx[t].uc_link = &cta.sched;
             makecontext(&cta.ctx[t], reinterpret_cast<void (*)()>(+[]() {
                             (*g_body)();
+                            drain_stores();          // a store still in flight at exit completes eventually
                             g->done[g->cur] = 1;
                             ++g->progress;
                         }),
@@ -217,26 +290,34 @@ inline void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
     sim::mbar_arrive(bar);
 }
 inline void mbar_arrive(uint64_t* bar) { sim::mbar_arrive(bar); }
-inline bool mbar_try_wait(uint64_t* bar, uint32_t parity) { return sim::g->mbars[bar].phase != parity; }
+inline bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+    if (sim::lazy) sim::flush_barrier(bar);
+    return sim::g->mbars[bar].phase != parity;
+}
 inline void mbar_wait(uint64_t* bar, uint32_t parity) {
     while (!mbar_try_wait(bar, parity)) sim::yield();
 }
 inline void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
     if ((reinterpret_cast<uintptr_t>(dst_smem) | reinterpret_cast<uintptr_t>(src_gmem) | bytes) & 15)
         sim::g->error = "bulk_g2s: address or size not a multiple of 16 bytes";
-    std::memcpy(dst_smem, src_gmem, bytes);
-    sim::mbar_complete_tx(bar, bytes);
+    sim::g2s(dst_smem, src_gmem, bytes, bar);
 }
 inline void bulk_s2g(void* dst_gmem, const void* src_smem, uint32_t bytes) {
     if ((reinterpret_cast<uintptr_t>(dst_gmem) | reinterpret_cast<uintptr_t>(src_smem) | bytes) & 15)
         sim::g->error = "bulk_s2g: address or size not a multiple of 16 bytes";
-    std::memcpy(dst_gmem, src_smem, bytes);
+    sim::s2g(dst_gmem, src_smem, bytes);
 }
 inline void bulk_commit() {}
 template <int N>
-inline void bulk_wait_read() {}
+inline void bulk_wait_read() {
+    static_assert(N == 0, "the kernels only wait for all groups");
+    sim::drain_stores();
+}
 template <int N>
-inline void bulk_wait_all() {}
+inline void bulk_wait_all() {
+    static_assert(N == 0, "the kernels only wait for all groups");
+    sim::drain_stores();
+}
 
 // ---- math (libm instead of the .approx MUFU ops: differences are far below the parity tolerance)
 inline float ex2f(float x) { return exp2f(x); }
