@@ -162,3 +162,35 @@ def test_simulator_selftest(sim):
     o = np.zeros(32, np.float32)
     assert sim.sim_selftest_mbar(1, o.ctypes.data) is None and np.array_equal(o[:4], [1, 2, 3, 4])
     assert b"deadlock" in sim.sim_selftest_mbar(0, o.ctypes.data)
+
+
+@pytest.mark.parametrize("lazy", [0, 1], ids=["eager-copies", "lazy-copies"])
+@pytest.mark.parametrize("fam,H,D,B,bf16,grid", [("std", 12, 64, 2, False, 2), ("line", 24, 16, 2, True, 1),
+                                                 ("window", 48, 8, 1, False, 2), ("dilation", 96, 3, 1, True, 2),
+                                                 ("line", 96, 2, 1, False, 1)])
+def test_merge_skewed_on_the_cpu_simulator(sim, fam, H, D, B, bf16, grid, lazy):
+    """tramba_cross_merge_skewed's kernel (dx = CrossScan*.backward(du) of the fused backward), product and
+    candidate: exact against the transpose of the gather on integer-valued data (any summation order is exact)."""
+    from oracle import scan_orders as so
+    order, K = ORDER[fam]
+    L = H * H
+    args = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p] + [ctypes.c_int] * 4 + [ctypes.c_uint32, ctypes.c_int,
+                                                                                      ctypes.c_int]
+    sim.sim_set_lazy(lazy)
+    rs = np.random.RandomState(H + D)
+    ys = torch.from_numpy(rs.randint(-4, 5, size=(B, K, D, L)).astype(np.float32))
+    t16 = np.empty((K, L), dtype=np.uint16)
+    _lib.check(_lib.lib.tramba_order_table16_skewed(order, H, H, param_of(fam, H), t16.ctypes.data))
+    want = so.cross_merge(ys.numpy(), so.order_table(fam, H, param_of(fam, H)), "custom")
+    src = _dev(ys, bf16)
+    outs = []
+    for name in ("sim_merge", "sim_merge_cg"):
+        fn = getattr(sim, name)
+        fn.restype, fn.argtypes = ctypes.c_char_p, args
+        y = np.zeros((B, D, L), np.uint16 if bf16 else np.float32)
+        err = fn(src.ctypes.data, y.ctypes.data, t16.ctypes.data, K, B, D, L, 0xF0 if fam == "line" else 0,
+                 _lib.BF16 if bf16 else _lib.F32, grid)
+        assert err is None, (name, err.decode())
+        assert np.array_equal(_host(y, bf16).numpy(), want), name
+        outs.append(y)
+    assert np.array_equal(outs[0], outs[1])

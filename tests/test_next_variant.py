@@ -39,7 +39,7 @@ def test_candidate_library_has_the_same_abi(next_lib):
 def test_candidate_kernels_only_in_the_candidate_library(next_lib):
     base = os.path.join(os.path.dirname(next_lib), "libtramba_b200.so")
     cand_syms, base_syms = _kernel_names(next_lib), _kernel_names(base)
-    for k in ("ss2d_fwd_cg_kernel", "ss2d_bwd_cg_kernel"):
+    for k in ("ss2d_fwd_cg_kernel", "ss2d_bwd_cg_kernel", "merge_skewed_cg_kernel"):
         assert k in cand_syms, k
         assert k not in base_syms, k             # the default build is the verified kernels only
     for k in ("ss2d_fwd_kernel", "ss2d_bwd_kernel"):   # the generic kernels stay in both (fallback for other shapes)

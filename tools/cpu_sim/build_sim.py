@@ -146,12 +146,62 @@ extern "C" const char* sim_bwd_cg(const FusedArgs* a, int in_dtype, int grid) { 
 }  // namespace tramba
 '''
 
+TAIL_MERGE = r'''
+template <typename T>
+static const char* run(const T* ys, T* y, const uint16_t* idx, int K, int B, int D, int L, uint32_t dup_mask, int grid) {
+    const int TP = L / S, PP = NT / TP, rounds = B * D / PP;
+    if (grid > rounds) grid = rounds;
+    return sim::launch(grid, NT, MergeLayout(L, sizeof(T)).total,
+                       [&] { merge_skewed_kernel<T>(ys, y, idx, K, D, L, TP, PP, rounds, dup_mask); });
+}
+}  // namespace
+extern "C" const char* sim_merge(const void* ys, void* y, const uint16_t* idx, int K, int B, int D, int L,
+                                 uint32_t dup_mask, int dtype, int grid) {
+    return dtype == TRAMBA_F32 ? run(static_cast<const float*>(ys), static_cast<float*>(y), idx, K, B, D, L, dup_mask, grid)
+                               : run(static_cast<const __nv_bfloat16*>(ys), static_cast<__nv_bfloat16*>(y), idx, K, B, D, L,
+                                     dup_mask, grid);
+}
+}  // namespace tramba
+'''
+
+TAIL_MERGE_CG = r'''
+template <typename T, int TPC>
+static const char* run1(const T* ys, T* y, const uint16_t* idx, int K, int B, int D, uint32_t dup_mask, int grid) {
+    constexpr int L = S * TPC, PP = NT / TPC;
+    const int rounds = B * D / PP;
+    if (grid > rounds) grid = rounds;
+    return sim::launch(grid, NT, MergeLayout(L, sizeof(T)).total,
+                       [&] { merge_skewed_cg_kernel<T, TPC>(ys, y, idx, K, D, rounds, dup_mask); });
+}
+template <typename T>
+static const char* run(const T* ys, T* y, const uint16_t* idx, int K, int B, int D, int L, uint32_t dup_mask, int grid) {
+    switch (L / S) {
+        case 8: return run1<T, 8>(ys, y, idx, K, B, D, dup_mask, grid);
+        case 32: return run1<T, 32>(ys, y, idx, K, B, D, dup_mask, grid);
+        case 128: return run1<T, 128>(ys, y, idx, K, B, D, dup_mask, grid);
+        case 512: return run1<T, 512>(ys, y, idx, K, B, D, dup_mask, grid);
+        default: return "threads per plane not specialised";
+    }
+}
+}  // namespace
+extern "C" const char* sim_merge_cg(const void* ys, void* y, const uint16_t* idx, int K, int B, int D, int L,
+                                    uint32_t dup_mask, int dtype, int grid) {
+    return dtype == TRAMBA_F32 ? run(static_cast<const float*>(ys), static_cast<float*>(y), idx, K, B, D, L, dup_mask, grid)
+                               : run(static_cast<const __nv_bfloat16*>(ys), static_cast<__nv_bfloat16*>(y), idx, K, B, D, L,
+                                     dup_mask, grid);
+}
+}  // namespace tramba
+'''
+
 KERNELS = [  # source, cut marker (everything from it on is replaced by the tail), tail, anonymous namespace still open?
     ("ss2d_fused_fwd.cu", "}  // namespace\n\nsize_t ss2d_fused_fwd_smem", TAIL_FWD),
     ("ss2d_fused_bwd.cu", "}  // namespace\n\nsize_t ss2d_fused_bwd_smem", TAIL_BWD),
     (os.path.join("next", "ss2d_fused_fwd_cg.cu"),
      "template <typename in_t, bool SOFTPLUS, int TPC, int XB>\nstatic cudaError_t launch_cg", TAIL_FWD_CG),
     (os.path.join("next", "ss2d_fused_bwd_cg.cu"), "// Channels per item: enough rounds that the per-item", TAIL_BWD_CG),
+    ("ss2d_fused_merge.cu", "}  // namespace\n\ntemplate <typename T>\nstatic cudaError_t launch_t", TAIL_MERGE),
+    (os.path.join("next", "ss2d_fused_merge_cg.cu"), "template <typename T, int TPC>\nstatic cudaError_t launch_cg",
+     TAIL_MERGE_CG),
 ]
 
 
@@ -177,13 +227,19 @@ def build(force=False):
         return LIB
     gen_header()
     srcs = [gen_kernel(*k) for k in KERNELS]
-    cmd = ["g++", "-std=c++17", "-O1", "-fPIC", "-shared", "-w", "-I" + HERE, "-I" + GEN,
-           "-I" + os.path.join(ROOT, "include"), "-I/usr/local/cuda/include"] + srcs + [
-               os.path.join(HERE, "selftest.cpp"), "-o", LIB]
-    res = subprocess.run(cmd, capture_output=True, text=True)
-    if res.returncode != 0:
-        sys.stderr.write(res.stdout + res.stderr)
-        raise RuntimeError("cpu_sim build failed")
+    srcs.append(os.path.join(HERE, "selftest.cpp"))
+    flags = ["-std=c++17", "-O1", "-fPIC", "-w", "-I" + HERE, "-I" + GEN, "-I" + os.path.join(ROOT, "include"),
+             "-I/usr/local/cuda/include"]
+    objs = [os.path.join(GEN, os.path.splitext(os.path.basename(f))[0] + ".o") for f in srcs]
+    from concurrent.futures import ThreadPoolExecutor
+    with ThreadPoolExecutor(max_workers=min(len(srcs), os.cpu_count() or 4)) as ex:
+        results = list(ex.map(lambda so: subprocess.run(["g++"] + flags + ["-c", so[0], "-o", so[1]],
+                                                        capture_output=True, text=True), zip(srcs, objs)))
+    for res in results:
+        if res.returncode != 0:
+            sys.stderr.write(res.stdout + res.stderr)
+            raise RuntimeError("cpu_sim build failed")
+    subprocess.check_call(["g++", "-shared", "-o", LIB] + objs)
     return LIB
 
 

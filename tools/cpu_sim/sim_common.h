@@ -340,5 +340,23 @@ inline float softplus20_fast(float x) {
 }
 inline float to_f32(float v) { return v; }
 inline float to_f32(__nv_bfloat16 v) { return __bfloat162float(v); }
+template <typename T>
+inline T from_f32(float v);
+template <>
+inline float from_f32<float>(float v) {
+    return v;
+}
+template <>
+inline __nv_bfloat16 from_f32<__nv_bfloat16>(float v) {
+    return __float2bfloat16_rn(v);
+}
+template <int CNT, typename T>
+inline void load_vec(const T* p, float (&v)[CNT]) {
+    for (int i = 0; i < CNT; ++i) v[i] = to_f32(p[i]);
+}
+template <int CNT, typename T>
+inline void store_vec(T* p, const float (&v)[CNT]) {
+    for (int i = 0; i < CNT; ++i) p[i] = from_f32<T>(v[i]);
+}
 
 }  // namespace tramba

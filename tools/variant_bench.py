@@ -82,7 +82,7 @@ def main(argv=None):
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream if dev.type == "cuda" else 0)
     B = a.batch
-    tot = {"base": [0.0, 0.0], "cand": [0.0, 0.0]}
+    tot = {"base": [0.0, 0.0, 0.0], "cand": [0.0, 0.0, 0.0]}
     ok_all = True
     for name, order, param, K, D, H, calls in SITES:
         if a.only and a.only not in name:
@@ -124,8 +124,14 @@ def main(argv=None):
                                                      dC.data_ptr(), part[0].data_ptr(), part[1].data_ptr(),
                                                      part[2].data_ptr(), order, K, B, D, H, H, 1, code, 1, st))
 
-            times[tag] = (timeit(fwd, a.reps, flush), timeit(bwd, a.reps, flush))
-            outs[tag] = (y, du, dd, part, dB, dC)
+            dx = torch.empty(B, D, L, device=dev, dtype=dt)
+
+            def merge(lib=lib, du=du, dx=dx):
+                check(lib, lib.tramba_cross_merge_skewed(du.data_ptr(), dx.data_ptr(), idx.data_ptr(), order, K, B, D,
+                                                         H, H, code, st))
+
+            times[tag] = (timeit(fwd, a.reps, flush), timeit(bwd, a.reps, flush), timeit(merge, a.reps, flush))
+            outs[tag] = (y, du, dd, part, dB, dC, dx)
         b_, c_ = outs["base"], outs["cand"]
         line_dup = order == _lib.ORDER_LINE    # helix directions merge duplicate pixels with smem atomics (fwd y)
         exact = {"y": torch.equal(b_[0], c_[0]) if not line_dup else bool(torch.allclose(b_[0], c_[0], rtol=1e-5, atol=1e-5)),
@@ -133,6 +139,8 @@ def main(argv=None):
                  "dA_dD_dbias": torch.equal(b_[3], c_[3]),
                  "dB": bool(torch.allclose(b_[4], c_[4], rtol=1e-4, atol=1e-4 * float(b_[4].abs().max()))),
                  "dC": bool(torch.allclose(b_[5], c_[5], rtol=1e-4, atol=1e-4 * float(b_[5].abs().max())))}
+        exact["dx_merge"] = torch.equal(b_[6], c_[6]) if not line_dup else bool(
+            torch.allclose(b_[6].float(), c_[6].float(), rtol=1e-2, atol=1e-2 * float(b_[6].float().abs().max())))
         # not bit-identical (e.g. the compiler contracted an FMA differently): report how far, accept fp32 rounding
         drift = {}
         for key, i in (("y", 0), ("du", 1), ("ddelta", 2), ("dA_dD_dbias", 3)):
@@ -147,12 +155,14 @@ def main(argv=None):
         for tag in libs:
             tot[tag][0] += calls * times[tag][0]
             tot[tag][1] += calls * times[tag][1]
+            tot[tag][2] += calls * times[tag][2]
         print(json.dumps({"site": name, "dtype": a.dtype, "parity_vs_product": exact, "max_rel_drift_where_not_bit_identical": drift, "ok": ok,
                           "fwd_us": {k: round(v[0], 1) for k, v in times.items()},
                           "bwd_us": {k: round(v[1], 1) for k, v in times.items()},
+                          "merge_us": {k: round(v[2], 1) for k, v in times.items()},
                           "fwd_gbs": {k: round(fb / v[0] / 1e3, 1) for k, v in times.items()},
                           "bwd_gbs": {k: round(bb / v[1] / 1e3, 1) for k, v in times.items()}}), flush=True)
-    print(json.dumps({"summary_us_per_step_weighted_by_calls": {k: {"fwd": round(v[0], 1), "bwd": round(v[1], 1)}
+    print(json.dumps({"summary_us_per_step_weighted_by_calls": {k: {"fwd": round(v[0], 1), "bwd": round(v[1], 1), "merge": round(v[2], 1)}
                                                                 for k, v in tot.items()},
                       "all_parity_ok": ok_all}))
     return 0 if ok_all else 1

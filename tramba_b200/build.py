@@ -38,7 +38,8 @@ def sources_newer_than_lib():
     return _stale(LIB, deps)
 
 
-NEXT_SOURCES = [os.path.join("next", "ss2d_fused_fwd_cg.cu"), os.path.join("next", "ss2d_fused_bwd_cg.cu")]
+NEXT_SOURCES = [os.path.join("next", "ss2d_fused_fwd_cg.cu"), os.path.join("next", "ss2d_fused_bwd_cg.cu"),
+                os.path.join("next", "ss2d_fused_merge_cg.cu")]
 LIB_NEXT = os.path.join(HERE, "libtramba_b200_next.so")
 
 

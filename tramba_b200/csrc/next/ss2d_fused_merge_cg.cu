@@ -1,4 +1,8 @@
-// Cross-merge through the skewed scan-order table (sm_100a): y[b,d,p] = sum_k sum_{t: idx[k,t]=p} ys[b,k,d,t].
+// Cross-merge through the skewed scan-order table (sm_100a) -- COMPILE-TIME-GEOMETRY candidate ("next" build only).
+// Same algorithm, layout and results as ss2d_fused_merge.cu; threads-per-plane is a template constant (tid / TP,
+// e / L, the plane strides and the shared-memory layout fold) and the table words of the next direction are loaded
+// one stage ahead.  NOT part of libtramba_b200.so: see csrc/next/ss2d_fused_bwd_cg.cu.
+// y[b,d,p] = sum_k sum_{t: idx[k,t]=p} ys[b,k,d,t].
 // Used by the fused SS2D backward to fold the scan-ordered du back to image order
 // (= CrossScan*.backward, Models/SS2D/csms6s.py:25-31,75-80,124-129,175-185).  Same data model as
 // the fused forward (ss2d_fused.cuh): a round = PP whole planes; per direction the PP token rows
@@ -6,7 +10,7 @@
 // skewed shared image plane; after the K directions the plane is written out once.  fp32
 // accumulation, directions in order k = 0..K-1; duplicate hits of a pixel (helix lines) use shared
 // fp32 atomics.  The deterministic, reference-association-order merge is tramba_cross_merge.
-#include "ss2d_fused.cuh"
+#include "../ss2d_fused.cuh"
 
 namespace tramba {
 
@@ -32,11 +36,12 @@ struct MergeLayout {
     }
 };
 
-template <typename T>
-__global__ void __launch_bounds__(NT, 2) merge_skewed_kernel(const T* __restrict__ ys, T* __restrict__ y,
-                                                             const uint16_t* __restrict__ idx, int K, int D, int L,
-                                                             int TP, int PP, int rounds, uint32_t dup_mask) {
+template <typename T, int TPC>
+__global__ void __launch_bounds__(NT, 2) merge_skewed_cg_kernel(const T* __restrict__ ys, T* __restrict__ y,
+                                                                const uint16_t* __restrict__ idx, int K, int D,
+                                                                int rounds, uint32_t dup_mask) {
     extern __shared__ __align__(128) unsigned char smem[];
+    constexpr int TP = TPC, L = S * TPC, PP = NT / TPC;
     const MergeLayout lay(L, sizeof(T));
     const int LSK = lay.lsk;
     T* sd = reinterpret_cast<T*>(smem + lay.d);          // [2][TOK]
@@ -64,15 +69,26 @@ __global__ void __launch_bounds__(NT, 2) merge_skewed_kernel(const T* __restrict
     };
     if (tid == 0) issue(0);
     float* yq = sy + static_cast<size_t>(q) * LSK;
+    uint32_t npk[S / 2];   // table words of the next stage's direction
+    {
+        const uint32_t* tp = reinterpret_cast<const uint32_t*>(idx + j * S);
+#pragma unroll
+        for (int m = 0; m < S / 2; ++m) npk[m] = __ldg(tp + m);
+    }
     int s = 0;
     for (int i = 0; i < my_rounds; ++i) {
         const long long plane0 = (static_cast<long long>(blockIdx.x) + static_cast<long long>(i) * gridDim.x) * PP;
         for (int k = 0; k < K; ++k, ++s) {
             if (tid == 0 && s + 1 < nstages) issue(s + 1);  // buffer (s+1)&1 was released by the barrier of stage s-1
             uint32_t pk[S / 2];
-            const uint32_t* tp = reinterpret_cast<const uint32_t*>(idx + static_cast<size_t>(k) * L + j * S);
 #pragma unroll
-            for (int m = 0; m < S / 2; ++m) pk[m] = __ldg(tp + m);
+            for (int m = 0; m < S / 2; ++m) pk[m] = npk[m];
+            if (s + 1 < nstages) {
+                const int kn = (k + 1 < K) ? k + 1 : 0;
+                const uint32_t* tp = reinterpret_cast<const uint32_t*>(idx + static_cast<size_t>(kn) * L + j * S);
+#pragma unroll
+                for (int m = 0; m < S / 2; ++m) npk[m] = __ldg(tp + m);
+            }
             mbar_wait(&bar[s & 1], static_cast<uint32_t>((s >> 1) & 1));
             float v[S];
             load_tokens<S>(sd + static_cast<size_t>(s & 1) * TOK + static_cast<size_t>(q) * L + j * S, v);
@@ -102,12 +118,10 @@ __global__ void __launch_bounds__(NT, 2) merge_skewed_kernel(const T* __restrict
     }
 }
 
-}  // namespace
-
-template <typename T>
-static cudaError_t launch_t(const T* ys, T* y, const uint16_t* idx, int K, int B, int D, int L, uint32_t dup_mask,
-                            cudaStream_t st) {
-    auto kern = merge_skewed_kernel<T>;
+template <typename T, int TPC>
+static cudaError_t launch_cg(const T* ys, T* y, const uint16_t* idx, int K, int B, int D, uint32_t dup_mask,
+                             cudaStream_t st) {
+    auto kern = merge_skewed_cg_kernel<T, TPC>;
     static bool configured = false;
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
@@ -120,33 +134,40 @@ static cudaError_t launch_t(const T* ys, T* y, const uint16_t* idx, int K, int B
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     }
-    const int TP = L / S, PP = NT / TP;
+    constexpr int L = S * TPC, PP = NT / TPC;
     const int rounds = B * D / PP;
     const size_t smem = MergeLayout(L, sizeof(T)).total;
-    const int cap = 2 * sms;  // two CTAs per SM (75 KB each for bf16)
+    const int cap = 2 * sms;  // two CTAs per SM, as the generic launcher
     const int grid = rounds < cap ? rounds : cap;
-    kern<<<grid, NT, smem, st>>>(ys, y, idx, K, D, L, TP, PP, rounds, dup_mask);
+    kern<<<grid, NT, smem, st>>>(ys, y, idx, K, D, rounds, dup_mask);
     note_launch();
     return cudaGetLastError();
 }
 
-#ifdef TRAMBA_NEXT
-cudaError_t launch_merge_skewed_cg(const void* ys, void* y, const uint16_t* idx, int K, int B, int D, int L,
-                                   uint32_t dup_mask, int dtype, cudaStream_t st);  // csrc/next/
-#endif
+template <typename T>
+static cudaError_t dispatch_tp(const T* ys, T* y, const uint16_t* idx, int K, int B, int D, int L, uint32_t dup_mask,
+                               cudaStream_t st) {
+    switch (L / S) {
+        case 8: return launch_cg<T, 8>(ys, y, idx, K, B, D, dup_mask, st);
+        case 32: return launch_cg<T, 32>(ys, y, idx, K, B, D, dup_mask, st);
+        case 128: return launch_cg<T, 128>(ys, y, idx, K, B, D, dup_mask, st);
+        case 512: return launch_cg<T, 512>(ys, y, idx, K, B, D, dup_mask, st);
+        default: return cudaErrorNotSupported;
+    }
+}
 
-cudaError_t launch_merge_skewed(const void* ys, void* y, const uint16_t* idx, int K, int B, int D, int L,
-                                uint32_t dup_mask, int dtype, cudaStream_t st) {
-#ifdef TRAMBA_NEXT  // candidate build (libtramba_b200_next.so)
-    const cudaError_t e = launch_merge_skewed_cg(ys, y, idx, K, B, D, L, dup_mask, dtype, st);
-    if (e != cudaErrorNotSupported) return e;
-#endif
+}  // namespace
+
+// cudaErrorNotSupported = not one of the specialised shapes (the caller launches the generic kernel)
+cudaError_t launch_merge_skewed_cg(const void* ys, void* y, const uint16_t* idx, int K, int B, int D, int L,
+                                   uint32_t dup_mask, int dtype, cudaStream_t st) {
+    if (L % S != 0) return cudaErrorNotSupported;
     if (dtype == TRAMBA_F32)
-        return launch_t(static_cast<const float*>(ys), static_cast<float*>(y), idx, K, B, D, L, dup_mask, st);
+        return dispatch_tp(static_cast<const float*>(ys), static_cast<float*>(y), idx, K, B, D, L, dup_mask, st);
     if (dtype == TRAMBA_BF16)
-        return launch_t(static_cast<const __nv_bfloat16*>(ys), static_cast<__nv_bfloat16*>(y), idx, K, B, D, L,
-                        dup_mask, st);
-    return cudaErrorInvalidValue;
+        return dispatch_tp(static_cast<const __nv_bfloat16*>(ys), static_cast<__nv_bfloat16*>(y), idx, K, B, D, L,
+                           dup_mask, st);
+    return cudaErrorNotSupported;
 }
 
 }  // namespace tramba
