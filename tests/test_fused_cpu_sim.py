@@ -194,3 +194,60 @@ def test_merge_skewed_on_the_cpu_simulator(sim, fam, H, D, B, bf16, grid, lazy):
         assert np.array_equal(_host(y, bf16).numpy(), want), name
         outs.append(y)
     assert np.array_equal(outs[0], outs[1])
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# operator selective scan (csrc/sscan_fwd.cu, sscan_bwd.cu): the whole files are translated -- kernels AND host
+# launchers (plan selection, template dispatch), only the <<<>>> launches / PTX / shared-memory declaration rewritten
+SSCAN_CASES = [  # batch, dim, L, N, groups, bf16     (plans: see make_sscan_plan in csrc/sscan.cuh)
+    (2, 16, 576, 1, 4, False),     # the model's shape class: N = 1, TMA ring, 2 chunks of 288 per row
+    (1, 8, 2304, 1, 2, True),      # bf16 in, fp32 out, 384-token chunks
+    (2, 16, 144, 1, 4, False),     # two 144-token rows per chunk (regular, rpc = 2)
+    (1, 8, 1152, 16, 4, False),    # config-2 state size N = 16
+    (1, 6, 50, 3, 3, False),       # rows that are not 16-byte multiples: the DIRECT scalar path, N = 3
+    (2, 8, 9216, 1, 4, True),      # 96 x 96 rows
+]
+
+
+@pytest.mark.parametrize("lazy", [0, 1], ids=["eager-copies", "lazy-copies"])
+@pytest.mark.parametrize("batch,dim,L,N,groups,bf16", SSCAN_CASES)
+def test_operator_selective_scan_on_the_cpu_simulator(sim, batch, dim, L, N, groups, bf16, lazy):
+    from oracle import sscan as osscan
+    vp, fp, ci = ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int
+    sim.sim_sscan_ckpt_elems.restype, sim.sim_sscan_ckpt_elems.argtypes = ctypes.c_size_t, [ci] * 5
+    sim.sim_sscan_fwd.restype, sim.sim_sscan_fwd.argtypes = ctypes.c_char_p, [vp] * 9 + [ci] * 9
+    sim.sim_sscan_bwd.restype, sim.sim_sscan_bwd.argtypes = ctypes.c_char_p, [vp] * 16 + [ci] * 9
+    sim.sim_set_lazy(lazy)
+    g = torch.Generator().manual_seed(L + N)
+    u, delta = torch.randn(batch, dim, L, generator=g), torch.randn(batch, dim, L, generator=g)
+    A = -(0.3 + torch.rand(dim, N, generator=g))
+    Bm, Cm = torch.randn(batch, groups, N, L, generator=g), torch.randn(batch, groups, N, L, generator=g)
+    D, bias = 1 + 0.1 * torch.randn(dim, generator=g), torch.randn(dim, generator=g) - 2.0
+    dout = torch.randn(batch, dim, L, generator=g)
+    if bf16:
+        u, delta, Bm, Cm = [t.bfloat16().float() for t in (u, delta, Bm, Cm)]
+    code = _lib.BF16 if bf16 else _lib.F32
+    hu, hd, hB, hC = _dev(u, bf16), _dev(delta, bf16), _dev(Bm, bf16), _dev(Cm, bf16)
+    hA, hD, hb, hdo = _dev(A, False), _dev(D, False), _dev(bias, False), _dev(dout, False)
+    out = np.full((batch, dim, L), np.nan, np.float32)
+    ckpt = np.zeros(max(int(sim.sim_sscan_ckpt_elems(batch, dim, L, N, code)), 1), np.float32)
+    p = lambda a: a.ctypes.data
+    err = sim.sim_sscan_fwd(p(hu), p(hd), p(hA), p(hB), p(hC), p(hD), p(hb), p(out), p(ckpt), batch, dim, L, N, groups,
+                            code, _lib.F32, 1, 3)
+    assert err is None, err.decode()
+    f = lambda t: t.double().numpy()
+    ref = osscan.selective_scan_fwd(f(u), f(delta), f(A), f(Bm), f(Cm), f(D), f(bias), True)
+    rtol = 1e-2 if bf16 else 1e-3
+    _close(out, torch.from_numpy(ref), rtol, "out")
+    du = np.zeros((batch, dim, L), np.uint16 if bf16 else np.float32)
+    dd = np.zeros_like(du)
+    dA, dB, dC = np.zeros((dim, N), np.float32), np.zeros((batch, groups, N, L), np.float32), \
+        np.zeros((batch, groups, N, L), np.float32)
+    dD, db = np.zeros(dim, np.float32), np.zeros(dim, np.float32)
+    err = sim.sim_sscan_bwd(p(hu), p(hd), p(hA), p(hB), p(hC), p(hD), p(hb), p(hdo), p(ckpt), p(du), p(dd), p(dA), p(dB),
+                            p(dC), p(dD), p(db), batch, dim, L, N, groups, code, _lib.F32, 1, 3)
+    assert err is None, err.decode()
+    refg = osscan.selective_scan_bwd(f(u), f(delta), f(A), f(Bm), f(Cm), f(D), f(bias), f(dout), True)
+    got = [_host(du, bf16).numpy(), _host(dd, bf16).numpy(), dA, dB, dC, dD, db]
+    for name, a, b in zip(("du", "ddelta", "dA", "dB", "dC", "dD", "dbias"), got, refg):
+        _close(a, torch.from_numpy(np.asarray(b)), 2 * rtol, name)

@@ -218,15 +218,112 @@ def gen_kernel(rel, marker, tail):
     return out
 
 
+LAUNCH = re.compile(r"(\w+)<<<(.+?), (.+?), (.+?), st>>>\((.*?)\);")
+RED4 = re.compile(r'asm volatile\("red\.global\.add\.v4\.f32 \[%0\], \{%1, %2, %3, %4\};" ::"l"\((.*?)\), "f"\((.*?)\),\s*'
+                  r'"f"\((.*?)\), "f"\((.*?)\), "f"\((.*?)\)\s*: "memory"\);', re.S)
+
+SSCAN_DRIVER = r'''
+// C-ABI-shaped drivers of the operator selective-scan kernels: the argument / plan set-up of tramba_sscan_fwd / _bwd
+// (tramba_b200/csrc/capi.cu) followed by the translated launchers.
+#include "sscan.cuh"
+using namespace tramba;
+static int es_of(int dt) { return dt == TRAMBA_F32 ? 4 : 2; }
+static void fill_args(SScanArgs& a, const SScanPlan& p, int batch, int dim, int L, int N, int groups, int softplus) {
+    a.batch = batch, a.dim = dim, a.L = L, a.N = N, a.groups = groups, a.dpg = dim / groups;
+    a.rows = batch * dim;
+    a.R = p.R, a.cpu = p.cpu, a.units = p.units;
+    a.softplus = softplus ? 1 : 0;
+    a.uniform = p.uniform ? 1 : 0;
+    a.rpc = p.rpc;
+    a.rw = 1;
+    a.divL.init(static_cast<uint32_t>(L));
+    a.divDim.init(static_cast<uint32_t>(dim));
+    a.divDpg.init(static_cast<uint32_t>(dim / groups));
+}
+extern "C" size_t sim_sscan_ckpt_elems(int batch, int dim, int L, int N, int in_dtype) {
+    const SScanPlan p = make_sscan_plan(static_cast<long long>(batch) * dim, L, es_of(in_dtype));
+    return static_cast<size_t>(p.units) * p.cpu * N;
+}
+extern "C" const char* sim_sscan_fwd(const void* u, const void* delta, const float* A, const void* Bm, const void* Cm,
+                                     const float* D, const float* bias, void* out, float* ckpt, int batch, int dim,
+                                     int L, int N, int groups, int in_dtype, int out_dtype, int softplus, int sms) {
+    sim::sm_count = sms, sim::last_error = nullptr;
+    const SScanPlan p = make_sscan_plan(static_cast<long long>(batch) * dim, L, es_of(in_dtype));
+    SScanArgs a;
+    std::memset(&a, 0, sizeof(a));
+    a.u = u, a.delta = delta, a.A = A, a.Bm = Bm, a.Cm = Cm, a.D = D, a.bias = bias, a.out = out, a.ckpt = ckpt;
+    fill_args(a, p, batch, dim, L, N, groups, softplus);
+    const cudaError_t e = launch_sscan_fwd(a, p, in_dtype, out_dtype, nullptr);
+    return sim::last_error ? sim::last_error : (e == cudaSuccess ? nullptr : "launcher rejected the arguments");
+}
+extern "C" const char* sim_sscan_bwd(const void* u, const void* delta, const float* A, const void* Bm, const void* Cm,
+                                     const float* D, const float* bias, const void* dout, const float* ckpt, void* du,
+                                     void* ddelta, float* dA, float* dB, float* dC, float* dD, float* dbias, int batch,
+                                     int dim, int L, int N, int groups, int in_dtype, int dout_dtype, int softplus,
+                                     int sms) {
+    sim::sm_count = sms, sim::last_error = nullptr;
+    const SScanPlan p = make_sscan_plan(static_cast<long long>(batch) * dim, L, es_of(in_dtype));
+    const size_t nbc = static_cast<size_t>(batch) * groups * N * L * sizeof(float);
+    std::memset(dB, 0, nbc), std::memset(dC, 0, nbc), std::memset(dA, 0, static_cast<size_t>(dim) * N * sizeof(float));
+    if (dD) std::memset(dD, 0, static_cast<size_t>(dim) * sizeof(float));
+    if (dbias) std::memset(dbias, 0, static_cast<size_t>(dim) * sizeof(float));
+    SScanArgs a;
+    std::memset(&a, 0, sizeof(a));
+    a.u = u, a.delta = delta, a.A = A, a.Bm = Bm, a.Cm = Cm, a.D = D, a.bias = bias;
+    a.dout = dout, a.ckpt_in = ckpt, a.du = du, a.ddelta = ddelta;
+    a.dA = dA, a.dB = dB, a.dC = dC, a.dD = dD, a.dbias = dbias;
+    fill_args(a, p, batch, dim, L, N, groups, softplus);
+    if (p.regular) {                      // dB / dC pre-reduction over RW rows, as capi.cu chooses it
+        if (N == 1) {
+            const int rows_per_group = dim / groups;
+            for (int rw = 8; rw >= 1; rw >>= 1) {
+                if (rows_per_group % (rw * p.rpc) != 0) continue;
+                a.rw = rw;
+                if (p.units / rw >= 12ll * sms) break;
+            }
+        }
+    } else if (p.uniform && N == 1 && (dim / groups) % 8 == 0) {
+        a.rw = 8;
+    }
+    const cudaError_t e = launch_sscan_bwd(a, p, in_dtype, dout_dtype, nullptr);
+    return sim::last_error ? sim::last_error : (e == cudaSuccess ? nullptr : "launcher rejected the arguments");
+}
+'''
+
+
+def gen_whole_file(rel):
+    """A .cu file translated as a whole: kernels AND their host launchers (plan selection, template dispatch);
+    only the <<<...>>> launches, the shared-memory declaration and inline PTX are rewritten."""
+    s = open(os.path.join(CSRC, rel)).read()
+    s = s.replace("extern __shared__ __align__(128) unsigned char smem_raw[];", "unsigned char* smem_raw = sim::smem();")
+    s = LAUNCH.sub(r"sim::launch_kernel(\2, \3, \4, [&] { \1(\5); });", s)
+    s = RED4.sub(r"sim::red_add_v4(\1, \2, \3, \4, \5);", s)
+    assert "<<<" not in s and "asm" not in s.replace("__nv_bfloat16", ""), rel
+    out = os.path.join(GEN, os.path.basename(rel).replace(".cu", "_sim.cpp"))
+    open(out, "w").write(s)
+    return out
+
+
+def gen_sscan():
+    h = open(os.path.join(CSRC, "sscan.cuh")).read()
+    h = sub1(h, '#include "common.cuh"', '#include "sim_common.h"')
+    open(os.path.join(GEN, "sscan.cuh"), "w").write(h)
+    drv = os.path.join(GEN, "sscan_driver_sim.cpp")
+    open(drv, "w").write(SSCAN_DRIVER)
+    return [gen_whole_file("sscan_fwd.cu"), gen_whole_file("sscan_bwd.cu"), drv]
+
+
 def build(force=False):
     os.makedirs(GEN, exist_ok=True)
-    deps = [os.path.join(CSRC, k[0]) for k in KERNELS] + [os.path.join(CSRC, "ss2d_fused.cuh"),
+    deps = [os.path.join(CSRC, k[0]) for k in KERNELS] + [os.path.join(CSRC, f) for f in ("sscan.cuh", "sscan_fwd.cu",
+                                                                                         "sscan_bwd.cu")] + [
+        os.path.join(CSRC, "ss2d_fused.cuh"),
                                                           os.path.join(HERE, "sim_common.h"), os.path.join(HERE, "selftest.cpp"),
                                                           os.path.abspath(__file__)]
     if not force and os.path.exists(LIB) and all(os.path.getmtime(d) <= os.path.getmtime(LIB) for d in deps):
         return LIB
     gen_header()
-    srcs = [gen_kernel(*k) for k in KERNELS]
+    srcs = [gen_kernel(*k) for k in KERNELS] + gen_sscan()
     srcs.append(os.path.join(HERE, "selftest.cpp"))
     flags = ["-std=c++17", "-O1", "-fPIC", "-w", "-I" + HERE, "-I" + GEN, "-I" + os.path.join(ROOT, "include"),
              "-I/usr/local/cuda/include"]

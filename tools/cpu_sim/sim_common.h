@@ -56,7 +56,8 @@ struct Cta {
     std::unordered_map<const void*, std::vector<Copy>> bar_copies;     // lazy g2s copies, per mbarrier
     std::unordered_map<const void*, std::vector<long long>> bar_tx;    // ... and their complete_tx bytes (-1: an arrive)
     std::vector<std::vector<Copy>> thread_async;                       // cp.async issued, not yet bound to a barrier
-    std::vector<std::vector<Copy>> thread_stores;                      // lazy s2g bulk stores of each thread
+    std::vector<std::vector<Copy>> thread_stores;                      // lazy s2g bulk stores of each thread (open group)
+    std::vector<std::vector<std::vector<Copy>>> thread_groups;         // ... and its committed bulk async-groups, oldest first
     unsigned char* smem = nullptr;
     ucontext_t sched;
     std::vector<ucontext_t> ctx;
@@ -184,10 +185,21 @@ inline void s2g(void* dst, const void* src, size_t bytes) {
     if (!lazy) std::memcpy(dst, src, bytes);
     else g->thread_stores[g->cur].push_back(Copy{dst, src, bytes});
 }
-inline void drain_stores() {                                            // cp.async.bulk.wait_group[.read] 0
-    auto& q = g->thread_stores[g->cur];
-    for (const Copy& c : q) std::memcpy(c.dst, c.src, c.bytes);
-    q.clear();
+inline void commit_stores() {                                           // cp.async.bulk.commit_group
+    auto& open = g->thread_stores[g->cur];
+    g->thread_groups[g->cur].push_back(open);
+    open.clear();
+}
+inline void drain_stores(size_t keep) {                                 // cp.async.bulk.wait_group[.read] N
+    auto& groups = g->thread_groups[g->cur];
+    while (groups.size() > keep) {
+        for (const Copy& c : groups.front()) std::memcpy(c.dst, c.src, c.bytes);
+        groups.erase(groups.begin());
+    }
+}
+inline void drain_all_stores() {                                        // thread exit: everything in flight completes
+    commit_stores();
+    drain_stores(0);
 }
 
 // Runs `body` as grid x nthreads CUDA threads, CTA after CTA.  Returns nullptr or an error string.
@@ -205,7 +217,7 @@ inline const char* launch(int grid, int nthreads, size_t smem_bytes, std::functi
         cta.smem = static_cast<unsigned char*>(raw);
         std::memset(cta.smem, 0xCD, smem_bytes);   // poison: uninitialised shared memory must not go unnoticed
         cta.ctx.resize(nthreads), cta.done.assign(nthreads, 0), cta.warps.resize((nthreads + 31) / 32);
-        cta.thread_async.resize(nthreads), cta.thread_stores.resize(nthreads);
+        cta.thread_async.resize(nthreads), cta.thread_stores.resize(nthreads), cta.thread_groups.resize(nthreads);
         g = &cta;
         for (int t = 0; t < nthreads; ++t) {
             getcontext(&cta.ctx[t]);
@@ -214,7 +226,7 @@ inline const char* launch(int grid, int nthreads, size_t smem_bytes, std::functi
             cta.ctx[t].uc_link = &cta.sched;
             makecontext(&cta.ctx[t], reinterpret_cast<void (*)()>(+[]() {
                             (*g_body)();
-                            drain_stores();          // a store still in flight at exit completes eventually
+                            drain_all_stores();      // a store still in flight at exit completes eventually
                             g->done[g->cur] = 1;
                             ++g->progress;
                         }),
@@ -239,7 +251,36 @@ inline const char* launch(int grid, int nthreads, size_t smem_bytes, std::functi
     return err;
 }
 
+// ---- what the host launchers of a translated .cu file see instead of the CUDA runtime
+inline int sm_count = 3;                 // cudaDevAttrMultiProcessorCount: small grids keep the simulation quick
+inline const char* last_error = nullptr; // first simulator error of the current driver call
+template <typename F>
+inline void launch_kernel(int grid, int block, size_t smem_bytes, F&& body) {
+    const char* e = launch(grid, block, smem_bytes, std::function<void()>(body));
+    if (e && !last_error) last_error = e;
+}
+inline void red_add_v4(float* p, float a, float b, float c, float d) { p[0] += a, p[1] += b, p[2] += c, p[3] += d; }
+
 }  // namespace sim
+
+template <typename K>
+inline cudaError_t cudaFuncSetAttribute(K, cudaFuncAttribute, int) {
+    return cudaSuccess;
+}
+inline cudaError_t cudaGetDevice(int* dev) {
+    *dev = 0;
+    return cudaSuccess;
+}
+inline cudaError_t cudaDeviceGetAttribute(int* v, cudaDeviceAttr attr, int) {
+    *v = attr == cudaDevAttrMultiProcessorCount ? sim::sm_count : 0;
+    return cudaSuccess;
+}
+inline cudaError_t cudaGetLastError() { return sim::last_error ? cudaErrorLaunchFailure : cudaSuccess; }
+template <typename K>
+inline cudaError_t cudaOccupancyMaxActiveBlocksPerMultiprocessor(int* n, K, int, size_t) {
+    *n = 1;
+    return cudaSuccess;
+}
 
 // ---------------------------------------------------------------------------------------------- CUDA surface
 #define threadIdx (sim::tidx())
@@ -259,10 +300,20 @@ inline float __shfl_xor_sync(unsigned, float v, int mask, int width = 32) {
     const int lane = sim::g->cur & 31, src = lane ^ mask;
     return sim::u2f(sim::shfl(sim::f2u(v), (src / width) == (lane / width) ? src : -1));
 }
+inline float __shfl_sync(unsigned, float v, int src_lane, int width = 32) {
+    const int lane = sim::g->cur & 31;
+    return sim::u2f(sim::shfl(sim::f2u(v), (lane / width) * width + (src_lane % width)));
+}
+inline void __syncwarp(unsigned = 0xffffffffu) { sim::warp_barrier(); }
+inline uint32_t __umulhi(uint32_t a, uint32_t b) { return static_cast<uint32_t>((static_cast<uint64_t>(a) * b) >> 32); }
+using std::max;
+using std::min;
 template <typename T>
 inline T __ldg(const T* p) {
     return *p;
 }
+inline float __int_as_float(int i) { return sim::u2f(static_cast<uint32_t>(i)); }
+inline int __float_as_int(float f) { return static_cast<int>(sim::f2u(f)); }
 inline float __uint_as_float(uint32_t u) { return sim::u2f(u); }
 inline uint32_t __float_as_uint(float f) { return sim::f2u(f); }
 inline float atomicAdd(float* p, float v) {
@@ -307,21 +358,20 @@ inline void bulk_s2g(void* dst_gmem, const void* src_smem, uint32_t bytes) {
         sim::g->error = "bulk_s2g: address or size not a multiple of 16 bytes";
     sim::s2g(dst_gmem, src_smem, bytes);
 }
-inline void bulk_commit() {}
+inline void bulk_commit() { sim::commit_stores(); }
 template <int N>
 inline void bulk_wait_read() {
-    static_assert(N == 0, "the kernels only wait for all groups");
-    sim::drain_stores();
+    sim::drain_stores(N);
 }
 template <int N>
 inline void bulk_wait_all() {
-    static_assert(N == 0, "the kernels only wait for all groups");
-    sim::drain_stores();
+    sim::drain_stores(N);
 }
 
 // ---- math (libm instead of the .approx MUFU ops: differences are far below the parity tolerance)
 inline float ex2f(float x) { return exp2f(x); }
 inline float lg2f(float x) { return log2f(x); }
+inline float rcpf(float x) { return 1.0f / x; }
 inline float softplus20(float x, float& e_out, float& w_out) {
     const float e = ex2f(x * kLog2e);
     const float w = 1.0f + e;
