@@ -251,3 +251,60 @@ def test_operator_selective_scan_on_the_cpu_simulator(sim, batch, dim, L, N, gro
     got = [_host(du, bf16).numpy(), _host(dd, bf16).numpy(), dA, dB, dC, dD, db]
     for name, a, b in zip(("du", "ddelta", "dA", "dB", "dC", "dD", "dbias"), got, refg):
         _close(a, torch.from_numpy(np.asarray(b)), 2 * rtol, name)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# table-driven cross-scan / cross-merge (csrc/cross_scan.cu, translated whole): every order family, including the
+# ablation orders whose merge configuration (permutation vs CSR path) was added without a GPU at hand
+SCAN_FAMS = {"std": (_lib.ORDER_STD, 0), "dilation": (_lib.ORDER_DILATION, 4), "window": (_lib.ORDER_WINDOW, None),
+             "line": (_lib.ORDER_LINE, 0), "line4": (_lib.ORDER_LINE4, 0), "spiral": (_lib.ORDER_SPIRAL, 0),
+             "hilbert": (_lib.ORDER_HILBERT, 0), "diagonal": (_lib.ORDER_DIAGONAL, 0), "ds": (_lib.ORDER_DS, 0),
+             "ab2": (_lib.ORDER_AB2, 0), "ab1": (_lib.ORDER_AB1, 0), "custom": (_lib.ORDER_CUSTOM, 0)}
+
+
+SCAN_CASES = [(f, H, B, C, bf) for f in SCAN_FAMS for (H, B, C, bf) in ((12, 2, 3, False), (24, 1, 5, True),
+                                                                         (96, 1, 2, False))]
+SCAN_CASES += [(f, 192, 1, 1, False) for f in ("dilation", "line", "ds")]   # planes too large to stage: the direct kernel
+
+
+@pytest.mark.parametrize("fam,H,B,C,bf16", SCAN_CASES)
+def test_cross_scan_merge_on_the_cpu_simulator(sim, fam, H, B, C, bf16):
+    """Bit-exact against the oracle (gather; sequential fp32 sums in the reference's association order for
+    std / dilation / window / line, sequential over k for the ablation and custom orders)."""
+    from oracle import scan_orders as so
+    from tramba_b200 import ops
+    vp, ci = ctypes.c_void_p, ctypes.c_int
+    for fn in (sim.sim_cross_scan, sim.sim_cross_merge):
+        fn.restype, fn.argtypes = ctypes.c_char_p, [vp, vp, vp] + [ci] * 7
+    sim.sim_set_lazy(0)
+    order, param = SCAN_FAMS[fam]
+    if fam == "window":
+        param = {12: 4, 24: 8, 96: 16}[H]
+    L = H * H
+    rs = np.random.RandomState(H + C)
+    if H == 192:
+        ops.line_sizes.append(192) if 192 not in ops.line_sizes else None
+    if fam == "custom":
+        tab = rs.randint(0, L, size=(3, L)).astype(np.int64)            # arbitrary table with repeats
+        K, plan_t = ops._custom_plan(tab, "cpu")
+        plan = plan_t.numpy()
+    else:
+        tab = so.order_table(fam, H, param)
+        K, plan = ops.order_plan_host(order, H, param)
+    x = torch.from_numpy(rs.standard_normal((B, C, H, H)).astype(np.float32))
+    ys = torch.from_numpy(rs.standard_normal((B, K, C, L)).astype(np.float32))
+    if bf16:
+        x, ys = x.bfloat16().float(), ys.bfloat16().float()
+    code = _lib.BF16 if bf16 else _lib.F32
+    hx, hys = _dev(x, bf16), _dev(ys, bf16)
+    xs = np.zeros((B, K, C, L), hx.dtype)
+    y = np.zeros((B, C, L), hx.dtype)
+    err = sim.sim_cross_scan(hx.ctypes.data, xs.ctypes.data, plan.ctypes.data, order, K, B, C, H, H, code)
+    assert err is None, err.decode()
+    assert np.array_equal(_host(xs, bf16).numpy(), so.cross_scan(x.numpy(), tab))
+    err = sim.sim_cross_merge(hys.ctypes.data, y.ctypes.data, plan.ctypes.data, order, K, B, C, H, H, code)
+    assert err is None, err.decode()
+    want = so.cross_merge(ys.numpy(), tab, fam if fam in ("std", "dilation", "window", "line") else "custom")
+    if bf16:
+        want = torch.from_numpy(want).bfloat16().float().numpy()           # fp32 sums, one rounding
+    assert np.array_equal(_host(y, bf16).numpy(), want)

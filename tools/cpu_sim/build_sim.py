@@ -218,7 +218,8 @@ def gen_kernel(rel, marker, tail):
     return out
 
 
-LAUNCH = re.compile(r"(\w+)<<<(.+?), (.+?), (.+?), st>>>\((.*?)\);")
+LAUNCH = re.compile(r"([\w:]+(?:<[^<>;]*>)?)<<<(.+?), (.+?), (.+?), st>>>\((.*?)\);", re.S)
+SHARED = re.compile(r"extern __shared__ (?:__align__\(\d+\) )?(\w+(?: \w+)?) (\w+)\[\];")
 RED4 = re.compile(r'asm volatile\("red\.global\.add\.v4\.f32 \[%0\], \{%1, %2, %3, %4\};" ::"l"\((.*?)\), "f"\((.*?)\),\s*'
                   r'"f"\((.*?)\), "f"\((.*?)\), "f"\((.*?)\)\s*: "memory"\);', re.S)
 
@@ -295,13 +296,48 @@ def gen_whole_file(rel):
     """A .cu file translated as a whole: kernels AND their host launchers (plan selection, template dispatch);
     only the <<<...>>> launches, the shared-memory declaration and inline PTX are rewritten."""
     s = open(os.path.join(CSRC, rel)).read()
-    s = s.replace("extern __shared__ __align__(128) unsigned char smem_raw[];", "unsigned char* smem_raw = sim::smem();")
+    s = SHARED.sub(r"\1* \2 = reinterpret_cast<\1*>(sim::smem());", s)
     s = LAUNCH.sub(r"sim::launch_kernel(\2, \3, \4, [&] { \1(\5); });", s)
     s = RED4.sub(r"sim::red_add_v4(\1, \2, \3, \4, \5);", s)
-    assert "<<<" not in s and "asm" not in s.replace("__nv_bfloat16", ""), rel
+    assert "<<<" not in s and "__shared__" not in s and "asm" not in s.replace("__nv_bfloat16", ""), rel
     out = os.path.join(GEN, os.path.basename(rel).replace(".cu", "_sim.cpp"))
     open(out, "w").write(s)
     return out
+
+
+SCAN_DRIVER = r'''
+// C-ABI-shaped drivers of the table-driven cross-scan / cross-merge kernels (csrc/cross_scan.cu): what
+// tramba_cross_scan / tramba_cross_merge do after argument validation.
+#include "sim_common.h"
+namespace tramba {
+cudaError_t launch_cross_scan(const void* x, void* xs, const int32_t* plan, int K, int B, int C, int L, int dtype,
+                              cudaStream_t st);
+cudaError_t launch_cross_merge(const void* ys, void* y, const int32_t* plan, int order, int K, int B, int D, int L,
+                               int dtype, cudaStream_t st);
+}
+extern "C" const char* sim_cross_scan(const void* x, void* xs, const int32_t* plan, int order, int K, int B, int C, int H,
+                                      int W, int dtype) {
+    sim::last_error = nullptr;
+    const cudaError_t e = tramba::launch_cross_scan(x, xs, plan, K, B, C, H * W, dtype, nullptr);
+    return sim::last_error ? sim::last_error : (e == cudaSuccess ? nullptr : "launcher rejected the arguments");
+}
+extern "C" const char* sim_cross_merge(const void* ys, void* y, const int32_t* plan, int order, int K, int B, int D, int H,
+                                       int W, int dtype) {
+    sim::last_error = nullptr;
+    const cudaError_t e = tramba::launch_cross_merge(ys, y, plan, order, K, B, D, H * W, dtype, nullptr);
+    return sim::last_error ? sim::last_error : (e == cudaSuccess ? nullptr : "launcher rejected the arguments");
+}
+'''
+
+
+def gen_scan():
+    src = gen_whole_file("cross_scan.cu")
+    t = open(src).read()
+    t = sub1(t, '#include "common.cuh"', '#include "sim_common.h"')
+    open(src, "w").write(t)
+    drv = os.path.join(GEN, "scan_driver_sim.cpp")
+    open(drv, "w").write(SCAN_DRIVER)
+    return [src, drv]
 
 
 def gen_sscan():
@@ -316,14 +352,14 @@ def gen_sscan():
 def build(force=False):
     os.makedirs(GEN, exist_ok=True)
     deps = [os.path.join(CSRC, k[0]) for k in KERNELS] + [os.path.join(CSRC, f) for f in ("sscan.cuh", "sscan_fwd.cu",
-                                                                                         "sscan_bwd.cu")] + [
+                                                                                         "sscan_bwd.cu", "cross_scan.cu")] + [
         os.path.join(CSRC, "ss2d_fused.cuh"),
                                                           os.path.join(HERE, "sim_common.h"), os.path.join(HERE, "selftest.cpp"),
                                                           os.path.abspath(__file__)]
     if not force and os.path.exists(LIB) and all(os.path.getmtime(d) <= os.path.getmtime(LIB) for d in deps):
         return LIB
     gen_header()
-    srcs = [gen_kernel(*k) for k in KERNELS] + gen_sscan()
+    srcs = [gen_kernel(*k) for k in KERNELS] + gen_sscan() + gen_scan()
     srcs.append(os.path.join(HERE, "selftest.cpp"))
     flags = ["-std=c++17", "-O1", "-fPIC", "-w", "-I" + HERE, "-I" + GEN, "-I" + os.path.join(ROOT, "include"),
              "-I/usr/local/cuda/include"]

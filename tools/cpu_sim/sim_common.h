@@ -18,6 +18,7 @@
 #pragma once
 #include <cuda_bf16.h>
 #include <driver_types.h>
+#include <vector_types.h>
 #include <stdint.h>
 #include <ucontext.h>
 
