@@ -1,12 +1,18 @@
-"""The fused SS2D kernels executed on the CPU (tools/cpu_sim: the CUDA sources compiled as host code, every CUDA
-thread a cooperative fiber, inline PTX replaced by functional equivalents) against the float64 oracle composition
-CrossScan -> selective scan -> CrossMerge (tests/_fused_oracle.py).
+"""The library's CUDA kernels executed on the CPU (tools/cpu_sim: the .cu sources compiled as host code, every CUDA
+thread a cooperative fiber, inline PTX and <<<>>> launches replaced by functional equivalents) against the oracle.
 
-Covers what can be known without a GPU: index arithmetic, work decomposition over CTAs / rounds / items, the
-three-level scan and its carries, barrier and mbarrier protocols (a mismatch is reported as a deadlock), and the
-numerics of the recurrence -- for the product kernels (GPU-verified in tests/test_gpu_fused.py; here they validate
-the simulator) and for the compile-time-geometry candidates under csrc/next/ (not yet run on a GPU; here they
-must reproduce the product kernels bit for bit).  Asynchrony, memory ordering and performance are out of its reach."""
+  fused SS2D core fwd / bwd and the skewed merge          product kernels AND the candidates under csrc/next/
+  operator selective scan fwd / bwd (sscan_*.cu)          whole files: kernels + host launchers, every plan type
+  table-driven cross-scan / cross-merge (cross_scan.cu)   every order family incl. ablation orders and caller tables
+  depthwise conv (+ SiLU) fwd / bwd, projected-channel gather / scatter
+
+Covers what can be known without a GPU: index arithmetic, work decomposition over CTAs / rounds / items, the scans
+and their carries, barrier and mbarrier protocols (a mismatch is reported as a deadlock), asynchronous-copy
+discipline at both extremes (copies landing at issue / only at the wait), and the numerics of the recurrences.  The
+product kernels are GPU-verified (tests/test_gpu_*.py): here they validate the simulator, and protect later edits;
+the candidates (not yet run on a GPU) must reproduce the product kernels bit for bit.  Interleavings between the two
+copy extremes, memory-model ordering and performance are out of its reach; LayerNorm2d (clusters / DSMEM) and the
+tensor-pipe DCT (mma.sync) are not translated."""
 import ctypes
 import importlib.util
 import os
@@ -308,3 +314,78 @@ def test_cross_scan_merge_on_the_cpu_simulator(sim, fam, H, B, C, bf16):
     if bf16:
         want = torch.from_numpy(want).bfloat16().float().numpy()           # fp32 sums, one rounding
     assert np.array_equal(_host(y, bf16).numpy(), want)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# either side of the core: depthwise conv (+ SiLU) and the projected-channel gather / scatter
+@pytest.mark.parametrize("B,C,H,k,act,bf16", [(2, 6, 24, 3, "silu", False), (1, 5, 12, 3, "silu", True),
+                                              (1, 4, 48, 7, "none", False), (2, 3, 96, 3, "silu", False),
+                                              (1, 2, 24, 5, "silu", False)])
+def test_dwconv_on_the_cpu_simulator(sim, B, C, H, k, act, bf16):
+    from oracle import dwconv as odw
+    vp, ci = ctypes.c_void_p, ctypes.c_int
+    sim.sim_dwconv2d_fwd.restype, sim.sim_dwconv2d_fwd.argtypes = ctypes.c_char_p, [vp] * 4 + [ci] * 7
+    sim.sim_dwconv2d_bwd.restype, sim.sim_dwconv2d_bwd.argtypes = ctypes.c_char_p, [vp] * 6 + [ci] * 7
+    sim.sim_set_lazy(0)
+    g = torch.Generator().manual_seed(H + k)
+    x, dy = torch.randn(B, C, H, H, generator=g), torch.randn(B, C, H, H, generator=g)
+    w, b = 0.3 * torch.randn(C, 1, k, k, generator=g), 0.1 * torch.randn(C, generator=g)
+    if bf16:
+        x, dy = x.bfloat16().float(), dy.bfloat16().float()
+    code, actc = (_lib.BF16 if bf16 else _lib.F32), (_lib.ACT_SILU if act == "silu" else _lib.ACT_NONE)
+    hx, hdy, hw, hb = _dev(x, bf16), _dev(dy, bf16), _dev(w, False), _dev(b, False)
+    y, dx = np.zeros_like(hx), np.zeros_like(hx)
+    part = np.full((B, C, k * k + 1), np.nan, np.float32)
+    p = lambda a: a.ctypes.data
+    err = sim.sim_dwconv2d_fwd(p(hx), p(hw), p(hb), p(y), B, C, H, H, k, actc, code)
+    assert err is None, err.decode()
+    err = sim.sim_dwconv2d_bwd(p(hx), p(hw), p(hb), p(hdy), p(dx), p(part), B, C, H, H, k, actc, code)
+    assert err is None, err.decode()
+    f = lambda t: t.double().numpy()
+    rtol = 1e-2 if bf16 else 1e-4
+    _close(_host(y, bf16).numpy(), torch.from_numpy(odw.dwconv_fwd(f(x), f(w), f(b), act)), rtol, "y")
+    gx, gw, gb = odw.dwconv_bwd(f(dy), f(x), f(w), f(b), act)
+    _close(_host(dx, bf16).numpy(), torch.from_numpy(gx), rtol, "dx")
+    _close(part.sum(0)[:, :k * k].reshape(C, 1, k, k), torch.from_numpy(gw), 10 * rtol, "dw")
+    _close(part.sum(0)[:, k * k], torch.from_numpy(gb), 10 * rtol, "db")
+
+
+@pytest.mark.parametrize("fam,H,R,N,bf16", [("std", 12, 2, 1, False), ("line", 24, 2, 1, True),
+                                            ("window", 24, 4, 2, False), ("dilation", 96, 8, 1, False)])
+def test_proj_gather_scatter_on_the_cpu_simulator(sim, fam, H, R, N, bf16):
+    from oracle import scan_orders as so
+    from tramba_b200 import ops
+    vp, ci = ctypes.c_void_p, ctypes.c_int
+    sim.sim_proj_gather.restype, sim.sim_proj_gather.argtypes = ctypes.c_char_p, [vp] * 5 + [ci] * 6
+    sim.sim_proj_scatter.restype, sim.sim_proj_scatter.argtypes = ctypes.c_char_p, [vp] * 5 + [ci] * 7
+    sim.sim_set_lazy(0)
+    order, param = SCAN_FAMS[fam]
+    if fam == "window":
+        param = 8
+    L, B = H * H, 2
+    tab = so.order_table(fam, H, param)
+    K, plan = ops.order_plan_host(order, H, param)
+    CX = R + 2 * N
+    rs = np.random.RandomState(H)
+    src = torch.from_numpy(rs.randint(-8, 9, size=(B, K, CX, L)).astype(np.float32))      # exact in bf16 too
+    hsrc = _dev(src, bf16)
+    code = _lib.BF16 if bf16 else _lib.F32
+    dts, Bs, Cs = (np.zeros((B, K, n, L), hsrc.dtype) for n in (R, N, N))
+    p = lambda a: a.ctypes.data
+    err = sim.sim_proj_gather(p(hsrc), p(dts), p(Bs), p(Cs), p(plan), K, B, R, N, L, code)
+    assert err is None, err.decode()
+    want = np.stack([src.numpy()[:, k][:, :, tab[k]] for k in range(K)], axis=1)
+    got = np.concatenate([_host(a, bf16).numpy() for a in (dts, Bs, Cs)], axis=2)
+    assert np.array_equal(got, want)
+    # adjoint: scatter(gather-shaped gradients) == transpose, exact on small integers; fp32 B / C gradients
+    gB, gC = (rs.randint(-8, 9, size=(B, K, N, L)).astype(np.float32) for _ in range(2))
+    gsrc = np.zeros_like(hsrc)
+    err = sim.sim_proj_scatter(p(dts), p(gB), p(gC), p(gsrc), p(plan), K, B, R, N, L, code, _lib.F32)
+    assert err is None, err.decode()
+    g = np.concatenate([_host(dts, bf16).numpy(), gB, gC], axis=2)
+    ref = np.zeros((B, K, CX, L), np.float32)
+    for k in range(K):
+        np.add.at(ref[:, k], (slice(None), slice(None), tab[k]), g[:, k])
+    if bf16:
+        ref = torch.from_numpy(ref).bfloat16().float().numpy()
+    assert np.array_equal(_host(gsrc, bf16).numpy(), ref)

@@ -340,6 +340,58 @@ def gen_scan():
     return [src, drv]
 
 
+SIDE_DRIVER = r'''
+// C-ABI-shaped drivers of the depthwise-convolution and projected-channel kernels (csrc/dwconv2d.cu, proj_gather.cu).
+#include "sim_common.h"
+namespace tramba {
+cudaError_t launch_dwconv2d_fwd(const void* x, const float* w, const float* b, void* y, int B, int C, int H, int W,
+                                int K, int act, int dtype, cudaStream_t st);
+cudaError_t launch_dwconv2d_bwd(const void* x, const float* w, const float* b, const void* dy, void* dx, float* dwp,
+                                int B, int C, int H, int W, int K, int act, int dtype, cudaStream_t st);
+cudaError_t launch_proj_gather(const void* src, void* dts, void* Bs, void* Cs, const int32_t* plan, int K, int B, int R,
+                               int N, int L, int dtype, cudaStream_t st);
+cudaError_t launch_proj_scatter(const void* gdts, const void* gBs, const void* gCs, void* gsrc, const int32_t* plan,
+                                int K, int B, int R, int N, int L, int dtype, int bc_dtype, cudaStream_t st);
+}
+static const char* done(cudaError_t e) {
+    return sim::last_error ? sim::last_error : (e == cudaSuccess ? nullptr : "launcher rejected the arguments");
+}
+extern "C" const char* sim_dwconv2d_fwd(const void* x, const float* w, const float* b, void* y, int B, int C, int H, int W,
+                                        int K, int act, int dtype) {
+    sim::last_error = nullptr;
+    return done(tramba::launch_dwconv2d_fwd(x, w, b, y, B, C, H, W, K, act, dtype, nullptr));
+}
+extern "C" const char* sim_dwconv2d_bwd(const void* x, const float* w, const float* b, const void* dy, void* dx,
+                                        float* dwp, int B, int C, int H, int W, int K, int act, int dtype) {
+    sim::last_error = nullptr;
+    return done(tramba::launch_dwconv2d_bwd(x, w, b, dy, dx, dwp, B, C, H, W, K, act, dtype, nullptr));
+}
+extern "C" const char* sim_proj_gather(const void* src, void* dts, void* Bs, void* Cs, const int32_t* plan, int K, int B,
+                                       int R, int N, int L, int dtype) {
+    sim::last_error = nullptr;
+    return done(tramba::launch_proj_gather(src, dts, Bs, Cs, plan, K, B, R, N, L, dtype, nullptr));
+}
+extern "C" const char* sim_proj_scatter(const void* gdts, const void* gBs, const void* gCs, void* gsrc,
+                                        const int32_t* plan, int K, int B, int R, int N, int L, int dtype, int bc_dtype) {
+    sim::last_error = nullptr;
+    return done(tramba::launch_proj_scatter(gdts, gBs, gCs, gsrc, plan, K, B, R, N, L, dtype, bc_dtype, nullptr));
+}
+'''
+
+
+def gen_side():
+    out = []
+    for rel in ("dwconv2d.cu", "proj_gather.cu"):
+        src = gen_whole_file(rel)
+        t = open(src).read()
+        t = sub1(t, '#include "common.cuh"', '#include "sim_common.h"')
+        open(src, "w").write(t)
+        out.append(src)
+    drv = os.path.join(GEN, "side_driver_sim.cpp")
+    open(drv, "w").write(SIDE_DRIVER)
+    return out + [drv]
+
+
 def gen_sscan():
     h = open(os.path.join(CSRC, "sscan.cuh")).read()
     h = sub1(h, '#include "common.cuh"', '#include "sim_common.h"')
@@ -352,14 +404,15 @@ def gen_sscan():
 def build(force=False):
     os.makedirs(GEN, exist_ok=True)
     deps = [os.path.join(CSRC, k[0]) for k in KERNELS] + [os.path.join(CSRC, f) for f in ("sscan.cuh", "sscan_fwd.cu",
-                                                                                         "sscan_bwd.cu", "cross_scan.cu")] + [
+                                                                                         "sscan_bwd.cu", "cross_scan.cu", "dwconv2d.cu",
+                                                                                         "proj_gather.cu")] + [
         os.path.join(CSRC, "ss2d_fused.cuh"),
                                                           os.path.join(HERE, "sim_common.h"), os.path.join(HERE, "selftest.cpp"),
                                                           os.path.abspath(__file__)]
     if not force and os.path.exists(LIB) and all(os.path.getmtime(d) <= os.path.getmtime(LIB) for d in deps):
         return LIB
     gen_header()
-    srcs = [gen_kernel(*k) for k in KERNELS] + gen_sscan() + gen_scan()
+    srcs = [gen_kernel(*k) for k in KERNELS] + gen_sscan() + gen_scan() + gen_side()
     srcs.append(os.path.join(HERE, "selftest.cpp"))
     flags = ["-std=c++17", "-O1", "-fPIC", "-w", "-I" + HERE, "-I" + GEN, "-I" + os.path.join(ROOT, "include"),
              "-I/usr/local/cuda/include"]

@@ -19,6 +19,7 @@
 #include <cuda_bf16.h>
 #include <driver_types.h>
 #include <vector_types.h>
+#include <vector_functions.h>
 #include <stdint.h>
 #include <ucontext.h>
 
