@@ -389,3 +389,83 @@ def test_proj_gather_scatter_on_the_cpu_simulator(sim, fam, H, R, N, bf16):
     if bf16:
         ref = torch.from_numpy(ref).bfloat16().float().numpy()
     assert np.array_equal(_host(gsrc, bf16).numpy(), ref)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# LayerNorm2d (+ GELU): the register-resident CLUSTER kernels (cluster.sync, distributed shared memory) and the
+# streaming fallback; DCT2D on the tensor pipe (mma.sync m16n8k8 TF32 emulated fragment by fragment) and SIMT
+@pytest.mark.parametrize("B,C,L,act,in_bf16,out_bf16,sms", [
+    (2, 32, 576, "gelu", False, False, 3),      # few channels: one CTA per tile
+    (1, 256, 144, "none", False, True, 148),    # many channels, small map: cluster of CTAs over the channels (DSMEM)
+    (2, 128, 2304, "gelu", True, False, 8),
+    (1, 64, 50, "none", False, False, 3),       # odd L: streaming kernels
+    (1, 512, 144, "gelu", False, False, 148),
+])
+def test_layernorm2d_on_the_cpu_simulator(sim, B, C, L, act, in_bf16, out_bf16, sms):
+    from oracle import layernorm2d as oln
+    vp, ci = ctypes.c_void_p, ctypes.c_int
+    sim.sim_layernorm2d_tiles.restype, sim.sim_layernorm2d_tiles.argtypes = ci, [ci] * 4
+    sim.sim_layernorm2d_fwd.restype = ctypes.c_char_p
+    sim.sim_layernorm2d_fwd.argtypes = [vp] * 6 + [ci] * 3 + [ctypes.c_float] + [ci] * 4
+    sim.sim_layernorm2d_bwd.restype, sim.sim_layernorm2d_bwd.argtypes = ctypes.c_char_p, [vp] * 9 + [ci] * 7
+    sim.sim_set_lazy(0)
+    g = torch.Generator().manual_seed(C + L)
+    x = torch.randn(B, C, L, generator=g) * 2 + 0.5
+    gy = torch.randn(B, C, L, generator=g)
+    w, b = 1 + 0.1 * torch.randn(C, generator=g), 0.1 * torch.randn(C, generator=g)
+    if in_bf16:
+        x = x.bfloat16().float()
+    actc = _lib.ACT_GELU if act == "gelu" else _lib.ACT_NONE
+    ic, oc = (_lib.BF16 if in_bf16 else _lib.F32), (_lib.BF16 if out_bf16 else _lib.F32)
+    hx, hw, hb, hgy = _dev(x, in_bf16), _dev(w, False), _dev(b, False), _dev(gy, False)
+    y = np.zeros((B, C, L), np.uint16 if out_bf16 else np.float32)
+    mean, rstd = np.zeros((B, L), np.float32), np.zeros((B, L), np.float32)
+    p = lambda a: a.ctypes.data
+    err = sim.sim_layernorm2d_fwd(p(hx), p(hw), p(hb), p(y), p(mean), p(rstd), B, C, L, 1e-5, actc, ic, oc, sms)
+    assert err is None, err.decode()
+    f = lambda t: t.double().numpy()
+    _close(_host(y, out_bf16).numpy(), torch.from_numpy(oln.layernorm2d_fwd(f(x), f(w), f(b), 1e-5, act)),
+           1e-2 if out_bf16 else 1e-4, "y")
+    tiles = sim.sim_layernorm2d_tiles(B, C, L, sms)
+    assert tiles > 0
+    gx = np.zeros_like(hx)
+    gw, gb = np.full((B * tiles, C), np.nan, np.float32), np.full((B * tiles, C), np.nan, np.float32)
+    err = sim.sim_layernorm2d_bwd(p(hgy), p(hx), p(hw), p(hb), p(mean), p(rstd), p(gx), p(gw), p(gb), B, C, L, actc, ic,
+                                  _lib.F32, sms)
+    assert err is None, err.decode()
+    rx, rw, rb = oln.layernorm2d_bwd(f(gy), f(x), f(w), f(b), 1e-5, act)
+    _close(_host(gx, in_bf16).numpy(), torch.from_numpy(rx), 1e-2 if in_bf16 else 2e-4, "gx")
+    _close(gw.sum(0), torch.from_numpy(rw), 1e-3, "gw")
+    _close(gb.sum(0), torch.from_numpy(rb), 1e-3, "gb")
+    sim.sim_last_cluster_size.restype = ci
+    cs = sim.sim_last_cluster_size()
+    if (C, L, sms) in ((256, 144, 148), (512, 144, 148)):
+        assert cs > 1, "expected the cluster / DSMEM kernels for many channels on a small map"
+    if L % 2:
+        assert cs == 1            # odd L: streaming kernels
+
+
+@pytest.mark.parametrize("planes,H,tc", [(3, 24, 1), (2, 48, 1), (1, 96, 1), (2, 12, 0), (3, 24, 0)])
+def test_dct2d_on_the_cpu_simulator(sim, planes, H, tc):
+    from oracle import dct as odct
+    vp, ci = ctypes.c_void_p, ctypes.c_int
+    sim.sim_dct2d.restype, sim.sim_dct2d.argtypes = ctypes.c_char_p, [ci, ci] + [vp] * 6 + [ci] * 3
+    for lazy in (0, 1):          # the tensor-pipe kernel double-buffers its planes with cp.async groups
+        sim.sim_set_lazy(lazy)
+        rs = np.random.RandomState(H)
+        x = rs.standard_normal((1, planes, H, H)).astype(np.float32)
+        w = np.empty((H, H), np.float32)
+        _lib.lib.tramba_dct_basis(H, w.ctypes.data)
+        hi, lo = np.zeros((planes, H // 2, H // 2), np.float32), np.zeros((planes, H // 2, H // 2), np.float32)
+        p = lambda a: a.ctypes.data
+        err = sim.sim_dct2d(0, tc, p(x), None, p(w), p(w), p(hi), p(lo), planes, H, H)
+        assert err is None, err.decode()
+        rhi, rlo = odct.dct2d_split(x.astype(np.float64))
+        _close(hi, torch.from_numpy(np.ascontiguousarray(rhi[0])), 1e-5, "high")
+        _close(lo, torch.from_numpy(np.ascontiguousarray(rlo[0])), 1e-5, "low")
+        gh, gl = rs.standard_normal(hi.shape).astype(np.float32), rs.standard_normal(hi.shape).astype(np.float32)
+        gx = np.zeros((planes, H, H), np.float32)
+        err = sim.sim_dct2d(1, tc, p(gh), p(gl), p(w), p(w), p(gx), None, planes, H, H)
+        assert err is None, err.decode()
+        ref = odct.dct2d_split_bwd(gh[None].astype(np.float64), gl[None].astype(np.float64), H, H)
+        _close(gx, torch.from_numpy(np.ascontiguousarray(ref[0])), 1e-5, "gx")

@@ -292,11 +292,25 @@ extern "C" const char* sim_sscan_bwd(const void* u, const void* delta, const flo
 '''
 
 
+MACRO_LAUNCH = re.compile(r"([\w:]+<[^;\n]*?>)<<<(\w[\w.]*), ([\w.]+), ([\w.]+), st>>>\(([^\n]*)\)$", re.M)
+STATIC_SHARED = re.compile(r"^(\s*)__shared__ (\w+) (\w+)((?:\[[^\]]+\])+);", re.M)
+MMA = re.compile(r'asm volatile\(\s*"mma\.sync\.aligned\.m16n8k8\.row\.col\.f32\.tf32\.tf32\.f32.*?\);', re.S)
+
+
 def gen_whole_file(rel):
     """A .cu file translated as a whole: kernels AND their host launchers (plan selection, template dispatch);
     only the <<<...>>> launches, the shared-memory declaration and inline PTX are rewritten."""
     s = open(os.path.join(CSRC, rel)).read()
     s = SHARED.sub(r"\1* \2 = reinterpret_cast<\1*>(sim::smem());", s)
+    s = STATIC_SHARED.sub(r"\1typedef \2 \3_sim_t\4; \3_sim_t& \3 = *reinterpret_cast<\3_sim_t*>("
+                          r"sim::sshared(__LINE__, sizeof(\3_sim_t)));", s)
+    s = s.replace("#include <cooperative_groups.h>", "")
+    s = MMA.sub("sim::mma_m16n8k8_tf32(c, a, b);", s)
+    s = s.replace('asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");',
+                  "sim::cp_async_g(dst, src, 16);")
+    s = s.replace('asm volatile("cp.async.commit_group;" ::: "memory");', "sim::cp_commit();")
+    s = s.replace('asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");', "sim::cp_wait(N);")
+    s = MACRO_LAUNCH.sub(r"sim::launch_kernel(\2, \3, \4, [&] { \1(\5); })", s)
     s = LAUNCH.sub(r"sim::launch_kernel(\2, \3, \4, [&] { \1(\5); });", s)
     s = RED4.sub(r"sim::red_add_v4(\1, \2, \3, \4, \5);", s)
     assert "<<<" not in s and "__shared__" not in s and "asm" not in s.replace("__nv_bfloat16", ""), rel
@@ -353,6 +367,23 @@ cudaError_t launch_proj_gather(const void* src, void* dts, void* Bs, void* Cs, c
 cudaError_t launch_proj_scatter(const void* gdts, const void* gBs, const void* gCs, void* gsrc, const int32_t* plan,
                                 int K, int B, int R, int N, int L, int dtype, int bc_dtype, cudaStream_t st);
 }
+namespace tramba {
+int layernorm2d_tiles(int B, int C, int L);
+cudaError_t launch_layernorm2d_fwd(const void* x, const float* w, const float* b, void* y, float* mean, float* rstd,
+                                   int B, int C, int L, float eps, int act, int in_dtype, int out_dtype, cudaStream_t st);
+cudaError_t launch_layernorm2d_bwd(const void* gy, const void* x, const float* w, const float* b, const float* mean,
+                                   const float* rstd, void* gx, float* gw_part, float* gb_part, int B, int C, int L,
+                                   int act, int in_dtype, int g_dtype, cudaStream_t st);
+bool dct2d_tc_supported(int H, int W);
+cudaError_t launch_dct2d_fwd(const float* x, const float* wy, const float* wx, float* high, float* low, int planes, int H,
+                             int W, cudaStream_t st);
+cudaError_t launch_dct2d_bwd(const float* ghigh, const float* glow, const float* wy, const float* wx, float* gx,
+                             int planes, int H, int W, cudaStream_t st);
+cudaError_t launch_dct2d_fwd_tc(const float* x, const float* wy, const float* wx, float* high, float* low, int planes,
+                                int H, int W, cudaStream_t st);
+cudaError_t launch_dct2d_bwd_tc(const float* ghigh, const float* glow, const float* wy, const float* wx, float* gx,
+                                int planes, int H, int W, cudaStream_t st);
+}
 static const char* done(cudaError_t e) {
     return sim::last_error ? sim::last_error : (e == cudaSuccess ? nullptr : "launcher rejected the arguments");
 }
@@ -365,6 +396,31 @@ extern "C" const char* sim_dwconv2d_bwd(const void* x, const float* w, const flo
                                         float* dwp, int B, int C, int H, int W, int K, int act, int dtype) {
     sim::last_error = nullptr;
     return done(tramba::launch_dwconv2d_bwd(x, w, b, dy, dx, dwp, B, C, H, W, K, act, dtype, nullptr));
+}
+extern "C" int sim_layernorm2d_tiles(int B, int C, int L, int sms) {
+    sim::sm_count = sms;
+    return tramba::layernorm2d_tiles(B, C, L);
+}
+extern "C" const char* sim_layernorm2d_fwd(const void* x, const float* w, const float* b, void* y, float* mean, float* rstd,
+                                           int B, int C, int L, float eps, int act, int in_dtype, int out_dtype, int sms) {
+    sim::sm_count = sms, sim::last_error = nullptr;
+    return done(tramba::launch_layernorm2d_fwd(x, w, b, y, mean, rstd, B, C, L, eps, act, in_dtype, out_dtype, nullptr));
+}
+extern "C" const char* sim_layernorm2d_bwd(const void* gy, const void* x, const float* w, const float* b, const float* mean,
+                                           const float* rstd, void* gx, float* gw_part, float* gb_part, int B, int C, int L,
+                                           int act, int in_dtype, int g_dtype, int sms) {
+    sim::sm_count = sms, sim::last_error = nullptr;
+    return done(tramba::launch_layernorm2d_bwd(gy, x, w, b, mean, rstd, gx, gw_part, gb_part, B, C, L, act, in_dtype, g_dtype,
+                                               nullptr));
+}
+extern "C" const char* sim_dct2d(int bwd, int tensor_pipe, const float* a, const float* b2, const float* wy, const float* wx,
+                                 float* o1, float* o2, int planes, int H, int W) {
+    sim::last_error = nullptr;
+    if (tensor_pipe && !tramba::dct2d_tc_supported(H, W)) return "shape not covered by the tensor-pipe kernel";
+    if (!bwd) return done(tensor_pipe ? tramba::launch_dct2d_fwd_tc(a, wy, wx, o1, o2, planes, H, W, nullptr)
+                                      : tramba::launch_dct2d_fwd(a, wy, wx, o1, o2, planes, H, W, nullptr));
+    return done(tensor_pipe ? tramba::launch_dct2d_bwd_tc(a, b2, wy, wx, o1, planes, H, W, nullptr)
+                            : tramba::launch_dct2d_bwd(a, b2, wy, wx, o1, planes, H, W, nullptr));
 }
 extern "C" const char* sim_proj_gather(const void* src, void* dts, void* Bs, void* Cs, const int32_t* plan, int K, int B,
                                        int R, int N, int L, int dtype) {
@@ -381,7 +437,7 @@ extern "C" const char* sim_proj_scatter(const void* gdts, const void* gBs, const
 
 def gen_side():
     out = []
-    for rel in ("dwconv2d.cu", "proj_gather.cu"):
+    for rel in ("dwconv2d.cu", "proj_gather.cu", "layernorm2d.cu", "dct2d.cu", "dct2d_tc.cu"):
         src = gen_whole_file(rel)
         t = open(src).read()
         t = sub1(t, '#include "common.cuh"', '#include "sim_common.h"')
@@ -405,7 +461,8 @@ def build(force=False):
     os.makedirs(GEN, exist_ok=True)
     deps = [os.path.join(CSRC, k[0]) for k in KERNELS] + [os.path.join(CSRC, f) for f in ("sscan.cuh", "sscan_fwd.cu",
                                                                                          "sscan_bwd.cu", "cross_scan.cu", "dwconv2d.cu",
-                                                                                         "proj_gather.cu")] + [
+                                                                                         "proj_gather.cu", "layernorm2d.cu",
+                                                                                         "dct2d.cu", "dct2d_tc.cu")] + [
         os.path.join(CSRC, "ss2d_fused.cuh"),
                                                           os.path.join(HERE, "sim_common.h"), os.path.join(HERE, "selftest.cpp"),
                                                           os.path.abspath(__file__)]

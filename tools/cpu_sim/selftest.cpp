@@ -51,3 +51,4 @@ extern "C" const char* sim_selftest_mbar(int complete, float* out) {
     return sim::launch(1, 32, 64, [&] { mbar_kernel(complete, out); });
 }
 extern "C" void sim_set_lazy(int on) { sim::lazy = on != 0; }
+extern "C" int sim_last_cluster_size() { return sim::last_cluster_size; }

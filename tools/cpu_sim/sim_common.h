@@ -46,6 +46,7 @@ struct Mbar {
 };
 struct Warp {
     uint32_t slot[32];
+    uint32_t frag[32][6];   // mma.sync operands published by the lanes
     int count = 0, gen = 0;
 };
 struct Copy {
@@ -53,15 +54,24 @@ struct Copy {
     const void* src;
     size_t bytes;
 };
+struct Cluster;
 struct Cta {
     int nthreads = 0, bx = 0, gdim = 0;
+    int by = 0, bz = 0, gdim_y = 1, gdim_z = 1;
+    Cluster* cluster = nullptr;
+    int rank = 0;                                                      // rank of this CTA in its cluster
+    std::vector<unsigned char> sshared;                                // static __shared__ arena
+    size_t sshared_used = 0;
+    std::unordered_map<int, size_t> sshared_at;                        // declaration (source line) -> offset
+    std::vector<std::vector<Copy>> thread_cp;                          // cp.async.commit_group style copies: open group
+    std::vector<std::vector<std::vector<Copy>>> thread_cp_groups;      // ... committed groups, oldest first
     std::unordered_map<const void*, std::vector<Copy>> bar_copies;     // lazy g2s copies, per mbarrier
     std::unordered_map<const void*, std::vector<long long>> bar_tx;    // ... and their complete_tx bytes (-1: an arrive)
     std::vector<std::vector<Copy>> thread_async;                       // cp.async issued, not yet bound to a barrier
     std::vector<std::vector<Copy>> thread_stores;                      // lazy s2g bulk stores of each thread (open group)
     std::vector<std::vector<std::vector<Copy>>> thread_groups;         // ... and its committed bulk async-groups, oldest first
     unsigned char* smem = nullptr;
-    ucontext_t sched;
+    ucontext_t* sched_ptr = nullptr;
     std::vector<ucontext_t> ctx;
     std::vector<char> done;
     int cur = 0;
@@ -71,17 +81,26 @@ struct Cta {
     long long progress = 0;
     const char* error = nullptr;
 };
+struct Cluster {
+    std::vector<Cta*> ctas;
+    int count = 0, gen = 0, threads = 0;
+};
 inline Cta* g = nullptr;
 inline std::function<void()>* g_body = nullptr;
 inline bool lazy = false;
 
 inline Idx3 tidx() { return Idx3{static_cast<unsigned>(g->cur), 0, 0}; }
-inline Idx3 bidx() { return Idx3{static_cast<unsigned>(g->bx), 0, 0}; }
-inline Idx3 gdim() { return Idx3{static_cast<unsigned>(g->gdim), 1, 1}; }
+inline Idx3 bidx() { return Idx3{static_cast<unsigned>(g->bx), static_cast<unsigned>(g->by), static_cast<unsigned>(g->bz)}; }
+inline Idx3 gdim() {
+    return Idx3{static_cast<unsigned>(g->gdim), static_cast<unsigned>(g->gdim_y), static_cast<unsigned>(g->gdim_z)};
+}
 inline Idx3 bdim() { return Idx3{static_cast<unsigned>(g->nthreads), 1, 1}; }
 inline unsigned char* smem() { return g->smem; }
 
-inline void yield() { swapcontext(&g->ctx[g->cur], &g->sched); }
+inline void yield() {
+    Cta* me = g;   // the scheduler repoints g at whichever CTA it resumes next; it is restored before we continue
+    swapcontext(&me->ctx[me->cur], me->sched_ptr);
+}
 
 inline void syncthreads() {
     const int gen = g->bar_gen;
@@ -118,6 +137,79 @@ inline float u2f(uint32_t u) {
     float f;
     std::memcpy(&f, &u, 4);
     return f;
+}
+
+inline void cluster_sync() {                 // barrier.cluster.arrive + wait over every thread of the cluster
+    Cluster& c = *g->cluster;
+    const int gen = c.gen;
+    if (++c.count == c.threads) {
+        c.count = 0, ++c.gen, ++g->progress;
+    } else {
+        while (c.gen == gen) yield();
+    }
+}
+// static `__shared__ T name[...]` declarations: one arena per CTA, keyed by the declaration's source line
+inline void* sshared(int key, size_t bytes) {
+    auto it = g->sshared_at.find(key);
+    if (it == g->sshared_at.end()) {
+        const size_t off = (g->sshared_used + 15) & ~size_t(15);
+        if (off + bytes > g->sshared.size()) {
+            g->error = "static shared memory arena exhausted";
+            return g->sshared.data();
+        }
+        g->sshared_used = off + bytes;
+        it = g->sshared_at.emplace(key, off).first;
+    }
+    return g->sshared.data() + it->second;
+}
+template <typename T>
+inline T* map_rank(T* p, unsigned rank) {     // cluster.map_shared_rank: same offset in the peer CTA's shared memory
+    unsigned char* q = reinterpret_cast<unsigned char*>(const_cast<typename std::remove_const<T>::type*>(p));
+    Cta* peer = g->cluster->ctas[rank];
+    if (q >= g->sshared.data() && q < g->sshared.data() + g->sshared.size())
+        return reinterpret_cast<T*>(peer->sshared.data() + (q - g->sshared.data()));
+    return reinterpret_cast<T*>(peer->smem + (q - g->smem));
+}
+// cp.async + commit_group / wait_group (per-thread groups)
+inline void cp_async_g(void* dst, const void* src, size_t n) {
+    if (!lazy) {
+        std::memcpy(dst, src, n);
+        return;
+    }
+    std::memset(dst, 0xCD, n);
+    g->thread_cp[g->cur].push_back(Copy{dst, src, n});
+}
+inline void cp_commit() {
+    auto& open = g->thread_cp[g->cur];
+    g->thread_cp_groups[g->cur].push_back(open);
+    open.clear();
+}
+inline void cp_wait(size_t keep) {
+    auto& groups = g->thread_cp_groups[g->cur];
+    while (groups.size() > keep) {
+        for (const Copy& c : groups.front()) std::memcpy(c.dst, c.src, c.bytes);
+        groups.erase(groups.begin());
+    }
+}
+// mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32: C (16x8) += A (16x8) . B (8x8), operands truncated to TF32
+inline void mma_m16n8k8_tf32(float (&c)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+    Warp& w = g->warps[g->cur >> 5];
+    const int lane = g->cur & 31;
+    for (int i = 0; i < 4; ++i) w.frag[lane][i] = a[i] & 0xffffe000u;
+    for (int i = 0; i < 2; ++i) w.frag[lane][4 + i] = b[i] & 0xffffe000u;
+    warp_barrier();
+    const int gid = lane >> 2, t = lane & 3;
+    for (int i = 0; i < 4; ++i) {
+        const int row = gid + ((i & 2) ? 8 : 0), col = 2 * t + (i & 1);
+        float acc = c[i];
+        for (int k = 0; k < 8; ++k) {
+            const float av = u2f(w.frag[(row & 7) * 4 + (k & 3)][(row >= 8 ? 1 : 0) + (k >= 4 ? 2 : 0)]);
+            const float bv = u2f(w.frag[col * 4 + (k & 3)][4 + (k >= 4 ? 1 : 0)]);
+            acc += av * bv;
+        }
+        c[i] = acc;
+    }
+    warp_barrier();
 }
 
 // ---- mbarrier (phase completes when the pending arrivals and the pending transaction bytes are both zero)
@@ -205,52 +297,89 @@ inline void drain_all_stores() {                                        // threa
 }
 
 // Runs `body` as grid x nthreads CUDA threads, CTA after CTA.  Returns nullptr or an error string.
-inline const char* launch(int grid, int nthreads, size_t smem_bytes, std::function<void()> body) {
+struct Dim3 {
+    int x = 1, y = 1, z = 1;
+};
+inline int last_cluster_size = 0;   // CTAs per cluster of the most recent launch (tests check which path ran)
+// Runs `body` as grid x nthreads CUDA threads.  CTAs run one cluster at a time (cluster = {1,1,1}: one CTA at a
+// time); the CTAs of a cluster run concurrently, which cluster.sync() and distributed shared memory need.
+inline const char* launch3(Dim3 grid, Dim3 cl, int nthreads, size_t smem_bytes, std::function<void()> body) {
     static std::vector<char*> stacks;
-    const size_t kStack = 256 * 1024;
-    while (static_cast<int>(stacks.size()) < nthreads) stacks.push_back(static_cast<char*>(std::malloc(kStack)));
-    void* raw = nullptr;
-    if (posix_memalign(&raw, 1024, smem_bytes + 1024) != 0) return "out of memory";
+    const size_t kStack = 192 * 1024;
+    const int csize = cl.x * cl.y * cl.z;
+    last_cluster_size = csize;
+    if (grid.x % cl.x || grid.y % cl.y || grid.z % cl.z) return "grid is not a multiple of the cluster shape";
+    while (static_cast<int>(stacks.size()) < nthreads * csize) stacks.push_back(static_cast<char*>(std::malloc(kStack)));
+    std::vector<void*> raws(csize, nullptr);
+    for (void*& r : raws)
+        if (posix_memalign(&r, 1024, smem_bytes + 1024) != 0) return "out of memory";
     const char* err = nullptr;
     g_body = &body;
-    for (int bx = 0; bx < grid && !err; ++bx) {
-        Cta cta;
-        cta.nthreads = nthreads, cta.bx = bx, cta.gdim = grid;
-        cta.smem = static_cast<unsigned char*>(raw);
-        std::memset(cta.smem, 0xCD, smem_bytes);   // poison: uninitialised shared memory must not go unnoticed
-        cta.ctx.resize(nthreads), cta.done.assign(nthreads, 0), cta.warps.resize((nthreads + 31) / 32);
-        cta.thread_async.resize(nthreads), cta.thread_stores.resize(nthreads), cta.thread_groups.resize(nthreads);
-        g = &cta;
-        for (int t = 0; t < nthreads; ++t) {
-            getcontext(&cta.ctx[t]);
-            cta.ctx[t].uc_stack.ss_sp = stacks[t];
-            cta.ctx[t].uc_stack.ss_size = kStack;
-            cta.ctx[t].uc_link = &cta.sched;
-            makecontext(&cta.ctx[t], reinterpret_cast<void (*)()>(+[]() {
-                            (*g_body)();
-                            drain_all_stores();      // a store still in flight at exit completes eventually
-                            g->done[g->cur] = 1;
-                            ++g->progress;
-                        }),
-                        0);
-        }
-        int alive = nthreads;
-        while (alive > 0 && !cta.error) {
-            const long long before = cta.progress;
-            alive = 0;
-            for (int t = 0; t < nthreads; ++t) {
-                if (cta.done[t]) continue;
-                cta.cur = t;
-                swapcontext(&cta.sched, &cta.ctx[t]);
-                if (!cta.done[t]) ++alive;
+    for (int oz = 0; oz < grid.z && !err; oz += cl.z)
+        for (int oy = 0; oy < grid.y && !err; oy += cl.y)
+            for (int ox = 0; ox < grid.x && !err; ox += cl.x) {
+                std::vector<Cta> ctas(csize);
+                Cluster cluster;
+                cluster.threads = nthreads * csize;
+                ucontext_t sched;
+                int r = 0;
+                for (int cz = 0; cz < cl.z; ++cz)
+                    for (int cy = 0; cy < cl.y; ++cy)
+                        for (int cx = 0; cx < cl.x; ++cx, ++r) {
+                            Cta& cta = ctas[r];
+                            cta.nthreads = nthreads, cta.rank = r, cta.cluster = &cluster;
+                            cta.bx = ox + cx, cta.by = oy + cy, cta.bz = oz + cz;
+                            cta.gdim = grid.x, cta.gdim_y = grid.y, cta.gdim_z = grid.z;
+                            cta.smem = static_cast<unsigned char*>(raws[r]);
+                            std::memset(cta.smem, 0xCD, smem_bytes);   // poison: uninitialised shared memory must show
+                            cta.sshared.assign(48 * 1024, 0xCD);
+                            cta.ctx.resize(nthreads), cta.done.assign(nthreads, 0), cta.warps.resize((nthreads + 31) / 32);
+                            cta.thread_async.resize(nthreads), cta.thread_stores.resize(nthreads);
+                            cta.thread_groups.resize(nthreads), cta.thread_cp.resize(nthreads);
+                            cta.thread_cp_groups.resize(nthreads);
+                            cluster.ctas.push_back(&cta);
+                            for (int t = 0; t < nthreads; ++t) {
+                                getcontext(&cta.ctx[t]);
+                                cta.ctx[t].uc_stack.ss_sp = stacks[r * nthreads + t];
+                                cta.ctx[t].uc_stack.ss_size = kStack;
+                                cta.ctx[t].uc_link = &sched;
+                                makecontext(&cta.ctx[t], reinterpret_cast<void (*)()>(+[]() {
+                                                (*g_body)();
+                                                drain_all_stores();   // a store still in flight at exit completes eventually
+                                                cp_wait(0);
+                                                g->done[g->cur] = 1;
+                                                ++g->progress;
+                                            }),
+                                            0);
+                            }
+                        }
+                int alive = 1;
+                while (alive > 0 && !err) {
+                    long long before = 0;
+                    for (Cta& c : ctas) before += c.progress;
+                    alive = 0;
+                    for (Cta& cta : ctas) {
+                        g = &cta;
+                        for (int t = 0; t < nthreads; ++t) {
+                            if (cta.done[t]) continue;
+                            cta.cur = t;
+                            cta.sched_ptr = &sched;
+                            swapcontext(&sched, &cta.ctx[t]);
+                            if (!cta.done[t]) ++alive;
+                        }
+                        if (cta.error) err = cta.error;
+                    }
+                    long long after = 0;
+                    for (Cta& c : ctas) after += c.progress;
+                    if (alive > 0 && after == before && !err) err = "deadlock: every live thread is blocked";
+                }
+                g = nullptr;
             }
-            if (alive > 0 && cta.progress == before) cta.error = "deadlock: every live thread is blocked";
-        }
-        err = cta.error;
-        g = nullptr;
-    }
-    std::free(raw);
+    for (void* r : raws) std::free(r);
     return err;
+}
+inline const char* launch(int grid, int nthreads, size_t smem_bytes, std::function<void()> body) {
+    return launch3(Dim3{grid, 1, 1}, Dim3{1, 1, 1}, nthreads, smem_bytes, std::move(body));
 }
 
 // ---- what the host launchers of a translated .cu file see instead of the CUDA runtime
@@ -259,6 +388,12 @@ inline const char* last_error = nullptr; // first simulator error of the current
 template <typename F>
 inline void launch_kernel(int grid, int block, size_t smem_bytes, F&& body) {
     const char* e = launch(grid, block, smem_bytes, std::function<void()>(body));
+    if (e && !last_error) last_error = e;
+}
+template <typename F>
+inline void launch_kernel(dim3 grid, int block, size_t smem_bytes, F&& body) {
+    const char* e = launch3(Dim3{static_cast<int>(grid.x), static_cast<int>(grid.y), static_cast<int>(grid.z)},
+                            Dim3{1, 1, 1}, block, smem_bytes, std::function<void()>(body));
     if (e && !last_error) last_error = e;
 }
 inline void red_add_v4(float* p, float a, float b, float c, float d) { p[0] += a, p[1] += b, p[2] += c, p[3] += d; }
@@ -278,6 +413,40 @@ inline cudaError_t cudaDeviceGetAttribute(int* v, cudaDeviceAttr attr, int) {
     return cudaSuccess;
 }
 inline cudaError_t cudaGetLastError() { return sim::last_error ? cudaErrorLaunchFailure : cudaSuccess; }
+inline cudaError_t cudaMemsetAsync(void* p, int v, size_t n, cudaStream_t) {
+    std::memset(p, v, n);
+    return cudaSuccess;
+}
+inline const char* cudaGetErrorString(cudaError_t) { return "simulated CUDA error"; }
+template <typename... KA, typename... A>
+inline cudaError_t cudaLaunchKernelEx(const cudaLaunchConfig_t* cfg, void (*kern)(KA...), A... args) {
+    sim::Dim3 cl;
+    for (unsigned i = 0; i < cfg->numAttrs; ++i)
+        if (cfg->attrs[i].id == cudaLaunchAttributeClusterDimension) {
+            cl.x = static_cast<int>(cfg->attrs[i].val.clusterDim.x);
+            cl.y = static_cast<int>(cfg->attrs[i].val.clusterDim.y);
+            cl.z = static_cast<int>(cfg->attrs[i].val.clusterDim.z);
+        }
+    const char* e = sim::launch3(sim::Dim3{static_cast<int>(cfg->gridDim.x), static_cast<int>(cfg->gridDim.y),
+                                           static_cast<int>(cfg->gridDim.z)},
+                                 cl, static_cast<int>(cfg->blockDim.x), cfg->dynamicSmemBytes,
+                                 [=] { kern(args...); });
+    if (e && !sim::last_error) sim::last_error = e;
+    return cudaSuccess;
+}
+
+namespace cooperative_groups {   // the slice of <cooperative_groups.h> the kernels use
+struct cluster_group {
+    void sync() const { sim::cluster_sync(); }
+    template <typename T>
+    T* map_shared_rank(T* p, unsigned rank) const {
+        return sim::map_rank(p, rank);
+    }
+    unsigned block_rank() const { return static_cast<unsigned>(sim::g->rank); }
+    unsigned num_blocks() const { return static_cast<unsigned>(sim::g->cluster->ctas.size()); }
+};
+inline cluster_group this_cluster() { return cluster_group{}; }
+}  // namespace cooperative_groups
 template <typename K>
 inline cudaError_t cudaOccupancyMaxActiveBlocksPerMultiprocessor(int* n, K, int, size_t) {
     *n = 1;
@@ -285,10 +454,26 @@ inline cudaError_t cudaOccupancyMaxActiveBlocksPerMultiprocessor(int* n, K, int,
 }
 
 // ---------------------------------------------------------------------------------------------- CUDA surface
-#define threadIdx (sim::tidx())
-#define blockIdx (sim::bidx())
-#define gridDim (sim::gdim())
-#define blockDim (sim::bdim())
+// threadIdx / blockIdx / blockDim / gridDim as objects (not macros: `cfg.gridDim` in host code must keep working)
+namespace sim {
+template <int WHICH, int AXIS>
+struct BuiltinField {
+    operator unsigned() const {
+        const Idx3 v = WHICH == 0 ? tidx() : WHICH == 1 ? bidx() : WHICH == 2 ? bdim() : gdim();
+        return AXIS == 0 ? v.x : AXIS == 1 ? v.y : v.z;
+    }
+};
+template <int WHICH>
+struct Builtin3 {
+    BuiltinField<WHICH, 0> x;
+    BuiltinField<WHICH, 1> y;
+    BuiltinField<WHICH, 2> z;
+};
+}  // namespace sim
+static const sim::Builtin3<0> threadIdx{};
+static const sim::Builtin3<1> blockIdx{};
+static const sim::Builtin3<2> blockDim{};
+static const sim::Builtin3<3> gridDim{};
 inline void __syncthreads() { sim::syncthreads(); }
 inline float __shfl_up_sync(unsigned, float v, int delta, int width = 32) {
     const int lane = sim::g->cur & 31, sl = lane % width;
@@ -374,6 +559,19 @@ inline void bulk_wait_all() {
 inline float ex2f(float x) { return exp2f(x); }
 inline float lg2f(float x) { return log2f(x); }
 inline float rcpf(float x) { return 1.0f / x; }
+}  // namespace tramba
+inline float rsqrtf(float x) { return 1.0f / sqrtf(x); }
+namespace tramba {
+template <typename T>
+struct DTypeOf;
+template <>
+struct DTypeOf<float> {
+    static constexpr int value = TRAMBA_F32;
+};
+template <>
+struct DTypeOf<__nv_bfloat16> {
+    static constexpr int value = TRAMBA_BF16;
+};
 inline float softplus20(float x, float& e_out, float& w_out) {
     const float e = ex2f(x * kLog2e);
     const float w = 1.0f + e;
