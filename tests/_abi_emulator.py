@@ -276,12 +276,45 @@ class _Stream:
     cuda_stream = 0
 
 
+class _SimLib:
+    """The product's C ABI exported by tools/cpu_sim's library: the REAL entry points (capi.cu) and the REAL kernels
+    (every .cu of the library), compiled as host code and executed on the CPU simulator."""
+
+    def __init__(self, sms=4):
+        import importlib.util
+        import os
+        from tramba_b200 import _lib
+        root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+        spec = importlib.util.spec_from_file_location("build_sim", os.path.join(root, "tools", "cpu_sim", "build_sim.py"))
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+        self._dll = ctypes.CDLL(mod.build())
+        for name, (res, args) in _lib.SIGNATURES.items():
+            fn = getattr(self._dll, name)
+            fn.restype, fn.argtypes = res, args
+        self._dll.sim_set_sm_count.restype, self._dll.sim_set_sm_count.argtypes = None, [ctypes.c_int]
+        self._dll.sim_set_sm_count(sms)
+        self.calls = []
+
+    def __getattr__(self, name):
+        fn = getattr(self._dll, name)
+        if not name.startswith("tramba_"):
+            return fn
+
+        def call(*args):
+            self.calls.append(name)
+            return fn(*args)
+        return call
+
+
 @contextlib.contextmanager
-def installed():
-    """Within this scope the product's Python host runs on CPU tensors against the emulated entry points."""
+def installed(backend="oracle", sms=4):
+    """Within this scope the product's Python host runs on CPU tensors against
+      backend="oracle": the compute entry points emulated by the oracle (fast; checks the host logic only), or
+      backend="sim":    the product's own C ABI and kernels executed on the CPU simulator (tools/cpu_sim)."""
     from tramba_b200 import _lib
     saved = (_lib.lib, torch.Tensor.cuda, torch.nn.Module.cuda, torch.cuda.current_stream, torch.cuda.device)
-    proxy = _Proxy(_lib.lib)
+    proxy = _Proxy(_lib.lib) if backend == "oracle" else _SimLib(sms)
     _lib.lib = proxy
     torch.Tensor.cuda = lambda self, *a, **k: self
     torch.nn.Module.cuda = lambda self, *a, **k: self

@@ -122,3 +122,44 @@ def test_ss2d_module_bf16_marshalling():
     assert rel < 5e-2, rel
     relg = (x16.grad - g32).abs().max() / g32.abs().max()
     assert relg < 1e-1, relg
+
+
+SIM_CASES = [("std", "CrossScan", "CrossMerge", 4, 1, 12), ("line", "CrossScan_Line", "CrossMerge_Line", 8, 1, 24),
+             ("dilation", "CrossScan_Dilation", "CrossMerge_Dilation", 4, 2, 12),
+             ("hilbert", "CrossScan_Hilbert", "CrossMerge_Hilbert", 4, 1, 12)]
+
+
+@pytest.mark.parametrize("fam,scan,merge,K,N,H", SIM_CASES)
+def test_ss2d_module_on_the_simulated_library(fam, scan, merge, K, N, H):
+    """Same module test as above, but nothing is emulated by the oracle: the product's Python host calls the product's
+    own C ABI (capi.cu) and kernels (fused core or cross-scan / selective scan / cross-merge, proj gather / scatter,
+    LayerNorm2d cluster kernels, depthwise conv), compiled as host code and executed on the CPU simulator
+    (tools/cpu_sim).  The oracle is only the reference the results are compared with."""
+    torch.manual_seed(0)
+    m = tramba_b200.SS2D(d_model=32, d_state=N, ssm_ratio=2.0, dt_rank="auto", d_conv=3, conv_bias=False,
+                         channel_first=True, disable_z=True, scan=getattr(tramba_b200, scan),
+                         merge=getattr(tramba_b200, merge), k_group=K)
+    ref = copy.deepcopy(m)
+    ref.scan, ref.merge = make_pair(fam)
+    ref.selective_scan = OracleSelectiveScan
+    ref.fused_dwconv = False
+    x = torch.randn(2, 32, H, H)
+    xr = x.clone().requires_grad_(True)
+    yr = ref(xr)
+    gy = torch.randn_like(yr)
+    yr.backward(gy)
+    with installed("sim") as lib:
+        xg = x.clone().requires_grad_(True)
+        yg = m(xg)
+        yg.backward(gy)
+    fused_expected = N == 1 and fam in ("std", "line")
+    assert ("tramba_ss2d_fused_bwd" in lib.calls) == fused_expected
+    assert ("tramba_sscan_bwd" in lib.calls) == (not fused_expected)
+    for name in ("tramba_layernorm2d_fwd", "tramba_layernorm2d_bwd", "tramba_dwconv2d_fwd", "tramba_dwconv2d_bwd"):
+        assert name in lib.calls
+    np.testing.assert_allclose(yg.detach().numpy(), yr.detach().numpy(), rtol=1e-3,
+                               atol=1e-3 * float(yr.detach().abs().max()))
+    np.testing.assert_allclose(xg.grad.numpy(), xr.grad.numpy(), rtol=1e-3, atol=1e-3 * float(xr.grad.abs().max()))
+    for (n, pg), (_, pr) in zip(m.named_parameters(), ref.named_parameters()):
+        np.testing.assert_allclose(pg.grad.numpy(), pr.grad.numpy(), rtol=2e-3,
+                                   atol=2e-3 * float(pr.grad.abs().max()) + 1e-7, err_msg=n)

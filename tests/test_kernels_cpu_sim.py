@@ -11,8 +11,9 @@ and their carries, barrier and mbarrier protocols (a mismatch is reported as a d
 discipline at both extremes (copies landing at issue / only at the wait), and the numerics of the recurrences.  The
 product kernels are GPU-verified (tests/test_gpu_*.py): here they validate the simulator, and protect later edits;
 the candidates (not yet run on a GPU) must reproduce the product kernels bit for bit.  Interleavings between the two
-copy extremes, memory-model ordering and performance are out of its reach; LayerNorm2d (clusters / DSMEM) and the
-tensor-pipe DCT (mma.sync) are not translated."""
+copy extremes, memory-model ordering and performance are out of its reach.  LayerNorm2d (thread-block clusters,
+distributed shared memory) and DCT2D (mma.sync TF32) are covered at the end of this file; the library's whole C ABI on
+the simulator is exercised from the Python host in tests/test_host_logic_emulated.py and tests/test_model_parity.py."""
 import ctypes
 import importlib.util
 import os

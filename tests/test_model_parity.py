@@ -78,6 +78,22 @@ def test_harness_product_host_emulated_abi_matches_reference_golden():
     _check(m, outs, loss, 1e-3)
 
 
+@pytest.mark.skipif(os.environ.get("TRAMBA_SIM_MODEL", "") != "1",
+                    reason="4-5 minutes on the CPU simulator: run with TRAMBA_SIM_MODEL=1 (passed in round 1, DESIGN 8)")
+def test_harness_on_the_simulated_library_matches_reference_golden():
+    """The whole Tramba-V forward + backward on the product's OWN C ABI and kernel sources, compiled as host code and
+    executed on the CPU simulator (tools/cpu_sim): 27 fused-core + 6 op-by-op SS2D calls, 108 LayerNorm2d launches
+    (cluster kernels included), depthwise convs, proj gathers, 3 tensor-pipe DCTs -- against the REAL reference's
+    fixture.  Nothing is computed by the oracle here."""
+    from _abi_emulator import installed
+    m = det_fill(build_model(img_size=384, dims=int(GOLD["dims"]))).eval()
+    with installed("sim") as lib:
+        outs, loss = _run(m, "cpu")
+    assert lib.calls.count("tramba_ss2d_fused_fwd") == 27 and lib.calls.count("tramba_sscan_fwd") == 6
+    assert lib.calls.count("tramba_dct2d_fwd") == 3 and lib.calls.count("tramba_layernorm2d_fwd") > 100
+    _check(m, outs, loss, 1e-3)
+
+
 @pytest.mark.gpu
 def test_harness_gpu_kernels_match_reference_golden():
     # the harness' own convolutions must not round to TF32 here: this test pins OUR kernels through a

@@ -1,10 +1,12 @@
 #!/usr/bin/env python
-"""Builds tools/cpu_sim/_gen/libtramba_sim.so: the fused SS2D kernels (product: csrc/ss2d_fused_{fwd,bwd}.cu,
-candidates: csrc/next/*_cg.cu) compiled as HOST code against tools/cpu_sim/sim_common.h (see there).
+"""Builds tools/cpu_sim/_gen/libtramba_sim.so: EVERY source file of libtramba_b200 (capi.cu, orders.cpp, all kernel .cu
+files, plus the candidates under csrc/next/) compiled as HOST code against tools/cpu_sim/sim_common.h (see there), so
+that the product's C ABI and kernels can be executed on a CPU.
 
-The kernel sources are copied, not edited in place; the only textual changes are (1) inline PTX -> the simulator's
-functions, (2) `extern __shared__ ... smem[]` -> the simulator's per-CTA buffer, (3) the CUDA launchers at the end
-of each file are cut off and replaced by a small `extern "C"` driver.  TEST INFRASTRUCTURE (g++ only, no GPU).
+The sources are copied, not edited in place; the only textual changes are (1) inline PTX -> the simulator's functions,
+(2) `extern __shared__ ... name[]` / static `__shared__` arrays -> the simulator's per-CTA buffers, (3) `<<<...>>>`
+launches -> sim::launch_kernel, (4) SM counts cached in function-local statics made per call, (5) small `extern "C"`
+drivers appended for the tests that call kernels directly.  TEST INFRASTRUCTURE (g++ only, no nvcc, no GPU).
 
     python tools/cpu_sim/build_sim.py        # -> path of the library
 """
@@ -41,181 +43,64 @@ def gen_header():
 RED = re.compile(r'asm volatile\("red\.global\.add\.v2\.f32 \[%0\], \{%1, %2\};" ::"l"\((.*?)\), "f"\((.*?)\), '
                  r'"f"\((.*?)\)\s*: "memory"\);', re.S)
 
-TAIL_FWD = r'''
-template <typename in_t>
-static const char* run(const FusedArgs& a, int grid) {
-    FusedArgs b = a;
-    b.xb = FwdLayout(a.L, sizeof(in_t), 2).total <= 227 * 1024 ? 2 : 1;
-    const size_t smem = FwdLayout(a.L, sizeof(in_t), b.xb).total;
-    if (smem > 227 * 1024) return "shared memory does not fit";
-    if (grid > a.rounds) grid = a.rounds;
-    return sim::launch(grid, NT, smem, [&] { ss2d_fwd_kernel<in_t, true>(b); });
+FUSED_DRIVER = r'''
+// Drivers of the fused SS2D core: product launchers (csrc/ss2d_fused_*.cu) and candidates (csrc/next/*_cg.cu).
+// `grid` plays the role of the SM count: the launchers size their persistent grids from it.
+#include "ss2d_fused.cuh"
+namespace tramba {
+cudaError_t launch_ss2d_fused_fwd_cg(const FusedArgs& a, int in_dtype, cudaStream_t st);
+cudaError_t launch_ss2d_fused_bwd_cg(const FusedArgs& a, int in_dtype, cudaStream_t st);
+cudaError_t launch_merge_skewed(const void* ys, void* y, const uint16_t* idx, int K, int B, int D, int L,
+                                uint32_t dup_mask, int dtype, cudaStream_t st);
+cudaError_t launch_merge_skewed_cg(const void* ys, void* y, const uint16_t* idx, int K, int B, int D, int L,
+                                   uint32_t dup_mask, int dtype, cudaStream_t st);
 }
-}  // namespace
+using namespace tramba;
+static const char* done(cudaError_t e) {
+    return sim::last_error ? sim::last_error : (e == cudaSuccess ? nullptr : "launcher rejected the arguments");
+}
+static FusedArgs with_depth(const FusedArgs& a, int in_dtype) {   // the staging depth tramba_ss2d_fused_fwd picks
+    FusedArgs b = a;
+    const int es = in_dtype == TRAMBA_F32 ? 4 : 2;
+    b.xb = ss2d_fused_fwd_smem(a.L, es, 2) <= 227 * 1024 ? 2 : 1;
+    return b;
+}
 extern "C" const char* sim_fwd(const FusedArgs* a, int in_dtype, int grid) {
-    return in_dtype == TRAMBA_F32 ? run<float>(*a, grid) : run<__nv_bfloat16>(*a, grid);
+    sim::sm_count = grid, sim::last_error = nullptr;
+    return done(launch_ss2d_fused_fwd(with_depth(*a, in_dtype), in_dtype, nullptr));
 }
-}  // namespace tramba
-'''
-
-TAIL_FWD_CG = r'''
-template <typename in_t, int TPC, int XB>
-static const char* run1(const FusedArgs& a, int grid) {
-    FusedArgs b = a;
-    b.xb = XB;
-    const size_t smem = FwdLayout(a.L, sizeof(in_t), XB).total;
-    if (grid > a.rounds) grid = a.rounds;
-    return sim::launch(grid, NT, smem, [&] { ss2d_fwd_cg_kernel<in_t, true, TPC, XB>(b); });
-}
-template <typename in_t, int XB>
-static const char* run_tp(const FusedArgs& a, int grid) {
-    switch (a.TP) {
-        case 8: return run1<in_t, 8, XB>(a, grid);
-        case 32: return run1<in_t, 32, XB>(a, grid);
-        case 128: return run1<in_t, 128, XB>(a, grid);
-        case 512: return run1<in_t, 512, XB>(a, grid);
-        default: return "threads per plane not specialised";
-    }
-}
-template <typename in_t>
-static const char* run(const FusedArgs& a, int grid) {
-    const int xb = FwdLayout(a.L, sizeof(in_t), 2).total <= 227 * 1024 ? 2 : 1;
-    if (FwdLayout(a.L, sizeof(in_t), xb).total > 227 * 1024) return "shared memory does not fit";
-    return xb == 2 ? run_tp<in_t, 2>(a, grid) : run_tp<in_t, 1>(a, grid);
-}
-}  // namespace
 extern "C" const char* sim_fwd_cg(const FusedArgs* a, int in_dtype, int grid) {
-    return in_dtype == TRAMBA_F32 ? run<float>(*a, grid) : run<__nv_bfloat16>(*a, grid);
+    sim::sm_count = grid, sim::last_error = nullptr;
+    return done(launch_ss2d_fused_fwd_cg(with_depth(*a, in_dtype), in_dtype, nullptr));
 }
-}  // namespace tramba
-'''
-
-PICK = r'''
-static int pick_rounds(const FusedArgs& a) {   // as in ss2d_fused_bwd.cu
-    int R = 1;
-    while (R * a.PP < 8 && a.D % (2 * R * a.PP) == 0) R *= 2;
-    return R;
-}
-'''
-
-TAIL_BWD = PICK + r'''
-template <typename in_t>
-static const char* run(const FusedArgs& a, int grid) {
-    FusedArgs b = a;
-    b.xb = BwdLayout(a.L, sizeof(in_t), 2).total <= 227 * 1024 ? 2 : 1;
-    const size_t smem = BwdLayout(a.L, sizeof(in_t), b.xb).total;
-    if (smem > 227 * 1024) return "shared memory does not fit";
-    const int R = pick_rounds(a);
-    const int items = a.B * a.K * (a.D / (R * a.PP));
-    if (grid > items) grid = items;
-    return sim::launch(grid, NT, smem, [&] { ss2d_bwd_kernel<in_t, true>(b, R); });
-}
-}  // namespace
 extern "C" const char* sim_bwd(const FusedArgs* a, int in_dtype, int grid) {
-    return in_dtype == TRAMBA_F32 ? run<float>(*a, grid) : run<__nv_bfloat16>(*a, grid);
+    sim::sm_count = grid, sim::last_error = nullptr;
+    return done(launch_ss2d_fused_bwd(*a, in_dtype, nullptr));
 }
-}  // namespace tramba
-'''
-
-TAIL_BWD_CG = PICK + r'''
-template <typename in_t, int TPC, int XB>
-static const char* run1(const FusedArgs& a, int grid) {
-    FusedArgs b = a;
-    b.xb = XB;
-    const size_t smem = BwdLayout(a.L, sizeof(in_t), XB).total;
-    if (smem > 227 * 1024) return "shared memory does not fit";
-    const int R = pick_rounds(a);
-    const int items = a.B * a.K * (a.D / (R * a.PP));
-    if (grid > items) grid = items;
-    return sim::launch(grid, NT, smem, [&] { ss2d_bwd_cg_kernel<in_t, true, TPC, XB>(b, R); });
+extern "C" const char* sim_bwd_cg(const FusedArgs* a, int in_dtype, int grid) {
+    sim::sm_count = grid, sim::last_error = nullptr;
+    return done(launch_ss2d_fused_bwd_cg(*a, in_dtype, nullptr));
 }
-template <typename in_t, int XB>
-static const char* run(const FusedArgs& a, int grid) {
-    switch (a.TP) {
-        case 8: return run1<in_t, 8, XB>(a, grid);
-        case 32: return run1<in_t, 32, XB>(a, grid);
-        case 128: return run1<in_t, 128, XB>(a, grid);
-        case 512: return run1<in_t, 512, XB>(a, grid);
-        default: return "threads per plane not specialised";
-    }
-}
-}  // namespace
-extern "C" const char* sim_bwd_cg(const FusedArgs* a, int in_dtype, int grid) {   // staging depth as launch_ss2d_fused_bwd_cg
-    return in_dtype == TRAMBA_F32 ? run<float, 1>(*a, grid) : run<__nv_bfloat16, 2>(*a, grid);
-}
-}  // namespace tramba
-'''
-
-TAIL_MERGE = r'''
-template <typename T>
-static const char* run(const T* ys, T* y, const uint16_t* idx, int K, int B, int D, int L, uint32_t dup_mask, int grid) {
-    const int TP = L / S, PP = NT / TP, rounds = B * D / PP;
-    if (grid > rounds) grid = rounds;
-    return sim::launch(grid, NT, MergeLayout(L, sizeof(T)).total,
-                       [&] { merge_skewed_kernel<T>(ys, y, idx, K, D, L, TP, PP, rounds, dup_mask); });
-}
-}  // namespace
 extern "C" const char* sim_merge(const void* ys, void* y, const uint16_t* idx, int K, int B, int D, int L,
                                  uint32_t dup_mask, int dtype, int grid) {
-    return dtype == TRAMBA_F32 ? run(static_cast<const float*>(ys), static_cast<float*>(y), idx, K, B, D, L, dup_mask, grid)
-                               : run(static_cast<const __nv_bfloat16*>(ys), static_cast<__nv_bfloat16*>(y), idx, K, B, D, L,
-                                     dup_mask, grid);
+    sim::sm_count = grid, sim::last_error = nullptr;
+    return done(launch_merge_skewed(ys, y, idx, K, B, D, L, dup_mask, dtype, nullptr));
 }
-}  // namespace tramba
-'''
-
-TAIL_MERGE_CG = r'''
-template <typename T, int TPC>
-static const char* run1(const T* ys, T* y, const uint16_t* idx, int K, int B, int D, uint32_t dup_mask, int grid) {
-    constexpr int L = S * TPC, PP = NT / TPC;
-    const int rounds = B * D / PP;
-    if (grid > rounds) grid = rounds;
-    return sim::launch(grid, NT, MergeLayout(L, sizeof(T)).total,
-                       [&] { merge_skewed_cg_kernel<T, TPC>(ys, y, idx, K, D, rounds, dup_mask); });
-}
-template <typename T>
-static const char* run(const T* ys, T* y, const uint16_t* idx, int K, int B, int D, int L, uint32_t dup_mask, int grid) {
-    switch (L / S) {
-        case 8: return run1<T, 8>(ys, y, idx, K, B, D, dup_mask, grid);
-        case 32: return run1<T, 32>(ys, y, idx, K, B, D, dup_mask, grid);
-        case 128: return run1<T, 128>(ys, y, idx, K, B, D, dup_mask, grid);
-        case 512: return run1<T, 512>(ys, y, idx, K, B, D, dup_mask, grid);
-        default: return "threads per plane not specialised";
-    }
-}
-}  // namespace
 extern "C" const char* sim_merge_cg(const void* ys, void* y, const uint16_t* idx, int K, int B, int D, int L,
                                     uint32_t dup_mask, int dtype, int grid) {
-    return dtype == TRAMBA_F32 ? run(static_cast<const float*>(ys), static_cast<float*>(y), idx, K, B, D, L, dup_mask, grid)
-                               : run(static_cast<const __nv_bfloat16*>(ys), static_cast<__nv_bfloat16*>(y), idx, K, B, D, L,
-                                     dup_mask, grid);
+    sim::sm_count = grid, sim::last_error = nullptr;
+    return done(launch_merge_skewed_cg(ys, y, idx, K, B, D, L, dup_mask, dtype, nullptr));
 }
-}  // namespace tramba
 '''
 
-KERNELS = [  # source, cut marker (everything from it on is replaced by the tail), tail, anonymous namespace still open?
-    ("ss2d_fused_fwd.cu", "}  // namespace\n\nsize_t ss2d_fused_fwd_smem", TAIL_FWD),
-    ("ss2d_fused_bwd.cu", "}  // namespace\n\nsize_t ss2d_fused_bwd_smem", TAIL_BWD),
-    (os.path.join("next", "ss2d_fused_fwd_cg.cu"),
-     "template <typename in_t, bool SOFTPLUS, int TPC, int XB>\nstatic cudaError_t launch_cg", TAIL_FWD_CG),
-    (os.path.join("next", "ss2d_fused_bwd_cg.cu"), "// Channels per item: enough rounds that the per-item", TAIL_BWD_CG),
-    ("ss2d_fused_merge.cu", "}  // namespace\n\ntemplate <typename T>\nstatic cudaError_t launch_t", TAIL_MERGE),
-    (os.path.join("next", "ss2d_fused_merge_cg.cu"), "template <typename T, int TPC>\nstatic cudaError_t launch_cg",
-     TAIL_MERGE_CG),
-]
+FUSED_FILES = ["ss2d_fused_fwd.cu", "ss2d_fused_bwd.cu", "ss2d_fused_merge.cu", os.path.join("next", "ss2d_fused_fwd_cg.cu"),
+               os.path.join("next", "ss2d_fused_bwd_cg.cu"), os.path.join("next", "ss2d_fused_merge_cg.cu")]
 
 
-def gen_kernel(rel, marker, tail):
-    s = open(os.path.join(CSRC, rel)).read()
-    i = s.index(marker)
-    s = s[:i] + tail
-    s = s.replace('#include "../ss2d_fused.cuh"', '#include "ss2d_fused.cuh"')
-    s = sub1(s, "extern __shared__ __align__(128) unsigned char smem[];", "unsigned char* smem = sim::smem();")
-    s = RED.sub(r"sim::red_add_v2(\1, \2, \3);", s)
-    assert "asm" not in s.replace("__nv_bfloat16", ""), rel
-    out = os.path.join(GEN, os.path.basename(rel).replace(".cu", "_sim.cpp"))
-    open(out, "w").write(s)
-    return out
+def gen_fused():
+    drv = os.path.join(GEN, "fused_driver_sim.cpp")
+    open(drv, "w").write(FUSED_DRIVER)
+    return [gen_whole_file(f) for f in FUSED_FILES] + [drv]
 
 
 LAUNCH = re.compile(r"([\w:]+(?:<[^<>;]*>)?)<<<(.+?), (.+?), (.+?), st>>>\((.*?)\);", re.S)
@@ -310,6 +195,9 @@ def gen_whole_file(rel):
                   "sim::cp_async_g(dst, src, 16);")
     s = s.replace('asm volatile("cp.async.commit_group;" ::: "memory");', "sim::cp_commit();")
     s = s.replace('asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");', "sim::cp_wait(N);")
+    s = RED.sub(r"sim::red_add_v2(\1, \2, \3);", s)
+    s = re.sub(r"static int sms = 0(, occ = 0)?;", r"int sms = 0\1;", s)     # the SM count is per call in the simulator
+    s = s.replace('#include "../ss2d_fused.cuh"', '#include "ss2d_fused.cuh"')
     s = MACRO_LAUNCH.sub(r"sim::launch_kernel(\2, \3, \4, [&] { \1(\5); })", s)
     s = LAUNCH.sub(r"sim::launch_kernel(\2, \3, \4, [&] { \1(\5); });", s)
     s = RED4.sub(r"sim::red_add_v4(\1, \2, \3, \4, \5);", s)
@@ -448,6 +336,20 @@ def gen_side():
     return out + [drv]
 
 
+def gen_abi():
+    """capi.cu (argument validation, plan selection: the real extern "C" entry points) and orders.cpp (host tables):
+    with them the simulator library exports the product's whole C ABI, computed by the product's kernels."""
+    src = gen_whole_file("capi.cu")
+    t = open(src).read()
+    t = sub1(t, '#include "common.cuh"', '#include "sim_common.h"')
+    open(src, "w").write(t)
+    o = open(os.path.join(CSRC, "orders.cpp")).read()
+    o = sub1(o, '#include "../../include/tramba_b200.h"', '#include "tramba_b200.h"')
+    dst = os.path.join(GEN, "orders_sim.cpp")
+    open(dst, "w").write(o)
+    return [src, dst]
+
+
 def gen_sscan():
     h = open(os.path.join(CSRC, "sscan.cuh")).read()
     h = sub1(h, '#include "common.cuh"', '#include "sim_common.h"')
@@ -459,7 +361,7 @@ def gen_sscan():
 
 def build(force=False):
     os.makedirs(GEN, exist_ok=True)
-    deps = [os.path.join(CSRC, k[0]) for k in KERNELS] + [os.path.join(CSRC, f) for f in ("sscan.cuh", "sscan_fwd.cu",
+    deps = [os.path.join(CSRC, f) for f in FUSED_FILES] + [os.path.join(CSRC, f) for f in ("capi.cu", "orders.cpp","sscan.cuh", "sscan_fwd.cu",
                                                                                          "sscan_bwd.cu", "cross_scan.cu", "dwconv2d.cu",
                                                                                          "proj_gather.cu", "layernorm2d.cu",
                                                                                          "dct2d.cu", "dct2d_tc.cu")] + [
@@ -469,7 +371,7 @@ def build(force=False):
     if not force and os.path.exists(LIB) and all(os.path.getmtime(d) <= os.path.getmtime(LIB) for d in deps):
         return LIB
     gen_header()
-    srcs = [gen_kernel(*k) for k in KERNELS] + gen_sscan() + gen_scan() + gen_side()
+    srcs = gen_fused() + gen_sscan() + gen_scan() + gen_side() + gen_abi()
     srcs.append(os.path.join(HERE, "selftest.cpp"))
     flags = ["-std=c++17", "-O1", "-fPIC", "-w", "-I" + HERE, "-I" + GEN, "-I" + os.path.join(ROOT, "include"),
              "-I/usr/local/cuda/include"]

@@ -52,3 +52,4 @@ extern "C" const char* sim_selftest_mbar(int complete, float* out) {
 }
 extern "C" void sim_set_lazy(int on) { sim::lazy = on != 0; }
 extern "C" int sim_last_cluster_size() { return sim::last_cluster_size; }
+extern "C" void sim_set_sm_count(int n) { sim::sm_count = n; }

@@ -409,7 +409,7 @@ inline cudaError_t cudaGetDevice(int* dev) {
     return cudaSuccess;
 }
 inline cudaError_t cudaDeviceGetAttribute(int* v, cudaDeviceAttr attr, int) {
-    *v = attr == cudaDevAttrMultiProcessorCount ? sim::sm_count : 0;
+    *v = attr == cudaDevAttrMultiProcessorCount ? sim::sm_count : attr == cudaDevAttrComputeCapabilityMajor ? 10 : 0;
     return cudaSuccess;
 }
 inline cudaError_t cudaGetLastError() { return sim::last_error ? cudaErrorLaunchFailure : cudaSuccess; }
@@ -514,7 +514,7 @@ namespace tramba {
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kLn2 = 0.6931471805599453f;
 
-inline void note_launch() {}
+void note_launch();   // capi.cu (translated) defines it
 
 // ---- mbarrier + TMA bulk: the same names as csrc/common.cuh
 inline void mbar_init(uint64_t* bar, uint32_t count) {
