@@ -280,7 +280,7 @@ class _SimLib:
     """The product's C ABI exported by tools/cpu_sim's library: the REAL entry points (capi.cu) and the REAL kernels
     (every .cu of the library), compiled as host code and executed on the CPU simulator."""
 
-    def __init__(self, sms=4):
+    def __init__(self, sms=4, next_variant=False):
         import importlib.util
         import os
         from tramba_b200 import _lib
@@ -288,7 +288,7 @@ class _SimLib:
         spec = importlib.util.spec_from_file_location("build_sim", os.path.join(root, "tools", "cpu_sim", "build_sim.py"))
         mod = importlib.util.module_from_spec(spec)
         spec.loader.exec_module(mod)
-        self._dll = ctypes.CDLL(mod.build())
+        self._dll = ctypes.CDLL(mod.build(next_variant=next_variant))
         for name, (res, args) in _lib.SIGNATURES.items():
             fn = getattr(self._dll, name)
             fn.restype, fn.argtypes = res, args
@@ -311,12 +311,13 @@ class _SimLib:
 def installed(backend="oracle", sms=4):
     """Within this scope the product's Python host runs on CPU tensors against
       backend="oracle": the compute entry points emulated by the oracle (fast; checks the host logic only), or
-      backend="sim":    the product's own C ABI and kernels executed on the CPU simulator (tools/cpu_sim)."""
+      backend="sim":    the product's own C ABI and kernels executed on the CPU simulator (tools/cpu_sim);
+      backend="sim-next": the same with -DTRAMBA_NEXT, i.e. dispatching to the candidate kernels of csrc/next/."""
     from tramba_b200 import _lib
     saved = (_lib.lib, torch.Tensor.cuda, torch.nn.Module.cuda, torch.cuda.current_stream, torch.cuda.device)
-    proxy = _Proxy(_lib.lib) if backend == "oracle" else _SimLib(sms)
+    proxy = _Proxy(_lib.lib) if backend == "oracle" else _SimLib(sms, next_variant=(backend == "sim-next"))
     _lib.lib = proxy
-    torch.Tensor.cuda = lambda self, *a, **k: self
+    torch.Tensor.cuda = lambda self, *a, **k: self.clone()        # like the real one: a new tensor, differentiable
     torch.nn.Module.cuda = lambda self, *a, **k: self
     torch.Tensor.is_cuda = property(lambda self: True)
     torch.cuda.current_stream = lambda *a, **k: _Stream()

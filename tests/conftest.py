@@ -39,10 +39,12 @@ def golden_ablation():
 # on the CPU simulator (tools/cpu_sim; tests/_abi_emulator.py: installed("sim")).  "cuda" devices are mapped to the
 # CPU for the session.  Meant for the small / medium cases (`-k ...`): BASELINE-size tests take minutes to hours there.
 #     TRAMBA_GPU_TESTS_ON_SIM=1 python -m pytest tests/test_z_gpu_ablation.py -m gpu -q
+#     TRAMBA_GPU_TESTS_ON_SIM=next ...      the same with the candidate kernels of csrc/next/ dispatched (-DTRAMBA_NEXT)
 # ----------------------------------------------------------------------------------------------------------------
 @pytest.fixture(scope="session", autouse=True)
 def _gpu_tests_on_the_simulator():
-    if os.environ.get("TRAMBA_GPU_TESTS_ON_SIM", "") != "1":
+    mode = os.environ.get("TRAMBA_GPU_TESTS_ON_SIM", "")
+    if mode not in ("1", "next"):
         yield
         return
     import functools
@@ -70,14 +72,16 @@ def _gpu_tests_on_the_simulator():
         setattr(torch, n, wrap(saved[n]))
 
     def to(self, *a, **k):
+        moved = any(cpu_device(x) is not x for x in a) or ("device" in k and cpu_device(k["device"]) is not k["device"])
         a = tuple(cpu_device(x) for x in a)
         if "device" in k:
             k["device"] = cpu_device(k["device"])
-        return saved_to(self, *a, **k)
+        out = saved_to(self, *a, **k)
+        return out.clone() if moved and out is self else out       # a host -> device move is a copy
 
     torch.Tensor.to = to
     torch.cuda.synchronize = lambda *a, **k: None
-    with installed("sim", sms=4):
+    with installed("sim-next" if mode == "next" else "sim", sms=4):     # "next": the candidate kernels (csrc/next/)
         yield
     for n in names:
         setattr(torch, n, saved[n])

@@ -359,7 +359,16 @@ def gen_sscan():
     return [gen_whole_file("sscan_fwd.cu"), gen_whole_file("sscan_bwd.cu"), drv]
 
 
-def build(force=False):
+def build(force=False, next_variant=False):
+    """next_variant: compile with -DTRAMBA_NEXT, i.e. the product launchers dispatch to the candidate kernels of
+    csrc/next/ exactly as libtramba_b200_next.so does (library: libtramba_sim_next.so)."""
+    global GEN, LIB
+    if next_variant:
+        GEN = os.path.join(HERE, "_gen_next")
+        LIB = os.path.join(GEN, "libtramba_sim_next.so")
+    else:
+        GEN = os.path.join(HERE, "_gen")
+        LIB = os.path.join(GEN, "libtramba_sim.so")
     os.makedirs(GEN, exist_ok=True)
     deps = [os.path.join(CSRC, f) for f in FUSED_FILES] + [os.path.join(CSRC, f) for f in ("capi.cu", "orders.cpp","sscan.cuh", "sscan_fwd.cu",
                                                                                          "sscan_bwd.cu", "cross_scan.cu", "dwconv2d.cu",
@@ -374,7 +383,7 @@ def build(force=False):
     srcs = gen_fused() + gen_sscan() + gen_scan() + gen_side() + gen_abi()
     srcs.append(os.path.join(HERE, "selftest.cpp"))
     flags = ["-std=c++17", "-O1", "-fPIC", "-w", "-I" + HERE, "-I" + GEN, "-I" + os.path.join(ROOT, "include"),
-             "-I/usr/local/cuda/include"]
+             "-I/usr/local/cuda/include"] + (["-DTRAMBA_NEXT"] if next_variant else [])
     objs = [os.path.join(GEN, os.path.splitext(os.path.basename(f))[0] + ".o") for f in srcs]
     from concurrent.futures import ThreadPoolExecutor
     with ThreadPoolExecutor(max_workers=min(len(srcs), os.cpu_count() or 4)) as ex:
@@ -389,4 +398,4 @@ def build(force=False):
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv))
+    print(build(force="--force" in sys.argv, next_variant="--next" in sys.argv))
