@@ -294,6 +294,9 @@ class _SimLib:
             fn.restype, fn.argtypes = res, args
         self._dll.sim_set_sm_count.restype, self._dll.sim_set_sm_count.argtypes = None, [ctypes.c_int]
         self._dll.sim_set_sm_count(sms)
+        self._dll.sim_set_lazy.restype, self._dll.sim_set_lazy.argtypes = None, [ctypes.c_int]
+        import os as _os
+        self._dll.sim_set_lazy(1 if _os.environ.get("TRAMBA_SIM_LAZY", "") == "1" else 0)   # copies land at the wait
         self.calls = []
 
     def __getattr__(self, name):
