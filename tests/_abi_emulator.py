@@ -297,6 +297,8 @@ class _SimLib:
         self._dll.sim_set_lazy.restype, self._dll.sim_set_lazy.argtypes = None, [ctypes.c_int]
         import os as _os
         self._dll.sim_set_lazy(1 if _os.environ.get("TRAMBA_SIM_LAZY", "") == "1" else 0)   # copies land at the wait
+        self._dll.sim_set_schedule.restype, self._dll.sim_set_schedule.argtypes = None, [ctypes.c_uint]
+        self._dll.sim_set_schedule(int(_os.environ.get("TRAMBA_SIM_SCHEDULE", "0")))       # thread order per sweep
         self.calls = []
 
     def __getattr__(self, name):

@@ -47,8 +47,14 @@ def sim():
         fn = getattr(lib, name)
         fn.restype, fn.argtypes = ctypes.c_char_p, [ctypes.POINTER(FusedArgs), ctypes.c_int, ctypes.c_int]
     lib.sim_set_lazy.restype, lib.sim_set_lazy.argtypes = None, [ctypes.c_int]
+    lib.sim_set_schedule.restype, lib.sim_set_schedule.argtypes = None, [ctypes.c_uint]
+    # TRAMBA_SIM_SCHEDULE = 0 (default: ascending thread order) | 1 (descending) | n >= 2 (random permutation per sweep,
+    # seed n): every test of this file must pass under every schedule -- a result that depends on the order in which
+    # the threads of a barrier interval run is a missing barrier
+    lib.sim_set_schedule(int(os.environ.get("TRAMBA_SIM_SCHEDULE", "0")))
     yield lib
     lib.sim_set_lazy(0)
+    lib.sim_set_schedule(0)
 
 
 def _dev(t, bf16):
@@ -470,3 +476,18 @@ def test_dct2d_on_the_cpu_simulator(sim, planes, H, tc):
         assert err is None, err.decode()
         ref = odct.dct2d_split_bwd(gh[None].astype(np.float64), gl[None].astype(np.float64), H, H)
         _close(gx, torch.from_numpy(np.ascontiguousarray(ref[0])), 1e-5, "gx")
+
+
+def test_schedule_shuffling_exposes_a_missing_barrier(sim):
+    """The detector behind TRAMBA_SIM_SCHEDULE: a kernel that reads a neighbour's shared-memory slot without a barrier
+    gives schedule-dependent results; the library's kernels must not (the whole file is run under schedules 1, 7, 12345
+    as well as the default -- see profiles/r01_offline_gpu_tests_on_simulator.txt)."""
+    sim.sim_selftest_race.restype, sim.sim_selftest_race.argtypes = ctypes.c_char_p, [ctypes.c_void_p]
+    outs = []
+    for mode in (0, 1, 7):
+        sim.sim_set_schedule(mode)
+        o = np.zeros(64, np.float32)
+        assert sim.sim_selftest_race(o.ctypes.data) is None
+        outs.append(o.copy())
+    sim.sim_set_schedule(int(os.environ.get("TRAMBA_SIM_SCHEDULE", "0")))
+    assert not (np.array_equal(outs[0], outs[1]) and np.array_equal(outs[0], outs[2]))

@@ -53,3 +53,18 @@ extern "C" const char* sim_selftest_mbar(int complete, float* out) {
 extern "C" void sim_set_lazy(int on) { sim::lazy = on != 0; }
 extern "C" int sim_last_cluster_size() { return sim::last_cluster_size; }
 extern "C" void sim_set_sm_count(int n) { sim::sm_count = n; }
+extern "C" void sim_set_schedule(unsigned mode) { sim::sched_mode = mode; }
+
+namespace {
+void racy_kernel(float* out) {        // thread t reads its neighbour's slot without a barrier after the write
+    float* buf = reinterpret_cast<float*>(sim::smem());
+    const int tid = threadIdx.x;
+    buf[tid] = static_cast<float>(tid + 1);
+    // missing __syncthreads()
+    out[tid] = buf[(tid + 1) % blockDim.x];
+    __syncthreads();
+}
+}  // namespace
+extern "C" const char* sim_selftest_race(float* out) {
+    return sim::launch(1, 64, 64 * 4, [&] { racy_kernel(out); });
+}

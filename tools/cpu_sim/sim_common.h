@@ -301,6 +301,15 @@ struct Dim3 {
     int x = 1, y = 1, z = 1;
 };
 inline int last_cluster_size = 0;   // CTAs per cluster of the most recent launch (tests check which path ran)
+// Order in which the runnable fibers of a sweep are resumed: 0 = ascending thread index, 1 = descending, >= 2 = a
+// fresh pseudo-random permutation per sweep (seeded with the value).  Results must not depend on it: two threads that
+// touch the same shared-memory word between two barriers (a missing __syncthreads) give order-dependent results.
+inline unsigned sched_mode = 0;
+inline unsigned sched_state = 1;
+inline unsigned sched_rand() {
+    sched_state = sched_state * 1664525u + 1013904223u;
+    return sched_state >> 8;
+}
 // Runs `body` as grid x nthreads CUDA threads.  CTAs run one cluster at a time (cluster = {1,1,1}: one CTA at a
 // time); the CTAs of a cluster run concurrently, which cluster.sync() and distributed shared memory need.
 inline const char* launch3(Dim3 grid, Dim3 cl, int nthreads, size_t smem_bytes, std::function<void()> body) {
@@ -354,13 +363,19 @@ inline const char* launch3(Dim3 grid, Dim3 cl, int nthreads, size_t smem_bytes, 
                             }
                         }
                 int alive = 1;
+                std::vector<int> order(nthreads);
+                for (int t = 0; t < nthreads; ++t) order[t] = sched_mode == 1 ? nthreads - 1 - t : t;
+                if (sched_mode >= 2) sched_state = sched_mode;
                 while (alive > 0 && !err) {
                     long long before = 0;
                     for (Cta& c : ctas) before += c.progress;
                     alive = 0;
+                    if (sched_mode >= 2)
+                        for (int t = nthreads - 1; t > 0; --t) std::swap(order[t], order[sched_rand() % (t + 1)]);
                     for (Cta& cta : ctas) {
                         g = &cta;
-                        for (int t = 0; t < nthreads; ++t) {
+                        for (int oi = 0; oi < nthreads; ++oi) {
+                            const int t = order[oi];
                             if (cta.done[t]) continue;
                             cta.cur = t;
                             cta.sched_ptr = &sched;
