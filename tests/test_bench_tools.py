@@ -23,6 +23,10 @@ def test_kernel_name_to_kind():
     assert b.kind_of("tramba::ln2d_bwd_reg_kernel<float, __nv_bfloat16, 1>") == "layernorm2d_bwd"
     assert b.kind_of("tramba::merge_skewed_kernel<__nv_bfloat16>") == "cross_merge_skewed"
     assert b.kind_of("at::native::vectorized_elementwise_kernel<4, ...>") is None
+    # the candidate kernels (TRAMBA_B200_LIB=next) report under the same kinds
+    assert b.kind_of("tramba::ss2d_bwd_cg_kernel<__nv_bfloat16, true, 512, 2>") == "ss2d_fused_bwd"
+    assert b.kind_of("tramba::ss2d_fwd_cg_kernel<float, true, 32, 1>") == "ss2d_fused_fwd"
+    assert b.kind_of("tramba::merge_skewed_cg_kernel<__nv_bfloat16, 128>") == "cross_merge_skewed"
 
 
 def test_roofline_traffic_json_matches_committed_ncu_list(tmp_path):
