@@ -78,8 +78,6 @@ def test_harness_product_host_emulated_abi_matches_reference_golden():
     _check(m, outs, loss, 1e-3)
 
 
-@pytest.mark.skipif(os.environ.get("TRAMBA_SIM_MODEL", "") != "1",
-                    reason="4-5 minutes on the CPU simulator: run with TRAMBA_SIM_MODEL=1 (passed in round 1, DESIGN 8)")
 def test_harness_on_the_simulated_library_matches_reference_golden():
     """The whole Tramba-V forward + backward on the product's OWN C ABI and kernel sources, compiled as host code and
     executed on the CPU simulator (tools/cpu_sim): 27 fused-core + 6 op-by-op SS2D calls, 108 LayerNorm2d launches

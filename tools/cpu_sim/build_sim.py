@@ -382,7 +382,8 @@ def build(force=False, next_variant=False):
     gen_header()
     srcs = gen_fused() + gen_sscan() + gen_scan() + gen_side() + gen_abi()
     srcs.append(os.path.join(HERE, "selftest.cpp"))
-    flags = ["-std=c++17", "-O1", "-fPIC", "-w", "-I" + HERE, "-I" + GEN, "-I" + os.path.join(ROOT, "include"),
+    flags = ["-std=c++17", "-O1", "-fPIC", "-w", "-U_FORTIFY_SOURCE", "-D_FORTIFY_SOURCE=0",   # _longjmp across fiber stacks
+             "-I" + HERE, "-I" + GEN, "-I" + os.path.join(ROOT, "include"),
              "-I/usr/local/cuda/include"] + (["-DTRAMBA_NEXT"] if next_variant else [])
     objs = [os.path.join(GEN, os.path.splitext(os.path.basename(f))[0] + ".o") for f in srcs]
     from concurrent.futures import ThreadPoolExecutor

@@ -21,6 +21,7 @@
 #include <vector_types.h>
 #include <vector_functions.h>
 #include <stdint.h>
+#include <setjmp.h>
 #include <ucontext.h>
 
 #include <cmath>
@@ -71,7 +72,13 @@ struct Cta {
     std::vector<std::vector<Copy>> thread_stores;                      // lazy s2g bulk stores of each thread (open group)
     std::vector<std::vector<std::vector<Copy>>> thread_groups;         // ... and its committed bulk async-groups, oldest first
     unsigned char* smem = nullptr;
-    ucontext_t* sched_ptr = nullptr;
+    ucontext_t* sched_ptr = nullptr;               // ucontext only BOOTSTRAPS a fiber (first entry); every later switch is
+    jmp_buf* sched_jb = nullptr;                   // _setjmp / _longjmp: swapcontext costs a sigprocmask system call each time
+    struct Jb {
+        jmp_buf b;
+    };
+    std::vector<Jb> jb;
+    std::vector<char> started;
     std::vector<ucontext_t> ctx;
     std::vector<char> done;
     int cur = 0;
@@ -99,7 +106,7 @@ inline unsigned char* smem() { return g->smem; }
 
 inline void yield() {
     Cta* me = g;   // the scheduler repoints g at whichever CTA it resumes next; it is restored before we continue
-    swapcontext(&me->ctx[me->cur], me->sched_ptr);
+    if (_setjmp(me->jb[me->cur].b) == 0) _longjmp(*me->sched_jb, 1);
 }
 
 inline void syncthreads() {
@@ -327,25 +334,39 @@ inline const char* launch3(Dim3 grid, Dim3 cl, int nthreads, size_t smem_bytes, 
     for (int oz = 0; oz < grid.z && !err; oz += cl.z)
         for (int oy = 0; oy < grid.y && !err; oy += cl.y)
             for (int ox = 0; ox < grid.x && !err; ox += cl.x) {
-                std::vector<Cta> ctas(csize);
+                static std::vector<Cta> ctas;                 // pooled: their per-thread vectors keep their capacity
+                if (static_cast<int>(ctas.size()) < csize) ctas.resize(csize);
                 Cluster cluster;
                 cluster.threads = nthreads * csize;
                 ucontext_t sched;
+                jmp_buf sched_jb;
                 int r = 0;
                 for (int cz = 0; cz < cl.z; ++cz)
                     for (int cy = 0; cy < cl.y; ++cy)
                         for (int cx = 0; cx < cl.x; ++cx, ++r) {
                             Cta& cta = ctas[r];
+                            cta.bar_count = cta.bar_gen = 0, cta.progress = 0, cta.error = nullptr, cta.cur = 0;
+                            cta.mbars.clear(), cta.bar_copies.clear(), cta.bar_tx.clear();
+                            cta.sshared_used = 0, cta.sshared_at.clear();
                             cta.nthreads = nthreads, cta.rank = r, cta.cluster = &cluster;
                             cta.bx = ox + cx, cta.by = oy + cy, cta.bz = oz + cz;
                             cta.gdim = grid.x, cta.gdim_y = grid.y, cta.gdim_z = grid.z;
                             cta.smem = static_cast<unsigned char*>(raws[r]);
                             std::memset(cta.smem, 0xCD, smem_bytes);   // poison: uninitialised shared memory must show
-                            cta.sshared.assign(48 * 1024, 0xCD);
-                            cta.ctx.resize(nthreads), cta.done.assign(nthreads, 0), cta.warps.resize((nthreads + 31) / 32);
-                            cta.thread_async.resize(nthreads), cta.thread_stores.resize(nthreads);
-                            cta.thread_groups.resize(nthreads), cta.thread_cp.resize(nthreads);
-                            cta.thread_cp_groups.resize(nthreads);
+                            if (cta.sshared.size() != 48 * 1024) cta.sshared.resize(48 * 1024);
+                            std::memset(cta.sshared.data(), 0xCD, 16 * 1024);   // the kernels' static arrays fit 16 KB
+                            cta.ctx.resize(nthreads), cta.done.assign(nthreads, 0);
+                            cta.jb.resize(nthreads), cta.started.assign(nthreads, 0);
+                            cta.sched_jb = &sched_jb;
+                            cta.warps.assign((nthreads + 31) / 32, Warp{});
+                            for (auto* v : {&cta.thread_async, &cta.thread_stores, &cta.thread_cp}) {
+                                v->resize(nthreads);
+                                for (auto& q : *v) q.clear();
+                            }
+                            for (auto* v : {&cta.thread_groups, &cta.thread_cp_groups}) {
+                                v->resize(nthreads);
+                                for (auto& q : *v) q.clear();
+                            }
                             cluster.ctas.push_back(&cta);
                             for (int t = 0; t < nthreads; ++t) {
                                 getcontext(&cta.ctx[t]);
@@ -358,6 +379,7 @@ inline const char* launch3(Dim3 grid, Dim3 cl, int nthreads, size_t smem_bytes, 
                                                 cp_wait(0);
                                                 g->done[g->cur] = 1;
                                                 ++g->progress;
+                                                _longjmp(*g->sched_jb, 1);     // never falls off the fiber's stack
                                             }),
                                             0);
                             }
@@ -368,24 +390,32 @@ inline const char* launch3(Dim3 grid, Dim3 cl, int nthreads, size_t smem_bytes, 
                 if (sched_mode >= 2) sched_state = sched_mode;
                 while (alive > 0 && !err) {
                     long long before = 0;
-                    for (Cta& c : ctas) before += c.progress;
+                    for (int ci = 0; ci < csize; ++ci) before += ctas[ci].progress;
                     alive = 0;
                     if (sched_mode >= 2)
                         for (int t = nthreads - 1; t > 0; --t) std::swap(order[t], order[sched_rand() % (t + 1)]);
-                    for (Cta& cta : ctas) {
+                    for (int ci = 0; ci < csize; ++ci) {
+                        Cta& cta = ctas[ci];
                         g = &cta;
                         for (int oi = 0; oi < nthreads; ++oi) {
                             const int t = order[oi];
                             if (cta.done[t]) continue;
                             cta.cur = t;
                             cta.sched_ptr = &sched;
-                            swapcontext(&sched, &cta.ctx[t]);
+                            if (_setjmp(sched_jb) == 0) {
+                                if (!cta.started[t]) {
+                                    cta.started[t] = 1;
+                                    setcontext(&cta.ctx[t]);              // first entry: onto the fiber's own stack
+                                } else {
+                                    _longjmp(cta.jb[t].b, 1);
+                                }
+                            }
                             if (!cta.done[t]) ++alive;
                         }
                         if (cta.error) err = cta.error;
                     }
                     long long after = 0;
-                    for (Cta& c : ctas) after += c.progress;
+                    for (int ci = 0; ci < csize; ++ci) after += ctas[ci].progress;
                     if (alive > 0 && after == before && !err) err = "deadlock: every live thread is blocked";
                 }
                 g = nullptr;

@@ -1,6 +1,6 @@
 #!/bin/bash
 # Runs the `-m gpu` test files WITHOUT a GPU, against the product's own C ABI and kernel sources executed on the CPU
-# simulator (tools/cpu_sim; tests/conftest.py: TRAMBA_GPU_TESTS_ON_SIM).  About 20 minutes on 8 cores.
+# simulator (tools/cpu_sim; tests/conftest.py: TRAMBA_GPU_TESTS_ON_SIM).  A few minutes on 8 cores.
 #   bash tools/run_gpu_tests_on_sim.sh            product kernels
 #   bash tools/run_gpu_tests_on_sim.sh next       candidate kernels of csrc/next/ dispatched (-DTRAMBA_NEXT)
 # Extra checks: TRAMBA_SIM_LAZY=1 (asynchronous copies land at their wait), TRAMBA_SIM_SCHEDULE=n (thread order).
@@ -17,8 +17,8 @@ out=$(TRAMBA_GPU_TESTS_ON_SIM=$mode timeout 1800 python -m pytest tests/test_gpu
       -p no:cacheprovider -k "not config2 and not full and not 9216 and not 192" 2>&1 | tail -1)
 echo "== test_gpu_sscan (small and medium cases): $out"
 case "$out" in *failed*|*error*) rc=1;; esac
-# whole-model parity on the simulated library (4-5 minutes)
-out=$(TRAMBA_SIM_MODEL=1 timeout 1800 python -m pytest tests/test_model_parity.py -q -k simulated -p no:cacheprovider 2>&1 | tail -1)
+# whole-model parity on the simulated library
+out=$(timeout 1800 python -m pytest tests/test_model_parity.py -q -k simulated -p no:cacheprovider 2>&1 | tail -1)
 echo "== test_model_parity (simulated library): $out"
 case "$out" in *failed*|*error*) rc=1;; esac
 exit $rc
