@@ -12,7 +12,8 @@ for f in test_gpu_scan_merge test_gpu_proj_gather test_gpu_ss2d test_gpu_fused t
   echo "== $f: $out"
   case "$out" in *failed*|*error*) rc=1;; esac
 done
-# the operator selective scan: everything but the two BASELINE-size cases (hours on the simulator)
+# the operator selective scan: everything but the two BASELINE-size cases (3.5 minutes on the simulator; add them with
+# `TRAMBA_GPU_TESTS_ON_SIM=1 python -m pytest tests/test_gpu_sscan.py -m gpu -k "config2 or full"`)
 out=$(TRAMBA_GPU_TESTS_ON_SIM=$mode timeout 1800 python -m pytest tests/test_gpu_sscan.py -m gpu -q --timeout 600 \
       -p no:cacheprovider -k "not config2 and not full and not 9216 and not 192" 2>&1 | tail -1)
 echo "== test_gpu_sscan (small and medium cases): $out"
