@@ -78,14 +78,16 @@ def test_harness_product_host_emulated_abi_matches_reference_golden():
     _check(m, outs, loss, 1e-3)
 
 
-def test_harness_on_the_simulated_library_matches_reference_golden():
+@pytest.mark.parametrize("backend", ["sim", "sim-next"], ids=["product-kernels", "candidate-kernels"])
+def test_harness_on_the_simulated_library_matches_reference_golden(backend):
     """The whole Tramba-V forward + backward on the product's OWN C ABI and kernel sources, compiled as host code and
     executed on the CPU simulator (tools/cpu_sim): 27 fused-core + 6 op-by-op SS2D calls, 108 LayerNorm2d launches
     (cluster kernels included), depthwise convs, proj gathers, 3 tensor-pipe DCTs -- against the REAL reference's
-    fixture.  Nothing is computed by the oracle here."""
+    fixture.  Nothing is computed by the oracle here.  "candidate-kernels": the same with the launchers dispatching to
+    the compile-time-geometry kernels of csrc/next/ (-DTRAMBA_NEXT), which have not run on a GPU yet."""
     from _abi_emulator import installed
     m = det_fill(build_model(img_size=384, dims=int(GOLD["dims"]))).eval()
-    with installed("sim") as lib:
+    with installed(backend) as lib:
         outs, loss = _run(m, "cpu")
     assert lib.calls.count("tramba_ss2d_fused_fwd") == 27 and lib.calls.count("tramba_sscan_fwd") == 6
     assert lib.calls.count("tramba_dct2d_fwd") == 3 and lib.calls.count("tramba_layernorm2d_fwd") > 100
