@@ -288,14 +288,15 @@ class _SimLib:
         spec = importlib.util.spec_from_file_location("build_sim", os.path.join(root, "tools", "cpu_sim", "build_sim.py"))
         mod = importlib.util.module_from_spec(spec)
         spec.loader.exec_module(mod)
-        self._dll = ctypes.CDLL(mod.build(next_variant=next_variant))
+        import os as _os
+        asan = _os.environ.get("TRAMBA_SIM_ASAN", "") == "1"          # AddressSanitizer build (needs libasan preloaded)
+        self._dll = ctypes.CDLL(mod.build(next_variant=next_variant and not asan, asan=asan))
         for name, (res, args) in _lib.SIGNATURES.items():
             fn = getattr(self._dll, name)
             fn.restype, fn.argtypes = res, args
         self._dll.sim_set_sm_count.restype, self._dll.sim_set_sm_count.argtypes = None, [ctypes.c_int]
         self._dll.sim_set_sm_count(sms)
         self._dll.sim_set_lazy.restype, self._dll.sim_set_lazy.argtypes = None, [ctypes.c_int]
-        import os as _os
         self._dll.sim_set_lazy(1 if _os.environ.get("TRAMBA_SIM_LAZY", "") == "1" else 0)   # copies land at the wait
         self._dll.sim_set_schedule.restype, self._dll.sim_set_schedule.argtypes = None, [ctypes.c_uint]
         self._dll.sim_set_schedule(int(_os.environ.get("TRAMBA_SIM_SCHEDULE", "0")))       # thread order per sweep

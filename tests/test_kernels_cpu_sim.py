@@ -42,7 +42,9 @@ def sim():
     spec = importlib.util.spec_from_file_location("build_sim", os.path.join(ROOT, "tools", "cpu_sim", "build_sim.py"))
     mod = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(mod)
-    lib = ctypes.CDLL(mod.build())
+    # TRAMBA_SIM_ASAN=1 (with LD_PRELOAD=$(gcc -print-file-name=libasan.so) ASAN_OPTIONS=detect_leaks=0): the
+    # AddressSanitizer build -- an out-of-bounds global or shared memory access of a kernel aborts the run
+    lib = ctypes.CDLL(mod.build(asan=os.environ.get("TRAMBA_SIM_ASAN", "") == "1"))
     for name in ("sim_fwd", "sim_bwd", "sim_fwd_cg", "sim_bwd_cg"):
         fn = getattr(lib, name)
         fn.restype, fn.argtypes = ctypes.c_char_p, [ctypes.POINTER(FusedArgs), ctypes.c_int, ctypes.c_int]

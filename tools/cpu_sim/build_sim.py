@@ -359,11 +359,14 @@ def gen_sscan():
     return [gen_whole_file("sscan_fwd.cu"), gen_whole_file("sscan_bwd.cu"), drv]
 
 
-def build(force=False, next_variant=False):
+def build(force=False, next_variant=False, asan=False):
     """next_variant: compile with -DTRAMBA_NEXT, i.e. the product launchers dispatch to the candidate kernels of
     csrc/next/ exactly as libtramba_b200_next.so does (library: libtramba_sim_next.so)."""
     global GEN, LIB
-    if next_variant:
+    if asan:     # AddressSanitizer build: out-of-bounds global / shared memory accesses of the kernels abort the run
+        GEN = os.path.join(HERE, "_gen_asan")
+        LIB = os.path.join(GEN, "libtramba_sim_asan.so")
+    elif next_variant:
         GEN = os.path.join(HERE, "_gen_next")
         LIB = os.path.join(GEN, "libtramba_sim_next.so")
     else:
@@ -384,7 +387,8 @@ def build(force=False, next_variant=False):
     srcs.append(os.path.join(HERE, "selftest.cpp"))
     flags = ["-std=c++17", "-O1", "-fPIC", "-w", "-U_FORTIFY_SOURCE", "-D_FORTIFY_SOURCE=0",   # _longjmp across fiber stacks
              "-I" + HERE, "-I" + GEN, "-I" + os.path.join(ROOT, "include"),
-             "-I/usr/local/cuda/include"] + (["-DTRAMBA_NEXT"] if next_variant else [])
+             "-I/usr/local/cuda/include"] + (["-DTRAMBA_NEXT"] if next_variant else []) + (
+                 ["-fsanitize=address", "-fno-omit-frame-pointer", "-g", "-DSIM_ASAN"] if asan else [])
     objs = [os.path.join(GEN, os.path.splitext(os.path.basename(f))[0] + ".o") for f in srcs]
     from concurrent.futures import ThreadPoolExecutor
     with ThreadPoolExecutor(max_workers=min(len(srcs), os.cpu_count() or 4)) as ex:
@@ -394,9 +398,9 @@ def build(force=False, next_variant=False):
         if res.returncode != 0:
             sys.stderr.write(res.stdout + res.stderr)
             raise RuntimeError("cpu_sim build failed")
-    subprocess.check_call(["g++", "-shared", "-o", LIB] + objs)
+    subprocess.check_call(["g++", "-shared", "-o", LIB] + objs + (["-fsanitize=address"] if asan else []))
     return LIB
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, next_variant="--next" in sys.argv))
+    print(build(force="--force" in sys.argv, next_variant="--next" in sys.argv, asan="--asan" in sys.argv))

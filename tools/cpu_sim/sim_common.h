@@ -328,7 +328,11 @@ inline const char* launch3(Dim3 grid, Dim3 cl, int nthreads, size_t smem_bytes, 
     while (static_cast<int>(stacks.size()) < nthreads * csize) stacks.push_back(static_cast<char*>(std::malloc(kStack)));
     std::vector<void*> raws(csize, nullptr);
     for (void*& r : raws)
+#ifdef SIM_ASAN   // exact size: AddressSanitizer's red zones sit right behind the dynamic shared memory
+        if (posix_memalign(&r, 1024, smem_bytes ? smem_bytes : 16) != 0) return "out of memory";
+#else
         if (posix_memalign(&r, 1024, smem_bytes + 1024) != 0) return "out of memory";
+#endif
     const char* err = nullptr;
     g_body = &body;
     for (int oz = 0; oz < grid.z && !err; oz += cl.z)
