@@ -142,6 +142,14 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
+    # This arm is the reference's CPU path: it must not map our CUDA library (the driver records which .so files a
+    # bench process loads) and it uses every host core even under torchrun (which exports OMP_NUM_THREADS=1).
+    os.environ["TRAMBA_B200_NO_LIB"] = "1"
+    ncores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    os.environ["OMP_NUM_THREADS"] = str(ncores)
+    os.environ["MKL_NUM_THREADS"] = str(ncores)
+    import torch
+    torch.set_num_threads(ncores)
     step, cores, sample = cpu_path_step_fn(1)
     t_begin = time.time()
     t = time.perf_counter()
@@ -484,7 +492,10 @@ def run_ours(args):
             pass
         k = kern[dom]
         roofline = {"bound": "hbm", "kernel": dom, "achieved": k["gbs"], "peak": peak, "unit": "GB/s",
-                    "frac": k["gbs"] / peak, "traffic": traffic, "peak_source": peak_src,
+                    "frac": k["gbs"] / peak, "traffic": traffic,
+                    "traffic_source": "profiles/roofline_traffic.json (ncu --set full dram__bytes_read+write per "
+                                      "launch, captured in an earlier run of the same kernels; not measured live)",
+                    "peak_source": peak_src,
                     "launches": k["launches"], "us_per_launch": k["us_per_launch"],
                     "algorithmic_bytes_per_launch": k["bytes"] / k["launches"],
                     "share_of_step": (k["ms"] / args.steps) / step_ms_for_share,

@@ -34,10 +34,11 @@ def _inputs(fam, H, D, B, seed, dtype=torch.float32):
     return order, K, ts + [A, Ds, bias]
 
 
-def _close(a, b, rtol, what):
+def _close(a, b, rtol, what, floor=0.05):
+    """|a - b| <= rtol * |b| + floor * rtol * max|b| -- the same absolute floor as test_gpu_sscan.py."""
     a = a.detach().double().cpu().numpy()
     b = b.detach().double().cpu().numpy()
-    tol = rtol * np.abs(b) + rtol * np.abs(b).max()
+    tol = rtol * np.abs(b) + floor * rtol * np.abs(b).max()
     err = np.abs(a - b)
     assert (err <= tol).all(), f"{what}: max err {err.max():.3e} (ref max {np.abs(b).max():.3e}) at {np.argmax(err - tol)}"
 
@@ -79,7 +80,9 @@ def test_fused_fwd_bwd_bf16_vs_oracle(fam, H, D):
     yr, gr = _oracle(fam, H, tensors, dy)
     _close(y, yr, 1e-3, "y")        # bf16 inputs are exact in both; internals fp32 vs fp64
     for name, g, r in zip("dx ddts dBs dCs dA dDs dbias".split(), grads, gr):
-        _close(g, r, 1e-2, name)    # du / ddelta / dB / dC are rounded to bf16 on the way out
+        # du / ddelta / dB / dC are rounded to bf16 on the way out; dx sums K bf16-rounded du terms, so its floor is
+        # relative to the terms (test_gpu_fused_sites.py)
+        _close(g, r, 1e-2, name, floor=1.0 if name == "dx" else 0.05)
 
 
 @pytest.mark.parametrize("fam,H,D", [("std", 24, 16), ("dilation", 48, 4), ("window", 96, 1), ("line", 24, 16),

@@ -71,6 +71,16 @@ SHAPES = [
     (2, 4, 8, 2304, 16),        # BASELINE config-2 state size
     (1, 4, 8, 576, 4),
     (1, 1, 8, 36864, 1),        # 192x192 (768^2 stress)
+    # rows % R != 0: the last unit is partial and its trailing chunks are empty (generic TMA path)
+    (1, 2, 3, 96, 1),
+    (1, 1, 5, 96, 2),
+    # several rows per chunk with channels-per-group NOT a multiple of rows-per-chunk: sub-rows of one
+    # chunk belong to different (batch, group)s -> must not take the side-by-side backward kernel
+    (1, 2, 3, 64, 1),
+    (1, 2, 3, 64, 2),
+    (2, 2, 3, 32, 1),
+    (1, 2, 2, 32, 1),
+    (1, 2, 4, 64, 1),           # same plan, aligned groups (side-by-side kernel)
 ]
 
 
@@ -189,3 +199,28 @@ def test_errors_are_loud():
     rc = _lib.lib.tramba_sscan_fwd(u.data_ptr(), delta.data_ptr(), A.data_ptr(), B.data_ptr(), C.data_ptr(), None,
                                    None, u.data_ptr(), None, 1, 8, 48, 1, 3, 0, 0, 1, None)
     assert rc == -2                                                     # dim % groups
+
+
+def test_fwd_cross_check_against_vllm_selective_scan():
+    """Independent GPU-side cross-check: vLLM's `selective_scan_fn` is a CUDA build of the same
+    state-spaces/mamba selective-scan lineage the reference's absent `selective_scan_cuda_oflex` derives from
+    (SURVEY 8c).  Forward only (vLLM ships no backward).  Skips cleanly when the op is not importable / has no sm_100
+    image.  Same operands (fp32, grouped B/C, D skip, delta_bias, softplus) -> same output to rtol 1e-3."""
+    try:
+        from vllm.model_executor.layers.mamba.ops.mamba_ssm import selective_scan_fn
+    except Exception as e:  # noqa: BLE001
+        pytest.skip(f"vLLM selective_scan_fn not importable: {type(e).__name__}")
+    b, K, Dg, L, N = 2, 4, 8, 2304, 16
+    args = make_inputs(b, K, Dg, L, N, seed=21)
+    u, delta, A, B, C, D, bias = [t.cuda() for t in args]
+    ours = tramba_b200.SelectiveScanOflex.apply(u, delta, A, B, C, D, bias, True, -1, -1, True)
+    try:
+        state = torch.zeros(b, K * Dg, N, device="cuda")
+        d2 = delta.clone()
+        theirs = selective_scan_fn(u.clone(), state, d2, A.contiguous(), B.clone(), C.clone(), D, None, bias, True)
+        torch.cuda.synchronize()
+    except Exception as e:  # noqa: BLE001
+        pytest.skip(f"vLLM selective_scan_fn did not run on this device: {type(e).__name__}: {str(e)[:120]}")
+    if theirs is None:
+        theirs = d2          # older builds write the output in place of delta
+    check("out vs vLLM", ours, theirs.double().cpu().numpy(), 1e-3)

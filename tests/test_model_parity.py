@@ -108,6 +108,64 @@ def test_harness_gpu_kernels_match_reference_golden():
 
 
 @pytest.mark.gpu
+def test_harness_gpu_bf16_every_core_call_matches_oracle_on_its_own_operands():
+    """bf16 autocast is the benchmarked precision.  A whole-network bf16 output cannot be held to 1e-2 against an fp32
+    fixture (37 blocks of bf16 convolutions in between), so the bound is applied where it is meaningful: EVERY fused
+    SS2D core call of one training step (forward + backward through the deep-supervision loss) is recorded with the
+    bf16 operands the network actually fed it, and replayed through the fp64 oracle composition
+    (CrossScan -> selective scan -> CrossMerge, Models/vmamba.py:231-259) on those same operands:
+    y (fp32 out) rtol 1e-3; dx / ddelta / dB / dC (bf16 out) and dA / dD / ddelta_bias rtol 1e-2."""
+    from tramba_b200 import fused
+    from _fused_oracle import fused_core_oracle
+    fam_of = {tramba_b200._lib.ORDER_STD: "std", tramba_b200._lib.ORDER_DILATION: "dilation",
+              tramba_b200._lib.ORDER_WINDOW: "window", tramba_b200._lib.ORDER_LINE: "line"}
+    records = []
+    real = fused.ss2d_core_fused
+
+    def recording(x, dts, Bs, Cs, A, Ds, bias, order, param=0, delta_softplus=True):
+        ins = [x, dts, Bs, Cs, A, Ds, bias]
+        rec = {"order": order, "H": x.shape[-1], "in": [t.detach().clone() for t in ins], "g": [None] * 7}
+        for i, t in enumerate(ins):
+            if t.requires_grad:
+                t.register_hook(lambda g, i=i, rec=rec: rec["g"].__setitem__(i, g.detach().clone()))
+        y = real(x, dts, Bs, Cs, A, Ds, bias, order, param, delta_softplus)
+        rec["y"] = y.detach().clone()
+        y.register_hook(lambda g, rec=rec: rec.__setitem__("dy", g.detach().clone()))
+        records.append(rec)
+        return y
+
+    m = det_fill(build_model(img_size=384, dims=int(GOLD["dims"]))).eval().cuda()
+    x = det_input((1, 3, 384, 384), 7).cuda()
+    label = (det_input((1, 1, 384, 384), 8) > 0).float().cuda()
+    fused.ss2d_core_fused = recording
+    try:
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            outs = m(x)
+            loss = tsod_loss(outs, label)
+        loss.backward()
+    finally:
+        fused.ss2d_core_fused = real
+    assert len(records) == 33 and all(r["in"][0].dtype == torch.bfloat16 for r in records)   # SURVEY 3.3: 33 calls
+
+    def close(a, b, rtol, what, floor=0.05):
+        a, b = a.double().cpu().numpy(), b.double().numpy()
+        tol = rtol * np.abs(b) + floor * rtol * np.abs(b).max()
+        err = np.abs(a - b)
+        assert (err <= tol).all(), f"{what}: max err {err.max():.3e} (ref max {np.abs(b).max():.3e})"
+
+    for n, r in enumerate(records):
+        fam = fam_of[r["order"]]
+        yr, gr = fused_core_oracle(fam, r["H"], [t.float().cpu() for t in r["in"]], r["dy"].float().cpu())
+        close(r["y"], yr, 1e-3, f"call {n} ({fam}, H={r['H']}) y")
+        names = "dx ddts dBs dCs dA dDs dbias".split()
+        for i, name in enumerate(names):
+            assert r["g"][i] is not None, (n, name)
+            # dx: K bf16-rounded du terms are summed (see test_gpu_fused_sites.py); everything else: one rounding
+            close(r["g"][i].reshape(gr[i].shape), gr[i], 1e-2, f"call {n} ({fam}, H={r['H']}) {name}",
+                  floor=1.0 if name == "dx" else 0.05)
+
+
+@pytest.mark.gpu
 def test_harness_gpu_bf16_autocast_close():
     m = det_fill(build_model(img_size=384, dims=int(GOLD["dims"]))).eval().cuda()
     x = det_input((1, 3, 384, 384), 7).cuda()

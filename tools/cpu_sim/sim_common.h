@@ -565,6 +565,13 @@ constexpr float kLn2 = 0.6931471805599453f;
 
 void note_launch();   // capi.cu (translated) defines it
 
+// per-device launch configuration helpers of csrc/common.cuh (one simulated device; sm_count may change per test)
+template <typename Kern>
+inline cudaError_t ensure_dyn_smem(Kern, int) {
+    return cudaSuccess;
+}
+inline int device_sms() { return sim::sm_count; }
+
 // ---- mbarrier + TMA bulk: the same names as csrc/common.cuh
 inline void mbar_init(uint64_t* bar, uint32_t count) {
     sim::Mbar& b = sim::g->mbars[bar];

@@ -98,7 +98,16 @@ def _load():
     return lib
 
 
-lib = _load()
+class _NotLoaded:
+    """TRAMBA_B200_NO_LIB=1 (set by `bench.py --impl reference` only): the process must not map the CUDA library --
+    the reference arm times the CPU path and its record must show no native code of ours.  Any use raises."""
+
+    def __getattr__(self, name):
+        raise RuntimeError(f"tramba_b200: libtramba_b200.so deliberately not loaded (TRAMBA_B200_NO_LIB=1); "
+                           f"`{name}` is not available in this process")
+
+
+lib = _NotLoaded() if os.environ.get("TRAMBA_B200_NO_LIB", "") == "1" else _load()
 
 
 def check(rc):

@@ -241,7 +241,11 @@ extern "C" int tramba_sscan_bwd(const void* u, const void* delta, const float* A
     if ((D && !dD) || (delta_bias && !ddelta_bias)) return TRAMBA_E_NULL;
     int rc = sscan_common(batch, dim, L, N, groups, in_dtype, dout_dtype);
     if (rc != TRAMBA_OK) return rc;
-    const SScanPlan p = make_sscan_plan(static_cast<long long>(batch) * dim, L, elem_size(in_dtype));
+    SScanPlan p = make_sscan_plan(static_cast<long long>(batch) * dim, L, elem_size(in_dtype));
+    // The side-by-side kernel (rpc rows per chunk) takes one B/C base per chunk and reduces dB/dC over the
+    // sub-rows: all of them must belong to one (batch, group).  Otherwise: the generic kernel (same chunking,
+    // per-lane coordinates).  The forward's checkpoints are not read when a chunk holds whole rows (cpu == 1).
+    if (p.regular && p.rpc > 1 && (dim / groups) % p.rpc != 0) p.regular = false, p.rpc = 1;
     const int need = p.tma ? 16 : elem_size(in_dtype);
     if (!aligned(u, need) || !aligned(delta, need) || !aligned(Bm, need) || !aligned(Cm, need) ||
         !aligned(du, need) || !aligned(ddelta, need) || !aligned(dout, p.tma ? 16 : elem_size(dout_dtype)) ||

@@ -16,6 +16,36 @@ constexpr float kLn2 = 0.6931471805599453f;
 // ------------------------------------------------------------------ launch accounting
 void note_launch();  // capi.cu
 
+// ------------------------------------------------------------------ per-device launch configuration
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is a PER-DEVICE setting: a process that drives several GPUs
+// (threads per device, nn.DataParallel) must configure every kernel on each of them.  One bit per device ordinal
+// and kernel instantiation; `bytes` may grow (kernels whose footprint depends on N).
+constexpr int kMaxDevices = 64;
+template <typename Kern>
+inline cudaError_t ensure_dyn_smem(Kern kern, int bytes) {
+    static int done[kMaxDevices] = {};  // largest size configured so far, per device (benign race: idempotent)
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    const int slot = dev & (kMaxDevices - 1);
+    if (done[slot] >= bytes) return cudaSuccess;
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e == cudaSuccess) done[slot] = bytes;
+    return e;
+}
+inline int device_sms() {
+    static int sms[kMaxDevices] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const int slot = dev & (kMaxDevices - 1);
+    if (!sms[slot]) {
+        int v = 0;
+        cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+        sms[slot] = v > 0 ? v : 148;
+    }
+    return sms[slot];
+}
+
 // ------------------------------------------------------------------ mbarrier + TMA bulk
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
     return static_cast<uint32_t>(__cvta_generic_to_shared(p));

@@ -340,12 +340,7 @@ cudaError_t launch_dct2d_fwd_tc(const float* x, const float* wy, const float* wx
                                 int H, int W, cudaStream_t st) {
     Plan p = make_plan(H, W);
     if (!p.ok) return cudaErrorInvalidConfiguration;
-    static int sms = 0;
-    if (!sms) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    }
+    const int sms = device_sms();
     const int groups = (planes + p.gm.ppl - 1) / p.gm.ppl;
     const int grid = groups < sms ? groups : sms;
     // NTA * 8 must divide W; NTB * 8 tiles the quadrant width
@@ -368,12 +363,7 @@ cudaError_t launch_dct2d_bwd_tc(const float* ghigh, const float* glow, const flo
                                 int planes, int H, int W, cudaStream_t st) {
     Plan p = make_plan(H, W);
     if (!p.ok) return cudaErrorInvalidConfiguration;
-    static int sms = 0;
-    if (!sms) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    }
+    const int sms = device_sms();
     DctGeom gm = p.gm;
     gm.ldt = pad_to(W, 8);
     const int groups = (planes + gm.ppl - 1) / gm.ppl;

@@ -378,12 +378,7 @@ DwPlan dw_plan(int B, int C, int H, int W, int K) {
 }
 
 int sm_count() {
-    static int sms = 0;
-    if (!sms) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    }
+    const int sms = device_sms();
     return sms;
 }
 

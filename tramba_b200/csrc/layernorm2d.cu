@@ -465,12 +465,7 @@ struct LnPlan {
     int wp;   // 64-pixel sub-tiles per CTA (register-resident kernels)
 };
 LnPlan ln_plan(int B, int C, int L) {
-    static int sms = 0;
-    if (!sms) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    }
+    const int sms = device_sms();
     LnPlan p;
     p.cs = 0, p.wp = 1;
     if (L % 2 == 0) {

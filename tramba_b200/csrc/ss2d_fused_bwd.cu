@@ -371,18 +371,8 @@ template <typename in_t, bool SOFTPLUS>
 static cudaError_t launch_t(const FusedArgs& a, cudaStream_t st) {
     const size_t cap = 227 * 1024;
     auto kern = ss2d_bwd_kernel<in_t, SOFTPLUS>;
-    static bool configured = false;
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        if (e != cudaSuccess) return e;
-        configured = true;
-    }
-    static int sms = 0;
-    if (!sms) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    }
+    if (cudaError_t e = ensure_dyn_smem(kern, 227 * 1024); e != cudaSuccess) return e;
+    const int sms = device_sms();
     FusedArgs b = a;
     b.xb = BwdLayout(a.L, sizeof(in_t), 2).total <= cap ? 2 : 1;
     const size_t smem = BwdLayout(a.L, sizeof(in_t), b.xb).total;

@@ -206,18 +206,8 @@ size_t ss2d_fused_fwd_smem(int L, int es, int xb) { return FwdLayout(L, es, xb).
 template <typename in_t, bool SOFTPLUS>
 static cudaError_t launch_t(const FusedArgs& a, cudaStream_t st) {
     auto kern = ss2d_fwd_kernel<in_t, SOFTPLUS>;
-    static bool configured = false;
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        if (e != cudaSuccess) return e;
-        configured = true;
-    }
-    static int sms = 0;
-    if (!sms) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    }
+    if (cudaError_t e = ensure_dyn_smem(kern, 227 * 1024); e != cudaSuccess) return e;
+    const int sms = device_sms();
     const size_t smem = FwdLayout(a.L, sizeof(in_t), a.xb).total;
     const int grid = a.rounds < sms ? a.rounds : sms;
     kern<<<grid, NT, smem, st>>>(a);

@@ -108,18 +108,8 @@ template <typename T>
 static cudaError_t launch_t(const T* ys, T* y, const uint16_t* idx, int K, int B, int D, int L, uint32_t dup_mask,
                             cudaStream_t st) {
     auto kern = merge_skewed_kernel<T>;
-    static bool configured = false;
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        if (e != cudaSuccess) return e;
-        configured = true;
-    }
-    static int sms = 0;
-    if (!sms) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    }
+    if (cudaError_t e = ensure_dyn_smem(kern, 227 * 1024); e != cudaSuccess) return e;
+    const int sms = device_sms();
     const int TP = L / S, PP = NT / TP;
     const int rounds = B * D / PP;
     const size_t smem = MergeLayout(L, sizeof(T)).total;

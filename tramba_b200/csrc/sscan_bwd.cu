@@ -103,8 +103,9 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) sscan_bwd_kernel(const SSca
             if (lane == 0) {
                 int chunk;
                 const long long unit = tile_unit(pj, pcr, chunk);
-                if (unit < p.units) {
-                    const int unit_rows = min(p.R, p.rows - static_cast<int>(unit) * p.R);
+                const int unit_rows = unit < p.units ? min(p.R, p.rows - static_cast<int>(unit) * p.R) : 0;
+                // a partial last unit (rows % R != 0) still walks p.cpu chunks: chunks past its tokens are empty
+                if (unit_rows * p.L - chunk * CH > 0) {
                     const int unit_tokens = unit_rows * p.L;
                     const long long tok0 =
                         unit * p.R * static_cast<long long>(p.L) + static_cast<long long>(chunk) * CH;
@@ -703,15 +704,9 @@ cudaError_t launch_regular(const SScanArgs& a, cudaStream_t st) {
     auto kern = sscan_bwd_regular_kernel<TSEG, NS, in_t, go_t, LPR, RW>;
     const int warp_bytes = SM::warp_bytes(RW, 32 / LPR, a.N);
     const int smem = kWarpsPerCta * warp_bytes;
-    static int configured = 0;
-    if (configured < smem) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        if (e != cudaSuccess) return e;
-        configured = smem;
-    }
-    int dev = 0, sms = 148, occ = 1;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (cudaError_t e = ensure_dyn_smem(kern, smem); e != cudaSuccess) return e;
+    const int sms = device_sms();
+    int occ = 1;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kWarpsPerCta * 32, smem);
     if (occ < 1) occ = 1;
     const long long sunits = a.units / RW;
@@ -740,15 +735,8 @@ cudaError_t launch_one(const SScanArgs& a, cudaStream_t st) {
     auto kern = sscan_bwd_kernel<TSEG, NS, in_t, go_t, TMA, RW>;
     const int warp_bytes = SM::warp_bytes(RW, a.N);
     const int smem = kWarpsPerCta * warp_bytes;
-    static int configured = 0;  // per instantiation; grows with N
-    if (configured < smem) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        if (e != cudaSuccess) return e;
-        configured = smem;
-    }
-    int dev = 0, sms = 148;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (cudaError_t e = ensure_dyn_smem(kern, smem); e != cudaSuccess) return e;
+    const int sms = device_sms();
     int occ = 1;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kWarpsPerCta * 32, smem);
     if (occ < 1) occ = 1;

@@ -66,12 +66,17 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) sscan_fwd_kernel(const SSca
                 const int unit_rows = min(p.R, p.rows - static_cast<int>(unit) * p.R);
                 const int unit_tokens = unit_rows * p.L;
                 const long long tok0 = unit * p.R * static_cast<long long>(p.L) + static_cast<long long>(pc) * CH;
-                const int nt = min(CH, unit_tokens - pc * CH);
+                // a partial last unit (rows % R != 0) still walks p.cpu chunks: chunks past its tokens are empty
+                const int nt = max(0, min(CH, unit_tokens - pc * CH));
                 const uint32_t bytes = nt * sizeof(in_t);
                 const int st = static_cast<int>(pq % kFwdStages);
-                mbar_expect_tx(&full[st], 2 * bytes);
-                bulk_g2s(s_in + (st * 2 + 0) * CH, gu + tok0, bytes, &full[st]);
-                bulk_g2s(s_in + (st * 2 + 1) * CH, gd + tok0, bytes, &full[st]);
+                if (nt > 0) {
+                    mbar_expect_tx(&full[st], 2 * bytes);
+                    bulk_g2s(s_in + (st * 2 + 0) * CH, gu + tok0, bytes, &full[st]);
+                    bulk_g2s(s_in + (st * 2 + 1) * CH, gd + tok0, bytes, &full[st]);
+                } else {
+                    mbar_arrive(&full[st]);  // empty tail tile: complete the phase without a copy
+                }
             }
             ++pq;
             if (++pc == p.cpu) pc = 0, ++pj;
@@ -91,7 +96,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) sscan_fwd_kernel(const SSca
         const int unit_rows = min(p.R, p.rows - static_cast<int>(unit) * p.R);
         const int unit_tokens = unit_rows * p.L;
         const long long tok0 = unit * p.R * static_cast<long long>(p.L) + static_cast<long long>(cc) * CH;
-        const int nt = min(CH, unit_tokens - cc * CH);
+        const int nt = max(0, min(CH, unit_tokens - cc * CH));
         const LaneCoord lc = lane_coord(p, unit, cc, lane, TSEG, CH, unit_tokens);
 
         float u[TSEG], dl[TSEG];
@@ -175,7 +180,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) sscan_fwd_kernel(const SSca
             fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0) {
-                bulk_s2g(gout + tok0, s_out + ob * CH, nt * sizeof(out_t));
+                if (nt > 0) bulk_s2g(gout + tok0, s_out + ob * CH, nt * sizeof(out_t));
                 bulk_commit();
             }
         } else {
@@ -392,19 +397,13 @@ cudaError_t launch_regular(const SScanArgs& a, cudaStream_t st) {
     using SM = FwdSmem<TSEG, in_t, out_t>;
     auto kern = sscan_fwd_regular_kernel<TSEG, NS, in_t, out_t, LPR>;
     const int smem = kWarpsPerCta * SM::WARP_BYTES;
-    static bool configured = false;
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        if (e != cudaSuccess) return e;
-        configured = true;
-    }
-    static int sms = 0, occ = 0;
-    if (!sms) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kWarpsPerCta * 32, smem);
-        if (occ < 1) occ = 1;
+    if (cudaError_t e = ensure_dyn_smem(kern, smem); e != cudaSuccess) return e;
+    const int sms = device_sms();
+    static int occ = 0;  // a property of the kernel image, identical on every (sm_100) device of the process
+    if (!occ) {
+        int o = 0;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, kern, kWarpsPerCta * 32, smem);
+        occ = o < 1 ? 1 : o;
     }
     // one resident wave of CTAs; each warp strides over its share of the units
     long long want = (a.units + kWarpsPerCta - 1) / kWarpsPerCta;
@@ -426,15 +425,8 @@ cudaError_t launch_one(const SScanArgs& a, cudaStream_t st) {
     using SM = FwdSmem<TSEG, in_t, out_t>;
     auto kern = sscan_fwd_kernel<TSEG, NS, in_t, out_t, TMA>;
     const int smem = TMA ? kWarpsPerCta * SM::WARP_BYTES : kWarpsPerCta * kMaxState * 4;
-    static bool configured = false;  // per instantiation
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        if (e != cudaSuccess) return e;
-        configured = true;
-    }
-    int dev = 0, sms = 148;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (cudaError_t e = ensure_dyn_smem(kern, smem); e != cudaSuccess) return e;
+    const int sms = device_sms();
     int occ = 1;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kWarpsPerCta * 32, smem);
     if (occ < 1) occ = 1;

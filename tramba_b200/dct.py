@@ -14,6 +14,12 @@ from . import _lib
 
 
 def _basis(n):
+    if isinstance(_lib.lib, _lib._NotLoaded):
+        # bench.py --impl reference (library deliberately not mapped): the buffer is a host constant,
+        # W[v, j] = cos(pi (j + 1/2) v / n) / sqrt(n) * (sqrt(2) if v > 0)   (DCT_2D.py:37-45)
+        v, j = np.arange(n, dtype=np.float64).reshape(n, 1), np.arange(n, dtype=np.float64).reshape(1, n)
+        w = np.cos(np.pi * (j + 0.5) * v / n) / np.sqrt(n) * np.where(v > 0, np.sqrt(2.0), 1.0)
+        return torch.from_numpy(w.astype(np.float32))
     w = np.empty((n, n), dtype=np.float32)
     _lib.lib.tramba_dct_basis(n, w.ctypes.data)  # DCT_2D.py:37-45, bit-exact
     return torch.from_numpy(w)

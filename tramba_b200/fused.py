@@ -111,7 +111,7 @@ class SS2DCoreFused(torch.autograd.Function):
         ddts = torch.empty((B, K, D, L), device=x.device, dtype=dt)
         dBs = torch.empty((B, K, L), device=x.device, dtype=torch.float32)
         dCs = torch.empty((B, K, L), device=x.device, dtype=torch.float32)
-        part = torch.empty((3, B, K * D), device=x.device, dtype=torch.float32)   # dA | dD | dbias partials per b
+        part = torch.zeros((3, B, K * D), device=x.device, dtype=torch.float32)   # dA | dD | dbias partials per b
         dA, dD, db = part[0], (None if Ds is None else part[1]), (None if delta_bias is None else part[2])
         es = x.element_size()
         # algorithmic bytes: per direction read x, delta, dy; write du, ddelta; B/C in, dB/dC out
@@ -126,8 +126,6 @@ class SS2DCoreFused(torch.autograd.Function):
         with torch.cuda.device(x.device), _lib.timed("cross_merge_skewed", (1 + K) * B * D * L * es):
             _lib.check(_lib.lib.tramba_cross_merge_skewed(du.data_ptr(), dx.data_ptr(), idx.data_ptr(), order, K, B,
                                                           D, H, W, _DTYPE[dt], _stream()))
-        if Ds is None or delta_bias is None:
-            part[1 if Ds is None else 2].zero_()
         part = part.sum(1)                                                        # one reduction over the batch
         return (dx, ddts, dBs.to(dt), dCs.to(dt), part[0], None if Ds is None else part[1],
                 None if delta_bias is None else part[2], None, None, None)
