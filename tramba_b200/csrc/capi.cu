@@ -1,8 +1,11 @@
 // extern "C" entry points of libtramba_b200.so (see include/tramba_b200.h).
 // Argument validation, plan selection and kernel launch; no torch, no allocation.
+#include <array>
 #include <atomic>
 #include <cstdio>
 #include <cstring>
+#include <mutex>
+#include <unordered_map>
 #include <vector>
 
 #include "common.cuh"
@@ -13,6 +16,15 @@ namespace tramba {
 
 static std::atomic<uint64_t> g_launches{0};
 void note_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+
+int* dyn_smem_slot(const void* kern, int dev) {
+    static std::mutex mu;
+    static std::unordered_map<const void*, std::array<int, kMaxDevices>> table;  // node-based: slots never move
+    std::lock_guard<std::mutex> lock(mu);
+    auto it = table.find(kern);
+    if (it == table.end()) it = table.emplace(kern, std::array<int, kMaxDevices>{}).first;
+    return &it->second[dev];
+}
 
 cudaError_t launch_cross_scan(const void* x, void* xs, const int32_t* plan, int K, int B, int C, int L,
                               int dtype, cudaStream_t st);

@@ -21,16 +21,18 @@ void note_launch();  // capi.cu
 // (threads per device, nn.DataParallel) must configure every kernel on each of them.  One bit per device ordinal
 // and kernel instantiation; `bytes` may grow (kernels whose footprint depends on N).
 constexpr int kMaxDevices = 64;
+// (kernel entry point, device ordinal) -> largest size configured so far.  Keyed by the function's ADDRESS:
+// instantiations of one kernel template share a function-pointer TYPE, so a per-type static would be shared.
+int* dyn_smem_slot(const void* kern, int dev);  // capi.cu (mutex-protected map; the slot itself is benign-racy)
 template <typename Kern>
 inline cudaError_t ensure_dyn_smem(Kern kern, int bytes) {
-    static int done[kMaxDevices] = {};  // largest size configured so far, per device (benign race: idempotent)
     int dev = 0;
     cudaError_t e = cudaGetDevice(&dev);
     if (e != cudaSuccess) return e;
-    const int slot = dev & (kMaxDevices - 1);
-    if (done[slot] >= bytes) return cudaSuccess;
+    int* done = dyn_smem_slot(reinterpret_cast<const void*>(kern), dev & (kMaxDevices - 1));
+    if (*done >= bytes) return cudaSuccess;
     e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
-    if (e == cudaSuccess) done[slot] = bytes;
+    if (e == cudaSuccess) *done = bytes;
     return e;
 }
 inline int device_sms() {
