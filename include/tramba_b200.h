@@ -177,6 +177,24 @@ TRAMBA_API int tramba_ss2d_fused_fwd(const void* x, const void* dts, const void*
                                      const float* A, const float* Dp, const float* delta_bias,
                                      const uint16_t* idx16, float* y, int order, int K, int B, int D, int H,
                                      int W, int N, int in_dtype, int delta_softplus, void* stream);
+/* Backward with the merge of du folded in (replaces CrossMerge*.backward -> SelectiveScanOflex.backward ->
+ * CrossScan*.backward, csms6s.py:45-55, 914-923, 25-31, in ONE kernel): dx (B, D, L) fp32 IMAGE order comes back
+ * already summed over the K directions (zeroed here, accumulated with TMA bulk reductions); no du tensor exists.
+ *   sched (K, sched_len) uint32, device: tramba_order_sched -- per direction a bank-conflict-free schedule of the
+ *          shared-memory permutation image order <-> token order (entry = 2*pixel | 2*token << 16, 0xFFFFFFFF = none)
+ *   kinds (K) int32, HOST: 0 identity, 1 reversed identity, 2 permutation, 3 table with repeated pixels
+ * tramba_order_sched_len: entries per direction (0 = unsupported size). */
+TRAMBA_API size_t tramba_order_sched_len(int order, int H, int W, int param);
+TRAMBA_API int tramba_order_sched(int order, int H, int W, int param, uint32_t* sched_out /* K*len, host */,
+                                  int32_t* kind_out /* K, host */);
+TRAMBA_API int tramba_ss2d_fused_bwd_dx_supported(int order, int K, int D, int H, int W, int N, int in_dtype);
+TRAMBA_API int tramba_ss2d_fused_bwd_dx(const void* x, const void* dts, const void* Bs, const void* Cs,
+                                        const float* A, const float* Dp, const float* delta_bias,
+                                        const uint32_t* sched, int sched_len, const int32_t* kinds,
+                                        const float* dy, float* dx, void* ddts, float* dBs, float* dCs,
+                                        float* dA_part, float* dD_part, float* dbias_part, int order, int K, int B,
+                                        int D, int H, int W, int N, int in_dtype, int delta_softplus,
+                                        void* stream);
 TRAMBA_API int tramba_ss2d_fused_bwd(const void* x, const void* dts, const void* Bs, const void* Cs,
                                      const float* A, const float* Dp, const float* delta_bias,
                                      const uint16_t* idx16, const float* dy, void* du, void* ddts, float* dBs,

@@ -80,9 +80,8 @@ def test_fused_fwd_bwd_bf16_vs_oracle(fam, H, D):
     yr, gr = _oracle(fam, H, tensors, dy)
     _close(y, yr, 1e-3, "y")        # bf16 inputs are exact in both; internals fp32 vs fp64
     for name, g, r in zip("dx ddts dBs dCs dA dDs dbias".split(), grads, gr):
-        # du / ddelta / dB / dC are rounded to bf16 on the way out; dx sums K bf16-rounded du terms, so its floor is
-        # relative to the terms (test_gpu_fused_sites.py)
-        _close(g, r, 1e-2, name, floor=1.0 if name == "dx" else 0.05)
+        # ddelta / dB / dC / dx are rounded to bf16 once on the way out (dx is accumulated over K in fp32)
+        _close(g, r, 1e-2, name)
 
 
 @pytest.mark.parametrize("fam,H,D", [("std", 24, 16), ("dilation", 48, 4), ("window", 96, 1), ("line", 24, 16),
@@ -109,6 +108,10 @@ def test_fused_indexing_bit_exact(fam, H, D):
 
 
 def test_ss2d_module_fused_matches_unfused():
+    # the two routes evaluate x_proj / dt_proj differently (one GEMM on the image-ordered map vs grouped conv1d on
+    # xs): keep cuDNN / cuBLAS out of TF32 so that the comparison is about OUR kernels
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
     torch.manual_seed(0)
     for scan, merge, K, H in ((tramba_b200.CrossScan, tramba_b200.CrossMerge, 4, 24),
                               (tramba_b200.CrossScan_Line, tramba_b200.CrossMerge_Line, 8, 24),

@@ -123,7 +123,9 @@ def test_harness_gpu_bf16_every_core_call_matches_oracle_on_its_own_operands():
     real = fused.ss2d_core_fused
 
     def recording(x, dts, Bs, Cs, A, Ds, bias, order, param=0, delta_softplus=True):
-        ins = [x, dts, Bs, Cs, A, Ds, bias]
+        # fresh autograd nodes: a hook on `x` itself would also see the gradient of its OTHER use (x_proj)
+        ins = [t.view(t.shape) for t in (x, dts, Bs, Cs, A, Ds, bias)]
+        x, dts, Bs, Cs, A, Ds, bias = ins
         rec = {"order": order, "H": x.shape[-1], "in": [t.detach().clone() for t in ins], "g": [None] * 7}
         for i, t in enumerate(ins):
             if t.requires_grad:
@@ -160,9 +162,7 @@ def test_harness_gpu_bf16_every_core_call_matches_oracle_on_its_own_operands():
         names = "dx ddts dBs dCs dA dDs dbias".split()
         for i, name in enumerate(names):
             assert r["g"][i] is not None, (n, name)
-            # dx: K bf16-rounded du terms are summed (see test_gpu_fused_sites.py); everything else: one rounding
-            close(r["g"][i].reshape(gr[i].shape), gr[i], 1e-2, f"call {n} ({fam}, H={r['H']}) {name}",
-                  floor=1.0 if name == "dx" else 0.05)
+            close(r["g"][i].reshape(gr[i].shape), gr[i], 1e-2, f"call {n} ({fam}, H={r['H']}) {name}")
 
 
 @pytest.mark.gpu

@@ -54,7 +54,17 @@ struct Copy {
     void* dst;
     const void* src;
     size_t bytes;
+    bool add_f32 = false;   // cp.reduce.async.bulk ... .add.f32: dst[i] += src[i] instead of a copy
 };
+inline void apply_copy(const Copy& c) {
+    if (!c.add_f32) {
+        std::memcpy(c.dst, c.src, c.bytes);
+        return;
+    }
+    float* d = static_cast<float*>(c.dst);
+    const float* s = static_cast<const float*>(c.src);
+    for (size_t i = 0; i < c.bytes / 4; ++i) d[i] += s[i];
+}
 struct Cluster;
 struct Cta {
     int nthreads = 0, bx = 0, gdim = 0;
@@ -194,7 +204,7 @@ inline void cp_commit() {
 inline void cp_wait(size_t keep) {
     auto& groups = g->thread_cp_groups[g->cur];
     while (groups.size() > keep) {
-        for (const Copy& c : groups.front()) std::memcpy(c.dst, c.src, c.bytes);
+        for (const Copy& c : groups.front()) apply_copy(c);
         groups.erase(groups.begin());
     }
 }
@@ -282,9 +292,10 @@ inline void flush_barrier(const void* bar) {                            // someb
         }
     }
 }
-inline void s2g(void* dst, const void* src, size_t bytes) {
-    if (!lazy) std::memcpy(dst, src, bytes);
-    else g->thread_stores[g->cur].push_back(Copy{dst, src, bytes});
+inline void s2g(void* dst, const void* src, size_t bytes, bool add_f32 = false) {
+    const Copy c{dst, src, bytes, add_f32};
+    if (!lazy) apply_copy(c);
+    else g->thread_stores[g->cur].push_back(c);
 }
 inline void commit_stores() {                                           // cp.async.bulk.commit_group
     auto& open = g->thread_stores[g->cur];
@@ -294,7 +305,7 @@ inline void commit_stores() {                                           // cp.as
 inline void drain_stores(size_t keep) {                                 // cp.async.bulk.wait_group[.read] N
     auto& groups = g->thread_groups[g->cur];
     while (groups.size() > keep) {
-        for (const Copy& c : groups.front()) std::memcpy(c.dst, c.src, c.bytes);
+        for (const Copy& c : groups.front()) apply_copy(c);
         groups.erase(groups.begin());
     }
 }
@@ -566,6 +577,7 @@ constexpr float kLn2 = 0.6931471805599453f;
 void note_launch();   // capi.cu (translated) defines it
 
 // per-device launch configuration helpers of csrc/common.cuh (one simulated device; sm_count may change per test)
+constexpr int kMaxDevices = 64;
 template <typename Kern>
 inline cudaError_t ensure_dyn_smem(Kern, int) {
     return cudaSuccess;
@@ -600,6 +612,11 @@ inline void bulk_s2g(void* dst_gmem, const void* src_smem, uint32_t bytes) {
     if ((reinterpret_cast<uintptr_t>(dst_gmem) | reinterpret_cast<uintptr_t>(src_smem) | bytes) & 15)
         sim::g->error = "bulk_s2g: address or size not a multiple of 16 bytes";
     sim::s2g(dst_gmem, src_smem, bytes);
+}
+inline void bulk_reduce_add_f32_s2g(float* dst_gmem, const float* src_smem, uint32_t bytes) {
+    if ((reinterpret_cast<uintptr_t>(dst_gmem) | reinterpret_cast<uintptr_t>(src_smem) | bytes) & 15)
+        sim::g->error = "bulk_reduce_add_f32_s2g: address or size not a multiple of 16 bytes";
+    sim::s2g(dst_gmem, src_smem, bytes, true);
 }
 inline void bulk_commit() { sim::commit_stores(); }
 template <int N>

@@ -46,6 +46,11 @@ SIGNATURES = {
     "tramba_ss2d_fused_fwd": (_i, [_vp, _vp, _vp, _vp, _fp, _fp, _fp, _vp, _fp] + [_i] * 9 + [_vp]),
     "tramba_ss2d_fused_bwd": (_i, [_vp, _vp, _vp, _vp, _fp, _fp, _fp, _vp, _fp, _vp, _vp, _fp, _fp, _fp, _fp, _fp]
                               + [_i] * 9 + [_vp]),
+    "tramba_order_sched_len": (ctypes.c_size_t, [_i, _i, _i, _i]),
+    "tramba_order_sched": (_i, [_i, _i, _i, _i, _vp, _i32p]),
+    "tramba_ss2d_fused_bwd_dx_supported": (_i, [_i] * 7),
+    "tramba_ss2d_fused_bwd_dx": (_i, [_vp, _vp, _vp, _vp, _fp, _fp, _fp, _vp, _i, _i32p, _fp, _fp, _vp, _fp, _fp, _fp,
+                                      _fp, _fp] + [_i] * 9 + [_vp]),
     "tramba_cross_merge_skewed": (_i, [_vp, _vp, _vp] + [_i] * 7 + [_vp]),
     "tramba_layernorm2d_tiles": (_i, [_i, _i, _i]),
     "tramba_layernorm2d_fwd": (_i, [_vp, _fp, _fp, _vp, _fp, _fp, _i, _i, _i, ctypes.c_float, _i, _i, _i, _vp]),

@@ -451,6 +451,60 @@ extern "C" int tramba_ss2d_fused_bwd(const void* x, const void* dts, const void*
     return cuda_rc(e);
 }
 
+// Backward with dx: the merge of du (CrossScan*.backward, csms6s.py:25-31) happens inside the kernel.
+extern "C" int tramba_ss2d_fused_bwd_dx_supported(int order, int K, int D, int H, int W, int N, int in_dtype) {
+    FusedArgs a;
+    std::memset(&a, 0, sizeof(a));
+    if (in_dtype != TRAMBA_F32 && in_dtype != TRAMBA_BF16) return 0;
+    if (fused_geometry(a, order, K, 1, D, H, W, N) != TRAMBA_OK) return 0;
+    return ss2d_fused_bwd_dx_fits(a.L, elem_size(in_dtype)) ? 1 : 0;
+}
+
+extern "C" int tramba_ss2d_fused_bwd_dx(const void* x, const void* dts, const void* Bs, const void* Cs,
+                                        const float* A, const float* Dp, const float* delta_bias,
+                                        const uint32_t* sched, int sched_len, const int32_t* kinds,
+                                        const float* dy, float* dx, void* ddts, float* dBs, float* dCs,
+                                        float* dA_part, float* dD_part, float* dbias_part, int order, int K, int B,
+                                        int D, int H, int W, int N, int in_dtype, int delta_softplus,
+                                        void* stream) {
+    if (!x || !dts || !Bs || !Cs || !A || !sched || !kinds || !dy || !dx || !ddts || !dBs || !dCs || !dA_part)
+        return TRAMBA_E_NULL;
+    if ((Dp && !dD_part) || (delta_bias && !dbias_part)) return TRAMBA_E_NULL;
+    if (in_dtype != TRAMBA_F32 && in_dtype != TRAMBA_BF16) return TRAMBA_E_DTYPE;
+    FusedArgs g;
+    std::memset(&g, 0, sizeof(g));
+    int rc = fused_geometry(g, order, K, B, D, H, W, N);
+    if (rc != TRAMBA_OK) return rc;
+    if (!aligned(x, 16) || !aligned(dts, 16) || !aligned(Bs, 16) || !aligned(Cs, 16) || !aligned(dy, 16) ||
+        !aligned(dx, 16) || !aligned(ddts, 16) || !aligned(dBs, 16) || !aligned(dCs, 16) || !aligned(sched, 8))
+        return TRAMBA_E_ALIGN;
+    if (sched_len <= 0 || sched_len % (2 * g.TP) != 0 || sched_len % 64 != 0) return TRAMBA_E_SHAPE;
+    if (!ss2d_fused_bwd_dx_fits(g.L, elem_size(in_dtype))) return TRAMBA_E_LIMIT;
+    rc = check_device();
+    if (rc != TRAMBA_OK) return rc;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const size_t nbc = static_cast<size_t>(B) * K * g.L * sizeof(float);
+    cudaError_t e = cudaMemsetAsync(dBs, 0, nbc, st);
+    if (e == cudaSuccess) e = cudaMemsetAsync(dCs, 0, nbc, st);
+    if (e == cudaSuccess) e = cudaMemsetAsync(dx, 0, static_cast<size_t>(B) * D * g.L * sizeof(float), st);
+    if (e != cudaSuccess) return cuda_rc(e);
+    FusedDxArgs a;
+    std::memset(&a, 0, sizeof(a));
+    a.x = x, a.dts = dts, a.Bs = Bs, a.Cs = Cs, a.A = A, a.Dp = Dp, a.bias = delta_bias, a.sched = sched;
+    a.dy = dy, a.dx = dx, a.ddts = ddts, a.dBs = dBs, a.dCs = dCs, a.dA = dA_part, a.dD = dD_part,
+    a.dbias = dbias_part;
+    a.B = B, a.K = K, a.D = D, a.sched_len = sched_len;
+    a.kinds = 0;
+    for (int k = 0; k < K; ++k) {
+        if (kinds[k] < 0 || kinds[k] > 3) return TRAMBA_E_ORDER;
+        a.kinds |= static_cast<uint32_t>(kinds[k]) << (4 * k);
+    }
+    a.softplus = delta_softplus ? 1 : 0;
+    e = launch_ss2d_fused_bwd_dx(a, g.L, in_dtype, st);
+    if (e == cudaErrorInvalidConfiguration) return TRAMBA_E_LIMIT;
+    return cuda_rc(e);
+}
+
 extern "C" int tramba_cross_merge_skewed(const void* ys, void* y, const uint16_t* idx16, int order, int K, int B,
                                          int D, int H, int W, int dtype, void* stream) {
     if (!ys || !y || !idx16) return TRAMBA_E_NULL;

@@ -97,6 +97,12 @@ __device__ __forceinline__ void bulk_s2g(void* dst_gmem, const void* src_smem, u
                  "r"(smem_u32(src_smem)), "r"(bytes)
                  : "memory");
 }
+// shared -> global bulk REDUCTION (TMA, 1-D): dst[i] += src[i] in fp32, performed at L2; same group tracking.
+__device__ __forceinline__ void bulk_reduce_add_f32_s2g(float* dst_gmem, const float* src_smem, uint32_t bytes) {
+    asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f32 [%0], [%1], %2;" ::"l"(dst_gmem),
+                 "r"(smem_u32(src_smem)), "r"(bytes)
+                 : "memory");
+}
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void bulk_wait_read() {

@@ -372,6 +372,128 @@ extern "C" int tramba_order_table(int order, int H, int W, int param, int32_t* i
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Shared-memory permutation schedule of a scan order (consumed by the fused backward, ss2d_fused_bwd.cu).
+//
+// The kernel stages an image-ordered plane with one linear TMA bulk copy and re-orders it into token order inside
+// shared memory (and scatters the token-ordered du back into the image plane).  Which (pixel -> token) move a lane
+// performs in which step is free, so it is chosen here, once per (order, H): a proper EDGE COLOURING of the bipartite
+// multigraph {source bank = pixel mod 32} x {destination bank = token mod 32} whose edges are the L tokens.  Every
+// colour class is one warp step in which all 32 source banks and all 32 destination banks are distinct: the
+// permutation runs without bank conflicts for 4-byte elements in either direction (and with at most 2-way conflicts
+// for 2-byte elements), for ANY order table -- column-major, windows, dilation phases, Bresenham lines with
+// duplicates.  Koenig: Delta colours suffice (Delta = largest bank degree = L / 32 for permutations).
+//
+// Entry = (2 * pixel) | (2 * token) << 16 (byte offsets for 2-byte elements; << 1 for 4-byte), 0xFFFFFFFF = no move.
+// Layout: blocks of 64 entries = two steps interleaved (entry 2 * lane + c of a block = step c of that block), since a
+// thread fetches two consecutive entries with one 8-byte load.  `len` (entries per direction, a multiple of
+// max(64, 2 * L / 18)) is common to all directions of the order.
+// kind[k]: 0 = identity (token t = pixel t: no permutation pass), 1 = reversed identity, 2 = permutation,
+//          3 = table with repeated pixels (the merge side needs atomic adds and a zeroed plane).
+namespace {
+
+int colour_tokens(const int32_t* idx, int L, std::vector<int>& colour) {
+    constexpr int NB = 32;
+    std::vector<int> degL(NB, 0), degR(NB, 0);
+    for (int t = 0; t < L; ++t) ++degL[idx[t] & (NB - 1)], ++degR[t & (NB - 1)];
+    int delta = 0;
+    for (int b = 0; b < NB; ++b) delta = std::max(delta, std::max(degL[b], degR[b]));
+    std::vector<int> atL(static_cast<size_t>(NB) * delta, -1), atR(static_cast<size_t>(NB) * delta, -1);
+    colour.assign(L, -1);
+    auto slotL = [&](int u, int c) -> int& { return atL[static_cast<size_t>(u) * delta + c]; };
+    auto slotR = [&](int v, int c) -> int& { return atR[static_cast<size_t>(v) * delta + c]; };
+    std::vector<int> path;
+    for (int e = 0; e < L; ++e) {
+        const int u = idx[e] & (NB - 1), v = e & (NB - 1);
+        int a = 0, b = 0;
+        while (slotL(u, a) != -1) ++a;
+        while (slotR(v, b) != -1) ++b;
+        if (a != b) {
+            // free colour a at v: swap a <-> b along the alternating path that starts with v's a-edge
+            path.clear();
+            int side = 1, node = v, want = a;  // side 1 = right vertex
+            for (;;) {
+                const int f = side ? slotR(node, want) : slotL(node, want);
+                if (f == -1) break;
+                path.push_back(f);
+                node = side ? (idx[f] & (NB - 1)) : (f & (NB - 1));
+                side ^= 1;
+                want = (want == a) ? b : a;
+            }
+            for (int f : path) slotL(idx[f] & (NB - 1), colour[f]) = -1, slotR(f & (NB - 1), colour[f]) = -1;
+            for (int f : path) {
+                colour[f] = (colour[f] == a) ? b : a;
+                slotL(idx[f] & (NB - 1), colour[f]) = f, slotR(f & (NB - 1), colour[f]) = f;
+            }
+        }
+        colour[e] = a;
+        slotL(u, a) = e, slotR(v, a) = e;
+    }
+    return delta;
+}
+
+int table_kind(const int32_t* idx, int L) {
+    bool ident = true, rev = true;
+    std::vector<uint8_t> seen(L, 0);
+    bool dup = false;
+    for (int t = 0; t < L; ++t) {
+        ident = ident && idx[t] == t;
+        rev = rev && idx[t] == L - 1 - t;
+        if (seen[idx[t]]) dup = true;
+        seen[idx[t]] = 1;
+    }
+    return ident ? 0 : rev ? 1 : dup ? 3 : 2;
+}
+
+size_t sched_granule(int L) { return static_cast<size_t>(std::max(64, 2 * (L / 18))); }
+
+}  // namespace
+
+extern "C" size_t tramba_order_sched_len(int order, int H, int W, int param) {
+    const int K = tramba_order_num_directions(order);
+    if (K < 0 || H <= 0 || W <= 0 || static_cast<long long>(H) * W > 32768) return 0;
+    const int L = H * W;
+    std::vector<int32_t> t(static_cast<size_t>(K) * L);
+    if (tramba_order_table(order, H, W, param, t.data()) != TRAMBA_OK) return 0;
+    int delta = 0;
+    for (int k = 0; k < K; ++k) {
+        std::vector<int> deg(32, 0);
+        for (int i = 0; i < L; ++i) ++deg[t[static_cast<size_t>(k) * L + i] & 31];
+        for (int b = 0; b < 32; ++b) delta = std::max(delta, deg[b]);
+    }
+    delta = std::max(delta, (L + 31) / 32);
+    const size_t g = sched_granule(L);
+    return (static_cast<size_t>(delta) * 32 + g - 1) / g * g;
+}
+
+extern "C" int tramba_order_sched(int order, int H, int W, int param, uint32_t* sched_out, int32_t* kind_out) {
+    if (!sched_out || !kind_out) return TRAMBA_E_NULL;
+    const int K = tramba_order_num_directions(order);
+    if (K < 0) return K;
+    const size_t len = tramba_order_sched_len(order, H, W, param);
+    if (len == 0) return TRAMBA_E_LIMIT;
+    const int L = H * W;
+    std::vector<int32_t> t(static_cast<size_t>(K) * L);
+    const int rc = tramba_order_table(order, H, W, param, t.data());
+    if (rc != TRAMBA_OK) return rc;
+    std::vector<int> colour, fill;
+    for (int k = 0; k < K; ++k) {
+        const int32_t* idx = t.data() + static_cast<size_t>(k) * L;
+        uint32_t* out = sched_out + static_cast<size_t>(k) * len;
+        std::fill(out, out + len, 0xFFFFFFFFu);
+        kind_out[k] = table_kind(idx, L);
+        const int steps = colour_tokens(idx, L, colour);
+        if (static_cast<size_t>(steps) * 32 > len) return TRAMBA_E_LIMIT;
+        fill.assign(steps, 0);
+        for (int e = 0; e < L; ++e) {
+            const int s = colour[e], lane = fill[s]++;
+            const size_t pos = static_cast<size_t>(s >> 1) * 64 + 2 * lane + (s & 1);
+            out[pos] = (static_cast<uint32_t>(idx[e]) * 2u) | (static_cast<uint32_t>(e) * 2u) << 16;
+        }
+    }
+    return TRAMBA_OK;
+}
+
 // DCT_2D.py:37-45: W[v][j] = cos(pi*(0.5+j)*v/n)/sqrt(n) * (v ? sqrt(2) : 1), in double, stored fp32.
 extern "C" void tramba_dct_basis(int n, float* w_out) {
     const double pi = 3.141592653589793;  // == math.pi

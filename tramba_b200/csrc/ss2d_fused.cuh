@@ -61,6 +61,33 @@ struct FusedArgs {
     int xb;               // 2 = double-buffered staging, 1 = single
 };
 
+// Backward with the merge of du folded in (ss2d_fused_bwd_dx.cu)
+struct FusedDxArgs {
+    const void* x;          // (B, D, L) image order
+    const void* dts;        // (B, K, D, L) scan order
+    const void* Bs;         // (B, K, L)
+    const void* Cs;         // (B, K, L)
+    const float* A;         // (K*D)
+    const float* Dp;        // (K*D) or null
+    const float* bias;      // (K*D) or null
+    const uint32_t* sched;  // (K, sched_len) permutation schedule (tramba_order_sched), device
+    const float* dy;        // (B, D, L) fp32 image order
+    float* dx;              // (B, D, L) fp32 image order, ZEROED by the caller; accumulated with bulk reductions
+    void* ddts;             // (B, K, D, L) in_t scan order
+    float* dBs;             // (B, K, L) fp32, zeroed by the caller
+    float* dCs;
+    float* dA;              // (B, K*D) partials
+    float* dD;
+    float* dbias;
+    int B, K, D;
+    int sched_len;          // entries per direction
+    uint32_t kinds;         // 4 bits per direction: 0 identity, 1 reversed identity, 2 permutation, 3 with repeats
+    int softplus;
+    int R;                  // rounds per item (set by the launcher)
+};
+cudaError_t launch_ss2d_fused_bwd_dx(const FusedDxArgs& a, int L, int in_dtype, cudaStream_t st);
+bool ss2d_fused_bwd_dx_fits(int L, int es);
+
 cudaError_t launch_ss2d_fused_fwd(const FusedArgs& a, int in_dtype, cudaStream_t st);
 cudaError_t launch_ss2d_fused_bwd(const FusedArgs& a, int in_dtype, cudaStream_t st);
 size_t ss2d_fused_fwd_smem(int L, int es, int xb);

@@ -1,0 +1,512 @@
+// Fused SS2D core, backward WITH the cross-merge of du folded in (sm_100a).  See ss2d_fused.cuh for the data model.
+//
+// Replaces CrossMerge*.backward -> SelectiveScanOflex.backward -> CrossScan*.backward of
+// Models/SS2D/csms6s.py:45-55, 914-923, 25-31 (and the _Dilation / _Window / _Line variants) for N = 1 in ONE kernel:
+//     in : x, dy (B, D, L) IMAGE order; delta (B, K, D, L), B, C (B, K, L) scan order
+//     out: dx (B, D, L) fp32 IMAGE order (accumulated over the K directions with TMA bulk reductions at L2),
+//          ddelta (B, K, D, L) scan order, dB / dC (B, K, L), per-(b, row) partials of dA / dD / ddelta_bias.
+// Neither xs, nor the K-fold copy of dy, nor du (the K-fold gradient w.r.t. xs) is ever written to HBM.
+//
+// Differences from the first-generation kernel (ss2d_fused_bwd.cu):
+//   * every operand plane moves with 1-D TMA bulk copies (no per-thread cp.async staging, no skewed planes);
+//   * geometry is a template parameter (TP threads per plane, L = 18 * TP): all index arithmetic folds;
+//   * the scan order is applied ONCE per round by a shared -> shared permutation pass that follows a host-made,
+//     bank-conflict-free schedule (tramba_order_sched: an edge colouring of pixel banks x token banks), after which
+//     the three recurrence passes read token-ordered chunks with conflict-free vector loads -- instead of five
+//     table-driven gathers per token; directions whose table is the identity skip the pass altogether;
+//   * du never leaves the SM in scan order: it is scattered back into an image-ordered fp32 plane by the inverse of
+//     the same schedule and added to dx in global memory with cp.reduce.async.bulk (.add.f32).
+//
+// Work item = (b, k, block of R*PP channels); round = PP whole planes of direction k (NT * S = 9216 tokens).
+// Per round:  wait x/dy -> [permute image -> token order] -> pass 1 (forward fold + reverse fold of the segment)
+//   -> scans over the plane's threads -> pass 2a (dh, right to left) -> pass 2b (h, du, ddelta, dB/dC/dA/dD/dbias)
+//   -> [scatter du token -> image order] -> bulk store ddelta, bulk reduce-add dx.
+// PIPE (16-bit operands): two (x, dy) plane sets used alternately and two delta buffers, so the TMA loads of round
+// s + 1 overlap round s.  !PIPE (fp32 operands, which need twice the staging): one set (+ the token-ordered set),
+// loads issued when the round's stores have been read.
+#include "ss2d_fused.cuh"
+
+namespace tramba {
+
+namespace {
+
+constexpr int S = kFusedS;
+constexpr int NT = kFusedNT;
+constexpr int TOK = kFusedTok;
+constexpr int NW = NT / 32;
+
+constexpr size_t al16(size_t v) { return (v + 15) / 16 * 16; }
+
+template <int ES, int TP, bool PIPE>
+struct DxLayout {
+    static constexpr int L = TP * S;
+    static constexpr size_t XB = static_cast<size_t>(TOK) * ES, YB = static_cast<size_t>(TOK) * 4;
+    static constexpr size_t x0 = 0, y0 = XB, x1 = XB + YB, y1 = 2 * XB + YB;  // plane sets 0 and 1
+    static constexpr size_t d0 = 2 * (XB + YB);                               // delta in / ddelta out (in place)
+    static constexpr size_t d1 = PIPE ? d0 + XB : d0;
+    static constexpr size_t dx = d1 + XB;                                     // PIPE: image-ordered du staging
+    static constexpr size_t b = PIPE ? dx + YB : dx;
+    static constexpr size_t c = b + al16(static_cast<size_t>(L) * ES);
+    static constexpr size_t tot = c + al16(static_cast<size_t>(L) * ES);
+    static constexpr size_t red = tot + 2 * 2 * NW * sizeof(float2);
+    static constexpr size_t bar = al16(red + 3 * NW * sizeof(float));
+    static constexpr size_t total = bar + 8 * sizeof(uint64_t);
+};
+
+template <typename in_t, bool SOFTPLUS, int TP, bool PIPE>
+__global__ void __launch_bounds__(NT, 1) ss2d_bwd_dx_kernel(const FusedDxArgs p) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    constexpr int ES = sizeof(in_t);
+    constexpr int L = TP * S, PP = NT / TP;
+    using Lay = DxLayout<ES, TP, PIPE>;
+    float* const sDXs = reinterpret_cast<float*>(smem + Lay::dx);  // PIPE only
+    in_t* const sB = reinterpret_cast<in_t*>(smem + Lay::b);
+    in_t* const sC = reinterpret_cast<in_t*>(smem + Lay::c);
+    float2* const stot = reinterpret_cast<float2*>(smem + Lay::tot);  // [2 parity][2 fwd/rev][NW]
+    float* const sred = reinterpret_cast<float*>(smem + Lay::red);    // [3][NW]
+    uint64_t* const barXY = reinterpret_cast<uint64_t*>(smem + Lay::bar);  // [2] per plane set
+    uint64_t* const barD = barXY + 2;                                      // [2] per delta buffer
+    uint64_t* const barBC = barXY + 4;                                     // [1]
+    auto sX = [&](int set) { return reinterpret_cast<in_t*>(smem + (set ? Lay::x1 : Lay::x0)); };
+    auto sY = [&](int set) { return reinterpret_cast<float*>(smem + (set ? Lay::y1 : Lay::y0)); };
+    auto sD = [&](int buf) { return reinterpret_cast<in_t*>(smem + (buf ? Lay::d1 : Lay::d0)); };
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int q = tid / TP;
+    const int j = tid - q * TP;
+    constexpr int width = TP < 32 ? TP : 32;
+    const int sl = lane & (width - 1);
+    constexpr int nwg = TP > 32 ? (TP >> 5) : 1;  // warps per plane
+    const int wq = TP > 32 ? (j >> 5) : 0;
+    const int gw0 = TP > 32 ? q * nwg : 0;
+
+    const in_t* __restrict__ gx = static_cast<const in_t*>(p.x);
+    const in_t* __restrict__ gd = static_cast<const in_t*>(p.dts);
+    const in_t* __restrict__ gB = static_cast<const in_t*>(p.Bs);
+    const in_t* __restrict__ gC = static_cast<const in_t*>(p.Cs);
+    in_t* __restrict__ gdd = static_cast<in_t*>(p.ddts);
+
+    const int K = p.K, D = p.D, R = p.R;
+    const int RB = R * PP;  // channels per item
+    const int dblocks = D / RB;
+    const int items = p.B * K * dblocks;
+    const int my_items = (items - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) /
+                         static_cast<int>(gridDim.x);
+    const int nrounds = my_items * R;
+    if (nrounds <= 0) return;
+
+    if (tid == 0) {
+        mbar_init(&barXY[0], 1), mbar_init(&barXY[1], 1), mbar_init(&barD[0], 1), mbar_init(&barD[1], 1);
+        mbar_init(&barBC[0], 1);
+        fence_mbar_init();
+        fence_proxy_async_smem();
+    }
+    __syncthreads();
+
+    auto item_coord = [&](int it, int& b, int& k, int& d0) {
+        const int item = static_cast<int>(blockIdx.x) + it * static_cast<int>(gridDim.x);
+        const int db = item % dblocks;
+        const int bk = item / dblocks;
+        k = bk % K;
+        b = bk / K;
+        d0 = db * RB;
+    };
+    // ---- producers (thread 0 only): coordinates of global round s of this CTA
+    auto issue_xy = [&](int set, int s) {
+        int b, k, d0;
+        item_coord(s / R, b, k, d0);
+        d0 += (s % R) * PP;
+        const long long pl = (static_cast<long long>(b) * D + d0) * L;
+        mbar_expect_tx(&barXY[set], TOK * (ES + 4));
+        bulk_g2s(sX(set), gx + pl, TOK * ES, &barXY[set]);
+        bulk_g2s(sY(set), p.dy + pl, TOK * 4, &barXY[set]);
+    };
+    auto issue_d = [&](int buf, int s) {
+        int b, k, d0;
+        item_coord(s / R, b, k, d0);
+        d0 += (s % R) * PP;
+        mbar_expect_tx(&barD[buf], TOK * ES);
+        bulk_g2s(sD(buf), gd + ((static_cast<long long>(b) * K + k) * D + d0) * L, TOK * ES, &barD[buf]);
+    };
+    auto issue_bc = [&](int it) {
+        int b, k, d0;
+        item_coord(it, b, k, d0);
+        constexpr uint32_t lb = L * ES;
+        mbar_expect_tx(&barBC[0], 2 * lb);
+        bulk_g2s(sB, gB + (static_cast<long long>(b) * K + k) * L, lb, &barBC[0]);
+        bulk_g2s(sC, gC + (static_cast<long long>(b) * K + k) * L, lb, &barBC[0]);
+    };
+    if (tid == 0) {
+        issue_bc(0);
+        issue_xy(0, 0);
+        issue_d(0, 0);
+    }
+
+    uint32_t phXY0 = 0, phXY1 = 0, phD0 = 0, phD1 = 0;  // mbarrier phase parities (uniform)
+    int ld = 0;                                         // plane set that receives / holds this round's x, dy
+    int s = 0;
+    for (int it = 0; it < my_items; ++it) {
+        int b, k, d00;
+        item_coord(it, b, k, d00);
+        const int kind = (p.kinds >> (4 * k)) & 15;  // 0 identity, 1 reversed identity, 2 permutation, 3 with repeats
+        const bool perm = kind != 0;
+        const bool dup = kind == 3;
+        const uint2* __restrict__ sched = reinterpret_cast<const uint2*>(p.sched + static_cast<size_t>(k) * p.sched_len) + j;
+        const int sched_iters = p.sched_len / (2 * TP);
+        float accB[S], accC[S];
+#pragma unroll
+        for (int m = 0; m < S; ++m) accB[m] = 0.f, accC[m] = 0.f;
+        mbar_wait(&barBC[0], static_cast<uint32_t>(it & 1));
+        const in_t* Bq = sB + j * S;
+        const in_t* Cq = sC + j * S;
+
+        for (int r = 0; r < R; ++r, ++s) {
+            const bool has_next = s + 1 < nrounds;
+            const int dbuf = PIPE ? (s & 1) : 0;
+            if (PIPE && !perm && has_next && tid == 0) issue_xy(ld ^ 1, s + 1);
+            if (ld == 0) {
+                mbar_wait(&barXY[0], phXY0);
+                phXY0 ^= 1;
+            } else {
+                mbar_wait(&barXY[1], phXY1);
+                phXY1 ^= 1;
+            }
+            int ds = ld;  // set the recurrence passes read (token order)
+            if (perm) {
+                // ---- image order -> token order, by the conflict-free schedule (entry: 2*pixel | 2*token << 16)
+                const unsigned char* xi = reinterpret_cast<const unsigned char*>(sX(ld) + static_cast<size_t>(q) * L);
+                const unsigned char* yi = reinterpret_cast<const unsigned char*>(sY(ld) + static_cast<size_t>(q) * L);
+                unsigned char* xt = reinterpret_cast<unsigned char*>(sX(ld ^ 1) + static_cast<size_t>(q) * L);
+                unsigned char* yt = reinterpret_cast<unsigned char*>(sY(ld ^ 1) + static_cast<size_t>(q) * L);
+                const uint2* sc = sched;
+#pragma unroll 3
+                for (int n = 0; n < sched_iters; ++n, sc += TP) {
+                    const uint2 e2 = __ldg(sc);
+#pragma unroll
+                    for (int c = 0; c < 2; ++c) {
+                        const uint32_t e = c ? e2.y : e2.x;
+                        if (e != 0xFFFFFFFFu) {
+                            const uint32_t src2 = e & 0xFFFFu, dst2 = e >> 16;
+                            if constexpr (ES == 2) {
+                                *reinterpret_cast<uint16_t*>(xt + dst2) = *reinterpret_cast<const uint16_t*>(xi + src2);
+                            } else {
+                                *reinterpret_cast<float*>(xt + 2 * dst2) = *reinterpret_cast<const float*>(xi + 2 * src2);
+                            }
+                            *reinterpret_cast<float*>(yt + 2 * dst2) = *reinterpret_cast<const float*>(yi + 2 * src2);
+                        }
+                    }
+                }
+                __syncthreads();  // token-ordered set complete; the image-ordered set is dead
+                if (PIPE && has_next && tid == 0) issue_xy(ld, s + 1);
+                ds = ld ^ 1;
+            }
+            const int d0 = d00 + r * PP;
+            const int d = d0 + q;
+            const int row = k * D + d;
+            const float Ar = __ldg(p.A + row);
+            const float A2 = Ar * kLog2e;
+            const float Dd = p.Dp ? __ldg(p.Dp + row) : 0.f;
+            const float bias = p.bias ? __ldg(p.bias + row) : 0.f;
+            if (dbuf == 0) {
+                mbar_wait(&barD[0], phD0);
+                phD0 ^= 1;
+            } else {
+                mbar_wait(&barD[1], phD1);
+                phD1 ^= 1;
+            }
+            const in_t* xq = sX(ds) + static_cast<size_t>(q) * L + j * S;  // token order: this thread's chunk
+            float* yq = sY(ds) + static_cast<size_t>(q) * L + j * S;
+            in_t* dq = sD(dbuf) + static_cast<size_t>(q) * L + j * S;
+
+            // ---- pass 1: forward fold (P, Sf) and reverse fold (P, Sr) of the segment
+            float sp[S];
+            float P = 1.f, Sf = 0.f, Sr = 0.f;
+            {
+                load_tokens<S>(dq, sp);
+#pragma unroll
+                for (int mp = 0; mp < S / 2; ++mp) {
+                    float Bv[2], Cv[2], uv[2], yv[2];
+                    load_pair(Bq, mp, Bv[0], Bv[1]);
+                    load_pair(Cq, mp, Cv[0], Cv[1]);
+                    load_pair(xq, mp, uv[0], uv[1]);
+                    load_pair(yq, mp, yv[0], yv[1]);
+#pragma unroll
+                    for (int h2 = 0; h2 < 2; ++h2) {
+                        const int m = 2 * mp + h2;
+                        const float raw = sp[m] + bias;
+                        float e;
+                        sp[m] = !SOFTPLUS ? raw : (ES == 2 ? softplus20_fast(raw) : softplus20(raw, e));
+                        const float a = ex2f(sp[m] * A2);
+                        const float bb = sp[m] * Bv[h2] * uv[h2];
+                        const float g = Cv[h2] * yv[h2];
+                        Sf = fmaf(a, Sf, bb);
+                        P *= a;
+                        Sr = fmaf(P, g, Sr);
+                    }
+                }
+            }
+            // ---- carries: forward scan (h entering from the left), reverse scan (E entering from the right)
+            float Pf = P, Pr = P;
+            fused_scan(Pf, Sf, sl, width);
+            fused_scan_rev(Pr, Sr, sl, width);
+            float Pfe = __shfl_up_sync(0xffffffffu, Pf, 1, width);
+            float Sfe = __shfl_up_sync(0xffffffffu, Sf, 1, width);
+            float Pre = __shfl_down_sync(0xffffffffu, Pr, 1, width);
+            float Sre = __shfl_down_sync(0xffffffffu, Sr, 1, width);
+            if (sl == 0) Pfe = 1.f, Sfe = 0.f;
+            if (sl == width - 1) Pre = 1.f, Sre = 0.f;
+            const int par = s & 1;
+            float2* totF = stot + (par * 2 + 0) * NW;
+            float2* totR = stot + (par * 2 + 1) * NW;
+            if (TP > 32) {
+                if (lane == 31) totF[warp] = make_float2(Pf, Sf);
+                if (lane == 0) totR[warp] = make_float2(Pr, Sr);
+            }
+            if (PIPE && tid == 0 && s > 0) bulk_wait_read<0>();  // previous round's ddelta / du staging have left
+            __syncthreads();
+            if (PIPE && has_next && tid == 0) issue_d((s + 1) & 1, s + 1);
+            float* const dxp = PIPE ? sDXs : sY(ld);  // image-ordered du of this round (!PIPE: the dead dy planes)
+            if (dup) {  // directions that skip pixels / hit pixels repeatedly: start from zero, add atomically
+                float4* z = reinterpret_cast<float4*>(dxp);
+                for (int e = tid; e < TOK / 4; e += NT) z[e] = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+            float hin = Sfe, Ein = Sre;
+            if (TP > 32) {
+                float hp = 0.f;
+                for (int w = 0; w < wq; ++w) {
+                    const float2 t = totF[gw0 + w];
+                    hp = fmaf(t.x, hp, t.y);
+                }
+                hin = fmaf(Pfe, hp, Sfe);
+                float ep = 0.f;
+                for (int w = nwg - 1; w > wq; --w) {
+                    const float2 t = totR[gw0 + w];
+                    ep = fmaf(t.x, ep, t.y);
+                }
+                Ein = fmaf(Pre, ep, Sre);
+            }
+            // ---- pass 2a: right-to-left, dh_t = g_t + E_{t+1}
+            float dh[S];
+            {
+                float E = Ein;
+#pragma unroll
+                for (int mp = S / 2 - 1; mp >= 0; --mp) {
+                    float Cv[2], yv[2];
+                    load_pair(Cq, mp, Cv[0], Cv[1]);
+                    load_pair(yq, mp, yv[0], yv[1]);
+#pragma unroll
+                    for (int h2 = 1; h2 >= 0; --h2) {
+                        const int m = 2 * mp + h2;
+                        const float g = Cv[h2] * yv[h2];
+                        const float a = ex2f(sp[m] * A2);
+                        dh[m] = g + E;
+                        E = a * dh[m];
+                    }
+                }
+            }
+            // ---- pass 2b: left-to-right, h_t; du, ddelta; accumulate dB, dC, dA, dD, dbias
+            float h = hin, sA = 0.f, sDs = 0.f, sb = 0.f;
+#pragma unroll
+            for (int mp = 0; mp < S / 2; ++mp) {
+                float Bv[2], uv[2], yv[2];
+                load_pair(Bq, mp, Bv[0], Bv[1]);
+                load_pair(xq, mp, uv[0], uv[1]);
+                load_pair(yq, mp, yv[0], yv[1]);
+#pragma unroll
+                for (int h2 = 0; h2 < 2; ++h2) {
+                    const int m = 2 * mp + h2;
+                    const float u = uv[h2], dyv = yv[h2], Bm = Bv[h2];
+                    const float a = ex2f(sp[m] * A2);
+                    const float w = a * h;  // a_t * h_{t-1}
+                    const float bu = Bm * u;
+                    h = fmaf(sp[m], bu, w);  // h_t
+                    const float dhs = dh[m] * sp[m];
+                    const float du = fmaf(Dd, dyv, dhs * Bm);
+                    float dd = dh[m] * fmaf(Ar, w, bu);
+                    if (SOFTPLUS) {
+                        // sigmoid(raw) = 1 - exp(-softplus(raw)) = -expm1(-sp); series below 1/8 keeps fp32 relative
+                        // accuracy where 1 - exp(.) would cancel (moot for 16-bit operands: <= 6e-8 absolute)
+                        const float t = sp[m];
+                        if (ES == 2) {
+                            dd *= 1.0f - ex2f(-t * kLog2e);
+                        } else {
+                            const float ser = t * (1.0f - t * (0.5f - t * (0.16666667f - t * 0.041666668f)));
+                            dd *= (t < 0.125f) ? ser : (1.0f - ex2f(-t * kLog2e));
+                        }
+                    }
+                    accB[m] = fmaf(dhs, u, accB[m]);
+                    accC[m] = fmaf(dyv, h, accC[m]);
+                    sA = fmaf(dhs, w, sA);
+                    sDs = fmaf(dyv, u, sDs);
+                    sb += dd;
+                    sp[m] = dd;  // reuse: sp <- ddelta, dh <- du
+                    dh[m] = du;
+                }
+            }
+            store_tokens<S>(dq, sp);  // ddelta over delta, in place (this thread's own chunk)
+            // du: identity order -> straight into the image-ordered plane (!PIPE: over this thread's own dy chunk,
+            // all of which has been read); otherwise token order over dy_tok, scattered below
+            store_tokens<S>((perm ? yq : dxp + static_cast<size_t>(q) * L + j * S), dh);
+            // ---- per-row sums over L: warp reduce, then over the plane's warps
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) {
+                if (off < width) {
+                    sA += __shfl_xor_sync(0xffffffffu, sA, off, width);
+                    sDs += __shfl_xor_sync(0xffffffffu, sDs, off, width);
+                    sb += __shfl_xor_sync(0xffffffffu, sb, off, width);
+                }
+            }
+            if (TP > 32 && lane == 0) sred[warp] = sA, sred[NW + warp] = sDs, sred[2 * NW + warp] = sb;
+            if (perm) {
+                __syncthreads();  // du in token order complete (and the zero fill of a dup direction)
+                // ---- token order -> image order: inverse walk of the same schedule
+                const unsigned char* ut = reinterpret_cast<const unsigned char*>(sY(ds) + static_cast<size_t>(q) * L);
+                unsigned char* di = reinterpret_cast<unsigned char*>(dxp + static_cast<size_t>(q) * L);
+                const uint2* sc = sched;
+#pragma unroll 3
+                for (int n = 0; n < sched_iters; ++n, sc += TP) {
+                    const uint2 e2 = __ldg(sc);
+#pragma unroll
+                    for (int c = 0; c < 2; ++c) {
+                        const uint32_t e = c ? e2.y : e2.x;
+                        if (e != 0xFFFFFFFFu) {
+                            const uint32_t src2 = e & 0xFFFFu, dst2 = e >> 16;
+                            const float v = *reinterpret_cast<const float*>(ut + 2 * dst2);
+                            if (dup) {
+                                atomicAdd(reinterpret_cast<float*>(di + 2 * src2), v);
+                            } else {
+                                *reinterpret_cast<float*>(di + 2 * src2) = v;
+                            }
+                        }
+                    }
+                }
+            }
+            fence_proxy_async_smem();
+            __syncthreads();
+            if (tid == 0) {
+                bulk_s2g(gdd + ((static_cast<long long>(b) * K + k) * D + d0) * L, sD(dbuf), TOK * ES);
+                bulk_reduce_add_f32_s2g(p.dx + (static_cast<long long>(b) * D + d0) * L, dxp, TOK * 4);
+                bulk_commit();
+                if (!PIPE) {
+                    bulk_wait_read<0>();
+                    if (has_next) {
+                        issue_xy(ld, s + 1);
+                        issue_d(0, s + 1);
+                    }
+                }
+            }
+            if (TP > 32 && j == 0) {
+                float tA = 0.f, tD = 0.f, tb = 0.f;
+                for (int w = 0; w < nwg; ++w) tA += sred[gw0 + w], tD += sred[NW + gw0 + w], tb += sred[2 * NW + gw0 + w];
+                sA = tA, sDs = tD, sb = tb;
+            }
+            if (j == 0) {
+                const size_t o = static_cast<size_t>(b) * K * D + row;
+                p.dA[o] = sA;
+                if (p.dD) p.dD[o] = sDs;
+                if (p.dbias) p.dbias[o] = sb;
+            }
+            if (PIPE && !perm) ld ^= 1;
+        }
+        // ---- item flush: dB / dC of the item's channels (token order, registers) -> global reds
+        {
+            float* gdB = p.dBs + (static_cast<size_t>(b) * K + k) * L + j * S;
+            float* gdC = p.dCs + (static_cast<size_t>(b) * K + k) * L + j * S;
+            if (PP == 1) {
+#pragma unroll
+                for (int m = 0; m < S; m += 2) {
+                    asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(gdB + m), "f"(accB[m]), "f"(accB[m + 1])
+                                 : "memory");
+                    asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(gdC + m), "f"(accC[m]), "f"(accC[m + 1])
+                                 : "memory");
+                }
+            } else {
+                // PP planes hold partial sums for the same tokens: add them up in shared memory first.  Scratch =
+                // a plane buffer nobody uses between items: the du staging once its bulk reduction has been read
+                // (PIPE), the token-ordered dy planes (!PIPE; the next round's loads went to the other set).
+                if (PIPE && tid == 0) bulk_wait_read<0>();
+                __syncthreads();
+                float* f = PIPE ? sDXs : sY(ld ^ 1);  // [2][L] floats, 2 * L <= TOK
+                for (int e = tid; e < 2 * L; e += NT) f[e] = 0.f;
+                __syncthreads();
+#pragma unroll
+                for (int m = 0; m < S; ++m) {
+                    atomicAdd(f + j * S + m, accB[m]);
+                    atomicAdd(f + L + j * S + m, accC[m]);
+                }
+                __syncthreads();
+                float* gB2 = p.dBs + (static_cast<size_t>(b) * K + k) * L;
+                float* gC2 = p.dCs + (static_cast<size_t>(b) * K + k) * L;
+                for (int e = tid * 2; e < L; e += NT * 2) {
+                    asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(gB2 + e), "f"(f[e]), "f"(f[e + 1]) : "memory");
+                    asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(gC2 + e), "f"(f[L + e]), "f"(f[L + e + 1])
+                                 : "memory");
+                }
+            }
+            __syncthreads();  // everybody is done with sB / sC (and the scratch) before the next item's loads
+            if (tid == 0 && it + 1 < my_items) issue_bc(it + 1);
+        }
+    }
+    if (tid == 0) bulk_wait_all<0>();
+}
+
+// Channels per item: enough rounds that the per-item dB/dC flush is amortised (>= 8 channels).
+int pick_rounds(int D, int PP) {
+    int R = 1;
+    while (R * PP < 8 && D % (2 * R * PP) == 0) R *= 2;
+    return R;
+}
+
+template <typename in_t, bool SOFTPLUS, int TP>
+cudaError_t launch_tp(const FusedDxArgs& a, cudaStream_t st) {
+    constexpr bool PIPE = sizeof(in_t) == 2;
+    using Lay = DxLayout<sizeof(in_t), TP, PIPE>;
+    if (Lay::total > 227 * 1024) return cudaErrorInvalidConfiguration;
+    auto kern = ss2d_bwd_dx_kernel<in_t, SOFTPLUS, TP, PIPE>;
+    if (cudaError_t e = ensure_dyn_smem(kern, static_cast<int>(Lay::total)); e != cudaSuccess) return e;
+    const int sms = device_sms();
+    FusedDxArgs b = a;
+    constexpr int PP = NT / TP;
+    b.R = pick_rounds(a.D, PP);
+    const int items = a.B * a.K * (a.D / (b.R * PP));
+    const int grid = items < sms ? items : sms;
+    kern<<<grid, NT, Lay::total, st>>>(b);
+    note_launch();
+    return cudaGetLastError();
+}
+
+template <typename in_t, bool SOFTPLUS>
+cudaError_t launch_t(const FusedDxArgs& a, int TP, cudaStream_t st) {
+    switch (TP) {
+        case 512: return launch_tp<in_t, SOFTPLUS, 512>(a, st);
+        case 128: return launch_tp<in_t, SOFTPLUS, 128>(a, st);
+        case 32: return launch_tp<in_t, SOFTPLUS, 32>(a, st);
+        case 8: return launch_tp<in_t, SOFTPLUS, 8>(a, st);
+        default: return cudaErrorInvalidConfiguration;
+    }
+}
+
+}  // namespace
+
+bool ss2d_fused_bwd_dx_fits(int L, int es) {
+    const int TP = L / S;
+    if (TP * S != L) return false;
+    auto tot = [&](auto lay) { return decltype(lay)::total <= 227 * 1024; };
+    switch (TP) {
+        case 512: return es == 2 ? tot(DxLayout<2, 512, true>{}) : tot(DxLayout<4, 512, false>{});
+        case 128: return es == 2 ? tot(DxLayout<2, 128, true>{}) : tot(DxLayout<4, 128, false>{});
+        case 32: return es == 2 ? tot(DxLayout<2, 32, true>{}) : tot(DxLayout<4, 32, false>{});
+        case 8: return es == 2 ? tot(DxLayout<2, 8, true>{}) : tot(DxLayout<4, 8, false>{});
+        default: return false;
+    }
+}
+
+cudaError_t launch_ss2d_fused_bwd_dx(const FusedDxArgs& a, int L, int in_dtype, cudaStream_t st) {
+    const int TP = L / S;
+    if (in_dtype == TRAMBA_F32) return a.softplus ? launch_t<float, true>(a, TP, st) : launch_t<float, false>(a, TP, st);
+    if (in_dtype == TRAMBA_BF16)
+        return a.softplus ? launch_t<__nv_bfloat16, true>(a, TP, st) : launch_t<__nv_bfloat16, false>(a, TP, st);
+    return cudaErrorInvalidValue;
+}
+
+}  // namespace tramba

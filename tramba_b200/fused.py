@@ -12,6 +12,7 @@ emits du / ddelta in scan order, followed by the cross-merge of du (= CrossScan.
 only; shapes the fused kernels do not cover are reported by `supported()` and run un-fused.
 """
 import ctypes
+import os
 
 import numpy as np
 import torch
@@ -57,10 +58,41 @@ def token_index(order, H, param, device):
     return hit
 
 
+# TRAMBA_FUSED_BWD=v1: the first-generation backward (du in scan order to HBM + tramba_cross_merge_skewed) instead
+# of the one that folds the merge in (tramba_ss2d_fused_bwd_dx); A/B measurements only
+_BWD_V1 = os.environ.get("TRAMBA_FUSED_BWD", "") == "v1"
+
+
+def _sched(order, H, param, device):
+    """(device (K, len) int32 schedule, host (K,) int32 kinds) of tramba_order_sched for this order / size."""
+    key = ("sched", order, H, param, device)
+    hit = _idx_cache.get(key)
+    if hit is None:
+        K = _lib.lib.tramba_order_num_directions(order)
+        n = int(_lib.lib.tramba_order_sched_len(order, H, H, param))
+        if n == 0:
+            raise RuntimeError("tramba_b200: no permutation schedule for this order / size")
+        t = np.empty((K, n), dtype=np.uint32)
+        kinds = np.empty((K,), dtype=np.int32)
+        _lib.check(_lib.lib.tramba_order_sched(order, H, H, param, t.ctypes.data, kinds.ctypes.data))
+        hit = (torch.from_numpy(t.view(np.int32)).to(device), kinds)
+        _idx_cache[key] = hit
+    return hit
+
+
+def bwd_dx_supported(order, K, D, H, W, N, dtype):
+    code = _DTYPE.get(dtype)
+    if code is None or H != W or _BWD_V1:
+        return False
+    return bool(_lib.lib.tramba_ss2d_fused_bwd_dx_supported(order, K, D, H, W, N, code))
+
+
 def supported(order, K, D, H, W, N, dtype, need_bwd=True):
     code = _DTYPE.get(dtype)
     if code is None or H != W:
         return False
+    if need_bwd and bwd_dx_supported(order, K, D, H, W, N, dtype):
+        need_bwd = False          # the merged backward covers it; only the forward's own limits remain
     return bool(_lib.lib.tramba_ss2d_fused_supported(order, K, D, H, W, N, code, int(need_bwd)))
 
 
@@ -107,6 +139,8 @@ class SS2DCoreFused(torch.autograd.Function):
         L = H * W
         dt = x.dtype
         dy = _c16(dy.float())
+        if bwd_dx_supported(order, K, D, H, W, 1, dt):
+            return SS2DCoreFused._backward_dx(ctx, dy)
         du = torch.empty((B, K, D, L), device=x.device, dtype=dt)
         ddts = torch.empty((B, K, D, L), device=x.device, dtype=dt)
         dBs = torch.empty((B, K, L), device=x.device, dtype=torch.float32)
@@ -129,6 +163,38 @@ class SS2DCoreFused(torch.autograd.Function):
         part = part.sum(1)                                                        # one reduction over the batch
         return (dx, ddts, dBs.to(dt), dCs.to(dt), part[0], None if Ds is None else part[1],
                 None if delta_bias is None else part[2], None, None, None)
+
+
+def _backward_dx(ctx, dy):
+    """One kernel: CrossMerge*.backward -> SelectiveScanOflex.backward -> CrossScan*.backward (csms6s.py:45-55,
+    914-923, 25-31).  dx comes back merged over the K directions in fp32; du never exists in HBM."""
+    x, dts, Bs, Cs, A, Ds, delta_bias, idx = ctx.saved_tensors
+    order, param, K, B, D, H, W, softplus = ctx.meta
+    L = H * W
+    dt = x.dtype
+    sched, kinds = _sched(order, H, param, x.device)
+    dx = torch.empty((B, D, L), device=x.device, dtype=torch.float32)
+    ddts = torch.empty((B, K, D, L), device=x.device, dtype=dt)
+    dBs = torch.empty((B, K, L), device=x.device, dtype=torch.float32)
+    dCs = torch.empty((B, K, L), device=x.device, dtype=torch.float32)
+    part = torch.zeros((3, B, K * D), device=x.device, dtype=torch.float32)   # dA | dD | dbias partials per b
+    dA, dD, db = part[0], (None if Ds is None else part[1]), (None if delta_bias is None else part[2])
+    es = x.element_size()
+    # SURVEY 8(d) operator formula per direction (read u, delta, dout; write du, ddelta; B/C in, dB/dC out): what the
+    # kernel REPLACES.  bytes_min = what it must move itself (x, dy once; dx once; delta / ddelta per direction).
+    nbytes = K * B * D * L * (4 * es + 4) + 2 * Bs.numel() * (es + 4)
+    with torch.cuda.device(x.device), _lib.timed("ss2d_fused_bwd", nbytes):
+        _lib.check(_lib.lib.tramba_ss2d_fused_bwd_dx(
+            x.data_ptr(), dts.data_ptr(), Bs.data_ptr(), Cs.data_ptr(), A.data_ptr(), _ptr(Ds), _ptr(delta_bias),
+            sched.data_ptr(), sched.shape[1], kinds.ctypes.data, dy.data_ptr(), dx.data_ptr(), ddts.data_ptr(),
+            dBs.data_ptr(), dCs.data_ptr(), dA.data_ptr(), _ptr(dD), _ptr(db), order, K, B, D, H, W, 1, _DTYPE[dt],
+            int(softplus), _stream()))
+    part = part.sum(1)                                                        # one reduction over the batch
+    return (dx.to(dt).view(B, D, H, W), ddts, dBs.to(dt), dCs.to(dt), part[0], None if Ds is None else part[1],
+            None if delta_bias is None else part[2], None, None, None)
+
+
+SS2DCoreFused._backward_dx = staticmethod(_backward_dx)
 
 
 def ss2d_core_fused(x, dts, Bs, Cs, A, Ds, delta_bias, order, param=0, delta_softplus=True):
