@@ -183,6 +183,9 @@ TRAMBA_API int tramba_ss2d_fused_fwd(const void* x, const void* dts, const void*
  *   sched (K, sched_len) uint32, device: tramba_order_sched -- per direction a bank-conflict-free schedule of the
  *          shared-memory permutation image order <-> token order (entry = 2*pixel | 2*token << 16, 0xFFFFFFFF = none)
  *   kinds (K) int32, HOST: 0 identity, 1 reversed identity, 2 permutation, 3 table with repeated pixels
+ *   dA_part, dD_part, dbias_part: here (K*D) fp32 TOTALS over the batch (zeroed here, added with reds) -- not
+ *          per-batch partials as in tramba_ss2d_fused_bwd.  All zeroing uses one memset when dx, dBs, dCs, dA, dD,
+ *          dbias are carved contiguously (in that order) out of one allocation.
  * tramba_order_sched_len: entries per direction (0 = unsupported size). */
 TRAMBA_API size_t tramba_order_sched_len(int order, int H, int W, int param);
 TRAMBA_API int tramba_order_sched(int order, int H, int W, int param, uint32_t* sched_out /* K*len, host */,

@@ -1,5 +1,6 @@
 // extern "C" entry points of libtramba_b200.so (see include/tramba_b200.h).
 // Argument validation, plan selection and kernel launch; no torch, no allocation.
+#include <algorithm>
 #include <array>
 #include <atomic>
 #include <cstdio>
@@ -483,10 +484,26 @@ extern "C" int tramba_ss2d_fused_bwd_dx(const void* x, const void* dts, const vo
     rc = check_device();
     if (rc != TRAMBA_OK) return rc;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    // every fp32 output is an accumulation target: zero them, with as few memset nodes as the caller's layout
+    // allows (the Python host carves all six out of one workspace -> one memset)
     const size_t nbc = static_cast<size_t>(B) * K * g.L * sizeof(float);
-    cudaError_t e = cudaMemsetAsync(dBs, 0, nbc, st);
-    if (e == cudaSuccess) e = cudaMemsetAsync(dCs, 0, nbc, st);
-    if (e == cudaSuccess) e = cudaMemsetAsync(dx, 0, static_cast<size_t>(B) * D * g.L * sizeof(float), st);
+    const size_t nrow = static_cast<size_t>(K) * D * sizeof(float);
+    std::vector<std::pair<char*, size_t>> z = {{reinterpret_cast<char*>(dx), static_cast<size_t>(B) * D * g.L * sizeof(float)},
+                                               {reinterpret_cast<char*>(dBs), nbc},
+                                               {reinterpret_cast<char*>(dCs), nbc},
+                                               {reinterpret_cast<char*>(dA_part), nrow}};
+    if (dD_part) z.push_back({reinterpret_cast<char*>(dD_part), nrow});
+    if (dbias_part) z.push_back({reinterpret_cast<char*>(dbias_part), nrow});
+    std::sort(z.begin(), z.end());
+    cudaError_t e = cudaSuccess;
+    for (size_t i = 0; i < z.size() && e == cudaSuccess;) {
+        char* p0 = z[i].first;
+        size_t n = z[i].second;
+        size_t jn = i + 1;
+        while (jn < z.size() && z[jn].first == p0 + n) n += z[jn].second, ++jn;
+        e = cudaMemsetAsync(p0, 0, n, st);
+        i = jn;
+    }
     if (e != cudaSuccess) return cuda_rc(e);
     FusedDxArgs a;
     std::memset(&a, 0, sizeof(a));

@@ -76,7 +76,7 @@ struct FusedDxArgs {
     void* ddts;             // (B, K, D, L) in_t scan order
     float* dBs;             // (B, K, L) fp32, zeroed by the caller
     float* dCs;
-    float* dA;              // (B, K*D) partials
+    float* dA;              // (K*D) fp32, zeroed by the caller (red.global.add over the batch)
     float* dD;
     float* dbias;
     int B, K, D;

@@ -4,7 +4,7 @@
 // Models/SS2D/csms6s.py:45-55, 914-923, 25-31 (and the _Dilation / _Window / _Line variants) for N = 1 in ONE kernel:
 //     in : x, dy (B, D, L) IMAGE order; delta (B, K, D, L), B, C (B, K, L) scan order
 //     out: dx (B, D, L) fp32 IMAGE order (accumulated over the K directions with TMA bulk reductions at L2),
-//          ddelta (B, K, D, L) scan order, dB / dC (B, K, L), per-(b, row) partials of dA / dD / ddelta_bias.
+//          ddelta (B, K, D, L) scan order, dB / dC (B, K, L), dA / dD / ddelta_bias (K*D) (fp32 reds over b).
 // Neither xs, nor the K-fold copy of dy, nor du (the K-fold gradient w.r.t. xs) is ever written to HBM.
 //
 // Differences from the first-generation kernel (ss2d_fused_bwd.cu):
@@ -400,11 +400,10 @@ __global__ void __launch_bounds__(NT, 1) ss2d_bwd_dx_kernel(const FusedDxArgs p)
                 for (int w = 0; w < nwg; ++w) tA += sred[gw0 + w], tD += sred[NW + gw0 + w], tb += sred[2 * NW + gw0 + w];
                 sA = tA, sDs = tD, sb = tb;
             }
-            if (j == 0) {
-                const size_t o = static_cast<size_t>(b) * K * D + row;
-                p.dA[o] = sA;
-                if (p.dD) p.dD[o] = sDs;
-                if (p.dbias) p.dbias[o] = sb;
+            if (j == 0) {  // per-row sums over (b, t): B contributions per row, added at L2 (buffers zeroed by the host)
+                atomicAdd(p.dA + row, sA);
+                if (p.dD) atomicAdd(p.dD + row, sDs);
+                if (p.dbias) atomicAdd(p.dbias + row, sb);
             }
             if (PIPE && !perm) ld ^= 1;
         }

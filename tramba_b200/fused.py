@@ -173,12 +173,11 @@ def _backward_dx(ctx, dy):
     L = H * W
     dt = x.dtype
     sched, kinds = _sched(order, H, param, x.device)
-    dx = torch.empty((B, D, L), device=x.device, dtype=torch.float32)
+    # all fp32 accumulation targets from ONE workspace (-> one memset inside the entry point)
+    n_dx, n_bc, n_row = B * D * L, B * K * L, K * D
+    ws = torch.empty((n_dx + 2 * n_bc + 3 * n_row,), device=x.device, dtype=torch.float32)
+    dx, dBs, dCs, dA, dD, db = torch.split(ws, [n_dx, n_bc, n_bc, n_row, n_row, n_row])
     ddts = torch.empty((B, K, D, L), device=x.device, dtype=dt)
-    dBs = torch.empty((B, K, L), device=x.device, dtype=torch.float32)
-    dCs = torch.empty((B, K, L), device=x.device, dtype=torch.float32)
-    part = torch.zeros((3, B, K * D), device=x.device, dtype=torch.float32)   # dA | dD | dbias partials per b
-    dA, dD, db = part[0], (None if Ds is None else part[1]), (None if delta_bias is None else part[2])
     es = x.element_size()
     # SURVEY 8(d) operator formula per direction (read u, delta, dout; write du, ddelta; B/C in, dB/dC out): what the
     # kernel REPLACES.  bytes_min = what it must move itself (x, dy once; dx once; delta / ddelta per direction).
@@ -187,11 +186,11 @@ def _backward_dx(ctx, dy):
         _lib.check(_lib.lib.tramba_ss2d_fused_bwd_dx(
             x.data_ptr(), dts.data_ptr(), Bs.data_ptr(), Cs.data_ptr(), A.data_ptr(), _ptr(Ds), _ptr(delta_bias),
             sched.data_ptr(), sched.shape[1], kinds.ctypes.data, dy.data_ptr(), dx.data_ptr(), ddts.data_ptr(),
-            dBs.data_ptr(), dCs.data_ptr(), dA.data_ptr(), _ptr(dD), _ptr(db), order, K, B, D, H, W, 1, _DTYPE[dt],
+            dBs.data_ptr(), dCs.data_ptr(), dA.data_ptr(), None if Ds is None else dD.data_ptr(),
+            None if delta_bias is None else db.data_ptr(), order, K, B, D, H, W, 1, _DTYPE[dt],
             int(softplus), _stream()))
-    part = part.sum(1)                                                        # one reduction over the batch
-    return (dx.to(dt).view(B, D, H, W), ddts, dBs.to(dt), dCs.to(dt), part[0], None if Ds is None else part[1],
-            None if delta_bias is None else part[2], None, None, None)
+    return (dx.to(dt).view(B, D, H, W), ddts, dBs.view(B, K, L).to(dt), dCs.view(B, K, L).to(dt), dA,
+            None if Ds is None else dD, None if delta_bias is None else db, None, None, None)
 
 
 SS2DCoreFused._backward_dx = staticmethod(_backward_dx)
