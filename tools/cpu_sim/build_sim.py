@@ -36,6 +36,15 @@ def gen_header():
              "sim::cp_async(dst_smem, src, 8);")
     s = sub1(s, 'asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");',
              "sim::cp_async_arrive(bar);")
+    # explicit shared-window accessors -> plain host accesses at (base + byte offset)
+    s = sub1(s, 'asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(smem_u32(base) + off) : "memory");',
+             "v = *reinterpret_cast<const uint16_t*>(static_cast<const unsigned char*>(base) + off);")
+    s = sub1(s, 'asm volatile("st.shared.u16 [%0], %1;" ::"r"(smem_u32(base) + off), "h"(static_cast<uint16_t>(v)) : "memory");',
+             "*reinterpret_cast<uint16_t*>(static_cast<unsigned char*>(base) + off) = static_cast<uint16_t>(v);")
+    s = sub1(s, 'asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(smem_u32(base) + off) : "memory");',
+             "v = *reinterpret_cast<const float*>(static_cast<const unsigned char*>(base) + off);")
+    s = sub1(s, 'asm volatile("st.shared.f32 [%0], %1;" ::"r"(smem_u32(base) + off), "f"(v) : "memory");',
+             "*reinterpret_cast<float*>(static_cast<unsigned char*>(base) + off) = v;")
     assert "asm" not in s
     open(os.path.join(GEN, "ss2d_fused.cuh"), "w").write(s)
 

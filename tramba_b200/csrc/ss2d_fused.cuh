@@ -185,6 +185,26 @@ __device__ __forceinline__ void stage_plane_skewed_c(void* dst_plane, const void
     }
 }
 
+// ---- explicit shared-window accesses at (base pointer + byte offset): the address is formed in 32-bit shared space
+// once per base (no generic-address conversion inside the permutation loops); loads first, stores later = the
+// caller's instruction-level parallelism
+__device__ __forceinline__ uint32_t lds_u16(const void* base, uint32_t off) {
+    uint16_t v;
+    asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(smem_u32(base) + off) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts_u16(void* base, uint32_t off, uint32_t v) {
+    asm volatile("st.shared.u16 [%0], %1;" ::"r"(smem_u32(base) + off), "h"(static_cast<uint16_t>(v)) : "memory");
+}
+__device__ __forceinline__ float lds_f32(const void* base, uint32_t off) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(smem_u32(base) + off) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts_f32(void* base, uint32_t off, float v) {
+    asm volatile("st.shared.f32 [%0], %1;" ::"r"(smem_u32(base) + off), "f"(v) : "memory");
+}
+
 // Affine-map inclusive scan over `width` lanes (width = 32 or a power of two below).
 __device__ __forceinline__ void fused_scan(float& P, float& S, int sl, int width) {
 #pragma unroll
@@ -240,6 +260,21 @@ __device__ __forceinline__ void load_pair(const float* p, int i, float& lo, floa
 __device__ __forceinline__ void load_pair(const __nv_bfloat16* p, int i, float& lo, float& hi) {
     const uint32_t t = reinterpret_cast<const uint32_t*>(p)[i];
     lo = __uint_as_float(t << 16), hi = __uint_as_float(t & 0xffff0000u);
+}
+// The same chunk read / written BACKWARDS (token m <-> element CNT-1-m): a direction that walks the image in reverse.
+template <bool REV, typename T>
+__device__ __forceinline__ void chunk_pair(const T* p, int mp, float& lo, float& hi) {
+    if constexpr (!REV) {
+        load_pair(p, mp, lo, hi);
+    } else {
+        load_pair(p, kFusedS / 2 - 1 - mp, hi, lo);
+    }
+}
+template <int CNT>
+__device__ __forceinline__ void store_tokens_rev(float* p, const float (&v)[CNT]) {
+    float2* q = reinterpret_cast<float2*>(p);
+#pragma unroll
+    for (int i = 0; i < CNT / 2; ++i) q[i] = make_float2(v[CNT - 1 - 2 * i], v[CNT - 2 - 2 * i]);
 }
 template <int CNT>
 __device__ __forceinline__ void store_tokens(float* p, const float (&v)[CNT]) {

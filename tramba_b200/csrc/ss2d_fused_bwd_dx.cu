@@ -24,6 +24,8 @@
 // PIPE (16-bit operands): two (x, dy) plane sets used alternately and two delta buffers, so the TMA loads of round
 // s + 1 overlap round s.  !PIPE (fp32 operands, which need twice the staging): one set (+ the token-ordered set),
 // loads issued when the round's stores have been read.
+#include <type_traits>
+
 #include "ss2d_fused.cuh"
 
 namespace tramba {
@@ -149,7 +151,7 @@ __global__ void __launch_bounds__(NT, 1) ss2d_bwd_dx_kernel(const FusedDxArgs p)
         int b, k, d00;
         item_coord(it, b, k, d00);
         const int kind = (p.kinds >> (4 * k)) & 15;  // 0 identity, 1 reversed identity, 2 permutation, 3 with repeats
-        const bool perm = kind != 0;
+        const bool perm = kind >= 2;
         const bool dup = kind == 3;
         const uint2* __restrict__ sched = reinterpret_cast<const uint2*>(p.sched + static_cast<size_t>(k) * p.sched_len) + j;
         const int sched_iters = p.sched_len / (2 * TP);
@@ -160,7 +162,11 @@ __global__ void __launch_bounds__(NT, 1) ss2d_bwd_dx_kernel(const FusedDxArgs p)
         const in_t* Bq = sB + j * S;
         const in_t* Cq = sC + j * S;
 
-        for (int r = 0; r < R; ++r, ++s) {
+        // One round of the item.  REV (compile time): the direction walks the image backwards (token t = pixel
+        // L-1-t): the thread owning tokens [jS, (j+1)S) reads / writes image chunk TP-1-j back to front, no
+        // permutation pass.
+        auto round = [&](auto rev_tag, const int r) __attribute__((always_inline)) {
+            constexpr bool REV = decltype(rev_tag)::value;
             const bool has_next = s + 1 < nrounds;
             const int dbuf = PIPE ? (s & 1) : 0;
             if (PIPE && !perm && has_next && tid == 0) issue_xy(ld ^ 1, s + 1);
@@ -171,30 +177,60 @@ __global__ void __launch_bounds__(NT, 1) ss2d_bwd_dx_kernel(const FusedDxArgs p)
                 mbar_wait(&barXY[1], phXY1);
                 phXY1 ^= 1;
             }
-            int ds = ld;  // set the recurrence passes read (token order)
+            int ds = ld;  // set the recurrence passes read
             if (perm) {
-                // ---- image order -> token order, by the conflict-free schedule (entry: 2*pixel | 2*token << 16)
-                const unsigned char* xi = reinterpret_cast<const unsigned char*>(sX(ld) + static_cast<size_t>(q) * L);
-                const unsigned char* yi = reinterpret_cast<const unsigned char*>(sY(ld) + static_cast<size_t>(q) * L);
-                unsigned char* xt = reinterpret_cast<unsigned char*>(sX(ld ^ 1) + static_cast<size_t>(q) * L);
-                unsigned char* yt = reinterpret_cast<unsigned char*>(sY(ld ^ 1) + static_cast<size_t>(q) * L);
-                const uint2* sc = sched;
-#pragma unroll 3
-                for (int n = 0; n < sched_iters; ++n, sc += TP) {
-                    const uint2 e2 = __ldg(sc);
+                // ---- image order -> token order, by the conflict-free schedule (entry: 2*pixel | 2*token << 16).
+                // Batches of 6 moves: all loads, then all stores; the next batch's entries are fetched meanwhile.
+                const in_t* xi = sX(ld) + static_cast<size_t>(q) * L;
+                const float* yi = sY(ld) + static_cast<size_t>(q) * L;
+                in_t* xt = sX(ld ^ 1) + static_cast<size_t>(q) * L;
+                float* yt = sY(ld ^ 1) + static_cast<size_t>(q) * L;
+                auto move = [&](const uint2 (&e2)[3], int cnt) __attribute__((always_inline)) {
+                    uint32_t xv[6];
+                    float yv[6];
 #pragma unroll
-                    for (int c = 0; c < 2; ++c) {
-                        const uint32_t e = c ? e2.y : e2.x;
-                        if (e != 0xFFFFFFFFu) {
-                            const uint32_t src2 = e & 0xFFFFu, dst2 = e >> 16;
-                            if constexpr (ES == 2) {
-                                *reinterpret_cast<uint16_t*>(xt + dst2) = *reinterpret_cast<const uint16_t*>(xi + src2);
-                            } else {
-                                *reinterpret_cast<float*>(xt + 2 * dst2) = *reinterpret_cast<const float*>(xi + 2 * src2);
-                            }
-                            *reinterpret_cast<float*>(yt + 2 * dst2) = *reinterpret_cast<const float*>(yi + 2 * src2);
+                    for (int i = 0; i < 6; ++i) {
+                        const uint32_t e = (i & 1) ? e2[i >> 1].y : e2[i >> 1].x;
+                        const uint32_t src2 = (e == 0xFFFFFFFFu ? 0u : e) & 0xFFFFu;
+                        if ((i >> 1) < cnt) {
+                            if constexpr (ES == 2) xv[i] = lds_u16(xi, src2);
+                            else xv[i] = __float_as_uint(lds_f32(xi, 2 * src2));
+                            yv[i] = lds_f32(yi, 2 * src2);
                         }
                     }
+#pragma unroll
+                    for (int i = 0; i < 6; ++i) {
+                        const uint32_t e = (i & 1) ? e2[i >> 1].y : e2[i >> 1].x;
+                        const uint32_t dst2 = e >> 16;
+                        if ((i >> 1) < cnt && e != 0xFFFFFFFFu) {
+                            if constexpr (ES == 2) sts_u16(xt, dst2, xv[i]);
+                            else sts_f32(xt, 2 * dst2, __uint_as_float(xv[i]));
+                            sts_f32(yt, 2 * dst2, yv[i]);
+                        }
+                    }
+                };
+                const uint2* sc = sched;
+                int n = 0;
+                uint2 cur[3], nxt[3];
+                if (sched_iters >= 3) {
+#pragma unroll
+                    for (int u = 0; u < 3; ++u) cur[u] = __ldg(sc + u * TP);
+                }
+                for (; n + 3 <= sched_iters; n += 3) {
+                    sc += 3 * TP;
+                    if (n + 6 <= sched_iters) {
+#pragma unroll
+                        for (int u = 0; u < 3; ++u) nxt[u] = __ldg(sc + u * TP);
+                    }
+                    move(cur, 3);
+#pragma unroll
+                    for (int u = 0; u < 3; ++u) cur[u] = nxt[u];
+                }
+                if (n < sched_iters) {  // 1 or 2 left
+                    const int cnt = sched_iters - n;
+#pragma unroll
+                    for (int u = 0; u < 3; ++u) cur[u] = u < cnt ? __ldg(sc + u * TP) : make_uint2(0xFFFFFFFFu, 0xFFFFFFFFu);
+                    move(cur, cnt);
                 }
                 __syncthreads();  // token-ordered set complete; the image-ordered set is dead
                 if (PIPE && has_next && tid == 0) issue_xy(ld, s + 1);
@@ -214,12 +250,13 @@ __global__ void __launch_bounds__(NT, 1) ss2d_bwd_dx_kernel(const FusedDxArgs p)
                 mbar_wait(&barD[1], phD1);
                 phD1 ^= 1;
             }
-            const in_t* xq = sX(ds) + static_cast<size_t>(q) * L + j * S;  // token order: this thread's chunk
-            float* yq = sY(ds) + static_cast<size_t>(q) * L + j * S;
-            in_t* dq = sD(dbuf) + static_cast<size_t>(q) * L + j * S;
+            const int jc = REV ? TP - 1 - j : j;  // chunk of the plane that holds this thread's tokens
+            const in_t* xq = sX(ds) + static_cast<size_t>(q) * L + jc * S;
+            float* yq = sY(ds) + static_cast<size_t>(q) * L + jc * S;
+            in_t* dq = sD(dbuf) + static_cast<size_t>(q) * L + j * S;  // delta / ddelta: always token order
 
-            // ---- pass 1: forward fold (P, Sf) and reverse fold (P, Sr) of the segment
-            float sp[S];
+            // ---- pass 1: forward fold (P, Sf) and reverse fold (P, Sr) of the segment; g_t = C_t * dy_t stays in dh
+            float sp[S], dh[S];
             float P = 1.f, Sf = 0.f, Sr = 0.f;
             {
                 load_tokens<S>(dq, sp);
@@ -228,8 +265,8 @@ __global__ void __launch_bounds__(NT, 1) ss2d_bwd_dx_kernel(const FusedDxArgs p)
                     float Bv[2], Cv[2], uv[2], yv[2];
                     load_pair(Bq, mp, Bv[0], Bv[1]);
                     load_pair(Cq, mp, Cv[0], Cv[1]);
-                    load_pair(xq, mp, uv[0], uv[1]);
-                    load_pair(yq, mp, yv[0], yv[1]);
+                    chunk_pair<REV>(xq, mp, uv[0], uv[1]);
+                    chunk_pair<REV>(yq, mp, yv[0], yv[1]);
 #pragma unroll
                     for (int h2 = 0; h2 < 2; ++h2) {
                         const int m = 2 * mp + h2;
@@ -239,6 +276,7 @@ __global__ void __launch_bounds__(NT, 1) ss2d_bwd_dx_kernel(const FusedDxArgs p)
                         const float a = ex2f(sp[m] * A2);
                         const float bb = sp[m] * Bv[h2] * uv[h2];
                         const float g = Cv[h2] * yv[h2];
+                        dh[m] = g;
                         Sf = fmaf(a, Sf, bb);
                         P *= a;
                         Sr = fmaf(P, g, Sr);
@@ -286,22 +324,13 @@ __global__ void __launch_bounds__(NT, 1) ss2d_bwd_dx_kernel(const FusedDxArgs p)
                 Ein = fmaf(Pre, ep, Sre);
             }
             // ---- pass 2a: right-to-left, dh_t = g_t + E_{t+1}
-            float dh[S];
             {
                 float E = Ein;
 #pragma unroll
-                for (int mp = S / 2 - 1; mp >= 0; --mp) {
-                    float Cv[2], yv[2];
-                    load_pair(Cq, mp, Cv[0], Cv[1]);
-                    load_pair(yq, mp, yv[0], yv[1]);
-#pragma unroll
-                    for (int h2 = 1; h2 >= 0; --h2) {
-                        const int m = 2 * mp + h2;
-                        const float g = Cv[h2] * yv[h2];
-                        const float a = ex2f(sp[m] * A2);
-                        dh[m] = g + E;
-                        E = a * dh[m];
-                    }
+                for (int m = S - 1; m >= 0; --m) {
+                    const float a = ex2f(sp[m] * A2);
+                    dh[m] += E;
+                    E = a * dh[m];
                 }
             }
             // ---- pass 2b: left-to-right, h_t; du, ddelta; accumulate dB, dC, dA, dD, dbias
@@ -310,8 +339,8 @@ __global__ void __launch_bounds__(NT, 1) ss2d_bwd_dx_kernel(const FusedDxArgs p)
             for (int mp = 0; mp < S / 2; ++mp) {
                 float Bv[2], uv[2], yv[2];
                 load_pair(Bq, mp, Bv[0], Bv[1]);
-                load_pair(xq, mp, uv[0], uv[1]);
-                load_pair(yq, mp, yv[0], yv[1]);
+                chunk_pair<REV>(xq, mp, uv[0], uv[1]);
+                chunk_pair<REV>(yq, mp, yv[0], yv[1]);
 #pragma unroll
                 for (int h2 = 0; h2 < 2; ++h2) {
                     const int m = 2 * mp + h2;
@@ -344,9 +373,13 @@ __global__ void __launch_bounds__(NT, 1) ss2d_bwd_dx_kernel(const FusedDxArgs p)
                 }
             }
             store_tokens<S>(dq, sp);  // ddelta over delta, in place (this thread's own chunk)
-            // du: identity order -> straight into the image-ordered plane (!PIPE: over this thread's own dy chunk,
+            // du: contiguous orders -> straight into the image-ordered plane (!PIPE: over this thread's own dy chunk,
             // all of which has been read); otherwise token order over dy_tok, scattered below
-            store_tokens<S>((perm ? yq : dxp + static_cast<size_t>(q) * L + j * S), dh);
+            if constexpr (REV) {
+                store_tokens_rev<S>(dxp + static_cast<size_t>(q) * L + jc * S, dh);
+            } else {
+                store_tokens<S>((perm ? yq : dxp + static_cast<size_t>(q) * L + j * S), dh);
+            }
             // ---- per-row sums over L: warp reduce, then over the plane's warps
 #pragma unroll
             for (int off = 16; off > 0; off >>= 1) {
@@ -360,24 +393,55 @@ __global__ void __launch_bounds__(NT, 1) ss2d_bwd_dx_kernel(const FusedDxArgs p)
             if (perm) {
                 __syncthreads();  // du in token order complete (and the zero fill of a dup direction)
                 // ---- token order -> image order: inverse walk of the same schedule
-                const unsigned char* ut = reinterpret_cast<const unsigned char*>(sY(ds) + static_cast<size_t>(q) * L);
-                unsigned char* di = reinterpret_cast<unsigned char*>(dxp + static_cast<size_t>(q) * L);
-                const uint2* sc = sched;
-#pragma unroll 3
-                for (int n = 0; n < sched_iters; ++n, sc += TP) {
-                    const uint2 e2 = __ldg(sc);
+                const float* ut = sY(ds) + static_cast<size_t>(q) * L;
+                float* di = dxp + static_cast<size_t>(q) * L;
+                auto move = [&](const uint2 (&e2)[3], int cnt) __attribute__((always_inline)) {
+                    float v[6];
 #pragma unroll
-                    for (int c = 0; c < 2; ++c) {
-                        const uint32_t e = c ? e2.y : e2.x;
-                        if (e != 0xFFFFFFFFu) {
-                            const uint32_t src2 = e & 0xFFFFu, dst2 = e >> 16;
-                            const float v = *reinterpret_cast<const float*>(ut + 2 * dst2);
-                            if (dup) {
-                                atomicAdd(reinterpret_cast<float*>(di + 2 * src2), v);
-                            } else {
-                                *reinterpret_cast<float*>(di + 2 * src2) = v;
-                            }
+                    for (int i = 0; i < 6; ++i) {
+                        const uint32_t e = (i & 1) ? e2[i >> 1].y : e2[i >> 1].x;
+                        const uint32_t dst2 = (e == 0xFFFFFFFFu ? 0u : e) >> 16;
+                        if ((i >> 1) < cnt) v[i] = lds_f32(ut, 2 * dst2);
+                    }
+#pragma unroll
+                    for (int i = 0; i < 6; ++i) {
+                        const uint32_t e = (i & 1) ? e2[i >> 1].y : e2[i >> 1].x;
+                        const uint32_t src2 = e & 0xFFFFu;
+                        if ((i >> 1) < cnt && e != 0xFFFFFFFFu) sts_f32(di, 2 * src2, v[i]);
+                    }
+                };
+                const uint2* sc = sched;
+                if (dup) {
+                    // repeated pixels: one move at a time, added with shared-memory atomics (a CAS loop each; the
+                    // schedule still keeps the 32 lanes of a step on distinct banks)
+                    for (int n = 0; n < sched_iters; ++n, sc += TP) {
+                        const uint2 e2 = __ldg(sc);
+                        if (e2.x != 0xFFFFFFFFu) atomicAdd(di + ((e2.x & 0xFFFFu) >> 1), ut[e2.x >> 17]);
+                        if (e2.y != 0xFFFFFFFFu) atomicAdd(di + ((e2.y & 0xFFFFu) >> 1), ut[e2.y >> 17]);
+                    }
+                } else {
+                    int n = 0;
+                    uint2 cur[3], nxt[3];
+                    if (sched_iters >= 3) {
+#pragma unroll
+                        for (int u = 0; u < 3; ++u) cur[u] = __ldg(sc + u * TP);
+                    }
+                    for (; n + 3 <= sched_iters; n += 3) {
+                        sc += 3 * TP;
+                        if (n + 6 <= sched_iters) {
+#pragma unroll
+                            for (int u = 0; u < 3; ++u) nxt[u] = __ldg(sc + u * TP);
                         }
+                        move(cur, 3);
+#pragma unroll
+                        for (int u = 0; u < 3; ++u) cur[u] = nxt[u];
+                    }
+                    if (n < sched_iters) {
+                        const int cnt = sched_iters - n;
+#pragma unroll
+                        for (int u = 0; u < 3; ++u)
+                            cur[u] = u < cnt ? __ldg(sc + u * TP) : make_uint2(0xFFFFFFFFu, 0xFFFFFFFFu);
+                        move(cur, cnt);
                     }
                 }
             }
@@ -406,6 +470,11 @@ __global__ void __launch_bounds__(NT, 1) ss2d_bwd_dx_kernel(const FusedDxArgs p)
                 if (p.dbias) atomicAdd(p.dbias + row, sb);
             }
             if (PIPE && !perm) ld ^= 1;
+            ++s;
+        };
+        for (int r = 0; r < R; ++r) {
+            if (kind == 1) round(std::true_type{}, r);
+            else round(std::false_type{}, r);
         }
         // ---- item flush: dB / dC of the item's channels (token order, registers) -> global reds
         {
@@ -449,11 +518,23 @@ __global__ void __launch_bounds__(NT, 1) ss2d_bwd_dx_kernel(const FusedDxArgs p)
     if (tid == 0) bulk_wait_all<0>();
 }
 
-// Channels per item: enough rounds that the per-item dB/dC flush is amortised (>= 8 channels).
-int pick_rounds(int D, int PP) {
-    int R = 1;
-    while (R * PP < 8 && D % (2 * R * PP) == 0) R *= 2;
-    return R;
+// Rounds (channel groups) per item.  More rounds amortise the per-item dB / dC flush (>= 8 channels is the target);
+// fewer rounds make more, smaller items, which matters when the item count is a small non-multiple of the SM count
+// (512 items on 148 persistent CTAs leave a 14 % tail).  Largest R <= target whose last wave is >= 92 % full, else
+// the best-filled one.
+int pick_rounds(int B, int K, int D, int PP, int sms) {
+    int best = 1;
+    double best_eff = -1.0;
+    for (int R = 8; R >= 1; R >>= 1) {
+        if (R * PP > 8 && R > 1) continue;
+        if (D % (R * PP) != 0) continue;
+        const long long items = static_cast<long long>(B) * K * (D / (R * PP));
+        const long long waves = (items + sms - 1) / sms;
+        const double eff = static_cast<double>(items) / static_cast<double>(waves * sms);
+        if (eff >= 0.92) return R;
+        if (eff > best_eff) best_eff = eff, best = R;
+    }
+    return best;
 }
 
 template <typename in_t, bool SOFTPLUS, int TP>
@@ -466,7 +547,7 @@ cudaError_t launch_tp(const FusedDxArgs& a, cudaStream_t st) {
     const int sms = device_sms();
     FusedDxArgs b = a;
     constexpr int PP = NT / TP;
-    b.R = pick_rounds(a.D, PP);
+    b.R = pick_rounds(a.B, a.K, a.D, PP, sms);
     const int items = a.B * a.K * (a.D / (b.R * PP));
     const int grid = items < sms ? items : sms;
     kern<<<grid, NT, Lay::total, st>>>(b);
