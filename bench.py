@@ -50,6 +50,8 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="do not capture the step in a CUDA graph")
     ap.add_argument("--unfused", action="store_true", help="op-by-op SS2D path instead of the fused core")
+    ap.add_argument("--no-shadow", action="store_true", help="plain autocast (weights cast on every use) instead of "
+                    "bf16 shadow weights refreshed after the optimizer step")
     ap.add_argument("--cpu-budget-s", type=float, default=240.0, help="wall budget of the reference arm")
     ap.add_argument("--kernel-table", default="", help="write a per-kernel device-time table of 3 graph-replayed "
                     "steps (torch.profiler / CUPTI; not part of the timed regions) to this file")
@@ -297,15 +299,17 @@ def run_ours(args):
     # Data parallel over images (the path shards by image): replicas start identical
     # (broadcast from rank 0) and every gradient lives in ONE flat fp32 buffer that is all-reduced
     # (NCCL, AVG) once per step between backward and the Adam step -- 446 MB over NVLink/NVSwitch.
-    from tramba_b200.dp import FlatGradients
+    from tramba_b200.dp import FlatGradients, ShadowParams
     params = [p for p in model.parameters()]
-    fg = FlatGradients(params)
+    amp = torch.bfloat16 if args.dtype == "bf16" else None
+    # bf16 shadow copies of the conv / linear / projection weights (what autocast would cast on every use)
+    shadow = ShadowParams(model, amp) if (amp is not None and not args.no_shadow) else None
+    fg = FlatGradients(params, [shadow.source_of(p) for p in params] if shadow else None)
     if world > 1:
         for p in params:
             dist.broadcast(p.data, 0)
     net = model
     B = args.batch
-    amp = torch.bfloat16 if args.dtype == "bf16" else None
     g = torch.Generator().manual_seed(rank)
     h_img = torch.randn(B, 3, IMG, IMG, generator=g).pin_memory()
     h_lab = (torch.rand(B, 1, IMG, IMG, generator=g) > 0.5).float().pin_memory()
@@ -316,7 +320,7 @@ def run_ours(args):
         # then packed into the flat buffer with one multi-tensor copy and the optimizer sees the flat views
         fg.begin()
         with torch.autocast("cuda", dtype=amp, enabled=amp is not None):
-            outs = net(img)
+            outs = torch.func.functional_call(net, shadow.mapping(), (img,)) if shadow else net(img)
         loss = tsod_loss(outs, lab)
         loss.backward()
         fg.pack()
@@ -325,10 +329,15 @@ def run_ours(args):
     def reduce_grads():
         fg.all_reduce(world)
 
+    def opt_step():
+        opt.step()
+        if shadow:
+            shadow.refresh()            # one multi-tensor copy: the bf16 weights of the next forward
+
     def step(img, lab):
         loss = fwd_bwd(img, lab)
         reduce_grads()
-        opt.step()
+        opt_step()
         return loss
 
     def sync():
@@ -365,7 +374,7 @@ def run_ours(args):
                 s_loss = fwd_bwd(s_img, s_lab)
             g_opt = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g_opt, pool=g_fb.pool()):
-                opt.step()
+                opt_step()
             for _ in range(2):
                 g_fb.replay(), reduce_grads(), g_opt.replay()
             sync()
@@ -509,6 +518,7 @@ def run_ours(args):
             "config": {"workload": "Tramba-V-TSOD training step 384x384, batch 4 per GPU (BASELINE config 3)",
                        "img_size": IMG, "global_batch": world * B, "parallelism": f"dp{world}",
                        "weights": "random-init, 111.44 M params", "optimizer": "Adam (fused); flat-buffer NCCL all-reduce (AVG) of all gradients per step",
+                       "weight_precision": "fp32 masters + bf16 shadows refreshed after Adam" if shadow else "fp32, autocast casts per use",
                        "ss2d_path": "op-by-op kernels" if args.unfused else "fused core kernels",
                        "step_launch": "CUDA graphs (fwd+bwd graph, all-reduce, Adam graph)" if graph is not None else "eager",
                        "l2": "no explicit flush: a step streams several GB of activations (>> 126 MB L2)"},

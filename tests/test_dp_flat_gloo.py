@@ -85,3 +85,46 @@ def test_flat_gradients_unused_parameter_is_zeroed():
     fg.pack()
     assert torch.equal(a.grad, torch.full((3,), 2.0)) and torch.equal(b.grad, torch.zeros(2))
     assert torch.equal(fg.flat, torch.tensor([2.0, 2.0, 2.0, 0.0, 0.0]))
+
+
+def test_shadow_params_reproduce_autocast_gradients_and_updates():
+    """ShadowParams + FlatGradients (what bench.py's bf16 step uses) against plain autocast on the same model: the bf16
+    shadows are the values autocast would cast to, so outputs, gradients (after widening into the flat fp32 buffer)
+    and the weights after two Adam steps are IDENTICAL bit for bit; parameters consumed in fp32 keep no shadow."""
+    sys.path.insert(0, os.path.dirname(HERE))
+    from tramba_b200.dp import FlatGradients, ShadowParams
+
+    def make():
+        torch.manual_seed(0)
+        return torch.nn.Sequential(torch.nn.Conv2d(3, 8, 3, padding=1), torch.nn.GroupNorm(2, 8), torch.nn.GELU(),
+                                   torch.nn.Conv2d(8, 8, 3, padding=1, groups=8),      # depthwise: stays fp32-owned
+                                   torch.nn.Conv2d(8, 4, 1), torch.nn.Flatten(), torch.nn.Linear(4 * 8 * 8, 5))
+    x = torch.randn(2, 3, 8, 8, generator=torch.Generator().manual_seed(3))
+    ref, new = make(), make()
+    opt_r = torch.optim.Adam(ref.parameters(), lr=1e-2)
+    params = list(new.parameters())
+    shadow = ShadowParams(new, torch.bfloat16)
+    assert len(shadow.shadows) == 6                                   # conv0 w,b; conv 1x1 w,b; linear w,b
+    assert all(s.dtype == torch.bfloat16 for s in shadow.shadows)
+    assert shadow.source_of(new[3].weight) is new[3].weight           # depthwise conv: no shadow
+    fg = FlatGradients(params, [shadow.source_of(p) for p in params])
+    opt_n = torch.optim.Adam(params, lr=1e-2)
+    for _ in range(2):
+        opt_r.zero_grad(set_to_none=True)
+        with torch.autocast("cpu", dtype=torch.bfloat16):
+            yr = ref(x)
+        yr.float().square().mean().backward()
+        opt_r.step()
+        fg.begin()
+        with torch.autocast("cpu", dtype=torch.bfloat16):
+            yn = torch.func.functional_call(new, shadow.mapping(), (x,))
+        yn.float().square().mean().backward()
+        fg.pack()
+        assert torch.equal(yr, yn)
+        assert all(p.grad.dtype == torch.float32 and p.grad.data_ptr() == v.data_ptr() for p, v in zip(params, fg.views))
+        opt_n.step()
+        shadow.refresh()
+    for a, b in zip(ref.parameters(), new.parameters()):
+        assert torch.equal(a, b)
+    for m, s in zip(shadow.masters, shadow.shadows):
+        assert torch.equal(m.detach().to(torch.bfloat16), s.detach())

@@ -628,6 +628,8 @@ inline void bulk_wait_all() {
     sim::drain_stores(N);
 }
 
+inline void red_add_v4(float* p, float a, float b, float c, float d) { sim::red_add_v4(p, a, b, c, d); }
+
 // ---- math (libm instead of the .approx MUFU ops: differences are far below the parity tolerance)
 inline float ex2f(float x) { return exp2f(x); }
 inline float lg2f(float x) { return log2f(x); }

@@ -113,6 +113,11 @@ __device__ __forceinline__ void bulk_wait_all() {
     asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory");
 }
 
+// 16-byte vector reduction (fp32 adds performed at L2, no return value); p 16-byte aligned
+__device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
 // ------------------------------------------------------------------ math
 __device__ __forceinline__ float ex2f(float x) {
     float y;

@@ -290,6 +290,237 @@ __global__ void __launch_bounds__(kThreads, 1) dct2d_bwd_tc_kernel(const float* 
     }
 }
 
+// ------------------------------------------------------------------------------------ large planes
+// Planes whose bases do not fit next to them in one SM's shared memory (H = W = 192 of the 768^2 stress
+// configuration; supported: H = W in {64, 128, 192}).  Same contraction,
+// same 3xTF32 tensor-core arithmetic, but every operand is STREAMED through double-buffered cp.async k-chunks
+// (KC = 32) and the intermediate of one work item stays in shared memory:
+//   forward  item = (plane, half q):  T_q = Wy[q*Hh:(q+1)*Hh, :] . X      (Hh x W, shared memory)
+//                                     out_q = T_q . Wx[q*Wh:(q+1)*Wh, :]^T (Hh x Wh: low for q = 0, high for q = 1)
+//   adjoint  item = (plane, column half c):  S = [G_0 . Wx[:Wh, cols] ; G_1 . Wx[Wh:, cols]]   (H x W/2, shared)
+//                                            gx[:, cols] = Wy^T . S
+// 12 warps; stage-1 warps own a 16-row x (N/2)-column block, stage-2 warps a 16-row block of the output.
+constexpr int kKC = 32;
+
+// A operand k-major: element (m, k) at A[k * ldk + m], ldk = 8 mod 32 (conflict-free fragment loads)
+template <int NT>
+__device__ __forceinline__ void warp_gemm_akm(float (&acc)[NT][4], const float* __restrict__ A, int ldk,
+                                              const float* __restrict__ B, int ldb_k, int ldb_n, int K, int lane) {
+    const int g = lane >> 2, t = lane & 3;
+    for (int k0 = 0; k0 < K; k0 += 8) {
+        uint32_t ah[4], al[4];
+        split_tf32(A[(k0 + t) * ldk + g], ah[0], al[0]);
+        split_tf32(A[(k0 + t) * ldk + g + 8], ah[1], al[1]);
+        split_tf32(A[(k0 + t + 4) * ldk + g], ah[2], al[2]);
+        split_tf32(A[(k0 + t + 4) * ldk + g + 8], ah[3], al[3]);
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) {
+            uint32_t bh[2], bl[2];
+            const float* bp = B + (k0 + t) * ldb_k + (nt * 8 + g) * ldb_n;
+            split_tf32(bp[0], bh[0], bl[0]);
+            split_tf32(bp[4 * ldb_k], bh[1], bl[1]);
+            mma_tf32(acc[nt], al, bh);
+            mma_tf32(acc[nt], ah, bl);
+            mma_tf32(acc[nt], ah, bh);
+        }
+    }
+}
+
+struct BigGeom {
+    int H, W, Hh, Wh;
+    int lda;   // [rows][kKC + 4]: row-major A chunks / n-major B chunks (4 mod 32)
+    int ldb;   // forward stage A: X chunk rows [kKC][W + 8]; adjoint stage 1: Wx chunk rows [kKC][Wh + 8] (8 mod 32)
+    int ldt;   // forward: T [Hh][W + 4] (4 mod 32);  adjoint: S [H][Wh + 8] (8 mod 32)
+    int ldw;   // adjoint stage 2: Wy chunk rows [kKC][H + 8] (k-major A, 8 mod 32)
+};
+
+// rows x cols floats (cols % 4 == 0) global (row stride gs) -> shared (row stride ss), 16-byte cp.async
+__device__ __forceinline__ void stage_tile(float* dst, int ss, const float* src, int gs, int rows, int cols, int tid) {
+    const int cpr = cols >> 2;
+    for (int e = tid; e < rows * cpr; e += kThreads) {
+        const int r = e / cpr, c = e - r * cpr;
+        cp_async16(dst + r * ss + c * 4, src + static_cast<size_t>(r) * gs + c * 4);
+    }
+}
+
+template <int NTA, int NTB>  // NTA = W / 16, NTB = Wh / 16 (n-tiles of 8 per warp in stage A / B)
+__global__ void __launch_bounds__(kThreads, 1) dct2d_fwd_big_kernel(const float* __restrict__ x,
+                                                                    const float* __restrict__ wy,
+                                                                    const float* __restrict__ wx,
+                                                                    float* __restrict__ high, float* __restrict__ low,
+                                                                    int planes, BigGeom gm) {
+    extern __shared__ __align__(16) float sm[];
+    const int H = gm.H, W = gm.W, Hh = gm.Hh, Wh = gm.Wh;
+    float* As = sm;                          // [2][Hh][lda]   Wy / Wx row chunks
+    float* Bs = As + 2 * Hh * gm.lda;        // [2][kKC][ldb]  X row chunks
+    float* Ts = Bs + 2 * kKC * gm.ldb;       // [Hh][ldt]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g = lane >> 2, t = lane & 3;
+    const int mtiles = Hh / 16;              // <= 6
+    const int mt = warp >> 1, nh = warp & 1; // stage tiles: 16 rows x half of the columns
+    const bool active = mt < mtiles;
+    const int items = planes * 2;
+    const int nk = H / kKC;                  // k-chunks of stage A (over h) and of stage B (over w; W == H)
+    for (int item = blockIdx.x; item < items; item += gridDim.x) {
+        const int pl = item >> 1, q = item & 1;
+        const float* X = x + static_cast<size_t>(pl) * H * W;
+        const float* Wyq = wy + static_cast<size_t>(q) * Hh * H;   // rows q*Hh .. of Wy (H columns)
+        const float* Wxq = wx + static_cast<size_t>(q) * Wh * W;   // rows q*Wh .. of Wx (W columns)
+        auto issueA = [&](int kc, int buf) {
+            stage_tile(As + buf * Hh * gm.lda, gm.lda, Wyq + kc * kKC, H, Hh, kKC, tid);
+            stage_tile(Bs + buf * kKC * gm.ldb, gm.ldb, X + static_cast<size_t>(kc) * kKC * W, W, kKC, W, tid);
+            cp_async_commit();
+        };
+        auto issueB = [&](int kc, int buf) {
+            stage_tile(As + buf * Hh * gm.lda, gm.lda, Wxq + kc * kKC, W, Wh, kKC, tid);
+            cp_async_commit();
+        };
+        // ---- stage A: T = Wy_q . X
+        float acc[NTA][4];
+#pragma unroll
+        for (int i = 0; i < NTA; ++i) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f;
+        issueA(0, 0);
+        for (int kc = 0; kc < nk; ++kc) {
+            const int buf = kc & 1;
+            if (kc + 1 < nk) issueA(kc + 1, buf ^ 1);
+            if (kc + 1 < nk) cp_async_wait<1>(); else cp_async_wait<0>();
+            __syncthreads();
+            if (active)
+                warp_gemm<NTA>(acc, As + buf * Hh * gm.lda + mt * 16 * gm.lda, gm.lda,
+                               Bs + buf * kKC * gm.ldb + nh * NTA * 8, gm.ldb, 1, kKC, lane);
+            __syncthreads();
+        }
+        issueB(0, 0);  // the first Wx chunk travels while T is written
+        if (active) {
+            float* Tp = Ts + mt * 16 * gm.ldt + nh * NTA * 8;
+#pragma unroll
+            for (int nt = 0; nt < NTA; ++nt) {
+                *reinterpret_cast<float2*>(Tp + g * gm.ldt + nt * 8 + 2 * t) = make_float2(acc[nt][0], acc[nt][1]);
+                *reinterpret_cast<float2*>(Tp + (g + 8) * gm.ldt + nt * 8 + 2 * t) = make_float2(acc[nt][2], acc[nt][3]);
+            }
+        }
+        // ---- stage B: out_q = T . Wx_q^T   (B[k = w][n = v] = Wx_q[v][w]: n-major chunk rows)
+        float acc2[NTB][4];
+#pragma unroll
+        for (int i = 0; i < NTB; ++i) acc2[i][0] = acc2[i][1] = acc2[i][2] = acc2[i][3] = 0.f;
+        for (int kc = 0; kc < nk; ++kc) {
+            const int buf = kc & 1;
+            if (kc + 1 < nk) issueB(kc + 1, buf ^ 1);
+            if (kc + 1 < nk) cp_async_wait<1>(); else cp_async_wait<0>();
+            __syncthreads();  // (first pass: also publishes T)
+            if (active)
+                warp_gemm<NTB>(acc2, Ts + mt * 16 * gm.ldt + kc * kKC, gm.ldt,
+                               As + buf * Hh * gm.lda + (nh * NTB * 8) * gm.lda, 1, gm.lda, kKC, lane);
+            __syncthreads();
+        }
+        if (active) {
+            float* out = (q ? high : low) + static_cast<size_t>(pl) * Hh * Wh + (mt * 16) * Wh + nh * NTB * 8;
+#pragma unroll
+            for (int nt = 0; nt < NTB; ++nt) {
+                *reinterpret_cast<float2*>(out + g * Wh + nt * 8 + 2 * t) = make_float2(acc2[nt][0], acc2[nt][1]);
+                *reinterpret_cast<float2*>(out + (g + 8) * Wh + nt * 8 + 2 * t) = make_float2(acc2[nt][2], acc2[nt][3]);
+            }
+        }
+    }
+}
+
+template <int NT1, int NT2>  // NT1 = Wh / 16 (stage 1: half of the item's Wh columns per warp), NT2 = Wh / 8 (stage 2)
+__global__ void __launch_bounds__(kThreads, 1) dct2d_bwd_big_kernel(const float* __restrict__ ghigh,
+                                                                    const float* __restrict__ glow,
+                                                                    const float* __restrict__ wy,
+                                                                    const float* __restrict__ wx, float* __restrict__ gx,
+                                                                    int planes, BigGeom gm) {
+    extern __shared__ __align__(16) float sm[];
+    const int H = gm.H, W = gm.W, Hh = gm.Hh, Wh = gm.Wh;
+    float* As = sm;                          // [2][Hh][lda]   G_q column chunks (row-major A)
+    float* Bs = As + 2 * Hh * gm.lda;        // [2][kKC][ldb]  Wx row chunks restricted to the item's columns
+    float* Ws = Bs + 2 * kKC * gm.ldb;       // [2][kKC][ldw]  Wy row chunks (k-major A of stage 2)
+    float* Ss = Ws + 2 * kKC * gm.ldw;       // [H][ldt]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g = lane >> 2, t = lane & 3;
+    const int mtiles1 = Hh / 16;             // <= 6
+    const int mt1 = warp >> 1, nh1 = warp & 1;
+    const bool active1 = mt1 < mtiles1;
+    const int mtiles2 = H / 16;              // <= 12
+    const bool active2 = warp < mtiles2;
+    const int items = planes * 2;
+    const int nk1 = Wh / kKC;                // per quadrant (over v)
+    const int nk2 = H / kKC;                 // over u
+    for (int item = blockIdx.x; item < items; item += gridDim.x) {
+        const int pl = item >> 1, c = item & 1;  // c: column half [c*Wh, (c+1)*Wh) of gx / S
+        auto issue1 = [&](int step, int buf) {   // step = q * nk1 + kc
+            const int q = step / nk1, kc = step - q * nk1;
+            const float* G = (q ? ghigh : glow) + static_cast<size_t>(pl) * Hh * Wh;
+            stage_tile(As + buf * Hh * gm.lda, gm.lda, G + kc * kKC, Wh, Hh, kKC, tid);
+            stage_tile(Bs + buf * kKC * gm.ldb, gm.ldb,
+                       wx + (static_cast<size_t>(q) * Wh + kc * kKC) * W + c * Wh, W, kKC, Wh, tid);
+            cp_async_commit();
+        };
+        auto issue2 = [&](int kc, int buf) {
+            stage_tile(Ws + buf * kKC * gm.ldw, gm.ldw, wy + static_cast<size_t>(kc) * kKC * H, H, kKC, H, tid);
+            cp_async_commit();
+        };
+        // ---- stage 1: S[q*Hh + u][w] = sum_v G_q[u][v] Wx[q*Wh + v][c*Wh + w]
+        issue1(0, 0);
+        for (int q = 0; q < 2; ++q) {
+            float acc[NT1][4];
+#pragma unroll
+            for (int i = 0; i < NT1; ++i) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f;
+            for (int kc = 0; kc < nk1; ++kc) {
+                const int step = q * nk1 + kc, buf = step & 1;
+                if (step + 1 < 2 * nk1) issue1(step + 1, buf ^ 1);
+                if (step + 1 < 2 * nk1) cp_async_wait<1>(); else cp_async_wait<0>();
+                __syncthreads();
+                if (active1)
+                    warp_gemm<NT1>(acc, As + buf * Hh * gm.lda + mt1 * 16 * gm.lda, gm.lda,
+                                   Bs + buf * kKC * gm.ldb + nh1 * NT1 * 8, gm.ldb, 1, kKC, lane);
+                __syncthreads();
+            }
+            if (q == 1) issue2(0, 0);  // the first Wy chunk travels while S is completed
+            if (active1) {
+                float* Sp = Ss + (q * Hh + mt1 * 16) * gm.ldt + nh1 * NT1 * 8;
+#pragma unroll
+                for (int nt = 0; nt < NT1; ++nt) {
+                    *reinterpret_cast<float2*>(Sp + g * gm.ldt + nt * 8 + 2 * t) = make_float2(acc[nt][0], acc[nt][1]);
+                    *reinterpret_cast<float2*>(Sp + (g + 8) * gm.ldt + nt * 8 + 2 * t) = make_float2(acc[nt][2], acc[nt][3]);
+                }
+            }
+        }
+        // ---- stage 2: gx[h][c*Wh + w] = sum_u Wy[u][h] S[u][w]   (A k-major: chunk rows u, columns h)
+        float acc2[NT2][4];
+#pragma unroll
+        for (int i = 0; i < NT2; ++i) acc2[i][0] = acc2[i][1] = acc2[i][2] = acc2[i][3] = 0.f;
+        for (int kc = 0; kc < nk2; ++kc) {
+            const int buf = kc & 1;
+            if (kc + 1 < nk2) issue2(kc + 1, buf ^ 1);
+            if (kc + 1 < nk2) cp_async_wait<1>(); else cp_async_wait<0>();
+            __syncthreads();  // (first pass: also publishes S)
+            if (active2)
+                warp_gemm_akm<NT2>(acc2, Ws + buf * kKC * gm.ldw + warp * 16, gm.ldw, Ss + kc * kKC * gm.ldt, gm.ldt, 1,
+                                   kKC, lane);
+            __syncthreads();
+        }
+        if (active2) {
+            float* out = gx + static_cast<size_t>(pl) * H * W + (warp * 16) * W + c * Wh;
+#pragma unroll
+            for (int nt = 0; nt < NT2; ++nt) {
+                *reinterpret_cast<float2*>(out + g * W + nt * 8 + 2 * t) = make_float2(acc2[nt][0], acc2[nt][1]);
+                *reinterpret_cast<float2*>(out + (g + 8) * W + nt * 8 + 2 * t) = make_float2(acc2[nt][2], acc2[nt][3]);
+            }
+        }
+    }
+}
+
+bool big_supported(int H, int W) {
+    return H == W && H % 64 == 0 && H <= 192;  // H/2 a multiple of the k-chunk (32) and of the m-tile (16)
+}
+BigGeom big_geom(int H, int W) {
+    BigGeom g;
+    g.H = H, g.W = W, g.Hh = H / 2, g.Wh = W / 2;
+    g.lda = kKC + 4;
+    return g;
+}
+
 struct Plan {
     DctGeom gm;
     size_t smem_fwd, smem_bwd;
@@ -334,12 +565,51 @@ Plan make_plan(int H, int W) {
 
 }  // namespace
 
-bool dct2d_tc_supported(int H, int W) { return make_plan(H, W).ok; }
+bool dct2d_tc_supported(int H, int W) { return make_plan(H, W).ok || big_supported(H, W); }
+
+template <int NTA, int NTB>
+static cudaError_t launch_fwd_big(const float* x, const float* wy, const float* wx, float* high, float* low, int planes,
+                                  int H, int W, cudaStream_t st) {
+    BigGeom g = big_geom(H, W);
+    g.ldb = pad_to(W, 8), g.ldt = pad_to(W, 4), g.ldw = 0;
+    const size_t smem = (2ull * g.Hh * g.lda + 2ull * kKC * g.ldb + static_cast<size_t>(g.Hh) * g.ldt) * 4;
+    auto kern = dct2d_fwd_big_kernel<NTA, NTB>;
+    if (cudaError_t e = ensure_dyn_smem(kern, 220 * 1024); e != cudaSuccess) return e;
+    if (smem > 220 * 1024) return cudaErrorInvalidConfiguration;
+    const int items = planes * 2, sms = device_sms();
+    kern<<<items < sms ? items : sms, kThreads, smem, st>>>(x, wy, wx, high, low, planes, g);
+    return cudaGetLastError();
+}
+template <int NT1, int NT2>
+static cudaError_t launch_bwd_big(const float* ghigh, const float* glow, const float* wy, const float* wx, float* gx,
+                                  int planes, int H, int W, cudaStream_t st) {
+    BigGeom g = big_geom(H, W);
+    g.ldb = pad_to(g.Wh, 8), g.ldt = pad_to(g.Wh, 8), g.ldw = pad_to(H, 8);
+    const size_t smem = (2ull * g.Hh * g.lda + 2ull * kKC * g.ldb + 2ull * kKC * g.ldw + static_cast<size_t>(H) * g.ldt) * 4;
+    auto kern = dct2d_bwd_big_kernel<NT1, NT2>;
+    if (cudaError_t e = ensure_dyn_smem(kern, 220 * 1024); e != cudaSuccess) return e;
+    if (smem > 220 * 1024) return cudaErrorInvalidConfiguration;
+    const int items = planes * 2, sms = device_sms();
+    kern<<<items < sms ? items : sms, kThreads, smem, st>>>(ghigh, glow, wy, wx, gx, planes, g);
+    return cudaGetLastError();
+}
+
 
 cudaError_t launch_dct2d_fwd_tc(const float* x, const float* wy, const float* wx, float* high, float* low, int planes,
                                 int H, int W, cudaStream_t st) {
     Plan p = make_plan(H, W);
-    if (!p.ok) return cudaErrorInvalidConfiguration;
+    if (!p.ok) {  // bases + planes exceed one SM's shared memory: the streamed kernel
+        if (!big_supported(H, W)) return cudaErrorInvalidConfiguration;
+        cudaError_t e = cudaErrorInvalidConfiguration;
+        switch (W) {
+            case 192: e = launch_fwd_big<12, 6>(x, wy, wx, high, low, planes, H, W, st); break;
+            case 128: e = launch_fwd_big<8, 4>(x, wy, wx, high, low, planes, H, W, st); break;
+            case 64: e = launch_fwd_big<4, 2>(x, wy, wx, high, low, planes, H, W, st); break;
+            default: break;
+        }
+        note_launch();
+        return e;
+    }
     const int sms = device_sms();
     const int groups = (planes + p.gm.ppl - 1) / p.gm.ppl;
     const int grid = groups < sms ? groups : sms;
@@ -362,7 +632,18 @@ cudaError_t launch_dct2d_fwd_tc(const float* x, const float* wy, const float* wx
 cudaError_t launch_dct2d_bwd_tc(const float* ghigh, const float* glow, const float* wy, const float* wx, float* gx,
                                 int planes, int H, int W, cudaStream_t st) {
     Plan p = make_plan(H, W);
-    if (!p.ok) return cudaErrorInvalidConfiguration;
+    if (!p.ok) {
+        if (!big_supported(H, W)) return cudaErrorInvalidConfiguration;
+        cudaError_t e = cudaErrorInvalidConfiguration;
+        switch (W) {
+            case 192: e = launch_bwd_big<6, 12>(ghigh, glow, wy, wx, gx, planes, H, W, st); break;
+            case 128: e = launch_bwd_big<4, 8>(ghigh, glow, wy, wx, gx, planes, H, W, st); break;
+            case 64: e = launch_bwd_big<2, 4>(ghigh, glow, wy, wx, gx, planes, H, W, st); break;
+            default: break;
+        }
+        note_launch();
+        return e;
+    }
     const int sms = device_sms();
     DctGeom gm = p.gm;
     gm.ldt = pad_to(W, 8);

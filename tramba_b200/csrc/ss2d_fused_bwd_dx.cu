@@ -55,6 +55,31 @@ struct DxLayout {
     static constexpr size_t total = bar + 8 * sizeof(uint64_t);
 };
 
+// Walks this thread's entries of a permutation schedule (uint2 = two moves; stride TP between a thread's entries) in
+// batches of three loads, the next batch in flight while `move(dense, e0, e1, e2, count)` performs the current one.
+// DENSE: every entry is a move and the entry count is a multiple of three (permutations: sched_len == L).
+template <int TP, bool DENSE, typename Move>
+__device__ __forceinline__ void walk_schedule(const uint2* __restrict__ sc, int iters, Move&& move) {
+    const uint2 none = make_uint2(0xFFFFFFFFu, 0xFFFFFFFFu);
+    constexpr std::integral_constant<bool, DENSE> dense{};
+    int n = 0;
+    uint2 c0 = none, c1 = none, c2 = none;
+    if (iters >= 3) c0 = __ldg(sc), c1 = __ldg(sc + TP), c2 = __ldg(sc + 2 * TP);
+    for (; n + 3 <= iters; n += 3) {
+        sc += 3 * TP;
+        uint2 n0 = none, n1 = none, n2 = none;
+        if (n + 6 <= iters) n0 = __ldg(sc), n1 = __ldg(sc + TP), n2 = __ldg(sc + 2 * TP);
+        move(dense, c0, c1, c2, 3);
+        c0 = n0, c1 = n1, c2 = n2;
+    }
+    if (!DENSE && n < iters) {  // 1 or 2 left
+        const int cnt = iters - n;
+        c0 = __ldg(sc);
+        c1 = cnt > 1 ? __ldg(sc + TP) : none;
+        move(dense, c0, c1, none, cnt);
+    }
+}
+
 template <typename in_t, bool SOFTPLUS, int TP, bool PIPE>
 __global__ void __launch_bounds__(NT, 1) ss2d_bwd_dx_kernel(const FusedDxArgs p) {
     extern __shared__ __align__(128) unsigned char smem[];
@@ -153,12 +178,14 @@ __global__ void __launch_bounds__(NT, 1) ss2d_bwd_dx_kernel(const FusedDxArgs p)
         const int kind = (p.kinds >> (4 * k)) & 15;  // 0 identity, 1 reversed identity, 2 permutation, 3 with repeats
         const bool perm = kind >= 2;
         const bool dup = kind == 3;
+        const bool dense = kind == 2 && p.sched_len == L;  // a permutation: every schedule entry is a move
         const uint2* __restrict__ sched = reinterpret_cast<const uint2*>(p.sched + static_cast<size_t>(k) * p.sched_len) + j;
         const int sched_iters = p.sched_len / (2 * TP);
-        float accB[S], accC[S];
-#pragma unroll
-        for (int m = 0; m < S; ++m) accB[m] = 0.f, accC[m] = 0.f;
         mbar_wait(&barBC[0], static_cast<uint32_t>(it & 1));
+        // dB / dC: this thread's tokens of direction k, (b, k) row of the (B, K, L) outputs
+        float* const gdB = p.dBs + (static_cast<size_t>(b) * K + k) * L + j * S;
+        float* const gdC = p.dCs + (static_cast<size_t>(b) * K + k) * L + j * S;
+        const bool odd = j & 1;
         const in_t* Bq = sB + j * S;
         const in_t* Cq = sC + j * S;
 
@@ -185,14 +212,17 @@ __global__ void __launch_bounds__(NT, 1) ss2d_bwd_dx_kernel(const FusedDxArgs p)
                 const float* yi = sY(ld) + static_cast<size_t>(q) * L;
                 in_t* xt = sX(ld ^ 1) + static_cast<size_t>(q) * L;
                 float* yt = sY(ld ^ 1) + static_cast<size_t>(q) * L;
-                auto move = [&](const uint2 (&e2)[3], int cnt) __attribute__((always_inline)) {
+                auto move = [&](auto dense_tag, const uint2 ea, const uint2 eb, const uint2 ec, int cnt)
+                                __attribute__((always_inline)) {
+                    constexpr bool DENSE = decltype(dense_tag)::value;
+                    const uint32_t ee[6] = {ea.x, ea.y, eb.x, eb.y, ec.x, ec.y};
                     uint32_t xv[6];
                     float yv[6];
 #pragma unroll
                     for (int i = 0; i < 6; ++i) {
-                        const uint32_t e = (i & 1) ? e2[i >> 1].y : e2[i >> 1].x;
-                        const uint32_t src2 = (e == 0xFFFFFFFFu ? 0u : e) & 0xFFFFu;
-                        if ((i >> 1) < cnt) {
+                        const uint32_t e = ee[i];
+                        const uint32_t src2 = (DENSE ? e : (e == 0xFFFFFFFFu ? 0u : e)) & 0xFFFFu;
+                        if (DENSE || (i >> 1) < cnt) {
                             if constexpr (ES == 2) xv[i] = lds_u16(xi, src2);
                             else xv[i] = __float_as_uint(lds_f32(xi, 2 * src2));
                             yv[i] = lds_f32(yi, 2 * src2);
@@ -200,38 +230,17 @@ __global__ void __launch_bounds__(NT, 1) ss2d_bwd_dx_kernel(const FusedDxArgs p)
                     }
 #pragma unroll
                     for (int i = 0; i < 6; ++i) {
-                        const uint32_t e = (i & 1) ? e2[i >> 1].y : e2[i >> 1].x;
+                        const uint32_t e = ee[i];
                         const uint32_t dst2 = e >> 16;
-                        if ((i >> 1) < cnt && e != 0xFFFFFFFFu) {
+                        if (DENSE || ((i >> 1) < cnt && e != 0xFFFFFFFFu)) {
                             if constexpr (ES == 2) sts_u16(xt, dst2, xv[i]);
                             else sts_f32(xt, 2 * dst2, __uint_as_float(xv[i]));
                             sts_f32(yt, 2 * dst2, yv[i]);
                         }
                     }
                 };
-                const uint2* sc = sched;
-                int n = 0;
-                uint2 cur[3], nxt[3];
-                if (sched_iters >= 3) {
-#pragma unroll
-                    for (int u = 0; u < 3; ++u) cur[u] = __ldg(sc + u * TP);
-                }
-                for (; n + 3 <= sched_iters; n += 3) {
-                    sc += 3 * TP;
-                    if (n + 6 <= sched_iters) {
-#pragma unroll
-                        for (int u = 0; u < 3; ++u) nxt[u] = __ldg(sc + u * TP);
-                    }
-                    move(cur, 3);
-#pragma unroll
-                    for (int u = 0; u < 3; ++u) cur[u] = nxt[u];
-                }
-                if (n < sched_iters) {  // 1 or 2 left
-                    const int cnt = sched_iters - n;
-#pragma unroll
-                    for (int u = 0; u < 3; ++u) cur[u] = u < cnt ? __ldg(sc + u * TP) : make_uint2(0xFFFFFFFFu, 0xFFFFFFFFu);
-                    move(cur, cnt);
-                }
+                if (dense) walk_schedule<TP, true>(sched, sched_iters, move);
+                else walk_schedule<TP, false>(sched, sched_iters, move);
                 __syncthreads();  // token-ordered set complete; the image-ordered set is dead
                 if (PIPE && has_next && tid == 0) issue_xy(ld, s + 1);
                 ds = ld ^ 1;
@@ -334,7 +343,13 @@ __global__ void __launch_bounds__(NT, 1) ss2d_bwd_dx_kernel(const FusedDxArgs p)
                 }
             }
             // ---- pass 2b: left-to-right, h_t; du, ddelta; accumulate dB, dC, dA, dD, dbias
+            // dB_t += dh_t*delta_t*u_t and dC_t += dy_t*h_t leave per round as 16-byte vector reds (fp32 adds at L2
+            // over the channels of (b, k)): no accumulator registers live across the rounds of an item.  A chunk of
+            // 18 floats starts 16-byte aligned for even j only, so a lane pair shares its 36 floats as 9 quads: the
+            // even lane sends quads 0-3 from its own values and quad 4 = its last two + the odd lane's first two
+            // (one shuffle pair after the loop), the odd lane quads 5-8 = its values 2..17.
             float h = hin, sA = 0.f, sDs = 0.f, sb = 0.f;
+            float cB[S], cC[S];
 #pragma unroll
             for (int mp = 0; mp < S / 2; ++mp) {
                 float Bv[2], uv[2], yv[2];
@@ -363,13 +378,36 @@ __global__ void __launch_bounds__(NT, 1) ss2d_bwd_dx_kernel(const FusedDxArgs p)
                             dd *= (t < 0.125f) ? ser : (1.0f - ex2f(-t * kLog2e));
                         }
                     }
-                    accB[m] = fmaf(dhs, u, accB[m]);
-                    accC[m] = fmaf(dyv, h, accC[m]);
+                    cB[m] = dhs * u;
+                    cC[m] = dyv * h;
                     sA = fmaf(dhs, w, sA);
                     sDs = fmaf(dyv, u, sDs);
                     sb += dd;
                     sp[m] = dd;  // reuse: sp <- ddelta, dh <- du
                     dh[m] = du;
+                }
+                // quads that are complete after this pair of tokens (m = 2*mp + 1)
+                if (mp % 2 == 1 && mp < S / 2 - 1) {  // m = 3, 7, 11, 15: even lanes, values m-3 .. m
+                    if (!odd) {
+                        red_add_v4(gdB + 2 * mp - 2, cB[2 * mp - 2], cB[2 * mp - 1], cB[2 * mp], cB[2 * mp + 1]);
+                        red_add_v4(gdC + 2 * mp - 2, cC[2 * mp - 2], cC[2 * mp - 1], cC[2 * mp], cC[2 * mp + 1]);
+                    }
+                }
+                if (mp % 2 == 0 && mp >= 2) {  // m = 5, 9, 13, 17: odd lanes, values m-3 .. m
+                    if (odd) {
+                        red_add_v4(gdB + 2 * mp - 2, cB[2 * mp - 2], cB[2 * mp - 1], cB[2 * mp], cB[2 * mp + 1]);
+                        red_add_v4(gdC + 2 * mp - 2, cC[2 * mp - 2], cC[2 * mp - 1], cC[2 * mp], cC[2 * mp + 1]);
+                    }
+                }
+            }
+            {
+                const float b0 = __shfl_down_sync(0xffffffffu, cB[0], 1, width);
+                const float b1 = __shfl_down_sync(0xffffffffu, cB[1], 1, width);
+                const float c0 = __shfl_down_sync(0xffffffffu, cC[0], 1, width);
+                const float c1 = __shfl_down_sync(0xffffffffu, cC[1], 1, width);
+                if (!odd) {
+                    red_add_v4(gdB + S - 2, cB[S - 2], cB[S - 1], b0, b1);
+                    red_add_v4(gdC + S - 2, cC[S - 2], cC[S - 1], c0, c1);
                 }
             }
             store_tokens<S>(dq, sp);  // ddelta over delta, in place (this thread's own chunk)
@@ -395,19 +433,22 @@ __global__ void __launch_bounds__(NT, 1) ss2d_bwd_dx_kernel(const FusedDxArgs p)
                 // ---- token order -> image order: inverse walk of the same schedule
                 const float* ut = sY(ds) + static_cast<size_t>(q) * L;
                 float* di = dxp + static_cast<size_t>(q) * L;
-                auto move = [&](const uint2 (&e2)[3], int cnt) __attribute__((always_inline)) {
+                auto move = [&](auto dense_tag, const uint2 ea, const uint2 eb, const uint2 ec, int cnt)
+                                __attribute__((always_inline)) {
+                    constexpr bool DENSE = decltype(dense_tag)::value;
+                    const uint32_t ee[6] = {ea.x, ea.y, eb.x, eb.y, ec.x, ec.y};
                     float v[6];
 #pragma unroll
                     for (int i = 0; i < 6; ++i) {
-                        const uint32_t e = (i & 1) ? e2[i >> 1].y : e2[i >> 1].x;
-                        const uint32_t dst2 = (e == 0xFFFFFFFFu ? 0u : e) >> 16;
-                        if ((i >> 1) < cnt) v[i] = lds_f32(ut, 2 * dst2);
+                        const uint32_t e = ee[i];
+                        const uint32_t dst2 = (DENSE ? e : (e == 0xFFFFFFFFu ? 0u : e)) >> 16;
+                        if (DENSE || (i >> 1) < cnt) v[i] = lds_f32(ut, 2 * dst2);
                     }
 #pragma unroll
                     for (int i = 0; i < 6; ++i) {
-                        const uint32_t e = (i & 1) ? e2[i >> 1].y : e2[i >> 1].x;
+                        const uint32_t e = ee[i];
                         const uint32_t src2 = e & 0xFFFFu;
-                        if ((i >> 1) < cnt && e != 0xFFFFFFFFu) sts_f32(di, 2 * src2, v[i]);
+                        if (DENSE || ((i >> 1) < cnt && e != 0xFFFFFFFFu)) sts_f32(di, 2 * src2, v[i]);
                     }
                 };
                 const uint2* sc = sched;
@@ -420,29 +461,8 @@ __global__ void __launch_bounds__(NT, 1) ss2d_bwd_dx_kernel(const FusedDxArgs p)
                         if (e2.y != 0xFFFFFFFFu) atomicAdd(di + ((e2.y & 0xFFFFu) >> 1), ut[e2.y >> 17]);
                     }
                 } else {
-                    int n = 0;
-                    uint2 cur[3], nxt[3];
-                    if (sched_iters >= 3) {
-#pragma unroll
-                        for (int u = 0; u < 3; ++u) cur[u] = __ldg(sc + u * TP);
-                    }
-                    for (; n + 3 <= sched_iters; n += 3) {
-                        sc += 3 * TP;
-                        if (n + 6 <= sched_iters) {
-#pragma unroll
-                            for (int u = 0; u < 3; ++u) nxt[u] = __ldg(sc + u * TP);
-                        }
-                        move(cur, 3);
-#pragma unroll
-                        for (int u = 0; u < 3; ++u) cur[u] = nxt[u];
-                    }
-                    if (n < sched_iters) {
-                        const int cnt = sched_iters - n;
-#pragma unroll
-                        for (int u = 0; u < 3; ++u)
-                            cur[u] = u < cnt ? __ldg(sc + u * TP) : make_uint2(0xFFFFFFFFu, 0xFFFFFFFFu);
-                        move(cur, cnt);
-                    }
+                    if (dense) walk_schedule<TP, true>(sc, sched_iters, move);
+                    else walk_schedule<TP, false>(sc, sched_iters, move);
                 }
             }
             fence_proxy_async_smem();
@@ -476,44 +496,8 @@ __global__ void __launch_bounds__(NT, 1) ss2d_bwd_dx_kernel(const FusedDxArgs p)
             if (kind == 1) round(std::true_type{}, r);
             else round(std::false_type{}, r);
         }
-        // ---- item flush: dB / dC of the item's channels (token order, registers) -> global reds
-        {
-            float* gdB = p.dBs + (static_cast<size_t>(b) * K + k) * L + j * S;
-            float* gdC = p.dCs + (static_cast<size_t>(b) * K + k) * L + j * S;
-            if (PP == 1) {
-#pragma unroll
-                for (int m = 0; m < S; m += 2) {
-                    asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(gdB + m), "f"(accB[m]), "f"(accB[m + 1])
-                                 : "memory");
-                    asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(gdC + m), "f"(accC[m]), "f"(accC[m + 1])
-                                 : "memory");
-                }
-            } else {
-                // PP planes hold partial sums for the same tokens: add them up in shared memory first.  Scratch =
-                // a plane buffer nobody uses between items: the du staging once its bulk reduction has been read
-                // (PIPE), the token-ordered dy planes (!PIPE; the next round's loads went to the other set).
-                if (PIPE && tid == 0) bulk_wait_read<0>();
-                __syncthreads();
-                float* f = PIPE ? sDXs : sY(ld ^ 1);  // [2][L] floats, 2 * L <= TOK
-                for (int e = tid; e < 2 * L; e += NT) f[e] = 0.f;
-                __syncthreads();
-#pragma unroll
-                for (int m = 0; m < S; ++m) {
-                    atomicAdd(f + j * S + m, accB[m]);
-                    atomicAdd(f + L + j * S + m, accC[m]);
-                }
-                __syncthreads();
-                float* gB2 = p.dBs + (static_cast<size_t>(b) * K + k) * L;
-                float* gC2 = p.dCs + (static_cast<size_t>(b) * K + k) * L;
-                for (int e = tid * 2; e < L; e += NT * 2) {
-                    asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(gB2 + e), "f"(f[e]), "f"(f[e + 1]) : "memory");
-                    asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(gC2 + e), "f"(f[L + e]), "f"(f[L + e + 1])
-                                 : "memory");
-                }
-            }
-            __syncthreads();  // everybody is done with sB / sC (and the scratch) before the next item's loads
-            if (tid == 0 && it + 1 < my_items) issue_bc(it + 1);
-        }
+        // the last round's closing barrier has every thread past its reads of sB / sC: the next item's B / C may land
+        if (tid == 0 && it + 1 < my_items) issue_bc(it + 1);
     }
     if (tid == 0) bulk_wait_all<0>();
 }

@@ -94,8 +94,6 @@ class DCT2D(nn.Module):
             raise ValueError("tramba_b200.DCT2D: H and W must be even for the quadrant split")
         H, W = x.shape[2], x.shape[3]
         if x.is_cuda and not _lib.lib.tramba_dct2d_supported(H, W):
-            # planes too large for one SM's shared memory (H = 192: the 768^2 stress config only): the same
-            # contraction Wy . X . Wx^T as two plain library GEMMs (cuBLAS), quadrants sliced afterwards
-            y = torch.matmul(torch.matmul(self.dct_y.weight, x.float()), self.dct_x.weight.t())
-            return y[:, :, H // 2:, W // 2:].contiguous(), y[:, :, :H // 2, :W // 2].contiguous()
+            raise RuntimeError(f"tramba_b200.DCT2D: no kernel for {H} x {W} planes (tramba_dct2d_supported); there is "
+                               f"no library fallback")
         return dct2d_split(x, self.dct_y.weight, self.dct_x.weight)  # (high, low), DCT_2D.py:12-18
