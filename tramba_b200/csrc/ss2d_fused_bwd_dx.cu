@@ -186,6 +186,16 @@ __global__ void __launch_bounds__(NT, 1) ss2d_bwd_dx_kernel(const FusedDxArgs p)
         float* const gdB = p.dBs + (static_cast<size_t>(b) * K + k) * L + j * S;
         float* const gdC = p.dCs + (static_cast<size_t>(b) * K + k) * L + j * S;
         const bool odd = j & 1;
+        // ACC (several planes per round, L <= 2304): the PP planes of a round -- and every CTA working on the same
+        // (b, k) -- would all add into the same few KB of dB / dC, and same-address reds serialise at L2.  There the
+        // contributions stay in registers over the item's rounds and are folded over the planes in shared memory
+        // first (one red per token per ITEM).  PP == 1 (L = 9216): per-round vector reds, no accumulator registers.
+        constexpr bool ACC = PP > 1;
+        float accB[ACC ? S : 1], accC[ACC ? S : 1];
+        if constexpr (ACC) {
+#pragma unroll
+            for (int m = 0; m < S; ++m) accB[m] = 0.f, accC[m] = 0.f;
+        }
         const in_t* Bq = sB + j * S;
         const in_t* Cq = sC + j * S;
 
@@ -265,6 +275,7 @@ __global__ void __launch_bounds__(NT, 1) ss2d_bwd_dx_kernel(const FusedDxArgs p)
             in_t* dq = sD(dbuf) + static_cast<size_t>(q) * L + j * S;  // delta / ddelta: always token order
 
             // ---- pass 1: forward fold (P, Sf) and reverse fold (P, Sr) of the segment; g_t = C_t * dy_t stays in dh
+            constexpr bool KEEPG = true;  // (recomputing g in pass 2a measured MORE spills, not fewer)
             float sp[S], dh[S];
             float P = 1.f, Sf = 0.f, Sr = 0.f;
             {
@@ -285,7 +296,7 @@ __global__ void __launch_bounds__(NT, 1) ss2d_bwd_dx_kernel(const FusedDxArgs p)
                         const float a = ex2f(sp[m] * A2);
                         const float bb = sp[m] * Bv[h2] * uv[h2];
                         const float g = Cv[h2] * yv[h2];
-                        dh[m] = g;
+                        if constexpr (KEEPG) dh[m] = g;
                         Sf = fmaf(a, Sf, bb);
                         P *= a;
                         Sr = fmaf(P, g, Sr);
@@ -333,13 +344,28 @@ __global__ void __launch_bounds__(NT, 1) ss2d_bwd_dx_kernel(const FusedDxArgs p)
                 Ein = fmaf(Pre, ep, Sre);
             }
             // ---- pass 2a: right-to-left, dh_t = g_t + E_{t+1}
-            {
+            if constexpr (KEEPG) {
                 float E = Ein;
 #pragma unroll
                 for (int m = S - 1; m >= 0; --m) {
                     const float a = ex2f(sp[m] * A2);
                     dh[m] += E;
                     E = a * dh[m];
+                }
+            } else {
+                float E = Ein;
+#pragma unroll
+                for (int mp = S / 2 - 1; mp >= 0; --mp) {
+                    float Cv[2], yv[2];
+                    load_pair(Cq, mp, Cv[0], Cv[1]);
+                    chunk_pair<REV>(yq, mp, yv[0], yv[1]);
+#pragma unroll
+                    for (int h2 = 1; h2 >= 0; --h2) {
+                        const int m = 2 * mp + h2;
+                        const float a = ex2f(sp[m] * A2);
+                        dh[m] = fmaf(Cv[h2], yv[h2], E);
+                        E = a * dh[m];
+                    }
                 }
             }
             // ---- pass 2b: left-to-right, h_t; du, ddelta; accumulate dB, dC, dA, dD, dbias
@@ -378,8 +404,13 @@ __global__ void __launch_bounds__(NT, 1) ss2d_bwd_dx_kernel(const FusedDxArgs p)
                             dd *= (t < 0.125f) ? ser : (1.0f - ex2f(-t * kLog2e));
                         }
                     }
-                    cB[m] = dhs * u;
-                    cC[m] = dyv * h;
+                    if constexpr (ACC) {
+                        accB[m] = fmaf(dhs, u, accB[m]);
+                        accC[m] = fmaf(dyv, h, accC[m]);
+                    } else {
+                        cB[m] = dhs * u;
+                        cC[m] = dyv * h;
+                    }
                     sA = fmaf(dhs, w, sA);
                     sDs = fmaf(dyv, u, sDs);
                     sb += dd;
@@ -387,20 +418,20 @@ __global__ void __launch_bounds__(NT, 1) ss2d_bwd_dx_kernel(const FusedDxArgs p)
                     dh[m] = du;
                 }
                 // quads that are complete after this pair of tokens (m = 2*mp + 1)
-                if (mp % 2 == 1 && mp < S / 2 - 1) {  // m = 3, 7, 11, 15: even lanes, values m-3 .. m
+                if (!ACC && mp % 2 == 1 && mp < S / 2 - 1) {  // m = 3, 7, 11, 15: even lanes, values m-3 .. m
                     if (!odd) {
                         red_add_v4(gdB + 2 * mp - 2, cB[2 * mp - 2], cB[2 * mp - 1], cB[2 * mp], cB[2 * mp + 1]);
                         red_add_v4(gdC + 2 * mp - 2, cC[2 * mp - 2], cC[2 * mp - 1], cC[2 * mp], cC[2 * mp + 1]);
                     }
                 }
-                if (mp % 2 == 0 && mp >= 2) {  // m = 5, 9, 13, 17: odd lanes, values m-3 .. m
+                if (!ACC && mp % 2 == 0 && mp >= 2) {  // m = 5, 9, 13, 17: odd lanes, values m-3 .. m
                     if (odd) {
                         red_add_v4(gdB + 2 * mp - 2, cB[2 * mp - 2], cB[2 * mp - 1], cB[2 * mp], cB[2 * mp + 1]);
                         red_add_v4(gdC + 2 * mp - 2, cC[2 * mp - 2], cC[2 * mp - 1], cC[2 * mp], cC[2 * mp + 1]);
                     }
                 }
             }
-            {
+            if constexpr (!ACC) {
                 const float b0 = __shfl_down_sync(0xffffffffu, cB[0], 1, width);
                 const float b1 = __shfl_down_sync(0xffffffffu, cB[1], 1, width);
                 const float c0 = __shfl_down_sync(0xffffffffu, cC[0], 1, width);
@@ -495,6 +526,29 @@ __global__ void __launch_bounds__(NT, 1) ss2d_bwd_dx_kernel(const FusedDxArgs p)
         for (int r = 0; r < R; ++r) {
             if (kind == 1) round(std::true_type{}, r);
             else round(std::false_type{}, r);
+        }
+        if constexpr (ACC) {
+            // ---- item flush: fold the PP planes' partial sums in shared memory, then one red per token.  Scratch =
+            // a plane buffer nobody uses between items: the du staging once its bulk reduction has been read (PIPE),
+            // the token-ordered dy planes (!PIPE; the next round's loads went to the other set).
+            if (PIPE && tid == 0) bulk_wait_read<0>();
+            __syncthreads();
+            float* f = PIPE ? sDXs : sY(ld ^ 1);  // [2][L] floats, 2 * L <= TOK
+            for (int e = tid; e < 2 * L; e += NT) f[e] = 0.f;
+            __syncthreads();
+#pragma unroll
+            for (int m = 0; m < S; ++m) {
+                atomicAdd(f + j * S + m, accB[m]);
+                atomicAdd(f + L + j * S + m, accC[m]);
+            }
+            __syncthreads();
+            float* gB2 = p.dBs + (static_cast<size_t>(b) * K + k) * L;
+            float* gC2 = p.dCs + (static_cast<size_t>(b) * K + k) * L;
+            for (int e = tid * 4; e < L; e += NT * 4) {
+                red_add_v4(gB2 + e, f[e], f[e + 1], f[e + 2], f[e + 3]);
+                red_add_v4(gC2 + e, f[L + e], f[L + e + 1], f[L + e + 2], f[L + e + 3]);
+            }
+            __syncthreads();  // everybody is done with the scratch (and with sB / sC)
         }
         // the last round's closing barrier has every thread past its reads of sB / sC: the next item's B / C may land
         if (tid == 0 && it + 1 < my_items) issue_bc(it + 1);
