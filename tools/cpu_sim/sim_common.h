@@ -576,6 +576,25 @@ constexpr float kLn2 = 0.6931471805599453f;
 
 void note_launch();   // capi.cu (translated) defines it
 
+// division by a run-time constant (csrc/common.cuh FastDiv; host arithmetic here)
+struct FastDiv {
+    uint32_t d, mul, shift;
+    void init(uint32_t d_) {
+        d = d_;
+        if (d <= 1) {
+            mul = 0;
+            shift = 0;
+            return;
+        }
+        shift = 0;
+        while ((1ull << shift) < d) ++shift;
+        mul = static_cast<uint32_t>((((1ull << shift) - d) << 32) / d + 1);
+    }
+    uint32_t div(uint32_t n) const {
+        return static_cast<uint32_t>(((static_cast<uint64_t>(n) * mul >> 32) + n) >> shift);
+    }
+};
+
 // per-device launch configuration helpers of csrc/common.cuh (one simulated device; sm_count may change per test)
 constexpr int kMaxDevices = 64;
 template <typename Kern>

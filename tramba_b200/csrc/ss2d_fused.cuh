@@ -84,6 +84,7 @@ struct FusedDxArgs {
     uint32_t kinds;         // 4 bits per direction: 0 identity, 1 reversed identity, 2 permutation, 3 with repeats
     int softplus;
     int R;                  // rounds per item (set by the launcher)
+    FastDiv div_db, div_k, div_r;  // / (D / (R*PP)), / K, / R (set by the launcher)
 };
 cudaError_t launch_ss2d_fused_bwd_dx(const FusedDxArgs& a, int L, int in_dtype, cudaStream_t st);
 bool ss2d_fused_bwd_dx_fits(int L, int es);

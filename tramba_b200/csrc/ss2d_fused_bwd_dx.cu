@@ -131,18 +131,22 @@ __global__ void __launch_bounds__(NT, 1) ss2d_bwd_dx_kernel(const FusedDxArgs p)
     __syncthreads();
 
     auto item_coord = [&](int it, int& b, int& k, int& d0) {
-        const int item = static_cast<int>(blockIdx.x) + it * static_cast<int>(gridDim.x);
-        const int db = item % dblocks;
-        const int bk = item / dblocks;
-        k = bk % K;
-        b = bk / K;
-        d0 = db * RB;
+        const uint32_t item = blockIdx.x + static_cast<uint32_t>(it) * gridDim.x;
+        const uint32_t bk = p.div_db.div(item);
+        const uint32_t db = item - bk * static_cast<uint32_t>(dblocks);
+        b = static_cast<int>(p.div_k.div(bk));
+        k = static_cast<int>(bk) - b * K;
+        d0 = static_cast<int>(db) * RB;
+    };
+    auto round_coord = [&](int s, int& b, int& k, int& d0) {  // global round s of this CTA -> its PP planes
+        const int it = static_cast<int>(p.div_r.div(static_cast<uint32_t>(s)));
+        item_coord(it, b, k, d0);
+        d0 += (s - it * R) * PP;
     };
     // ---- producers (thread 0 only): coordinates of global round s of this CTA
     auto issue_xy = [&](int set, int s) {
         int b, k, d0;
-        item_coord(s / R, b, k, d0);
-        d0 += (s % R) * PP;
+        round_coord(s, b, k, d0);
         const long long pl = (static_cast<long long>(b) * D + d0) * L;
         mbar_expect_tx(&barXY[set], TOK * (ES + 4));
         bulk_g2s(sX(set), gx + pl, TOK * ES, &barXY[set]);
@@ -150,8 +154,7 @@ __global__ void __launch_bounds__(NT, 1) ss2d_bwd_dx_kernel(const FusedDxArgs p)
     };
     auto issue_d = [&](int buf, int s) {
         int b, k, d0;
-        item_coord(s / R, b, k, d0);
-        d0 += (s % R) * PP;
+        round_coord(s, b, k, d0);
         mbar_expect_tx(&barD[buf], TOK * ES);
         bulk_g2s(sD(buf), gd + ((static_cast<long long>(b) * K + k) * D + d0) * L, TOK * ES, &barD[buf]);
     };
@@ -276,7 +279,8 @@ __global__ void __launch_bounds__(NT, 1) ss2d_bwd_dx_kernel(const FusedDxArgs p)
 
             // ---- pass 1: forward fold (P, Sf) and reverse fold (P, Sr) of the segment; g_t = C_t * dy_t stays in dh
             constexpr bool KEEPG = true;  // (recomputing g in pass 2a measured MORE spills, not fewer)
-            float sp[S], dh[S];
+            constexpr bool KEEPA = PP == 1;  // a_t = exp(delta_t A) kept for passes 2a / 2b where registers allow
+            float sp[S], dh[S], av[KEEPA ? S : 1];
             float P = 1.f, Sf = 0.f, Sr = 0.f;
             {
                 load_tokens<S>(dq, sp);
@@ -294,6 +298,7 @@ __global__ void __launch_bounds__(NT, 1) ss2d_bwd_dx_kernel(const FusedDxArgs p)
                         float e;
                         sp[m] = !SOFTPLUS ? raw : (ES == 2 ? softplus20_fast(raw) : softplus20(raw, e));
                         const float a = ex2f(sp[m] * A2);
+                        if constexpr (KEEPA) av[m] = a;
                         const float bb = sp[m] * Bv[h2] * uv[h2];
                         const float g = Cv[h2] * yv[h2];
                         if constexpr (KEEPG) dh[m] = g;
@@ -348,7 +353,7 @@ __global__ void __launch_bounds__(NT, 1) ss2d_bwd_dx_kernel(const FusedDxArgs p)
                 float E = Ein;
 #pragma unroll
                 for (int m = S - 1; m >= 0; --m) {
-                    const float a = ex2f(sp[m] * A2);
+                    const float a = KEEPA ? av[m] : ex2f(sp[m] * A2);
                     dh[m] += E;
                     E = a * dh[m];
                 }
@@ -386,7 +391,7 @@ __global__ void __launch_bounds__(NT, 1) ss2d_bwd_dx_kernel(const FusedDxArgs p)
                 for (int h2 = 0; h2 < 2; ++h2) {
                     const int m = 2 * mp + h2;
                     const float u = uv[h2], dyv = yv[h2], Bm = Bv[h2];
-                    const float a = ex2f(sp[m] * A2);
+                    const float a = KEEPA ? av[m] : ex2f(sp[m] * A2);
                     const float w = a * h;  // a_t * h_{t-1}
                     const float bu = Bm * u;
                     h = fmaf(sp[m], bu, w);  // h_t
@@ -528,25 +533,37 @@ __global__ void __launch_bounds__(NT, 1) ss2d_bwd_dx_kernel(const FusedDxArgs p)
             else round(std::false_type{}, r);
         }
         if constexpr (ACC) {
-            // ---- item flush: fold the PP planes' partial sums in shared memory, then one red per token.  Scratch =
-            // a plane buffer nobody uses between items: the du staging once its bulk reduction has been read (PIPE),
-            // the token-ordered dy planes (!PIPE; the next round's loads went to the other set).
+            // ---- item flush: fold the PP planes' partial sums with a binary tree through shared memory (the upper
+            // half of the planes parks its 2*S values, element-major so that lanes hit consecutive banks; the lower
+            // half adds them), then plane 0 sends one red per token.  No shared-memory atomics (a CAS loop each, and
+            // all PP planes would hit the same word in lockstep).  Scratch = a plane buffer nobody uses between items:
+            // the du staging once its bulk reduction has been read (PIPE), the token-ordered dy planes (!PIPE; the
+            // next round's loads went to the other set); (PP/2) * TP * 2S floats = TOK floats at most.
             if (PIPE && tid == 0) bulk_wait_read<0>();
-            __syncthreads();
-            float* f = PIPE ? sDXs : sY(ld ^ 1);  // [2][L] floats, 2 * L <= TOK
-            for (int e = tid; e < 2 * L; e += NT) f[e] = 0.f;
-            __syncthreads();
+            float* f = PIPE ? sDXs : sY(ld ^ 1);
+#pragma unroll 1
+            for (int hp = PP / 2; hp >= 1; hp >>= 1) {
+                __syncthreads();  // (first turn: the staging has left; later turns: the previous readers are done)
+                const int slot = (q - hp) * TP + j, stride = hp * TP;
+                if (q >= hp && q < 2 * hp) {
 #pragma unroll
-            for (int m = 0; m < S; ++m) {
-                atomicAdd(f + j * S + m, accB[m]);
-                atomicAdd(f + L + j * S + m, accC[m]);
+                    for (int m = 0; m < S; ++m) f[m * stride + slot] = accB[m], f[(S + m) * stride + slot] = accC[m];
+                }
+                __syncthreads();
+                if (q < hp) {
+                    const int mine = q * TP + j;
+#pragma unroll
+                    for (int m = 0; m < S; ++m) accB[m] += f[m * stride + mine], accC[m] += f[(S + m) * stride + mine];
+                }
             }
-            __syncthreads();
-            float* gB2 = p.dBs + (static_cast<size_t>(b) * K + k) * L;
-            float* gC2 = p.dCs + (static_cast<size_t>(b) * K + k) * L;
-            for (int e = tid * 4; e < L; e += NT * 4) {
-                red_add_v4(gB2 + e, f[e], f[e + 1], f[e + 2], f[e + 3]);
-                red_add_v4(gC2 + e, f[L + e], f[L + e + 1], f[L + e + 2], f[L + e + 3]);
+            if (q == 0) {
+#pragma unroll
+                for (int m = 0; m < S; m += 2) {
+                    asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(gdB + m), "f"(accB[m]), "f"(accB[m + 1])
+                                 : "memory");
+                    asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(gdC + m), "f"(accC[m]), "f"(accC[m + 1])
+                                 : "memory");
+                }
             }
             __syncthreads();  // everybody is done with the scratch (and with sB / sC)
         }
@@ -586,6 +603,9 @@ cudaError_t launch_tp(const FusedDxArgs& a, cudaStream_t st) {
     FusedDxArgs b = a;
     constexpr int PP = NT / TP;
     b.R = pick_rounds(a.B, a.K, a.D, PP, sms);
+    b.div_db.init(static_cast<uint32_t>(a.D / (b.R * PP)));
+    b.div_k.init(static_cast<uint32_t>(a.K));
+    b.div_r.init(static_cast<uint32_t>(b.R));
     const int items = a.B * a.K * (a.D / (b.R * PP));
     const int grid = items < sms ? items : sms;
     kern<<<grid, NT, Lay::total, st>>>(b);

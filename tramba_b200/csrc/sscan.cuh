@@ -25,28 +25,6 @@
 
 namespace tramba {
 
-struct FastDiv {
-    uint32_t d, mul, shift;
-    __host__ void init(uint32_t d_) {
-        d = d_;
-        if (d <= 1) {
-            mul = 0;
-            shift = 0;
-            return;
-        }
-        shift = 0;
-        while ((1ull << shift) < d) ++shift;
-        mul = static_cast<uint32_t>((((1ull << shift) - d) << 32) / d + 1);
-    }
-    __host__ __device__ __forceinline__ uint32_t div(uint32_t n) const {
-#ifdef __CUDA_ARCH__
-        return static_cast<uint32_t>((static_cast<uint64_t>(__umulhi(n, mul)) + n) >> shift);
-#else
-        return static_cast<uint32_t>(((static_cast<uint64_t>(n) * mul >> 32) + n) >> shift);
-#endif
-    }
-};
-
 struct SScanPlan {
     int tseg;     // tokens per lane per chunk
     int ch;       // 32 * tseg
