@@ -54,6 +54,9 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="do not capture the step in a CUDA graph")
     ap.add_argument("--unfused", action="store_true", help="op-by-op SS2D path instead of the fused core")
+    ap.add_argument("--no-overlap", action="store_true", help="N > 1: one blocking all-reduce of the flat gradient buffer "
+                    "after backward instead of bucketed all-reduces overlapped with backward")
+    ap.add_argument("--buckets", type=int, default=4, help="gradient buckets of the overlapped all-reduce")
     ap.add_argument("--no-shadow", action="store_true", help="plain autocast (weights cast on every use) instead of "
                     "bf16 shadow weights refreshed after the optimizer step")
     ap.add_argument("--cpu-budget-s", type=float, default=240.0, help="wall budget of the reference arm")
@@ -207,7 +210,7 @@ def summarize_prof(prof):
 
 
 # kernel-name fragment -> the `kind` tramba_b200._lib.timed records for it
-KIND_OF = {"ss2d_bwd_kernel": "ss2d_fused_bwd", "ss2d_fwd_kernel": "ss2d_fused_fwd", "merge_skewed_kernel": "cross_merge_skewed",
+KIND_OF = {"ss2d_bwd_dx_kernel": "ss2d_fused_bwd", "ss2d_bwd_kernel": "ss2d_fused_bwd", "ss2d_fwd_kernel": "ss2d_fused_fwd", "merge_skewed_kernel": "cross_merge_skewed",
            # the compile-time-geometry candidates (TRAMBA_B200_LIB=next) report under the same kinds
            "ss2d_bwd_cg_kernel": "ss2d_fused_bwd", "ss2d_fwd_cg_kernel": "ss2d_fused_fwd",
            "merge_skewed_cg_kernel": "cross_merge_skewed",
@@ -312,6 +315,9 @@ def run_ours(args):
     if world > 1:
         for p in params:
             dist.broadcast(p.data, 0)
+        if not args.no_overlap:
+            # bucketed all-reduce launched from inside backward on a side stream (captured in the step's CUDA graph)
+            fg.enable_overlap(world, n_buckets=args.buckets, stream=torch.cuda.Stream())
     net = model
     B = args.batch
     g = torch.Generator().manual_seed(rank)
@@ -521,7 +527,11 @@ def run_ours(args):
             "data": "synthetic",
             "config": {"workload": "Tramba-V-TSOD training step 384x384, batch 4 per GPU (BASELINE config 3)",
                        "img_size": IMG, "global_batch": world * B, "parallelism": f"dp{world}",
-                       "weights": "random-init, 111.44 M params", "optimizer": "Adam (fused); flat-buffer NCCL all-reduce (AVG) of all gradients per step",
+                       "weights": "random-init, 111.44 M params", "optimizer": "Adam (fused)",
+                       "collective": ("none (single GPU)" if world == 1 else
+                                      f"NCCL all-reduce (AVG) of the flat fp32 gradient buffer, {fg.flat.numel() * 4} bytes per step, "
+                                      + ("one blocking call after backward" if args.no_overlap else
+                                         f"{args.buckets} buckets launched from inside backward on a side stream")),
                        "weight_precision": "fp32 masters + bf16 shadows refreshed after Adam" if shadow else "fp32, autocast casts per use",
                        "ss2d_path": "op-by-op kernels" if args.unfused else "fused core kernels",
                        "step_launch": "CUDA graphs (fwd+bwd graph, all-reduce, Adam graph)" if graph is not None else "eager",

@@ -26,7 +26,7 @@ def _model():
                                torch.nn.Flatten(), torch.nn.Linear(4 * 8 * 8, 5), torch.nn.Linear(5, 1, bias=False))
 
 
-def _worker(rank, world, port, out_dir):
+def _worker(rank, world, port, out_dir, overlap=0):
     sys.path.insert(0, os.path.dirname(HERE))
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     torch.set_num_threads(1)
@@ -37,6 +37,10 @@ def _worker(rank, world, port, out_dir):
     params = list(model.parameters())
     opt = torch.optim.Adam(params, lr=1e-2)
     fg = FlatGradients(params)
+    if overlap:      # bucketed all-reduce launched from the gradient hooks DURING backward (inline on CPU: stream=None)
+        fg.enable_overlap(world, n_buckets=overlap, stream=None)
+        assert len(fg.buckets) >= 2 and sum(len(b["idx"]) for b in fg.buckets) == len(params)
+        assert fg.buckets[0]["lo"] == 0 and fg.buckets[-1]["hi"] == fg.flat.numel()
     assert all(p.grad.data_ptr() == v.data_ptr() for p, v in zip(params, fg.views))
     g = torch.Generator().manual_seed(100 + rank)
     x = torch.randn(2, 3, 8, 8, generator=g)
@@ -44,11 +48,23 @@ def _worker(rank, world, port, out_dir):
     for _ in range(2):                                        # two steps: the views must survive a step
         fg.begin()
         assert all(p.grad is None for p in params)
+        if overlap:
+            local = []
+            hooks = [p.register_post_accumulate_grad_hook(lambda t, local=local: local.append((id(t), t.grad.clone())))
+                     for p in params]      # registered AFTER fg's hooks?  order is irrelevant: grads are not mutated
         model(x).square().mean().backward()
-        local = [p.grad.clone() for p in params]
+        if overlap:
+            for h in hooks:
+                h.remove()
+            byid = dict(local)
+            local = [byid[id(p)] for p in params]
+            assert all(fg._launched[:-1]) or all(fg._launched)   # every complete bucket left during backward
+        else:
+            local = [p.grad.clone() for p in params]
         fg.pack()
         assert all(p.grad.data_ptr() == v.data_ptr() for p, v in zip(params, fg.views))
-        assert all(torch.equal(p.grad, l) for p, l in zip(params, local))
+        if not overlap:
+            assert all(torch.equal(p.grad, l) for p, l in zip(params, local))
         fg.all_reduce(world)
         for p, l in zip(params, local):
             mean = l.clone()
@@ -68,6 +84,18 @@ def _worker(rank, world, port, out_dir):
 def test_flat_gradients_world2_gloo(tmp_path):
     world = 2
     mp.spawn(_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    for r in range(world):
+        worst, same = np.load(tmp_path / f"r{r}.npy")
+        assert worst < 1e-6, worst
+        assert same == 1.0
+
+
+@pytest.mark.timeout(300)
+def test_flat_gradients_overlapped_buckets_world2_gloo(tmp_path):
+    """The overlapped mode (bench.py at N > 1): gradient hooks pack + all-reduce each bucket as soon as its last
+    gradient exists; pack() completes whatever is left.  Same result as the blocking path: the mean on every rank."""
+    world = 2
+    mp.spawn(_worker, args=(world, _free_port(), str(tmp_path), 3), nprocs=world, join=True)
     for r in range(world):
         worst, same = np.load(tmp_path / f"r{r}.npy")
         assert worst < 1e-6, worst

@@ -70,7 +70,7 @@ def main():
     for _ in range(3):
         step()
     torch.cuda.synchronize()
-    with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA]) as prof:
+    with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA], with_stack=True) as prof:
         for _ in range(a.steps):
             step()
         torch.cuda.synchronize()
@@ -89,6 +89,29 @@ def main():
     print("\nself device time per operator (autograd nodes appear under their own names):")
     for k, (n, t) in sorted(ops.items(), key=lambda kv: -kv[1][1])[:60]:
         print(f"{100 * t / tot:6.2f}% {t / a.steps / 1e3:8.3f} ms/step {n // a.steps:6d} x  {k[:100]}")
+    # who calls the glue operators: device time of copy_ / sum / add / mul ... grouped by the innermost Python frame
+    # inside this repository (forward ops; autograd nodes have no Python stack and are grouped under their node name)
+    callers = collections.defaultdict(lambda: [0, 0.0])
+    glue = ("aten::copy_", "aten::sum", "aten::add", "aten::add_", "aten::mul", "aten::fill_", "aten::zero_",
+            "aten::gelu", "aten::cat", "aten::clone", "aten::contiguous")
+    for ev in prof.events():
+        if ev.name not in glue:
+            continue
+        t = dev_time(ev)
+        if t <= 0:
+            continue
+        where = "(no python frame: autograd node / optimizer)"
+        for fr in (ev.stack or []):
+            if "/tramba_b200/" in fr or "/tools/" in fr or "bench.py" in fr:
+                where = fr.split("/root/")[-1] if "/root/" in fr else fr
+                where = where[-90:]
+                break
+        c = callers[(ev.name, where)]
+        c[0] += 1
+        c[1] += t
+    print("\nglue operators by calling frame (self device time):")
+    for (op, where), (n, t) in sorted(callers.items(), key=lambda kv: -kv[1][1])[:45]:
+        print(f"{t / a.steps / 1e3:8.3f} ms/step {n // a.steps:5d} x  {op:16s} {where}")
     print("\nforward device time per module range (nested ranges overlap; backward is not attributed):")
     for k, (n, t) in sorted(mods.items(), key=lambda kv: -kv[1][1])[:40]:
         print(f"{t / a.steps / 1e3:8.3f} ms/step {n // a.steps:4d} x  {k}")

@@ -6,6 +6,8 @@ is the gradient all-reduce.  Every gradient lives in ONE flat fp32 buffer that i
     loss.backward()                 #                per-parameter accumulate kernels)
     fg.pack()                       # one multi-tensor copy into the flat buffer; p.grad = views of it
     fg.all_reduce(world)            # NCCL: AVG; gloo (CPU tests): SUM then scale
+    (or fg.enable_overlap(world, n_buckets, side_stream) once: the all-reduce then runs bucket by bucket on a side
+     stream DURING backward, and pack() only joins it)
     optimizer.step()                # sees the flat views
 
 The reference has no distributed code (`run.py:46-50` only prints); this is build-side.
@@ -72,12 +74,109 @@ class FlatGradients:
             p.grad = self.views[-1]
             off += p.numel()
 
+    # ---- overlap of the gradient all-reduce with the backward pass (world > 1) -----------------------------------
+    def enable_overlap(self, world, n_buckets=4, stream=None):
+        """Splits the flat buffer into `n_buckets` contiguous ranges (by bytes, cut at parameter boundaries).  A
+        post-accumulate hook on every gradient source counts arrivals; when the last gradient of a range has been
+        produced, the range is packed (one multi-tensor copy) and all-reduced on a SIDE stream while autograd keeps
+        running on the main one -- the decoder's gradients travel while the encoder's are still being computed.
+        pack() then only joins the side stream.  `stream`: a torch.cuda.Stream, or None on CPU (gloo tests), where the
+        same bucket logic runs inline.  Capturable in a CUDA graph (the side stream forks from / joins the capturing
+        stream; NCCL collectives are graph-capturable)."""
+        self.world = world
+        self.side = stream
+        total = self.flat.numel()
+        target = (total + n_buckets - 1) // n_buckets
+        self.buckets, cur, acc, off = [], [], 0, 0
+        lo = 0
+        for i, p in enumerate(self.params):
+            cur.append(i)
+            acc += p.numel()
+            off += p.numel()
+            if acc >= target or i == len(self.params) - 1:
+                self.buckets.append({"idx": cur, "lo": lo, "hi": off})
+                cur, acc, lo = [], 0, off
+        self.bucket_of = {}
+        for b, bk in enumerate(self.buckets):
+            for i in bk["idx"]:
+                self.bucket_of[i] = b
+        self._arrived = [0] * len(self.buckets)
+        self._launched = [False] * len(self.buckets)
+        self._hooks = []
+        for i, src in enumerate(self.sources):
+            self._hooks.append(src.register_post_accumulate_grad_hook(lambda t, i=i: self._on_grad(i)))
+        self.overlap = True
+
+    def _on_grad(self, i):
+        if not getattr(self, "_armed", False):
+            return
+        b = self.bucket_of[i]
+        self._arrived[b] += 1
+        if self._arrived[b] == len(self.buckets[b]["idx"]) and not self._launched[b]:
+            self._launch(b)
+
+    def _launch(self, b):
+        bk = self.buckets[b]
+        self._launched[b] = True
+        views = [self.views[i] for i in bk["idx"]]
+        grads = [self.sources[i].grad for i in bk["idx"]]
+        chunk = self.flat[bk["lo"]:bk["hi"]]
+
+        def work():
+            torch._foreach_copy_(views, grads)
+            self._reduce(chunk)
+        if self.side is None:
+            work()
+        else:
+            self.side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(self.side):
+                work()
+
+    def _reduce(self, t):
+        if self.world <= 1:
+            return
+        if dist.get_backend() == "nccl":
+            dist.all_reduce(t, op=dist.ReduceOp.AVG)
+        else:                           # gloo has no AVG
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+            t.div_(self.world)
+
     def begin(self):
         for p, s in zip(self.params, self.sources):
             p.grad = None
             s.grad = None
+        if getattr(self, "overlap", False):
+            self._arrived = [0] * len(self.buckets)
+            self._launched = [False] * len(self.buckets)
+            self._armed = True
 
     def pack(self):
+        if getattr(self, "overlap", False):
+            # buckets whose gradients all arrived are already packed and reduced (or in flight on the side stream);
+            # the rest (parameters that received no gradient this step) are completed here
+            self._armed = False
+            for b, bk in enumerate(self.buckets):
+                if not self._launched[b]:
+                    for i in bk["idx"]:
+                        if self.sources[i].grad is None:
+                            self.views[i].zero_()
+                        else:
+                            self.views[i].copy_(self.sources[i].grad)
+                    self._launched[b] = True
+                    chunk = self.flat[bk["lo"]:bk["hi"]]
+                    if self.side is None:
+                        self._reduce(chunk)
+                    else:
+                        self.side.wait_stream(torch.cuda.current_stream())
+                        with torch.cuda.stream(self.side):
+                            self._reduce(chunk)
+            if self.side is not None:
+                torch.cuda.current_stream().wait_stream(self.side)
+            for v, p, s in zip(self.views, self.params, self.sources):
+                if s is not p:
+                    s.grad = None
+                p.grad = v
+            return
         got = [(v, s.grad) for v, s in zip(self.views, self.sources) if s.grad is not None]
         if got:
             torch._foreach_copy_([v for v, _ in got], [g for _, g in got])
@@ -89,7 +188,7 @@ class FlatGradients:
             p.grad = v
 
     def all_reduce(self, world):
-        if world <= 1:
+        if world <= 1 or getattr(self, "overlap", False):     # overlapped mode: done bucket by bucket during backward
             return
         if dist.get_backend() == "nccl":
             dist.all_reduce(self.flat, op=dist.ReduceOp.AVG)
