@@ -190,6 +190,16 @@ TRAMBA_API int tramba_ss2d_fused_fwd(const void* x, const void* dts, const void*
 TRAMBA_API size_t tramba_order_sched_len(int order, int H, int W, int param);
 TRAMBA_API int tramba_order_sched(int order, int H, int W, int param, uint32_t* sched_out /* K*len, host */,
                                   int32_t* kind_out /* K, host */);
+/* Forward on the same schedule, with DIRECTION PAIRING: a direction and the one that reverses it (partners, from
+ * tramba_order_pairs) share one token-ordered copy of the plane and one merge into the image; same inputs / output
+ * as tramba_ss2d_fused_fwd.  kinds / partners: (K) int32 each, HOST. */
+TRAMBA_API int tramba_order_pairs(int order, int H, int W, int param, int32_t* partner_out /* K, host */);
+TRAMBA_API int tramba_ss2d_fused_fwd_sched_supported(int order, int K, int D, int H, int W, int N, int in_dtype);
+TRAMBA_API int tramba_ss2d_fused_fwd_sched(const void* x, const void* dts, const void* Bs, const void* Cs,
+                                           const float* A, const float* Dp, const float* delta_bias,
+                                           const uint32_t* sched, int sched_len, const int32_t* kinds,
+                                           const int32_t* partners, float* y, int order, int K, int B, int D, int H,
+                                           int W, int N, int in_dtype, int delta_softplus, void* stream);
 TRAMBA_API int tramba_ss2d_fused_bwd_dx_supported(int order, int K, int D, int H, int W, int N, int in_dtype);
 TRAMBA_API int tramba_ss2d_fused_bwd_dx(const void* x, const void* dts, const void* Bs, const void* Cs,
                                         const float* A, const float* Dp, const float* delta_bias,

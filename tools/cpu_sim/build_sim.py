@@ -102,7 +102,7 @@ extern "C" const char* sim_merge_cg(const void* ys, void* y, const uint16_t* idx
 }
 '''
 
-FUSED_FILES = ["ss2d_fused_fwd.cu", "ss2d_fused_bwd.cu", "ss2d_fused_bwd_dx.cu", "ss2d_fused_merge.cu", os.path.join("next", "ss2d_fused_fwd_cg.cu"),
+FUSED_FILES = ["ss2d_fused_fwd.cu", "ss2d_fused_fwd_pair.cu", "ss2d_fused_bwd.cu", "ss2d_fused_bwd_dx.cu", "ss2d_fused_merge.cu", os.path.join("next", "ss2d_fused_fwd_cg.cu"),
                os.path.join("next", "ss2d_fused_bwd_cg.cu"), os.path.join("next", "ss2d_fused_merge_cg.cu")]
 
 

@@ -109,6 +109,31 @@ def main():
                 torch.cuda.synchronize()
                 r["ddelta_max_abs_diff"] = float((dd1.float() - ddt.float()).abs().max())
                 r["dx_rel_diff"] = float((dx1.float() - dx32).abs().max() / dx32.abs().max())
+        # ---- forward: first generation (skewed planes, table gathers) vs paired directions on the schedule
+        y1 = torch.empty(B, D, L, device=dev)
+        if _lib.lib.tramba_ss2d_fused_supported(order, K, D, H, H, 1, code, 0):
+            idx = fused._idx16(order, H, param, dev)
+            f1 = lambda: _lib.check(_lib.lib.tramba_ss2d_fused_fwd(
+                x.data_ptr(), dts.data_ptr(), Bs.data_ptr(), Cs.data_ptr(), A.data_ptr(), Dp.data_ptr(), bias.data_ptr(),
+                idx.data_ptr(), y1.data_ptr(), order, K, B, D, H, H, 1, code, 1, st()))
+            r["fwd_v1_us"] = round(timeit(f1, a.reps, flush), 1)
+            tot["fwd_v1"] = tot.get("fwd_v1", 0.0) + calls * r["fwd_v1_us"]
+        if _lib.lib.tramba_ss2d_fused_fwd_sched_supported(order, K, D, H, H, 1, code):
+            sched, kinds = fused._sched(order, H, param, dev)
+            partners = fused._pairs(order, H, param)
+            y2 = torch.empty(B, D, L, device=dev)
+            f2 = lambda: _lib.check(_lib.lib.tramba_ss2d_fused_fwd_sched(
+                x.data_ptr(), dts.data_ptr(), Bs.data_ptr(), Cs.data_ptr(), A.data_ptr(), Dp.data_ptr(), bias.data_ptr(),
+                sched.data_ptr(), sched.shape[1], kinds.ctypes.data, partners.ctypes.data, y2.data_ptr(), order, K, B, D,
+                H, H, 1, code, 1, st()))
+            r["fwd_pair_us"] = round(timeit(f2, a.reps, flush), 1)
+            fb = (B * D * L) * (es + 4) + K * B * D * L * es + 2 * B * K * L * es
+            r["fwd_pair_gbs_fused"] = round(fb / r["fwd_pair_us"] / 1e3, 1)
+            tot["fwd_pair"] = tot.get("fwd_pair", 0.0) + calls * r["fwd_pair_us"]
+            if "fwd_v1_us" in r:
+                f1(), f2()
+                torch.cuda.synchronize()
+                r["y_rel_diff"] = float((y1 - y2).abs().max() / y1.abs().max())
         print(json.dumps(r), flush=True)
     print(json.dumps({"us_per_image_step_weighted_by_calls": {k: round(v, 1) for k, v in tot.items()}}), flush=True)
 

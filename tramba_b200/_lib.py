@@ -48,6 +48,9 @@ SIGNATURES = {
                               + [_i] * 9 + [_vp]),
     "tramba_order_sched_len": (ctypes.c_size_t, [_i, _i, _i, _i]),
     "tramba_order_sched": (_i, [_i, _i, _i, _i, _vp, _i32p]),
+    "tramba_order_pairs": (_i, [_i, _i, _i, _i, _i32p]),
+    "tramba_ss2d_fused_fwd_sched_supported": (_i, [_i] * 7),
+    "tramba_ss2d_fused_fwd_sched": (_i, [_vp, _vp, _vp, _vp, _fp, _fp, _fp, _vp, _i, _i32p, _i32p, _fp] + [_i] * 9 + [_vp]),
     "tramba_ss2d_fused_bwd_dx_supported": (_i, [_i] * 7),
     "tramba_ss2d_fused_bwd_dx": (_i, [_vp, _vp, _vp, _vp, _fp, _fp, _fp, _vp, _i, _i32p, _fp, _fp, _vp, _fp, _fp, _fp,
                                       _fp, _fp] + [_i] * 9 + [_vp]),

@@ -18,7 +18,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "_obj")
 LIB = os.path.join(HERE, "libtramba_b200.so")
-SOURCES = ["capi.cu", "sscan_fwd.cu", "sscan_bwd.cu", "ss2d_fused_fwd.cu", "ss2d_fused_bwd.cu", "ss2d_fused_bwd_dx.cu", "ss2d_fused_merge.cu", "cross_scan.cu",
+SOURCES = ["capi.cu", "sscan_fwd.cu", "sscan_bwd.cu", "ss2d_fused_fwd.cu", "ss2d_fused_fwd_pair.cu", "ss2d_fused_bwd.cu", "ss2d_fused_bwd_dx.cu", "ss2d_fused_merge.cu", "cross_scan.cu",
            "dct2d.cu", "dct2d_tc.cu", "layernorm2d.cu", "dwconv2d.cu", "proj_gather.cu", "orders.cpp"]
 HEADERS = ["common.cuh", "sscan.cuh", "ss2d_fused.cuh", os.path.join("..", "..", "include", "tramba_b200.h")]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")

@@ -452,6 +452,71 @@ extern "C" int tramba_ss2d_fused_bwd(const void* x, const void* dts, const void*
     return cuda_rc(e);
 }
 
+// Forward on the permutation schedule with direction pairing (ss2d_fused_fwd_pair.cu).
+extern "C" int tramba_ss2d_fused_fwd_sched_supported(int order, int K, int D, int H, int W, int N, int in_dtype) {
+    FusedArgs a;
+    std::memset(&a, 0, sizeof(a));
+    if (in_dtype != TRAMBA_F32 && in_dtype != TRAMBA_BF16) return 0;
+    if (fused_geometry(a, order, K, 1, D, H, W, N) != TRAMBA_OK) return 0;
+    return ss2d_fused_fwd_pair_fits(a.L, elem_size(in_dtype)) ? 1 : 0;
+}
+
+extern "C" int tramba_ss2d_fused_fwd_sched(const void* x, const void* dts, const void* Bs, const void* Cs,
+                                           const float* A, const float* Dp, const float* delta_bias,
+                                           const uint32_t* sched, int sched_len, const int32_t* kinds,
+                                           const int32_t* partners, float* y, int order, int K, int B, int D, int H,
+                                           int W, int N, int in_dtype, int delta_softplus, void* stream) {
+    if (!x || !dts || !Bs || !Cs || !A || !sched || !kinds || !partners || !y) return TRAMBA_E_NULL;
+    if (in_dtype != TRAMBA_F32 && in_dtype != TRAMBA_BF16) return TRAMBA_E_DTYPE;
+    FusedArgs g;
+    std::memset(&g, 0, sizeof(g));
+    int rc = fused_geometry(g, order, K, B, D, H, W, N);
+    if (rc != TRAMBA_OK) return rc;
+    if (K > 8) return TRAMBA_E_LIMIT;
+    if (!aligned(x, 16) || !aligned(dts, 16) || !aligned(Bs, 16) || !aligned(Cs, 16) || !aligned(y, 16) ||
+        !aligned(sched, 8))
+        return TRAMBA_E_ALIGN;
+    if (sched_len <= 0 || sched_len % (2 * g.TP) != 0 || sched_len % 64 != 0) return TRAMBA_E_SHAPE;
+    if (!ss2d_fused_fwd_pair_fits(g.L, elem_size(in_dtype))) return TRAMBA_E_LIMIT;
+    rc = check_device();
+    if (rc != TRAMBA_OK) return rc;
+    FusedFwdPairArgs a;
+    std::memset(&a, 0, sizeof(a));
+    a.x = x, a.dts = dts, a.Bs = Bs, a.Cs = Cs, a.A = A, a.Dp = Dp, a.bias = delta_bias, a.sched = sched, a.y = y;
+    a.B = B, a.K = K, a.D = D, a.sched_len = sched_len, a.softplus = delta_softplus ? 1 : 0;
+    // ---- the step list: identity-ordered groups first, then permutations, then tables with repeated pixels; inside
+    // a group the base direction, then the direction that reverses it
+    int n = 0, last_x_reader = -1;
+    for (int pass = 0; pass < 3; ++pass) {
+        for (int k = 0; k < K; ++k) {
+            if (kinds[k] < 0 || kinds[k] > 3 || partners[k] >= k) return TRAMBA_E_ORDER;
+            if (partners[k] >= 0) continue;  // a reversed member: emitted with its base
+            const int kind = kinds[k] == 1 ? 2 : kinds[k];  // a lone reversed identity is just a permutation
+            if ((pass == 0 && kind != 0) || (pass == 1 && kind != 2) || (pass == 2 && kind != 3)) continue;
+            int mate = -1;
+            for (int j = k + 1; j < K; ++j)
+                if (partners[j] == k) mate = j;
+            a.step_k[n] = static_cast<unsigned char>(k), a.step_base[n] = static_cast<unsigned char>(k);
+            a.step_rev[n] = 0, a.step_kind[n] = static_cast<unsigned char>(kind);
+            a.step_gather[n] = kind >= 2, a.step_merge[n] = mate < 0;
+            last_x_reader = n++;
+            if (mate >= 0) {
+                a.step_k[n] = static_cast<unsigned char>(mate), a.step_base[n] = static_cast<unsigned char>(k);
+                a.step_rev[n] = 1, a.step_kind[n] = static_cast<unsigned char>(kind);
+                a.step_gather[n] = 0, a.step_merge[n] = 1;
+                if (kind == 0) last_x_reader = n;  // identity pair: the reversed step reads the image planes too
+                ++n;
+            }
+        }
+    }
+    if (n != K || last_x_reader < 0) return TRAMBA_E_ORDER;
+    a.nsteps = n;
+    a.step_xfree[last_x_reader] = 1;
+    cudaError_t e = launch_ss2d_fused_fwd_pair(a, g.L, in_dtype, static_cast<cudaStream_t>(stream));
+    if (e == cudaErrorInvalidConfiguration) return TRAMBA_E_LIMIT;
+    return cuda_rc(e);
+}
+
 // Backward with dx: the merge of du (CrossScan*.backward, csms6s.py:25-31) happens inside the kernel.
 extern "C" int tramba_ss2d_fused_bwd_dx_supported(int order, int K, int D, int H, int W, int N, int in_dtype) {
     FusedArgs a;

@@ -26,6 +26,8 @@
 // The recurrence over a plane's L = TP*S tokens is a three-level scan: sequential fold in the
 // thread, shuffle scan over the warp, running combine over the TP/32 warps of the plane.
 #pragma once
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace tramba {
@@ -88,6 +90,35 @@ struct FusedDxArgs {
 };
 cudaError_t launch_ss2d_fused_bwd_dx(const FusedDxArgs& a, int L, int in_dtype, cudaStream_t st);
 bool ss2d_fused_bwd_dx_fits(int L, int es);
+
+// Forward on TMA-staged planes with direction pairing (ss2d_fused_fwd_pair.cu)
+struct FusedFwdPairArgs {
+    const void* x;          // (B, D, L) image order
+    const void* dts;        // (B, K, D, L) scan order
+    const void* Bs;         // (B, K, L)
+    const void* Cs;         // (B, K, L)
+    const float* A;         // (K*D)
+    const float* Dp;        // (K*D) or null
+    const float* bias;      // (K*D) or null
+    const uint32_t* sched;  // (K, sched_len) permutation schedule (tramba_order_sched), device
+    float* y;               // (B, D, L) fp32 image order, merged over the K directions
+    int B, K, D;
+    int sched_len;
+    int softplus;
+    // the K directions as a list of steps, grouped: a direction and (optionally) the one that reverses it share one
+    // token-ordered copy of the plane and their outputs are summed in registers before ONE merge into the image
+    int nsteps;
+    unsigned char step_k[8];       // direction of the step (delta / B / C / A rows come from it)
+    unsigned char step_base[8];    // direction whose table orders the tokens of the group (== step_k unless reversed)
+    unsigned char step_rev[8];     // 1: tokens of step_k are the base's tokens back to front
+    unsigned char step_kind[8];    // kind of the base table: 0 identity, 2 permutation, 3 with repeated pixels
+    unsigned char step_gather[8];  // 1: first step of a non-identity group -> gather the image into token order first
+    unsigned char step_merge[8];   // 1: last step of its group -> merge the summed outputs into the image plane
+    unsigned char step_xfree[8];   // 1: the image-ordered x planes are dead after this step's first barrier
+    FastDiv div_d;                 // / D
+};
+cudaError_t launch_ss2d_fused_fwd_pair(const FusedFwdPairArgs& a, int L, int in_dtype, cudaStream_t st);
+bool ss2d_fused_fwd_pair_fits(int L, int es);
 
 cudaError_t launch_ss2d_fused_fwd(const FusedArgs& a, int in_dtype, cudaStream_t st);
 cudaError_t launch_ss2d_fused_bwd(const FusedArgs& a, int in_dtype, cudaStream_t st);
@@ -204,6 +235,31 @@ __device__ __forceinline__ float lds_f32(const void* base, uint32_t off) {
 }
 __device__ __forceinline__ void sts_f32(void* base, uint32_t off, float v) {
     asm volatile("st.shared.f32 [%0], %1;" ::"r"(smem_u32(base) + off), "f"(v) : "memory");
+}
+
+// Walks this thread's entries of a permutation schedule (uint2 = two moves; stride TP between a thread's entries) in
+// batches of three loads, the next batch in flight while `move(dense, e0, e1, e2, count)` performs the current one.
+// DENSE: every entry is a move and the entry count is a multiple of three (permutations: sched_len == L).
+template <int TP, bool DENSE, typename Move>
+__device__ __forceinline__ void walk_schedule(const uint2* __restrict__ sc, int iters, Move&& move) {
+    const uint2 none = make_uint2(0xFFFFFFFFu, 0xFFFFFFFFu);
+    constexpr std::integral_constant<bool, DENSE> dense{};
+    int n = 0;
+    uint2 c0 = none, c1 = none, c2 = none;
+    if (iters >= 3) c0 = __ldg(sc), c1 = __ldg(sc + TP), c2 = __ldg(sc + 2 * TP);
+    for (; n + 3 <= iters; n += 3) {
+        sc += 3 * TP;
+        uint2 n0 = none, n1 = none, n2 = none;
+        if (n + 6 <= iters) n0 = __ldg(sc), n1 = __ldg(sc + TP), n2 = __ldg(sc + 2 * TP);
+        move(dense, c0, c1, c2, 3);
+        c0 = n0, c1 = n1, c2 = n2;
+    }
+    if (!DENSE && n < iters) {  // 1 or 2 left
+        const int cnt = iters - n;
+        c0 = __ldg(sc);
+        c1 = cnt > 1 ? __ldg(sc + TP) : none;
+        move(dense, c0, c1, none, cnt);
+    }
 }
 
 // Affine-map inclusive scan over `width` lanes (width = 32 or a power of two below).

@@ -55,31 +55,6 @@ struct DxLayout {
     static constexpr size_t total = bar + 8 * sizeof(uint64_t);
 };
 
-// Walks this thread's entries of a permutation schedule (uint2 = two moves; stride TP between a thread's entries) in
-// batches of three loads, the next batch in flight while `move(dense, e0, e1, e2, count)` performs the current one.
-// DENSE: every entry is a move and the entry count is a multiple of three (permutations: sched_len == L).
-template <int TP, bool DENSE, typename Move>
-__device__ __forceinline__ void walk_schedule(const uint2* __restrict__ sc, int iters, Move&& move) {
-    const uint2 none = make_uint2(0xFFFFFFFFu, 0xFFFFFFFFu);
-    constexpr std::integral_constant<bool, DENSE> dense{};
-    int n = 0;
-    uint2 c0 = none, c1 = none, c2 = none;
-    if (iters >= 3) c0 = __ldg(sc), c1 = __ldg(sc + TP), c2 = __ldg(sc + 2 * TP);
-    for (; n + 3 <= iters; n += 3) {
-        sc += 3 * TP;
-        uint2 n0 = none, n1 = none, n2 = none;
-        if (n + 6 <= iters) n0 = __ldg(sc), n1 = __ldg(sc + TP), n2 = __ldg(sc + 2 * TP);
-        move(dense, c0, c1, c2, 3);
-        c0 = n0, c1 = n1, c2 = n2;
-    }
-    if (!DENSE && n < iters) {  // 1 or 2 left
-        const int cnt = iters - n;
-        c0 = __ldg(sc);
-        c1 = cnt > 1 ? __ldg(sc + TP) : none;
-        move(dense, c0, c1, none, cnt);
-    }
-}
-
 template <typename in_t, bool SOFTPLUS, int TP, bool PIPE>
 __global__ void __launch_bounds__(NT, 1) ss2d_bwd_dx_kernel(const FusedDxArgs p) {
     extern __shared__ __align__(128) unsigned char smem[];

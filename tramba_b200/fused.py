@@ -80,6 +80,27 @@ def _sched(order, H, param, device):
     return hit
 
 
+_FWD_V1 = os.environ.get("TRAMBA_FUSED_FWD", "") == "v1"
+
+
+def _pairs(order, H, param):
+    key = ("pairs", order, H, param)
+    hit = _idx_cache.get(key)
+    if hit is None:
+        K = _lib.lib.tramba_order_num_directions(order)
+        hit = np.empty((K,), dtype=np.int32)
+        _lib.check(_lib.lib.tramba_order_pairs(order, H, H, param, hit.ctypes.data))
+        _idx_cache[key] = hit
+    return hit
+
+
+def fwd_sched_supported(order, K, D, H, W, N, dtype):
+    code = _DTYPE.get(dtype)
+    if code is None or H != W or _FWD_V1:
+        return False
+    return bool(_lib.lib.tramba_ss2d_fused_fwd_sched_supported(order, K, D, H, W, N, code))
+
+
 def bwd_dx_supported(order, K, D, H, W, N, dtype):
     code = _DTYPE.get(dtype)
     if code is None or H != W or _BWD_V1:
@@ -93,6 +114,8 @@ def supported(order, K, D, H, W, N, dtype, need_bwd=True):
         return False
     if need_bwd and bwd_dx_supported(order, K, D, H, W, N, dtype):
         need_bwd = False          # the merged backward covers it; only the forward's own limits remain
+    if not need_bwd and fwd_sched_supported(order, K, D, H, W, N, dtype):
+        return True
     return bool(_lib.lib.tramba_ss2d_fused_supported(order, K, D, H, W, N, code, int(need_bwd)))
 
 
@@ -122,6 +145,17 @@ class SS2DCoreFused(torch.autograd.Function):
         y = torch.empty((B, D, L), device=x.device, dtype=torch.float32)
         es = x.element_size()
         nbytes = (B * D * L) * (es + 4) + dts.numel() * es + 2 * Bs.numel() * es   # fused core
+        if fwd_sched_supported(order, K, D, H, W, 1, dt):
+            sched, kinds = _sched(order, H, param, x.device)
+            partners = _pairs(order, H, param)
+            with torch.cuda.device(x.device), _lib.timed("ss2d_fused_fwd", nbytes):
+                _lib.check(_lib.lib.tramba_ss2d_fused_fwd_sched(
+                    x.data_ptr(), dts.data_ptr(), Bs.data_ptr(), Cs.data_ptr(), A.data_ptr(), _ptr(Ds),
+                    _ptr(delta_bias), sched.data_ptr(), sched.shape[1], kinds.ctypes.data, partners.ctypes.data,
+                    y.data_ptr(), order, K, B, D, H, W, 1, _DTYPE[dt], int(bool(delta_softplus)), _stream()))
+            ctx.save_for_backward(x, dts, Bs, Cs, A, Ds, delta_bias, idx)
+            ctx.meta = (order, param, K, B, D, H, W, bool(delta_softplus))
+            return y
         with torch.cuda.device(x.device), _lib.timed("ss2d_fused_fwd", nbytes):
             _lib.check(_lib.lib.tramba_ss2d_fused_fwd(
                 x.data_ptr(), dts.data_ptr(), Bs.data_ptr(), Cs.data_ptr(), A.data_ptr(), _ptr(Ds),
