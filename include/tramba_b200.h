@@ -182,24 +182,26 @@ TRAMBA_API int tramba_ss2d_fused_fwd(const void* x, const void* dts, const void*
  * already summed over the K directions (zeroed here, accumulated with TMA bulk reductions); no du tensor exists.
  *   sched (K, sched_len) uint32, device: tramba_order_sched -- per direction a bank-conflict-free schedule of the
  *          shared-memory permutation image order <-> token order (entry = 2*pixel | 2*token << 16, 0xFFFFFFFF = none)
- *   kinds (K) int32, HOST: 0 identity, 1 reversed identity, 2 permutation, 3 table with repeated pixels
+ *   kinds (2K) int32, HOST, as tramba_order_sched writes them: [k] = 0 identity, 1 reversed identity, 2 permutation,
+ *          3 table with repeated pixels; [K + k] = schedule entries direction k uses (<= sched_len)
  *   dA_part, dD_part, dbias_part: here (K*D) fp32 TOTALS over the batch (zeroed here, added with reds) -- not
  *          per-batch partials as in tramba_ss2d_fused_bwd.  All zeroing uses one memset when dx, dBs, dCs, dA, dD,
  *          dbias are carved contiguously (in that order) out of one allocation.
  * tramba_order_sched_len: entries per direction (0 = unsupported size). */
 TRAMBA_API size_t tramba_order_sched_len(int order, int H, int W, int param);
 TRAMBA_API int tramba_order_sched(int order, int H, int W, int param, uint32_t* sched_out /* K*len, host */,
-                                  int32_t* kind_out /* K, host */);
+                                  int32_t* kind_out /* 2K, host */);
 /* Forward on the same schedule, with DIRECTION PAIRING: a direction and the one that reverses it (partners, from
  * tramba_order_pairs) share one token-ordered copy of the plane and one merge into the image; same inputs / output
- * as tramba_ss2d_fused_fwd.  kinds / partners: (K) int32 each, HOST. */
+ * as tramba_ss2d_fused_fwd.  kinds: (2K) int32 as above, partners: (K) int32, both HOST. */
 TRAMBA_API int tramba_order_pairs(int order, int H, int W, int param, int32_t* partner_out /* K, host */);
 TRAMBA_API int tramba_ss2d_fused_fwd_sched_supported(int order, int K, int D, int H, int W, int N, int in_dtype);
 TRAMBA_API int tramba_ss2d_fused_fwd_sched(const void* x, const void* dts, const void* Bs, const void* Cs,
                                            const float* A, const float* Dp, const float* delta_bias,
                                            const uint32_t* sched, int sched_len, const int32_t* kinds,
-                                           const int32_t* partners, float* y, int order, int K, int B, int D, int H,
-                                           int W, int N, int in_dtype, int delta_softplus, void* stream);
+                                           const int32_t* partners, const uint16_t* idx16 /* tramba_order_table16, device */,
+                                           float* y, int order, int K, int B, int D, int H, int W, int N, int in_dtype,
+                                           int delta_softplus, void* stream);
 TRAMBA_API int tramba_ss2d_fused_bwd_dx_supported(int order, int K, int D, int H, int W, int N, int in_dtype);
 TRAMBA_API int tramba_ss2d_fused_bwd_dx(const void* x, const void* dts, const void* Bs, const void* Cs,
                                         const float* A, const float* Dp, const float* delta_bias,
@@ -253,6 +255,10 @@ TRAMBA_API int tramba_dct2d_bwd(const float* ghigh, const float* glow, const flo
  * -------------------------------------------------------------------------------------- */
 TRAMBA_API int tramba_proj_gather(const void* src, void* dts, void* Bs, void* Cs, const int32_t* plan_dev, int K,
                                   int B, int R, int N, int L, int dtype, void* stream);
+/* out (n) = sum_b in (B, n), fp32 accumulation, same dtype in and out: the reduction over the image batch of the
+ * x_proj / dt_proj weight gradients, which the host evaluates as ONE batched GEMM dY_b . X_b^T (the reference's
+ * grouped conv1d weight gradient, Models/vmamba.py:233-236 backward).  in / out 16-byte aligned. */
+TRAMBA_API int tramba_batch_sum(const void* in, void* out, int B, long long n, int dtype, void* stream);
 TRAMBA_API int tramba_proj_scatter(const void* gdts, const void* gBs, const void* gCs, void* gsrc,
                                    const int32_t* plan_dev, int K, int B, int R, int N, int L, int dtype, int bc_dtype,
                                    void* stream);

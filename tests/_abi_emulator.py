@@ -163,6 +163,62 @@ def tramba_ss2d_fused_bwd(x, dts, Bs, Cs, A, Dp, bias, idx16, dy, du, ddts, dBs,
     return 0
 
 
+def _sched_table(sched, sched_len, K, L):
+    """(K, L) pixel of every token, recovered from the permutation schedule (entry = 2*pixel | 2*token << 16)."""
+    ent = np.ctypeslib.as_array((ctypes.c_uint32 * (K * sched_len)).from_address(sched)).reshape(K, sched_len)
+    tab = np.full((K, L), -1, dtype=np.int64)
+    for k in range(K):
+        e = ent[k][ent[k] != 0xFFFFFFFF].astype(np.int64)
+        tab[k, (e >> 16) >> 1] = (e & 0xFFFF) >> 1
+    assert (tab >= 0).all(), "schedule does not cover every token"
+    return tab
+
+
+def _sched_operands(x, dts, Bs, Cs, A, Dp, bias, sched, sched_len, K, B, D, H, W, dt):
+    L = H * W
+    tab = _sched_table(sched, sched_len, K, L)
+    xs = so.cross_scan(_buf(x, (B, D, H, W), dt).get(), tab).reshape(B, K * D, L)
+    return (tab, xs, _buf(dts, (B, K * D, L), dt).get(), _buf(A, (K * D, 1)).get(),
+            _buf(Bs, (B, K, 1, L), dt).get(), _buf(Cs, (B, K, 1, L), dt).get(), _get(_buf(Dp, (K * D,))),
+            _get(_buf(bias, (K * D,))))
+
+
+def tramba_ss2d_fused_fwd_sched(x, dts, Bs, Cs, A, Dp, bias, sched, sched_len, kinds, partners, idx16, y, order, K, B, D,
+                                H, W, N, in_dtype, softplus, stream):
+    assert N == 1
+    tab, xs, d, A_, B_, C_, D_, b_ = _sched_operands(x, dts, Bs, Cs, A, Dp, bias, sched, sched_len, K, B, D, H, W, in_dtype)
+    part = _i32(partners, K)
+    assert np.array_equal(_u16(idx16, K * H * W).reshape(K, H * W), tab)      # the plain table agrees with the schedule
+    for k in range(K):       # the pairing the kernel relies on: a partner's table is this one back to front
+        if part[k] >= 0:
+            assert np.array_equal(tab[k], tab[part[k]][::-1])
+    ys = osscan.selective_scan_fwd(xs, d, A_, B_, C_, D_, b_, bool(softplus)).reshape(B, K, D, H * W)
+    _buf(y, (B, D, H * W)).set(so.cross_merge(ys, tab, "custom"))
+    return 0
+
+
+def tramba_ss2d_fused_bwd_dx(x, dts, Bs, Cs, A, Dp, bias, sched, sched_len, kinds, dy, dx, ddts, dBs, dCs, dA, dD, dbias,
+                             order, K, B, D, H, W, N, in_dtype, softplus, stream):
+    assert N == 1
+    L = H * W
+    tab, xs, d, A_, B_, C_, D_, b_ = _sched_operands(x, dts, Bs, Cs, A, Dp, bias, sched, sched_len, K, B, D, H, W, in_dtype)
+    dys = so.cross_scan(_buf(dy, (B, D, H, W)).get(), tab).reshape(B, K * D, L)     # CrossMerge.backward
+    g = osscan.selective_scan_bwd(xs, d, A_, B_, C_, D_, b_, dys, bool(softplus))
+    _buf(dx, (B, D, L)).set(so.cross_merge(g[0].reshape(B, K, D, L), tab, "custom"))   # CrossScan.backward, folded in
+    _buf(ddts, (B, K * D, L), in_dtype).set(g[1])
+    _buf(dBs, (B, K, 1, L)).set(g[3])
+    _buf(dCs, (B, K, 1, L)).set(g[4])
+    for ptr, val in ((dA, g[2].reshape(-1)), (dD, g[5]), (dbias, g[6])):               # totals over the batch
+        if ptr:
+            _buf(ptr, (K * D,)).set(val)
+    return 0
+
+
+def tramba_batch_sum(src, out, B, n, dtype, stream):
+    _buf(out, (n,), dtype).set(_buf(src, (B, n), dtype).get().sum(0))
+    return 0
+
+
 def tramba_proj_gather(src, dts, Bs, Cs, plan, K, B, R, N, L, dtype, stream):
     tab = _i32(plan, K * L).reshape(K, L)
     s = _buf(src, (B, K, R + 2 * N, L), dtype).get()
@@ -251,7 +307,8 @@ def tramba_dct2d_bwd(ghigh, glow, wy, wx, gx, planes, H, W, stream):
 
 _EMULATED = {f.__name__: f for f in (
     tramba_cross_scan, tramba_cross_merge, tramba_cross_merge_skewed, tramba_sscan_fwd, tramba_sscan_bwd,
-    tramba_ss2d_fused_fwd, tramba_ss2d_fused_bwd, tramba_proj_gather, tramba_proj_scatter, tramba_layernorm2d_fwd,
+    tramba_ss2d_fused_fwd, tramba_ss2d_fused_bwd, tramba_ss2d_fused_fwd_sched, tramba_ss2d_fused_bwd_dx, tramba_batch_sum,
+    tramba_proj_gather, tramba_proj_scatter, tramba_layernorm2d_fwd,
     tramba_layernorm2d_bwd, tramba_layernorm2d_tiles, tramba_dwconv2d_fwd, tramba_dwconv2d_bwd, tramba_dct2d_fwd, tramba_dct2d_bwd)}
 
 

@@ -124,8 +124,8 @@ def main():
             y2 = torch.empty(B, D, L, device=dev)
             f2 = lambda: _lib.check(_lib.lib.tramba_ss2d_fused_fwd_sched(
                 x.data_ptr(), dts.data_ptr(), Bs.data_ptr(), Cs.data_ptr(), A.data_ptr(), Dp.data_ptr(), bias.data_ptr(),
-                sched.data_ptr(), sched.shape[1], kinds.ctypes.data, partners.ctypes.data, y2.data_ptr(), order, K, B, D,
-                H, H, 1, code, 1, st()))
+                sched.data_ptr(), sched.shape[1], kinds.ctypes.data, partners.ctypes.data,
+                fused._idx16_plain(order, H, param, dev).data_ptr(), y2.data_ptr(), order, K, B, D, H, H, 1, code, 1, st()))
             r["fwd_pair_us"] = round(timeit(f2, a.reps, flush), 1)
             fb = (B * D * L) * (es + 4) + K * B * D * L * es + 2 * B * K * L * es
             r["fwd_pair_gbs_fused"] = round(fb / r["fwd_pair_us"] / 1e3, 1)

@@ -36,6 +36,7 @@ cudaError_t launch_dct2d_fwd(const float* x, const float* wy, const float* wx, f
 cudaError_t launch_dct2d_bwd(const float* ghigh, const float* glow, const float* wy, const float* wx, float* gx,
                              int planes, int H, int W, cudaStream_t st);
 
+cudaError_t launch_batch_sum(const void* in, void* out, int B, long long n, int dtype, cudaStream_t st);
 bool ss2d_fused_bwd_fits(int L, int es, uint32_t dup_mask, int K);
 cudaError_t launch_merge_skewed(const void* ys, void* y, const uint16_t* idx, int K, int B, int D, int L,
                                 uint32_t dup_mask, int dtype, cudaStream_t st);
@@ -464,9 +465,10 @@ extern "C" int tramba_ss2d_fused_fwd_sched_supported(int order, int K, int D, in
 extern "C" int tramba_ss2d_fused_fwd_sched(const void* x, const void* dts, const void* Bs, const void* Cs,
                                            const float* A, const float* Dp, const float* delta_bias,
                                            const uint32_t* sched, int sched_len, const int32_t* kinds,
-                                           const int32_t* partners, float* y, int order, int K, int B, int D, int H,
-                                           int W, int N, int in_dtype, int delta_softplus, void* stream) {
-    if (!x || !dts || !Bs || !Cs || !A || !sched || !kinds || !partners || !y) return TRAMBA_E_NULL;
+                                           const int32_t* partners, const uint16_t* idx16, float* y, int order, int K,
+                                           int B, int D, int H, int W, int N, int in_dtype, int delta_softplus,
+                                           void* stream) {
+    if (!x || !dts || !Bs || !Cs || !A || !sched || !kinds || !partners || !idx16 || !y) return TRAMBA_E_NULL;
     if (in_dtype != TRAMBA_F32 && in_dtype != TRAMBA_BF16) return TRAMBA_E_DTYPE;
     FusedArgs g;
     std::memset(&g, 0, sizeof(g));
@@ -483,7 +485,14 @@ extern "C" int tramba_ss2d_fused_fwd_sched(const void* x, const void* dts, const
     FusedFwdPairArgs a;
     std::memset(&a, 0, sizeof(a));
     a.x = x, a.dts = dts, a.Bs = Bs, a.Cs = Cs, a.A = A, a.Dp = Dp, a.bias = delta_bias, a.sched = sched, a.y = y;
+    a.idx = idx16;
+    if (!aligned(idx16, 4)) return TRAMBA_E_ALIGN;
     a.B = B, a.K = K, a.D = D, a.sched_len = sched_len, a.softplus = delta_softplus ? 1 : 0;
+    for (int k = 0; k < K; ++k) {
+        const int used = kinds[K + k];
+        if (used <= 0 || used > sched_len || used % (2 * g.TP) != 0) return TRAMBA_E_SHAPE;
+        a.sched_used[k] = used;
+    }
     // ---- the step list: identity-ordered groups first, then permutations, then tables with repeated pixels; inside
     // a group the base direction, then the direction that reverses it
     int n = 0, last_x_reader = -1;
@@ -577,9 +586,13 @@ extern "C" int tramba_ss2d_fused_bwd_dx(const void* x, const void* dts, const vo
     a.dbias = dbias_part;
     a.B = B, a.K = K, a.D = D, a.sched_len = sched_len;
     a.kinds = 0;
+    if (K > 8) return TRAMBA_E_LIMIT;
     for (int k = 0; k < K; ++k) {
         if (kinds[k] < 0 || kinds[k] > 3) return TRAMBA_E_ORDER;
         a.kinds |= static_cast<uint32_t>(kinds[k]) << (4 * k);
+        const int used = kinds[K + k];
+        if (used <= 0 || used > sched_len || used % (2 * g.TP) != 0) return TRAMBA_E_SHAPE;
+        a.sched_used[k] = used;
     }
     a.softplus = delta_softplus ? 1 : 0;
     e = launch_ss2d_fused_bwd_dx(a, g.L, in_dtype, st);
@@ -686,6 +699,17 @@ extern "C" int tramba_proj_gather(const void* src, void* dts, void* Bs, void* Cs
     int rc = check_device();
     if (rc != TRAMBA_OK) return rc;
     return cuda_rc(launch_proj_gather(src, dts, Bs, Cs, plan_dev, K, B, R, N, L, dtype, static_cast<cudaStream_t>(stream)));
+}
+
+// Batch reduction of the projection weight gradients (Models/vmamba.py:233-236 backward): out (n) = sum_b in (B, n).
+extern "C" int tramba_batch_sum(const void* in, void* out, int B, long long n, int dtype, void* stream) {
+    if (!in || !out) return TRAMBA_E_NULL;
+    if (B <= 0 || n <= 0) return TRAMBA_E_SHAPE;
+    if (!ln_dtype_ok(dtype)) return TRAMBA_E_DTYPE;
+    if (!aligned(in, 16) || !aligned(out, 16)) return TRAMBA_E_ALIGN;
+    int rc = check_device();
+    if (rc != TRAMBA_OK) return rc;
+    return cuda_rc(launch_batch_sum(in, out, B, n, dtype, static_cast<cudaStream_t>(stream)));
 }
 
 extern "C" int tramba_proj_scatter(const void* gdts, const void* gBs, const void* gCs, void* gsrc,

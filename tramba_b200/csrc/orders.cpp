@@ -388,8 +388,9 @@ extern "C" int tramba_order_table(int order, int H, int W, int param, int32_t* i
 // Layout: blocks of 64 entries = two steps interleaved (entry 2 * lane + c of a block = step c of that block), since a
 // thread fetches two consecutive entries with one 8-byte load.  `len` (entries per direction, a multiple of
 // max(64, 2 * L / 18)) is common to all directions of the order.
-// kind[k]: 0 = identity (token t = pixel t: no permutation pass), 1 = reversed identity, 2 = permutation,
-//          3 = table with repeated pixels (the merge side needs atomic adds and a zeroed plane).
+// kind_out has 2K entries.  [k]: 0 = identity (token t = pixel t: no permutation pass), 1 = reversed identity,
+//          2 = permutation, 3 = table with repeated pixels (the merge side needs atomic adds and a zeroed plane);
+//          [K + k]: entries direction k uses (<= len, a multiple of the granule; == L for a permutation).
 namespace {
 
 int colour_tokens(const int32_t* idx, int L, std::vector<int>& colour) {
@@ -508,6 +509,9 @@ extern "C" int tramba_order_sched(int order, int H, int W, int param, uint32_t* 
         kind_out[k] = table_kind(idx, L);
         const int steps = colour_tokens(idx, L, colour);
         if (static_cast<size_t>(steps) * 32 > len) return TRAMBA_E_LIMIT;
+        // entries this direction really uses (the row stride `len` is the order's maximum): a permutation needs L
+        const size_t g = sched_granule(L);
+        kind_out[K + k] = static_cast<int32_t>((static_cast<size_t>(steps) * 32 + g - 1) / g * g);
         fill.assign(steps, 0);
         for (int e = 0; e < L; ++e) {
             const int s = colour[e], lane = fill[s]++;

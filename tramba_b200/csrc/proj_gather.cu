@@ -71,7 +71,54 @@ __global__ void __launch_bounds__(kThreads) proj_scatter_kernel(const T* __restr
     }
 }
 
+// out[n] = sum_b in[b][n] (fp32 accumulation): the batch reduction of the x_proj / dt_proj weight gradients
+// (dW = sum_b dY_b X_b^T is evaluated as one batched GEMM; B is the image batch, n = one weight tensor).  8 elements
+// per thread, 16-byte accesses; n % 8 == 0 and 16-byte aligned rows take the vector path.
+template <typename T>
+__global__ void __launch_bounds__(256) batch_sum_kernel(const T* __restrict__ in, T* __restrict__ out, int B, long long n) {
+    constexpr int V = 16 / sizeof(T);
+    const long long i0 = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) * V;
+    if (i0 >= n) return;
+    float acc[V];
+#pragma unroll
+    for (int v = 0; v < V; ++v) acc[v] = 0.f;
+    if (i0 + V <= n && (n % V) == 0) {
+        for (int b = 0; b < B; ++b) {
+            const uint4 q = *reinterpret_cast<const uint4*>(in + static_cast<long long>(b) * n + i0);
+            const T* h = reinterpret_cast<const T*>(&q);
+#pragma unroll
+            for (int v = 0; v < V; ++v) acc[v] += to_f32(h[v]);
+        }
+        uint4 o;
+        T* h = reinterpret_cast<T*>(&o);
+#pragma unroll
+        for (int v = 0; v < V; ++v) h[v] = from_f32<T>(acc[v]);
+        *reinterpret_cast<uint4*>(out + i0) = o;
+    } else {
+        for (int v = 0; v < V && i0 + v < n; ++v) {
+            float a = 0.f;
+            for (int b = 0; b < B; ++b) a += to_f32(in[static_cast<long long>(b) * n + i0 + v]);
+            out[i0 + v] = from_f32<T>(a);
+        }
+    }
+}
+
 }  // namespace
+
+cudaError_t launch_batch_sum(const void* in, void* out, int B, long long n, int dtype, cudaStream_t st) {
+    const int V = dtype == TRAMBA_F32 ? 4 : 8;
+    const long long threads = (n + V - 1) / V;
+    const int grid = static_cast<int>((threads + 255) / 256);
+    if (dtype == TRAMBA_F32)
+        batch_sum_kernel<float><<<grid, 256, 0, st>>>(static_cast<const float*>(in), static_cast<float*>(out), B, n);
+    else if (dtype == TRAMBA_BF16)
+        batch_sum_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(in),
+                                                              static_cast<__nv_bfloat16*>(out), B, n);
+    else
+        return cudaErrorInvalidValue;
+    note_launch();
+    return cudaGetLastError();
+}
 
 cudaError_t launch_proj_gather(const void* src, void* dts, void* Bs, void* Cs, const int32_t* plan, int K, int B, int R,
                                int N, int L, int dtype, cudaStream_t st) {

@@ -82,7 +82,8 @@ struct FusedDxArgs {
     float* dD;
     float* dbias;
     int B, K, D;
-    int sched_len;          // entries per direction
+    int sched_len;          // row stride of sched (entries)
+    int sched_used[8];      // entries direction k really uses (<= sched_len; == L for a permutation)
     uint32_t kinds;         // 4 bits per direction: 0 identity, 1 reversed identity, 2 permutation, 3 with repeats
     int softplus;
     int R;                  // rounds per item (set by the launcher)
@@ -101,9 +102,11 @@ struct FusedFwdPairArgs {
     const float* Dp;        // (K*D) or null
     const float* bias;      // (K*D) or null
     const uint32_t* sched;  // (K, sched_len) permutation schedule (tramba_order_sched), device
+    const uint16_t* idx;    // (K, L) pixel of every token (tramba_order_table16), device: merge of repeated-pixel orders
     float* y;               // (B, D, L) fp32 image order, merged over the K directions
     int B, K, D;
-    int sched_len;
+    int sched_len;          // row stride of sched (entries)
+    int sched_used[8];      // entries direction k really uses
     int softplus;
     // the K directions as a list of steps, grouped: a direction and (optionally) the one that reverses it share one
     // token-ordered copy of the plane and their outputs are summed in registers before ONE merge into the image

@@ -156,9 +156,9 @@ __global__ void __launch_bounds__(NT, 1) ss2d_bwd_dx_kernel(const FusedDxArgs p)
         const int kind = (p.kinds >> (4 * k)) & 15;  // 0 identity, 1 reversed identity, 2 permutation, 3 with repeats
         const bool perm = kind >= 2;
         const bool dup = kind == 3;
-        const bool dense = kind == 2 && p.sched_len == L;  // a permutation: every schedule entry is a move
+        const bool dense = kind == 2 && p.sched_used[k] == L;  // a permutation: every schedule entry is a move
         const uint2* __restrict__ sched = reinterpret_cast<const uint2*>(p.sched + static_cast<size_t>(k) * p.sched_len) + j;
-        const int sched_iters = p.sched_len / (2 * TP);
+        const int sched_iters = p.sched_used[k] / (2 * TP);
         mbar_wait(&barBC[0], static_cast<uint32_t>(it & 1));
         // dB / dC: this thread's tokens of direction k, (b, k) row of the (B, K, L) outputs
         float* const gdB = p.dBs + (static_cast<size_t>(b) * K + k) * L + j * S;

@@ -140,8 +140,15 @@ __global__ void __launch_bounds__(NT, 1) ss2d_fwd_pair_kernel(const FusedFwdPair
             if (DB && tid == 0 && sg + 1 < nstages) issue_dir(sg + 1);  // the other buffers: free since the last barrier
             const uint2* __restrict__ sched =
                 reinterpret_cast<const uint2*>(p.sched + static_cast<size_t>(p.step_base[st]) * p.sched_len) + j;
-            const int sched_iters = p.sched_len / (2 * TP);
-            const bool dense = kind == 2 && p.sched_len == L;
+            const int sched_used = p.sched_used[p.step_base[st]];
+            const int sched_iters = sched_used / (2 * TP);
+            const bool dense = kind == 2 && sched_used == L;
+            uint32_t pix[S / 2];  // kind 3: pixels of this thread's tokens (two 16-bit indices per word), fetched early
+            if (kind == 3) {
+                const uint32_t* tp = reinterpret_cast<const uint32_t*>(p.idx + static_cast<size_t>(p.step_base[st]) * L + j * S);
+#pragma unroll
+                for (int m = 0; m < S / 2; ++m) pix[m] = __ldg(tp + m);
+            }
             if (p.step_gather[st]) {
                 // ---- image order -> token order of the group's base direction
                 const in_t* xi = sX + static_cast<size_t>(q) * L;
@@ -271,24 +278,26 @@ __global__ void __launch_bounds__(NT, 1) ss2d_fwd_pair_kernel(const FusedFwdPair
                             reinterpret_cast<float2*>(yq)[mp] = make_float2(lo + ysum[2 * mp], hi + ysum[2 * mp + 1]);
                         }
                     }
-                } else {
-                    const bool dup = kind == 3;
-                    store_tokens<S>(sYt + static_cast<size_t>(q) * L + j * S, ysum);
-                    if (dup && first_merge) {  // (no order of the reference starts with such a group)
+                } else if (kind == 3) {
+                    // repeated pixels (helix lines): every token is added to its pixel straight from the registers
+                    // with a shared-memory atomic; the pixel of each token comes from the plain order table
+                    float* yo = sY + static_cast<size_t>(q) * L;
+                    if (first_merge) {  // (no order of the reference starts with such a group)
                         float4* z = reinterpret_cast<float4*>(sY);
                         for (int e = tid; e < TOK / 4; e += NT) z[e] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        __syncthreads();
                     }
+#pragma unroll
+                    for (int mp = 0; mp < S / 2; ++mp) {
+                        atomicAdd(yo + (pix[mp] & 0xFFFFu), ysum[2 * mp]);
+                        atomicAdd(yo + (pix[mp] >> 16), ysum[2 * mp + 1]);
+                    }
+                } else {
+                    store_tokens<S>(sYt + static_cast<size_t>(q) * L + j * S, ysum);
                     __syncthreads();  // token-ordered outputs complete
                     const float* yi = sYt + static_cast<size_t>(q) * L;
                     float* yo = sY + static_cast<size_t>(q) * L;
-                    if (dup) {
-                        const uint2* sc = sched;
-                        for (int n = 0; n < sched_iters; ++n, sc += TP) {
-                            const uint2 e2 = __ldg(sc);
-                            if (e2.x != 0xFFFFFFFFu) atomicAdd(yo + ((e2.x & 0xFFFFu) >> 1), yi[e2.x >> 17]);
-                            if (e2.y != 0xFFFFFFFFu) atomicAdd(yo + ((e2.y & 0xFFFFu) >> 1), yi[e2.y >> 17]);
-                        }
-                    } else {
+                    {
                         const bool init = first_merge;
                         auto move = [&](auto dense_tag, const uint2 ea, const uint2 eb, const uint2 ec, int cnt)
                                         __attribute__((always_inline)) {

@@ -48,6 +48,16 @@ def _idx16(order, H, param, device):
     return hit
 
 
+def _idx16_plain(order, H, param, device):
+    """Device (K, L) uint16 table: pixel of every token (unskewed), bit-exact with the reference generators."""
+    key = ("plain16", order, H, param, device)
+    hit = _idx_cache.get(key)
+    if hit is None:
+        hit = torch.from_numpy(order_table16_host(order, H, param).view(np.int16)).to(device)
+        _idx_cache[key] = hit
+    return hit
+
+
 def token_index(order, H, param, device):
     """(K, L) int64 pixel index of every token (for gathering small per-token tensors into scan order)."""
     key = ("i64", order, H, param, device)
@@ -73,7 +83,7 @@ def _sched(order, H, param, device):
         if n == 0:
             raise RuntimeError("tramba_b200: no permutation schedule for this order / size")
         t = np.empty((K, n), dtype=np.uint32)
-        kinds = np.empty((K,), dtype=np.int32)
+        kinds = np.empty((2 * K,), dtype=np.int32)       # K kinds, then K used lengths
         _lib.check(_lib.lib.tramba_order_sched(order, H, H, param, t.ctypes.data, kinds.ctypes.data))
         hit = (torch.from_numpy(t.view(np.int32)).to(device), kinds)
         _idx_cache[key] = hit
@@ -152,7 +162,8 @@ class SS2DCoreFused(torch.autograd.Function):
                 _lib.check(_lib.lib.tramba_ss2d_fused_fwd_sched(
                     x.data_ptr(), dts.data_ptr(), Bs.data_ptr(), Cs.data_ptr(), A.data_ptr(), _ptr(Ds),
                     _ptr(delta_bias), sched.data_ptr(), sched.shape[1], kinds.ctypes.data, partners.ctypes.data,
-                    y.data_ptr(), order, K, B, D, H, W, 1, _DTYPE[dt], int(bool(delta_softplus)), _stream()))
+                    _idx16_plain(order, H, param, x.device).data_ptr(), y.data_ptr(), order, K, B, D, H, W, 1,
+                    _DTYPE[dt], int(bool(delta_softplus)), _stream()))
             ctx.save_for_backward(x, dts, Bs, Cs, A, Ds, delta_bias, idx)
             ctx.meta = (order, param, K, B, D, H, W, bool(delta_softplus))
             return y
@@ -273,3 +284,64 @@ class ProjGather(torch.autograd.Function):
 
 def proj_gather(src, order, param, H, R, N):
     return ProjGather.apply(src, order, param, H, R, N)
+
+
+def _batch_sum(t):
+    """(B, ...) -> (...): sum over the leading (image batch) axis on the library's kernel (fp32 accumulation)."""
+    t = _c16(t)
+    out = torch.empty(t.shape[1:], device=t.device, dtype=t.dtype)
+    with torch.cuda.device(t.device), _lib.timed("batch_sum", t.numel() * t.element_size()):
+        _lib.check(_lib.lib.tramba_batch_sum(t.data_ptr(), out.data_ptr(), t.shape[0], out.numel(), _DTYPE[t.dtype],
+                                             _stream()))
+    return out
+
+
+class ProjX(torch.autograd.Function):
+    """x_proj on the image-ordered map as ONE GEMM per image: Y (B, M, L) = W (M, D) @ X (B, D, L)
+    (Models/vmamba.py:233-234 evaluated before the gather).  Same products as torch.bmm on the expanded
+    weight; the weight gradient sum_b dY_b X_b^T is one batched GEMM + the library's batch reduction instead of
+    autograd's generic reduce over the expanded dimension."""
+
+    @staticmethod
+    @torch.amp.custom_fwd(device_type="cuda", cast_inputs=None)
+    def forward(ctx, W, X):
+        if torch.is_autocast_enabled():
+            dt = torch.get_autocast_dtype("cuda")
+            W, X = W.to(dt), X.to(dt)
+        ctx.save_for_backward(W, X)
+        with torch.autocast("cuda", enabled=False):
+            return torch.bmm(W.unsqueeze(0).expand(X.shape[0], -1, -1), X)
+
+    @staticmethod
+    @torch.amp.custom_bwd(device_type="cuda")
+    def backward(ctx, dY):
+        W, X = ctx.saved_tensors
+        dY = dY.to(X.dtype)
+        B = X.shape[0]
+        dX = torch.bmm(W.t().unsqueeze(0).expand(B, -1, -1), dY) if ctx.needs_input_grad[1] else None
+        dW = _batch_sum(torch.bmm(dY, X.transpose(1, 2))) if ctx.needs_input_grad[0] else None
+        return dW, dX
+
+
+class ProjDt(torch.autograd.Function):
+    """dt_proj per direction: Y (B, K, D, L) = W (K, D, R) @ X (B, K, R, L) (Models/vmamba.py:236); weight gradient as
+    in ProjX."""
+
+    @staticmethod
+    @torch.amp.custom_fwd(device_type="cuda", cast_inputs=None)
+    def forward(ctx, W, X):
+        if torch.is_autocast_enabled():
+            dt = torch.get_autocast_dtype("cuda")
+            W, X = W.to(dt), X.to(dt)
+        ctx.save_for_backward(W, X)
+        with torch.autocast("cuda", enabled=False):
+            return torch.matmul(W, X)
+
+    @staticmethod
+    @torch.amp.custom_bwd(device_type="cuda")
+    def backward(ctx, dY):
+        W, X = ctx.saved_tensors
+        dY = dY.to(X.dtype)
+        dX = torch.matmul(W.transpose(1, 2), dY) if ctx.needs_input_grad[1] else None
+        dW = _batch_sum(torch.matmul(dY, X.transpose(2, 3))) if ctx.needs_input_grad[0] else None
+        return dW, dX

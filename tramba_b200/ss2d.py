@@ -202,7 +202,7 @@ class SS2D(nn.Module):
         L = H * W
         xf = x.contiguous().view(B, D, L)
         if _PROJ_GEMM:
-            x_dbl = torch.bmm(self.x_proj_weight.view(1, -1, D).expand(B, -1, -1), xf).view(B, K, R + 2 * N, L)
+            x_dbl = fused.ProjX.apply(self.x_proj_weight.view(-1, D), xf).view(B, K, R + 2 * N, L)
         else:
             x_dbl = F.conv1d(xf, self.x_proj_weight.view(-1, D, 1), bias=None).view(B, K, R + 2 * N, L)
         if _PROJ_KERNEL:    # one kernel: image -> scan order + split (contiguous dts_r, Bs, Cs)
@@ -212,7 +212,7 @@ class SS2D(nn.Module):
             x_dbl = x_dbl.gather(3, tok.view(1, K, 1, L).expand(B, K, R + 2 * N, L))  # image -> scan order
             dts, Bs, Cs = torch.split(x_dbl, [R, N, N], dim=2)
         if _PROJ_GEMM:
-            dts = torch.matmul(self.dt_projs_weight, dts)                        # (K, D, R) @ (B, K, R, L)
+            dts = fused.ProjDt.apply(self.dt_projs_weight, dts)                  # (K, D, R) @ (B, K, R, L)
         else:
             dts = F.conv1d(dts.contiguous().view(B, -1, L), self.dt_projs_weight.view(K * D, -1, 1), groups=K)
         As = -torch.exp(self.A_logs.to(torch.float)).view(-1)
