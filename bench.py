@@ -210,10 +210,7 @@ def summarize_prof(prof):
 
 
 # kernel-name fragment -> the `kind` tramba_b200._lib.timed records for it
-KIND_OF = {"ss2d_bwd_dx_kernel": "ss2d_fused_bwd", "ss2d_bwd_kernel": "ss2d_fused_bwd", "ss2d_fwd_kernel": "ss2d_fused_fwd", "merge_skewed_kernel": "cross_merge_skewed",
-           # the compile-time-geometry candidates (TRAMBA_B200_LIB=next) report under the same kinds
-           "ss2d_bwd_cg_kernel": "ss2d_fused_bwd", "ss2d_fwd_cg_kernel": "ss2d_fused_fwd",
-           "merge_skewed_cg_kernel": "cross_merge_skewed",
+KIND_OF = {"ss2d_bwd_kernel": "ss2d_fused_bwd", "ss2d_fwd_kernel": "ss2d_fused_fwd", "batch_sum": "batch_sum",
            "ln2d_fwd": "layernorm2d_fwd", "ln2d_bwd": "layernorm2d_bwd", "dct2d_fwd": "dct2d_fwd", "dct2d_bwd": "dct2d_bwd",
            "proj_gather": "proj_gather", "proj_scatter": "proj_scatter", "dwconv_fwd": "dwconv_fwd", "dwconv_bwd": "dwconv_bwd",
            "sscan_fwd": "sscan_fwd", "sscan_bwd": "sscan_bwd", "cross_scan_kernel": "cross_scan", "cross_merge": "cross_merge"}

@@ -158,71 +158,43 @@ TRAMBA_API int tramba_sscan_bwd(const void* u, const void* delta, const float* A
  *                           (tramba_order_table16_skewed; tramba_order_table16 is the plain table,
  *                           bit-exact with the reference generators)
  *   y      (B, D, L)        fp32       IMAGE order, merged over the K directions (oflex=True contract)
- * Supported: order STD / DILATION / WINDOW / LINE, N == 1, L = 18 * 2^m <= 9216 (H = 12, 24, 48,
- * 96), D a multiple of 512*18/L, and shared-memory fit (tramba_ss2d_fused_supported says which;
- * everything else runs through the un-fused entry points above).  Helix-line directions add
- * duplicate hits of a pixel with shared-memory fp32 atomics, so their merged sums are
- * order-nondeterministic at rounding level, like the reference's CUDA scatter_add_.
- * Backward: dy (B, D, L) fp32 image order in; du (B, K, D, L) in_dtype, scan order = the gradient
- * w.r.t. xs (the caller folds it back with tramba_cross_merge: dx = CrossScan.backward(du));
- * ddts (B, K, D, L) in_dtype scan order; dBs, dCs (B, K, L) fp32 (zeroed here, accumulated over
- * channels with vector reds); dA_part, dD_part, dbias_part (B, K*D) fp32 partial sums over L
- * (the caller sums over B; no atomics).
+ * Supported: order STD / DILATION / WINDOW / LINE, N == 1, L in {144, 576, 2304, 9216} (H = 12, 24, 48, 96 -- every
+ * Tramba-V map at 384^2), D a multiple of 512*18/L, and shared-memory fit (tramba_ss2d_fused_supported says which;
+ * the backward in fp32 at L = 9216 does not fit and, like everything else, runs through the un-fused entry points
+ * above).  Helix-line directions add duplicate hits of a pixel with shared-memory fp32 atomics, so their merged
+ * sums are order-nondeterministic at rounding level, like the reference's CUDA scatter_add_.
+ *
+ * Backward = CrossMerge*.backward -> SelectiveScanOflex.backward -> CrossScan*.backward (csms6s.py:45-55, 914-923,
+ * 25-31) in ONE kernel: dy (B, D, L) fp32 image order in; dx (B, D, L) fp32 IMAGE order out, already summed over the
+ * K directions (TMA bulk reductions at L2) -- the K-fold gradient du w.r.t. xs never exists in HBM;
+ * ddts (B, K, D, L) in_dtype scan order; dBs, dCs (B, K, L) fp32 (vector reds over the channels);
+ * dA, dD, dbias (K*D) fp32 TOTALS over batch and tokens (reds).  Every fp32 output is an accumulation target and is
+ * zeroed here -- with one memset when dx, dBs, dCs, dA, dD, dbias are carved contiguously, in that order, out of one
+ * allocation.
+ *   sched (K, sched_len) uint32, device: tramba_order_sched -- per direction a bank-conflict-free schedule of the
+ *          shared-memory permutation image order <-> token order (entry = 2*pixel | 2*token << 16, 0xFFFFFFFF = none);
+ *          tramba_order_sched_len = entries per direction (row stride; 0 = unsupported size)
+ *   kinds (2K) int32, HOST, as tramba_order_sched writes them: [k] = 0 identity, 1 reversed identity, 2 permutation,
+ *          3 table with repeated pixels; [K + k] = schedule entries direction k uses (<= sched_len)
  * -------------------------------------------------------------------------------------- */
 TRAMBA_API int tramba_order_table16(int order, int H, int W, int param, uint16_t* idx_out /* K*L, host */);
 TRAMBA_API int tramba_order_table16_skewed(int order, int H, int W, int param, uint16_t* idx_out /* K*L, host */);
+TRAMBA_API size_t tramba_order_sched_len(int order, int H, int W, int param);
+TRAMBA_API int tramba_order_sched(int order, int H, int W, int param, uint32_t* sched_out /* K*len, host */,
+                                  int32_t* kind_out /* 2K, host */);
 TRAMBA_API int tramba_ss2d_fused_supported(int order, int K, int D, int H, int W, int N, int in_dtype,
                                            int need_bwd);
 TRAMBA_API int tramba_ss2d_fused_fwd(const void* x, const void* dts, const void* Bs, const void* Cs,
                                      const float* A, const float* Dp, const float* delta_bias,
                                      const uint16_t* idx16, float* y, int order, int K, int B, int D, int H,
                                      int W, int N, int in_dtype, int delta_softplus, void* stream);
-/* Backward with the merge of du folded in (replaces CrossMerge*.backward -> SelectiveScanOflex.backward ->
- * CrossScan*.backward, csms6s.py:45-55, 914-923, 25-31, in ONE kernel): dx (B, D, L) fp32 IMAGE order comes back
- * already summed over the K directions (zeroed here, accumulated with TMA bulk reductions); no du tensor exists.
- *   sched (K, sched_len) uint32, device: tramba_order_sched -- per direction a bank-conflict-free schedule of the
- *          shared-memory permutation image order <-> token order (entry = 2*pixel | 2*token << 16, 0xFFFFFFFF = none)
- *   kinds (2K) int32, HOST, as tramba_order_sched writes them: [k] = 0 identity, 1 reversed identity, 2 permutation,
- *          3 table with repeated pixels; [K + k] = schedule entries direction k uses (<= sched_len)
- *   dA_part, dD_part, dbias_part: here (K*D) fp32 TOTALS over the batch (zeroed here, added with reds) -- not
- *          per-batch partials as in tramba_ss2d_fused_bwd.  All zeroing uses one memset when dx, dBs, dCs, dA, dD,
- *          dbias are carved contiguously (in that order) out of one allocation.
- * tramba_order_sched_len: entries per direction (0 = unsupported size). */
-TRAMBA_API size_t tramba_order_sched_len(int order, int H, int W, int param);
-TRAMBA_API int tramba_order_sched(int order, int H, int W, int param, uint32_t* sched_out /* K*len, host */,
-                                  int32_t* kind_out /* 2K, host */);
-/* Forward on the same schedule, with DIRECTION PAIRING: a direction and the one that reverses it (partners, from
- * tramba_order_pairs) share one token-ordered copy of the plane and one merge into the image; same inputs / output
- * as tramba_ss2d_fused_fwd.  kinds: (2K) int32 as above, partners: (K) int32, both HOST. */
-TRAMBA_API int tramba_order_pairs(int order, int H, int W, int param, int32_t* partner_out /* K, host */);
-TRAMBA_API int tramba_ss2d_fused_fwd_sched_supported(int order, int K, int D, int H, int W, int N, int in_dtype);
-TRAMBA_API int tramba_ss2d_fused_fwd_sched(const void* x, const void* dts, const void* Bs, const void* Cs,
-                                           const float* A, const float* Dp, const float* delta_bias,
-                                           const uint32_t* sched, int sched_len, const int32_t* kinds,
-                                           const int32_t* partners, const uint16_t* idx16 /* tramba_order_table16, device */,
-                                           float* y, int order, int K, int B, int D, int H, int W, int N, int in_dtype,
-                                           int delta_softplus, void* stream);
-TRAMBA_API int tramba_ss2d_fused_bwd_dx_supported(int order, int K, int D, int H, int W, int N, int in_dtype);
-TRAMBA_API int tramba_ss2d_fused_bwd_dx(const void* x, const void* dts, const void* Bs, const void* Cs,
-                                        const float* A, const float* Dp, const float* delta_bias,
-                                        const uint32_t* sched, int sched_len, const int32_t* kinds,
-                                        const float* dy, float* dx, void* ddts, float* dBs, float* dCs,
-                                        float* dA_part, float* dD_part, float* dbias_part, int order, int K, int B,
-                                        int D, int H, int W, int N, int in_dtype, int delta_softplus,
-                                        void* stream);
 TRAMBA_API int tramba_ss2d_fused_bwd(const void* x, const void* dts, const void* Bs, const void* Cs,
                                      const float* A, const float* Dp, const float* delta_bias,
-                                     const uint16_t* idx16, const float* dy, void* du, void* ddts, float* dBs,
-                                     float* dCs, float* dA_part, float* dD_part, float* dbias_part, int order,
-                                     int K, int B, int D, int H, int W, int N, int in_dtype, int delta_softplus,
+                                     const uint32_t* sched, int sched_len, const int32_t* kinds,
+                                     const float* dy, float* dx, void* ddts, float* dBs, float* dCs,
+                                     float* dA, float* dD, float* dbias, int order, int K, int B,
+                                     int D, int H, int W, int N, int in_dtype, int delta_softplus,
                                      void* stream);
-
-/* Cross-merge through the skewed table (same shape limits as the fused core): y (B, D, L) =
- * fold of ys (B, K, D, L), fp32 accumulation in direction order k = 0..K-1, shared-memory atomics for
- * duplicate pixels (helix lines).  Same sums as tramba_cross_merge up to fp32 association order;
- * used by the fused backward for dx = CrossScan*.backward(du) (csms6s.py:25-31,75-80,124-129,175-185). */
-TRAMBA_API int tramba_cross_merge_skewed(const void* ys, void* y, const uint16_t* idx16, int order, int K, int B,
-                                         int D, int H, int W, int dtype, void* stream);
 
 /* ----------------------------------------------------------------------------------------
  * DCT2D high/low split.  Replaces DCT2D.forward (Models/DCT_2D.py:12-29) and the two basis

@@ -91,13 +91,6 @@ def tramba_cross_merge(ys, y, plan, order, K, B, D, H, W, dtype, stream):
     return 0
 
 
-def tramba_cross_merge_skewed(ys, y, idx16, order, K, B, D, H, W, dtype, stream):
-    L = H * W
-    tab = _unskew(_u16(idx16, K * L)).reshape(K, L)
-    _buf(y, (B, D, L), dtype).set(so.cross_merge(_buf(ys, (B, K, D, L), dtype).get(), tab, "custom"))
-    return 0
-
-
 def tramba_sscan_fwd(u, delta, A, Bm, Cm, D, bias, out, ckpt, batch, dim, L, N, groups, in_dtype, out_dtype,
                      softplus, stream):
     o = osscan.selective_scan_fwd(_buf(u, (batch, dim, L), in_dtype).get(), _buf(delta, (batch, dim, L), in_dtype).get(),
@@ -143,26 +136,6 @@ def tramba_ss2d_fused_fwd(x, dts, Bs, Cs, A, Dp, bias, idx16, y, order, K, B, D,
     return 0
 
 
-def tramba_ss2d_fused_bwd(x, dts, Bs, Cs, A, Dp, bias, idx16, dy, du, ddts, dBs, dCs, dA_part, dD_part, dbias_part,
-                          order, K, B, D, H, W, N, in_dtype, softplus, stream):
-    assert N == 1
-    L = H * W
-    tab, xs, d, A_, B_, C_, D_, b_ = _fused_operands(x, dts, Bs, Cs, A, Dp, bias, idx16, K, B, D, H, W, in_dtype)
-    dys = so.cross_scan(_buf(dy, (B, D, H, W)).get(), tab).reshape(B, K * D, L)     # CrossMerge.backward
-    g = osscan.selective_scan_bwd(xs, d, A_, B_, C_, D_, b_, dys, bool(softplus))
-    _buf(du, (B, K * D, L), in_dtype).set(g[0])
-    _buf(ddts, (B, K * D, L), in_dtype).set(g[1])
-    _buf(dBs, (B, K, 1, L)).set(g[3])
-    _buf(dCs, (B, K, 1, L)).set(g[4])
-    # per-(b, row) partials that the caller sums over b: put the whole sum in row b = 0
-    for ptr, val in ((dA_part, g[2].reshape(-1)), (dD_part, g[5]), (dbias_part, g[6])):
-        if ptr:
-            part = np.zeros((B, K * D))
-            part[0] = val
-            _buf(ptr, (B, K * D)).set(part)
-    return 0
-
-
 def _sched_table(sched, sched_len, K, L):
     """(K, L) pixel of every token, recovered from the permutation schedule (entry = 2*pixel | 2*token << 16)."""
     ent = np.ctypeslib.as_array((ctypes.c_uint32 * (K * sched_len)).from_address(sched)).reshape(K, sched_len)
@@ -183,21 +156,7 @@ def _sched_operands(x, dts, Bs, Cs, A, Dp, bias, sched, sched_len, K, B, D, H, W
             _get(_buf(bias, (K * D,))))
 
 
-def tramba_ss2d_fused_fwd_sched(x, dts, Bs, Cs, A, Dp, bias, sched, sched_len, kinds, partners, idx16, y, order, K, B, D,
-                                H, W, N, in_dtype, softplus, stream):
-    assert N == 1
-    tab, xs, d, A_, B_, C_, D_, b_ = _sched_operands(x, dts, Bs, Cs, A, Dp, bias, sched, sched_len, K, B, D, H, W, in_dtype)
-    part = _i32(partners, K)
-    assert np.array_equal(_u16(idx16, K * H * W).reshape(K, H * W), tab)      # the plain table agrees with the schedule
-    for k in range(K):       # the pairing the kernel relies on: a partner's table is this one back to front
-        if part[k] >= 0:
-            assert np.array_equal(tab[k], tab[part[k]][::-1])
-    ys = osscan.selective_scan_fwd(xs, d, A_, B_, C_, D_, b_, bool(softplus)).reshape(B, K, D, H * W)
-    _buf(y, (B, D, H * W)).set(so.cross_merge(ys, tab, "custom"))
-    return 0
-
-
-def tramba_ss2d_fused_bwd_dx(x, dts, Bs, Cs, A, Dp, bias, sched, sched_len, kinds, dy, dx, ddts, dBs, dCs, dA, dD, dbias,
+def tramba_ss2d_fused_bwd(x, dts, Bs, Cs, A, Dp, bias, sched, sched_len, kinds, dy, dx, ddts, dBs, dCs, dA, dD, dbias,
                              order, K, B, D, H, W, N, in_dtype, softplus, stream):
     assert N == 1
     L = H * W
@@ -306,8 +265,8 @@ def tramba_dct2d_bwd(ghigh, glow, wy, wx, gx, planes, H, W, stream):
 
 
 _EMULATED = {f.__name__: f for f in (
-    tramba_cross_scan, tramba_cross_merge, tramba_cross_merge_skewed, tramba_sscan_fwd, tramba_sscan_bwd,
-    tramba_ss2d_fused_fwd, tramba_ss2d_fused_bwd, tramba_ss2d_fused_fwd_sched, tramba_ss2d_fused_bwd_dx, tramba_batch_sum,
+    tramba_cross_scan, tramba_cross_merge, tramba_sscan_fwd, tramba_sscan_bwd,
+    tramba_ss2d_fused_fwd, tramba_ss2d_fused_bwd, tramba_batch_sum,
     tramba_proj_gather, tramba_proj_scatter, tramba_layernorm2d_fwd,
     tramba_layernorm2d_bwd, tramba_layernorm2d_tiles, tramba_dwconv2d_fwd, tramba_dwconv2d_bwd, tramba_dct2d_fwd, tramba_dct2d_bwd)}
 
@@ -337,7 +296,7 @@ class _SimLib:
     """The product's C ABI exported by tools/cpu_sim's library: the REAL entry points (capi.cu) and the REAL kernels
     (every .cu of the library), compiled as host code and executed on the CPU simulator."""
 
-    def __init__(self, sms=4, next_variant=False):
+    def __init__(self, sms=4):
         import importlib.util
         import os
         from tramba_b200 import _lib
@@ -347,7 +306,7 @@ class _SimLib:
         spec.loader.exec_module(mod)
         import os as _os
         asan = _os.environ.get("TRAMBA_SIM_ASAN", "") == "1"          # AddressSanitizer build (needs libasan preloaded)
-        self._dll = ctypes.CDLL(mod.build(next_variant=next_variant and not asan, asan=asan))
+        self._dll = ctypes.CDLL(mod.build(asan=asan))
         for name, (res, args) in _lib.SIGNATURES.items():
             fn = getattr(self._dll, name)
             fn.restype, fn.argtypes = res, args
@@ -374,11 +333,10 @@ class _SimLib:
 def installed(backend="oracle", sms=4):
     """Within this scope the product's Python host runs on CPU tensors against
       backend="oracle": the compute entry points emulated by the oracle (fast; checks the host logic only), or
-      backend="sim":    the product's own C ABI and kernels executed on the CPU simulator (tools/cpu_sim);
-      backend="sim-next": the same with -DTRAMBA_NEXT, i.e. dispatching to the candidate kernels of csrc/next/."""
+      backend="sim":    the product's own C ABI and kernels executed on the CPU simulator (tools/cpu_sim)."""
     from tramba_b200 import _lib
     saved = (_lib.lib, torch.Tensor.cuda, torch.nn.Module.cuda, torch.cuda.current_stream, torch.cuda.device)
-    proxy = _Proxy(_lib.lib) if backend == "oracle" else _SimLib(sms, next_variant=(backend == "sim-next"))
+    proxy = _Proxy(_lib.lib) if backend == "oracle" else _SimLib(sms)
     _lib.lib = proxy
     torch.Tensor.cuda = lambda self, *a, **k: self.clone()        # like the real one: a new tensor, differentiable
     torch.nn.Module.cuda = lambda self, *a, **k: self

@@ -39,12 +39,11 @@ def golden_ablation():
 # on the CPU simulator (tools/cpu_sim; tests/_abi_emulator.py: installed("sim")).  "cuda" devices are mapped to the
 # CPU for the session.  Meant for the small / medium cases (`-k ...`): BASELINE-size tests take minutes to hours there.
 #     TRAMBA_GPU_TESTS_ON_SIM=1 python -m pytest tests/test_z_gpu_ablation.py -m gpu -q
-#     TRAMBA_GPU_TESTS_ON_SIM=next ...      the same with the candidate kernels of csrc/next/ dispatched (-DTRAMBA_NEXT)
 # ----------------------------------------------------------------------------------------------------------------
 @pytest.fixture(scope="session", autouse=True)
 def _gpu_tests_on_the_simulator():
     mode = os.environ.get("TRAMBA_GPU_TESTS_ON_SIM", "")
-    if mode not in ("1", "next"):
+    if mode != "1":
         yield
         return
     import functools
@@ -81,7 +80,7 @@ def _gpu_tests_on_the_simulator():
 
     torch.Tensor.to = to
     torch.cuda.synchronize = lambda *a, **k: None
-    with installed("sim-next" if mode == "next" else "sim", sms=4):     # "next": the candidate kernels (csrc/next/)
+    with installed("sim", sms=4):
         yield
     for n in names:
         setattr(torch, n, saved[n])

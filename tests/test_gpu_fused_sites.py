@@ -29,7 +29,7 @@ SITES = [("std", 96, 256), ("std", 48, 512), ("std", 24, 1024), ("std", 12, 2048
          ("dilation", 96, 256), ("dilation", 48, 512), ("dilation", 24, 1024),
          ("line", 96, 256), ("line", 48, 512), ("line", 24, 1024)]
 # on the CPU simulator (tests/conftest.py) the same test logic runs on a 16x thinner problem
-_SIM = os.environ.get("TRAMBA_GPU_TESTS_ON_SIM", "") in ("1", "next")
+_SIM = os.environ.get("TRAMBA_GPU_TESTS_ON_SIM", "") == "1"
 BATCH = 2 if _SIM else 4
 NSUB = 10
 DX_FLOOR = 0.05

@@ -1,7 +1,7 @@
 """The library's CUDA kernels executed on the CPU (tools/cpu_sim: the .cu sources compiled as host code, every CUDA
 thread a cooperative fiber, inline PTX and <<<>>> launches replaced by functional equivalents) against the oracle.
 
-  fused SS2D core fwd / bwd and the skewed merge          product kernels AND the candidates under csrc/next/
+  fused SS2D core fwd / bwd (through the simulated C ABI)  every order family, both dtypes, several items per CTA
   operator selective scan fwd / bwd (sscan_*.cu)          whole files: kernels + host launchers, every plan type
   table-driven cross-scan / cross-merge (cross_scan.cu)   every order family incl. ablation orders and caller tables
   depthwise conv (+ SiLU) fwd / bwd, projected-channel gather / scatter
@@ -9,8 +9,8 @@ thread a cooperative fiber, inline PTX and <<<>>> launches replaced by functiona
 Covers what can be known without a GPU: index arithmetic, work decomposition over CTAs / rounds / items, the scans
 and their carries, barrier and mbarrier protocols (a mismatch is reported as a deadlock), asynchronous-copy
 discipline at both extremes (copies landing at issue / only at the wait), and the numerics of the recurrences.  The
-product kernels are GPU-verified (tests/test_gpu_*.py): here they validate the simulator, and protect later edits;
-the candidates (not yet run on a GPU) must reproduce the product kernels bit for bit.  Interleavings between the two
+kernels are GPU-verified (tests/test_gpu_*.py): here they validate the simulator, and protect later edits.
+Interleavings between the two
 copy extremes, memory-model ordering and performance are out of its reach.  LayerNorm2d (thread-block clusters,
 distributed shared memory) and DCT2D (mma.sync TF32) are covered at the end of this file; the library's whole C ABI on
 the simulator is exercised from the Python host in tests/test_host_logic_emulated.py and tests/test_model_parity.py."""
@@ -28,15 +28,6 @@ from _fused_oracle import fused_core_oracle, param_of
 
 ORDER = {"std": (_lib.ORDER_STD, 4), "dilation": (_lib.ORDER_DILATION, 4), "window": (_lib.ORDER_WINDOW, 4),
          "line": (_lib.ORDER_LINE, 8)}
-PTRS = ["x", "dts", "Bs", "Cs", "A", "Dp", "bias", "idx", "y", "dy", "du", "ddts", "dBs", "dCs", "dA", "dD", "dbias"]
-
-
-class FusedArgs(ctypes.Structure):            # csrc/ss2d_fused.cuh: struct FusedArgs
-    _fields_ = [(n, ctypes.c_void_p) for n in PTRS] + [(n, ctypes.c_int) for n in ("B", "K", "D", "L", "TP", "PP",
-                                                                                  "rounds", "softplus")] + \
-               [("dup_mask", ctypes.c_uint32), ("xb", ctypes.c_int)]
-
-
 @pytest.fixture(scope="module")
 def sim():
     spec = importlib.util.spec_from_file_location("build_sim", os.path.join(ROOT, "tools", "cpu_sim", "build_sim.py"))
@@ -45,9 +36,10 @@ def sim():
     # TRAMBA_SIM_ASAN=1 (with LD_PRELOAD=$(gcc -print-file-name=libasan.so) ASAN_OPTIONS=detect_leaks=0): the
     # AddressSanitizer build -- an out-of-bounds global or shared memory access of a kernel aborts the run
     lib = ctypes.CDLL(mod.build(asan=os.environ.get("TRAMBA_SIM_ASAN", "") == "1"))
-    for name in ("sim_fwd", "sim_bwd", "sim_fwd_cg", "sim_bwd_cg"):
+    for name in ("tramba_ss2d_fused_fwd", "tramba_ss2d_fused_bwd", "tramba_ss2d_fused_supported"):
         fn = getattr(lib, name)
-        fn.restype, fn.argtypes = ctypes.c_char_p, [ctypes.POINTER(FusedArgs), ctypes.c_int, ctypes.c_int]
+        fn.restype, fn.argtypes = _lib.SIGNATURES[name]
+    lib.sim_set_sm_count.restype, lib.sim_set_sm_count.argtypes = None, [ctypes.c_int]
     lib.sim_set_lazy.restype, lib.sim_set_lazy.argtypes = None, [ctypes.c_int]
     lib.sim_set_schedule.restype, lib.sim_set_schedule.argtypes = None, [ctypes.c_uint]
     # TRAMBA_SIM_SCHEDULE = 0 (default: ascending thread order) | 1 (descending) | n >= 2 (random permutation per sweep,
@@ -70,6 +62,8 @@ def _host(a, bf16):
 
 
 def _run(sim, fam, H, D, B, bf16, grid, seed=0):
+    """The fused core through the simulated library's C ABI (tramba_ss2d_fused_fwd / _bwd as include/tramba_b200.h
+    declares them) on raw host buffers; `grid` plays the role of the SM count (persistent grids are sized from it)."""
     order, K = ORDER[fam]
     L = H * H
     g = torch.Generator().manual_seed(seed)
@@ -82,34 +76,39 @@ def _run(sim, fam, H, D, B, bf16, grid, seed=0):
     dy = torch.randn(B, D, L, generator=g)
     if bf16:      # round once so the oracle and the kernels start from identical values
         x, dts, Bs, Cs = [t.bfloat16().float() for t in (x, dts, Bs, Cs)]
+    param = param_of(fam, H)
     t16 = np.empty((K, L), dtype=np.uint16)
-    _lib.check(_lib.lib.tramba_order_table16_skewed(order, H, H, param_of(fam, H), t16.ctypes.data))
+    _lib.check(_lib.lib.tramba_order_table16_skewed(order, H, H, param, t16.ctypes.data))
+    n = int(_lib.lib.tramba_order_sched_len(order, H, H, param))
+    sched, kinds = np.empty((K, n), np.uint32), np.empty((2 * K,), np.int32)
+    _lib.check(_lib.lib.tramba_order_sched(order, H, H, param, sched.ctypes.data, kinds.ctypes.data))
     code = _lib.BF16 if bf16 else _lib.F32
     ins = dict(x=_dev(x, bf16), dts=_dev(dts, bf16), Bs=_dev(Bs, bf16), Cs=_dev(Cs, bf16), A=_dev(A, False),
-               Dp=_dev(Ds, False), bias=_dev(bias, False), idx=t16, dy=_dev(dy, False))
-    TP = L // 18
-    res = {}
-    for tag in ("", "_cg"):
-        out = dict(y=np.full((B, D, L), np.nan, np.float32),
-                   du=np.zeros((B, K, D, L), np.uint16 if bf16 else np.float32),
-                   ddts=np.zeros((B, K, D, L), np.uint16 if bf16 else np.float32),
-                   dBs=np.zeros((B, K, L), np.float32), dCs=np.zeros((B, K, L), np.float32),
-                   dA=np.full((B, K * D), np.nan, np.float32), dD=np.full((B, K * D), np.nan, np.float32),
-                   dbias=np.full((B, K * D), np.nan, np.float32))
-        a = FusedArgs(B=B, K=K, D=D, L=L, TP=TP, PP=512 // TP, rounds=B * D // (512 // TP), softplus=1,
-                      dup_mask=0xF0 if fam == "line" else 0, xb=0,
-                      **{k: v.ctypes.data for k, v in {**ins, **out}.items()})
-        for fn in ("sim_fwd", "sim_bwd"):
-            err = getattr(sim, fn + tag)(ctypes.byref(a), code, grid)
-            assert err is None, (fn + tag, err.decode())
-        res[tag] = out
+               Dp=_dev(Ds, False), bias=_dev(bias, False), dy=_dev(dy, False))
+    out = dict(y=np.full((B, D, L), np.nan, np.float32), dx=np.full((B, D, L), np.nan, np.float32),
+               ddts=np.zeros((B, K, D, L), np.uint16 if bf16 else np.float32),
+               dBs=np.full((B, K, L), np.nan, np.float32), dCs=np.full((B, K, L), np.nan, np.float32),
+               dA=np.full((K * D,), np.nan, np.float32), dD=np.full((K * D,), np.nan, np.float32),
+               dbias=np.full((K * D,), np.nan, np.float32))
+    p = lambda a: a.ctypes.data
+    sim.sim_set_sm_count(grid)
+    rc = sim.tramba_ss2d_fused_fwd(p(ins["x"]), p(ins["dts"]), p(ins["Bs"]), p(ins["Cs"]), p(ins["A"]), p(ins["Dp"]),
+                                   p(ins["bias"]), p(t16), p(out["y"]), order, K, B, D, H, H, 1, code, 1, None)
+    assert rc == 0, ("fwd", rc)
+    have_bwd = bool(sim.tramba_ss2d_fused_supported(order, K, D, H, H, 1, code, 1))
+    if have_bwd:
+        rc = sim.tramba_ss2d_fused_bwd(p(ins["x"]), p(ins["dts"]), p(ins["Bs"]), p(ins["Cs"]), p(ins["A"]), p(ins["Dp"]),
+                                       p(ins["bias"]), p(sched), n, p(kinds), p(ins["dy"]), p(out["dx"]), p(out["ddts"]),
+                                       p(out["dBs"]), p(out["dCs"]), p(out["dA"]), p(out["dD"]), p(out["dbias"]), order,
+                                       K, B, D, H, H, 1, code, 1, None)
+        assert rc == 0, ("bwd", rc)
     ref_y, ref_g = fused_core_oracle(fam, H, [x, dts, Bs, Cs, A, Ds, bias], dy)
-    return res, ref_y, ref_g, bf16
+    return out, have_bwd, ref_y, ref_g
 
 
 def _close(a, b, rtol, what):
     a, b = np.asarray(a, np.float64), b.detach().double().numpy()
-    tol = rtol * np.abs(b) + rtol * np.abs(b).max()
+    tol = rtol * np.abs(b) + 0.05 * rtol * np.abs(b).max()
     bad = np.abs(a - b) > tol
     assert not bad.any(), f"{what}: {bad.sum()} of {bad.size} off, max err {np.abs(a - b).max():.3e}"
 
@@ -118,8 +117,9 @@ CASES = [  # family, H, D, B, bf16, grid
     ("std", 12, 64, 2, False, 3), ("std", 12, 128, 1, True, 2), ("line", 12, 64, 1, False, 3),
     ("window", 24, 32, 2, False, 3), ("dilation", 24, 16, 1, True, 1), ("line", 24, 16, 1, True, 2),
     ("std", 48, 8, 1, False, 2), ("window", 48, 4, 1, True, 1), ("std", 96, 2, 1, True, 2),
-    ("dilation", 96, 8, 1, True, 3),   # 96 x 96, one plane per round, R = 8 rounds per backward item, several items per CTA
+    ("dilation", 96, 8, 1, True, 3),   # 96 x 96, one plane per round, several rounds per backward item and items per CTA
     ("line", 96, 2, 1, True, 2),       # helix duplicates (shared-memory atomics) with 512 threads per plane
+    ("std", 96, 2, 1, False, 2),       # fp32 at 96 x 96: forward only (the backward's staging does not fit)
 ]
 
 
@@ -127,36 +127,22 @@ CASES = [  # family, H, D, B, bf16, grid
 @pytest.mark.parametrize("fam,H,D,B,bf16,grid", CASES)
 def test_fused_kernels_on_the_cpu_simulator(sim, fam, H, D, B, bf16, grid, lazy):
     """lazy = 0: asynchronous copies land when issued (a buffer refilled too early corrupts its readers);
-    lazy = 1: they land when waited for and their destinations are poisoned meanwhile, bulk stores read their shared
-    source at the wait_group (a read before the barrier / a staging buffer overwritten too early corrupts data)."""
+    lazy = 1: they land when waited for and their destinations are poisoned meanwhile, bulk stores / reductions read
+    their shared source at the wait_group (a read before the barrier / a staging buffer overwritten too early
+    corrupts data)."""
     sim.sim_set_lazy(lazy)
-    res, ref_y, ref_g, bf16 = _run(sim, fam, H, D, B, bf16, grid)
+    out, have_bwd, ref_y, ref_g = _run(sim, fam, H, D, B, bf16, grid)
     rtol = 1e-2 if bf16 else 1e-3
-    for tag, out in res.items():
-        K = out["du"].shape[1]
-        _close(out["y"], ref_y, rtol, f"y{tag}")
-        # du is the gradient w.r.t. xs (scan order); the oracle differentiates w.r.t. the image: fold du back
-        from oracle import scan_orders as so
-        tab = so.order_table(fam, H, param_of(fam, H))
-        dx = so.cross_merge(_host(out["du"], bf16).double().numpy(), tab, "custom").reshape(ref_g[0].shape)
-        _close(dx, ref_g[0], 2 * rtol, f"dx{tag}")
-        _close(_host(out["ddts"], bf16).numpy(), ref_g[1], rtol, f"ddelta{tag}")
-        _close(out["dBs"], ref_g[2], rtol, f"dB{tag}")
-        _close(out["dCs"], ref_g[3], rtol, f"dC{tag}")
-        _close(out["dA"].sum(0), ref_g[4], rtol, f"dA{tag}")
-        _close(out["dD"].sum(0), ref_g[5], rtol, f"dD{tag}")
-        _close(out["dbias"].sum(0), ref_g[6], rtol, f"dbias{tag}")
-    # the candidates perform the same floating-point operations in the same order as the product kernels
-    for k in ("y", "du", "ddts", "dA", "dD", "dbias"):
-        assert np.array_equal(res[""][k], res["_cg"][k]), k
-    for k in ("dBs", "dCs"):        # accumulated across CTAs: the simulator runs CTAs in order, so still identical
-        assert np.array_equal(res[""][k], res["_cg"][k]), k
-
-
-def test_simulator_runs_an_empty_launch(sim):
-    """Zero rounds: every thread returns before touching a barrier; the scheduler must terminate cleanly."""
-    a = FusedArgs(B=1, K=4, D=64, L=144, TP=8, PP=64, rounds=0, softplus=1, dup_mask=0, xb=0)
-    assert sim.sim_fwd(ctypes.byref(a), _lib.F32, 1) is None
+    _close(out["y"], ref_y, 1e-3, "y")
+    assert have_bwd == (bf16 or H < 96)
+    if have_bwd:
+        _close(out["dx"].reshape(ref_g[0].shape), ref_g[0], rtol, "dx")
+        _close(_host(out["ddts"], bf16).numpy(), ref_g[1], rtol, "ddelta")
+        _close(out["dBs"], ref_g[2], rtol, "dB")
+        _close(out["dCs"], ref_g[3], rtol, "dC")
+        _close(out["dA"], ref_g[4], rtol, "dA")
+        _close(out["dD"], ref_g[5], rtol, "dD")
+        _close(out["dbias"], ref_g[6], rtol, "dbias")
 
 
 def test_simulator_selftest(sim):
@@ -177,38 +163,6 @@ def test_simulator_selftest(sim):
     o = np.zeros(32, np.float32)
     assert sim.sim_selftest_mbar(1, o.ctypes.data) is None and np.array_equal(o[:4], [1, 2, 3, 4])
     assert b"deadlock" in sim.sim_selftest_mbar(0, o.ctypes.data)
-
-
-@pytest.mark.parametrize("lazy", [0, 1], ids=["eager-copies", "lazy-copies"])
-@pytest.mark.parametrize("fam,H,D,B,bf16,grid", [("std", 12, 64, 2, False, 2), ("line", 24, 16, 2, True, 1),
-                                                 ("window", 48, 8, 1, False, 2), ("dilation", 96, 3, 1, True, 2),
-                                                 ("line", 96, 2, 1, False, 1)])
-def test_merge_skewed_on_the_cpu_simulator(sim, fam, H, D, B, bf16, grid, lazy):
-    """tramba_cross_merge_skewed's kernel (dx = CrossScan*.backward(du) of the fused backward), product and
-    candidate: exact against the transpose of the gather on integer-valued data (any summation order is exact)."""
-    from oracle import scan_orders as so
-    order, K = ORDER[fam]
-    L = H * H
-    args = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p] + [ctypes.c_int] * 4 + [ctypes.c_uint32, ctypes.c_int,
-                                                                                      ctypes.c_int]
-    sim.sim_set_lazy(lazy)
-    rs = np.random.RandomState(H + D)
-    ys = torch.from_numpy(rs.randint(-4, 5, size=(B, K, D, L)).astype(np.float32))
-    t16 = np.empty((K, L), dtype=np.uint16)
-    _lib.check(_lib.lib.tramba_order_table16_skewed(order, H, H, param_of(fam, H), t16.ctypes.data))
-    want = so.cross_merge(ys.numpy(), so.order_table(fam, H, param_of(fam, H)), "custom")
-    src = _dev(ys, bf16)
-    outs = []
-    for name in ("sim_merge", "sim_merge_cg"):
-        fn = getattr(sim, name)
-        fn.restype, fn.argtypes = ctypes.c_char_p, args
-        y = np.zeros((B, D, L), np.uint16 if bf16 else np.float32)
-        err = fn(src.ctypes.data, y.ctypes.data, t16.ctypes.data, K, B, D, L, 0xF0 if fam == "line" else 0,
-                 _lib.BF16 if bf16 else _lib.F32, grid)
-        assert err is None, (name, err.decode())
-        assert np.array_equal(_host(y, bf16).numpy(), want), name
-        outs.append(y)
-    assert np.array_equal(outs[0], outs[1])
 
 
 # ------------------------------------------------------------------------------------------------------------------

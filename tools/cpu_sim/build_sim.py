@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Builds tools/cpu_sim/_gen/libtramba_sim.so: EVERY source file of libtramba_b200 (capi.cu, orders.cpp, all kernel .cu
-files, plus the candidates under csrc/next/) compiled as HOST code against tools/cpu_sim/sim_common.h (see there), so
+files) compiled as HOST code against tools/cpu_sim/sim_common.h (see there), so
 that the product's C ABI and kernels can be executed on a CPU.
 
 The sources are copied, not edited in place; the only textual changes are (1) inline PTX -> the simulator's functions,
@@ -53,17 +53,9 @@ RED = re.compile(r'asm volatile\("red\.global\.add\.v2\.f32 \[%0\], \{%1, %2\};"
                  r'"f"\((.*?)\)\s*: "memory"\);', re.S)
 
 FUSED_DRIVER = r'''
-// Drivers of the fused SS2D core: product launchers (csrc/ss2d_fused_*.cu) and candidates (csrc/next/*_cg.cu).
-// `grid` plays the role of the SM count: the launchers size their persistent grids from it.
+// Drivers of the fused SS2D core launchers (csrc/ss2d_fused_fwd.cu / _bwd.cu) for tests that call the kernels without
+// the C ABI.  `grid` plays the role of the SM count: the launchers size their persistent grids from it.
 #include "ss2d_fused.cuh"
-namespace tramba {
-cudaError_t launch_ss2d_fused_fwd_cg(const FusedArgs& a, int in_dtype, cudaStream_t st);
-cudaError_t launch_ss2d_fused_bwd_cg(const FusedArgs& a, int in_dtype, cudaStream_t st);
-cudaError_t launch_merge_skewed(const void* ys, void* y, const uint16_t* idx, int K, int B, int D, int L,
-                                uint32_t dup_mask, int dtype, cudaStream_t st);
-cudaError_t launch_merge_skewed_cg(const void* ys, void* y, const uint16_t* idx, int K, int B, int D, int L,
-                                   uint32_t dup_mask, int dtype, cudaStream_t st);
-}
 using namespace tramba;
 static const char* done(cudaError_t e) {
     return sim::last_error ? sim::last_error : (e == cudaSuccess ? nullptr : "launcher rejected the arguments");
@@ -78,32 +70,9 @@ extern "C" const char* sim_fwd(const FusedArgs* a, int in_dtype, int grid) {
     sim::sm_count = grid, sim::last_error = nullptr;
     return done(launch_ss2d_fused_fwd(with_depth(*a, in_dtype), in_dtype, nullptr));
 }
-extern "C" const char* sim_fwd_cg(const FusedArgs* a, int in_dtype, int grid) {
-    sim::sm_count = grid, sim::last_error = nullptr;
-    return done(launch_ss2d_fused_fwd_cg(with_depth(*a, in_dtype), in_dtype, nullptr));
-}
-extern "C" const char* sim_bwd(const FusedArgs* a, int in_dtype, int grid) {
-    sim::sm_count = grid, sim::last_error = nullptr;
-    return done(launch_ss2d_fused_bwd(*a, in_dtype, nullptr));
-}
-extern "C" const char* sim_bwd_cg(const FusedArgs* a, int in_dtype, int grid) {
-    sim::sm_count = grid, sim::last_error = nullptr;
-    return done(launch_ss2d_fused_bwd_cg(*a, in_dtype, nullptr));
-}
-extern "C" const char* sim_merge(const void* ys, void* y, const uint16_t* idx, int K, int B, int D, int L,
-                                 uint32_t dup_mask, int dtype, int grid) {
-    sim::sm_count = grid, sim::last_error = nullptr;
-    return done(launch_merge_skewed(ys, y, idx, K, B, D, L, dup_mask, dtype, nullptr));
-}
-extern "C" const char* sim_merge_cg(const void* ys, void* y, const uint16_t* idx, int K, int B, int D, int L,
-                                    uint32_t dup_mask, int dtype, int grid) {
-    sim::sm_count = grid, sim::last_error = nullptr;
-    return done(launch_merge_skewed_cg(ys, y, idx, K, B, D, L, dup_mask, dtype, nullptr));
-}
 '''
 
-FUSED_FILES = ["ss2d_fused_fwd.cu", "ss2d_fused_fwd_pair.cu", "ss2d_fused_bwd.cu", "ss2d_fused_bwd_dx.cu", "ss2d_fused_merge.cu", os.path.join("next", "ss2d_fused_fwd_cg.cu"),
-               os.path.join("next", "ss2d_fused_bwd_cg.cu"), os.path.join("next", "ss2d_fused_merge_cg.cu")]
+FUSED_FILES = ["ss2d_fused_fwd.cu", "ss2d_fused_bwd.cu"]
 
 
 def gen_fused():
@@ -206,7 +175,6 @@ def gen_whole_file(rel):
     s = s.replace('asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");', "sim::cp_wait(N);")
     s = RED.sub(r"sim::red_add_v2(\1, \2, \3);", s)
     s = re.sub(r"static int sms = 0(, occ = 0)?;", r"int sms = 0\1;", s)     # the SM count is per call in the simulator
-    s = s.replace('#include "../ss2d_fused.cuh"', '#include "ss2d_fused.cuh"')
     s = MACRO_LAUNCH.sub(r"sim::launch_kernel(\2, \3, \4, [&] { \1(\5); })", s)
     s = LAUNCH.sub(r"sim::launch_kernel(\2, \3, \4, [&] { \1(\5); });", s)
     s = RED4.sub(r"sim::red_add_v4(\1, \2, \3, \4, \5);", s)
@@ -368,16 +336,11 @@ def gen_sscan():
     return [gen_whole_file("sscan_fwd.cu"), gen_whole_file("sscan_bwd.cu"), drv]
 
 
-def build(force=False, next_variant=False, asan=False):
-    """next_variant: compile with -DTRAMBA_NEXT, i.e. the product launchers dispatch to the candidate kernels of
-    csrc/next/ exactly as libtramba_b200_next.so does (library: libtramba_sim_next.so)."""
+def build(force=False, asan=False):
     global GEN, LIB
     if asan:     # AddressSanitizer build: out-of-bounds global / shared memory accesses of the kernels abort the run
         GEN = os.path.join(HERE, "_gen_asan")
         LIB = os.path.join(GEN, "libtramba_sim_asan.so")
-    elif next_variant:
-        GEN = os.path.join(HERE, "_gen_next")
-        LIB = os.path.join(GEN, "libtramba_sim_next.so")
     else:
         GEN = os.path.join(HERE, "_gen")
         LIB = os.path.join(GEN, "libtramba_sim.so")
@@ -396,7 +359,7 @@ def build(force=False, next_variant=False, asan=False):
     srcs.append(os.path.join(HERE, "selftest.cpp"))
     flags = ["-std=c++17", "-O1", "-fPIC", "-w", "-U_FORTIFY_SOURCE", "-D_FORTIFY_SOURCE=0",   # _longjmp across fiber stacks
              "-I" + HERE, "-I" + GEN, "-I" + os.path.join(ROOT, "include"),
-             "-I/usr/local/cuda/include"] + (["-DTRAMBA_NEXT"] if next_variant else []) + (
+             "-I/usr/local/cuda/include"] + (
                  ["-fsanitize=address", "-fno-omit-frame-pointer", "-g", "-DSIM_ASAN"] if asan else [])
     objs = [os.path.join(GEN, os.path.splitext(os.path.basename(f))[0] + ".o") for f in srcs]
     from concurrent.futures import ThreadPoolExecutor
@@ -412,4 +375,4 @@ def build(force=False, next_variant=False, asan=False):
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, next_variant="--next" in sys.argv, asan="--asan" in sys.argv))
+    print(build(force="--force" in sys.argv, asan="--asan" in sys.argv))

@@ -16,7 +16,9 @@ SITES = [  # name, order, K, d_inner, H
     ("enc0/std", _lib.ORDER_STD, 4, 256, 96), ("enc1/std", _lib.ORDER_STD, 4, 512, 48),
     ("enc2/std", _lib.ORDER_STD, 4, 1024, 24), ("enc3/std", _lib.ORDER_STD, 4, 2048, 12),
     ("freq96/win", _lib.ORDER_WINDOW, 4, 256, 96), ("freq96/dil", _lib.ORDER_DILATION, 4, 256, 96),
-    ("freq24/win", _lib.ORDER_WINDOW, 4, 1024, 24), ("dec96/line", _lib.ORDER_LINE, 8, 256, 96),
+    ("freq48/win", _lib.ORDER_WINDOW, 4, 512, 48), ("freq48/dil", _lib.ORDER_DILATION, 4, 512, 48),
+    ("freq24/win", _lib.ORDER_WINDOW, 4, 1024, 24), ("freq24/dil", _lib.ORDER_DILATION, 4, 1024, 24),
+    ("dec96/line", _lib.ORDER_LINE, 8, 256, 96),
     ("dec48/line", _lib.ORDER_LINE, 8, 512, 48), ("dec24/line", _lib.ORDER_LINE, 8, 1024, 24),
 ]
 PARAM = {(_lib.ORDER_WINDOW, 96): 16, (_lib.ORDER_WINDOW, 48): 12, (_lib.ORDER_WINDOW, 24): 8,
@@ -87,16 +89,21 @@ def main():
             r.update(ffwd_us=t_ff * 1e6, ffwd_gbs=by_ff / t_ff / 1e9, ffwd_gtok=K * B * D * L / t_ff / 1e9)
             if fused.supported(order, K, D, H, H, 1, dt, need_bwd=True):
                 dy = torch.randn(B, D, L, device=dev)
-                dxk, ddt = torch.empty_like(dts_img), torch.empty_like(dts_img)
-                dBs, dCs = torch.empty(B, K, L, device=dev), torch.empty(B, K, L, device=dev)
-                pA, pD, pb = (torch.empty(B, K * D, device=dev) for _ in range(3))
+                sched, kinds = fused._sched(order, H, param, dev)
+                n_dx, n_bc, n_row = B * D * L, B * K * L, K * D
+                ws = torch.empty(n_dx + 2 * n_bc + 3 * n_row, device=dev)          # one workspace -> one memset
+                dx, dBs, dCs, pA, pD, pb = torch.split(ws, [n_dx, n_bc, n_bc, n_row, n_row, n_row])
+                ddt = torch.empty_like(dts_img)
                 fbwd = lambda: _lib.check(_lib.lib.tramba_ss2d_fused_bwd(
                     x.data_ptr(), dts_img.data_ptr(), Bi.data_ptr(), Ci.data_ptr(), Af.data_ptr(), Dp.data_ptr(),
-                    bias.data_ptr(), idx.data_ptr(), dy.data_ptr(), dxk.data_ptr(), ddt.data_ptr(), dBs.data_ptr(),
-                    dCs.data_ptr(), pA.data_ptr(), pD.data_ptr(), pb.data_ptr(), order, K, B, D, H, H, 1, code, 1, st()))
+                    bias.data_ptr(), sched.data_ptr(), sched.shape[1], kinds.ctypes.data, dy.data_ptr(), dx.data_ptr(),
+                    ddt.data_ptr(), dBs.data_ptr(), dCs.data_ptr(), pA.data_ptr(), pD.data_ptr(), pb.data_ptr(), order, K,
+                    B, D, H, H, 1, code, 1, st()))
                 t_fb = timeit(fbwd, a.reps, flush)
-                by_fb = K * B * D * L * (4 * es + 4) + 2 * B * K * L * (es + 4)
-                r.update(fbwd_us=t_fb * 1e6, fbwd_gbs=by_fb / t_fb / 1e9, fbwd_gtok=K * B * D * L / t_fb / 1e9)
+                by_fb = K * B * D * L * (4 * es + 4) + 2 * B * K * L * (es + 4)      # what it replaces
+                by_min = B * D * L * (es + 4 + 4) + K * B * D * L * 2 * es + 2 * B * K * L * (es + 4)   # what it must move
+                r.update(fbwd_us=t_fb * 1e6, fbwd_gbs=by_fb / t_fb / 1e9, fbwd_gbs_min=by_min / t_fb / 1e9,
+                         fbwd_gtok=K * B * D * L / t_fb / 1e9)
         if a.fused_only:
             print(json.dumps({k: (round(v, 1) if isinstance(v, float) else v) for k, v in r.items()}), flush=True)
             continue

@@ -8,13 +8,7 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-# TRAMBA_B200_LIB=next loads the CANDIDATE build (libtramba_b200_next.so: same sources compiled with
-# -DTRAMBA_NEXT plus csrc/next/, see build.py) so that the whole test suite and bench.py can be pointed at kernels
-# under evaluation without touching the product library.  Unset (the default) = the product library.
-VARIANT = os.environ.get("TRAMBA_B200_LIB", "")
-if VARIANT not in ("", "next"):
-    raise ImportError(f"tramba_b200: unknown TRAMBA_B200_LIB={VARIANT!r} (expected unset or 'next')")
-LIB_PATH = os.path.join(_HERE, "libtramba_b200_next.so" if VARIANT == "next" else "libtramba_b200.so")
+LIB_PATH = os.path.join(_HERE, "libtramba_b200.so")
 
 F32, BF16, F16 = 0, 1, 2
 ACT_NONE, ACT_GELU, ACT_SILU = 0, 1, 2
@@ -44,18 +38,10 @@ SIGNATURES = {
     "tramba_order_table16_skewed": (_i, [_i, _i, _i, _i, _vp]),
     "tramba_ss2d_fused_supported": (_i, [_i] * 8),
     "tramba_ss2d_fused_fwd": (_i, [_vp, _vp, _vp, _vp, _fp, _fp, _fp, _vp, _fp] + [_i] * 9 + [_vp]),
-    "tramba_ss2d_fused_bwd": (_i, [_vp, _vp, _vp, _vp, _fp, _fp, _fp, _vp, _fp, _vp, _vp, _fp, _fp, _fp, _fp, _fp]
-                              + [_i] * 9 + [_vp]),
     "tramba_order_sched_len": (ctypes.c_size_t, [_i, _i, _i, _i]),
     "tramba_order_sched": (_i, [_i, _i, _i, _i, _vp, _i32p]),
-    "tramba_order_pairs": (_i, [_i, _i, _i, _i, _i32p]),
-    "tramba_ss2d_fused_fwd_sched_supported": (_i, [_i] * 7),
-    "tramba_ss2d_fused_fwd_sched": (_i, [_vp, _vp, _vp, _vp, _fp, _fp, _fp, _vp, _i, _i32p, _i32p, _vp, _fp] + [_i] * 9
-                                    + [_vp]),
-    "tramba_ss2d_fused_bwd_dx_supported": (_i, [_i] * 7),
-    "tramba_ss2d_fused_bwd_dx": (_i, [_vp, _vp, _vp, _vp, _fp, _fp, _fp, _vp, _i, _i32p, _fp, _fp, _vp, _fp, _fp, _fp,
+    "tramba_ss2d_fused_bwd": (_i, [_vp, _vp, _vp, _vp, _fp, _fp, _fp, _vp, _i, _i32p, _fp, _fp, _vp, _fp, _fp, _fp,
                                       _fp, _fp] + [_i] * 9 + [_vp]),
-    "tramba_cross_merge_skewed": (_i, [_vp, _vp, _vp] + [_i] * 7 + [_vp]),
     "tramba_layernorm2d_tiles": (_i, [_i, _i, _i]),
     "tramba_layernorm2d_fwd": (_i, [_vp, _fp, _fp, _vp, _fp, _fp, _i, _i, _i, ctypes.c_float, _i, _i, _i, _vp]),
     "tramba_layernorm2d_bwd": (_i, [_vp, _vp, _fp, _fp, _fp, _fp, _vp, _fp, _fp] + [_i] * 6 + [_vp]),
@@ -82,10 +68,7 @@ def _load():
     import fcntl
 
     def ensure_built():
-        if VARIANT == "next":
-            if not os.path.exists(LIB_PATH):
-                _build.build(next_variant=True)
-        elif not os.path.exists(LIB_PATH) or (_build.sources_newer_than_lib() and os.path.exists(_build.NVCC)):
+        if not os.path.exists(LIB_PATH) or (_build.sources_newer_than_lib() and os.path.exists(_build.NVCC)):
             _build.build()  # raises if nvcc is unavailable or fails: no silent fallback
 
     try:

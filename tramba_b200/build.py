@@ -1,9 +1,6 @@
 """Build libtramba_b200.so (C-ABI, sm_100a only) in-tree with nvcc.
 
     python -m tramba_b200.build [--force] [--verbose]
-    python -m tramba_b200.build --next      # libtramba_b200_next.so: the same library compiled with -DTRAMBA_NEXT
-                                            # plus the candidate kernels under csrc/next/ (not the product; see
-                                            # tools/variant_bench.py and TRAMBA_B200_LIB=next in _lib.py)
 
 The library links the CUDA runtime statically and has no torch / Python dependency; the
 Python host loads it with ctypes (tramba_b200/_lib.py).  Built artefacts are git-ignored but
@@ -18,7 +15,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "_obj")
 LIB = os.path.join(HERE, "libtramba_b200.so")
-SOURCES = ["capi.cu", "sscan_fwd.cu", "sscan_bwd.cu", "ss2d_fused_fwd.cu", "ss2d_fused_fwd_pair.cu", "ss2d_fused_bwd.cu", "ss2d_fused_bwd_dx.cu", "ss2d_fused_merge.cu", "cross_scan.cu",
+SOURCES = ["capi.cu", "sscan_fwd.cu", "sscan_bwd.cu", "ss2d_fused_fwd.cu", "ss2d_fused_bwd.cu", "cross_scan.cu",
            "dct2d.cu", "dct2d_tc.cu", "layernorm2d.cu", "dwconv2d.cu", "proj_gather.cu", "orders.cpp"]
 HEADERS = ["common.cuh", "sscan.cuh", "ss2d_fused.cuh", os.path.join("..", "..", "include", "tramba_b200.h")]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
@@ -38,18 +35,7 @@ def sources_newer_than_lib():
     return _stale(LIB, deps)
 
 
-NEXT_SOURCES = [os.path.join("next", "ss2d_fused_fwd_cg.cu"), os.path.join("next", "ss2d_fused_bwd_cg.cu"),
-                os.path.join("next", "ss2d_fused_merge_cg.cu")]
-LIB_NEXT = os.path.join(HERE, "libtramba_b200_next.so")
-
-
-def build(force=False, verbose=False, next_variant=False):
-    """next_variant: build libtramba_b200_next.so (candidate kernels, -DTRAMBA_NEXT) into its own object
-    directory; the product library and its objects are not touched."""
-    OBJ = os.path.join(HERE, "_obj_next" if next_variant else "_obj")
-    LIB = LIB_NEXT if next_variant else globals()["LIB"]
-    SOURCES = globals()["SOURCES"] + (NEXT_SOURCES if next_variant else [])
-    FLAGS = globals()["FLAGS"] + (["-DTRAMBA_NEXT"] if next_variant else [])
+def build(force=False, verbose=False):
     os.makedirs(OBJ, exist_ok=True)
     hdrs = [os.path.join(CSRC, h) for h in HEADERS] + [os.path.abspath(__file__)]
     jobs = []
@@ -79,4 +65,4 @@ def build(force=False, verbose=False, next_variant=False):
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv, next_variant="--next" in sys.argv))
+    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv))

@@ -37,9 +37,6 @@ cudaError_t launch_dct2d_bwd(const float* ghigh, const float* glow, const float*
                              int planes, int H, int W, cudaStream_t st);
 
 cudaError_t launch_batch_sum(const void* in, void* out, int B, long long n, int dtype, cudaStream_t st);
-bool ss2d_fused_bwd_fits(int L, int es, uint32_t dup_mask, int K);
-cudaError_t launch_merge_skewed(const void* ys, void* y, const uint16_t* idx, int K, int B, int D, int L,
-                                uint32_t dup_mask, int dtype, cudaStream_t st);
 
 bool dct2d_tc_supported(int H, int W);
 cudaError_t launch_dct2d_fwd_tc(const float* x, const float* wy, const float* wx, float* high, float* low, int planes,
@@ -374,7 +371,7 @@ static int fused_geometry(FusedArgs& a, int order, int K, int B, int D, int H, i
     const long long L = static_cast<long long>(H) * W;
     if (L > 65536 || L % kFusedS != 0) return TRAMBA_E_LIMIT;
     const int TP = static_cast<int>(L / kFusedS);
-    if (TP > kFusedNT || (TP & (TP - 1)) != 0) return TRAMBA_E_LIMIT;  // L = 18 * 2^m, m <= 9
+    if (TP != 8 && TP != 32 && TP != 128 && TP != 512) return TRAMBA_E_LIMIT;  // L = 144, 576, 2304, 9216 (H = 12 .. 96)
     const int PP = kFusedNT / TP;
     if (D % PP != 0) return TRAMBA_E_LIMIT;
     if (static_cast<long long>(B) * D / PP >= (1ll << 30)) return TRAMBA_E_LIMIT;
@@ -392,7 +389,7 @@ extern "C" int tramba_ss2d_fused_supported(int order, int K, int D, int H, int W
     if (in_dtype != TRAMBA_F32 && in_dtype != TRAMBA_BF16) return 0;
     if (fused_geometry(a, order, K, 1, D, H, W, N) != TRAMBA_OK) return 0;
     if (ss2d_fused_fwd_smem(a.L, es, 1) > 227 * 1024) return 0;
-    if (need_bwd && !ss2d_fused_bwd_fits(a.L, es, a.dup_mask, K)) return 0;
+    if (need_bwd && !ss2d_fused_bwd_fits(a.L, es)) return 0;
     return 1;
 }
 
@@ -419,123 +416,8 @@ extern "C" int tramba_ss2d_fused_fwd(const void* x, const void* dts, const void*
     return cuda_rc(launch_ss2d_fused_fwd(a, in_dtype, static_cast<cudaStream_t>(stream)));
 }
 
-extern "C" int tramba_ss2d_fused_bwd(const void* x, const void* dts, const void* Bs, const void* Cs,
-                                     const float* A, const float* Dp, const float* delta_bias,
-                                     const uint16_t* idx16, const float* dy, void* du, void* ddts, float* dBs,
-                                     float* dCs, float* dA_part, float* dD_part, float* dbias_part, int order,
-                                     int K, int B, int D, int H, int W, int N, int in_dtype, int delta_softplus,
-                                     void* stream) {
-    if (!x || !dts || !Bs || !Cs || !A || !idx16 || !dy || !du || !ddts || !dBs || !dCs || !dA_part)
-        return TRAMBA_E_NULL;
-    if ((Dp && !dD_part) || (delta_bias && !dbias_part)) return TRAMBA_E_NULL;
-    if (in_dtype != TRAMBA_F32 && in_dtype != TRAMBA_BF16) return TRAMBA_E_DTYPE;
-    FusedArgs a;
-    std::memset(&a, 0, sizeof(a));
-    int rc = fused_geometry(a, order, K, B, D, H, W, N);
-    if (rc != TRAMBA_OK) return rc;
-    if (!aligned(x, 16) || !aligned(dts, 16) || !aligned(Bs, 16) || !aligned(Cs, 16) || !aligned(dy, 16) ||
-        !aligned(du, 16) || !aligned(ddts, 16) || !aligned(dBs, 16) || !aligned(dCs, 16) || !aligned(idx16, 4))
-        return TRAMBA_E_ALIGN;
-    if (!ss2d_fused_bwd_fits(a.L, elem_size(in_dtype), a.dup_mask, K)) return TRAMBA_E_LIMIT;
-    rc = check_device();
-    if (rc != TRAMBA_OK) return rc;
-    cudaStream_t st = static_cast<cudaStream_t>(stream);
-    const size_t nbc = static_cast<size_t>(B) * K * a.L * sizeof(float);
-    cudaError_t e = cudaMemsetAsync(dBs, 0, nbc, st);
-    if (e == cudaSuccess) e = cudaMemsetAsync(dCs, 0, nbc, st);
-    if (e != cudaSuccess) return cuda_rc(e);
-    a.x = x, a.dts = dts, a.Bs = Bs, a.Cs = Cs, a.A = A, a.Dp = Dp, a.bias = delta_bias, a.idx = idx16;
-    a.dy = dy, a.du = du, a.ddts = ddts, a.dBs = dBs, a.dCs = dCs, a.dA = dA_part, a.dD = dD_part,
-    a.dbias = dbias_part;
-    a.softplus = delta_softplus ? 1 : 0;
-    e = launch_ss2d_fused_bwd(a, in_dtype, st);
-    if (e == cudaErrorInvalidConfiguration) return TRAMBA_E_LIMIT;
-    return cuda_rc(e);
-}
-
-// Forward on the permutation schedule with direction pairing (ss2d_fused_fwd_pair.cu).
-extern "C" int tramba_ss2d_fused_fwd_sched_supported(int order, int K, int D, int H, int W, int N, int in_dtype) {
-    FusedArgs a;
-    std::memset(&a, 0, sizeof(a));
-    if (in_dtype != TRAMBA_F32 && in_dtype != TRAMBA_BF16) return 0;
-    if (fused_geometry(a, order, K, 1, D, H, W, N) != TRAMBA_OK) return 0;
-    return ss2d_fused_fwd_pair_fits(a.L, elem_size(in_dtype)) ? 1 : 0;
-}
-
-extern "C" int tramba_ss2d_fused_fwd_sched(const void* x, const void* dts, const void* Bs, const void* Cs,
-                                           const float* A, const float* Dp, const float* delta_bias,
-                                           const uint32_t* sched, int sched_len, const int32_t* kinds,
-                                           const int32_t* partners, const uint16_t* idx16, float* y, int order, int K,
-                                           int B, int D, int H, int W, int N, int in_dtype, int delta_softplus,
-                                           void* stream) {
-    if (!x || !dts || !Bs || !Cs || !A || !sched || !kinds || !partners || !idx16 || !y) return TRAMBA_E_NULL;
-    if (in_dtype != TRAMBA_F32 && in_dtype != TRAMBA_BF16) return TRAMBA_E_DTYPE;
-    FusedArgs g;
-    std::memset(&g, 0, sizeof(g));
-    int rc = fused_geometry(g, order, K, B, D, H, W, N);
-    if (rc != TRAMBA_OK) return rc;
-    if (K > 8) return TRAMBA_E_LIMIT;
-    if (!aligned(x, 16) || !aligned(dts, 16) || !aligned(Bs, 16) || !aligned(Cs, 16) || !aligned(y, 16) ||
-        !aligned(sched, 8))
-        return TRAMBA_E_ALIGN;
-    if (sched_len <= 0 || sched_len % (2 * g.TP) != 0 || sched_len % 64 != 0) return TRAMBA_E_SHAPE;
-    if (!ss2d_fused_fwd_pair_fits(g.L, elem_size(in_dtype))) return TRAMBA_E_LIMIT;
-    rc = check_device();
-    if (rc != TRAMBA_OK) return rc;
-    FusedFwdPairArgs a;
-    std::memset(&a, 0, sizeof(a));
-    a.x = x, a.dts = dts, a.Bs = Bs, a.Cs = Cs, a.A = A, a.Dp = Dp, a.bias = delta_bias, a.sched = sched, a.y = y;
-    a.idx = idx16;
-    if (!aligned(idx16, 4)) return TRAMBA_E_ALIGN;
-    a.B = B, a.K = K, a.D = D, a.sched_len = sched_len, a.softplus = delta_softplus ? 1 : 0;
-    for (int k = 0; k < K; ++k) {
-        const int used = kinds[K + k];
-        if (used <= 0 || used > sched_len || used % (2 * g.TP) != 0) return TRAMBA_E_SHAPE;
-        a.sched_used[k] = used;
-    }
-    // ---- the step list: identity-ordered groups first, then permutations, then tables with repeated pixels; inside
-    // a group the base direction, then the direction that reverses it
-    int n = 0, last_x_reader = -1;
-    for (int pass = 0; pass < 3; ++pass) {
-        for (int k = 0; k < K; ++k) {
-            if (kinds[k] < 0 || kinds[k] > 3 || partners[k] >= k) return TRAMBA_E_ORDER;
-            if (partners[k] >= 0) continue;  // a reversed member: emitted with its base
-            const int kind = kinds[k] == 1 ? 2 : kinds[k];  // a lone reversed identity is just a permutation
-            if ((pass == 0 && kind != 0) || (pass == 1 && kind != 2) || (pass == 2 && kind != 3)) continue;
-            int mate = -1;
-            for (int j = k + 1; j < K; ++j)
-                if (partners[j] == k) mate = j;
-            a.step_k[n] = static_cast<unsigned char>(k), a.step_base[n] = static_cast<unsigned char>(k);
-            a.step_rev[n] = 0, a.step_kind[n] = static_cast<unsigned char>(kind);
-            a.step_gather[n] = kind >= 2, a.step_merge[n] = mate < 0;
-            last_x_reader = n++;
-            if (mate >= 0) {
-                a.step_k[n] = static_cast<unsigned char>(mate), a.step_base[n] = static_cast<unsigned char>(k);
-                a.step_rev[n] = 1, a.step_kind[n] = static_cast<unsigned char>(kind);
-                a.step_gather[n] = 0, a.step_merge[n] = 1;
-                if (kind == 0) last_x_reader = n;  // identity pair: the reversed step reads the image planes too
-                ++n;
-            }
-        }
-    }
-    if (n != K || last_x_reader < 0) return TRAMBA_E_ORDER;
-    a.nsteps = n;
-    a.step_xfree[last_x_reader] = 1;
-    cudaError_t e = launch_ss2d_fused_fwd_pair(a, g.L, in_dtype, static_cast<cudaStream_t>(stream));
-    if (e == cudaErrorInvalidConfiguration) return TRAMBA_E_LIMIT;
-    return cuda_rc(e);
-}
-
 // Backward with dx: the merge of du (CrossScan*.backward, csms6s.py:25-31) happens inside the kernel.
-extern "C" int tramba_ss2d_fused_bwd_dx_supported(int order, int K, int D, int H, int W, int N, int in_dtype) {
-    FusedArgs a;
-    std::memset(&a, 0, sizeof(a));
-    if (in_dtype != TRAMBA_F32 && in_dtype != TRAMBA_BF16) return 0;
-    if (fused_geometry(a, order, K, 1, D, H, W, N) != TRAMBA_OK) return 0;
-    return ss2d_fused_bwd_dx_fits(a.L, elem_size(in_dtype)) ? 1 : 0;
-}
-
-extern "C" int tramba_ss2d_fused_bwd_dx(const void* x, const void* dts, const void* Bs, const void* Cs,
+extern "C" int tramba_ss2d_fused_bwd(const void* x, const void* dts, const void* Bs, const void* Cs,
                                         const float* A, const float* Dp, const float* delta_bias,
                                         const uint32_t* sched, int sched_len, const int32_t* kinds,
                                         const float* dy, float* dx, void* ddts, float* dBs, float* dCs,
@@ -554,7 +436,7 @@ extern "C" int tramba_ss2d_fused_bwd_dx(const void* x, const void* dts, const vo
         !aligned(dx, 16) || !aligned(ddts, 16) || !aligned(dBs, 16) || !aligned(dCs, 16) || !aligned(sched, 8))
         return TRAMBA_E_ALIGN;
     if (sched_len <= 0 || sched_len % (2 * g.TP) != 0 || sched_len % 64 != 0) return TRAMBA_E_SHAPE;
-    if (!ss2d_fused_bwd_dx_fits(g.L, elem_size(in_dtype))) return TRAMBA_E_LIMIT;
+    if (!ss2d_fused_bwd_fits(g.L, elem_size(in_dtype))) return TRAMBA_E_LIMIT;
     rc = check_device();
     if (rc != TRAMBA_OK) return rc;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -579,7 +461,7 @@ extern "C" int tramba_ss2d_fused_bwd_dx(const void* x, const void* dts, const vo
         i = jn;
     }
     if (e != cudaSuccess) return cuda_rc(e);
-    FusedDxArgs a;
+    FusedBwdArgs a;
     std::memset(&a, 0, sizeof(a));
     a.x = x, a.dts = dts, a.Bs = Bs, a.Cs = Cs, a.A = A, a.Dp = Dp, a.bias = delta_bias, a.sched = sched;
     a.dy = dy, a.dx = dx, a.ddts = ddts, a.dBs = dBs, a.dCs = dCs, a.dA = dA_part, a.dD = dD_part,
@@ -595,24 +477,11 @@ extern "C" int tramba_ss2d_fused_bwd_dx(const void* x, const void* dts, const vo
         a.sched_used[k] = used;
     }
     a.softplus = delta_softplus ? 1 : 0;
-    e = launch_ss2d_fused_bwd_dx(a, g.L, in_dtype, st);
+    e = launch_ss2d_fused_bwd(a, g.L, in_dtype, st);
     if (e == cudaErrorInvalidConfiguration) return TRAMBA_E_LIMIT;
     return cuda_rc(e);
 }
 
-extern "C" int tramba_cross_merge_skewed(const void* ys, void* y, const uint16_t* idx16, int order, int K, int B,
-                                         int D, int H, int W, int dtype, void* stream) {
-    if (!ys || !y || !idx16) return TRAMBA_E_NULL;
-    if (dtype != TRAMBA_F32 && dtype != TRAMBA_BF16) return TRAMBA_E_DTYPE;
-    FusedArgs a;
-    std::memset(&a, 0, sizeof(a));
-    int rc = fused_geometry(a, order, K, B, D, H, W, 1);
-    if (rc != TRAMBA_OK) return rc;
-    if (!aligned(ys, 16) || !aligned(y, 16) || !aligned(idx16, 4)) return TRAMBA_E_ALIGN;
-    rc = check_device();
-    if (rc != TRAMBA_OK) return rc;
-    return cuda_rc(launch_merge_skewed(ys, y, idx16, K, B, D, a.L, a.dup_mask, dtype, static_cast<cudaStream_t>(stream)));
-}
 
 // ------------------------------------------------------------------------------ LayerNorm2d
 static bool ln_dtype_ok(int d) { return d == TRAMBA_F32 || d == TRAMBA_BF16; }

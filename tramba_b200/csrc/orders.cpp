@@ -467,30 +467,6 @@ extern "C" size_t tramba_order_sched_len(int order, int H, int W, int param) {
     return (static_cast<size_t>(delta) * 32 + g - 1) / g * g;
 }
 
-// partner[k]: the direction j < k whose table direction k reverses exactly (idx_k[t] == idx_j[L-1-t]), or -1.  The
-// fused forward walks such a pair on ONE token-ordered copy of the plane (the partner's), back to front.
-extern "C" int tramba_order_pairs(int order, int H, int W, int param, int32_t* partner_out) {
-    if (!partner_out) return TRAMBA_E_NULL;
-    const int K = tramba_order_num_directions(order);
-    if (K < 0) return K;
-    if (H <= 0 || W <= 0) return TRAMBA_E_SHAPE;
-    const int L = H * W;
-    std::vector<int32_t> t(static_cast<size_t>(K) * L);
-    const int rc = tramba_order_table(order, H, W, param, t.data());
-    if (rc != TRAMBA_OK) return rc;
-    std::vector<char> taken(K, 0);
-    for (int k = 0; k < K; ++k) {
-        partner_out[k] = -1;
-        for (int j = 0; j < k && partner_out[k] < 0; ++j) {
-            if (taken[j] || partner_out[j] >= 0) continue;
-            bool rev = true;
-            for (int i = 0; i < L && rev; ++i) rev = t[static_cast<size_t>(k) * L + i] == t[static_cast<size_t>(j) * L + L - 1 - i];
-            if (rev) partner_out[k] = j, taken[j] = 1;
-        }
-    }
-    return TRAMBA_OK;
-}
-
 extern "C" int tramba_order_sched(int order, int H, int W, int param, uint32_t* sched_out, int32_t* kind_out) {
     if (!sched_out || !kind_out) return TRAMBA_E_NULL;
     const int K = tramba_order_num_directions(order);

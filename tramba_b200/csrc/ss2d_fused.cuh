@@ -63,8 +63,8 @@ struct FusedArgs {
     int xb;               // 2 = double-buffered staging, 1 = single
 };
 
-// Backward with the merge of du folded in (ss2d_fused_bwd_dx.cu)
-struct FusedDxArgs {
+// Backward, with the merge of du folded in (ss2d_fused_bwd.cu)
+struct FusedBwdArgs {
     const void* x;          // (B, D, L) image order
     const void* dts;        // (B, K, D, L) scan order
     const void* Bs;         // (B, K, L)
@@ -89,44 +89,11 @@ struct FusedDxArgs {
     int R;                  // rounds per item (set by the launcher)
     FastDiv div_db, div_k, div_r;  // / (D / (R*PP)), / K, / R (set by the launcher)
 };
-cudaError_t launch_ss2d_fused_bwd_dx(const FusedDxArgs& a, int L, int in_dtype, cudaStream_t st);
-bool ss2d_fused_bwd_dx_fits(int L, int es);
-
-// Forward on TMA-staged planes with direction pairing (ss2d_fused_fwd_pair.cu)
-struct FusedFwdPairArgs {
-    const void* x;          // (B, D, L) image order
-    const void* dts;        // (B, K, D, L) scan order
-    const void* Bs;         // (B, K, L)
-    const void* Cs;         // (B, K, L)
-    const float* A;         // (K*D)
-    const float* Dp;        // (K*D) or null
-    const float* bias;      // (K*D) or null
-    const uint32_t* sched;  // (K, sched_len) permutation schedule (tramba_order_sched), device
-    const uint16_t* idx;    // (K, L) pixel of every token (tramba_order_table16), device: merge of repeated-pixel orders
-    float* y;               // (B, D, L) fp32 image order, merged over the K directions
-    int B, K, D;
-    int sched_len;          // row stride of sched (entries)
-    int sched_used[8];      // entries direction k really uses
-    int softplus;
-    // the K directions as a list of steps, grouped: a direction and (optionally) the one that reverses it share one
-    // token-ordered copy of the plane and their outputs are summed in registers before ONE merge into the image
-    int nsteps;
-    unsigned char step_k[8];       // direction of the step (delta / B / C / A rows come from it)
-    unsigned char step_base[8];    // direction whose table orders the tokens of the group (== step_k unless reversed)
-    unsigned char step_rev[8];     // 1: tokens of step_k are the base's tokens back to front
-    unsigned char step_kind[8];    // kind of the base table: 0 identity, 2 permutation, 3 with repeated pixels
-    unsigned char step_gather[8];  // 1: first step of a non-identity group -> gather the image into token order first
-    unsigned char step_merge[8];   // 1: last step of its group -> merge the summed outputs into the image plane
-    unsigned char step_xfree[8];   // 1: the image-ordered x planes are dead after this step's first barrier
-    FastDiv div_d;                 // / D
-};
-cudaError_t launch_ss2d_fused_fwd_pair(const FusedFwdPairArgs& a, int L, int in_dtype, cudaStream_t st);
-bool ss2d_fused_fwd_pair_fits(int L, int es);
+cudaError_t launch_ss2d_fused_bwd(const FusedBwdArgs& a, int L, int in_dtype, cudaStream_t st);
+bool ss2d_fused_bwd_fits(int L, int es);
 
 cudaError_t launch_ss2d_fused_fwd(const FusedArgs& a, int in_dtype, cudaStream_t st);
-cudaError_t launch_ss2d_fused_bwd(const FusedArgs& a, int in_dtype, cudaStream_t st);
 size_t ss2d_fused_fwd_smem(int L, int es, int xb);
-size_t ss2d_fused_bwd_smem(int L, int es, int xb);
 
 // skewed plane length in elements (element p lives at p + 2*(p >> 6); +2 keeps planes word-aligned)
 __host__ __device__ inline int fused_skew_len(int L) { return L + 2 * ((L + 63) >> 6) + 2; }
@@ -144,46 +111,9 @@ __device__ __forceinline__ void cp_async8(void* dst_smem, const void* src) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(dst_smem)), "l"(src) : "memory");
 }
 
-// Stage ONE global plane into a skewed shared plane, by the TP threads that own the plane (thread j
-// of TP copies words j, j+TP, j+2*TP, ...; consecutive threads -> consecutive words, coalesced).
-// Element p must land at p + 2*(p >> 6):
-//   2-byte elements: 32-bit word w -> w + (w >> 5)           (4-byte copies)
-//   4-byte elements: 64-bit pair  v -> v + (v >> 5) (pairs)  (8-byte copies; pads are 2 words per 64)
-// `n` = elements per plane.  The caller arrives on the mbarrier afterwards (cp_async_arrive).
-template <int ES>
-__device__ __forceinline__ void stage_plane_skewed(void* dst_plane, const void* __restrict__ src_plane, int n, int j,
-                                                   int TP) {
-    if constexpr (ES == 2) {
-        uint32_t* d = static_cast<uint32_t*>(dst_plane);
-        const uint32_t* s = static_cast<const uint32_t*>(src_plane);
-        const int nw = n >> 1;
-        if ((TP & 31) == 0) {  // (w >> 5) advances by TP/32 per step: constant strides
-            uint32_t* dp = d + j + (j >> 5);
-            const uint32_t* sp = s + j;
-            const int dstep = TP + (TP >> 5);
-            for (int w = j; w < nw; w += TP, dp += dstep, sp += TP) cp_async4(dp, sp);
-        } else {
-            for (int w = j; w < nw; w += TP) cp_async4(d + w + (w >> 5), s + w);
-        }
-    } else {
-        uint2* d = static_cast<uint2*>(dst_plane);
-        const uint2* s = static_cast<const uint2*>(src_plane);
-        const int nv = n >> 1;
-        if ((TP & 31) == 0) {
-            uint2* dp = d + j + (j >> 5);
-            const uint2* sp = s + j;
-            const int dstep = TP + (TP >> 5);
-            for (int v = j; v < nv; v += TP, dp += dstep, sp += TP) cp_async8(dp, sp);
-        } else {
-            for (int v = j; v < nv; v += TP) cp_async8(d + v + (v >> 5), s + v);
-        }
-    }
-}
-
 // Same staging with the geometry known at compile time (TPC = threads per plane, n = kFusedS * TPC elements):
 // the kFusedS / 2 copies of a thread are fully unrolled and, for TPC a multiple of 32, their source and
 // destination strides are constants (vector v = j + i*TPC lands at v + (v >> 5) = j + (j >> 5) + i*(TPC + TPC/32)).
-// Used by the compile-time-geometry kernels under csrc/next/.
 template <int ES, int TPC>
 __device__ __forceinline__ void stage_plane_skewed_c(void* dst_plane, const void* __restrict__ src_plane, int j) {
     static_assert(ES == 2 || ES == 4, "bf16 / fp32 planes");

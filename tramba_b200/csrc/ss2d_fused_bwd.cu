@@ -1,21 +1,33 @@
-// Fused SS2D core, backward (sm_100a).  See ss2d_fused.cuh for the data model.
-// Replaces CrossMerge*.backward -> SelectiveScanOflex.backward of Models/SS2D/csms6s.py:45-55,914-923
-// (and the _Dilation/_Window/_Line variants) for N = 1: the gradient of the merged map is
-// gathered through the scan-order table in shared memory, so neither the K-fold copy of dy
-// (CrossMerge.backward = a cross-scan) nor xs is ever materialised.
+// Fused SS2D core, backward WITH the cross-merge of du folded in (sm_100a).  See ss2d_fused.cuh for the data model.
 //
-// Work item = (b, k, block of RB = R*PP channels): the CTA walks the R rounds of the item, each
-// round = PP whole planes of direction k.  Nothing is stored by the forward: pass 1 re-runs the
-// forward fold AND the reverse fold of  E_t = a_t*(g_t + E_{t+1}),  g_t = C_t*dy_t,  dh_t = g_t + E_{t+1}
-// over the thread's S tokens (both are affine maps sharing the same product of a's), the two
-// carries come from a forward and a reverse scan over the plane's threads, pass 2 walks the
-// segment right-to-left for dh and left-to-right for h and emits, in scan order,
-//     du_t     = D*dy_t + dh_t*delta_t*B_t                      (the caller folds it back: dx = CrossMerge(du))
-//     ddelta_t = dh_t*(A*a_t*h_{t-1} + B_t*u_t) * sigmoid(raw)
-// through token-ordered shared staging that leaves with one bulk store per round.
-// dB_t = sum_d dh_t*delta_t*u_t and dC_t = sum_d dy_t*h_t are accumulated in registers over all
-// rounds of the item (same b, k) and added to global memory once per item.  dA, dD, ddelta_bias
-// leave as per-(b, row) partial sums (no atomics; the host sums over b).
+// Replaces CrossMerge*.backward -> SelectiveScanOflex.backward -> CrossScan*.backward of
+// Models/SS2D/csms6s.py:45-55, 914-923, 25-31 (and the _Dilation / _Window / _Line variants) for N = 1 in ONE kernel:
+//     in : x, dy (B, D, L) IMAGE order; delta (B, K, D, L), B, C (B, K, L) scan order
+//     out: dx (B, D, L) fp32 IMAGE order (accumulated over the K directions with TMA bulk reductions at L2),
+//          ddelta (B, K, D, L) scan order, dB / dC (B, K, L), dA / dD / ddelta_bias (K*D) (fp32 reds over b).
+// Neither xs, nor the K-fold copy of dy, nor du (the K-fold gradient w.r.t. xs) is ever written to HBM.
+//
+// How it is built (the first-generation kernel -- cp.async-staged skewed planes, five table-driven gathers per
+// token, du written to HBM in scan order and folded by a second kernel -- was measured against it and removed,
+// profiles/r02_fused_ab_bf16.jsonl):
+//   * every operand plane moves with 1-D TMA bulk copies (no per-thread cp.async staging, no skewed planes);
+//   * geometry is a template parameter (TP threads per plane, L = 18 * TP): all index arithmetic folds;
+//   * the scan order is applied ONCE per round by a shared -> shared permutation pass that follows a host-made,
+//     bank-conflict-free schedule (tramba_order_sched: an edge colouring of pixel banks x token banks), after which
+//     the three recurrence passes read token-ordered chunks with conflict-free vector loads -- instead of five
+//     table-driven gathers per token; directions whose table is the identity skip the pass altogether;
+//   * du never leaves the SM in scan order: it is scattered back into an image-ordered fp32 plane by the inverse of
+//     the same schedule and added to dx in global memory with cp.reduce.async.bulk (.add.f32).
+//
+// Work item = (b, k, block of R*PP channels); round = PP whole planes of direction k (NT * S = 9216 tokens).
+// Per round:  wait x/dy -> [permute image -> token order] -> pass 1 (forward fold + reverse fold of the segment)
+//   -> scans over the plane's threads -> pass 2a (dh, right to left) -> pass 2b (h, du, ddelta, dB/dC/dA/dD/dbias)
+//   -> [scatter du token -> image order] -> bulk store ddelta, bulk reduce-add dx.
+// PIPE (16-bit operands): two (x, dy) plane sets used alternately and two delta buffers, so the TMA loads of round
+// s + 1 overlap round s.  !PIPE (fp32 operands, which need twice the staging): one set (+ the token-ordered set),
+// loads issued when the round's stores have been read.
+#include <type_traits>
+
 #include "ss2d_fused.cuh"
 
 namespace tramba {
@@ -27,55 +39,48 @@ constexpr int NT = kFusedNT;
 constexpr int TOK = kFusedTok;
 constexpr int NW = NT / 32;
 
-__host__ __device__ inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+constexpr size_t al16(size_t v) { return (v + 15) / 16 * 16; }
 
-struct BwdLayout {
-    size_t x, dy, d, b, c, o0, o1, tot, red, bar, total;
-    int lsk;
-    __host__ __device__ BwdLayout(int L, int es, int xb) {
-        lsk = fused_skew_len(L);
-        const int pp = TOK / L;
-        size_t o = 0;
-        x = o, o += align_up(static_cast<size_t>(xb) * pp * lsk * es, 16);
-        dy = o, o += align_up(static_cast<size_t>(xb) * pp * lsk * 4, 16);
-        d = o, o += static_cast<size_t>(xb) * TOK * es;
-        b = o, o += align_up(static_cast<size_t>(L) * es, 16);
-        c = o, o += align_up(static_cast<size_t>(L) * es, 16);
-        o0 = o, o += static_cast<size_t>(TOK) * es;
-        o1 = o, o += static_cast<size_t>(TOK) * es;
-        tot = o, o += 2 * 2 * NW * sizeof(float2);
-        red = o, o += 3 * NW * sizeof(float);
-        bar = o, o += 8 * sizeof(uint64_t);
-        total = o;
-    }
+template <int ES, int TP, bool PIPE>
+struct DxLayout {
+    static constexpr int L = TP * S;
+    static constexpr size_t XB = static_cast<size_t>(TOK) * ES, YB = static_cast<size_t>(TOK) * 4;
+    static constexpr size_t x0 = 0, y0 = XB, x1 = XB + YB, y1 = 2 * XB + YB;  // plane sets 0 and 1
+    static constexpr size_t d0 = 2 * (XB + YB);                               // delta in / ddelta out (in place)
+    static constexpr size_t d1 = PIPE ? d0 + XB : d0;
+    static constexpr size_t dx = d1 + XB;                                     // PIPE: image-ordered du staging
+    static constexpr size_t b = PIPE ? dx + YB : dx;
+    static constexpr size_t c = b + al16(static_cast<size_t>(L) * ES);
+    static constexpr size_t tot = c + al16(static_cast<size_t>(L) * ES);
+    static constexpr size_t red = tot + 2 * 2 * NW * sizeof(float2);
+    static constexpr size_t bar = al16(red + 3 * NW * sizeof(float));
+    static constexpr size_t total = bar + 8 * sizeof(uint64_t);
 };
 
-template <typename in_t, bool SOFTPLUS>
-__global__ void __launch_bounds__(NT, 1) ss2d_bwd_kernel(const FusedArgs p, const int R) {
+template <typename in_t, bool SOFTPLUS, int TP, bool PIPE>
+__global__ void __launch_bounds__(NT, 1) ss2d_bwd_kernel(const FusedBwdArgs p) {
     extern __shared__ __align__(128) unsigned char smem[];
     constexpr int ES = sizeof(in_t);
-    const int L = p.L, K = p.K, D = p.D, TP = p.TP, PP = p.PP, XB = p.xb;
-    const BwdLayout lay(L, ES, XB);
-    const int LSK = lay.lsk;
-    in_t* sx = reinterpret_cast<in_t*>(smem + lay.x);      // [XB][PP][LSK] skewed
-    float* sdy = reinterpret_cast<float*>(smem + lay.dy);  // [XB][PP][LSK] skewed
-    in_t* sd = reinterpret_cast<in_t*>(smem + lay.d);      // [XB][TOK] token order
-    in_t* sB = reinterpret_cast<in_t*>(smem + lay.b);      // [L]
-    in_t* sC = reinterpret_cast<in_t*>(smem + lay.c);      // [L]
-    in_t* so_dd = reinterpret_cast<in_t*>(smem + lay.o0);  // [TOK] ddelta staging, token order
-    in_t* so_du = reinterpret_cast<in_t*>(smem + lay.o1);  // [TOK] du staging, token order
-    float2* stot = reinterpret_cast<float2*>(smem + lay.tot);  // [2 parity][2 fwd/rev][NW]
-    float* sred = reinterpret_cast<float*>(smem + lay.red);    // [3][NW]
-    uint64_t* barX = reinterpret_cast<uint64_t*>(smem + lay.bar);  // [2] count NT: x + dy (cp.async)
-    uint64_t* barD = barX + 2;                                     // [2] count 1: delta (TMA)
-    uint64_t* barBC = barX + 4;                                    // [1] count 1: item B/C (TMA)
+    constexpr int L = TP * S, PP = NT / TP;
+    using Lay = DxLayout<ES, TP, PIPE>;
+    float* const sDXs = reinterpret_cast<float*>(smem + Lay::dx);  // PIPE only
+    in_t* const sB = reinterpret_cast<in_t*>(smem + Lay::b);
+    in_t* const sC = reinterpret_cast<in_t*>(smem + Lay::c);
+    float2* const stot = reinterpret_cast<float2*>(smem + Lay::tot);  // [2 parity][2 fwd/rev][NW]
+    float* const sred = reinterpret_cast<float*>(smem + Lay::red);    // [3][NW]
+    uint64_t* const barXY = reinterpret_cast<uint64_t*>(smem + Lay::bar);  // [2] per plane set
+    uint64_t* const barD = barXY + 2;                                      // [2] per delta buffer
+    uint64_t* const barBC = barXY + 4;                                     // [1]
+    auto sX = [&](int set) { return reinterpret_cast<in_t*>(smem + (set ? Lay::x1 : Lay::x0)); };
+    auto sY = [&](int set) { return reinterpret_cast<float*>(smem + (set ? Lay::y1 : Lay::y0)); };
+    auto sD = [&](int buf) { return reinterpret_cast<in_t*>(smem + (buf ? Lay::d1 : Lay::d0)); };
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int q = tid / TP;
     const int j = tid - q * TP;
-    const int width = TP < 32 ? TP : 32;
+    constexpr int width = TP < 32 ? TP : 32;
     const int sl = lane & (width - 1);
-    const int nwg = TP > 32 ? (TP >> 5) : 1;  // warps per plane group
+    constexpr int nwg = TP > 32 ? (TP >> 5) : 1;  // warps per plane
     const int wq = TP > 32 ? (j >> 5) : 0;
     const int gw0 = TP > 32 ? q * nwg : 0;
 
@@ -83,9 +88,9 @@ __global__ void __launch_bounds__(NT, 1) ss2d_bwd_kernel(const FusedArgs p, cons
     const in_t* __restrict__ gd = static_cast<const in_t*>(p.dts);
     const in_t* __restrict__ gB = static_cast<const in_t*>(p.Bs);
     const in_t* __restrict__ gC = static_cast<const in_t*>(p.Cs);
-    in_t* __restrict__ gdu = static_cast<in_t*>(p.du);
     in_t* __restrict__ gdd = static_cast<in_t*>(p.ddts);
 
+    const int K = p.K, D = p.D, R = p.R;
     const int RB = R * PP;  // channels per item
     const int dblocks = D / RB;
     const int items = p.B * K * dblocks;
@@ -95,68 +100,141 @@ __global__ void __launch_bounds__(NT, 1) ss2d_bwd_kernel(const FusedArgs p, cons
     if (nrounds <= 0) return;
 
     if (tid == 0) {
-        mbar_init(&barX[0], NT), mbar_init(&barX[1], NT), mbar_init(&barD[0], 1), mbar_init(&barD[1], 1);
+        mbar_init(&barXY[0], 1), mbar_init(&barXY[1], 1), mbar_init(&barD[0], 1), mbar_init(&barD[1], 1);
         mbar_init(&barBC[0], 1);
         fence_mbar_init();
         fence_proxy_async_smem();
     }
     __syncthreads();
 
-    // item -> (b, k, first channel)
     auto item_coord = [&](int it, int& b, int& k, int& d0) {
-        const int item = static_cast<int>(blockIdx.x) + it * static_cast<int>(gridDim.x);
-        const int db = item % dblocks;
-        const int bk = item / dblocks;
-        k = bk % K;
-        b = bk / K;
-        d0 = db * RB;
+        const uint32_t item = blockIdx.x + static_cast<uint32_t>(it) * gridDim.x;
+        const uint32_t bk = p.div_db.div(item);
+        const uint32_t db = item - bk * static_cast<uint32_t>(dblocks);
+        b = static_cast<int>(p.div_k.div(bk));
+        k = static_cast<int>(bk) - b * K;
+        d0 = static_cast<int>(db) * RB;
     };
-    auto issue_round = [&](int s) {  // all threads (x, dy of the thread's own plane by cp.async); thread 0 adds delta
+    auto round_coord = [&](int s, int& b, int& k, int& d0) {  // global round s of this CTA -> its PP planes
+        const int it = static_cast<int>(p.div_r.div(static_cast<uint32_t>(s)));
+        item_coord(it, b, k, d0);
+        d0 += (s - it * R) * PP;
+    };
+    // ---- producers (thread 0 only): coordinates of global round s of this CTA
+    auto issue_xy = [&](int set, int s) {
         int b, k, d0;
-        item_coord(s / R, b, k, d0);
-        d0 += (s % R) * PP;
-        const int buf = s % XB;
-        const long long pl = static_cast<long long>(b) * D + d0 + q;
-        stage_plane_skewed<ES>(sx + (static_cast<size_t>(buf) * PP + q) * LSK, gx + pl * L, L, j, TP);
-        stage_plane_skewed<4>(sdy + (static_cast<size_t>(buf) * PP + q) * LSK, p.dy + pl * L, L, j, TP);
-        cp_async_arrive(&barX[buf]);
-        if (tid == 0) {
-            mbar_expect_tx(&barD[buf], TOK * sizeof(in_t));
-            bulk_g2s(sd + static_cast<size_t>(buf) * TOK, gd + ((static_cast<long long>(b) * K + k) * D + d0) * L,
-                     TOK * sizeof(in_t), &barD[buf]);
-        }
+        round_coord(s, b, k, d0);
+        const long long pl = (static_cast<long long>(b) * D + d0) * L;
+        mbar_expect_tx(&barXY[set], TOK * (ES + 4));
+        bulk_g2s(sX(set), gx + pl, TOK * ES, &barXY[set]);
+        bulk_g2s(sY(set), p.dy + pl, TOK * 4, &barXY[set]);
     };
-    auto issue_bc = [&](int it) {  // thread 0
+    auto issue_d = [&](int buf, int s) {
+        int b, k, d0;
+        round_coord(s, b, k, d0);
+        mbar_expect_tx(&barD[buf], TOK * ES);
+        bulk_g2s(sD(buf), gd + ((static_cast<long long>(b) * K + k) * D + d0) * L, TOK * ES, &barD[buf]);
+    };
+    auto issue_bc = [&](int it) {
         int b, k, d0;
         item_coord(it, b, k, d0);
-        const uint32_t lb = L * sizeof(in_t);
+        constexpr uint32_t lb = L * ES;
         mbar_expect_tx(&barBC[0], 2 * lb);
         bulk_g2s(sB, gB + (static_cast<long long>(b) * K + k) * L, lb, &barBC[0]);
         bulk_g2s(sC, gC + (static_cast<long long>(b) * K + k) * L, lb, &barBC[0]);
     };
-    if (tid == 0) issue_bc(0);
-    issue_round(0);
+    if (tid == 0) {
+        issue_bc(0);
+        issue_xy(0, 0);
+        issue_d(0, 0);
+    }
 
+    uint32_t phXY0 = 0, phXY1 = 0, phD0 = 0, phD1 = 0;  // mbarrier phase parities (uniform)
+    int ld = 0;                                         // plane set that receives / holds this round's x, dy
     int s = 0;
     for (int it = 0; it < my_items; ++it) {
         int b, k, d00;
         item_coord(it, b, k, d00);
-        uint32_t pk[S / 2];
-        {
-            const uint32_t* tp = reinterpret_cast<const uint32_t*>(p.idx + static_cast<size_t>(k) * L + j * S);
-#pragma unroll
-            for (int m = 0; m < S / 2; ++m) pk[m] = __ldg(tp + m);
-        }
-        float accB[S], accC[S];
-#pragma unroll
-        for (int m = 0; m < S; ++m) accB[m] = 0.f, accC[m] = 0.f;
+        const int kind = (p.kinds >> (4 * k)) & 15;  // 0 identity, 1 reversed identity, 2 permutation, 3 with repeats
+        const bool perm = kind >= 2;
+        const bool dup = kind == 3;
+        const bool dense = kind == 2 && p.sched_used[k] == L;  // a permutation: every schedule entry is a move
+        const uint2* __restrict__ sched = reinterpret_cast<const uint2*>(p.sched + static_cast<size_t>(k) * p.sched_len) + j;
+        const int sched_iters = p.sched_used[k] / (2 * TP);
         mbar_wait(&barBC[0], static_cast<uint32_t>(it & 1));
+        // dB / dC: this thread's tokens of direction k, (b, k) row of the (B, K, L) outputs
+        float* const gdB = p.dBs + (static_cast<size_t>(b) * K + k) * L + j * S;
+        float* const gdC = p.dCs + (static_cast<size_t>(b) * K + k) * L + j * S;
+        const bool odd = j & 1;
+        // ACC (several planes per round, L <= 2304): the PP planes of a round -- and every CTA working on the same
+        // (b, k) -- would all add into the same few KB of dB / dC, and same-address reds serialise at L2.  There the
+        // contributions stay in registers over the item's rounds and are folded over the planes in shared memory
+        // first (one red per token per ITEM).  PP == 1 (L = 9216): per-round vector reds, no accumulator registers.
+        constexpr bool ACC = PP > 1;
+        float accB[ACC ? S : 1], accC[ACC ? S : 1];
+        if constexpr (ACC) {
+#pragma unroll
+            for (int m = 0; m < S; ++m) accB[m] = 0.f, accC[m] = 0.f;
+        }
         const in_t* Bq = sB + j * S;
         const in_t* Cq = sC + j * S;
 
-        for (int r = 0; r < R; ++r, ++s) {
-            const int buf = s % XB;
-            if (XB == 2 && s + 1 < nrounds) issue_round(s + 1);
+        // One round of the item.  REV (compile time): the direction walks the image backwards (token t = pixel
+        // L-1-t): the thread owning tokens [jS, (j+1)S) reads / writes image chunk TP-1-j back to front, no
+        // permutation pass.
+        auto round = [&](auto rev_tag, const int r) __attribute__((always_inline)) {
+            constexpr bool REV = decltype(rev_tag)::value;
+            const bool has_next = s + 1 < nrounds;
+            const int dbuf = PIPE ? (s & 1) : 0;
+            if (PIPE && !perm && has_next && tid == 0) issue_xy(ld ^ 1, s + 1);
+            if (ld == 0) {
+                mbar_wait(&barXY[0], phXY0);
+                phXY0 ^= 1;
+            } else {
+                mbar_wait(&barXY[1], phXY1);
+                phXY1 ^= 1;
+            }
+            int ds = ld;  // set the recurrence passes read
+            if (perm) {
+                // ---- image order -> token order, by the conflict-free schedule (entry: 2*pixel | 2*token << 16).
+                // Batches of 6 moves: all loads, then all stores; the next batch's entries are fetched meanwhile.
+                const in_t* xi = sX(ld) + static_cast<size_t>(q) * L;
+                const float* yi = sY(ld) + static_cast<size_t>(q) * L;
+                in_t* xt = sX(ld ^ 1) + static_cast<size_t>(q) * L;
+                float* yt = sY(ld ^ 1) + static_cast<size_t>(q) * L;
+                auto move = [&](auto dense_tag, const uint2 ea, const uint2 eb, const uint2 ec, int cnt)
+                                __attribute__((always_inline)) {
+                    constexpr bool DENSE = decltype(dense_tag)::value;
+                    const uint32_t ee[6] = {ea.x, ea.y, eb.x, eb.y, ec.x, ec.y};
+                    uint32_t xv[6];
+                    float yv[6];
+#pragma unroll
+                    for (int i = 0; i < 6; ++i) {
+                        const uint32_t e = ee[i];
+                        const uint32_t src2 = (DENSE ? e : (e == 0xFFFFFFFFu ? 0u : e)) & 0xFFFFu;
+                        if (DENSE || (i >> 1) < cnt) {
+                            if constexpr (ES == 2) xv[i] = lds_u16(xi, src2);
+                            else xv[i] = __float_as_uint(lds_f32(xi, 2 * src2));
+                            yv[i] = lds_f32(yi, 2 * src2);
+                        }
+                    }
+#pragma unroll
+                    for (int i = 0; i < 6; ++i) {
+                        const uint32_t e = ee[i];
+                        const uint32_t dst2 = e >> 16;
+                        if (DENSE || ((i >> 1) < cnt && e != 0xFFFFFFFFu)) {
+                            if constexpr (ES == 2) sts_u16(xt, dst2, xv[i]);
+                            else sts_f32(xt, 2 * dst2, __uint_as_float(xv[i]));
+                            sts_f32(yt, 2 * dst2, yv[i]);
+                        }
+                    }
+                };
+                if (dense) walk_schedule<TP, true>(sched, sched_iters, move);
+                else walk_schedule<TP, false>(sched, sched_iters, move);
+                __syncthreads();  // token-ordered set complete; the image-ordered set is dead
+                if (PIPE && has_next && tid == 0) issue_xy(ld, s + 1);
+                ds = ld ^ 1;
+            }
             const int d0 = d00 + r * PP;
             const int d = d0 + q;
             const int row = k * D + d;
@@ -164,32 +242,43 @@ __global__ void __launch_bounds__(NT, 1) ss2d_bwd_kernel(const FusedArgs p, cons
             const float A2 = Ar * kLog2e;
             const float Dd = p.Dp ? __ldg(p.Dp + row) : 0.f;
             const float bias = p.bias ? __ldg(p.bias + row) : 0.f;
-            mbar_wait(&barX[buf], static_cast<uint32_t>((s / XB) & 1));
-            mbar_wait(&barD[buf], static_cast<uint32_t>((s / XB) & 1));
-            const in_t* xq = sx + (static_cast<size_t>(buf) * PP + q) * LSK;
-            const float* yq = sdy + (static_cast<size_t>(buf) * PP + q) * LSK;
+            if (dbuf == 0) {
+                mbar_wait(&barD[0], phD0);
+                phD0 ^= 1;
+            } else {
+                mbar_wait(&barD[1], phD1);
+                phD1 ^= 1;
+            }
+            const int jc = REV ? TP - 1 - j : j;  // chunk of the plane that holds this thread's tokens
+            const in_t* xq = sX(ds) + static_cast<size_t>(q) * L + jc * S;
+            float* yq = sY(ds) + static_cast<size_t>(q) * L + jc * S;
+            in_t* dq = sD(dbuf) + static_cast<size_t>(q) * L + j * S;  // delta / ddelta: always token order
 
-            // ---- pass 1: forward fold (P, Sf) and reverse fold (P, Sr) of the segment
-            float sp[S];
+            // ---- pass 1: forward fold (P, Sf) and reverse fold (P, Sr) of the segment; g_t = C_t * dy_t stays in dh
+            constexpr bool KEEPG = true;  // (recomputing g in pass 2a measured MORE spills, not fewer)
+            constexpr bool KEEPA = PP == 1;  // a_t = exp(delta_t A) kept for passes 2a / 2b where registers allow
+            float sp[S], dh[S], av[KEEPA ? S : 1];
             float P = 1.f, Sf = 0.f, Sr = 0.f;
             {
-                load_tokens<S>(sd + static_cast<size_t>(buf) * TOK + static_cast<size_t>(q) * L + j * S, sp);
+                load_tokens<S>(dq, sp);
 #pragma unroll
                 for (int mp = 0; mp < S / 2; ++mp) {
-                    float Bv[2], Cv[2];
+                    float Bv[2], Cv[2], uv[2], yv[2];
                     load_pair(Bq, mp, Bv[0], Bv[1]);
                     load_pair(Cq, mp, Cv[0], Cv[1]);
+                    chunk_pair<REV>(xq, mp, uv[0], uv[1]);
+                    chunk_pair<REV>(yq, mp, yv[0], yv[1]);
 #pragma unroll
                     for (int h2 = 0; h2 < 2; ++h2) {
                         const int m = 2 * mp + h2;
-                        const int px = h2 ? (pk[mp] >> 16) : (pk[mp] & 0xffffu);
-                        const float u = to_f32(xq[px]);
                         const float raw = sp[m] + bias;
                         float e;
                         sp[m] = !SOFTPLUS ? raw : (ES == 2 ? softplus20_fast(raw) : softplus20(raw, e));
                         const float a = ex2f(sp[m] * A2);
-                        const float bb = sp[m] * Bv[h2] * u;
-                        const float g = Cv[h2] * yq[px];
+                        if constexpr (KEEPA) av[m] = a;
+                        const float bb = sp[m] * Bv[h2] * uv[h2];
+                        const float g = Cv[h2] * yv[h2];
+                        if constexpr (KEEPG) dh[m] = g;
                         Sf = fmaf(a, Sf, bb);
                         P *= a;
                         Sr = fmaf(P, g, Sr);
@@ -213,8 +302,14 @@ __global__ void __launch_bounds__(NT, 1) ss2d_bwd_kernel(const FusedArgs p, cons
                 if (lane == 31) totF[warp] = make_float2(Pf, Sf);
                 if (lane == 0) totR[warp] = make_float2(Pr, Sr);
             }
-            if (tid == 0 && s > 0) bulk_wait_read<0>();  // previous round's staging planes have left
+            if (PIPE && tid == 0 && s > 0) bulk_wait_read<0>();  // previous round's ddelta / du staging have left
             __syncthreads();
+            if (PIPE && has_next && tid == 0) issue_d((s + 1) & 1, s + 1);
+            float* const dxp = PIPE ? sDXs : sY(ld);  // image-ordered du of this round (!PIPE: the dead dy planes)
+            if (dup) {  // directions that skip pixels / hit pixels repeatedly: start from zero, add atomically
+                float4* z = reinterpret_cast<float4*>(dxp);
+                for (int e = tid; e < TOK / 4; e += NT) z[e] = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
             float hin = Sfe, Ein = Sre;
             if (TP > 32) {
                 float hp = 0.f;
@@ -231,96 +326,214 @@ __global__ void __launch_bounds__(NT, 1) ss2d_bwd_kernel(const FusedArgs p, cons
                 Ein = fmaf(Pre, ep, Sre);
             }
             // ---- pass 2a: right-to-left, dh_t = g_t + E_{t+1}
-            float dh[S];
-            {
+            if constexpr (KEEPG) {
+                float E = Ein;
+#pragma unroll
+                for (int m = S - 1; m >= 0; --m) {
+                    const float a = KEEPA ? av[m] : ex2f(sp[m] * A2);
+                    dh[m] += E;
+                    E = a * dh[m];
+                }
+            } else {
                 float E = Ein;
 #pragma unroll
                 for (int mp = S / 2 - 1; mp >= 0; --mp) {
-                    float Cv[2];
+                    float Cv[2], yv[2];
                     load_pair(Cq, mp, Cv[0], Cv[1]);
+                    chunk_pair<REV>(yq, mp, yv[0], yv[1]);
 #pragma unroll
                     for (int h2 = 1; h2 >= 0; --h2) {
                         const int m = 2 * mp + h2;
-                        const int px = h2 ? (pk[mp] >> 16) : (pk[mp] & 0xffffu);
-                        const float g = Cv[h2] * yq[px];
                         const float a = ex2f(sp[m] * A2);
-                        dh[m] = g + E;
+                        dh[m] = fmaf(Cv[h2], yv[h2], E);
                         E = a * dh[m];
                     }
                 }
             }
-            // ---- pass 2b: left-to-right, h_t; emit du, ddelta; accumulate dB, dC, dA, dD, dbias
-            float h = hin, sA = 0.f, sD = 0.f, sb = 0.f;
+            // ---- pass 2b: left-to-right, h_t; du, ddelta; accumulate dB, dC, dA, dD, dbias
+            // dB_t += dh_t*delta_t*u_t and dC_t += dy_t*h_t leave per round as 16-byte vector reds (fp32 adds at L2
+            // over the channels of (b, k)): no accumulator registers live across the rounds of an item.  A chunk of
+            // 18 floats starts 16-byte aligned for even j only, so a lane pair shares its 36 floats as 9 quads: the
+            // even lane sends quads 0-3 from its own values and quad 4 = its last two + the odd lane's first two
+            // (one shuffle pair after the loop), the odd lane quads 5-8 = its values 2..17.
+            float h = hin, sA = 0.f, sDs = 0.f, sb = 0.f;
+            float cB[S], cC[S];
 #pragma unroll
-            for (int m = 0; m < S; ++m) {
-                const int px = (m & 1) ? (pk[m >> 1] >> 16) : (pk[m >> 1] & 0xffffu);
-                const float u = to_f32(xq[px]);
-                const float dyv = yq[px];
-                const float Bm = to_f32(Bq[m]);
-                const float a = ex2f(sp[m] * A2);
-                const float w = a * h;  // a_t * h_{t-1}
-                const float bu = Bm * u;
-                h = fmaf(sp[m], bu, w);  // h_t
-                const float dhs = dh[m] * sp[m];
-                const float du = fmaf(Dd, dyv, dhs * Bm);
-                float dd = dh[m] * fmaf(Ar, w, bu);
-                if (SOFTPLUS) {
-                    // sigmoid(raw) = 1 - exp(-softplus(raw)) = -expm1(-sp); series below 1/8 keeps
-                    // fp32 relative accuracy where 1 - exp(.) would cancel
-                    const float t = sp[m];
-                    if (ES == 2) {  // 16-bit operands: the cancellation error of 1 - exp(-t) (<= 6e-8 absolute) is moot
-                        dd *= 1.0f - ex2f(-t * kLog2e);
+            for (int mp = 0; mp < S / 2; ++mp) {
+                float Bv[2], uv[2], yv[2];
+                load_pair(Bq, mp, Bv[0], Bv[1]);
+                chunk_pair<REV>(xq, mp, uv[0], uv[1]);
+                chunk_pair<REV>(yq, mp, yv[0], yv[1]);
+#pragma unroll
+                for (int h2 = 0; h2 < 2; ++h2) {
+                    const int m = 2 * mp + h2;
+                    const float u = uv[h2], dyv = yv[h2], Bm = Bv[h2];
+                    const float a = KEEPA ? av[m] : ex2f(sp[m] * A2);
+                    const float w = a * h;  // a_t * h_{t-1}
+                    const float bu = Bm * u;
+                    h = fmaf(sp[m], bu, w);  // h_t
+                    const float dhs = dh[m] * sp[m];
+                    const float du = fmaf(Dd, dyv, dhs * Bm);
+                    float dd = dh[m] * fmaf(Ar, w, bu);
+                    if (SOFTPLUS) {
+                        // sigmoid(raw) = 1 - exp(-softplus(raw)) = -expm1(-sp); series below 1/8 keeps fp32 relative
+                        // accuracy where 1 - exp(.) would cancel (moot for 16-bit operands: <= 6e-8 absolute)
+                        const float t = sp[m];
+                        if (ES == 2) {
+                            dd *= 1.0f - ex2f(-t * kLog2e);
+                        } else {
+                            const float ser = t * (1.0f - t * (0.5f - t * (0.16666667f - t * 0.041666668f)));
+                            dd *= (t < 0.125f) ? ser : (1.0f - ex2f(-t * kLog2e));
+                        }
+                    }
+                    if constexpr (ACC) {
+                        accB[m] = fmaf(dhs, u, accB[m]);
+                        accC[m] = fmaf(dyv, h, accC[m]);
                     } else {
-                        const float ser = t * (1.0f - t * (0.5f - t * (0.16666667f - t * 0.041666668f)));
-                        dd *= (t < 0.125f) ? ser : (1.0f - ex2f(-t * kLog2e));
+                        cB[m] = dhs * u;
+                        cC[m] = dyv * h;
+                    }
+                    sA = fmaf(dhs, w, sA);
+                    sDs = fmaf(dyv, u, sDs);
+                    sb += dd;
+                    sp[m] = dd;  // reuse: sp <- ddelta, dh <- du
+                    dh[m] = du;
+                }
+                // quads that are complete after this pair of tokens (m = 2*mp + 1)
+                if (!ACC && mp % 2 == 1 && mp < S / 2 - 1) {  // m = 3, 7, 11, 15: even lanes, values m-3 .. m
+                    if (!odd) {
+                        red_add_v4(gdB + 2 * mp - 2, cB[2 * mp - 2], cB[2 * mp - 1], cB[2 * mp], cB[2 * mp + 1]);
+                        red_add_v4(gdC + 2 * mp - 2, cC[2 * mp - 2], cC[2 * mp - 1], cC[2 * mp], cC[2 * mp + 1]);
                     }
                 }
-                accB[m] = fmaf(dhs, u, accB[m]);
-                accC[m] = fmaf(dyv, h, accC[m]);
-                sA = fmaf(dhs, w, sA);
-                sD = fmaf(dyv, u, sD);
-                sb += dd;
-                sp[m] = dd;  // reuse: sp <- ddelta, dh <- du (token-ordered outputs)
-                dh[m] = du;
+                if (!ACC && mp % 2 == 0 && mp >= 2) {  // m = 5, 9, 13, 17: odd lanes, values m-3 .. m
+                    if (odd) {
+                        red_add_v4(gdB + 2 * mp - 2, cB[2 * mp - 2], cB[2 * mp - 1], cB[2 * mp], cB[2 * mp + 1]);
+                        red_add_v4(gdC + 2 * mp - 2, cC[2 * mp - 2], cC[2 * mp - 1], cC[2 * mp], cC[2 * mp + 1]);
+                    }
+                }
             }
-            store_tokens<S>(so_dd + static_cast<size_t>(q) * L + j * S, sp);
-            store_tokens<S>(so_du + static_cast<size_t>(q) * L + j * S, dh);
+            if constexpr (!ACC) {
+                const float b0 = __shfl_down_sync(0xffffffffu, cB[0], 1, width);
+                const float b1 = __shfl_down_sync(0xffffffffu, cB[1], 1, width);
+                const float c0 = __shfl_down_sync(0xffffffffu, cC[0], 1, width);
+                const float c1 = __shfl_down_sync(0xffffffffu, cC[1], 1, width);
+                if (!odd) {
+                    red_add_v4(gdB + S - 2, cB[S - 2], cB[S - 1], b0, b1);
+                    red_add_v4(gdC + S - 2, cC[S - 2], cC[S - 1], c0, c1);
+                }
+            }
+            store_tokens<S>(dq, sp);  // ddelta over delta, in place (this thread's own chunk)
+            // du: contiguous orders -> straight into the image-ordered plane (!PIPE: over this thread's own dy chunk,
+            // all of which has been read); otherwise token order over dy_tok, scattered below
+            if constexpr (REV) {
+                store_tokens_rev<S>(dxp + static_cast<size_t>(q) * L + jc * S, dh);
+            } else {
+                store_tokens<S>((perm ? yq : dxp + static_cast<size_t>(q) * L + j * S), dh);
+            }
             // ---- per-row sums over L: warp reduce, then over the plane's warps
 #pragma unroll
             for (int off = 16; off > 0; off >>= 1) {
                 if (off < width) {
                     sA += __shfl_xor_sync(0xffffffffu, sA, off, width);
-                    sD += __shfl_xor_sync(0xffffffffu, sD, off, width);
+                    sDs += __shfl_xor_sync(0xffffffffu, sDs, off, width);
                     sb += __shfl_xor_sync(0xffffffffu, sb, off, width);
                 }
             }
-            if (TP > 32 && lane == 0) sred[warp] = sA, sred[NW + warp] = sD, sred[2 * NW + warp] = sb;
+            if (TP > 32 && lane == 0) sred[warp] = sA, sred[NW + warp] = sDs, sred[2 * NW + warp] = sb;
+            if (perm) {
+                __syncthreads();  // du in token order complete (and the zero fill of a dup direction)
+                // ---- token order -> image order: inverse walk of the same schedule
+                const float* ut = sY(ds) + static_cast<size_t>(q) * L;
+                float* di = dxp + static_cast<size_t>(q) * L;
+                auto move = [&](auto dense_tag, const uint2 ea, const uint2 eb, const uint2 ec, int cnt)
+                                __attribute__((always_inline)) {
+                    constexpr bool DENSE = decltype(dense_tag)::value;
+                    const uint32_t ee[6] = {ea.x, ea.y, eb.x, eb.y, ec.x, ec.y};
+                    float v[6];
+#pragma unroll
+                    for (int i = 0; i < 6; ++i) {
+                        const uint32_t e = ee[i];
+                        const uint32_t dst2 = (DENSE ? e : (e == 0xFFFFFFFFu ? 0u : e)) >> 16;
+                        if (DENSE || (i >> 1) < cnt) v[i] = lds_f32(ut, 2 * dst2);
+                    }
+#pragma unroll
+                    for (int i = 0; i < 6; ++i) {
+                        const uint32_t e = ee[i];
+                        const uint32_t src2 = e & 0xFFFFu;
+                        if (DENSE || ((i >> 1) < cnt && e != 0xFFFFFFFFu)) sts_f32(di, 2 * src2, v[i]);
+                    }
+                };
+                const uint2* sc = sched;
+                if (dup) {
+                    // repeated pixels: one move at a time, added with shared-memory atomics (a CAS loop each; the
+                    // schedule still keeps the 32 lanes of a step on distinct banks)
+                    for (int n = 0; n < sched_iters; ++n, sc += TP) {
+                        const uint2 e2 = __ldg(sc);
+                        if (e2.x != 0xFFFFFFFFu) atomicAdd(di + ((e2.x & 0xFFFFu) >> 1), ut[e2.x >> 17]);
+                        if (e2.y != 0xFFFFFFFFu) atomicAdd(di + ((e2.y & 0xFFFFu) >> 1), ut[e2.y >> 17]);
+                    }
+                } else {
+                    if (dense) walk_schedule<TP, true>(sc, sched_iters, move);
+                    else walk_schedule<TP, false>(sc, sched_iters, move);
+                }
+            }
             fence_proxy_async_smem();
             __syncthreads();
             if (tid == 0) {
-                const long long po = ((static_cast<long long>(b) * K + k) * D + d0) * L;
-                bulk_s2g(gdd + po, so_dd, TOK * sizeof(in_t));
-                bulk_s2g(gdu + po, so_du, TOK * sizeof(in_t));
+                bulk_s2g(gdd + ((static_cast<long long>(b) * K + k) * D + d0) * L, sD(dbuf), TOK * ES);
+                bulk_reduce_add_f32_s2g(p.dx + (static_cast<long long>(b) * D + d0) * L, dxp, TOK * 4);
                 bulk_commit();
+                if (!PIPE) {
+                    bulk_wait_read<0>();
+                    if (has_next) {
+                        issue_xy(ld, s + 1);
+                        issue_d(0, s + 1);
+                    }
+                }
             }
-            if (XB == 1 && s + 1 < nrounds) issue_round(s + 1);
             if (TP > 32 && j == 0) {
                 float tA = 0.f, tD = 0.f, tb = 0.f;
                 for (int w = 0; w < nwg; ++w) tA += sred[gw0 + w], tD += sred[NW + gw0 + w], tb += sred[2 * NW + gw0 + w];
-                sA = tA, sD = tD, sb = tb;
+                sA = tA, sDs = tD, sb = tb;
             }
-            if (j == 0) {
-                const size_t o = static_cast<size_t>(b) * K * D + row;
-                p.dA[o] = sA;
-                if (p.dD) p.dD[o] = sD;
-                if (p.dbias) p.dbias[o] = sb;
+            if (j == 0) {  // per-row sums over (b, t): B contributions per row, added at L2 (buffers zeroed by the host)
+                atomicAdd(p.dA + row, sA);
+                if (p.dD) atomicAdd(p.dD + row, sDs);
+                if (p.dbias) atomicAdd(p.dbias + row, sb);
             }
+            if (PIPE && !perm) ld ^= 1;
+            ++s;
+        };
+        for (int r = 0; r < R; ++r) {
+            if (kind == 1) round(std::true_type{}, r);
+            else round(std::false_type{}, r);
         }
-        // ---- item flush: dB / dC of the item's channels (token order, registers) -> global reds
-        {
-            float* gdB = p.dBs + (static_cast<size_t>(b) * K + k) * L + j * S;
-            float* gdC = p.dCs + (static_cast<size_t>(b) * K + k) * L + j * S;
-            if (PP == 1) {
+        if constexpr (ACC) {
+            // ---- item flush: fold the PP planes' partial sums with a binary tree through shared memory (the upper
+            // half of the planes parks its 2*S values, element-major so that lanes hit consecutive banks; the lower
+            // half adds them), then plane 0 sends one red per token.  No shared-memory atomics (a CAS loop each, and
+            // all PP planes would hit the same word in lockstep).  Scratch = a plane buffer nobody uses between items:
+            // the du staging once its bulk reduction has been read (PIPE), the token-ordered dy planes (!PIPE; the
+            // next round's loads went to the other set); (PP/2) * TP * 2S floats = TOK floats at most.
+            if (PIPE && tid == 0) bulk_wait_read<0>();
+            float* f = PIPE ? sDXs : sY(ld ^ 1);
+#pragma unroll 1
+            for (int hp = PP / 2; hp >= 1; hp >>= 1) {
+                __syncthreads();  // (first turn: the staging has left; later turns: the previous readers are done)
+                const int slot = (q - hp) * TP + j, stride = hp * TP;
+                if (q >= hp && q < 2 * hp) {
+#pragma unroll
+                    for (int m = 0; m < S; ++m) f[m * stride + slot] = accB[m], f[(S + m) * stride + slot] = accC[m];
+                }
+                __syncthreads();
+                if (q < hp) {
+                    const int mine = q * TP + j;
+#pragma unroll
+                    for (int m = 0; m < S; ++m) accB[m] += f[m * stride + mine], accC[m] += f[(S + m) * stride + mine];
+                }
+            }
+            if (q == 0) {
 #pragma unroll
                 for (int m = 0; m < S; m += 2) {
                     asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(gdB + m), "f"(accB[m]), "f"(accB[m + 1])
@@ -328,81 +541,87 @@ __global__ void __launch_bounds__(NT, 1) ss2d_bwd_kernel(const FusedArgs p, cons
                     asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(gdC + m), "f"(accC[m]), "f"(accC[m + 1])
                                  : "memory");
                 }
-            } else {
-                // PP planes hold partial sums for the same tokens: add them up in shared memory first
-                if (tid == 0) bulk_wait_read<0>();  // the staging planes are reused as fp32 scratch
-                __syncthreads();
-                float* f = reinterpret_cast<float*>(smem + lay.o0);  // [2][L] floats <= 2 * TOK * ES bytes (PP >= 4)
-                for (int e = tid; e < 2 * L; e += NT) f[e] = 0.f;
-                __syncthreads();
-#pragma unroll
-                for (int m = 0; m < S; ++m) {
-                    atomicAdd(f + j * S + m, accB[m]);
-                    atomicAdd(f + L + j * S + m, accC[m]);
-                }
-                __syncthreads();
-                float* gB2 = p.dBs + (static_cast<size_t>(b) * K + k) * L;
-                float* gC2 = p.dCs + (static_cast<size_t>(b) * K + k) * L;
-                for (int e = tid * 2; e < L; e += NT * 2) {
-                    asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(gB2 + e), "f"(f[e]), "f"(f[e + 1]) : "memory");
-                    asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(gC2 + e), "f"(f[L + e]), "f"(f[L + e + 1])
-                                 : "memory");
-                }
             }
-            __syncthreads();  // everybody is done with sB / sC (and the scratch) before the next item's loads
-            if (tid == 0 && it + 1 < my_items) issue_bc(it + 1);
+            __syncthreads();  // everybody is done with the scratch (and with sB / sC)
         }
+        // the last round's closing barrier has every thread past its reads of sB / sC: the next item's B / C may land
+        if (tid == 0 && it + 1 < my_items) issue_bc(it + 1);
     }
     if (tid == 0) bulk_wait_all<0>();
 }
 
-}  // namespace
-
-size_t ss2d_fused_bwd_smem(int L, int es, int xb) { return BwdLayout(L, es, xb).total; }
-
-// Channels per item: enough rounds that the per-item dB/dC flush is amortised (>= 8 channels).
-static int pick_rounds(const FusedArgs& a) {
-    int R = 1;
-    while (R * a.PP < 8 && a.D % (2 * R * a.PP) == 0) R *= 2;
-    return R;
+// Rounds (channel groups) per item.  More rounds amortise the per-item dB / dC flush (>= 8 channels is the target);
+// fewer rounds make more, smaller items, which matters when the item count is a small non-multiple of the SM count
+// (512 items on 148 persistent CTAs leave a 14 % tail).  Largest R <= target whose last wave is >= 92 % full, else
+// the best-filled one.
+int pick_rounds(int B, int K, int D, int PP, int sms) {
+    int best = 1;
+    double best_eff = -1.0;
+    for (int R = 8; R >= 1; R >>= 1) {
+        if (R * PP > 8 && R > 1) continue;
+        if (D % (R * PP) != 0) continue;
+        const long long items = static_cast<long long>(B) * K * (D / (R * PP));
+        const long long waves = (items + sms - 1) / sms;
+        const double eff = static_cast<double>(items) / static_cast<double>(waves * sms);
+        if (eff >= 0.92) return R;
+        if (eff > best_eff) best_eff = eff, best = R;
+    }
+    return best;
 }
 
-template <typename in_t, bool SOFTPLUS>
-static cudaError_t launch_t(const FusedArgs& a, cudaStream_t st) {
-    const size_t cap = 227 * 1024;
-    auto kern = ss2d_bwd_kernel<in_t, SOFTPLUS>;
-    if (cudaError_t e = ensure_dyn_smem(kern, 227 * 1024); e != cudaSuccess) return e;
+template <typename in_t, bool SOFTPLUS, int TP>
+cudaError_t launch_tp(const FusedBwdArgs& a, cudaStream_t st) {
+    constexpr bool PIPE = sizeof(in_t) == 2;
+    using Lay = DxLayout<sizeof(in_t), TP, PIPE>;
+    if (Lay::total > 227 * 1024) return cudaErrorInvalidConfiguration;
+    auto kern = ss2d_bwd_kernel<in_t, SOFTPLUS, TP, PIPE>;
+    if (cudaError_t e = ensure_dyn_smem(kern, static_cast<int>(Lay::total)); e != cudaSuccess) return e;
     const int sms = device_sms();
-    FusedArgs b = a;
-    b.xb = BwdLayout(a.L, sizeof(in_t), 2).total <= cap ? 2 : 1;
-    const size_t smem = BwdLayout(a.L, sizeof(in_t), b.xb).total;
-    if (smem > cap) return cudaErrorInvalidConfiguration;
-    const int R = pick_rounds(a);
-    const int items = a.B * a.K * (a.D / (R * a.PP));
+    FusedBwdArgs b = a;
+    constexpr int PP = NT / TP;
+    b.R = pick_rounds(a.B, a.K, a.D, PP, sms);
+    b.div_db.init(static_cast<uint32_t>(a.D / (b.R * PP)));
+    b.div_k.init(static_cast<uint32_t>(a.K));
+    b.div_r.init(static_cast<uint32_t>(b.R));
+    const int items = a.B * a.K * (a.D / (b.R * PP));
     const int grid = items < sms ? items : sms;
-    kern<<<grid, NT, smem, st>>>(b, R);
+    kern<<<grid, NT, Lay::total, st>>>(b);
     note_launch();
     return cudaGetLastError();
 }
 
-#ifdef TRAMBA_NEXT
-cudaError_t launch_ss2d_fused_bwd_cg(const FusedArgs& a, int in_dtype, cudaStream_t st);  // csrc/next/
-#endif
-
-cudaError_t launch_ss2d_fused_bwd(const FusedArgs& a, int in_dtype, cudaStream_t st) {
-#ifdef TRAMBA_NEXT  // candidate build (libtramba_b200_next.so): compile-time-geometry kernels where they apply
-    const cudaError_t e = launch_ss2d_fused_bwd_cg(a, in_dtype, st);
-    if (e != cudaErrorNotSupported) return e;
-#endif
-    if (in_dtype == TRAMBA_F32) return a.softplus ? launch_t<float, true>(a, st) : launch_t<float, false>(a, st);
-    if (in_dtype == TRAMBA_BF16)
-        return a.softplus ? launch_t<__nv_bfloat16, true>(a, st) : launch_t<__nv_bfloat16, false>(a, st);
-    return cudaErrorInvalidValue;
+template <typename in_t, bool SOFTPLUS>
+cudaError_t launch_t(const FusedBwdArgs& a, int TP, cudaStream_t st) {
+    switch (TP) {
+        case 512: return launch_tp<in_t, SOFTPLUS, 512>(a, st);
+        case 128: return launch_tp<in_t, SOFTPLUS, 128>(a, st);
+        case 32: return launch_tp<in_t, SOFTPLUS, 32>(a, st);
+        case 8: return launch_tp<in_t, SOFTPLUS, 8>(a, st);
+        default: return cudaErrorInvalidConfiguration;
+    }
 }
 
-bool ss2d_fused_bwd_fits(int L, int es, uint32_t dup_mask, int K) {
-    (void)dup_mask, (void)K;
-    return BwdLayout(L, es, 1).total <= 227 * 1024;
+}  // namespace
+
+bool ss2d_fused_bwd_fits(int L, int es) {
+    const int TP = L / S;
+    if (TP * S != L) return false;
+    auto tot = [&](auto lay) { return decltype(lay)::total <= 227 * 1024; };
+    switch (TP) {
+        case 512: return es == 2 ? tot(DxLayout<2, 512, true>{}) : tot(DxLayout<4, 512, false>{});
+        case 128: return es == 2 ? tot(DxLayout<2, 128, true>{}) : tot(DxLayout<4, 128, false>{});
+        case 32: return es == 2 ? tot(DxLayout<2, 32, true>{}) : tot(DxLayout<4, 32, false>{});
+        case 8: return es == 2 ? tot(DxLayout<2, 8, true>{}) : tot(DxLayout<4, 8, false>{});
+        default: return false;
+    }
+}
+
+cudaError_t launch_ss2d_fused_bwd(const FusedBwdArgs& a, int L, int in_dtype, cudaStream_t st) {
+    const int TP = L / S;
+    if (in_dtype == TRAMBA_F32) return a.softplus ? launch_t<float, true>(a, TP, st) : launch_t<float, false>(a, TP, st);
+    if (in_dtype == TRAMBA_BF16)
+        return a.softplus ? launch_t<__nv_bfloat16, true>(a, TP, st) : launch_t<__nv_bfloat16, false>(a, TP, st);
+    return cudaErrorInvalidValue;
 }
 
 }  // namespace tramba

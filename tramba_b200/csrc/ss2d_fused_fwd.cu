@@ -1,5 +1,14 @@
 // Fused SS2D core, forward (sm_100a).  See ss2d_fused.cuh for the data model.
 // Replaces CrossScan* -> SelectiveScanOflex -> CrossMerge* of Models/vmamba.py:231-259 for N = 1.
+//
+// Persistent CTA (512 threads, one per SM) walks "rounds" of PP whole planes (PP * L = 9216 tokens) and loops the K
+// directions inside; thread = 18 consecutive tokens of one plane: local fold -> shuffle scan -> combine over the
+// plane's warps; every token's output is added to its pixel of the merged plane held in shared memory.  Geometry is a
+// template parameter (TPC = threads per plane = L / 18, XB = staging depth): the index arithmetic folds, the skewed
+// cp.async staging of x is fully unrolled, the un-skewing copy-out divides by a constant, and the per-direction
+// operands (A, D, bias, the thread's 9 table words) are loaded one stage ahead.  (Round 2 measured this
+// compile-time-geometry kernel 12 % faster than the run-time-geometry one it replaces, bit-identical outputs, and on
+// par or ahead of a TMA-staged direction-pairing variant: profiles/r02_fused_ab_bf16.jsonl)
 #include "ss2d_fused.cuh"
 
 namespace tramba {
@@ -32,11 +41,13 @@ struct FwdLayout {
     }
 };
 
-template <typename in_t, bool SOFTPLUS>
+template <typename in_t, bool SOFTPLUS, int TPC, int XB>
 __global__ void __launch_bounds__(NT, 1) ss2d_fwd_kernel(const FusedArgs p) {
     extern __shared__ __align__(128) unsigned char smem[];
     constexpr int ES = sizeof(in_t);
-    const int L = p.L, K = p.K, D = p.D, TP = p.TP, PP = p.PP, XB = p.xb;
+    constexpr int TP = TPC, L = S * TPC, PP = NT / TPC;
+    static_assert(TPC >= 1 && (TPC & (TPC - 1)) == 0 && TPC <= NT, "threads per plane: a power of two <= 512");
+    const int K = p.K, D = p.D;
     const FwdLayout lay(L, ES, XB);
     const int LSK = lay.lsk;
     in_t* sx = reinterpret_cast<in_t*>(smem + lay.x);    // [XB][PP][LSK] skewed
@@ -76,7 +87,7 @@ __global__ void __launch_bounds__(NT, 1) ss2d_fwd_kernel(const FusedArgs p) {
     auto issue_x = [&](int i) {  // all threads: thread (q, j) stages its own plane
         const long long plane0 = (static_cast<long long>(blockIdx.x) + static_cast<long long>(i) * gridDim.x) * PP;
         const int buf = i % XB;
-        stage_plane_skewed<ES>(sx + (static_cast<size_t>(buf) * PP + q) * LSK, gx + (plane0 + q) * L, L, j, TP);
+        stage_plane_skewed_c<ES, TPC>(sx + (static_cast<size_t>(buf) * PP + q) * LSK, gx + (plane0 + q) * L, j);
         cp_async_arrive(&barX[buf]);
     };
     auto issue_dir = [&](int s) {  // thread 0
@@ -93,6 +104,25 @@ __global__ void __launch_bounds__(NT, 1) ss2d_fwd_kernel(const FusedArgs p) {
     issue_x(0);
     if (tid == 0) issue_dir(0);
 
+    // operands of one (round, direction) stage that do not come through shared memory: the row's A / D / bias
+    // and the thread's S table entries (packed pairs).  Loaded one stage ahead of their use.
+    auto load_stage = [&](int d, int k, float& Ar, float& Dd, float& bias, uint32_t (&pk)[S / 2]) {
+        const int row = k * D + d;
+        Ar = __ldg(p.A + row);
+        Dd = p.Dp ? __ldg(p.Dp + row) : 0.f;
+        bias = p.bias ? __ldg(p.bias + row) : 0.f;
+        const uint32_t* tp = reinterpret_cast<const uint32_t*>(p.idx + static_cast<size_t>(k) * L + j * S);
+#pragma unroll
+        for (int m = 0; m < S / 2; ++m) pk[m] = __ldg(tp + m);
+    };
+    auto round_d = [&](int i) {  // channel of this thread's plane in round i
+        const long long plane0 = (static_cast<long long>(blockIdx.x) + static_cast<long long>(i) * gridDim.x) * PP;
+        return static_cast<int>(plane0 % D) + q;
+    };
+    float nAr, nDd, nbias;
+    uint32_t npk[S / 2];
+    load_stage(round_d(0), 0, nAr, nDd, nbias, npk);
+
     int s = 0;
     for (int i = 0; i < my_rounds; ++i) {
         const long long plane0 = (static_cast<long long>(blockIdx.x) + static_cast<long long>(i) * gridDim.x) * PP;
@@ -106,15 +136,13 @@ __global__ void __launch_bounds__(NT, 1) ss2d_fwd_kernel(const FusedArgs p) {
         for (int k = 0; k < K; ++k, ++s) {
             const int buf = s % XB;
             if (XB == 2 && tid == 0 && s + 1 < nstages) issue_dir(s + 1);
-            const int row = k * D + d;
-            const float A2 = __ldg(p.A + row) * kLog2e;
-            const float Dd = p.Dp ? __ldg(p.Dp + row) : 0.f;
-            const float bias = p.bias ? __ldg(p.bias + row) : 0.f;
+            const float A2 = nAr * kLog2e, Dd = nDd, bias = nbias;  // loaded during the previous stage
             uint32_t pk[S / 2];
-            {
-                const uint32_t* tp = reinterpret_cast<const uint32_t*>(p.idx + static_cast<size_t>(k) * L + j * S);
 #pragma unroll
-                for (int m = 0; m < S / 2; ++m) pk[m] = __ldg(tp + m);
+            for (int m = 0; m < S / 2; ++m) pk[m] = npk[m];
+            if (s + 1 < nstages) {  // stage s + 1 = next direction of this round, or direction 0 of the next round
+                if (k + 1 < K) load_stage(d, k + 1, nAr, nDd, nbias, npk);
+                else load_stage(round_d(i + 1), 0, nAr, nDd, nbias, npk);
             }
             mbar_wait(&barD[buf], static_cast<uint32_t>((s / XB) & 1));
 
@@ -199,34 +227,45 @@ __global__ void __launch_bounds__(NT, 1) ss2d_fwd_kernel(const FusedArgs p) {
     }
 }
 
-}  // namespace
-
-size_t ss2d_fused_fwd_smem(int L, int es, int xb) { return FwdLayout(L, es, xb).total; }
-
-template <typename in_t, bool SOFTPLUS>
-static cudaError_t launch_t(const FusedArgs& a, cudaStream_t st) {
-    auto kern = ss2d_fwd_kernel<in_t, SOFTPLUS>;
+template <typename in_t, bool SOFTPLUS, int TPC, int XB>
+static cudaError_t launch_fwd(const FusedArgs& a, cudaStream_t st) {
+    auto kern = ss2d_fwd_kernel<in_t, SOFTPLUS, TPC, XB>;
     if (cudaError_t e = ensure_dyn_smem(kern, 227 * 1024); e != cudaSuccess) return e;
     const int sms = device_sms();
-    const size_t smem = FwdLayout(a.L, sizeof(in_t), a.xb).total;
+    FusedArgs b = a;
+    b.xb = XB;
+    const size_t smem = FwdLayout(a.L, sizeof(in_t), XB).total;
     const int grid = a.rounds < sms ? a.rounds : sms;
-    kern<<<grid, NT, smem, st>>>(a);
+    kern<<<grid, NT, smem, st>>>(b);
     note_launch();
     return cudaGetLastError();
 }
 
-#ifdef TRAMBA_NEXT
-cudaError_t launch_ss2d_fused_fwd_cg(const FusedArgs& a, int in_dtype, cudaStream_t st);  // csrc/next/
-#endif
+template <typename in_t, bool SOFTPLUS, int XB>
+static cudaError_t dispatch_tp(const FusedArgs& a, cudaStream_t st) {
+    switch (a.TP) {  // L = 18 * TP: 144, 576, 2304, 9216 -- every Tramba-V map at 384^2
+        case 8: return launch_fwd<in_t, SOFTPLUS, 8, XB>(a, st);
+        case 32: return launch_fwd<in_t, SOFTPLUS, 32, XB>(a, st);
+        case 128: return launch_fwd<in_t, SOFTPLUS, 128, XB>(a, st);
+        case 512: return launch_fwd<in_t, SOFTPLUS, 512, XB>(a, st);
+        default: return cudaErrorInvalidConfiguration;
+    }
+}
+template <typename in_t, bool SOFTPLUS>
+static cudaError_t dispatch_xb(const FusedArgs& a, cudaStream_t st) {
+    return a.xb == 2 ? dispatch_tp<in_t, SOFTPLUS, 2>(a, st) : dispatch_tp<in_t, SOFTPLUS, 1>(a, st);
+}
 
+}  // namespace
+
+size_t ss2d_fused_fwd_smem(int L, int es, int xb) { return FwdLayout(L, es, xb).total; }
+
+// The staging depth is the caller's choice (a.xb, as tramba_ss2d_fused_fwd picks it: 2 if it fits 227 KB, else 1).
 cudaError_t launch_ss2d_fused_fwd(const FusedArgs& a, int in_dtype, cudaStream_t st) {
-#ifdef TRAMBA_NEXT  // candidate build (libtramba_b200_next.so): compile-time-geometry kernels where they apply
-    const cudaError_t e = launch_ss2d_fused_fwd_cg(a, in_dtype, st);
-    if (e != cudaErrorNotSupported) return e;
-#endif
-    if (in_dtype == TRAMBA_F32) return a.softplus ? launch_t<float, true>(a, st) : launch_t<float, false>(a, st);
+    if (a.L != S * a.TP || a.PP * a.TP != NT) return cudaErrorInvalidConfiguration;
     if (in_dtype == TRAMBA_BF16)
-        return a.softplus ? launch_t<__nv_bfloat16, true>(a, st) : launch_t<__nv_bfloat16, false>(a, st);
+        return a.softplus ? dispatch_xb<__nv_bfloat16, true>(a, st) : dispatch_xb<__nv_bfloat16, false>(a, st);
+    if (in_dtype == TRAMBA_F32) return a.softplus ? dispatch_xb<float, true>(a, st) : dispatch_xb<float, false>(a, st);
     return cudaErrorInvalidValue;
 }
 

@@ -7,9 +7,9 @@
     projections produce them)         A, Ds, delta_bias (K*D) fp32
     y   (B, D, L) fp32, image order -- what CrossMerge*.apply(SelectiveScanOflex.apply(...)) returns
 
-Forward = one kernel (tramba_ss2d_fused_fwd); backward = one kernel (tramba_ss2d_fused_bwd) that
-emits du / ddelta in scan order, followed by the cross-merge of du (= CrossScan.backward).  N = 1
-only; shapes the fused kernels do not cover are reported by `supported()` and run un-fused.
+Forward = one kernel (tramba_ss2d_fused_fwd); backward = one kernel (tramba_ss2d_fused_bwd) that returns dx
+already merged over the K directions (CrossScan*.backward folded in: no du tensor in HBM).  N = 1 only; shapes the
+fused kernels do not cover are reported by `supported()` and run un-fused.
 """
 import ctypes
 import os
@@ -48,16 +48,6 @@ def _idx16(order, H, param, device):
     return hit
 
 
-def _idx16_plain(order, H, param, device):
-    """Device (K, L) uint16 table: pixel of every token (unskewed), bit-exact with the reference generators."""
-    key = ("plain16", order, H, param, device)
-    hit = _idx_cache.get(key)
-    if hit is None:
-        hit = torch.from_numpy(order_table16_host(order, H, param).view(np.int16)).to(device)
-        _idx_cache[key] = hit
-    return hit
-
-
 def token_index(order, H, param, device):
     """(K, L) int64 pixel index of every token (for gathering small per-token tensors into scan order)."""
     key = ("i64", order, H, param, device)
@@ -66,11 +56,6 @@ def token_index(order, H, param, device):
         hit = torch.from_numpy(order_table16_host(order, H, param).astype(np.int64)).to(device)
         _idx_cache[key] = hit
     return hit
-
-
-# TRAMBA_FUSED_BWD=v1: the first-generation backward (du in scan order to HBM + tramba_cross_merge_skewed) instead
-# of the one that folds the merge in (tramba_ss2d_fused_bwd_dx); A/B measurements only
-_BWD_V1 = os.environ.get("TRAMBA_FUSED_BWD", "") == "v1"
 
 
 def _sched(order, H, param, device):
@@ -90,42 +75,10 @@ def _sched(order, H, param, device):
     return hit
 
 
-_FWD_V1 = os.environ.get("TRAMBA_FUSED_FWD", "") == "v1"
-
-
-def _pairs(order, H, param):
-    key = ("pairs", order, H, param)
-    hit = _idx_cache.get(key)
-    if hit is None:
-        K = _lib.lib.tramba_order_num_directions(order)
-        hit = np.empty((K,), dtype=np.int32)
-        _lib.check(_lib.lib.tramba_order_pairs(order, H, H, param, hit.ctypes.data))
-        _idx_cache[key] = hit
-    return hit
-
-
-def fwd_sched_supported(order, K, D, H, W, N, dtype):
-    code = _DTYPE.get(dtype)
-    if code is None or H != W or _FWD_V1:
-        return False
-    return bool(_lib.lib.tramba_ss2d_fused_fwd_sched_supported(order, K, D, H, W, N, code))
-
-
-def bwd_dx_supported(order, K, D, H, W, N, dtype):
-    code = _DTYPE.get(dtype)
-    if code is None or H != W or _BWD_V1:
-        return False
-    return bool(_lib.lib.tramba_ss2d_fused_bwd_dx_supported(order, K, D, H, W, N, code))
-
-
 def supported(order, K, D, H, W, N, dtype, need_bwd=True):
     code = _DTYPE.get(dtype)
     if code is None or H != W:
         return False
-    if need_bwd and bwd_dx_supported(order, K, D, H, W, N, dtype):
-        need_bwd = False          # the merged backward covers it; only the forward's own limits remain
-    if not need_bwd and fwd_sched_supported(order, K, D, H, W, N, dtype):
-        return True
     return bool(_lib.lib.tramba_ss2d_fused_supported(order, K, D, H, W, N, code, int(need_bwd)))
 
 
@@ -155,18 +108,6 @@ class SS2DCoreFused(torch.autograd.Function):
         y = torch.empty((B, D, L), device=x.device, dtype=torch.float32)
         es = x.element_size()
         nbytes = (B * D * L) * (es + 4) + dts.numel() * es + 2 * Bs.numel() * es   # fused core
-        if fwd_sched_supported(order, K, D, H, W, 1, dt):
-            sched, kinds = _sched(order, H, param, x.device)
-            partners = _pairs(order, H, param)
-            with torch.cuda.device(x.device), _lib.timed("ss2d_fused_fwd", nbytes):
-                _lib.check(_lib.lib.tramba_ss2d_fused_fwd_sched(
-                    x.data_ptr(), dts.data_ptr(), Bs.data_ptr(), Cs.data_ptr(), A.data_ptr(), _ptr(Ds),
-                    _ptr(delta_bias), sched.data_ptr(), sched.shape[1], kinds.ctypes.data, partners.ctypes.data,
-                    _idx16_plain(order, H, param, x.device).data_ptr(), y.data_ptr(), order, K, B, D, H, W, 1,
-                    _DTYPE[dt], int(bool(delta_softplus)), _stream()))
-            ctx.save_for_backward(x, dts, Bs, Cs, A, Ds, delta_bias, idx)
-            ctx.meta = (order, param, K, B, D, H, W, bool(delta_softplus))
-            return y
         with torch.cuda.device(x.device), _lib.timed("ss2d_fused_fwd", nbytes):
             _lib.check(_lib.lib.tramba_ss2d_fused_fwd(
                 x.data_ptr(), dts.data_ptr(), Bs.data_ptr(), Cs.data_ptr(), A.data_ptr(), _ptr(Ds),
@@ -179,66 +120,32 @@ class SS2DCoreFused(torch.autograd.Function):
     @staticmethod
     @torch.amp.custom_bwd(device_type="cuda")
     def backward(ctx, dy):
+        """One kernel: CrossMerge*.backward -> SelectiveScanOflex.backward -> CrossScan*.backward (csms6s.py:45-55,
+        914-923, 25-31).  dx comes back merged over the K directions in fp32; du never exists in HBM."""
         x, dts, Bs, Cs, A, Ds, delta_bias, idx = ctx.saved_tensors
         order, param, K, B, D, H, W, softplus = ctx.meta
         L = H * W
         dt = x.dtype
         dy = _c16(dy.float())
-        if bwd_dx_supported(order, K, D, H, W, 1, dt):
-            return SS2DCoreFused._backward_dx(ctx, dy)
-        du = torch.empty((B, K, D, L), device=x.device, dtype=dt)
+        sched, kinds = _sched(order, H, param, x.device)
+        # all fp32 accumulation targets from ONE workspace (-> one memset inside the entry point)
+        n_dx, n_bc, n_row = B * D * L, B * K * L, K * D
+        ws = torch.empty((n_dx + 2 * n_bc + 3 * n_row,), device=x.device, dtype=torch.float32)
+        dx, dBs, dCs, dA, dD, db = torch.split(ws, [n_dx, n_bc, n_bc, n_row, n_row, n_row])
         ddts = torch.empty((B, K, D, L), device=x.device, dtype=dt)
-        dBs = torch.empty((B, K, L), device=x.device, dtype=torch.float32)
-        dCs = torch.empty((B, K, L), device=x.device, dtype=torch.float32)
-        part = torch.zeros((3, B, K * D), device=x.device, dtype=torch.float32)   # dA | dD | dbias partials per b
-        dA, dD, db = part[0], (None if Ds is None else part[1]), (None if delta_bias is None else part[2])
         es = x.element_size()
-        # algorithmic bytes: per direction read x, delta, dy; write du, ddelta; B/C in, dB/dC out
+        # SURVEY 8(d) operator formula per direction (read u, delta, dout; write du, ddelta; B/C in, dB/dC out): what the
+        # kernel REPLACES.  bytes_min = what it must move itself (x, dy once; dx once; delta / ddelta per direction).
         nbytes = K * B * D * L * (4 * es + 4) + 2 * Bs.numel() * (es + 4)
         with torch.cuda.device(x.device), _lib.timed("ss2d_fused_bwd", nbytes):
             _lib.check(_lib.lib.tramba_ss2d_fused_bwd(
-                x.data_ptr(), dts.data_ptr(), Bs.data_ptr(), Cs.data_ptr(), A.data_ptr(), _ptr(Ds),
-                _ptr(delta_bias), idx.data_ptr(), dy.data_ptr(), du.data_ptr(), ddts.data_ptr(), dBs.data_ptr(),
-                dCs.data_ptr(), dA.data_ptr(), _ptr(dD), _ptr(db), order, K, B, D, H, W, 1, _DTYPE[dt],
+                x.data_ptr(), dts.data_ptr(), Bs.data_ptr(), Cs.data_ptr(), A.data_ptr(), _ptr(Ds), _ptr(delta_bias),
+                sched.data_ptr(), sched.shape[1], kinds.ctypes.data, dy.data_ptr(), dx.data_ptr(), ddts.data_ptr(),
+                dBs.data_ptr(), dCs.data_ptr(), dA.data_ptr(), None if Ds is None else dD.data_ptr(),
+                None if delta_bias is None else db.data_ptr(), order, K, B, D, H, W, 1, _DTYPE[dt],
                 int(softplus), _stream()))
-        dx = torch.empty((B, D, H, W), device=x.device, dtype=dt)   # CrossScan*.backward (csms6s.py:25-31 etc.)
-        with torch.cuda.device(x.device), _lib.timed("cross_merge_skewed", (1 + K) * B * D * L * es):
-            _lib.check(_lib.lib.tramba_cross_merge_skewed(du.data_ptr(), dx.data_ptr(), idx.data_ptr(), order, K, B,
-                                                          D, H, W, _DTYPE[dt], _stream()))
-        part = part.sum(1)                                                        # one reduction over the batch
-        return (dx, ddts, dBs.to(dt), dCs.to(dt), part[0], None if Ds is None else part[1],
-                None if delta_bias is None else part[2], None, None, None)
-
-
-def _backward_dx(ctx, dy):
-    """One kernel: CrossMerge*.backward -> SelectiveScanOflex.backward -> CrossScan*.backward (csms6s.py:45-55,
-    914-923, 25-31).  dx comes back merged over the K directions in fp32; du never exists in HBM."""
-    x, dts, Bs, Cs, A, Ds, delta_bias, idx = ctx.saved_tensors
-    order, param, K, B, D, H, W, softplus = ctx.meta
-    L = H * W
-    dt = x.dtype
-    sched, kinds = _sched(order, H, param, x.device)
-    # all fp32 accumulation targets from ONE workspace (-> one memset inside the entry point)
-    n_dx, n_bc, n_row = B * D * L, B * K * L, K * D
-    ws = torch.empty((n_dx + 2 * n_bc + 3 * n_row,), device=x.device, dtype=torch.float32)
-    dx, dBs, dCs, dA, dD, db = torch.split(ws, [n_dx, n_bc, n_bc, n_row, n_row, n_row])
-    ddts = torch.empty((B, K, D, L), device=x.device, dtype=dt)
-    es = x.element_size()
-    # SURVEY 8(d) operator formula per direction (read u, delta, dout; write du, ddelta; B/C in, dB/dC out): what the
-    # kernel REPLACES.  bytes_min = what it must move itself (x, dy once; dx once; delta / ddelta per direction).
-    nbytes = K * B * D * L * (4 * es + 4) + 2 * Bs.numel() * (es + 4)
-    with torch.cuda.device(x.device), _lib.timed("ss2d_fused_bwd", nbytes):
-        _lib.check(_lib.lib.tramba_ss2d_fused_bwd_dx(
-            x.data_ptr(), dts.data_ptr(), Bs.data_ptr(), Cs.data_ptr(), A.data_ptr(), _ptr(Ds), _ptr(delta_bias),
-            sched.data_ptr(), sched.shape[1], kinds.ctypes.data, dy.data_ptr(), dx.data_ptr(), ddts.data_ptr(),
-            dBs.data_ptr(), dCs.data_ptr(), dA.data_ptr(), None if Ds is None else dD.data_ptr(),
-            None if delta_bias is None else db.data_ptr(), order, K, B, D, H, W, 1, _DTYPE[dt],
-            int(softplus), _stream()))
-    return (dx.to(dt).view(B, D, H, W), ddts, dBs.view(B, K, L).to(dt), dCs.view(B, K, L).to(dt), dA,
-            None if Ds is None else dD, None if delta_bias is None else db, None, None, None)
-
-
-SS2DCoreFused._backward_dx = staticmethod(_backward_dx)
+        return (dx.to(dt).view(B, D, H, W), ddts, dBs.view(B, K, L).to(dt), dCs.view(B, K, L).to(dt), dA,
+                None if Ds is None else dD, None if delta_bias is None else db, None, None, None)
 
 
 def ss2d_core_fused(x, dts, Bs, Cs, A, Ds, delta_bias, order, param=0, delta_softplus=True):
@@ -308,6 +215,8 @@ class ProjX(torch.autograd.Function):
         if torch.is_autocast_enabled():
             dt = torch.get_autocast_dtype("cuda")
             W, X = W.to(dt), X.to(dt)
+        elif W.dtype != X.dtype:            # fp32 master weight on lower-precision activations: follow the activations
+            W = W.to(X.dtype)
         ctx.save_for_backward(W, X)
         with torch.autocast("cuda", enabled=False):
             return torch.bmm(W.unsqueeze(0).expand(X.shape[0], -1, -1), X)
@@ -333,6 +242,8 @@ class ProjDt(torch.autograd.Function):
         if torch.is_autocast_enabled():
             dt = torch.get_autocast_dtype("cuda")
             W, X = W.to(dt), X.to(dt)
+        elif W.dtype != X.dtype:            # fp32 master weight on lower-precision activations: follow the activations
+            W = W.to(X.dtype)
         ctx.save_for_backward(W, X)
         with torch.autocast("cuda", enabled=False):
             return torch.matmul(W, X)
