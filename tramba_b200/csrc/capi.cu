@@ -575,7 +575,7 @@ extern "C" int tramba_batch_sum(const void* in, void* out, int B, long long n, i
     if (!in || !out) return TRAMBA_E_NULL;
     if (B <= 0 || n <= 0) return TRAMBA_E_SHAPE;
     if (!ln_dtype_ok(dtype)) return TRAMBA_E_DTYPE;
-    if (!aligned(in, 16) || !aligned(out, 16)) return TRAMBA_E_ALIGN;
+    if (!aligned(in, 16) || !aligned(out, 16)) return TRAMBA_E_ALIGN;  // (rows: n * elem_size % 16 != 0 -> scalar path)
     int rc = check_device();
     if (rc != TRAMBA_OK) return rc;
     return cuda_rc(launch_batch_sum(in, out, B, n, dtype, static_cast<cudaStream_t>(stream)));

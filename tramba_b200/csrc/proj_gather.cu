@@ -71,34 +71,53 @@ __global__ void __launch_bounds__(kThreads) proj_scatter_kernel(const T* __restr
     }
 }
 
-// out[n] = sum_b in[b][n] (fp32 accumulation): the batch reduction of the x_proj / dt_proj weight gradients
-// (dW = sum_b dY_b X_b^T is evaluated as one batched GEMM; B is the image batch, n = one weight tensor).  8 elements
-// per thread, 16-byte accesses; n % 8 == 0 and 16-byte aligned rows take the vector path.
+// out[n] = sum_b in[b][n] (fp32 accumulation): the reduction over the image batch of the x_proj / dt_proj weight
+// gradients (dW = sum_b dY_b X_b^T is evaluated as one batched GEMM) and over the per-tile / per-plane partials of
+// the LayerNorm2d and depthwise-conv weight gradients.  Block = 32 column groups x 8 row slices: a thread adds the rows
+// b = slice, slice + 8, ... of its V columns (16-byte loads), the 8 slices are folded in shared memory.  Columns that
+// are not a multiple of V (or rows that are not 16-byte aligned) take the scalar path.
 template <typename T>
 __global__ void __launch_bounds__(256) batch_sum_kernel(const T* __restrict__ in, T* __restrict__ out, int B, long long n) {
     constexpr int V = 16 / sizeof(T);
-    const long long i0 = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) * V;
-    if (i0 >= n) return;
+    __shared__ float part[8][32][V + 1];
+    const int lane = threadIdx.x & 31, slice = threadIdx.x >> 5;
+    const long long i0 = (static_cast<long long>(blockIdx.x) * 32 + lane) * V;
+    const bool vec = (n % V) == 0;
     float acc[V];
 #pragma unroll
     for (int v = 0; v < V; ++v) acc[v] = 0.f;
-    if (i0 + V <= n && (n % V) == 0) {
-        for (int b = 0; b < B; ++b) {
-            const uint4 q = *reinterpret_cast<const uint4*>(in + static_cast<long long>(b) * n + i0);
-            const T* h = reinterpret_cast<const T*>(&q);
+    if (i0 < n) {
+        if (vec) {
+            for (int b = slice; b < B; b += 8) {
+                const uint4 q = *reinterpret_cast<const uint4*>(in + static_cast<long long>(b) * n + i0);
+                const T* h = reinterpret_cast<const T*>(&q);
 #pragma unroll
-            for (int v = 0; v < V; ++v) acc[v] += to_f32(h[v]);
+                for (int v = 0; v < V; ++v) acc[v] += to_f32(h[v]);
+            }
+        } else {
+            for (int b = slice; b < B; b += 8)
+                for (int v = 0; v < V && i0 + v < n; ++v) acc[v] += to_f32(in[static_cast<long long>(b) * n + i0 + v]);
         }
-        uint4 o;
-        T* h = reinterpret_cast<T*>(&o);
+    }
 #pragma unroll
-        for (int v = 0; v < V; ++v) h[v] = from_f32<T>(acc[v]);
-        *reinterpret_cast<uint4*>(out + i0) = o;
-    } else {
-        for (int v = 0; v < V && i0 + v < n; ++v) {
-            float a = 0.f;
-            for (int b = 0; b < B; ++b) a += to_f32(in[static_cast<long long>(b) * n + i0 + v]);
-            out[i0 + v] = from_f32<T>(a);
+    for (int v = 0; v < V; ++v) part[slice][lane][v] = acc[v];
+    __syncthreads();
+    if (slice == 0 && i0 < n) {
+#pragma unroll
+        for (int v = 0; v < V; ++v) {
+            float t = 0.f;
+#pragma unroll
+            for (int s8 = 0; s8 < 8; ++s8) t += part[s8][lane][v];
+            acc[v] = t;
+        }
+        if (vec) {
+            uint4 o;
+            T* h = reinterpret_cast<T*>(&o);
+#pragma unroll
+            for (int v = 0; v < V; ++v) h[v] = from_f32<T>(acc[v]);
+            *reinterpret_cast<uint4*>(out + i0) = o;
+        } else {
+            for (int v = 0; v < V && i0 + v < n; ++v) out[i0 + v] = from_f32<T>(acc[v]);
         }
     }
 }
@@ -107,8 +126,8 @@ __global__ void __launch_bounds__(256) batch_sum_kernel(const T* __restrict__ in
 
 cudaError_t launch_batch_sum(const void* in, void* out, int B, long long n, int dtype, cudaStream_t st) {
     const int V = dtype == TRAMBA_F32 ? 4 : 8;
-    const long long threads = (n + V - 1) / V;
-    const int grid = static_cast<int>((threads + 255) / 256);
+    const long long groups = (n + V - 1) / V;
+    const int grid = static_cast<int>((groups + 31) / 32);
     if (dtype == TRAMBA_F32)
         batch_sum_kernel<float><<<grid, 256, 0, st>>>(static_cast<const float*>(in), static_cast<float*>(out), B, n);
     else if (dtype == TRAMBA_BF16)

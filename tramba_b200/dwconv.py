@@ -66,7 +66,8 @@ class DWConv2dFn(torch.autograd.Function):
             _lib.check(_lib.lib.tramba_dwconv2d_bwd(
                 x.data_ptr(), w.data_ptr(), None if b is None else b.data_ptr(), dy.data_ptr(), dx.data_ptr(),
                 part.data_ptr(), B, C, H, W, k, _ACT[act], _DTYPE[x.dtype], _stream()))
-        part = part.sum(0)                                                            # one reduction over the batch
+        from .fused import _batch_sum
+        part = _batch_sum(part)                                                       # fold over the batch (library kernel)
         dw = part[:, :k * k].reshape(wshape).to(wdt)
         return dx, dw, None if b is None else part[:, k * k].to(bdt), None
 

@@ -73,8 +73,10 @@ class LayerNorm2dFn(torch.autograd.Function):
                     gy.data_ptr(), x.data_ptr(), w.data_ptr(), None if b is None else b.data_ptr(), mean.data_ptr(),
                     rstd.data_ptr(), gx.data_ptr(), gw.data_ptr(), None if gb is None else gb.data_ptr(),
                     B, C, L, _ACT[act], _DTYPE[x.dtype], _DTYPE[gy.dtype], _stream()))
-        part = part.sum(1)                                      # one reduction for dweight and dbias
-        return gx, part[0].to(wdt), None if b is None else part[1].to(bdt), None, None, None
+        from .fused import _batch_sum                            # fold the per-tile partials (library kernel)
+        gw = _batch_sum(gw)
+        gb = None if gb is None else _batch_sum(gb)
+        return gx, gw.to(wdt), None if gb is None else gb.to(bdt), None, None, None
 
 
 def layer_norm2d(x, weight, bias=None, eps=1e-5, act="none", out_dtype=None):
