@@ -173,26 +173,43 @@ __device__ __forceinline__ void sts_f32(void* base, uint32_t off, float v) {
 // Walks this thread's entries of a permutation schedule (uint2 = two moves; stride TP between a thread's entries) in
 // batches of three loads, the next batch in flight while `move(dense, e0, e1, e2, count)` performs the current one.
 // DENSE: every entry is a move and the entry count is a multiple of three (permutations: sched_len == L).
-template <int TP, bool DENSE, typename Move>
+template <bool FROM_SMEM>
+__device__ __forceinline__ uint2 sched_entry(const uint2* p) {
+    if constexpr (FROM_SMEM) return *p;   // staged in shared memory for the item
+    else return __ldg(p);                 // global (L2-resident table)
+}
+template <int TP, bool DENSE, bool FROM_SMEM = false, typename Move>
 __device__ __forceinline__ void walk_schedule(const uint2* __restrict__ sc, int iters, Move&& move) {
     const uint2 none = make_uint2(0xFFFFFFFFu, 0xFFFFFFFFu);
     constexpr std::integral_constant<bool, DENSE> dense{};
     int n = 0;
     uint2 c0 = none, c1 = none, c2 = none;
-    if (iters >= 3) c0 = __ldg(sc), c1 = __ldg(sc + TP), c2 = __ldg(sc + 2 * TP);
+    if (iters >= 3) c0 = sched_entry<FROM_SMEM>(sc), c1 = sched_entry<FROM_SMEM>(sc + TP), c2 = sched_entry<FROM_SMEM>(sc + 2 * TP);
     for (; n + 3 <= iters; n += 3) {
         sc += 3 * TP;
         uint2 n0 = none, n1 = none, n2 = none;
-        if (n + 6 <= iters) n0 = __ldg(sc), n1 = __ldg(sc + TP), n2 = __ldg(sc + 2 * TP);
+        if (n + 6 <= iters) n0 = sched_entry<FROM_SMEM>(sc), n1 = sched_entry<FROM_SMEM>(sc + TP), n2 = sched_entry<FROM_SMEM>(sc + 2 * TP);
         move(dense, c0, c1, c2, 3);
         c0 = n0, c1 = n1, c2 = n2;
     }
     if (!DENSE && n < iters) {  // 1 or 2 left
         const int cnt = iters - n;
-        c0 = __ldg(sc);
-        c1 = cnt > 1 ? __ldg(sc + TP) : none;
+        c0 = sched_entry<FROM_SMEM>(sc);
+        c1 = cnt > 1 ? sched_entry<FROM_SMEM>(sc + TP) : none;
         move(dense, c0, c1, none, cnt);
     }
+}
+
+// A permutation's schedule has exactly kFusedS / 2 entry pairs per thread: fetch them ALL first (one exposed L2 latency
+// per pass instead of one per batch), then perform the moves three pairs at a time.
+template <int TP, typename Move>
+__device__ __forceinline__ void walk_schedule_dense(const uint2* __restrict__ sc, Move&& move) {
+    constexpr std::integral_constant<bool, true> dense{};
+    uint2 e[kFusedS / 2];
+#pragma unroll
+    for (int i = 0; i < kFusedS / 2; ++i) e[i] = __ldg(sc + i * TP);
+#pragma unroll
+    for (int i = 0; i < kFusedS / 2; i += 3) move(dense, e[i], e[i + 1], e[i + 2], 3);
 }
 
 // Affine-map inclusive scan over `width` lanes (width = 32 or a power of two below).

@@ -51,7 +51,9 @@ struct DxLayout {
     static constexpr size_t dx = d1 + XB;                                     // PIPE: image-ordered du staging
     static constexpr size_t b = PIPE ? dx + YB : dx;
     static constexpr size_t c = b + al16(static_cast<size_t>(L) * ES);
-    static constexpr size_t tot = c + al16(static_cast<size_t>(L) * ES);
+    static constexpr bool SCH = TP < NT;                                      // room for the item's schedule (L <= 2304)
+    static constexpr size_t sch = c + al16(static_cast<size_t>(L) * ES);      // [2 * L] entries (orders with repeats: < 1.6 L)
+    static constexpr size_t tot = sch + (SCH ? 2 * static_cast<size_t>(L) * 4 : 0);
     static constexpr size_t red = tot + 2 * 2 * NW * sizeof(float2);
     static constexpr size_t bar = al16(red + 3 * NW * sizeof(float));
     static constexpr size_t total = bar + 8 * sizeof(uint64_t);
@@ -159,7 +161,19 @@ __global__ void __launch_bounds__(NT, 1) ss2d_bwd_kernel(const FusedBwdArgs p) {
         const bool perm = kind >= 2;
         const bool dup = kind == 3;
         const bool dense = kind == 2 && p.sched_used[k] == L;  // a permutation: every schedule entry is a move
-        const uint2* __restrict__ sched = reinterpret_cast<const uint2*>(p.sched + static_cast<size_t>(k) * p.sched_len) + j;
+        // the direction's permutation schedule: staged in shared memory for the item where there is room (short
+        // planes: no L2 latency inside the permutation passes, no registers to hold entries), else read from L2
+        constexpr bool SCH = Lay::SCH;
+        const uint2* gsched = reinterpret_cast<const uint2*>(p.sched + static_cast<size_t>(k) * p.sched_len);
+        if constexpr (SCH) {
+            uint2* ss = reinterpret_cast<uint2*>(smem + Lay::sch);
+            const int n2 = min(p.sched_used[k], 2 * L) / 2;
+            if (kind >= 2)
+                for (int e = tid; e < n2; e += NT) ss[e] = __ldg(gsched + e);
+            __syncthreads();
+        }
+        const bool sched_in_smem = SCH && p.sched_used[k] <= 2 * L;
+        const uint2* __restrict__ sched = (sched_in_smem ? reinterpret_cast<const uint2*>(smem + Lay::sch) : gsched) + j;
         const int sched_iters = p.sched_used[k] / (2 * TP);
         mbar_wait(&barBC[0], static_cast<uint32_t>(it & 1));
         // dB / dC: this thread's tokens of direction k, (b, k) row of the (B, K, L) outputs
@@ -186,6 +200,13 @@ __global__ void __launch_bounds__(NT, 1) ss2d_bwd_kernel(const FusedBwdArgs p) {
             constexpr bool REV = decltype(rev_tag)::value;
             const bool has_next = s + 1 < nrounds;
             const int dbuf = PIPE ? (s & 1) : 0;
+            // the row's constants first: their L2 latency hides behind the plane wait and the permutation pass
+            const int d0 = d00 + r * PP;
+            const int d = d0 + q;
+            const int row = k * D + d;
+            const float Ar = __ldg(p.A + row);
+            const float Dd = p.Dp ? __ldg(p.Dp + row) : 0.f;
+            const float bias = p.bias ? __ldg(p.bias + row) : 0.f;
             if (PIPE && !perm && has_next && tid == 0) issue_xy(ld ^ 1, s + 1);
             if (ld == 0) {
                 mbar_wait(&barXY[0], phXY0);
@@ -229,19 +250,18 @@ __global__ void __launch_bounds__(NT, 1) ss2d_bwd_kernel(const FusedBwdArgs p) {
                         }
                     }
                 };
-                if (dense) walk_schedule<TP, true>(sched, sched_iters, move);
-                else walk_schedule<TP, false>(sched, sched_iters, move);
+                if (sched_in_smem) {
+                    if (dense) walk_schedule<TP, true, true>(sched, sched_iters, move);
+                    else walk_schedule<TP, false, true>(sched, sched_iters, move);
+                } else {
+                    if (dense) walk_schedule_dense<TP>(sched, move);
+                    else walk_schedule<TP, false>(sched, sched_iters, move);
+                }
                 __syncthreads();  // token-ordered set complete; the image-ordered set is dead
                 if (PIPE && has_next && tid == 0) issue_xy(ld, s + 1);
                 ds = ld ^ 1;
             }
-            const int d0 = d00 + r * PP;
-            const int d = d0 + q;
-            const int row = k * D + d;
-            const float Ar = __ldg(p.A + row);
             const float A2 = Ar * kLog2e;
-            const float Dd = p.Dp ? __ldg(p.Dp + row) : 0.f;
-            const float bias = p.bias ? __ldg(p.bias + row) : 0.f;
             if (dbuf == 0) {
                 mbar_wait(&barD[0], phD0);
                 phD0 ^= 1;
@@ -469,13 +489,18 @@ __global__ void __launch_bounds__(NT, 1) ss2d_bwd_kernel(const FusedBwdArgs p) {
                     // repeated pixels: one move at a time, added with shared-memory atomics (a CAS loop each; the
                     // schedule still keeps the 32 lanes of a step on distinct banks)
                     for (int n = 0; n < sched_iters; ++n, sc += TP) {
-                        const uint2 e2 = __ldg(sc);
+                        const uint2 e2 = sched_in_smem ? *sc : __ldg(sc);
                         if (e2.x != 0xFFFFFFFFu) atomicAdd(di + ((e2.x & 0xFFFFu) >> 1), ut[e2.x >> 17]);
                         if (e2.y != 0xFFFFFFFFu) atomicAdd(di + ((e2.y & 0xFFFFu) >> 1), ut[e2.y >> 17]);
                     }
                 } else {
-                    if (dense) walk_schedule<TP, true>(sc, sched_iters, move);
-                    else walk_schedule<TP, false>(sc, sched_iters, move);
+                    if (sched_in_smem) {
+                        if (dense) walk_schedule<TP, true, true>(sc, sched_iters, move);
+                        else walk_schedule<TP, false, true>(sc, sched_iters, move);
+                    } else {
+                        if (dense) walk_schedule_dense<TP>(sc, move);
+                        else walk_schedule<TP, false>(sc, sched_iters, move);
+                    }
                 }
             }
             fence_proxy_async_smem();
