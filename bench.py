@@ -54,8 +54,10 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="do not capture the step in a CUDA graph")
     ap.add_argument("--unfused", action="store_true", help="op-by-op SS2D path instead of the fused core")
-    ap.add_argument("--no-overlap", action="store_true", help="N > 1: one blocking all-reduce of the flat gradient buffer "
-                    "after backward instead of bucketed all-reduces overlapped with backward")
+    ap.add_argument("--overlap", action="store_true", help="N > 1: bucketed all-reduces launched from inside backward on "
+                    "a side stream instead of one all-reduce after backward (measured slower, see run_ours)")
+    ap.add_argument("--allreduce-dtype", default="bf16", choices=["bf16", "f32"], help="N > 1: dtype of the gradient "
+                    "all-reduce (bf16 halves the bytes on the wire; the optimizer still reads fp32)")
     ap.add_argument("--buckets", type=int, default=4, help="gradient buckets of the overlapped all-reduce")
     ap.add_argument("--no-shadow", action="store_true", help="plain autocast (weights cast on every use) instead of "
                     "bf16 shadow weights refreshed after the optimizer step")
@@ -312,9 +314,13 @@ def run_ours(args):
     if world > 1:
         for p in params:
             dist.broadcast(p.data, 0)
-        if not args.no_overlap:
-            # bucketed all-reduce launched from inside backward on a side stream (captured in the step's CUDA graph)
+        if args.overlap:
+            # bucketed all-reduce launched from inside backward on a side stream (captured in the step's CUDA graph).
+            # Measured SLOWER at N = 2 (31.0 against 30.3 ms): the step's kernels are persistent, one CTA per SM with
+            # ~220 KB of shared memory, so every SM an NCCL CTA sits on delays a whole CTA of theirs.  Off by default.
             fg.enable_overlap(world, n_buckets=args.buckets, stream=torch.cuda.Stream())
+        elif args.allreduce_dtype == "bf16" and amp is not None:
+            fg.enable_compressed_all_reduce(torch.bfloat16)
     net = model
     B = args.batch
     g = torch.Generator().manual_seed(rank)
@@ -526,9 +532,11 @@ def run_ours(args):
                        "img_size": IMG, "global_batch": world * B, "parallelism": f"dp{world}",
                        "weights": "random-init, 111.44 M params", "optimizer": "Adam (fused)",
                        "collective": ("none (single GPU)" if world == 1 else
-                                      f"NCCL all-reduce (AVG) of the flat fp32 gradient buffer, {fg.flat.numel() * 4} bytes per step, "
-                                      + ("one blocking call after backward" if args.no_overlap else
-                                         f"{args.buckets} buckets launched from inside backward on a side stream")),
+                                      "NCCL all-reduce (AVG) of the flat gradient buffer, "
+                                      + (f"{fg.wire.numel() * fg.wire.element_size()} bytes per step in bf16"
+                                         if getattr(fg, "wire", None) is not None else f"{fg.flat.numel() * 4} bytes per step in fp32")
+                                      + (f", {args.buckets} buckets launched from inside backward on a side stream"
+                                         if args.overlap else ", one call between backward and Adam")),
                        "weight_precision": "fp32 masters + bf16 shadows refreshed after Adam" if shadow else "fp32, autocast casts per use",
                        "ss2d_path": "op-by-op kernels" if args.unfused else "fused core kernels",
                        "step_launch": "CUDA graphs (fwd+bwd graph, all-reduce, Adam graph)" if graph is not None else "eager",

@@ -37,6 +37,12 @@ def _worker(rank, world, port, out_dir, overlap=0):
     params = list(model.parameters())
     opt = torch.optim.Adam(params, lr=1e-2)
     fg = FlatGradients(params)
+    if overlap == -1:   # gradients reduced in bf16 on the wire, widened into the fp32 buffer the optimizer reads
+        fg.enable_compressed_all_reduce(torch.bfloat16)
+        overlap = 0
+        wire = True
+    else:
+        wire = False
     if overlap:      # bucketed all-reduce launched from the gradient hooks DURING backward (inline on CPU: stream=None)
         fg.enable_overlap(world, n_buckets=overlap, stream=None)
         assert len(fg.buckets) >= 2 and sum(len(b["idx"]) for b in fg.buckets) == len(params)
@@ -63,14 +69,15 @@ def _worker(rank, world, port, out_dir, overlap=0):
             local = [p.grad.clone() for p in params]
         fg.pack()
         assert all(p.grad.data_ptr() == v.data_ptr() for p, v in zip(params, fg.views))
-        if not overlap:
+        if not overlap and not wire:
             assert all(torch.equal(p.grad, l) for p, l in zip(params, local))
         fg.all_reduce(world)
         for p, l in zip(params, local):
-            mean = l.clone()
+            mean = l.bfloat16().float() if wire else l.clone()     # bf16 wire: every rank's gradient is rounded once
             dist.all_reduce(mean)
             mean /= world
-            worst = max(worst, float((mean - p.grad).abs().max()))
+            err = float((mean - p.grad).abs().max())
+            worst = max(worst, err / (float(mean.abs().max()) + 1e-12) if wire else err)   # bf16 wire: relative error
         opt.step()
     w = torch.cat([p.detach().flatten() for p in params])
     ws = [torch.empty_like(w) for _ in range(world)]
@@ -99,6 +106,19 @@ def test_flat_gradients_overlapped_buckets_world2_gloo(tmp_path):
     for r in range(world):
         worst, same = np.load(tmp_path / f"r{r}.npy")
         assert worst < 1e-6, worst
+        assert same == 1.0
+
+
+@pytest.mark.timeout(300)
+def test_flat_gradients_bf16_wire_world2_gloo(tmp_path):
+    """bench.py's default at N > 1 in the bf16 step: the all-reduce runs on a bf16 copy of the gradients (half the
+    bytes), the optimizer reads the widened fp32 buffer.  Mean of the per-rank (bf16-rounded) gradients within bf16
+    resolution on every rank; replicas stay identical."""
+    world = 2
+    mp.spawn(_worker, args=(world, _free_port(), str(tmp_path), -1), nprocs=world, join=True)
+    for r in range(world):
+        worst, same = np.load(tmp_path / f"r{r}.npy")
+        assert worst < 2.0 ** -6, worst       # a few bf16 ulps of the tensor's largest entry
         assert same == 1.0
 
 

@@ -1,11 +1,11 @@
 #!/bin/bash
-# N-GPU training-step bench (one process per GPU, NCCL): overlapped bucketed all-reduce vs one blocking all-reduce.
+# N-GPU training-step bench (one process per GPU, NCCL): gradient all-reduce in bf16 (default) vs fp32.
 #   gpurun --gpus N --timeout 1200 -- 'bash tools/gpu_multi.sh N'
 N=${1:-2}
 mkdir -p gpurun_out
 run() {  # tag, extra args
   local tag=$1; shift
-  timeout 500 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 \
+  timeout 240 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 \
     bench.py --gpus $N --steps 20 --warmup 5 --no-cpu-baseline "$@" > gpurun_out/bench_${N}gpu_$tag.json 2> gpurun_out/bench_${N}gpu_$tag.err
   echo "bench N=$N $tag rc=$?"
   python - <<PY
@@ -19,5 +19,5 @@ PY
 }
 timeout 400 python bench.py --gpus 1 --steps 20 --warmup 5 --no-cpu-baseline > gpurun_out/bench_1gpu_ref.json 2> gpurun_out/bench_1gpu_ref.err
 python -c "import json; d=json.loads(open('gpurun_out/bench_1gpu_ref.json').read().strip().splitlines()[-1]); print('1 gpu', round(d['value'],1), round(d['ms_per_step'],3))"
-run overlap
-run blocking --no-overlap
+run bf16wire
+run f32wire --allreduce-dtype f32

@@ -1,5 +1,5 @@
 """profiles/roofline_traffic.json from an ncu per-launch DRAM-byte list of one bench step:
-    ncu --profile-from-start off -k regex:'ss2d_|ln2d_|dwconv_|dct2d_|merge_skewed|proj_' \
+    ncu --profile-from-start off -k regex:'ss2d_|ln2d_|dwconv_|dct2d_|batch_sum|proj_' \
         --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --csv --log-file X.csv python bench.py ...
 Usage: python tools/make_traffic_json.py X.csv profiles/roofline_traffic.json
 Writes {bench kind: mean (dram read + write) bytes per launch} -- bench.py's roofline.traffic."""
@@ -8,7 +8,7 @@ import csv
 import json
 import sys
 
-KIND = {"ss2d_bwd_kernel": "ss2d_fused_bwd", "ss2d_fwd_kernel": "ss2d_fused_fwd", "merge_skewed_kernel": "cross_merge_skewed",
+KIND = {"ss2d_bwd_kernel": "ss2d_fused_bwd", "ss2d_fwd_kernel": "ss2d_fused_fwd", "batch_sum": "batch_sum",
         "ln2d_fwd": "layernorm2d_fwd", "ln2d_bwd": "layernorm2d_bwd", "dct2d_fwd": "dct2d_fwd", "dct2d_bwd": "dct2d_bwd",
         "proj_gather": "proj_gather", "proj_scatter": "proj_scatter", "dwconv_fwd": "dwconv_fwd", "dwconv_bwd": "dwconv_bwd"}
 UNIT = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}

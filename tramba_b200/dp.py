@@ -177,18 +177,38 @@ class FlatGradients:
                     s.grad = None
                 p.grad = v
             return
-        got = [(v, s.grad) for v, s in zip(self.views, self.sources) if s.grad is not None]
+        dst = self.wire_views if getattr(self, "wire", None) is not None else self.views   # compressed: reduce first
+        got = [(v, s.grad) for v, s in zip(dst, self.sources) if s.grad is not None]
         if got:
             torch._foreach_copy_([v for v, _ in got], [g for _, g in got])
-        for v, p, s in zip(self.views, self.params, self.sources):
+        for v, w, p, s in zip(self.views, dst, self.params, self.sources):
             if s.grad is None:          # parameter unused in this step
-                v.zero_()
+                w.zero_()
             if s is not p:
                 s.grad = None
             p.grad = v
 
+    def enable_compressed_all_reduce(self, dtype=torch.bfloat16):
+        """All-reduce the gradients in `dtype` (half the bytes on the wire): pack() writes them into a second flat
+        buffer of that dtype, all_reduce() reduces it and widens it into the fp32 flat buffer the optimizer reads.  With
+        bf16 shadow weights most gradients ARE bf16 already, so only the few fp32-owned parameters (norms, A_logs, Ds,
+        biases) are rounded."""
+        self.wire = torch.zeros_like(self.flat, dtype=dtype)
+        self.wire_views, off = [], 0
+        for p in self.params:
+            self.wire_views.append(self.wire[off:off + p.numel()].view_as(p))
+            off += p.numel()
+
     def all_reduce(self, world):
         if world <= 1 or getattr(self, "overlap", False):     # overlapped mode: done bucket by bucket during backward
+            return
+        if getattr(self, "wire", None) is not None:
+            if dist.get_backend() == "nccl":
+                dist.all_reduce(self.wire, op=dist.ReduceOp.AVG)
+            else:
+                dist.all_reduce(self.wire, op=dist.ReduceOp.SUM)
+                self.wire.div_(world)
+            self.flat.copy_(self.wire)
             return
         if dist.get_backend() == "nccl":
             dist.all_reduce(self.flat, op=dist.ReduceOp.AVG)
