@@ -82,8 +82,7 @@ def test_harness_on_the_simulated_library_matches_reference_golden(backend="sim"
     """The whole Tramba-V forward + backward on the product's OWN C ABI and kernel sources, compiled as host code and
     executed on the CPU simulator (tools/cpu_sim): 27 fused-core + 6 op-by-op SS2D calls, 108 LayerNorm2d launches
     (cluster kernels included), depthwise convs, proj gathers, 3 tensor-pipe DCTs -- against the REAL reference's
-    fixture.  Nothing is computed by the oracle here.  "candidate-kernels": the same with the launchers dispatching to
-    the compile-time-geometry kernels of csrc/next/ (-DTRAMBA_NEXT), which have not run on a GPU yet."""
+    fixture.  Nothing is computed by the oracle here."""
     from _abi_emulator import installed
     m = det_fill(build_model(img_size=384, dims=int(GOLD["dims"]))).eval()
     with installed(backend) as lib:

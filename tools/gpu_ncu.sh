@@ -10,14 +10,24 @@ cap() {  # name, kernel regex, kernel_bench args...
   python tools/ncu_raw_summary.py /tmp/$name.ncu-rep > gpurun_out/${name}_summary.txt 2>&1
   ncu -i /tmp/$name.ncu-rep --page source --print-source cuda,sass --csv > /tmp/$name.csv 2>/dev/null
   python tools/ncu_cuda_lines.py /tmp/$name.csv 70 > gpurun_out/${name}_cuda_lines.txt 2>&1
+  ncu -i /tmp/$name.ncu-rep --page source --print-source sass --csv > /tmp/${name}_sass.csv 2>/dev/null
+  python tools/ncu_src_summary.py /tmp/${name}_sass.csv 40 > gpurun_out/${name}_sass_mix.txt 2>&1
+  python tools/ncu_stall_reasons.py 12 < /tmp/${name}_sass.csv > gpurun_out/${name}_stall_reasons.txt 2>&1
   ncu -i /tmp/$name.ncu-rep --page raw --csv --metrics dram__bytes_read.sum,dram__bytes_write.sum,lts__t_bytes.sum,smsp__inst_executed_pipe_fma.sum,smsp__inst_executed_pipe_alu.sum,smsp__inst_executed_pipe_xu.sum,smsp__inst_executed_pipe_lsu.sum,sm__inst_executed_pipe_fma.sum,sm__inst_executed_pipe_alu.sum,sm__inst_executed_pipe_xu.sum,sm__inst_executed_pipe_lsu.sum > gpurun_out/${name}_pipes.csv 2>/dev/null
-  rm -f /tmp/$name.ncu-rep /tmp/$name.csv
+  rm -f /tmp/$name.ncu-rep /tmp/$name.csv /tmp/${name}_sass.csv
 }
+WHAT=${1:-all}
+if [ "$WHAT" = all ] || [ "$WHAT" = fused ]; then
 cap r02_ncu_fbwd_enc0 ss2d_bwd_kernel --dtype bf16 --fused-only --only enc0
+cap r02_ncu_ffwd_enc0 ss2d_fwd_kernel --dtype bf16 --fused-only --only enc0
+fi
+if [ "$WHAT" = all ]; then
 cap r02_ncu_fbwd_dec96 ss2d_bwd_kernel --dtype bf16 --fused-only --only dec96
 cap r02_ncu_fbwd_enc2 ss2d_bwd_kernel --dtype bf16 --fused-only --only enc2
-cap r02_ncu_ffwd_enc0 ss2d_fwd_kernel --dtype bf16 --fused-only --only enc0
+fi
+if [ "$WHAT" = all ] || [ "$WHAT" = op ]; then
 cap r02_ncu_sscan_bwd_bf16_enc0 sscan_bwd_regular --dtype bf16 --only enc0
 cap r02_ncu_sscan_bwd_f32_enc0 sscan_bwd_regular --dtype f32 --only enc0
 cap r02_ncu_sscan_fwd_bf16_enc0 sscan_fwd_regular --dtype bf16 --only enc0
+fi
 ls -la gpurun_out

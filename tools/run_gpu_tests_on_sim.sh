@@ -1,12 +1,11 @@
 #!/bin/bash
 # Runs the `-m gpu` test files WITHOUT a GPU, against the product's own C ABI and kernel sources executed on the CPU
 # simulator (tools/cpu_sim; tests/conftest.py: TRAMBA_GPU_TESTS_ON_SIM).  A few minutes on 8 cores.
-#   bash tools/run_gpu_tests_on_sim.sh            product kernels
-#   bash tools/run_gpu_tests_on_sim.sh next       candidate kernels of csrc/next/ dispatched (-DTRAMBA_NEXT)
+#   bash tools/run_gpu_tests_on_sim.sh
 # Extra checks: TRAMBA_SIM_LAZY=1 (asynchronous copies land at their wait), TRAMBA_SIM_SCHEDULE=n (thread order).
-mode=${1:-1}
+mode=1
 rc=0
-for f in test_gpu_scan_merge test_gpu_proj_gather test_gpu_ss2d test_gpu_fused test_dwconv test_layernorm2d \
+for f in test_gpu_scan_merge test_gpu_proj_gather test_gpu_ss2d test_gpu_fused test_gpu_fused_sites test_dwconv test_layernorm2d \
          test_gpu_dct test_z_gpu_ablation; do
   out=$(TRAMBA_GPU_TESTS_ON_SIM=$mode timeout 1800 python -m pytest tests/$f.py -m gpu -q --timeout 900 -p no:cacheprovider 2>&1 | tail -1)
   echo "== $f: $out"

@@ -50,9 +50,13 @@ struct DxLayout {
     static constexpr size_t d1 = PIPE ? d0 + XB : d0;
     static constexpr size_t dx = d1 + XB;                                     // PIPE: image-ordered du staging
     static constexpr size_t b = PIPE ? dx + YB : dx;
-    static constexpr size_t c = b + al16(static_cast<size_t>(L) * ES);
+    // fp32 operands at L = 9216: the (b, k) rows of B and C do not fit next to the planes; they are read from global
+    // memory instead (36.9 KB rows shared by every channel of (b, k): L2 hits)
+    static constexpr bool BCG = !PIPE && TP == NT;
+    static constexpr size_t bcb = BCG ? 0 : al16(static_cast<size_t>(L) * ES);
+    static constexpr size_t c = b + bcb;
     static constexpr bool SCH = TP < NT;                                      // room for the item's schedule (L <= 2304)
-    static constexpr size_t sch = c + al16(static_cast<size_t>(L) * ES);      // [2 * L] entries (orders with repeats: < 1.6 L)
+    static constexpr size_t sch = c + bcb;                                    // [2 * L] entries (orders with repeats: < 1.6 L)
     static constexpr size_t tot = sch + (SCH ? 2 * static_cast<size_t>(L) * 4 : 0);
     static constexpr size_t red = tot + 2 * 2 * NW * sizeof(float2);
     static constexpr size_t bar = al16(red + 3 * NW * sizeof(float));
@@ -145,8 +149,9 @@ __global__ void __launch_bounds__(NT, 1) ss2d_bwd_kernel(const FusedBwdArgs p) {
         bulk_g2s(sB, gB + (static_cast<long long>(b) * K + k) * L, lb, &barBC[0]);
         bulk_g2s(sC, gC + (static_cast<long long>(b) * K + k) * L, lb, &barBC[0]);
     };
+    constexpr bool BCG = Lay::BCG;
     if (tid == 0) {
-        issue_bc(0);
+        if (!BCG) issue_bc(0);
         issue_xy(0, 0);
         issue_d(0, 0);
     }
@@ -175,7 +180,7 @@ __global__ void __launch_bounds__(NT, 1) ss2d_bwd_kernel(const FusedBwdArgs p) {
         const bool sched_in_smem = SCH && p.sched_used[k] <= 2 * L;
         const uint2* __restrict__ sched = (sched_in_smem ? reinterpret_cast<const uint2*>(smem + Lay::sch) : gsched) + j;
         const int sched_iters = p.sched_used[k] / (2 * TP);
-        mbar_wait(&barBC[0], static_cast<uint32_t>(it & 1));
+        if (!BCG) mbar_wait(&barBC[0], static_cast<uint32_t>(it & 1));
         // dB / dC: this thread's tokens of direction k, (b, k) row of the (B, K, L) outputs
         float* const gdB = p.dBs + (static_cast<size_t>(b) * K + k) * L + j * S;
         float* const gdC = p.dCs + (static_cast<size_t>(b) * K + k) * L + j * S;
@@ -190,8 +195,8 @@ __global__ void __launch_bounds__(NT, 1) ss2d_bwd_kernel(const FusedBwdArgs p) {
 #pragma unroll
             for (int m = 0; m < S; ++m) accB[m] = 0.f, accC[m] = 0.f;
         }
-        const in_t* Bq = sB + j * S;
-        const in_t* Cq = sC + j * S;
+        const in_t* Bq = BCG ? gB + (static_cast<size_t>(b) * K + k) * L + j * S : sB + j * S;
+        const in_t* Cq = BCG ? gC + (static_cast<size_t>(b) * K + k) * L + j * S : sC + j * S;
 
         // One round of the item.  REV (compile time): the direction walks the image backwards (token t = pixel
         // L-1-t): the thread owning tokens [jS, (j+1)S) reads / writes image chunk TP-1-j back to front, no
@@ -570,7 +575,7 @@ __global__ void __launch_bounds__(NT, 1) ss2d_bwd_kernel(const FusedBwdArgs p) {
             __syncthreads();  // everybody is done with the scratch (and with sB / sC)
         }
         // the last round's closing barrier has every thread past its reads of sB / sC: the next item's B / C may land
-        if (tid == 0 && it + 1 < my_items) issue_bc(it + 1);
+        if (!BCG && tid == 0 && it + 1 < my_items) issue_bc(it + 1);
     }
     if (tid == 0) bulk_wait_all<0>();
 }
