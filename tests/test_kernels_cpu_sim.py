@@ -134,7 +134,7 @@ def test_fused_kernels_on_the_cpu_simulator(sim, fam, H, D, B, bf16, grid, lazy)
     out, have_bwd, ref_y, ref_g = _run(sim, fam, H, D, B, bf16, grid)
     rtol = 1e-2 if bf16 else 1e-3
     _close(out["y"], ref_y, 1e-3, "y")
-    assert have_bwd == (bf16 or H < 96)
+    assert have_bwd            # every Tramba-V geometry, both dtypes (fp32 at 96 x 96 reads B / C from global memory)
     if have_bwd:
         _close(out["dx"].reshape(ref_g[0].shape), ref_g[0], rtol, "dx")
         _close(_host(out["ddts"], bf16).numpy(), ref_g[1], rtol, "ddelta")
