@@ -227,10 +227,12 @@ TRAMBA_API int tramba_dct2d_bwd(const float* ghigh, const float* glow, const flo
  * -------------------------------------------------------------------------------------- */
 TRAMBA_API int tramba_proj_gather(const void* src, void* dts, void* Bs, void* Cs, const int32_t* plan_dev, int K,
                                   int B, int R, int N, int L, int dtype, void* stream);
-/* out (n) = sum_b in (B, n), fp32 accumulation, same dtype in and out: the reduction over the image batch of the
+/* out (G, n) = sum_b in (G, B, n), fp32 accumulation, same dtype in and out: the reduction over the image batch of the
  * x_proj / dt_proj weight gradients, which the host evaluates as ONE batched GEMM dY_b . X_b^T (the reference's
- * grouped conv1d weight gradient, Models/vmamba.py:233-236 backward).  in / out 16-byte aligned. */
-TRAMBA_API int tramba_batch_sum(const void* in, void* out, int B, long long n, int dtype, void* stream);
+ * grouped conv1d weight gradient, Models/vmamba.py:233-236 backward), and the fold of the per-tile weight / bias
+ * gradient partials of LayerNorm2d (G = 2: dweight | dbias in one launch) and the depthwise conv.  in / out 16-byte
+ * aligned; G > 1 needs B * n * elem_size % 16 == 0. */
+TRAMBA_API int tramba_batch_sum(const void* in, void* out, int G, int B, long long n, int dtype, void* stream);
 TRAMBA_API int tramba_proj_scatter(const void* gdts, const void* gBs, const void* gCs, void* gsrc,
                                    const int32_t* plan_dev, int K, int B, int R, int N, int L, int dtype, int bc_dtype,
                                    void* stream);

@@ -173,8 +173,8 @@ def tramba_ss2d_fused_bwd(x, dts, Bs, Cs, A, Dp, bias, sched, sched_len, kinds, 
     return 0
 
 
-def tramba_batch_sum(src, out, B, n, dtype, stream):
-    _buf(out, (n,), dtype).set(_buf(src, (B, n), dtype).get().sum(0))
+def tramba_batch_sum(src, out, G, B, n, dtype, stream):
+    _buf(out, (G, n), dtype).set(_buf(src, (G, B, n), dtype).get().sum(1))
     return 0
 
 

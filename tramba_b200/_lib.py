@@ -47,7 +47,7 @@ SIGNATURES = {
     "tramba_layernorm2d_bwd": (_i, [_vp, _vp, _fp, _fp, _fp, _fp, _vp, _fp, _fp] + [_i] * 6 + [_vp]),
     "tramba_proj_gather": (_i, [_vp, _vp, _vp, _vp, _i32p] + [_i] * 6 + [_vp]),
     "tramba_proj_scatter": (_i, [_vp, _vp, _vp, _vp, _i32p] + [_i] * 7 + [_vp]),
-    "tramba_batch_sum": (_i, [_vp, _vp, _i, ctypes.c_longlong, _i, _vp]),
+    "tramba_batch_sum": (_i, [_vp, _vp, _i, _i, ctypes.c_longlong, _i, _vp]),
     "tramba_dwconv2d_supported": (_i, [_i] * 5),
     "tramba_dwconv2d_fwd": (_i, [_vp, _fp, _fp, _vp] + [_i] * 7 + [_vp]),
     "tramba_dwconv2d_bwd": (_i, [_vp, _fp, _fp, _vp, _vp, _fp] + [_i] * 7 + [_vp]),

@@ -36,7 +36,7 @@ cudaError_t launch_dct2d_fwd(const float* x, const float* wy, const float* wx, f
 cudaError_t launch_dct2d_bwd(const float* ghigh, const float* glow, const float* wy, const float* wx, float* gx,
                              int planes, int H, int W, cudaStream_t st);
 
-cudaError_t launch_batch_sum(const void* in, void* out, int B, long long n, int dtype, cudaStream_t st);
+cudaError_t launch_batch_sum(const void* in, void* out, int G, int B, long long n, int dtype, cudaStream_t st);
 
 bool dct2d_tc_supported(int H, int W);
 cudaError_t launch_dct2d_fwd_tc(const float* x, const float* wy, const float* wx, float* high, float* low, int planes,
@@ -570,15 +570,17 @@ extern "C" int tramba_proj_gather(const void* src, void* dts, void* Bs, void* Cs
     return cuda_rc(launch_proj_gather(src, dts, Bs, Cs, plan_dev, K, B, R, N, L, dtype, static_cast<cudaStream_t>(stream)));
 }
 
-// Batch reduction of the projection weight gradients (Models/vmamba.py:233-236 backward): out (n) = sum_b in (B, n).
-extern "C" int tramba_batch_sum(const void* in, void* out, int B, long long n, int dtype, void* stream) {
+// Batch reduction of the projection weight gradients (Models/vmamba.py:233-236 backward) and of per-tile partials:
+// out (G, n) = sum_b in (G, B, n).
+extern "C" int tramba_batch_sum(const void* in, void* out, int G, int B, long long n, int dtype, void* stream) {
     if (!in || !out) return TRAMBA_E_NULL;
-    if (B <= 0 || n <= 0) return TRAMBA_E_SHAPE;
+    if (G <= 0 || G > 65535 || B <= 0 || n <= 0) return TRAMBA_E_SHAPE;
     if (!ln_dtype_ok(dtype)) return TRAMBA_E_DTYPE;
     if (!aligned(in, 16) || !aligned(out, 16)) return TRAMBA_E_ALIGN;  // (rows: n * elem_size % 16 != 0 -> scalar path)
+    if (G > 1 && (n * (dtype == TRAMBA_F32 ? 4 : 2)) % 16 != 0) return TRAMBA_E_ALIGN;  // every group 16-byte aligned
     int rc = check_device();
     if (rc != TRAMBA_OK) return rc;
-    return cuda_rc(launch_batch_sum(in, out, B, n, dtype, static_cast<cudaStream_t>(stream)));
+    return cuda_rc(launch_batch_sum(in, out, G, B, n, dtype, static_cast<cudaStream_t>(stream)));
 }
 
 extern "C" int tramba_proj_scatter(const void* gdts, const void* gBs, const void* gCs, void* gsrc,

@@ -81,6 +81,7 @@ __global__ void __launch_bounds__(256) batch_sum_kernel(const T* __restrict__ in
     constexpr int V = 16 / sizeof(T);
     __shared__ float part[8][32][V + 1];
     const int lane = threadIdx.x & 31, slice = threadIdx.x >> 5;
+    in += static_cast<long long>(blockIdx.y) * B * n, out += static_cast<long long>(blockIdx.y) * n;  // group
     const long long i0 = (static_cast<long long>(blockIdx.x) * 32 + lane) * V;
     const bool vec = (n % V) == 0;
     float acc[V];
@@ -124,10 +125,10 @@ __global__ void __launch_bounds__(256) batch_sum_kernel(const T* __restrict__ in
 
 }  // namespace
 
-cudaError_t launch_batch_sum(const void* in, void* out, int B, long long n, int dtype, cudaStream_t st) {
+cudaError_t launch_batch_sum(const void* in, void* out, int G, int B, long long n, int dtype, cudaStream_t st) {
     const int V = dtype == TRAMBA_F32 ? 4 : 8;
     const long long groups = (n + V - 1) / V;
-    const int grid = static_cast<int>((groups + 31) / 32);
+    const dim3 grid(static_cast<unsigned>((groups + 31) / 32), static_cast<unsigned>(G));
     if (dtype == TRAMBA_F32)
         batch_sum_kernel<float><<<grid, 256, 0, st>>>(static_cast<const float*>(in), static_cast<float*>(out), B, n);
     else if (dtype == TRAMBA_BF16)

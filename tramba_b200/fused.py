@@ -193,13 +193,19 @@ def proj_gather(src, order, param, H, R, N):
     return ProjGather.apply(src, order, param, H, R, N)
 
 
-def _batch_sum(t):
-    """(B, ...) -> (...): sum over the leading (image batch) axis on the library's kernel (fp32 accumulation)."""
+def _batch_sum(t, groups=0):
+    """(B, ...) -> (...): sum over the leading (image batch) axis on the library's kernel (fp32 accumulation).
+    groups = G > 0: (G, B, ...) -> (G, ...) in one launch."""
     t = _c16(t)
-    out = torch.empty(t.shape[1:], device=t.device, dtype=t.dtype)
+    G = max(groups, 1)
+    assert groups == 0 or t.shape[0] == groups
+    out = torch.empty(t.shape[2:] if groups else t.shape[1:], device=t.device, dtype=t.dtype)
+    n = out.numel()
+    if groups:
+        out = torch.empty((G,) + tuple(out.shape), device=t.device, dtype=t.dtype)
     with torch.cuda.device(t.device), _lib.timed("batch_sum", t.numel() * t.element_size()):
-        _lib.check(_lib.lib.tramba_batch_sum(t.data_ptr(), out.data_ptr(), t.shape[0], out.numel(), _DTYPE[t.dtype],
-                                             _stream()))
+        _lib.check(_lib.lib.tramba_batch_sum(t.data_ptr(), out.data_ptr(), G, t.shape[1] if groups else t.shape[0], n,
+                                             _DTYPE[t.dtype], _stream()))
     return out
 
 

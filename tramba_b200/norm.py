@@ -74,8 +74,11 @@ class LayerNorm2dFn(torch.autograd.Function):
                     rstd.data_ptr(), gx.data_ptr(), gw.data_ptr(), None if gb is None else gb.data_ptr(),
                     B, C, L, _ACT[act], _DTYPE[x.dtype], _DTYPE[gy.dtype], _stream()))
         from .fused import _batch_sum                            # fold the per-tile partials (library kernel)
-        gw = _batch_sum(gw)
-        gb = None if gb is None else _batch_sum(gb)
+        if gb is not None and (C * 4) % 16 == 0:
+            gw, gb = _batch_sum(part, groups=2)                    # dweight | dbias in one launch
+        else:
+            gw = _batch_sum(gw)
+            gb = None if gb is None else _batch_sum(gb)
         return gx, gw.to(wdt), None if gb is None else gb.to(bdt), None, None, None
 
 
