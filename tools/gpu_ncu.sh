@@ -14,6 +14,7 @@ cap() {  # name, kernel regex, kernel_bench args...
   python tools/ncu_src_summary.py /tmp/${name}_sass.csv 40 > gpurun_out/${name}_sass_mix.txt 2>&1
   python tools/ncu_stall_reasons.py 12 < /tmp/${name}_sass.csv > gpurun_out/${name}_stall_reasons.txt 2>&1
   ncu -i /tmp/$name.ncu-rep --page raw --csv --metrics dram__bytes_read.sum,dram__bytes_write.sum,lts__t_bytes.sum,smsp__inst_executed_pipe_fma.sum,smsp__inst_executed_pipe_alu.sum,smsp__inst_executed_pipe_xu.sum,smsp__inst_executed_pipe_lsu.sum,sm__inst_executed_pipe_fma.sum,sm__inst_executed_pipe_alu.sum,sm__inst_executed_pipe_xu.sum,sm__inst_executed_pipe_lsu.sum > gpurun_out/${name}_pipes.csv 2>/dev/null
+  gzip -c /tmp/${name}_sass.csv > gpurun_out/${name}_sass.csv.gz   # per-instruction table (executed, stall columns) for offline reading
   rm -f /tmp/$name.ncu-rep /tmp/$name.csv /tmp/${name}_sass.csv
 }
 WHAT=${1:-all}

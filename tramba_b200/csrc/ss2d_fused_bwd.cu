@@ -34,6 +34,9 @@ namespace tramba {
 
 namespace {
 
+#ifndef TRAMBA_NKEEP
+#define TRAMBA_NKEEP 18
+#endif
 constexpr int S = kFusedS;
 constexpr int NT = kFusedNT;
 constexpr int TOK = kFusedTok;
@@ -281,8 +284,11 @@ __global__ void __launch_bounds__(NT, 1) ss2d_bwd_kernel(const FusedBwdArgs p) {
 
             // ---- pass 1: forward fold (P, Sf) and reverse fold (P, Sr) of the segment; g_t = C_t * dy_t stays in dh
             constexpr bool KEEPG = true;  // (recomputing g in pass 2a measured MORE spills, not fewer)
-            constexpr bool KEEPA = PP == 1;  // a_t = exp(delta_t A) kept for passes 2a / 2b where registers allow
-            float sp[S], dh[S], av[KEEPA ? S : 1];
+            // a_t = exp(delta_t A) kept for passes 2a / 2b for the first NKEEP tokens of the segment, recomputed
+            // (one MUFU) for the rest: as many as fit WITHOUT spilling -- with ~221 KB of shared memory the L1 is a few
+            // KB, so every spilled word costs an L2 round trip on the critical path (long-scoreboard stalls)
+            constexpr int NKEEP = PP == 1 ? TRAMBA_NKEEP : 0;
+            float sp[S], dh[S], av[NKEEP ? NKEEP : 1];
             float P = 1.f, Sf = 0.f, Sr = 0.f;
             {
                 load_tokens<S>(dq, sp);
@@ -300,7 +306,7 @@ __global__ void __launch_bounds__(NT, 1) ss2d_bwd_kernel(const FusedBwdArgs p) {
                         float e;
                         sp[m] = !SOFTPLUS ? raw : (ES == 2 ? softplus20_fast(raw) : softplus20(raw, e));
                         const float a = ex2f(sp[m] * A2);
-                        if constexpr (KEEPA) av[m] = a;
+                        if (m < NKEEP) av[m] = a;
                         const float bb = sp[m] * Bv[h2] * uv[h2];
                         const float g = Cv[h2] * yv[h2];
                         if constexpr (KEEPG) dh[m] = g;
@@ -355,7 +361,7 @@ __global__ void __launch_bounds__(NT, 1) ss2d_bwd_kernel(const FusedBwdArgs p) {
                 float E = Ein;
 #pragma unroll
                 for (int m = S - 1; m >= 0; --m) {
-                    const float a = KEEPA ? av[m] : ex2f(sp[m] * A2);
+                    const float a = m < NKEEP ? av[m] : ex2f(sp[m] * A2);
                     dh[m] += E;
                     E = a * dh[m];
                 }
@@ -393,7 +399,7 @@ __global__ void __launch_bounds__(NT, 1) ss2d_bwd_kernel(const FusedBwdArgs p) {
                 for (int h2 = 0; h2 < 2; ++h2) {
                     const int m = 2 * mp + h2;
                     const float u = uv[h2], dyv = yv[h2], Bm = Bv[h2];
-                    const float a = KEEPA ? av[m] : ex2f(sp[m] * A2);
+                    const float a = m < NKEEP ? av[m] : ex2f(sp[m] * A2);
                     const float w = a * h;  // a_t * h_{t-1}
                     const float bu = Bm * u;
                     h = fmaf(sp[m], bu, w);  // h_t

@@ -60,6 +60,19 @@ class ShadowParams:
             torch._foreach_copy_(self.shadows, self.masters)
 
 
+def _grouped_copy(dsts, srcs):
+    """torch._foreach_copy_ per (destination dtype, source dtype) group.  A list that mixes bf16 gradients (shadow
+    weights) with fp32 ones (norms, A_logs, Ds, biases) misses the multi-tensor fast path and degrades to one copy
+    kernel per tensor -- 673 launches per step for Tramba-V (measured: 314 cast kernels + 359 memcpys, 2.2 ms)."""
+    groups = {}
+    for d, s_ in zip(dsts, srcs):
+        a, b = groups.setdefault((d.dtype, s_.dtype), ([], []))
+        a.append(d)
+        b.append(s_)
+    for a, b in groups.values():
+        torch._foreach_copy_(a, b)
+
+
 class FlatGradients:
     def __init__(self, params, sources=None):
         """sources[i]: the tensor on which autograd leaves parameter i's gradient (the parameter itself, or its
@@ -123,7 +136,7 @@ class FlatGradients:
         chunk = self.flat[bk["lo"]:bk["hi"]]
 
         def work():
-            torch._foreach_copy_(views, grads)
+            _grouped_copy(views, grads)
             self._reduce(chunk)
         if self.side is None:
             work()
@@ -179,8 +192,7 @@ class FlatGradients:
             return
         dst = self.wire_views if getattr(self, "wire", None) is not None else self.views   # compressed: reduce first
         got = [(v, s.grad) for v, s in zip(dst, self.sources) if s.grad is not None]
-        if got:
-            torch._foreach_copy_([v for v, _ in got], [g for _, g in got])
+        _grouped_copy([v for v, _ in got], [g for _, g in got])
         for v, w, p, s in zip(self.views, dst, self.params, self.sources):
             if s.grad is None:          # parameter unused in this step
                 w.zero_()
