@@ -58,6 +58,11 @@ def parse():
                     "a side stream instead of one all-reduce after backward (measured slower, see run_ours)")
     ap.add_argument("--allreduce-dtype", default="bf16", choices=["bf16", "f32"], help="N > 1: dtype of the gradient "
                     "all-reduce (bf16 halves the bytes on the wire; the optimizer still reads fp32)")
+    ap.add_argument("--no-zero", action="store_true", help="N > 1: replicated optimizer step (all-reduce of every "
+                    "gradient, full Adam on every rank) instead of the ZeRO-1 step (reduce-scatter, sharded Adam, "
+                    "all-gather of the bf16 weights)")
+    ap.add_argument("--force-zero", action="store_true", help="run the ZeRO-1 step at N = 1 too (one shard: a functional "
+                    "check of the sharded step without a second GPU)")
     ap.add_argument("--buckets", type=int, default=4, help="gradient buckets of the overlapped all-reduce")
     ap.add_argument("--no-shadow", action="store_true", help="plain autocast (weights cast on every use) instead of "
                     "bf16 shadow weights refreshed after the optimizer step")
@@ -305,15 +310,28 @@ def run_ours(args):
     # Data parallel over images (the path shards by image): replicas start identical
     # (broadcast from rank 0) and every gradient lives in ONE flat fp32 buffer that is all-reduced
     # (NCCL, AVG) once per step between backward and the Adam step -- 446 MB over NVLink/NVSwitch.
-    from tramba_b200.dp import FlatGradients, ShadowParams
+    from tramba_b200.dp import FlatGradients, ShadowParams, ShardedStep
     params = [p for p in model.parameters()]
     amp = torch.bfloat16 if args.dtype == "bf16" else None
-    # bf16 shadow copies of the conv / linear / projection weights (what autocast would cast on every use)
-    shadow = ShadowParams(model, amp) if (amp is not None and not args.no_shadow) else None
-    fg = FlatGradients(params, [shadow.source_of(p) for p in params] if shadow else None)
     if world > 1:
         for p in params:
             dist.broadcast(p.data, 0)
+    # bf16 shadow copies of the conv / linear / projection weights (what autocast would cast on every use)
+    shadow = ShadowParams(model, amp) if (amp is not None and not args.no_shadow) else None
+    # N > 1 (default): ZeRO-1 for the shadowed weights (> 99 % of the parameters) -- reduce-scatter of the bf16 gradients,
+    # Adam on this rank's 1/N shard of the fp32 masters, all-gather of the bf16 shadows; the fp32-only parameters stay
+    # replicated (flat fp32 all-reduce + Adam), as everything does at N = 1.
+    zs = None
+    if (world > 1 or args.force_zero) and shadow is not None and not args.no_zero and not args.overlap:
+        zs = ShardedStep(shadow, [(enc, 1e-5), (dec, 1e-4)], world, rank, fused=True, capturable=True)
+        has = {id(m) for m in shadow.masters}
+        params = [p for p in params if id(p) not in has]
+        enc_r, dec_r = [p for p in enc if id(p) not in has], [p for p in dec if id(p) not in has]
+        opt = torch.optim.Adam([{"params": enc_r, "lr": 1e-5}, {"params": dec_r, "lr": 1e-4}], fused=True, capturable=True)
+        fg = FlatGradients(params)
+    else:
+        fg = FlatGradients(params, [shadow.source_of(p) for p in params] if shadow else None)
+    if world > 1 and zs is None:
         if args.overlap:
             # bucketed all-reduce launched from inside backward on a side stream (captured in the step's CUDA graph).
             # Measured SLOWER at N = 2 (31.0 against 30.3 ms): the step's kernels are persistent, one CTA per SM with
@@ -332,25 +350,38 @@ def run_ours(args):
         # autograd ASSIGNS fresh gradients (p.grad is None: no zero-fill + 679 accumulate kernels); they are
         # then packed into the flat buffer with one multi-tensor copy and the optimizer sees the flat views
         fg.begin()
+        if zs:
+            zs.begin()
         with torch.autocast("cuda", dtype=amp, enabled=amp is not None):
             outs = torch.func.functional_call(net, shadow.mapping(), (img,)) if shadow else net(img)
         loss = tsod_loss(outs, lab)
         loss.backward()
         fg.pack()
+        if zs:
+            zs.pack()
         return loss
 
     def reduce_grads():
+        if zs:
+            zs.reduce_scatter()
         fg.all_reduce(world)
 
     def opt_step():
+        if zs:
+            zs.update()                 # Adam on this rank's shard of the masters, rounded into its slice of the shadows
         opt.step()
-        if shadow:
+        if shadow and not zs:
             shadow.refresh()            # one multi-tensor copy: the bf16 weights of the next forward
+
+    def gather_weights():
+        if zs:
+            zs.all_gather()
 
     def step(img, lab):
         loss = fwd_bwd(img, lab)
         reduce_grads()
         opt_step()
+        gather_weights()
         return loss
 
     def sync():
@@ -389,7 +420,7 @@ def run_ours(args):
             with torch.cuda.graph(g_opt, pool=g_fb.pool()):
                 opt_step()
             for _ in range(2):
-                g_fb.replay(), reduce_grads(), g_opt.replay()
+                g_fb.replay(), reduce_grads(), g_opt.replay(), gather_weights()
             sync()
         except Exception as exc:
             import traceback
@@ -402,6 +433,7 @@ def run_ours(args):
         g_fb.replay()
         reduce_grads()
         g_opt.replay()
+        gather_weights()
 
     # per-kernel device time INSIDE the graph-replayed step (CUPTI): what the roofline is computed from.
     # Single-process runs only: the profiled replays happen on one rank, so they must not contain a collective
@@ -532,14 +564,19 @@ def run_ours(args):
                        "img_size": IMG, "global_batch": world * B, "parallelism": f"dp{world}",
                        "weights": "random-init, 111.44 M params", "optimizer": "Adam (fused)",
                        "collective": ("none (single GPU)" if world == 1 else
+                                      (f"ZeRO-1: NCCL reduce-scatter (AVG) of the bf16 gradients ({zs.bytes_on_the_wire()[0]} "
+                                       f"bytes in), Adam on 1/{world} of the fp32 masters per rank, all-gather of the bf16 "
+                                       f"weights ({zs.bytes_on_the_wire()[1]} bytes out); fp32-only parameters: all-reduce of "
+                                       f"{fg.flat.numel() * 4} bytes + replicated Adam") if zs else
                                       "NCCL all-reduce (AVG) of the flat gradient buffer, "
                                       + (f"{fg.wire.numel() * fg.wire.element_size()} bytes per step in bf16"
                                          if getattr(fg, "wire", None) is not None else f"{fg.flat.numel() * 4} bytes per step in fp32")
                                       + (f", {args.buckets} buckets launched from inside backward on a side stream"
                                          if args.overlap else ", one call between backward and Adam")),
-                       "weight_precision": "fp32 masters + bf16 shadows refreshed after Adam" if shadow else "fp32, autocast casts per use",
+                       "weight_precision": ("fp32 masters sharded over the ranks + bf16 shadows all-gathered after Adam" if zs else
+                                            "fp32 masters + bf16 shadows refreshed after Adam") if shadow else "fp32, autocast casts per use",
                        "ss2d_path": "op-by-op kernels" if args.unfused else "fused core kernels",
-                       "step_launch": "CUDA graphs (fwd+bwd graph, all-reduce, Adam graph)" if graph is not None else "eager",
+                       "step_launch": ("CUDA graphs (fwd+bwd graph, reduce-scatter, Adam graph, all-gather)" if zs else "CUDA graphs (fwd+bwd graph, all-reduce, Adam graph)") if graph is not None else "eager",
                        "l2": "no explicit flush: a step streams several GB of activations (>> 126 MB L2)"},
             "e2e": {"value": world * B * args.steps / (ms_e2e * 1e-3), "unit": UNIT,
                     "h2d_bytes_per_step": h_img.numel() * 4 + h_lab.numel() * 4, "d2h_bytes_per_step": 4,

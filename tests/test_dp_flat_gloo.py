@@ -122,6 +122,95 @@ def test_flat_gradients_bf16_wire_world2_gloo(tmp_path):
         assert same == 1.0
 
 
+def _zero_model():
+    torch.manual_seed(0)
+    return torch.nn.Sequential(torch.nn.Conv2d(3, 8, 3, padding=1), torch.nn.GroupNorm(2, 8), torch.nn.GELU(),
+                               torch.nn.Conv2d(8, 4, 1), torch.nn.Flatten(), torch.nn.Linear(4 * 8 * 8, 5),
+                               torch.nn.Linear(5, 1, bias=False))
+
+
+def _zero_worker(rank, world, port, out_dir, wire):
+    """ShardedStep (reduce-scatter -> Adam on the rank's shard of the fp32 masters -> all-gather of the bf16 shadows)
+    against the replicated step (all-reduce of the flat fp32 gradients -> Adam on every parameter -> refresh)."""
+    sys.path.insert(0, os.path.dirname(HERE))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.set_num_threads(1)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from tramba_b200.dp import FlatGradients, ShadowParams, ShardedStep
+
+    def groups_of(model):   # two learning rates, like the encoder / decoder split of train.py:266-280
+        ps = list(model.parameters())
+        return [(ps[:4], 1e-3), (ps[4:], 1e-2)]
+
+    # ---- replicated reference
+    ref = _zero_model()
+    ref_sh = ShadowParams(ref, torch.bfloat16)
+    ref_params = list(ref.parameters())
+    ref_fg = FlatGradients(ref_params, [ref_sh.source_of(p) for p in ref_params])
+    ref_opt = torch.optim.Adam([{"params": ps, "lr": lr} for ps, lr in groups_of(ref)])
+    # ---- sharded
+    net = _zero_model()
+    sh = ShadowParams(net, torch.bfloat16)
+    groups = groups_of(net)
+    zs = ShardedStep(sh, groups, world, rank, wire_dtype=wire)
+    assert zs.n == sum(m.numel() for m in sh.masters) and zs.n_pad % (8 * world) == 0
+    assert all(s.data_ptr() >= zs.w_flat.data_ptr() for s in sh.shadows)          # shadows are views of the flat buffer
+    has = {id(m) for m in sh.masters}
+    rest = [(p, lr) for ps, lr in groups for p in ps if id(p) not in has]       # fp32-only parameters: replicated
+    assert len(rest) == 2                                                        # the GroupNorm's weight and bias
+    fg = FlatGradients([p for p, _ in rest])
+    opt = torch.optim.Adam([{"params": [p], "lr": lr} for p, lr in rest])
+
+    g = torch.Generator().manual_seed(100 + rank)
+    x = torch.randn(2, 3, 8, 8, generator=g)
+    worst = 0.0
+    for _ in range(3):
+        ref_fg.begin()
+        with torch.autocast("cpu", dtype=torch.bfloat16):
+            torch.func.functional_call(ref, ref_sh.mapping(), (x,)).float().square().mean().backward()
+        ref_fg.pack()
+        ref_fg.all_reduce(world)
+        ref_opt.step()
+        ref_sh.refresh()
+
+        fg.begin()
+        zs.begin()
+        with torch.autocast("cpu", dtype=torch.bfloat16):
+            torch.func.functional_call(net, sh.mapping(), (x,)).float().square().mean().backward()
+        fg.pack()
+        zs.pack()
+        zs.reduce_scatter()
+        fg.all_reduce(world)
+        zs.update()
+        opt.step()
+        zs.all_gather()
+        for a, b in zip(sh.shadows, ref_sh.shadows):
+            worst = max(worst, float((a.float() - b.float()).abs().max()) / (float(b.float().abs().max()) + 1e-12))
+    zs.gather_masters()
+    exact = all(torch.equal(a, b) for a, b in zip(net.parameters(), ref.parameters()))
+    close = max(float((a - b).abs().max()) for a, b in zip(net.parameters(), ref.parameters()))
+    np.save(os.path.join(out_dir, f"r{rank}.npy"), np.array([worst, float(exact), close]))
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+@pytest.mark.parametrize("wire", ["f32", "bf16"])
+def test_sharded_step_matches_replicated_step_world2_gloo(tmp_path, wire):
+    """ZeRO-1 step of bench.py at N > 1.  fp32 on the wire: bit-identical weights (shadows AND gathered fp32 masters)
+    to the replicated all-reduce + full Adam step after 3 steps, with the shard boundary and the learning-rate
+    boundary inside parameters.  bf16 on the wire (bench.py's default: the gradients of shadowed weights ARE bf16):
+    the averaged gradient is rounded once more, so the weights agree to bf16 resolution."""
+    world = 2
+    mp.spawn(_zero_worker, args=(world, _free_port(), str(tmp_path), torch.float32 if wire == "f32" else torch.bfloat16),
+             nprocs=world, join=True)
+    for r in range(world):
+        worst, exact, close = np.load(tmp_path / f"r{r}.npy")
+        if wire == "f32":
+            assert exact == 1.0 and worst == 0.0, (worst, exact, close)
+        else:
+            assert worst < 2.0 ** -6 and close < 1e-2, (worst, close)
+
+
 def test_flat_gradients_unused_parameter_is_zeroed():
     sys.path.insert(0, os.path.dirname(HERE))
     from tramba_b200.dp import FlatGradients

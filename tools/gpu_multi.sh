@@ -1,5 +1,6 @@
 #!/bin/bash
-# N-GPU training-step bench (one process per GPU, NCCL): gradient all-reduce in bf16 (default) vs fp32.
+# N-GPU training-step bench (one process per GPU, NCCL): ZeRO-1 step (default) vs replicated step with a bf16 / fp32
+# gradient all-reduce; the 1-GPU line of the same box first.
 #   gpurun --gpus N --timeout 1200 -- 'bash tools/gpu_multi.sh N'
 N=${1:-2}
 mkdir -p gpurun_out
@@ -19,5 +20,6 @@ PY
 }
 timeout 400 python bench.py --gpus 1 --steps 20 --warmup 5 --no-cpu-baseline > gpurun_out/bench_1gpu_ref.json 2> gpurun_out/bench_1gpu_ref.err
 python -c "import json; d=json.loads(open('gpurun_out/bench_1gpu_ref.json').read().strip().splitlines()[-1]); print('1 gpu', round(d['value'],1), round(d['ms_per_step'],3))"
-run bf16wire
-run f32wire --allreduce-dtype f32
+run zero1
+run bf16wire --no-zero
+[ "${2:-}" = all ] && run f32wire --no-zero --allreduce-dtype f32

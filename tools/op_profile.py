@@ -70,7 +70,7 @@ def main():
     for _ in range(3):
         step()
     torch.cuda.synchronize()
-    with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA], with_stack=True) as prof:
+    with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA], with_stack=True, record_shapes=True) as prof:
         for _ in range(a.steps):
             step()
         torch.cuda.synchronize()
@@ -89,29 +89,50 @@ def main():
     print("\nself device time per operator (autograd nodes appear under their own names):")
     for k, (n, t) in sorted(ops.items(), key=lambda kv: -kv[1][1])[:60]:
         print(f"{100 * t / tot:6.2f}% {t / a.steps / 1e3:8.3f} ms/step {n // a.steps:6d} x  {k[:100]}")
-    # who calls the glue operators: device time of copy_ / sum / add / mul ... grouped by the innermost Python frame
-    # inside this repository (forward ops; autograd nodes have no Python stack and are grouped under their node name)
+    # who calls the glue operators: device time of copy_ / sum / add / mul ... grouped by the kernel they launch, the
+    # enclosing autograd node (backward) or module range (forward) found by walking the CPU parents, and the shapes
     callers = collections.defaultdict(lambda: [0, 0.0])
     glue = ("aten::copy_", "aten::sum", "aten::add", "aten::add_", "aten::mul", "aten::fill_", "aten::zero_",
-            "aten::gelu", "aten::cat", "aten::clone", "aten::contiguous")
+            "aten::gelu", "aten::cat", "aten::clone", "aten::contiguous", "aten::gelu_backward", "aten::mul_")
+
+    def enclosing(ev):
+        node, mod = None, None
+        p = getattr(ev, "cpu_parent", None)
+        while p is not None:
+            if node is None and (p.name.startswith("autograd::engine::evaluate_function: ") or p.name.endswith("Backward")):
+                node = p.name.replace("autograd::engine::evaluate_function: ", "bwd:")
+            if mod is None and p.name.startswith("mod:"):
+                mod = p.name[4:]
+            if node is None and not p.name.startswith(("aten::", "mod:", "autograd::", "cuda", "Optimizer", "ProfilerStep")):
+                node = "in:" + p.name                      # a custom autograd Function / Python range
+            p = getattr(p, "cpu_parent", None)
+        return f"{node or '-'} @ {mod or '-'}"
+
+    def kern_kind(ev):
+        ks = [k.name for k in getattr(ev, "kernels", [])]
+        if not ks:
+            return "-"
+        k = ks[0]
+        for tag in ("unrolled_elementwise_kernel", "vectorized_elementwise_kernel", "elementwise_kernel", "reduce_kernel",
+                    "multi_tensor_apply", "Memcpy", "memcpy"):
+            if tag in k:
+                extra = "direct_copy" if "direct_copy" in k else ("bfloat16_copy" if "bfloat16_copy" in k else "")
+                return (tag + " " + extra).strip()
+        return k[:40]
+
     for ev in prof.events():
         if ev.name not in glue:
             continue
         t = dev_time(ev)
         if t <= 0:
             continue
-        where = "(no python frame: autograd node / optimizer)"
-        for fr in (ev.stack or []):
-            if "/tramba_b200/" in fr or "/tools/" in fr or "bench.py" in fr:
-                where = fr.split("/root/")[-1] if "/root/" in fr else fr
-                where = where[-90:]
-                break
-        c = callers[(ev.name, where)]
+        shapes = str(getattr(ev, "input_shapes", ""))[:60]
+        c = callers[(ev.name, kern_kind(ev), enclosing(ev), shapes)]
         c[0] += 1
         c[1] += t
-    print("\nglue operators by calling frame (self device time):")
-    for (op, where), (n, t) in sorted(callers.items(), key=lambda kv: -kv[1][1])[:45]:
-        print(f"{t / a.steps / 1e3:8.3f} ms/step {n // a.steps:5d} x  {op:16s} {where}")
+    print("\nglue operators by launched kernel, enclosing autograd node / module range and input shapes (self device time):")
+    for (op, kk, where, shapes), (n, t) in sorted(callers.items(), key=lambda kv: -kv[1][1])[:90]:
+        print(f"{t / a.steps / 1e3:8.3f} ms/step {n // a.steps:5d} x  {op:14s} {kk:42s} {where[:70]:70s} {shapes}")
     print("\nforward device time per module range (nested ranges overlap; backward is not attributed):")
     for k, (n, t) in sorted(mods.items(), key=lambda kv: -kv[1][1])[:40]:
         print(f"{t / a.steps / 1e3:8.3f} ms/step {n // a.steps:4d} x  {k}")
