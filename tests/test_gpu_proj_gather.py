@@ -56,3 +56,26 @@ def test_adjoint_is_the_transpose():
     lhs = sum((o.double() * gi.double()).sum() for o, gi in zip(outs, gs))
     rhs = (x.double() * gx.double()).sum()
     assert abs(lhs.item() - rhs.item()) <= 1e-5 * abs(lhs.item()) + 1e-6
+
+
+@pytest.mark.parametrize("shape,groups,dtype", [
+    ((4, 192, 1024), 0, torch.bfloat16),        # x_proj weight-gradient batch sum (vector kernel)
+    ((4, 8, 6, 37), 0, torch.float32),          # odd column count: scalar path
+    ((576, 256), 0, torch.float32),             # per-tile partials: tall kernel
+    ((2, 576, 256), 2, torch.float32),          # LayerNorm2d: dweight | dbias in one launch
+    ((2, 100, 48), 2, torch.float32),           # tall, columns not a multiple of 32
+    ((130, 45), 0, torch.bfloat16),
+    ((2, 5, 64), 2, torch.float32),             # groups on the vector kernel
+])
+def test_batch_sum(shape, groups, dtype):
+    """tramba_batch_sum: out = sum over the batch axis with fp32 accumulation, same dtype out (both kernels, groups)."""
+    g = torch.Generator().manual_seed(sum(shape))
+    t = torch.randn(shape, generator=g).to(dtype)
+    ref = t.double().sum(1 if groups else 0)
+    out = fused._batch_sum(t.cuda(), groups=groups)
+    assert out.dtype == dtype and tuple(out.shape) == tuple(ref.shape)
+    tol = 1e-5 if dtype == torch.float32 else 2.0 ** -8
+    err = (out.double().cpu() - ref).abs().max() / ref.abs().max()
+    assert err < tol, float(err)
+    ti = torch.randint(-4, 5, shape, generator=g).to(dtype)                              # exact sums
+    assert torch.equal(fused._batch_sum(ti.cuda(), groups=groups).cpu().double(), ti.double().sum(1 if groups else 0))

@@ -123,12 +123,50 @@ __global__ void __launch_bounds__(256) batch_sum_kernel(const T* __restrict__ in
     }
 }
 
+// The same reduction for TALL inputs (hundreds of partial rows, a few hundred columns: the per-tile partials of the
+// LayerNorm2d / depthwise-conv weight gradients).  The vector kernel above would run on 2-4 CTAs; here a CTA owns 32
+// columns and its 32 warps each add every 32nd row (128-byte coalesced row segments), then fold in shared memory.
+template <typename T>
+__global__ void __launch_bounds__(1024) batch_sum_tall_kernel(const T* __restrict__ in, T* __restrict__ out, int B, long long n) {
+    __shared__ float part[32][33];
+    const int lane = threadIdx.x & 31, slice = threadIdx.x >> 5;
+    in += static_cast<long long>(blockIdx.y) * B * n, out += static_cast<long long>(blockIdx.y) * n;  // group
+    const long long i = static_cast<long long>(blockIdx.x) * 32 + lane;
+    float acc0 = 0.f, acc1 = 0.f;
+    if (i < n) {
+        int b = slice;
+        for (; b + 32 < B; b += 64)
+            acc0 += to_f32(in[static_cast<long long>(b) * n + i]), acc1 += to_f32(in[static_cast<long long>(b + 32) * n + i]);
+        if (b < B) acc0 += to_f32(in[static_cast<long long>(b) * n + i]);
+    }
+    part[slice][lane] = acc0 + acc1;
+    __syncthreads();
+    if (slice == 0 && i < n) {
+        float t = 0.f;
+#pragma unroll
+        for (int s32 = 0; s32 < 32; ++s32) t += part[s32][lane];
+        out[i] = from_f32<T>(t);
+    }
+}
+
 }  // namespace
 
 cudaError_t launch_batch_sum(const void* in, void* out, int G, int B, long long n, int dtype, cudaStream_t st) {
     const int V = dtype == TRAMBA_F32 ? 4 : 8;
     const long long groups = (n + V - 1) / V;
     const dim3 grid(static_cast<unsigned>((groups + 31) / 32), static_cast<unsigned>(G));
+    if (B >= 64 && static_cast<long long>(grid.x) * grid.y < 64) {  // tall and narrow: more, deeper CTAs
+        const dim3 gt(static_cast<unsigned>((n + 31) / 32), static_cast<unsigned>(G));
+        if (dtype == TRAMBA_F32)
+            batch_sum_tall_kernel<float><<<gt, 1024, 0, st>>>(static_cast<const float*>(in), static_cast<float*>(out), B, n);
+        else if (dtype == TRAMBA_BF16)
+            batch_sum_tall_kernel<__nv_bfloat16><<<gt, 1024, 0, st>>>(static_cast<const __nv_bfloat16*>(in),
+                                                                      static_cast<__nv_bfloat16*>(out), B, n);
+        else
+            return cudaErrorInvalidValue;
+        note_launch();
+        return cudaGetLastError();
+    }
     if (dtype == TRAMBA_F32)
         batch_sum_kernel<float><<<grid, 256, 0, st>>>(static_cast<const float*>(in), static_cast<float*>(out), B, n);
     else if (dtype == TRAMBA_BF16)
