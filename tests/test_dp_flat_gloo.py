@@ -153,7 +153,8 @@ def _zero_worker(rank, world, port, out_dir, wire):
     sh = ShadowParams(net, torch.bfloat16)
     groups = groups_of(net)
     zs = ShardedStep(sh, groups, world, rank, wire_dtype=wire)
-    assert zs.n == sum(m.numel() for m in sh.masters) and zs.n_pad % (8 * world) == 0
+    assert zs.n >= sum(m.numel() for m in sh.masters) and zs.n_pad % (8 * world) == 0
+    assert all((s.data_ptr() - zs.w_flat.data_ptr()) % 256 == 0 for s in sh.shadows)   # what cuDNN / cuBLAS read
     assert all(s.data_ptr() >= zs.w_flat.data_ptr() for s in sh.shadows)          # shadows are views of the flat buffer
     has = {id(m) for m in sh.masters}
     rest = [(p, lr) for ps, lr in groups for p in ps if id(p) not in has]       # fp32-only parameters: replicated
