@@ -506,6 +506,19 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_dev, ms_e2e = t.tolist()
 
+    # ---- after the timed regions: the replicas must still hold the same weights (a data-parallel step that lets them
+    # drift would be measuring the wrong thing).  Checksums of the weights the next forward reads, compared over ranks.
+    replica_check = None
+    if world > 1:
+        with torch.no_grad():
+            ws = ([zs.w_flat] if zs else []) + [p for p in params]
+            cs = torch.stack([torch.stack([w.double().sum(), w.double().abs().sum()]) for w in ws]).sum(0)
+        lo, hi = cs.clone(), cs.clone()
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+        dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+        replica_check = {"identical": bool(torch.equal(lo, hi)), "weight_abs_sum": float(cs[1]),
+                         "finite": bool(torch.isfinite(cs).all()), "loss": loss_val}
+
     if rank == 0:
         peaks = {}
         try:
@@ -583,6 +596,7 @@ def run_ours(args):
                     "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": launches,
             "clocks": clocks,
+            "replica_check": replica_check,
             "roofline": roofline,
             "kernels": {kk: {"launches": v["launches"], "us_per_launch": round(v["us_per_launch"], 2),
                              "gbs": round(v["gbs"], 1), "frac": round(v["gbs"] / peak, 4),

@@ -13,7 +13,7 @@ run() {  # tag, extra args
 import json
 try:
     d=json.loads(open('gpurun_out/bench_${N}gpu_$tag.json').read().strip().splitlines()[-1])
-    print('$tag', d['n_gpus'], round(d['value'],1), 'img/s', round(d['ms_per_step'],3), 'ms', d['config'].get('collective'))
+    print('$tag', d['n_gpus'], round(d['value'],1), 'img/s', round(d['ms_per_step'],3), 'ms', d.get('replica_check'), d['config'].get('collective'))
 except Exception as e:
     print('unreadable', e); print(open('gpurun_out/bench_${N}gpu_$tag.err').read()[-1500:])
 PY
@@ -21,5 +21,7 @@ PY
 timeout 400 python bench.py --gpus 1 --steps 20 --warmup 5 --no-cpu-baseline > gpurun_out/bench_1gpu_ref.json 2> gpurun_out/bench_1gpu_ref.err
 python -c "import json; d=json.loads(open('gpurun_out/bench_1gpu_ref.json').read().strip().splitlines()[-1]); print('1 gpu', round(d['value'],1), round(d['ms_per_step'],3))"
 run zero1
+[ "${2:-}" = zero ] && exit 0
 run bf16wire --no-zero
 [ "${2:-}" = all ] && run f32wire --no-zero --allreduce-dtype f32
+exit 0
