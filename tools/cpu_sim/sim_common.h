@@ -650,6 +650,10 @@ inline void bulk_wait_all() {
 inline void red_add_v4(float* p, float a, float b, float c, float d) { sim::red_add_v4(p, a, b, c, d); }
 
 // ---- math (libm instead of the .approx MUFU ops: differences are far below the parity tolerance)
+// packed fp32 pairs (FADD2 / FMUL2 / FFMA2 on sm_100): two IEEE operations
+inline float2 __fadd2_rn(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+inline float2 __fmul2_rn(float2 a, float2 b) { return make_float2(a.x * b.x, a.y * b.y); }
+inline float2 __ffma2_rn(float2 a, float2 b, float2 c) { return make_float2(fmaf(a.x, b.x, c.x), fmaf(a.y, b.y, c.y)); }
 inline float ex2f(float x) { return exp2f(x); }
 inline float lg2f(float x) { return log2f(x); }
 inline float rcpf(float x) { return 1.0f / x; }

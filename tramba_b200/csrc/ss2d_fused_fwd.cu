@@ -154,19 +154,50 @@ __global__ void __launch_bounds__(NT, 1) ss2d_fwd_kernel(const FusedArgs p) {
                 load_tokens<S>(sd + static_cast<size_t>(buf) * TOK + static_cast<size_t>(q) * L + j * S, dl);
                 load_tokens<S>(sB + static_cast<size_t>(buf) * L + j * S, Bv);
                 load_tokens<S>(sC + static_cast<size_t>(buf) * L + j * S, Cv);
+                if constexpr (SOFTPLUS && ES == 2) {
+                    // 16-bit operands: the per-token operations that do not depend on the running state are issued for
+                    // token PAIRS as packed fp32 instructions (FADD2 / FMUL2 / FFMA2: two tokens per issue slot, same
+                    // IEEE rounding as the scalar forms) -- the kernel is bound by issue slots, not by FMA throughput
+                    const float2 bias2 = make_float2(bias, bias), A22 = make_float2(A2, A2), Dd2 = make_float2(Dd, Dd);
+                    const float2 l2e = make_float2(kLog2e, kLog2e), ln2 = make_float2(kLn2, kLn2), one2 = make_float2(1.f, 1.f);
 #pragma unroll
-                for (int m = 0; m < S; ++m) {
-                    const int px = (m & 1) ? (pk[m >> 1] >> 16) : (pk[m >> 1] & 0xffffu);
-                    const float u = to_f32(xq[px]);
-                    const float raw = dl[m] + bias;
-                    float e;
-                    const float dsp = !SOFTPLUS ? raw : (ES == 2 ? softplus20_fast(raw) : softplus20(raw, e));
-                    const float a = ex2f(dsp * A2);
-                    const float bb = dsp * Bv[m] * u;
-                    Sacc = fmaf(a, Sacc, bb);
-                    P *= a;
-                    y0[m] = fmaf(Cv[m], Sacc, Dd * u);
-                    g[m] = Cv[m] * P;
+                    for (int mp = 0; mp < S / 2; ++mp) {
+                        const float2 u2 = make_float2(to_f32(xq[pk[mp] & 0xffffu]), to_f32(xq[pk[mp] >> 16]));
+                        const float2 raw2 = __fadd2_rn(make_float2(dl[2 * mp], dl[2 * mp + 1]), bias2);
+                        const float2 t2 = __fmul2_rn(raw2, l2e);
+                        const float2 w2 = __fadd2_rn(make_float2(ex2f(t2.x), ex2f(t2.y)), one2);
+                        float2 sp2 = __fmul2_rn(make_float2(lg2f(w2.x), lg2f(w2.y)), ln2);
+                        sp2.x = raw2.x > 20.f ? raw2.x : sp2.x;
+                        sp2.y = raw2.y > 20.f ? raw2.y : sp2.y;
+                        const float2 ea = __fmul2_rn(sp2, A22);
+                        const float a0 = ex2f(ea.x), a1 = ex2f(ea.y);
+                        const float2 Bm = make_float2(Bv[2 * mp], Bv[2 * mp + 1]), Cm = make_float2(Cv[2 * mp], Cv[2 * mp + 1]);
+                        const float2 bb2 = __fmul2_rn(__fmul2_rn(sp2, Bm), u2);
+                        const float2 du2 = __fmul2_rn(Dd2, u2);
+                        const float S0 = fmaf(a0, Sacc, bb2.x);
+                        const float P0 = P * a0;
+                        Sacc = fmaf(a1, S0, bb2.y);
+                        P = P0 * a1;
+                        const float2 y2 = __ffma2_rn(Cm, make_float2(S0, Sacc), du2);
+                        const float2 g2 = __fmul2_rn(Cm, make_float2(P0, P));
+                        y0[2 * mp] = y2.x, y0[2 * mp + 1] = y2.y;
+                        g[2 * mp] = g2.x, g[2 * mp + 1] = g2.y;
+                    }
+                } else {
+#pragma unroll
+                    for (int m = 0; m < S; ++m) {
+                        const int px = (m & 1) ? (pk[m >> 1] >> 16) : (pk[m >> 1] & 0xffffu);
+                        const float u = to_f32(xq[px]);
+                        const float raw = dl[m] + bias;
+                        float e;
+                        const float dsp = !SOFTPLUS ? raw : (ES == 2 ? softplus20_fast(raw) : softplus20(raw, e));
+                        const float a = ex2f(dsp * A2);
+                        const float bb = dsp * Bv[m] * u;
+                        Sacc = fmaf(a, Sacc, bb);
+                        P *= a;
+                        y0[m] = fmaf(Cv[m], Sacc, Dd * u);
+                        g[m] = Cv[m] * P;
+                    }
                 }
             }
             // ---- carry-in of this thread: scan over the TP threads of the plane
