@@ -20,7 +20,8 @@ SOURCES = ["capi.cu", "sscan_fwd.cu", "sscan_bwd.cu", "ss2d_fused_fwd.cu", "ss2d
 HEADERS = ["common.cuh", "sscan.cuh", "ss2d_fused.cuh", os.path.join("..", "..", "include", "tramba_b200.h")]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-         "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "--expt-relaxed-constexpr"]
+         "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "--expt-relaxed-constexpr"] + \
+        os.environ.get("TRAMBA_NVCC_EXTRA", "").split()        # e.g. -DTRAMBA_PACK=0 for an A/B build
 
 
 def _stale(target, deps):

@@ -11,6 +11,10 @@
 // par or ahead of a TMA-staged direction-pairing variant: profiles/r02_fused_ab_bf16.jsonl)
 #include "ss2d_fused.cuh"
 
+#ifndef TRAMBA_PACK
+#define TRAMBA_PACK 1
+#endif
+
 namespace tramba {
 
 namespace {
@@ -154,7 +158,7 @@ __global__ void __launch_bounds__(NT, 1) ss2d_fwd_kernel(const FusedArgs p) {
                 load_tokens<S>(sd + static_cast<size_t>(buf) * TOK + static_cast<size_t>(q) * L + j * S, dl);
                 load_tokens<S>(sB + static_cast<size_t>(buf) * L + j * S, Bv);
                 load_tokens<S>(sC + static_cast<size_t>(buf) * L + j * S, Cv);
-                if constexpr (SOFTPLUS && ES == 2) {
+                if constexpr (TRAMBA_PACK && SOFTPLUS && ES == 2) {
                     // 16-bit operands: the per-token operations that do not depend on the running state are issued for
                     // token PAIRS as packed fp32 instructions (FADD2 / FMUL2 / FFMA2: two tokens per issue slot, same
                     // IEEE rounding as the scalar forms) -- the kernel is bound by issue slots, not by FMA throughput
