@@ -34,9 +34,6 @@ namespace tramba {
 
 namespace {
 
-#ifndef TRAMBA_PACK
-#define TRAMBA_PACK 1
-#endif
 #ifndef TRAMBA_NKEEP
 #define TRAMBA_NKEEP 18
 #endif
@@ -73,7 +70,6 @@ template <typename in_t, bool SOFTPLUS, int TP, bool PIPE>
 __global__ void __launch_bounds__(NT, 1) ss2d_bwd_kernel(const FusedBwdArgs p) {
     extern __shared__ __align__(128) unsigned char smem[];
     constexpr int ES = sizeof(in_t);
-    constexpr bool PACK = TRAMBA_PACK && SOFTPLUS && ES == 2;  // packed fp32 pairs in the recurrence passes
     constexpr int L = TP * S, PP = NT / TP;
     using Lay = DxLayout<ES, TP, PIPE>;
     float* const sDXs = reinterpret_cast<float*>(smem + Lay::dx);  // PIPE only
@@ -303,46 +299,20 @@ __global__ void __launch_bounds__(NT, 1) ss2d_bwd_kernel(const FusedBwdArgs p) {
                     load_pair(Cq, mp, Cv[0], Cv[1]);
                     chunk_pair<REV>(xq, mp, uv[0], uv[1]);
                     chunk_pair<REV>(yq, mp, yv[0], yv[1]);
-                    if constexpr (PACK) {
-                        // token pairs on packed fp32 instructions (FADD2 / FMUL2: one issue slot for two tokens, same
-                        // rounding) for everything that does not depend on the running state
-                        const int m = 2 * mp;
-                        const float2 raw2 = __fadd2_rn(make_float2(sp[m], sp[m + 1]), make_float2(bias, bias));
-                        const float2 t2 = __fmul2_rn(raw2, make_float2(kLog2e, kLog2e));
-                        const float2 w2 = __fadd2_rn(make_float2(ex2f(t2.x), ex2f(t2.y)), make_float2(1.f, 1.f));
-                        float2 s2 = __fmul2_rn(make_float2(lg2f(w2.x), lg2f(w2.y)), make_float2(kLn2, kLn2));
-                        s2.x = raw2.x > 20.f ? raw2.x : s2.x;
-                        s2.y = raw2.y > 20.f ? raw2.y : s2.y;
-                        const float2 ea = __fmul2_rn(s2, make_float2(A2, A2));
-                        const float a0 = ex2f(ea.x), a1 = ex2f(ea.y);
-                        const float2 bb2 = __fmul2_rn(__fmul2_rn(s2, make_float2(Bv[0], Bv[1])), make_float2(uv[0], uv[1]));
-                        const float2 g2 = __fmul2_rn(make_float2(Cv[0], Cv[1]), make_float2(yv[0], yv[1]));
-                        sp[m] = s2.x, sp[m + 1] = s2.y;
-                        dh[m] = g2.x, dh[m + 1] = g2.y;
-                        if (m < NKEEP) av[m] = a0;
-                        if (m + 1 < NKEEP) av[m + 1] = a1;
-                        Sf = fmaf(a0, Sf, bb2.x);
-                        P *= a0;
-                        Sr = fmaf(P, g2.x, Sr);
-                        Sf = fmaf(a1, Sf, bb2.y);
-                        P *= a1;
-                        Sr = fmaf(P, g2.y, Sr);
-                    } else {
 #pragma unroll
-                        for (int h2 = 0; h2 < 2; ++h2) {
-                            const int m = 2 * mp + h2;
-                            const float raw = sp[m] + bias;
-                            float e;
-                            sp[m] = !SOFTPLUS ? raw : (ES == 2 ? softplus20_fast(raw) : softplus20(raw, e));
-                            const float a = ex2f(sp[m] * A2);
-                            if (m < NKEEP) av[m] = a;
-                            const float bb = sp[m] * Bv[h2] * uv[h2];
-                            const float g = Cv[h2] * yv[h2];
-                            if constexpr (KEEPG) dh[m] = g;
-                            Sf = fmaf(a, Sf, bb);
-                            P *= a;
-                            Sr = fmaf(P, g, Sr);
-                        }
+                    for (int h2 = 0; h2 < 2; ++h2) {
+                        const int m = 2 * mp + h2;
+                        const float raw = sp[m] + bias;
+                        float e;
+                        sp[m] = !SOFTPLUS ? raw : (ES == 2 ? softplus20_fast(raw) : softplus20(raw, e));
+                        const float a = ex2f(sp[m] * A2);
+                        if (m < NKEEP) av[m] = a;
+                        const float bb = sp[m] * Bv[h2] * uv[h2];
+                        const float g = Cv[h2] * yv[h2];
+                        if constexpr (KEEPG) dh[m] = g;
+                        Sf = fmaf(a, Sf, bb);
+                        P *= a;
+                        Sr = fmaf(P, g, Sr);
                     }
                 }
             }
@@ -418,7 +388,6 @@ __global__ void __launch_bounds__(NT, 1) ss2d_bwd_kernel(const FusedBwdArgs p) {
             // even lane sends quads 0-3 from its own values and quad 4 = its last two + the odd lane's first two
             // (one shuffle pair after the loop), the odd lane quads 5-8 = its values 2..17.
             float h = hin, sA = 0.f, sDs = 0.f, sb = 0.f;
-            float2 sA2 = make_float2(0.f, 0.f), sD2 = sA2, sb2 = sA2;  // PACK: even / odd token partial sums
             float cB[S], cC[S];
 #pragma unroll
             for (int mp = 0; mp < S / 2; ++mp) {
@@ -426,74 +395,40 @@ __global__ void __launch_bounds__(NT, 1) ss2d_bwd_kernel(const FusedBwdArgs p) {
                 load_pair(Bq, mp, Bv[0], Bv[1]);
                 chunk_pair<REV>(xq, mp, uv[0], uv[1]);
                 chunk_pair<REV>(yq, mp, yv[0], yv[1]);
-                if constexpr (PACK) {
-                    const int m = 2 * mp;
-                    const float2 u2 = make_float2(uv[0], uv[1]), y2 = make_float2(yv[0], yv[1]), B2 = make_float2(Bv[0], Bv[1]);
-                    const float2 sp2 = make_float2(sp[m], sp[m + 1]), dh2 = make_float2(dh[m], dh[m + 1]);
-                    const float a0 = m < NKEEP ? av[m] : ex2f(sp2.x * A2);
-                    const float a1 = m + 1 < NKEEP ? av[m + 1] : ex2f(sp2.y * A2);
-                    const float2 bu2 = __fmul2_rn(B2, u2);
-                    const float w0 = a0 * h;            // a_t * h_{t-1}
-                    const float h0 = fmaf(sp2.x, bu2.x, w0);
-                    const float w1 = a1 * h0;
-                    h = fmaf(sp2.y, bu2.y, w1);
-                    const float2 w2 = make_float2(w0, w1), hh2 = make_float2(h0, h);
-                    const float2 dhs2 = __fmul2_rn(dh2, sp2);
-                    const float2 du2 = __ffma2_rn(make_float2(Dd, Dd), y2, __fmul2_rn(dhs2, B2));
-                    float2 dd2 = __fmul2_rn(dh2, __ffma2_rn(make_float2(Ar, Ar), w2, bu2));
-                    // sigmoid(raw) = 1 - exp(-softplus(raw)) (16-bit operands: no series needed, see below)
-                    const float2 t2 = __fmul2_rn(sp2, make_float2(-kLog2e, -kLog2e));
-                    const float2 sg2 = __fadd2_rn(make_float2(1.f, 1.f), make_float2(-ex2f(t2.x), -ex2f(t2.y)));
-                    dd2 = __fmul2_rn(dd2, sg2);
-                    if constexpr (ACC) {
-                        const float2 nb = __ffma2_rn(dhs2, u2, make_float2(accB[m], accB[m + 1]));
-                        const float2 nc = __ffma2_rn(y2, hh2, make_float2(accC[m], accC[m + 1]));
-                        accB[m] = nb.x, accB[m + 1] = nb.y, accC[m] = nc.x, accC[m + 1] = nc.y;
-                    } else {
-                        const float2 nb = __fmul2_rn(dhs2, u2), nc = __fmul2_rn(y2, hh2);
-                        cB[m] = nb.x, cB[m + 1] = nb.y, cC[m] = nc.x, cC[m + 1] = nc.y;
-                    }
-                    sA2 = __ffma2_rn(dhs2, w2, sA2);
-                    sD2 = __ffma2_rn(y2, u2, sD2);
-                    sb2 = __fadd2_rn(sb2, dd2);
-                    sp[m] = dd2.x, sp[m + 1] = dd2.y;  // reuse: sp <- ddelta, dh <- du
-                    dh[m] = du2.x, dh[m + 1] = du2.y;
-                } else {
-    #pragma unroll
-                    for (int h2 = 0; h2 < 2; ++h2) {
-                        const int m = 2 * mp + h2;
-                        const float u = uv[h2], dyv = yv[h2], Bm = Bv[h2];
-                        const float a = m < NKEEP ? av[m] : ex2f(sp[m] * A2);
-                        const float w = a * h;  // a_t * h_{t-1}
-                        const float bu = Bm * u;
-                        h = fmaf(sp[m], bu, w);  // h_t
-                        const float dhs = dh[m] * sp[m];
-                        const float du = fmaf(Dd, dyv, dhs * Bm);
-                        float dd = dh[m] * fmaf(Ar, w, bu);
-                        if (SOFTPLUS) {
-                            // sigmoid(raw) = 1 - exp(-softplus(raw)) = -expm1(-sp); series below 1/8 keeps fp32 relative
-                            // accuracy where 1 - exp(.) would cancel (moot for 16-bit operands: <= 6e-8 absolute)
-                            const float t = sp[m];
-                            if (ES == 2) {
-                                dd *= 1.0f - ex2f(-t * kLog2e);
-                            } else {
-                                const float ser = t * (1.0f - t * (0.5f - t * (0.16666667f - t * 0.041666668f)));
-                                dd *= (t < 0.125f) ? ser : (1.0f - ex2f(-t * kLog2e));
-                            }
-                        }
-                        if constexpr (ACC) {
-                            accB[m] = fmaf(dhs, u, accB[m]);
-                            accC[m] = fmaf(dyv, h, accC[m]);
+#pragma unroll
+                for (int h2 = 0; h2 < 2; ++h2) {
+                    const int m = 2 * mp + h2;
+                    const float u = uv[h2], dyv = yv[h2], Bm = Bv[h2];
+                    const float a = m < NKEEP ? av[m] : ex2f(sp[m] * A2);
+                    const float w = a * h;  // a_t * h_{t-1}
+                    const float bu = Bm * u;
+                    h = fmaf(sp[m], bu, w);  // h_t
+                    const float dhs = dh[m] * sp[m];
+                    const float du = fmaf(Dd, dyv, dhs * Bm);
+                    float dd = dh[m] * fmaf(Ar, w, bu);
+                    if (SOFTPLUS) {
+                        // sigmoid(raw) = 1 - exp(-softplus(raw)) = -expm1(-sp); series below 1/8 keeps fp32 relative
+                        // accuracy where 1 - exp(.) would cancel (moot for 16-bit operands: <= 6e-8 absolute)
+                        const float t = sp[m];
+                        if (ES == 2) {
+                            dd *= 1.0f - ex2f(-t * kLog2e);
                         } else {
-                            cB[m] = dhs * u;
-                            cC[m] = dyv * h;
+                            const float ser = t * (1.0f - t * (0.5f - t * (0.16666667f - t * 0.041666668f)));
+                            dd *= (t < 0.125f) ? ser : (1.0f - ex2f(-t * kLog2e));
                         }
-                        sA = fmaf(dhs, w, sA);
-                        sDs = fmaf(dyv, u, sDs);
-                        sb += dd;
-                        sp[m] = dd;  // reuse: sp <- ddelta, dh <- du
-                        dh[m] = du;
                     }
+                    if constexpr (ACC) {
+                        accB[m] = fmaf(dhs, u, accB[m]);
+                        accC[m] = fmaf(dyv, h, accC[m]);
+                    } else {
+                        cB[m] = dhs * u;
+                        cC[m] = dyv * h;
+                    }
+                    sA = fmaf(dhs, w, sA);
+                    sDs = fmaf(dyv, u, sDs);
+                    sb += dd;
+                    sp[m] = dd;  // reuse: sp <- ddelta, dh <- du
+                    dh[m] = du;
                 }
                 // quads that are complete after this pair of tokens (m = 2*mp + 1)
                 if (!ACC && mp % 2 == 1 && mp < S / 2 - 1) {  // m = 3, 7, 11, 15: even lanes, values m-3 .. m
@@ -509,7 +444,6 @@ __global__ void __launch_bounds__(NT, 1) ss2d_bwd_kernel(const FusedBwdArgs p) {
                     }
                 }
             }
-            if constexpr (PACK) sA = sA2.x + sA2.y, sDs = sD2.x + sD2.y, sb = sb2.x + sb2.y;
             if constexpr (!ACC) {
                 const float b0 = __shfl_down_sync(0xffffffffu, cB[0], 1, width);
                 const float b1 = __shfl_down_sync(0xffffffffu, cB[1], 1, width);
