@@ -159,9 +159,9 @@ TRAMBA_API int tramba_sscan_bwd(const void* u, const void* delta, const float* A
  *                           bit-exact with the reference generators)
  *   y      (B, D, L)        fp32       IMAGE order, merged over the K directions (oflex=True contract)
  * Supported: order STD / DILATION / WINDOW / LINE, N == 1, L in {144, 576, 2304, 9216} (H = 12, 24, 48, 96 -- every
- * Tramba-V map at 384^2), D a multiple of 512*18/L, and shared-memory fit (tramba_ss2d_fused_supported says which;
- * the backward in fp32 at L = 9216 does not fit and, like everything else, runs through the un-fused entry points
- * above).  Helix-line directions add duplicate hits of a pixel with shared-memory fp32 atomics, so their merged
+ * Tramba-V map at 384^2) and D a multiple of 512*18/L (tramba_ss2d_fused_supported says which; everything else runs
+ * through the un-fused entry points above).  Forward and backward, F32 and BF16, at every one of these sizes (the
+ * backward in F32 at L = 9216 reads the B / C rows from global memory instead of staging them).  Helix-line directions add duplicate hits of a pixel with shared-memory fp32 atomics, so their merged
  * sums are order-nondeterministic at rounding level, like the reference's CUDA scatter_add_.
  *
  * Backward = CrossMerge*.backward -> SelectiveScanOflex.backward -> CrossScan*.backward (csms6s.py:45-55, 914-923,

@@ -11,6 +11,10 @@
 // warp walks chunk-by-chunk together, then added to global memory with vector reductions.
 #include "sscan.cuh"
 
+#ifndef TRAMBA_SSCAN_BWD_MINB
+#define TRAMBA_SSCAN_BWD_MINB 3
+#endif
+
 namespace tramba {
 
 namespace {
@@ -381,7 +385,7 @@ struct RegSmem {
 };
 
 template <int TSEG, int NS, typename in_t, typename go_t, int LPR, int RW>
-__global__ void __launch_bounds__(kWarpsPerCta * 32, 3)
+__global__ void __launch_bounds__(kWarpsPerCta * 32, TRAMBA_SSCAN_BWD_MINB)
     sscan_bwd_regular_kernel(const SScanArgs p, const int warp_bytes) {
     using SM = RegSmem<TSEG, in_t, go_t>;
     constexpr int CH = 32 * TSEG;
