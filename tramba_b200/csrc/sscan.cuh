@@ -53,6 +53,12 @@ inline SScanPlan make_sscan_plan(long long rows, int L, int es_in) {
     const bool al = (static_cast<long long>(L) * es_in) % 16 == 0;
     if (!al)
         p.tseg = 1;
+#ifdef TRAMBA_SSCAN_TSEG_FORCE   // A/B builds only: a shorter per-lane segment (fewer registers, more resident warps)
+    else if (TRAMBA_SSCAN_TSEG_FORCE == 4 && L % 128 == 0)
+        p.tseg = 4;
+    else if (TRAMBA_SSCAN_TSEG_FORCE == 9 && L % 288 == 0)
+        p.tseg = 9;
+#endif
     else if (L % 384 == 0)
         p.tseg = 12;
     else if (L % 288 == 0 || (288 % L == 0 && L % 9 == 0))
