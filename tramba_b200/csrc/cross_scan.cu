@@ -22,40 +22,42 @@ __device__ __forceinline__ int skew(int e) { return e + (e >> 5); }
 inline int skewed_len(int L) { return L + (L >> 5) + 1; }
 
 // Stage `np` consecutive rows of length L (global, contiguous) into skewed shared planes.
-template <typename T, bool VEC>
+template <typename T, bool VEC, int NTH>
 __device__ __forceinline__ void stage_rows(float* __restrict__ sp, int Lp, const T* __restrict__ g,
                                            long long row_stride, int np, int L) {
     for (int pl = 0; pl < np; ++pl) {
         const T* src = g + pl * row_stride;
         float* dst = sp + pl * Lp;
         if constexpr (VEC) {
-            for (int e = threadIdx.x * 4; e < L; e += kThreads * 4) {
+            for (int e = threadIdx.x * 4; e < L; e += NTH * 4) {
                 float v[4];
                 load_vec<4>(src + e, v);
 #pragma unroll
                 for (int j = 0; j < 4; ++j) dst[skew(e + j)] = v[j];
             }
         } else {
-            for (int e = threadIdx.x; e < L; e += kThreads) dst[skew(e)] = to_f32(src[e]);
+            for (int e = threadIdx.x; e < L; e += NTH) dst[skew(e)] = to_f32(src[e]);
         }
     }
 }
 
 // ------------------------------------------------------------------------------- scan
-template <typename T, bool VEC>
-__global__ void __launch_bounds__(kThreads) cross_scan_kernel(const T* __restrict__ x, T* __restrict__ xs,
+// NTH threads per CTA: 256, or 1024 where a CTA's planes leave room for only one or two CTAs per SM (192 x 192 maps:
+// 152 KB per plane) -- the gather is latency-bound and needs the warps.
+template <typename T, bool VEC, int NTH>
+__global__ void __launch_bounds__(NTH) cross_scan_kernel(const T* __restrict__ x, T* __restrict__ xs,
                                                               const int32_t* __restrict__ table, int K, int C,
                                                               int L, int planes, int ppb) {
     extern __shared__ float sp[];
     const int Lp = L + (L >> 5) + 1;
     const int plane0 = blockIdx.x * ppb;
     const int np = min(ppb, planes - plane0);
-    stage_rows<T, VEC>(sp, Lp, x + static_cast<long long>(plane0) * L, L, np, L);
+    stage_rows<T, VEC, NTH>(sp, Lp, x + static_cast<long long>(plane0) * L, L, np, L);
     __syncthreads();
     for (int k = 0; k < K; ++k) {
         const int32_t* tk = table + static_cast<long long>(k) * L;
         if constexpr (VEC) {
-            for (int t = threadIdx.x * 4; t < L; t += kThreads * 4) {
+            for (int t = threadIdx.x * 4; t < L; t += NTH * 4) {
                 const int4 id = *reinterpret_cast<const int4*>(tk + t);
                 const int p0 = skew(id.x), p1 = skew(id.y), p2 = skew(id.z), p3 = skew(id.w);
                 for (int pl = 0; pl < np; ++pl) {
@@ -67,7 +69,7 @@ __global__ void __launch_bounds__(kThreads) cross_scan_kernel(const T* __restric
                 }
             }
         } else {
-            for (int t = threadIdx.x; t < L; t += kThreads) {
+            for (int t = threadIdx.x; t < L; t += NTH) {
                 const int p0 = skew(tk[t]);
                 for (int pl = 0; pl < np; ++pl) {
                     const int plane = plane0 + pl;
@@ -88,8 +90,8 @@ struct MergeCfg {
 
 // Staged merge: per direction, the token rows of `np` planes are staged in shared memory and
 // every thread gathers the tokens of its own pixels (p = tid + i*blockDim) from them.
-template <typename T, bool VEC>
-__global__ void __launch_bounds__(kThreads) cross_merge_staged_kernel(const T* __restrict__ ys, T* __restrict__ y,
+template <typename T, bool VEC, int NTH>
+__global__ void __launch_bounds__(NTH) cross_merge_staged_kernel(const T* __restrict__ ys, T* __restrict__ y,
                                                                       const int32_t* __restrict__ plan, MergeCfg cfg,
                                                                       int K, int D, int L, int planes, int ppb) {
     extern __shared__ float sm[];
@@ -106,11 +108,11 @@ __global__ void __launch_bounds__(kThreads) cross_merge_staged_kernel(const T* _
     const T* ysb = ys + (static_cast<long long>(b0) * K * D + d0) * L;  // (b0, k=0, d0, 0)
 
     for (int k = cfg.klo; k < cfg.khi; ++k) {
-        stage_rows<T, VEC>(row, Lp, ysb + k * kstride, L, np, L);
+        stage_rows<T, VEC, NTH>(row, Lp, ysb + k * kstride, L, np, L);
         __syncthreads();
         const int32_t* ek = ent + static_cast<long long>(k) * L;
         const int32_t* ok = off + static_cast<long long>(k) * (L + 1);
-        for (int p = threadIdx.x; p < L; p += kThreads) {
+        for (int p = threadIdx.x; p < L; p += NTH) {
             int j0 = p, j1 = p + 1;
             if (!cfg.perm) j0 = ok[p], j1 = ok[p + 1];
             for (int pl = 0; pl < np; ++pl) {
@@ -124,10 +126,10 @@ __global__ void __launch_bounds__(kThreads) cross_merge_staged_kernel(const T* _
     if (cfg.has_std) {
         // T-part: ys1 gathered through inverse(k1), plus ys3 through inverse(k3)
         for (int kk = 1; kk <= 3; kk += 2) {
-            stage_rows<T, VEC>(row, Lp, ysb + kk * kstride, L, np, L);
+            stage_rows<T, VEC, NTH>(row, Lp, ysb + kk * kstride, L, np, L);
             __syncthreads();
             const int32_t* ek = ent + static_cast<long long>(kk) * L;
-            for (int p = threadIdx.x; p < L; p += kThreads) {
+            for (int p = threadIdx.x; p < L; p += NTH) {
                 const int sp_ = skew(ek[p]);
                 for (int pl = 0; pl < np; ++pl) {
                     const float v = row[pl * Lp + sp_];
@@ -141,7 +143,7 @@ __global__ void __launch_bounds__(kThreads) cross_merge_staged_kernel(const T* _
         const T* y0 = ysb + static_cast<long long>(pl) * L;  // k = 0
         const T* y2 = y0 + 2 * kstride;                      // k = 2
         T* yo = y + (static_cast<long long>(plane0) + pl) * L;
-        for (int p = threadIdx.x; p < L; p += kThreads) {
+        for (int p = threadIdx.x; p < L; p += NTH) {
             float o;
             if (cfg.has_std) {
                 const float s = (to_f32(y0[p]) + to_f32(y2[L - 1 - p])) + acc1[pl * L + p];
@@ -198,11 +200,13 @@ cudaError_t scan_t(const T* x, T* xs, const int32_t* plan, int K, int B, int C, 
     ppb = ppb < 1 ? 1 : (ppb > 16 ? 16 : ppb);
     const size_t smem = plane_bytes * ppb;
     const bool vec = (L % 4 == 0) && aligned16(x) && aligned16(xs) && aligned16(plan);
-    auto kern = vec ? cross_scan_kernel<T, true> : cross_scan_kernel<T, false>;
+    const bool wide = smem > 72 * 1024;  // at most two CTAs per SM: 1024 threads each
+    auto kern = wide ? (vec ? cross_scan_kernel<T, true, 1024> : cross_scan_kernel<T, false, 1024>)
+                     : (vec ? cross_scan_kernel<T, true, kThreads> : cross_scan_kernel<T, false, kThreads>);
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
     if (e != cudaSuccess) return e;
     const int grid = (planes + ppb - 1) / ppb;
-    kern<<<grid, kThreads, smem, st>>>(x, xs, plan, K, C, L, planes, ppb);
+    kern<<<grid, wide ? 1024 : kThreads, smem, st>>>(x, xs, plan, K, C, L, planes, ppb);
     note_launch();
     return cudaGetLastError();
 }
@@ -228,11 +232,13 @@ cudaError_t merge_t(const T* ys, T* y, const int32_t* plan, int order, int K, in
         while (D % ppb != 0) --ppb;  // a block never straddles a batch index
         const size_t smem = per_plane * ppb;
         const bool vec = (L % 4 == 0) && aligned16(ys);
-        auto kern = vec ? cross_merge_staged_kernel<T, true> : cross_merge_staged_kernel<T, false>;
+        const bool wide = smem > 72 * 1024;  // at most two CTAs per SM: 1024 threads each
+        auto kern = wide ? (vec ? cross_merge_staged_kernel<T, true, 1024> : cross_merge_staged_kernel<T, false, 1024>)
+                         : (vec ? cross_merge_staged_kernel<T, true, kThreads> : cross_merge_staged_kernel<T, false, kThreads>);
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
         if (e != cudaSuccess) return e;
         const int grid = planes / ppb;
-        kern<<<grid, kThreads, smem, st>>>(ys, y, plan, cfg, K, D, L, planes, ppb);
+        kern<<<grid, wide ? 1024 : kThreads, smem, st>>>(ys, y, plan, cfg, K, D, L, planes, ppb);
     } else {
         const long long total = static_cast<long long>(planes) * L;
         long long grid = (total + kThreads - 1) / kThreads;
