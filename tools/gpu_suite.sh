@@ -4,6 +4,9 @@
 mkdir -p gpurun_out
 bash run_gpu_tests.sh > gpurun_out/run_gpu_tests.log 2>&1; echo "gpu tests rc=$?"; grep -E "^== |FAILED|^E  " gpurun_out/run_gpu_tests.log | head -60
 timeout 300 python tools/kernel_bench.py --dtype bf16 --fused-only > gpurun_out/kernel_bench_fused_bf16.jsonl 2>&1; cat gpurun_out/kernel_bench_fused_bf16.jsonl | cut -c1-260
+for dt in bf16 f32; do timeout 300 python tools/kernel_bench.py --dtype $dt > gpurun_out/kernel_bench_$dt.jsonl 2>&1; done; echo "kernel_bench all rc=$?"
+timeout 200 python tools/side_bench.py > gpurun_out/side_bench.jsonl 2>&1; echo "side_bench rc=$?"
+timeout 300 python bench.py --impl reference --steps 2 --warmup 1 --cpu-budget-s 60 > gpurun_out/bench_reference.json 2> gpurun_out/bench_reference.err; echo "reference arm rc=$?"; cut -c1-200 gpurun_out/bench_reference.json
 timeout 600 python bench.py --steps 20 --warmup 5 --kernel-table gpurun_out/kernel_table.txt > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "bench rc=$?"
 python - <<'PY'
 import json
