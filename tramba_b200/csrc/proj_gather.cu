@@ -18,11 +18,11 @@ namespace tramba {
 
 namespace {
 
-constexpr int kThreads = 256;
 
 // row = (b, k, c); the row is staged in shared memory once (coalesced), the permuted side is an LDS
+// (block size chosen by the launcher: these one-row-per-CTA kernels are latency-bound, long rows get 1024 threads)
 template <typename T>
-__global__ void __launch_bounds__(kThreads) proj_gather_kernel(const T* __restrict__ src, T* __restrict__ dts,
+__global__ void __launch_bounds__(1024) proj_gather_kernel(const T* __restrict__ src, T* __restrict__ dts,
                                                                T* __restrict__ Bs, T* __restrict__ Cs,
                                                                const int32_t* __restrict__ table, int K, int R, int N,
                                                                int L) {
@@ -31,18 +31,19 @@ __global__ void __launch_bounds__(kThreads) proj_gather_kernel(const T* __restri
     const int row = blockIdx.x;               // (b * K + k) * CX + c
     const int c = row % CX, bk = row / CX, k = bk % K;
     const T* s = src + static_cast<size_t>(row) * L;
-    for (int e = threadIdx.x; e < L; e += kThreads) srow[e] = to_f32(s[e]);
+    const int nth = blockDim.x;
+    for (int e = threadIdx.x; e < L; e += nth) srow[e] = to_f32(s[e]);
     __syncthreads();
     T* out = c < R ? dts + (static_cast<size_t>(bk) * R + c) * L
                    : c < R + N ? Bs + (static_cast<size_t>(bk) * N + (c - R)) * L
                                : Cs + (static_cast<size_t>(bk) * N + (c - R - N)) * L;
     const int32_t* tk = table + static_cast<size_t>(k) * L;
-    for (int t = threadIdx.x; t < L; t += kThreads) out[t] = from_f32<T>(srow[__ldg(tk + t)]);
+    for (int t = threadIdx.x; t < L; t += nth) out[t] = from_f32<T>(srow[__ldg(tk + t)]);
 }
 
 // adjoint: gsrc[b, k, c, p] = sum_{t : idx[k][t] == p} g[b, k, c, t], tokens of a pixel in ascending order
 template <typename T, typename G>
-__global__ void __launch_bounds__(kThreads) proj_scatter_kernel(const T* __restrict__ gdts, const G* __restrict__ gBs,
+__global__ void __launch_bounds__(1024) proj_scatter_kernel(const T* __restrict__ gdts, const G* __restrict__ gBs,
                                                                 const G* __restrict__ gCs, T* __restrict__ gsrc,
                                                                 const int32_t* __restrict__ ent,
                                                                 const int32_t* __restrict__ off, int K, int R, int N,
@@ -51,19 +52,20 @@ __global__ void __launch_bounds__(kThreads) proj_scatter_kernel(const T* __restr
     const int CX = R + 2 * N;
     const int row = blockIdx.x;
     const int c = row % CX, bk = row / CX, k = bk % K;
+    const int nth = blockDim.x;
     if (c < R) {
         const T* g = gdts + (static_cast<size_t>(bk) * R + c) * L;
-        for (int e = threadIdx.x; e < L; e += kThreads) srow[e] = to_f32(g[e]);
+        for (int e = threadIdx.x; e < L; e += nth) srow[e] = to_f32(g[e]);
     } else {
         const G* g = c < R + N ? gBs + (static_cast<size_t>(bk) * N + (c - R)) * L
                                : gCs + (static_cast<size_t>(bk) * N + (c - R - N)) * L;
-        for (int e = threadIdx.x; e < L; e += kThreads) srow[e] = to_f32(g[e]);
+        for (int e = threadIdx.x; e < L; e += nth) srow[e] = to_f32(g[e]);
     }
     __syncthreads();
     const int32_t* ek = ent + static_cast<size_t>(k) * L;
     const int32_t* ok = off + static_cast<size_t>(k) * (L + 1);
     T* out = gsrc + static_cast<size_t>(row) * L;
-    for (int p = threadIdx.x; p < L; p += kThreads) {
+    for (int p = threadIdx.x; p < L; p += nth) {
         const int e0 = __ldg(ok + p), e1 = __ldg(ok + p + 1);
         float acc = 0.f;
         for (int e = e0; e < e1; ++e) acc += srow[__ldg(ek + e)];
@@ -178,6 +180,12 @@ cudaError_t launch_batch_sum(const void* in, void* out, int G, int B, long long 
     return cudaGetLastError();
 }
 
+// threads per one-row CTA: ~8 elements per thread, 256 .. 1024
+static int row_threads(int L) {
+    int t = (L / 8 + 31) / 32 * 32;
+    return t < 256 ? 256 : (t > 1024 ? 1024 : t);
+}
+
 cudaError_t launch_proj_gather(const void* src, void* dts, void* Bs, void* Cs, const int32_t* plan, int K, int B, int R,
                                int N, int L, int dtype, cudaStream_t st) {
     const int rows = B * K * (R + 2 * N);
@@ -187,7 +195,7 @@ cudaError_t launch_proj_gather(const void* src, void* dts, void* Bs, void* Cs, c
         using T = std::remove_pointer_t<decltype(tp)>;
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         if (e != cudaSuccess) return e;
-        kern<<<rows, kThreads, smem, st>>>(static_cast<const T*>(src), static_cast<T*>(dts), static_cast<T*>(Bs),
+        kern<<<rows, row_threads(L), smem, st>>>(static_cast<const T*>(src), static_cast<T*>(dts), static_cast<T*>(Bs),
                                            static_cast<T*>(Cs), plan, K, R, N, L);
         return cudaGetLastError();
     };
@@ -211,7 +219,7 @@ cudaError_t launch_proj_scatter(const void* gdts, const void* gBs, const void* g
         using G = std::remove_pointer_t<decltype(gp)>;
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         if (e != cudaSuccess) return e;
-        kern<<<rows, kThreads, smem, st>>>(static_cast<const T*>(gdts), static_cast<const G*>(gBs),
+        kern<<<rows, row_threads(L), smem, st>>>(static_cast<const T*>(gdts), static_cast<const G*>(gBs),
                                            static_cast<const G*>(gCs), static_cast<T*>(gsrc), ent, off, K, R, N, L);
         return cudaGetLastError();
     };
