@@ -183,7 +183,7 @@ __global__ void __launch_bounds__(NT, 1) ss2d_bwd_kernel(const FusedBwdArgs p) {
         const bool sched_in_smem = SCH && p.sched_used[k] <= 2 * L;
         const uint2* __restrict__ sched = (sched_in_smem ? reinterpret_cast<const uint2*>(smem + Lay::sch) : gsched) + j;
         const int sched_iters = p.sched_used[k] / (2 * TP);
-        if (!BCG) mbar_wait(&barBC[0], static_cast<uint32_t>(it & 1));
+        // (the item's B / C rows are awaited inside its first round, after the permutation pass that does not need them)
         // dB / dC: this thread's tokens of direction k, (b, k) row of the (B, K, L) outputs
         float* const gdB = p.dBs + (static_cast<size_t>(b) * K + k) * L + j * S;
         float* const gdC = p.dCs + (static_cast<size_t>(b) * K + k) * L + j * S;
@@ -277,6 +277,7 @@ __global__ void __launch_bounds__(NT, 1) ss2d_bwd_kernel(const FusedBwdArgs p) {
                 mbar_wait(&barD[1], phD1);
                 phD1 ^= 1;
             }
+            if (!BCG && r == 0) mbar_wait(&barBC[0], static_cast<uint32_t>(it & 1));
             const int jc = REV ? TP - 1 - j : j;  // chunk of the plane that holds this thread's tokens
             const in_t* xq = sX(ds) + static_cast<size_t>(q) * L + jc * S;
             float* yq = sY(ds) + static_cast<size_t>(q) * L + jc * S;
