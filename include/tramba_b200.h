@@ -174,16 +174,14 @@ TRAMBA_API int tramba_sscan_bwd(const void* u, const void* delta, const float* A
  *   sched (K, sched_len) uint32, device: tramba_order_sched -- per direction a bank-conflict-free schedule of the
  *          shared-memory permutation image order <-> token order (entry = 2*pixel | 2*token << 16, 0xFFFFFFFF = none);
  *          tramba_order_sched_len = entries per direction (row stride; 0 = unsupported size)
- *   kinds (3K) int32, HOST, as tramba_order_sched writes them: [k] = 0 identity, 1 reversed identity, 2 permutation,
- *          3 table with repeated pixels; [K + k] = schedule entries direction k uses (<= sched_len); [2K + k] = for
- *          kind 3 the leading entries that hold the first token of every pixel (merged with plain stores; the rest
- *          with shared-memory atomics), otherwise == [K + k]
+ *   kinds (2K) int32, HOST, as tramba_order_sched writes them: [k] = 0 identity, 1 reversed identity, 2 permutation,
+ *          3 table with repeated pixels; [K + k] = schedule entries direction k uses (<= sched_len)
  * -------------------------------------------------------------------------------------- */
 TRAMBA_API int tramba_order_table16(int order, int H, int W, int param, uint16_t* idx_out /* K*L, host */);
 TRAMBA_API int tramba_order_table16_skewed(int order, int H, int W, int param, uint16_t* idx_out /* K*L, host */);
 TRAMBA_API size_t tramba_order_sched_len(int order, int H, int W, int param);
 TRAMBA_API int tramba_order_sched(int order, int H, int W, int param, uint32_t* sched_out /* K*len, host */,
-                                  int32_t* kind_out /* 3K, host */);
+                                  int32_t* kind_out /* 2K, host */);
 TRAMBA_API int tramba_ss2d_fused_supported(int order, int K, int D, int H, int W, int N, int in_dtype,
                                            int need_bwd);
 TRAMBA_API int tramba_ss2d_fused_fwd(const void* x, const void* dts, const void* Bs, const void* Cs,

@@ -80,7 +80,7 @@ def _run(sim, fam, H, D, B, bf16, grid, seed=0):
     t16 = np.empty((K, L), dtype=np.uint16)
     _lib.check(_lib.lib.tramba_order_table16_skewed(order, H, H, param, t16.ctypes.data))
     n = int(_lib.lib.tramba_order_sched_len(order, H, H, param))
-    sched, kinds = np.empty((K, n), np.uint32), np.empty((3 * K,), np.int32)
+    sched, kinds = np.empty((K, n), np.uint32), np.empty((2 * K,), np.int32)
     _lib.check(_lib.lib.tramba_order_sched(order, H, H, param, sched.ctypes.data, kinds.ctypes.data))
     code = _lib.BF16 if bf16 else _lib.F32
     ins = dict(x=_dev(x, bf16), dts=_dev(dts, bf16), Bs=_dev(Bs, bf16), Cs=_dev(Cs, bf16), A=_dev(A, False),

@@ -475,9 +475,6 @@ extern "C" int tramba_ss2d_fused_bwd(const void* x, const void* dts, const void*
         const int used = kinds[K + k];
         if (used <= 0 || used > sched_len || used % (2 * g.TP) != 0) return TRAMBA_E_SHAPE;
         a.sched_used[k] = used;
-        const int first = kinds[2 * K + k];
-        if (first < 0 || first > used || first % (2 * g.TP) != 0) return TRAMBA_E_SHAPE;
-        a.sched_first[k] = first;
     }
     a.softplus = delta_softplus ? 1 : 0;
     e = launch_ss2d_fused_bwd(a, g.L, in_dtype, st);

@@ -388,32 +388,24 @@ extern "C" int tramba_order_table(int order, int H, int W, int param, int32_t* i
 // Layout: blocks of 64 entries = two steps interleaved (entry 2 * lane + c of a block = step c of that block), since a
 // thread fetches two consecutive entries with one 8-byte load.  `len` (entries per direction, a multiple of
 // max(64, 2 * L / 18)) is common to all directions of the order.
-// kind_out has 3K entries.  [k]: 0 = identity (token t = pixel t: no permutation pass), 1 = reversed identity,
-//          2 = permutation, 3 = table with repeated pixels (the merge side starts from a zeroed plane);
-//          [K + k]: entries direction k uses (<= len, a multiple of the granule; == L for a permutation);
-//          [2K + k]: kind 3 only -- the leading entries that hold the FIRST token of every pixel (stored without
-//          atomics; the remaining entries are added atomically); otherwise == [K + k].
+// kind_out has 2K entries.  [k]: 0 = identity (token t = pixel t: no permutation pass), 1 = reversed identity,
+//          2 = permutation, 3 = table with repeated pixels (the merge side needs atomic adds and a zeroed plane);
+//          [K + k]: entries direction k uses (<= len, a multiple of the granule; == L for a permutation).
 namespace {
 
-// Colours the tokens listed in `tok` (edges pixel bank -> token bank); colour[i] belongs to tok[i].  Returns the
-// number of colours (= steps).
-int colour_tokens(const int32_t* idx, const std::vector<int>& tok, std::vector<int>& colour) {
+int colour_tokens(const int32_t* idx, int L, std::vector<int>& colour) {
     constexpr int NB = 32;
-    const int n = static_cast<int>(tok.size());
     std::vector<int> degL(NB, 0), degR(NB, 0);
-    for (int i = 0; i < n; ++i) ++degL[idx[tok[i]] & (NB - 1)], ++degR[tok[i] & (NB - 1)];
+    for (int t = 0; t < L; ++t) ++degL[idx[t] & (NB - 1)], ++degR[t & (NB - 1)];
     int delta = 0;
     for (int b = 0; b < NB; ++b) delta = std::max(delta, std::max(degL[b], degR[b]));
-    colour.assign(n, -1);
-    if (n == 0) return 0;
     std::vector<int> atL(static_cast<size_t>(NB) * delta, -1), atR(static_cast<size_t>(NB) * delta, -1);
+    colour.assign(L, -1);
     auto slotL = [&](int u, int c) -> int& { return atL[static_cast<size_t>(u) * delta + c]; };
     auto slotR = [&](int v, int c) -> int& { return atR[static_cast<size_t>(v) * delta + c]; };
-    auto left = [&](int i) { return idx[tok[i]] & (NB - 1); };
-    auto right = [&](int i) { return tok[i] & (NB - 1); };
     std::vector<int> path;
-    for (int e = 0; e < n; ++e) {
-        const int u = left(e), v = right(e);
+    for (int e = 0; e < L; ++e) {
+        const int u = idx[e] & (NB - 1), v = e & (NB - 1);
         int a = 0, b = 0;
         while (slotL(u, a) != -1) ++a;
         while (slotR(v, b) != -1) ++b;
@@ -425,14 +417,14 @@ int colour_tokens(const int32_t* idx, const std::vector<int>& tok, std::vector<i
                 const int f = side ? slotR(node, want) : slotL(node, want);
                 if (f == -1) break;
                 path.push_back(f);
-                node = side ? left(f) : right(f);
+                node = side ? (idx[f] & (NB - 1)) : (f & (NB - 1));
                 side ^= 1;
                 want = (want == a) ? b : a;
             }
-            for (int f : path) slotL(left(f), colour[f]) = -1, slotR(right(f), colour[f]) = -1;
+            for (int f : path) slotL(idx[f] & (NB - 1), colour[f]) = -1, slotR(f & (NB - 1), colour[f]) = -1;
             for (int f : path) {
                 colour[f] = (colour[f] == a) ? b : a;
-                slotL(left(f), colour[f]) = f, slotR(right(f), colour[f]) = f;
+                slotL(idx[f] & (NB - 1), colour[f]) = f, slotR(f & (NB - 1), colour[f]) = f;
             }
         }
         colour[e] = a;
@@ -458,62 +450,21 @@ size_t sched_granule(int L) { return static_cast<size_t>(std::max(64, 2 * (L / 1
 
 }  // namespace
 
-namespace {
-
-struct DirSched {
-    std::vector<uint32_t> ent;  // used entries (a multiple of the granule)
-    int kind = 0, first = 0;
-};
-
-// Appends the coloured moves of `tok` to d.ent (whole granules; steps interleaved two per 64-entry block).
-void append_moves(const int32_t* idx, const std::vector<int>& tok, size_t g, DirSched& d) {
-    std::vector<int> colour;
-    const int steps = colour_tokens(idx, tok, colour);
-    const size_t base = d.ent.size();
-    const size_t need = (static_cast<size_t>(steps) * 32 + g - 1) / g * g;
-    d.ent.resize(base + need, 0xFFFFFFFFu);
-    std::vector<int> fill(steps, 0);
-    for (size_t i = 0; i < tok.size(); ++i) {
-        const int s = colour[i], lane = fill[s]++;
-        const size_t pos = base + static_cast<size_t>(s >> 1) * 64 + 2 * lane + (s & 1);
-        d.ent[pos] = (static_cast<uint32_t>(idx[tok[i]]) * 2u) | (static_cast<uint32_t>(tok[i]) * 2u) << 16;
-    }
-}
-
-// One direction's schedule.  Tables with repeated pixels (kind 3) come in two parts: the FIRST token of every pixel
-// that is hit at all (a partial injection: the merge side can store these without atomics), then the remaining tokens.
-DirSched build_direction(const int32_t* idx, int L) {
-    DirSched d;
-    d.kind = table_kind(idx, L);
-    const size_t g = sched_granule(L);
-    std::vector<int> a, b;
-    if (d.kind == 3) {
-        std::vector<uint8_t> seen(L, 0);
-        for (int t = 0; t < L; ++t) {
-            (seen[idx[t]] ? b : a).push_back(t);
-            seen[idx[t]] = 1;
-        }
-    } else {
-        a.resize(L);
-        for (int t = 0; t < L; ++t) a[t] = t;
-    }
-    append_moves(idx, a, g, d);
-    d.first = static_cast<int>(d.ent.size());
-    if (!b.empty()) append_moves(idx, b, g, d);
-    return d;
-}
-
-}  // namespace
-
 extern "C" size_t tramba_order_sched_len(int order, int H, int W, int param) {
     const int K = tramba_order_num_directions(order);
     if (K < 0 || H <= 0 || W <= 0 || static_cast<long long>(H) * W > 32768) return 0;
     const int L = H * W;
     std::vector<int32_t> t(static_cast<size_t>(K) * L);
     if (tramba_order_table(order, H, W, param, t.data()) != TRAMBA_OK) return 0;
-    size_t len = 0;
-    for (int k = 0; k < K; ++k) len = std::max(len, build_direction(t.data() + static_cast<size_t>(k) * L, L).ent.size());
-    return len;
+    int delta = 0;
+    for (int k = 0; k < K; ++k) {
+        std::vector<int> deg(32, 0);
+        for (int i = 0; i < L; ++i) ++deg[t[static_cast<size_t>(k) * L + i] & 31];
+        for (int b = 0; b < 32; ++b) delta = std::max(delta, deg[b]);
+    }
+    delta = std::max(delta, (L + 31) / 32);
+    const size_t g = sched_granule(L);
+    return (static_cast<size_t>(delta) * 32 + g - 1) / g * g;
 }
 
 extern "C" int tramba_order_sched(int order, int H, int W, int param, uint32_t* sched_out, int32_t* kind_out) {
@@ -526,14 +477,23 @@ extern "C" int tramba_order_sched(int order, int H, int W, int param, uint32_t* 
     std::vector<int32_t> t(static_cast<size_t>(K) * L);
     const int rc = tramba_order_table(order, H, W, param, t.data());
     if (rc != TRAMBA_OK) return rc;
+    std::vector<int> colour, fill;
     for (int k = 0; k < K; ++k) {
-        const DirSched d = build_direction(t.data() + static_cast<size_t>(k) * L, L);
+        const int32_t* idx = t.data() + static_cast<size_t>(k) * L;
         uint32_t* out = sched_out + static_cast<size_t>(k) * len;
         std::fill(out, out + len, 0xFFFFFFFFu);
-        std::copy(d.ent.begin(), d.ent.end(), out);
-        kind_out[k] = d.kind;
-        kind_out[K + k] = static_cast<int32_t>(d.ent.size());  // entries this direction really uses (== L for a permutation)
-        kind_out[2 * K + k] = d.first;                         // of which: first hits (kind 3), else all of them
+        kind_out[k] = table_kind(idx, L);
+        const int steps = colour_tokens(idx, L, colour);
+        if (static_cast<size_t>(steps) * 32 > len) return TRAMBA_E_LIMIT;
+        // entries this direction really uses (the row stride `len` is the order's maximum): a permutation needs L
+        const size_t g = sched_granule(L);
+        kind_out[K + k] = static_cast<int32_t>((static_cast<size_t>(steps) * 32 + g - 1) / g * g);
+        fill.assign(steps, 0);
+        for (int e = 0; e < L; ++e) {
+            const int s = colour[e], lane = fill[s]++;
+            const size_t pos = static_cast<size_t>(s >> 1) * 64 + 2 * lane + (s & 1);
+            out[pos] = (static_cast<uint32_t>(idx[e]) * 2u) | (static_cast<uint32_t>(e) * 2u) << 16;
+        }
     }
     return TRAMBA_OK;
 }

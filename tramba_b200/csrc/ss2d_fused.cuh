@@ -84,7 +84,6 @@ struct FusedBwdArgs {
     int B, K, D;
     int sched_len;          // row stride of sched (entries)
     int sched_used[8];      // entries direction k really uses (<= sched_len; == L for a permutation)
-    int sched_first[8];     // kind 3: leading entries that hold the first token of every pixel (no atomics needed)
     uint32_t kinds;         // 4 bits per direction: 0 identity, 1 reversed identity, 2 permutation, 3 with repeats
     int softplus;
     int R;                  // rounds per item (set by the launcher)

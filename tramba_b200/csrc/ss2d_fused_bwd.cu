@@ -498,16 +498,9 @@ __global__ void __launch_bounds__(NT, 1) ss2d_bwd_kernel(const FusedBwdArgs p) {
                 };
                 const uint2* sc = sched;
                 if (dup) {
-                    // repeated pixels.  The schedule lists the FIRST token of every pixel first: those are plain,
-                    // batched, conflict-free stores over the zeroed plane (75 % of a helix direction's moves).  The
-                    // remaining tokens are added one move at a time with shared-memory atomics (a CAS loop each; the
-                    // schedule still keeps the 32 lanes of a step on distinct banks).
-                    const int iters_a = p.sched_first[k] / (2 * TP);
-                    if (sched_in_smem) walk_schedule<TP, false, true>(sc, iters_a, move);
-                    else walk_schedule<TP, false>(sc, iters_a, move);
-                    __syncthreads();
-                    sc += static_cast<size_t>(iters_a) * TP;
-                    for (int n = iters_a; n < sched_iters; ++n, sc += TP) {
+                    // repeated pixels: one move at a time, added with shared-memory atomics (a CAS loop each; the
+                    // schedule still keeps the 32 lanes of a step on distinct banks)
+                    for (int n = 0; n < sched_iters; ++n, sc += TP) {
                         const uint2 e2 = sched_in_smem ? *sc : __ldg(sc);
                         if (e2.x != 0xFFFFFFFFu) atomicAdd(di + ((e2.x & 0xFFFFu) >> 1), ut[e2.x >> 17]);
                         if (e2.y != 0xFFFFFFFFu) atomicAdd(di + ((e2.y & 0xFFFFu) >> 1), ut[e2.y >> 17]);

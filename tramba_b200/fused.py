@@ -68,7 +68,7 @@ def _sched(order, H, param, device):
         if n == 0:
             raise RuntimeError("tramba_b200: no permutation schedule for this order / size")
         t = np.empty((K, n), dtype=np.uint32)
-        kinds = np.empty((3 * K,), dtype=np.int32)       # K kinds, K used lengths, K first-hit lengths
+        kinds = np.empty((2 * K,), dtype=np.int32)       # K kinds, then K used lengths
         _lib.check(_lib.lib.tramba_order_sched(order, H, H, param, t.ctypes.data, kinds.ctypes.data))
         hit = (torch.from_numpy(t.view(np.int32)).to(device), kinds)
         _idx_cache[key] = hit
