@@ -34,6 +34,9 @@ namespace tramba {
 
 namespace {
 
+#ifndef TRAMBA_ACC_MIN_PP
+#define TRAMBA_ACC_MIN_PP 1
+#endif
 #ifndef TRAMBA_NKEEP
 #define TRAMBA_NKEEP 18
 #endif
@@ -192,7 +195,7 @@ __global__ void __launch_bounds__(NT, 1) ss2d_bwd_kernel(const FusedBwdArgs p) {
         // (b, k) -- would all add into the same few KB of dB / dC, and same-address reds serialise at L2.  There the
         // contributions stay in registers over the item's rounds and are folded over the planes in shared memory
         // first (one red per token per ITEM).  PP == 1 (L = 9216): per-round vector reds, no accumulator registers.
-        constexpr bool ACC = PP > 1;
+        constexpr bool ACC = PP > TRAMBA_ACC_MIN_PP;
         float accB[ACC ? S : 1], accC[ACC ? S : 1];
         if constexpr (ACC) {
 #pragma unroll
