@@ -10,8 +10,6 @@
 // are stored skewed (one pad word per 32) so that the power-of-two strides of column-major
 // orders spread over all banks.  The merge is a gather through the inverse (CSR) table, so it
 // is deterministic and needs no atomics even where the helix order hits a pixel many times.
-#include <type_traits>
-
 #include "common.cuh"
 
 namespace tramba {
@@ -22,19 +20,6 @@ constexpr int kThreads = 256;
 
 __device__ __forceinline__ int skew(int e) { return e + (e >> 5); }
 inline int skewed_len(int L) { return L + (L >> 5) + 1; }
-
-// Staged token rows are kept either as fp32 (one pad word per 32) or, for 16-bit inputs whose fp32 rows would not fit
-// (192 x 192 planes), in the input type (one pad WORD = two elements per 64 elements: the same bank spreading).
-template <typename R>
-struct RowOps {
-    __host__ __device__ static int skew(int e) { return e + (e >> 5); }
-    __host__ __device__ static int len(int L) { return L + (L >> 5) + 1; }
-};
-template <>
-struct RowOps<__nv_bfloat16> {
-    __host__ __device__ static int skew(int e) { return e + 2 * (e >> 6); }
-    __host__ __device__ static int len(int L) { return L + 2 * (L >> 6) + 2; }
-};
 
 // Stage `np` consecutive rows of length L (global, contiguous) into skewed shared planes.
 template <typename T, bool VEC, int NTH>
@@ -52,29 +37,6 @@ __device__ __forceinline__ void stage_rows(float* __restrict__ sp, int Lp, const
             }
         } else {
             for (int e = threadIdx.x; e < L; e += NTH) dst[skew(e)] = to_f32(src[e]);
-        }
-    }
-}
-
-// The same staging into rows of element type R (R = float: identical to stage_rows; R = T: raw copy).
-template <typename T, typename R, bool VEC, int NTH>
-__device__ __forceinline__ void stage_rows_as(R* __restrict__ sp, int Lp, const T* __restrict__ g, long long row_stride,
-                                              int np, int L) {
-    if constexpr (std::is_same<R, float>::value) {
-        stage_rows<T, VEC, NTH>(sp, Lp, g, row_stride, np, L);
-    } else {
-        for (int pl = 0; pl < np; ++pl) {
-            const T* src = g + pl * row_stride;
-            R* dst = sp + pl * Lp;
-            if constexpr (VEC) {   // 4 elements (8 bytes) per load; a group of 4 never straddles a pad (4 | 64)
-                for (int e = threadIdx.x * 4; e < L; e += NTH * 4) {
-                    const uint2 q = *reinterpret_cast<const uint2*>(src + e);
-                    uint32_t* d = reinterpret_cast<uint32_t*>(dst + RowOps<R>::skew(e));
-                    d[0] = q.x, d[1] = q.y;
-                }
-            } else {
-                for (int e = threadIdx.x; e < L; e += NTH) dst[RowOps<R>::skew(e)] = src[e];
-            }
         }
     }
 }
@@ -128,15 +90,15 @@ struct MergeCfg {
 
 // Staged merge: per direction, the token rows of `np` planes are staged in shared memory and
 // every thread gathers the tokens of its own pixels (p = tid + i*blockDim) from them.
-template <typename T, typename R, bool VEC, int NTH>
+template <typename T, bool VEC, int NTH>
 __global__ void __launch_bounds__(NTH) cross_merge_staged_kernel(const T* __restrict__ ys, T* __restrict__ y,
                                                                       const int32_t* __restrict__ plan, MergeCfg cfg,
                                                                       int K, int D, int L, int planes, int ppb) {
     extern __shared__ float sm[];
-    const int Lp = RowOps<R>::len(L);
-    float* acc = sm;                                       // [ppb][L]  sequential part (if any)
+    const int Lp = L + (L >> 5) + 1;
+    float* row = sm;                                       // [ppb][Lp] skewed token rows
+    float* acc = row + static_cast<size_t>(ppb) * Lp;      // [ppb][L]  sequential part (if any)
     float* acc1 = acc + (cfg.khi > cfg.klo ? static_cast<size_t>(ppb) * L : 0);  // [ppb][L] std T-part
-    R* row = reinterpret_cast<R*>(acc1 + (cfg.has_std ? static_cast<size_t>(ppb) * L : 0));  // [ppb][Lp] skewed token rows
     const int32_t* ent = plan + static_cast<long long>(K) * L;
     const int32_t* off = plan + 2ll * K * L;
     const int plane0 = blockIdx.x * ppb;
@@ -146,7 +108,7 @@ __global__ void __launch_bounds__(NTH) cross_merge_staged_kernel(const T* __rest
     const T* ysb = ys + (static_cast<long long>(b0) * K * D + d0) * L;  // (b0, k=0, d0, 0)
 
     for (int k = cfg.klo; k < cfg.khi; ++k) {
-        stage_rows_as<T, R, VEC, NTH>(row, Lp, ysb + k * kstride, L, np, L);
+        stage_rows<T, VEC, NTH>(row, Lp, ysb + k * kstride, L, np, L);
         __syncthreads();
         const int32_t* ek = ent + static_cast<long long>(k) * L;
         const int32_t* ok = off + static_cast<long long>(k) * (L + 1);
@@ -155,7 +117,7 @@ __global__ void __launch_bounds__(NTH) cross_merge_staged_kernel(const T* __rest
             if (!cfg.perm) j0 = ok[p], j1 = ok[p + 1];
             for (int pl = 0; pl < np; ++pl) {
                 float s = (k == cfg.klo) ? 0.f : acc[pl * L + p];
-                for (int j = j0; j < j1; ++j) s += to_f32(row[pl * Lp + RowOps<R>::skew(ek[j])]);
+                for (int j = j0; j < j1; ++j) s += row[pl * Lp + skew(ek[j])];
                 acc[pl * L + p] = s;
             }
         }
@@ -164,13 +126,13 @@ __global__ void __launch_bounds__(NTH) cross_merge_staged_kernel(const T* __rest
     if (cfg.has_std) {
         // T-part: ys1 gathered through inverse(k1), plus ys3 through inverse(k3)
         for (int kk = 1; kk <= 3; kk += 2) {
-            stage_rows_as<T, R, VEC, NTH>(row, Lp, ysb + kk * kstride, L, np, L);
+            stage_rows<T, VEC, NTH>(row, Lp, ysb + kk * kstride, L, np, L);
             __syncthreads();
             const int32_t* ek = ent + static_cast<long long>(kk) * L;
             for (int p = threadIdx.x; p < L; p += NTH) {
-                const int sp_ = RowOps<R>::skew(ek[p]);
+                const int sp_ = skew(ek[p]);
                 for (int pl = 0; pl < np; ++pl) {
-                    const float v = to_f32(row[pl * Lp + sp_]);
+                    const float v = row[pl * Lp + sp_];
                     acc1[pl * L + p] = (kk == 1) ? v : acc1[pl * L + p] + v;
                 }
             }
@@ -263,27 +225,22 @@ cudaError_t merge_t(const T* ys, T* y, const int32_t* plan, int order, int K, in
                 order == TRAMBA_ORDER_HILBERT || order == TRAMBA_ORDER_DIAGONAL || order == TRAMBA_ORDER_AB2 ||
                 order == TRAMBA_ORDER_AB1);
     const int planes = B * D;
+    const int Lp = skewed_len(L);
     const int nacc = (cfg.khi > cfg.klo ? 1 : 0) + (cfg.has_std ? 1 : 0);
-    const size_t acc_bytes = static_cast<size_t>(nacc) * L * 4;
-    const size_t per_plane = static_cast<size_t>(RowOps<float>::len(L)) * 4 + acc_bytes;
-    // 16-bit inputs whose fp32 rows do not fit (192 x 192): rows staged in the input type
-    const size_t per_plane_raw = static_cast<size_t>(RowOps<T>::len(L)) * sizeof(T) + acc_bytes;
-    const bool raw = !std::is_same<T, float>::value && per_plane > 200 * 1024 && per_plane_raw <= 226 * 1024;
-    if (per_plane <= 200 * 1024 || raw) {
-        const size_t pp = raw ? per_plane_raw : per_plane;
-        int ppb = static_cast<int>((72 * 1024) / pp);
+    const size_t per_plane = static_cast<size_t>(Lp) * 4 + static_cast<size_t>(nacc) * L * 4;
+    if (per_plane <= 200 * 1024) {
+        int ppb = static_cast<int>((72 * 1024) / per_plane);
         ppb = ppb < 1 ? 1 : (ppb > 16 ? 16 : ppb);
         while (D % ppb != 0) --ppb;  // a block never straddles a batch index
-        const size_t smem = pp * ppb;
+        const size_t smem = per_plane * ppb;
         const bool vec = (L % 4 == 0) && aligned16(ys);
         const bool wide = smem > 72 * 1024;  // at most two CTAs per SM: 1024 threads each
-        auto kern = raw ? (vec ? cross_merge_staged_kernel<T, T, true, 1024> : cross_merge_staged_kernel<T, T, false, 1024>)
-                  : wide ? (vec ? cross_merge_staged_kernel<T, float, true, 1024> : cross_merge_staged_kernel<T, float, false, 1024>)
-                         : (vec ? cross_merge_staged_kernel<T, float, true, kThreads> : cross_merge_staged_kernel<T, float, false, kThreads>);
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        auto kern = wide ? (vec ? cross_merge_staged_kernel<T, true, 1024> : cross_merge_staged_kernel<T, false, 1024>)
+                         : (vec ? cross_merge_staged_kernel<T, true, kThreads> : cross_merge_staged_kernel<T, false, kThreads>);
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
         if (e != cudaSuccess) return e;
         const int grid = planes / ppb;
-        kern<<<grid, (wide || raw) ? 1024 : kThreads, smem, st>>>(ys, y, plan, cfg, K, D, L, planes, ppb);
+        kern<<<grid, wide ? 1024 : kThreads, smem, st>>>(ys, y, plan, cfg, K, D, L, planes, ppb);
     } else {
         const long long total = static_cast<long long>(planes) * L;
         long long grid = (total + kThreads - 1) / kThreads;
