@@ -83,6 +83,43 @@ def test_plan_inverse_is_the_sorted_csr(order, H, param):
         assert np.array_equal(np.diff(off[k]), np.bincount(fwd[k], minlength=L))
 
 
+@pytest.mark.parametrize("order,H,param", [(_lib.ORDER_STD, 12, 0), (_lib.ORDER_STD, 96, 0), (_lib.ORDER_LINE, 12, 0),
+                                           (_lib.ORDER_LINE, 24, 0), (_lib.ORDER_LINE, 48, 0), (_lib.ORDER_LINE, 96, 0),
+                                           (_lib.ORDER_WINDOW, 24, 8), (_lib.ORDER_WINDOW, 96, 16),
+                                           (_lib.ORDER_DILATION, 48, 4), (_lib.ORDER_DILATION, 96, 4)])
+def test_permutation_schedule_properties(order, H, param):
+    """tramba_order_sched (what the fused backward walks): per direction the moves (pixel, token) of the order table,
+    every token exactly once, nothing else; identity / reversed-identity / permutation / repeated-pixel kinds; a
+    permutation uses L entries (rounded up to the granule); and every warp step (32 moves) touches 32 distinct pixel banks AND 32 distinct
+    token banks -- the property that makes the shared-memory permutation bank-conflict-free in both directions."""
+    K = _lib.lib.tramba_order_num_directions(order)
+    L = H * H
+    tab = ops.order_table_host(order, H, param).reshape(K, L)
+    n = int(_lib.lib.tramba_order_sched_len(order, H, H, param))
+    assert n > 0 and n % max(64, 2 * L // 18) == 0
+    sched, kinds = np.empty((K, n), np.uint32), np.empty((2 * K,), np.int32)
+    _lib.check(_lib.lib.tramba_order_sched(order, H, H, param, sched.ctypes.data, kinds.ctypes.data))
+    for k in range(K):
+        used = int(kinds[K + k])
+        assert 0 < used <= n and (sched[k, used:] == 0xFFFFFFFF).all()
+        e = sched[k, :used]
+        v = e[e != 0xFFFFFFFF].astype(np.int64)
+        tok, pix = (v >> 16) >> 1, (v & 0xFFFF) >> 1
+        assert np.array_equal(np.sort(tok), np.arange(L)) and np.array_equal(tab[k][tok], pix)
+        ident, rev = np.array_equal(tab[k], np.arange(L)), np.array_equal(tab[k], np.arange(L)[::-1])
+        dup = len(np.unique(tab[k])) < L
+        assert kinds[k] == (0 if ident else 1 if rev else 3 if dup else 2)
+        if not dup:                                            # a permutation: L moves in the fewest whole granules
+            g = max(64, 2 * L // 18)
+            assert used == (L + g - 1) // g * g
+        steps = e.reshape(-1, 32, 2)                           # 64-entry blocks = two interleaved steps of 32 lanes
+        for c in range(2):
+            for row in steps[:, :, c]:
+                r = row[row != 0xFFFFFFFF].astype(np.int64)
+                pb, tb = ((r & 0xFFFF) >> 1) & 31, ((r >> 16) >> 1) & 31
+                assert len(np.unique(pb)) == len(pb) and len(np.unique(tb)) == len(tb)
+
+
 def test_order_errors():
     buf = np.zeros(16, np.int32)
     assert _lib.lib.tramba_order_table(_lib.ORDER_WINDOW, 12, 12, 5, buf.ctypes.data) == -4   # 12 % 5
