@@ -28,7 +28,7 @@ def test_kernel_name_to_kind():
 
 
 def test_roofline_traffic_json_matches_committed_ncu_list(tmp_path):
-    src = os.path.join(ROOT, "profiles", "r01_tramba_dram_per_launch.csv")
+    src = os.path.join(ROOT, "profiles", "r02_tramba_dram_per_launch.csv")
     dst = os.path.join(ROOT, "profiles", "roofline_traffic.json")
     if not (os.path.exists(src) and os.path.exists(dst)):
         import pytest
