@@ -34,6 +34,11 @@ namespace tramba {
 
 namespace {
 
+// TRAMBA_KO: knock-out timing experiments (WRONG results; never set in the product build): bit 0 skips the dB / dC
+// vector reds, bit 1 stores dx instead of reduce-adding it, bit 2 skips both permutation passes
+#ifndef TRAMBA_KO
+#define TRAMBA_KO 0
+#endif
 #ifndef TRAMBA_ACC_MIN_PP
 #define TRAMBA_ACC_MIN_PP 1
 #endif
@@ -169,7 +174,7 @@ __global__ void __launch_bounds__(NT, 1) ss2d_bwd_kernel(const FusedBwdArgs p) {
         int b, k, d00;
         item_coord(it, b, k, d00);
         const int kind = (p.kinds >> (4 * k)) & 15;  // 0 identity, 1 reversed identity, 2 permutation, 3 with repeats
-        const bool perm = kind >= 2;
+        const bool perm = kind >= 2 && !(TRAMBA_KO & 4);
         const bool dup = kind == 3;
         const bool dense = kind == 2 && p.sched_used[k] == L;  // a permutation: every schedule entry is a move
         // the direction's permutation schedule: staged in shared memory for the item where there is room (short
@@ -194,8 +199,13 @@ __global__ void __launch_bounds__(NT, 1) ss2d_bwd_kernel(const FusedBwdArgs p) {
         // ACC (several planes per round, L <= 2304): the PP planes of a round -- and every CTA working on the same
         // (b, k) -- would all add into the same few KB of dB / dC, and same-address reds serialise at L2.  There the
         // contributions stay in registers over the item's rounds and are folded over the planes in shared memory
-        // first (one red per token per ITEM).  PP == 1 (L = 9216): per-round vector reds, no accumulator registers.
-        constexpr bool ACC = PP > TRAMBA_ACC_MIN_PP;
+        // first (one red per token per ITEM).  PP == 1 (L = 9216): with 16-bit operands the accumulators are kept as
+        // well (reds once per item instead of once per round: the per-round 16-byte reds are 73 KB per round and SM of
+        // L2 atomic traffic -- more than the kernel's HBM traffic -- and cost 26 % of the kernel in a knock-out run;
+        // the accumulators spill ~30 words but are 4-9 % faster on the std / helix sites and equal on the others,
+        // profiles/r02_fused_bwd_knockout.txt).  fp32 operands keep the per-round vector reds (392 bytes of spills
+        // otherwise).  -DTRAMBA_ACC_MIN_PP=4 (A/B builds): per-round reds for up to 4 planes per round.
+        constexpr bool ACC = PP > TRAMBA_ACC_MIN_PP || (ES == 2 && TRAMBA_ACC_MIN_PP == 1);
         float accB[ACC ? S : 1], accC[ACC ? S : 1];
         if constexpr (ACC) {
 #pragma unroll
@@ -436,13 +446,13 @@ __global__ void __launch_bounds__(NT, 1) ss2d_bwd_kernel(const FusedBwdArgs p) {
                 }
                 // quads that are complete after this pair of tokens (m = 2*mp + 1)
                 if (!ACC && mp % 2 == 1 && mp < S / 2 - 1) {  // m = 3, 7, 11, 15: even lanes, values m-3 .. m
-                    if (!odd) {
+                    if (!odd && !((TRAMBA_KO & 1) && p.softplus != 77)) {
                         red_add_v4(gdB + 2 * mp - 2, cB[2 * mp - 2], cB[2 * mp - 1], cB[2 * mp], cB[2 * mp + 1]);
                         red_add_v4(gdC + 2 * mp - 2, cC[2 * mp - 2], cC[2 * mp - 1], cC[2 * mp], cC[2 * mp + 1]);
                     }
                 }
                 if (!ACC && mp % 2 == 0 && mp >= 2) {  // m = 5, 9, 13, 17: odd lanes, values m-3 .. m
-                    if (odd) {
+                    if (odd && !((TRAMBA_KO & 1) && p.softplus != 77)) {
                         red_add_v4(gdB + 2 * mp - 2, cB[2 * mp - 2], cB[2 * mp - 1], cB[2 * mp], cB[2 * mp + 1]);
                         red_add_v4(gdC + 2 * mp - 2, cC[2 * mp - 2], cC[2 * mp - 1], cC[2 * mp], cC[2 * mp + 1]);
                     }
@@ -453,7 +463,7 @@ __global__ void __launch_bounds__(NT, 1) ss2d_bwd_kernel(const FusedBwdArgs p) {
                 const float b1 = __shfl_down_sync(0xffffffffu, cB[1], 1, width);
                 const float c0 = __shfl_down_sync(0xffffffffu, cC[0], 1, width);
                 const float c1 = __shfl_down_sync(0xffffffffu, cC[1], 1, width);
-                if (!odd) {
+                if (!odd && !((TRAMBA_KO & 1) && p.softplus != 77)) {
                     red_add_v4(gdB + S - 2, cB[S - 2], cB[S - 1], b0, b1);
                     red_add_v4(gdC + S - 2, cC[S - 2], cC[S - 1], c0, c1);
                 }
@@ -522,7 +532,8 @@ __global__ void __launch_bounds__(NT, 1) ss2d_bwd_kernel(const FusedBwdArgs p) {
             __syncthreads();
             if (tid == 0) {
                 bulk_s2g(gdd + ((static_cast<long long>(b) * K + k) * D + d0) * L, sD(dbuf), TOK * ES);
-                bulk_reduce_add_f32_s2g(p.dx + (static_cast<long long>(b) * D + d0) * L, dxp, TOK * 4);
+                if (TRAMBA_KO & 2) bulk_s2g(p.dx + (static_cast<long long>(b) * D + d0) * L, dxp, TOK * 4);
+                else bulk_reduce_add_f32_s2g(p.dx + (static_cast<long long>(b) * D + d0) * L, dxp, TOK * 4);
                 bulk_commit();
                 if (!PIPE) {
                     bulk_wait_read<0>();
