@@ -560,10 +560,10 @@ __global__ void __launch_bounds__(NT, 1) ss2d_bwd_kernel(const FusedBwdArgs p) {
             if (kind == 1) round(std::true_type{}, r);
             else round(std::false_type{}, r);
         }
-        if constexpr (ACC) {
+        if constexpr (ACC) if (!((TRAMBA_KO & 8) && p.softplus != 77)) {
             // ---- item flush: fold the PP planes' partial sums with a binary tree through shared memory (the upper
             // half of the planes parks its 2*S values, element-major so that lanes hit consecutive banks; the lower
-            // half adds them), then plane 0 sends one red per token.  No shared-memory atomics (a CAS loop each, and
+            // half adds them); the sums then leave through the scratch by bulk reductions.  No shared-memory atomics (a CAS loop each, and
             // all PP planes would hit the same word in lockstep).  Scratch = a plane buffer nobody uses between items:
             // the du staging once its bulk reduction has been read (PIPE), the token-ordered dy planes (!PIPE; the
             // next round's loads went to the other set); (PP/2) * TP * 2S floats = TOK floats at most.
@@ -584,13 +584,45 @@ __global__ void __launch_bounds__(NT, 1) ss2d_bwd_kernel(const FusedBwdArgs p) {
                     for (int m = 0; m < S; ++m) accB[m] += f[m * stride + mine], accC[m] += f[(S + m) * stride + mine];
                 }
             }
-            if (q == 0) {
-#pragma unroll
-                for (int m = 0; m < S; m += 2) {
-                    asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(gdB + m), "f"(accB[m]), "f"(accB[m + 1])
-                                 : "memory");
-                    asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(gdC + m), "f"(accC[m]), "f"(accC[m + 1])
-                                 : "memory");
+            // Plane 0 now holds the item's dB / dC (every thread, when a round is one plane).  They leave COALESCED:
+            // written token-ordered into the scratch and added to the (b, k) rows by TMA bulk reductions.  (Reds
+            // straight from the registers -- lane stride 18 floats, one 32-byte sector per lane -- cost ~20 % of the
+            // kernel in a knock-out run, profiles/r02_fused_bwd_knockout.txt.)
+            float* const rowB = p.dBs + (static_cast<size_t>(b) * K + k) * L;
+            float* const rowC = p.dCs + (static_cast<size_t>(b) * K + k) * L;
+            if constexpr (PP > 1) {
+                __syncthreads();  // plane 0's reads of the tree are done before the scratch is rewritten
+                if (q == 0) {
+                    store_tokens<S>(f + j * S, accB);
+                    store_tokens<S>(f + L + j * S, accC);
+                }
+                fence_proxy_async_smem();
+                __syncthreads();
+                if (tid == 0) {
+                    bulk_reduce_add_f32_s2g(rowB, f, L * 4);
+                    bulk_reduce_add_f32_s2g(rowC, f + L, L * 4);
+                    bulk_commit();
+                    if (!PIPE) bulk_wait_read<0>();  // (PIPE: the next writer of the scratch waits for it mid-round)
+                }
+            } else {
+                // one plane per round: L floats fill the scratch, so dB and dC take turns
+                __syncthreads();  // the staging has left (tid 0 waited above)
+                store_tokens<S>(f + j * S, accB);
+                fence_proxy_async_smem();
+                __syncthreads();
+                if (tid == 0) {
+                    bulk_reduce_add_f32_s2g(rowB, f, L * 4);
+                    bulk_commit();
+                    bulk_wait_read<0>();
+                }
+                __syncthreads();
+                store_tokens<S>(f + j * S, accC);
+                fence_proxy_async_smem();
+                __syncthreads();
+                if (tid == 0) {
+                    bulk_reduce_add_f32_s2g(rowC, f, L * 4);
+                    bulk_commit();
+                    if (!PIPE) bulk_wait_read<0>();
                 }
             }
             __syncthreads();  // everybody is done with the scratch (and with sB / sC)
