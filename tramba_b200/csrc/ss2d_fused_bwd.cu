@@ -561,40 +561,49 @@ __global__ void __launch_bounds__(NT, 1) ss2d_bwd_kernel(const FusedBwdArgs p) {
             else round(std::false_type{}, r);
         }
         if constexpr (ACC) if (!((TRAMBA_KO & 8) && p.softplus != 77)) {
-            // ---- item flush: fold the PP planes' partial sums with a binary tree through shared memory (the upper
-            // half of the planes parks its 2*S values, element-major so that lanes hit consecutive banks; the lower
-            // half adds them); the sums then leave through the scratch by bulk reductions.  No shared-memory atomics (a CAS loop each, and
-            // all PP planes would hit the same word in lockstep).  Scratch = a plane buffer nobody uses between items:
-            // the du staging once its bulk reduction has been read (PIPE), the token-ordered dy planes (!PIPE; the
-            // next round's loads went to the other set); (PP/2) * TP * 2S floats = TOK floats at most.
+            // ---- item flush.  Several planes per round: the PP planes' partial sums are folded in shared memory in two
+            // steps -- the upper half of the planes parks its 2*S values per thread (token-ordered rows of 2L floats
+            // per plane), the lower half adds them and parks the sums, then ALL threads add up the PP/2 rows column by
+            // column (consecutive lanes = consecutive tokens) -- 5 barriers instead of the 2*log2(PP)+2 of a binary
+            // tree, and every thread busy in the last step.  The sums (for one plane per round: every thread's
+            // accumulators) then leave COALESCED, token-ordered from the scratch, by TMA bulk reductions into the
+            // (b, k) rows: reds straight from the registers -- lane stride 18 floats, one 32-byte sector per lane --
+            // cost ~20 % of the kernel in a knock-out run (profiles/r02_fused_bwd_knockout.txt).  No shared-memory
+            // atomics (a CAS loop each).  Scratch = a plane buffer nobody uses between items: the du staging once
+            // its bulk reduction has been read (PIPE), the token-ordered dy planes (!PIPE; the next round's loads
+            // went to the other set); (PP/2) rows of 2L floats = TOK floats.
             if (PIPE && tid == 0) bulk_wait_read<0>();
             float* f = PIPE ? sDXs : sY(ld ^ 1);
-#pragma unroll 1
-            for (int hp = PP / 2; hp >= 1; hp >>= 1) {
-                __syncthreads();  // (first turn: the staging has left; later turns: the previous readers are done)
-                const int slot = (q - hp) * TP + j, stride = hp * TP;
-                if (q >= hp && q < 2 * hp) {
-#pragma unroll
-                    for (int m = 0; m < S; ++m) f[m * stride + slot] = accB[m], f[(S + m) * stride + slot] = accC[m];
-                }
-                __syncthreads();
-                if (q < hp) {
-                    const int mine = q * TP + j;
-#pragma unroll
-                    for (int m = 0; m < S; ++m) accB[m] += f[m * stride + mine], accC[m] += f[(S + m) * stride + mine];
-                }
-            }
-            // Plane 0 now holds the item's dB / dC (every thread, when a round is one plane).  They leave COALESCED:
-            // written token-ordered into the scratch and added to the (b, k) rows by TMA bulk reductions.  (Reds
-            // straight from the registers -- lane stride 18 floats, one 32-byte sector per lane -- cost ~20 % of the
-            // kernel in a knock-out run, profiles/r02_fused_bwd_knockout.txt.)
             float* const rowB = p.dBs + (static_cast<size_t>(b) * K + k) * L;
             float* const rowC = p.dCs + (static_cast<size_t>(b) * K + k) * L;
             if constexpr (PP > 1) {
-                __syncthreads();  // plane 0's reads of the tree are done before the scratch is rewritten
-                if (q == 0) {
-                    store_tokens<S>(f + j * S, accB);
-                    store_tokens<S>(f + L + j * S, accC);
+                constexpr int HP = PP / 2;
+                __syncthreads();  // the staging has left
+                if (q >= HP) {
+                    store_tokens<S>(f + (q - HP) * 2 * L + j * S, accB);
+                    store_tokens<S>(f + (q - HP) * 2 * L + L + j * S, accC);
+                }
+                __syncthreads();
+                if (q < HP) {
+                    float tb[S], tc[S];
+                    load_tokens<S>(f + q * 2 * L + j * S, tb);
+                    load_tokens<S>(f + q * 2 * L + L + j * S, tc);
+#pragma unroll
+                    for (int m = 0; m < S; ++m) accB[m] += tb[m], accC[m] += tc[m];
+                }
+                __syncthreads();  // every parked row has been read
+                if (q < HP) {
+                    store_tokens<S>(f + q * 2 * L + j * S, accB);
+                    store_tokens<S>(f + q * 2 * L + L + j * S, accC);
+                }
+                if constexpr (HP > 1) {
+                    __syncthreads();
+                    for (int o = tid; o < 2 * L; o += NT) {
+                        float a = f[o];
+#pragma unroll 4
+                        for (int pl = 1; pl < HP; ++pl) a += f[pl * 2 * L + o];
+                        f[o] = a;
+                    }
                 }
                 fence_proxy_async_smem();
                 __syncthreads();
