@@ -181,6 +181,11 @@ __global__ void __launch_bounds__(NT, 1) ss2d_bwd_kernel(const FusedBwdArgs p) {
         // planes: no L2 latency inside the permutation passes, no registers to hold entries), else read from L2
         constexpr bool SCH = Lay::SCH;
         const uint2* gsched = reinterpret_cast<const uint2*>(p.sched + static_cast<size_t>(k) * p.sched_len);
+        // (PIPE, accumulated dB / dC) the previous item's flush is still reading its scratch plane: it must have been
+        // read before this item's first round loads or permutes into that plane set
+        constexpr bool FLUSH_WAIT = PIPE && (PP > 1 || ES == 2);
+        if (FLUSH_WAIT && it > 0 && tid == 0) bulk_wait_read<0>();
+        if (FLUSH_WAIT && !Lay::SCH && it > 0) __syncthreads();
         if constexpr (SCH) {
             uint2* ss = reinterpret_cast<uint2*>(smem + Lay::sch);
             const int n2 = min(p.sched_used[k], 2 * L) / 2;
@@ -569,16 +574,14 @@ __global__ void __launch_bounds__(NT, 1) ss2d_bwd_kernel(const FusedBwdArgs p) {
             // accumulators) then leave COALESCED, token-ordered from the scratch, by TMA bulk reductions into the
             // (b, k) rows: reds straight from the registers -- lane stride 18 floats, one 32-byte sector per lane --
             // cost ~20 % of the kernel in a knock-out run (profiles/r02_fused_bwd_knockout.txt).  No shared-memory
-            // atomics (a CAS loop each).  Scratch = a plane buffer nobody uses between items: the du staging once
-            // its bulk reduction has been read (PIPE), the token-ordered dy planes (!PIPE; the next round's loads
-            // went to the other set); (PP/2) rows of 2L floats = TOK floats.
-            if (PIPE && tid == 0) bulk_wait_read<0>();
-            float* f = PIPE ? sDXs : sY(ld ^ 1);
+            // atomics (a CAS loop each).  Scratch = the dy plane of the set that holds no live data between items (the
+            // next round's loads went / go to the other set, or -- PIPE -- are issued only after the item-start wait
+            // below); (PP/2) rows of 2L floats = TOK floats.  It is free at once: no wait for the round's own stores.
+            float* f = sY(ld ^ 1);
             float* const rowB = p.dBs + (static_cast<size_t>(b) * K + k) * L;
             float* const rowC = p.dCs + (static_cast<size_t>(b) * K + k) * L;
             if constexpr (PP > 1) {
                 constexpr int HP = PP / 2;
-                __syncthreads();  // the staging has left
                 if (q >= HP) {
                     store_tokens<S>(f + (q - HP) * 2 * L + j * S, accB);
                     store_tokens<S>(f + (q - HP) * 2 * L + L + j * S, accC);
@@ -615,7 +618,6 @@ __global__ void __launch_bounds__(NT, 1) ss2d_bwd_kernel(const FusedBwdArgs p) {
                 }
             } else {
                 // one plane per round: L floats fill the scratch, so dB and dC take turns
-                __syncthreads();  // the staging has left (tid 0 waited above)
                 store_tokens<S>(f + j * S, accB);
                 fence_proxy_async_smem();
                 __syncthreads();
