@@ -617,23 +617,20 @@ __global__ void __launch_bounds__(NT, 1) ss2d_bwd_kernel(const FusedBwdArgs p) {
                     if (!PIPE) bulk_wait_read<0>();  // (PIPE: the next writer of the scratch waits for it mid-round)
                 }
             } else {
-                // one plane per round: L floats fill the scratch, so dB and dC take turns
+                // one plane per round: dB fills the scratch plane (L floats); dC goes over the item's B / C rows, which
+                // every thread has finished reading (2 * L 16-bit values = L floats) -- the next item's rows are loaded
+                // only after this reduction has read them (below)
+                static_assert(!ACC || PP > 1 || (ES == 2 && !BCG), "one-plane flush assumes staged 16-bit B / C rows");
+                float* const fc = reinterpret_cast<float*>(sB);
                 store_tokens<S>(f + j * S, accB);
+                store_tokens<S>(fc + j * S, accC);
                 fence_proxy_async_smem();
                 __syncthreads();
                 if (tid == 0) {
                     bulk_reduce_add_f32_s2g(rowB, f, L * 4);
+                    bulk_reduce_add_f32_s2g(rowC, fc, L * 4);
                     bulk_commit();
-                    bulk_wait_read<0>();
-                }
-                __syncthreads();
-                store_tokens<S>(f + j * S, accC);
-                fence_proxy_async_smem();
-                __syncthreads();
-                if (tid == 0) {
-                    bulk_reduce_add_f32_s2g(rowC, f, L * 4);
-                    bulk_commit();
-                    if (!PIPE) bulk_wait_read<0>();
+                    bulk_wait_read<0>();  // tid 0 only: it issues the next item's B / C load right after
                 }
             }
             __syncthreads();  // everybody is done with the scratch (and with sB / sC)
