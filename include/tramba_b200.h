@@ -167,7 +167,7 @@ TRAMBA_API int tramba_sscan_bwd(const void* u, const void* delta, const float* A
  * Backward = CrossMerge*.backward -> SelectiveScanOflex.backward -> CrossScan*.backward (csms6s.py:45-55, 914-923,
  * 25-31) in ONE kernel: dy (B, D, L) fp32 image order in; dx (B, D, L) fp32 IMAGE order out, already summed over the
  * K directions (TMA bulk reductions at L2) -- the K-fold gradient du w.r.t. xs never exists in HBM;
- * ddts (B, K, D, L) in_dtype scan order; dBs, dCs (B, K, L) fp32 (vector reds over the channels);
+ * ddts (B, K, D, L) in_dtype scan order; dBs, dCs (B, K, L) fp32 (summed over the channels: per-item TMA bulk reductions);
  * dA, dD, dbias (K*D) fp32 TOTALS over batch and tokens (reds).  Every fp32 output is an accumulation target and is
  * zeroed here -- with one memset when dx, dBs, dCs, dA, dD, dbias are carved contiguously, in that order, out of one
  * allocation.

@@ -23,6 +23,8 @@
 // Per round:  wait x/dy -> [permute image -> token order] -> pass 1 (forward fold + reverse fold of the segment)
 //   -> scans over the plane's threads -> pass 2a (dh, right to left) -> pass 2b (h, du, ddelta, dB/dC/dA/dD/dbias)
 //   -> [scatter du token -> image order] -> bulk store ddelta, bulk reduce-add dx.
+// Per item:   dB / dC accumulated in registers over the item's rounds -> folded over the PP planes of a round in shared
+//   memory -> written token-ordered into an idle plane -> two bulk reduce-adds into the (b, k) rows (coalesced).
 // PIPE (16-bit operands): two (x, dy) plane sets used alternately and two delta buffers, so the TMA loads of round
 // s + 1 overlap round s.  !PIPE (fp32 operands, which need twice the staging): one set (+ the token-ordered set),
 // loads issued when the round's stores have been read.
@@ -401,8 +403,9 @@ __global__ void __launch_bounds__(NT, 1) ss2d_bwd_kernel(const FusedBwdArgs p) {
                 }
             }
             // ---- pass 2b: left-to-right, h_t; du, ddelta; accumulate dB, dC, dA, dD, dbias
-            // dB_t += dh_t*delta_t*u_t and dC_t += dy_t*h_t leave per round as 16-byte vector reds (fp32 adds at L2
-            // over the channels of (b, k)): no accumulator registers live across the rounds of an item.  A chunk of
+            // dB_t += dh_t*delta_t*u_t and dC_t += dy_t*h_t: accumulated in registers (ACC, see above) or -- fp32 operands
+            // at L = 9216 only -- sent per round as 16-byte vector reds (fp32 adds at L2 over the channels of (b, k)):
+            // no accumulator registers live across the rounds of an item.  A chunk of
             // 18 floats starts 16-byte aligned for even j only, so a lane pair shares its 36 floats as 9 quads: the
             // even lane sends quads 0-3 from its own values and quad 4 = its last two + the odd lane's first two
             // (one shuffle pair after the loop), the odd lane quads 5-8 = its values 2..17.
